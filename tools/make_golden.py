@@ -1,0 +1,211 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/nerf_rpn) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tools/make_golden.py
+
+The reference has no tests or fixtures of its own, so these vectors -- outputs of
+the reference's own Python run here -- are what pins the oracle and the CUDA path.  Two shims are needed
+to import it on a GPU-less box: a CPU stand-in for the `sort_vertices` pybind
+module (tools/ref_stub/sort_vertices.py) and a no-op Tensor.cuda().
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools", "ref_stub"))
+sys.path.insert(0, "/root/reference/nerf_rpn")
+torch.Tensor.cuda = lambda self, *a, **k: self
+_is_avail = torch.cuda.is_available
+torch.cuda.is_available = lambda: False
+
+from model.anchor import AnchorGenerator3D, RPNHead  # noqa: E402
+from model.coder import AABBCoder, MidpointOffsetCoder  # noqa: E402
+from model.feature_extractor import Bottleneck, ResNet_FPN_256  # noqa: E402
+from model.nerf_rpn import NeRFRegionProposalNetwork  # noqa: E402
+from model.rotated_iou.box_intersection_2d import (box_in_box_th, box_intersection_th,  # noqa: E402
+                                                   build_vertices)
+from model.rotated_iou.oriented_iou_loss import box2corners_th, cal_iou_3d  # noqa: E402
+from model.utils import batched_nms, box_iou_3d, nms  # noqa: E402
+import sort_vertices as sv_stub  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+ANCHOR_SIZES = ((8,), (16,), (32,), (64,),)
+ASPECT = (((1., 1., 1.), (1., 1., 2.), (1., 2., 2.), (1., 1., 3.), (1., 3., 3.)),) * 4
+
+
+def rand_obb(n, gen, extent=30.0, smin=1.0, smax=11.0):
+    return torch.cat([torch.rand(n, 3, generator=gen) * extent,
+                      torch.rand(n, 3, generator=gen) * (smax - smin) + smin,
+                      (torch.rand(n, 1, generator=gen) - 0.5) * math.pi], 1)
+
+
+def rand_aabb(n, gen, extent=30.0, smin=0.5, smax=12.0):
+    lo = torch.rand(n, 3, generator=gen) * extent
+    return torch.cat([lo, lo + torch.rand(n, 3, generator=gen) * (smax - smin) + smin], 1)
+
+
+def gen_iou():
+    A = [0, 0, 0, 3, 3, 3, 0]
+    B = [1, 1, 1, 2, 2, 2, math.pi / 3]
+    C = [16.704862594604492, 4.111976623535156, 11.86344051361084, 7.168941974639893, 2.519232749938965,
+         5.041347503662109, -0.7416284084320068]
+    kat = [(A, B), (A, A), ([0, 0, 0, 2, 2, 2, 0], [1, 0, 0, 2, 2, 2, 0]),
+           ([0, 0, 0, 2, 2, 2, 0], [0, 0, 0, 2, 2, 2, math.pi / 4]),
+           ([0, 0, 0, 2, 2, 2, 0], [0, 0, 1, 2, 2, 2, math.pi / 4]), (C, C),
+           ([0, 0, 0, 2, 2, 2, 0], [5, 5, 5, 1, 1, 1, 0.3]),            # disjoint
+           ([0, 0, 0, 4, 4, 4, 0.2], [0.1, 0.1, 0, 1, 1, 1, 1.0]),      # contained
+           ([0, 0, 0, 2, 2, 2, 0], [2, 0, 0, 2, 2, 2, 0])]              # touching faces
+    a = torch.tensor([p[0] for p in kat], dtype=torch.float32)
+    b = torch.tensor([p[1] for p in kat], dtype=torch.float32)
+    kat_iou = cal_iou_3d(a[None], b[None])[0]
+    g = torch.Generator().manual_seed(11)
+    ra = rand_obb(4000, g, extent=12.0)
+    rb = rand_obb(4000, g, extent=12.0)
+    r_iou = cal_iou_3d(ra[None], rb[None])[0]
+    g = torch.Generator().manual_seed(12)
+    m = rand_obb(160, g, extent=20.0)
+    mat = box_iou_3d(m, m)
+    ga = rand_aabb(300, g)
+    gmat = box_iou_3d(ga, ga)
+    np.savez_compressed(os.path.join(OUT, "iou.npz"), kat_a=a.numpy(), kat_b=b.numpy(), kat_iou=kat_iou.numpy(),
+                        rand_a=ra.numpy(), rand_b=rb.numpy(), rand_iou=r_iou.numpy(),
+                        mat_boxes=m.numpy(), mat_iou=mat.numpy(), aabb_boxes=ga.numpy(), aabb_iou=gmat.numpy())
+    print("iou.npz: kat", kat_iou.tolist(), "rand nonzero", int((r_iou > 0).sum()))
+
+
+def gen_sort_vertices():
+    """Inputs exactly as box_intersection_2d.py:161-174 would hand them to the native op."""
+    g = torch.Generator().manual_seed(21)
+    a = rand_obb(1500, g, extent=10.0)
+    b = rand_obb(1500, g, extent=10.0)
+    a[:50] = b[:50]                      # identical boxes -> the num_valid==8 special case
+    b[50:100, 6] = a[50:100, 6]          # parallel edges
+    c1 = box2corners_th(a[None][..., [0, 1, 3, 4, 6]])
+    c2 = box2corners_th(b[None][..., [0, 1, 3, 4, 6]])
+    inters, mask_inter = box_intersection_th(c1, c2)
+    c12, c21 = box_in_box_th(c1, c2)
+    vertices, mask = build_vertices(c1, c2, c12, c21, inters, mask_inter)
+    num_valid = torch.sum(mask.int(), dim=2).int()
+    mean = torch.sum(vertices * mask.float().unsqueeze(-1), dim=2, keepdim=True) / num_valid.unsqueeze(-1).unsqueeze(-1)
+    vn = (vertices - mean).float()
+    idx = sv_stub.sort_vertices_forward(vn, mask, num_valid)
+    np.savez_compressed(os.path.join(OUT, "sort_vertices.npz"), vertices=vn.numpy(), mask=mask.numpy(),
+                        num_valid=num_valid.numpy(), idx=idx.numpy())
+    print("sort_vertices.npz: num_valid hist", np.bincount(num_valid.numpy().ravel()).tolist())
+
+
+def gen_nms():
+    out = {}
+    torch.manual_seed(0)   # SURVEY.md section 8c vector
+    boxes = torch.cat([torch.rand(64, 3) * 20, torch.rand(64, 3) * 6 + 2, (torch.rand(64, 1) - .5) * math.pi], 1)
+    scores = torch.rand(64)
+    lv = torch.randint(0, 4, (64,))
+    out["s64_boxes"], out["s64_scores"], out["s64_levels"] = boxes.numpy(), scores.numpy(), lv.numpy()
+    out["s64_keep"] = nms(boxes, scores, 0.3).numpy()
+    out["s64_bkeep"] = batched_nms(boxes, scores, lv, 0.3).numpy()
+    g = torch.Generator().manual_seed(31)
+    boxes = rand_obb(700, g, extent=24.0, smin=2.0, smax=12.0)
+    scores = torch.rand(700, generator=g)
+    lv = torch.randint(0, 4, (700,), generator=g)
+    out["o700_boxes"], out["o700_scores"], out["o700_levels"] = boxes.numpy(), scores.numpy(), lv.numpy()
+    out["o700_keep"] = nms(boxes, scores, 0.3).numpy()
+    out["o700_bkeep"] = batched_nms(boxes, scores, lv, 0.3).numpy()
+    out["o700_keep_t5"] = nms(boxes, scores, 0.5).numpy()
+    boxes = rand_aabb(1500, g, extent=40.0, smin=2.0, smax=16.0)
+    scores = torch.rand(1500, generator=g)
+    lv = torch.randint(0, 4, (1500,), generator=g)
+    out["a1500_boxes"], out["a1500_scores"], out["a1500_levels"] = boxes.numpy(), scores.numpy(), lv.numpy()
+    out["a1500_keep"] = nms(boxes, scores, 0.3).numpy()
+    out["a1500_bkeep"] = batched_nms(boxes, scores, lv, 0.3).numpy()
+    np.savez_compressed(os.path.join(OUT, "nms.npz"), **out)
+    print("nms.npz:", {k: len(v) for k, v in out.items() if "keep" in k})
+
+
+def gen_decode_anchors():
+    g = torch.Generator().manual_seed(41)
+    ag = AnchorGenerator3D(ANCHOR_SIZES, ASPECT)
+    mesh = torch.zeros(1, 4, 32, 48, 40)
+    feats = [torch.zeros(1, 256, 8, 12, 10), torch.zeros(1, 256, 4, 6, 5), torch.zeros(1, 256, 2, 3, 3),
+             torch.zeros(1, 256, 1, 2, 2)]
+    anchors, _ = ag(mesh, feats)
+    cell = [c.numpy() for c in ag.cell_anchors]
+    anc = anchors[0]
+    n = anc.shape[0]
+    d6 = torch.randn(n, 6, generator=g) * 0.5
+    d6[::97, 3:] = 9.0       # exercise the exp clamp
+    dec6 = AABBCoder().decode_single(d6, anc)
+    d8 = torch.randn(n, 8, generator=g) * 0.5
+    d8[::89, 3:6] = 6.0
+    d8[::83, 6:] = 0.9
+    dec7 = MidpointOffsetCoder().decode_single(d8, anc)
+    np.savez_compressed(os.path.join(OUT, "decode.npz"), anchors=anc.numpy(), cell0=cell[0], cell1=cell[1],
+                        cell2=cell[2], cell3=cell[3], d6=d6.numpy(), dec6=dec6.numpy(), d8=d8.numpy(),
+                        dec7=dec7.numpy())
+    print("decode.npz: anchors", tuple(anc.shape), "cell0", cell[0][:, 3:].tolist())
+
+
+def gen_rpn_small():
+    """Full reference forward (ResNet50-FPN + anchor head + RPN post-processing) on a small grid."""
+    for rotated in (False, True):
+        torch.manual_seed(0)
+        backbone = ResNet_FPN_256(Bottleneck, [3, 4, 6, 3], input_dim=4, is_max_pool=True)
+        ag = AnchorGenerator3D(ANCHOR_SIZES, ASPECT)
+        head = RPNHead(256, ag.num_anchors_per_location()[0], 4, rotate=rotated)
+        # spread the objectness so top-k / NMS see a non-degenerate load
+        g = torch.Generator().manual_seed(7)
+        with torch.no_grad():
+            head.cls_logits.weight.copy_(torch.randn(head.cls_logits.weight.shape, generator=g) * 0.2)
+            head.bbox_pred.weight.copy_(torch.randn(head.bbox_pred.weight.shape, generator=g) * 0.05)
+            for m in backbone.modules():      # non-trivial BN statistics so the folding is exercised
+                if isinstance(m, torch.nn.BatchNorm3d):
+                    m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                    m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.5 + 0.75)
+                    m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+                    m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+        # calibrate the two predictors so logits have std ~2 and deltas std ~0.3 on this input
+        gi = torch.Generator().manual_seed(1000)
+        grid = torch.rand(32, 48, 40, 4, generator=gi)           # channels-last as on disk
+        x = grid.permute(3, 0, 1, 2).contiguous()
+        backbone.eval(); head.eval()
+        with torch.no_grad():
+            lg, dl = head(list(backbone(x[None])))
+            s_l = torch.cat([t.flatten() for t in lg]).std().item()
+            s_d = torch.cat([t.flatten() for t in dl]).std().item()
+            head.cls_logits.weight.mul_(2.0 / s_l)
+            head.bbox_pred.weight.mul_(0.3 / s_d)
+        model = NeRFRegionProposalNetwork(backbone, ag, head, rpn_pre_nms_top_n_test=2500, rpn_post_nms_top_n_test=2500,
+                                          rpn_nms_thresh=0.3, rpn_fg_iou_thresh=0.35, rpn_bg_iou_thresh=0.2,
+                                          rpn_score_thresh=0.0, rotated_bbox=rotated)
+        model.eval()
+        with torch.no_grad():
+            (features, proposals, level_index), _, scores = model([x])
+            logits, deltas = head(features)
+        chk = {k: float(v.double().sum()) for k, v in list(backbone.state_dict().items())[:3]}
+        out = dict(grid=grid.numpy(), proposals=proposals[0].numpy(), scores=scores[0].numpy(),
+                   level_index=level_index[0].numpy(),
+                   conv1_sum=np.float64(backbone.conv1.weight.double().sum().item()),
+                   head_sum=np.float64(head.conv[0].weight.double().sum().item()),
+                   cls_w=head.cls_logits.weight.detach().numpy().reshape(13, 256),
+                   bbox_w=head.bbox_pred.weight.detach().numpy().reshape(-1, 256))
+        for i in range(4):
+            out[f"feat{i}"] = features[i][0].numpy().astype(np.float16)
+            out[f"logits{i}"] = logits[i][0].numpy()
+            out[f"deltas{i}"] = deltas[i][0].numpy()
+        name = "rpn_small_obb.npz" if rotated else "rpn_small_aabb.npz"
+        np.savez_compressed(os.path.join(OUT, name), **out)
+        print(name, "proposals", tuple(proposals[0].shape), "score range", float(scores[0].min()), float(scores[0].max()), chk)
+
+
+if __name__ == "__main__":
+    gen_iou()
+    gen_sort_vertices()
+    gen_nms()
+    gen_decode_anchors()
+    gen_rpn_small()
