@@ -1,0 +1,172 @@
+/*
+ * nerf_rpn_b200.h -- C ABI of the B200-native NeRF-RPN hot path (libnerf_rpn_b200.so).
+ *
+ * The reference (lyclyc52/NeRF_RPN) has no FFI registry: its drop-in surface is Python module paths plus
+ * ONE native pybind module, `sort_vertices` (nerf_rpn/model/rotated_iou/cuda_op/sort_vert.cpp:6-34).
+ * This header is what a binding for the hot path links against.  Every entry point
+ *   - takes plain device pointers / sizes and a CUDA stream (no torch types),
+ *   - is stream-ordered and never synchronises the device or the host,
+ *   - owns no caller memory (the caller allocates inputs, outputs and workspaces),
+ *   - returns 0 on success or a negative nrpn_status; it never calls exit() (the reference's
+ *     CUDA_CHECK_ERRORS does, cuda_utils.h:26-35).
+ * All pointers are device pointers unless marked "host".  Kernels are compiled for sm_100a only.
+ */
+#ifndef NERF_RPN_B200_H
+#define NERF_RPN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *nrpn_stream_t; /* cudaStream_t */
+
+typedef enum {
+    NRPN_OK = 0,
+    NRPN_ERR_INVALID = -1,      /* bad argument (null pointer, negative size, unsupported box_dim ...) */
+    NRPN_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels were built for */
+    NRPN_ERR_WORKSPACE = -3,    /* workspace too small */
+    NRPN_ERR_CUDA = -4,         /* CUDA runtime / driver error (see nrpn_last_cuda_error) */
+    NRPN_ERR_NO_DEVICE = -5     /* no sm_100 device or driver entry point unavailable */
+} nrpn_status;
+
+int nrpn_version(void);
+const char *nrpn_status_string(int status);
+/* last cudaError_t observed by this library on the calling thread (0 if none). */
+int nrpn_last_cuda_error(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+unsigned long long nrpn_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Box overlap.  Boxes are fp32 rows of box_dim floats:
+ *   box_dim == 6: axis-aligned (x1,y1,z1,x2,y2,z2)        -- nerf_rpn/model/utils.py:418-458
+ *   box_dim == 7: yaw-oriented (x,y,z,w,h,d,theta)        -- nerf_rpn/model/rotated_iou/oriented_iou_loss.py:82-107
+ * ---------------------------------------------------------------------------------------------- */
+
+/* iou[i] = IoU3D(a[i], b[i]).  Replaces cal_iou_3d on (1,n,7)x(1,n,7) (oriented_iou_loss.py:82) and the
+ * element-wise AABB case. */
+int nrpn_iou3d_pairs(const float *a, const float *b, int n, int box_dim, float *iou, nrpn_stream_t stream);
+
+/* out[i*m + j] = IoU3D(a[i], b[j]).  Replaces box_iou_3d (utils.py:387-415), which tiles both sets to
+ * (n,m,7) in HBM and runs ~40 ATen kernels plus the native sort. */
+int nrpn_iou3d_matrix(const float *a, int n, const float *b, int m, int box_dim, float *out, nrpn_stream_t stream);
+
+/* Drop-in for the reference's only native op on the path:
+ *   sort_vertices.sort_vertices_forward(vertices (b,n,m,2) f32, mask (b,n,m) bool, num_valid (b,n) i32)
+ *       -> idx (b,n,9) i32                                   -- cuda_op/sort_vert.cpp:6-34
+ * m must be <= 32 (the reference always passes 24). */
+int nrpn_sort_vertices(const float *vertices, const uint8_t *mask, const int32_t *num_valid, int b, int n, int m,
+                       int32_t *idx, nrpn_stream_t stream);
+
+/* Greedy NMS, per group, fully on device (no host round trip per kept box as in utils.py:215-230).
+ *   boxes  (n, box_dim) f32, scores (n) f32, group (n) i32 in [0,255] or NULL (single group)
+ *   keep   (n) i64 out: indices kept, sorted by score descending (ties: lower index first)
+ *   n_keep (1) i32 out (device)
+ * A pair (i,j) with score_i >= score_j of the same group suppresses j when !(IoU(box_i, box_j) <= thr)
+ * (utils.py:228).  Equivalent to batched_nms (utils.py:233-265); with group == NULL, to nms().
+ * n <= nrpn_nms_max_boxes().  workspace: nrpn_nms_workspace_bytes(n) bytes, 256-byte aligned. */
+int nrpn_nms_max_boxes(void);
+size_t nrpn_nms_workspace_bytes(int n);
+int nrpn_nms(const float *boxes, int box_dim, const float *scores, const int32_t *group, int n, float thr,
+             int64_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes, nrpn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3-D convolution as an implicit GEMM on tcgen05 tensor cores (replaces every nn.Conv3d (+BatchNorm3d
+ * +ReLU +residual / FPN top-down add) on the path: feature_extractor.py:31-68,145-235, anchor.py:177-213).
+ *
+ * Layouts (all bf16 unless stated):
+ *   x  : (N, X, Y, Z, Cin)   channels-last, Cin % 64 == 0; the reference's NCDHW (N,C,W,L,H) permuted
+ *   w  : (taps, CoutPad, Cin) one K-major (Cout x Cin) matrix per filter tap, BN scale pre-multiplied,
+ *        CoutPad = Cout rounded up to the kernel's N tile (nrpn_conv3d_block_n)
+ *   shift : (CoutPad) fp32   bias or folded BN shift
+ *   y  : (N, Xo, Yo, Zo, ldy) bf16 or fp32 (out_fp32), first Cout channels of each row written
+ *   res: optional (N, Xr, Yr, Zr, ldr) bf16 added before the activation; when its extent differs from
+ *        the output it is read through nearest-neighbour up-sampling (F.interpolate(size=..), fpn top-down)
+ * Output voxel o takes input voxel  o * stride + tap_offset[t] (zero outside the grid), so padding and
+ * dilation are expressed by the tap table.  Up to NRPN_CONV_MAX_LEVELS problems that share w/shift
+ * (the RPN head applied to P2..P5) are executed by ONE persistent launch.
+ * ---------------------------------------------------------------------------------------------- */
+#define NRPN_CONV_MAX_LEVELS 4
+#define NRPN_CONV_MAX_TAPS 64
+
+typedef struct {
+    const void *x;      /* bf16 */
+    void *y;            /* bf16 or fp32 */
+    const void *res;    /* bf16 or NULL */
+    int32_t n;          /* batch */
+    int32_t xi, yi, zi; /* input extent */
+    int32_t xo, yo, zo; /* output extent */
+    int32_t xr, yr, zr; /* residual extent (ignored when res == NULL) */
+    int32_t ldy;        /* output row pitch in elements */
+    int32_t ldr;        /* residual row pitch in elements */
+} nrpn_conv_level;
+
+typedef struct {
+    int32_t cin, cout;              /* cin % 64 == 0 */
+    int32_t n_taps;                 /* 1 .. NRPN_CONV_MAX_TAPS */
+    int8_t tap_off[NRPN_CONV_MAX_TAPS][3]; /* per tap (dx,dy,dz) input offset */
+    int32_t stride;                 /* 1 or 2 (same on all axes) */
+    int32_t relu;                   /* apply max(.,0) last */
+    int32_t out_fp32;               /* y is fp32 */
+    const void *w;                  /* bf16 (taps, CoutPad, cin) */
+    const float *shift;             /* fp32 (CoutPad) */
+    int32_t n_levels;
+    nrpn_conv_level level[NRPN_CONV_MAX_LEVELS];
+} nrpn_conv_desc;
+
+/* N tile the kernel will use for this cout (64, 128 or 256); weights/shift must be padded to a multiple. */
+int nrpn_conv3d_block_n(int cout);
+int nrpn_conv3d_fprop(const nrpn_conv_desc *desc /*host*/, nrpn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bandwidth-bound helpers around the convolutions.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Stem input packing: fp32 NCDHW grid (4, X, Y, Z) as the reference feeds the backbone (datasets.py:55-57,
+ * nerf_rpn.py:210) -> bf16 (ceil(X/2), ceil(Y/2), ceil(Z/2)+1, 64): a 2x2x2 space-to-depth block (32 ch)
+ * of voxel (i,j,k-1) followed by the block of voxel (i,j,k), k in [0, ceil(Z/2)] (so the packed Z extent is
+ * ceil(Z/2)+1); turns the 7^3 stride-2 stem conv (feature_extractor.py:163) into a 4x4x2-tap stride-1
+ * implicit GEMM with K = 64 per tap. */
+int nrpn_pack_stem_input(const float *grid, int n, int x, int y, int z, void *packed, nrpn_stream_t stream);
+
+/* F.max_pool3d(kernel 3, stride 2, padding 1) on (N,X,Y,Z,C) bf16, C % 8 == 0 (feature_extractor.py:219). */
+int nrpn_maxpool3d_k3s2(const void *in, int n, int x, int y, int z, int c, void *out, nrpn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RPN post-processing (rpn.py:292-370, anchor.py:51-122, coder/AABB_coder.py:86-137,
+ * coder/midpoint_offset_coder.py:160-223, utils.py:268-367) for ONE scene, fully on device.
+ * ---------------------------------------------------------------------------------------------- */
+#define NRPN_RPN_MAX_LEVELS 4
+
+typedef struct {
+    const float *pred;   /* (X*Y*Z, ld) fp32 rows: [A logits | A*code deltas | pad], anchor-major deltas */
+    int32_t ld;
+    int32_t gx, gy, gz;  /* feature grid */
+    int32_t sx, sy, sz;  /* anchor stride = mesh // grid (anchor.py:160-162) */
+} nrpn_rpn_level;
+
+typedef struct {
+    int32_t n_levels;
+    nrpn_rpn_level level[NRPN_RPN_MAX_LEVELS];
+    int32_t num_anchors;              /* A, anchors per location (<= 16) */
+    float cell_anchors[NRPN_RPN_MAX_LEVELS][16][6]; /* rounded half extents, anchor.py:51-82 */
+    int32_t rotated;                  /* 0: 6 deltas -> AABB, 1: 8 deltas -> OBB */
+    int32_t pre_nms_top_n;            /* per level */
+    int32_t post_nms_top_n;
+    float nms_thresh, score_thresh, min_size;
+    int32_t mesh[3];                  /* (padded) mesh extent used for clipping */
+    int32_t valid[3];                 /* original extent (padding mask, anchor.py:124-152); == mesh if unpadded */
+} nrpn_rpn_desc;
+
+size_t nrpn_rpn_workspace_bytes(const nrpn_rpn_desc *desc /*host*/);
+/* Outputs: boxes (post_nms_top_n, 6|7) f32, scores (post_nms_top_n) f32, levels (post_nms_top_n) f32
+ * (the reference returns the level id as a float column), count (1) i32. */
+int nrpn_rpn_proposals(const nrpn_rpn_desc *desc /*host*/, float *boxes, float *scores, float *levels,
+                       int32_t *count, void *workspace, size_t workspace_bytes, nrpn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_RPN_B200_H */

@@ -1,0 +1,103 @@
+"""ctypes binding of libnerf_rpn_b200.so (the C ABI declared in include/nerf_rpn_b200.h).
+
+The library is the product: if it is missing or fails to load, importing the compute path fails loudly --
+there is no PyTorch / CPU fallback anywhere in this package.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libnerf_rpn_b200.so")
+
+MAX_LEVELS = 4
+MAX_TAPS = 64
+
+c_f32p = ctypes.c_void_p
+c_stream = ctypes.c_void_p
+
+
+class ConvLevel(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_void_p), ("y", ctypes.c_void_p), ("res", ctypes.c_void_p), ("n", ctypes.c_int32),
+                ("xi", ctypes.c_int32), ("yi", ctypes.c_int32), ("zi", ctypes.c_int32),
+                ("xo", ctypes.c_int32), ("yo", ctypes.c_int32), ("zo", ctypes.c_int32),
+                ("xr", ctypes.c_int32), ("yr", ctypes.c_int32), ("zr", ctypes.c_int32),
+                ("ldy", ctypes.c_int32), ("ldr", ctypes.c_int32)]
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("n_taps", ctypes.c_int32),
+                ("tap_off", (ctypes.c_int8 * 3) * MAX_TAPS), ("stride", ctypes.c_int32), ("relu", ctypes.c_int32),
+                ("out_fp32", ctypes.c_int32), ("w", ctypes.c_void_p), ("shift", ctypes.c_void_p),
+                ("n_levels", ctypes.c_int32), ("level", ConvLevel * MAX_LEVELS)]
+
+
+class RpnLevel(ctypes.Structure):
+    _fields_ = [("pred", ctypes.c_void_p), ("ld", ctypes.c_int32), ("gx", ctypes.c_int32), ("gy", ctypes.c_int32),
+                ("gz", ctypes.c_int32), ("sx", ctypes.c_int32), ("sy", ctypes.c_int32), ("sz", ctypes.c_int32)]
+
+
+class RpnDesc(ctypes.Structure):
+    _fields_ = [("n_levels", ctypes.c_int32), ("level", RpnLevel * MAX_LEVELS), ("num_anchors", ctypes.c_int32),
+                ("cell_anchors", ((ctypes.c_float * 6) * 16) * MAX_LEVELS), ("rotated", ctypes.c_int32),
+                ("pre_nms_top_n", ctypes.c_int32), ("post_nms_top_n", ctypes.c_int32), ("nms_thresh", ctypes.c_float),
+                ("score_thresh", ctypes.c_float), ("min_size", ctypes.c_float), ("mesh", ctypes.c_int32 * 3),
+                ("valid", ctypes.c_int32 * 3)]
+
+
+_SIGNATURES = {
+    "nrpn_version": (ctypes.c_int, []),
+    "nrpn_status_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "nrpn_last_cuda_error": (ctypes.c_int, []),
+    "nrpn_launch_count": (ctypes.c_ulonglong, []),
+    "nrpn_iou3d_pairs": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, c_f32p, c_stream]),
+    "nrpn_iou3d_matrix": (ctypes.c_int, [c_f32p, ctypes.c_int, c_f32p, ctypes.c_int, ctypes.c_int, c_f32p, c_stream]),
+    "nrpn_sort_vertices": (ctypes.c_int, [c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_void_p, c_stream]),
+    "nrpn_nms_max_boxes": (ctypes.c_int, []),
+    "nrpn_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "nrpn_nms": (ctypes.c_int, [c_f32p, ctypes.c_int, c_f32p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
+                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, c_stream]),
+    "nrpn_conv3d_block_n": (ctypes.c_int, [ctypes.c_int]),
+    "nrpn_conv3d_fprop": (ctypes.c_int, [ctypes.POINTER(ConvDesc), c_stream]),
+    "nrpn_pack_stem_input": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p, c_stream]),
+    "nrpn_maxpool3d_k3s2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_void_p, c_stream]),
+    "nrpn_rpn_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(RpnDesc)]),
+    "nrpn_rpn_proposals": (ctypes.c_int, [ctypes.POINTER(RpnDesc), c_f32p, c_f32p, c_f32p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_size_t, c_stream]),
+}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the native library (once). Raises NativeLibraryError if it is missing: build it with `make`."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} not found: the CUDA extension is required (run `make` or __graft_entry__.build()); "
+                "nerf_rpn_b200 has no CPU / PyTorch fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)       # AttributeError if the ABI is incomplete
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(status, what=""):
+    if status != 0:
+        L = lib()
+        msg = L.nrpn_status_string(status).decode()
+        raise RuntimeError(f"nerf_rpn_b200: {what} failed: {msg} (status {status}, cuda error {L.nrpn_last_cuda_error()})")

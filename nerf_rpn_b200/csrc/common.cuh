@@ -1,0 +1,58 @@
+// Shared host/device helpers for libnerf_rpn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <atomic>
+#include "../../include/nerf_rpn_b200.h"
+
+namespace nrpn {
+
+extern thread_local int g_last_cuda_error;
+extern std::atomic<unsigned long long> g_launch_count;
+
+inline int cuda_fail(cudaError_t e) {
+    g_last_cuda_error = (int)e;
+    return NRPN_ERR_CUDA;
+}
+
+// Every kernel launch goes through this so that nrpn_launch_count() is an honest count.
+#define NRPN_LAUNCH_CHECK()                                         \
+    do {                                                            \
+        ::nrpn::g_launch_count.fetch_add(1, std::memory_order_relaxed); \
+        cudaError_t e__ = cudaGetLastError();                       \
+        if (e__ != cudaSuccess) return ::nrpn::cuda_fail(e__);      \
+    } while (0)
+
+#define NRPN_CUDA_TRY(expr)                                         \
+    do {                                                            \
+        cudaError_t e__ = (expr);                                   \
+        if (e__ != cudaSuccess) return ::nrpn::cuda_fail(e__);      \
+    } while (0)
+
+inline int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    return sms;
+}
+
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Monotone map float -> uint32 (larger float => larger key); -0 < +0, NaNs sort to the ends.
+__host__ __device__ inline uint32_t float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+}  // namespace nrpn

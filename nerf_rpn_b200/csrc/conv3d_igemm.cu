@@ -1,0 +1,368 @@
+// 3-D convolution as an implicit GEMM on tcgen05 tensor cores (sm_100a).
+//
+// Replaces every nn.Conv3d (+ BatchNorm3d + ReLU + residual / FPN top-down add) of the reference path
+// (feature_extractor.py:31-68,145-235; anchor.py:177-213), which runs them as separate cuDNN / ATen kernels on
+// fp32 NCDHW tensors.
+//
+// GEMM view:  D[M = voxels, N = Cout] = sum over (tap, Cin)  A[voxel + tap_offset, Cin] * W[tap][Cout, Cin]
+//   - M tile  = a brick of bx*by*bz = 128 output voxels.  The A operand of one (tap, 64-channel) k-block is the
+//     same brick shifted by the tap offset: ONE 5-D TMA box load {64 ch, bz, by, bx, 1} from the channels-last
+//     activation tensor, out-of-bounds voxels zero-filled by TMA (= the convolution's zero padding).  The box
+//     lands in shared memory as 128 rows x 128 bytes in the 128B-swizzled K-major layout tcgen05.mma consumes:
+//     no im2col buffer, no index arithmetic on the SM.
+//   - N tile  = 64 / 128 / 256 output channels; W is pre-packed (tap, Cout, Cin) so a k-block of weights is a
+//     3-D TMA box {64, N, 1}.
+//   - warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one thread), warps 2-5 = epilogue.  smem ring of
+//     4-8 stages (full/empty mbarriers), accumulators double-buffered in TMEM (2 x N columns) so the epilogue of
+//     tile i overlaps the main loop of tile i+1.  Persistent CTAs (grid = #SMs) walk a static tile list that may
+//     span up to 4 pyramid levels sharing the same weights (the RPN head on P2..P5 is ONE launch per layer).
+//   - epilogue (fused): + shift (bias / folded BN), + residual (same shape, or nearest-upsampled coarser level
+//     for the FPN top-down path), ReLU, convert, 16-byte stores.
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace nrpn {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kABytes = kBlockM * kBlockK * 2;       // 16 KB
+constexpr int kSmemBudget = 200 * 1024;
+
+struct ConvLevelDev {
+    int n, xo, yo, zo;
+    int bx, by, bz;          // brick (product 128)
+    int tx, ty, tz;          // bricks per axis
+    int tile_begin;          // first m-tile of this level
+    int xr, yr, zr;          // residual extent
+    float rsx, rsy, rsz;     // nearest-neighbour scale = in / out
+    int ldy, ldr;
+    void* y;
+    const __nv_bfloat16* res;
+};
+
+struct ConvDev {
+    int n_levels, n_taps, kc_blocks, n_tiles_n, cout, relu, out_fp32;
+    int total_m_tiles;
+    signed char tap[NRPN_CONV_MAX_TAPS][4];
+    const float* shift;
+    ConvLevelDev lv[NRPN_CONV_MAX_LEVELS];
+};
+
+struct ConvMaps {
+    CUtensorMap x[NRPN_CONV_MAX_LEVELS];
+    CUtensorMap w;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192, 1) conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvDev P) {
+    constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    constexpr int kStageBytes = kABytes + kBBytes;
+    constexpr uint32_t kTmemCols = 2 * BLOCK_N;
+    constexpr uint32_t kIdesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tfull_bar = bars + 2 * STAGES;
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 128); }
+        ptx::fence_barrier_init();
+        for (int l = 0; l < P.n_levels; ++l) ptx::prefetch_tmap(&maps.x[l]);
+        ptx::prefetch_tmap(&maps.w);
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, kTmemCols); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = P.total_m_tiles * P.n_tiles_n;
+    const int kblocks = P.n_taps * P.kc_blocks;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (one thread)
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % P.n_tiles_n, m_tile = tile / P.n_tiles_n;
+                int l = 0;
+#pragma unroll
+                for (int i = 1; i < NRPN_CONV_MAX_LEVELS; ++i) if (i < P.n_levels && m_tile >= P.lv[i].tile_begin) l = i;
+                const ConvLevelDev& L = P.lv[l];
+                int t = m_tile - L.tile_begin;
+                const int tiz = t % L.tz; t /= L.tz;
+                const int tiy = t % L.ty; t /= L.ty;
+                const int tix = t % L.tx; const int nb = t / L.tx;
+                const int x0 = tix * L.bx, y0 = tiy * L.by, z0 = tiz * L.bz, n0 = n_tile * BLOCK_N;
+                for (int tap = 0; tap < P.n_taps; ++tap) {
+                    const int dx = P.tap[tap][0], dy = P.tap[tap][1], dz = P.tap[tap][2];
+                    for (int kc = 0; kc < P.kc_blocks; ++kc) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        uint8_t* sa = smem + stage * kStageBytes;
+                        uint8_t* sb = sa + kABytes;
+                        ptx::mbar_expect_tx(&full_bar[stage], kStageBytes);
+                        ptx::tma_load_5d(sa, &maps.x[l], &full_bar[stage], kc * kBlockK, z0 + dz, y0 + dy, x0 + dx, nb);
+                        ptx::tma_load_3d(sb, &maps.w, &full_bar[stage], kc * kBlockK, n0, tap);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
+                    const uint64_t da = ptx::make_desc_sw128(sa);
+                    const uint64_t db = ptx::make_desc_sw128(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in the >>4 address field
+                        ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | k) ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);        // frees the smem slot once the MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                ptx::umma_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;                   // accumulator row == voxel inside the brick
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % P.n_tiles_n, m_tile = tile / P.n_tiles_n;
+            int l = 0;
+#pragma unroll
+            for (int i = 1; i < NRPN_CONV_MAX_LEVELS; ++i) if (i < P.n_levels && m_tile >= P.lv[i].tile_begin) l = i;
+            const ConvLevelDev& L = P.lv[l];
+            int t = m_tile - L.tile_begin;
+            const int tiz = t % L.tz; t /= L.tz;
+            const int tiy = t % L.ty; t /= L.ty;
+            const int tix = t % L.tx; const int nb = t / L.tx;
+            const int zi = row % L.bz, yi = (row / L.bz) % L.by, xi = row / (L.bz * L.by);
+            const int gx = tix * L.bx + xi, gy = tiy * L.by + yi, gz = tiz * L.bz + zi;
+            const bool valid = gx < L.xo && gy < L.yo && gz < L.zo;
+            const size_t vox = (((size_t)nb * L.xo + gx) * L.yo + gy) * L.zo + gz;
+            const __nv_bfloat16* rrow = nullptr;
+            if (L.res != nullptr && valid) {
+                int rx = gx, ry = gy, rz = gz;
+                if (L.xr != L.xo || L.yr != L.yo || L.zr != L.zo) {   // F.interpolate(mode='nearest', size=...)
+                    rx = min((int)floorf((float)gx * L.rsx), L.xr - 1);
+                    ry = min((int)floorf((float)gy * L.rsy), L.yr - 1);
+                    rz = min((int)floorf((float)gz * L.rsz), L.zr - 1);
+                }
+                rrow = L.res + ((((size_t)nb * L.xr + rx) * L.yr + ry) * L.zr + rz) * L.ldr;
+            }
+            const int n0 = n_tile * BLOCK_N;
+
+            ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(t_base + (uint32_t)(c * 32), r);
+                ptx::tmem_ld_wait();
+                const int ch0 = n0 + c * 32;
+                if (valid && ch0 < P.cout) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {            // 4 groups of 8 channels
+                        const int ch = ch0 + g * 8;
+                        if (ch >= P.cout) break;
+                        float v[8];
+                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.shift + ch));
+                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(P.shift + ch + 4));
+                        v[0] = __uint_as_float(r[g * 8 + 0]) + s0.x; v[1] = __uint_as_float(r[g * 8 + 1]) + s0.y;
+                        v[2] = __uint_as_float(r[g * 8 + 2]) + s0.z; v[3] = __uint_as_float(r[g * 8 + 3]) + s0.w;
+                        v[4] = __uint_as_float(r[g * 8 + 4]) + s1.x; v[5] = __uint_as_float(r[g * 8 + 5]) + s1.y;
+                        v[6] = __uint_as_float(r[g * 8 + 6]) + s1.z; v[7] = __uint_as_float(r[g * 8 + 7]) + s1.w;
+                        if (rrow != nullptr) {
+                            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rrow + ch));
+                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(rb[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
+                        }
+                        if (P.relu) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+                        }
+                        if (P.out_fp32) {
+                            float* o = reinterpret_cast<float*>(L.y) + vox * L.ldy + ch;
+                            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                        } else {
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(L.y) + vox * L.ldy + ch;
+                            *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                                      pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <int BLOCK_N>
+constexpr int stages_for() { return kSmemBudget / (kABytes + BLOCK_N * kBlockK * 2) > 8 ? 8 : kSmemBudget / (kABytes + BLOCK_N * kBlockK * 2); }
+
+template <int BLOCK_N>
+static int launch_conv(const ConvMaps& maps, const ConvDev& P, int total_tiles, cudaStream_t st) {
+    constexpr int STAGES = stages_for<BLOCK_N>();
+    constexpr int smem = STAGES * (kABytes + BLOCK_N * kBlockK * 2) + 1024 + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NRPN_CUDA_TRY(cudaFuncSetAttribute(conv3d_igemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+    conv3d_igemm_kernel<BLOCK_N, STAGES><<<grid, 192, smem, st>>>(maps, P);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+static void choose_brick(int xo, int yo, int zo, int& bx, int& by, int& bz) {
+    long best = -1;
+    for (int ez = 0; ez <= 7; ++ez) for (int ey = 0; ey + ez <= 7; ++ey) {
+        const int ex = 7 - ez - ey;
+        const int cz = 1 << ez, cy = 1 << ey, cx = 1 << ex;
+        if (cz > 256 || cy > 256 || cx > 256) continue;
+        const long vol = (long)ceil_div(xo, cx) * cx * ceil_div(yo, cy) * cy * ceil_div(zo, cz) * cz;
+        // prefer less padding, then longer z runs (contiguous in memory), then y
+        const long score = vol * 1024 - ez * 16 - ey;
+        if (best < 0 || score < best) { best = score; bx = cx; by = cy; bz = cz; }
+    }
+}
+
+}  // namespace nrpn
+
+using namespace nrpn;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int nrpn_conv3d_block_n(int cout) { return cout <= 64 ? 64 : (cout <= 128 ? 128 : 256); }
+
+int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
+    if (!d || !d->w || !d->shift) return NRPN_ERR_INVALID;
+    if (d->cin < 64 || d->cin % 64 != 0 || d->cout < 8 || d->cout % 8 != 0) return NRPN_ERR_UNSUPPORTED;
+    if (d->n_taps < 1 || d->n_taps > NRPN_CONV_MAX_TAPS || d->n_levels < 1 || d->n_levels > NRPN_CONV_MAX_LEVELS)
+        return NRPN_ERR_INVALID;
+    if (d->stride != 1 && d->stride != 2) return NRPN_ERR_UNSUPPORTED;
+    if (d->stride == 2) {       // strided access is expressed through a sub-sampled tensor map: taps must not move
+        for (int t = 0; t < d->n_taps; ++t)
+            if (d->tap_off[t][0] || d->tap_off[t][1] || d->tap_off[t][2]) return NRPN_ERR_UNSUPPORTED;
+    }
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return NRPN_ERR_NO_DEVICE;
+
+    const int block_n = nrpn_conv3d_block_n(d->cout);
+    const int cout_pad = ceil_div(d->cout, block_n) * block_n;
+    ConvMaps maps;
+    ConvDev P;
+    memset(&P, 0, sizeof(P));
+    P.n_levels = d->n_levels; P.n_taps = d->n_taps; P.kc_blocks = d->cin / kBlockK; P.n_tiles_n = cout_pad / block_n;
+    P.cout = d->cout; P.relu = d->relu; P.out_fp32 = d->out_fp32; P.shift = d->shift;
+    for (int t = 0; t < d->n_taps; ++t) { P.tap[t][0] = d->tap_off[t][0]; P.tap[t][1] = d->tap_off[t][1]; P.tap[t][2] = d->tap_off[t][2]; P.tap[t][3] = 0; }
+
+    int tiles = 0;
+    const int s = d->stride;
+    for (int l = 0; l < d->n_levels; ++l) {
+        const nrpn_conv_level& S = d->level[l];
+        ConvLevelDev& L = P.lv[l];
+        if (!S.x || !S.y || S.n < 1 || S.xi < 1 || S.yi < 1 || S.zi < 1 || S.xo < 1 || S.yo < 1 || S.zo < 1) return NRPN_ERR_INVALID;
+        if (S.ldy < d->cout || S.ldy % 8 != 0) return NRPN_ERR_INVALID;
+        if (S.res && (S.ldr < d->cout || S.ldr % 8 != 0 || S.xr < 1 || S.yr < 1 || S.zr < 1)) return NRPN_ERR_INVALID;
+        if (s == 2 && (S.xo != (S.xi + 1) / 2 || S.yo != (S.yi + 1) / 2 || S.zo != (S.zi + 1) / 2)) return NRPN_ERR_INVALID;
+        L.n = S.n; L.xo = S.xo; L.yo = S.yo; L.zo = S.zo;
+        choose_brick(S.xo, S.yo, S.zo, L.bx, L.by, L.bz);
+        L.tx = ceil_div(S.xo, L.bx); L.ty = ceil_div(S.yo, L.by); L.tz = ceil_div(S.zo, L.bz);
+        L.tile_begin = tiles;
+        tiles += S.n * L.tx * L.ty * L.tz;
+        L.xr = S.res ? S.xr : S.xo; L.yr = S.res ? S.yr : S.yo; L.zr = S.res ? S.zr : S.zo;
+        L.rsx = (float)L.xr / (float)S.xo; L.rsy = (float)L.yr / (float)S.yo; L.rsz = (float)L.zr / (float)S.zo;
+        L.ldy = S.ldy; L.ldr = S.ldr; L.y = S.y; L.res = reinterpret_cast<const __nv_bfloat16*>(S.res);
+
+        // activation tensor map: (C, Z, Y, X, N), optionally sub-sampled by `stride` on the three spatial axes
+        const cuuint64_t cin = (cuuint64_t)d->cin;
+        cuuint64_t gdim[5] = {cin, (cuuint64_t)ceil_div(S.zi, s), (cuuint64_t)ceil_div(S.yi, s), (cuuint64_t)ceil_div(S.xi, s), (cuuint64_t)S.n};
+        cuuint64_t gstr[4] = {cin * 2 * s, (cuuint64_t)S.zi * cin * 2 * s, (cuuint64_t)S.yi * S.zi * cin * 2 * s,
+                              (cuuint64_t)S.xi * S.yi * S.zi * cin * 2};
+        cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)L.bz, (cuuint32_t)L.by, (cuuint32_t)L.bx, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = encode(&maps.x[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(S.x), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return NRPN_ERR_CUDA; }
+    }
+    for (int l = d->n_levels; l < NRPN_CONV_MAX_LEVELS; ++l) maps.x[l] = maps.x[0];
+    {
+        cuuint64_t gdim[3] = {(cuuint64_t)d->cin, (cuuint64_t)cout_pad, (cuuint64_t)d->n_taps};
+        cuuint64_t gstr[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)cout_pad * d->cin * 2};
+        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&maps.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->w), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return NRPN_ERR_CUDA; }
+    }
+    P.total_m_tiles = tiles;
+    const int total_tiles = tiles * P.n_tiles_n;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (block_n == 64) return launch_conv<64>(maps, P, total_tiles, st);
+    if (block_n == 128) return launch_conv<128>(maps, P, total_tiles, st);
+    return launch_conv<256>(maps, P, total_tiles, st);
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

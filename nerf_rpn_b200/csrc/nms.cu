@@ -1,0 +1,452 @@
+// Box-overlap entry points and device-resident greedy NMS.
+//   replaces: utils.py:215-265 (nms / batched_nms: Python while-loop, one host sync + ~40 ATen kernels +
+//             the native vertex sort per kept box), utils.py:387-415 (box_iou_3d), cuda_op/sort_vert_kernel.cu.
+// Design: sort once by (group, score desc, index) with an in-kernel bitonic network, build the 64-bit
+// suppression bit-matrix only for same-group upper-triangle tiles (one thread per row, 64 columns per word,
+// exact-zero culling by bounding circle / z range), resolve each group with one CTA that walks the matrix
+// 64 rows at a time (warp-shuffle resolve of the diagonal word, coalesced OR of the kept rows), then sort
+// the survivors by score.  No host round trips; everything is stream-ordered.
+#include "box_iou.cuh"
+#include "nms_internal.cuh"
+
+namespace nrpn {
+
+thread_local int g_last_cuda_error = 0;
+std::atomic<unsigned long long> g_launch_count{0};
+
+// ---------------------------------------------------------------------------------------------- IoU
+__global__ void iou_pairs_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, int box_dim,
+                                 float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (box_dim == 7) {
+        ObbPrep pa, pb;
+        obb_prepare(a + (size_t)i * 7, pa);
+        obb_prepare(b + (size_t)i * 7, pb);
+        out[i] = iou3d_obb(pa, pb, true);
+    } else {
+        out[i] = iou3d_aabb(a + (size_t)i * 6, b + (size_t)i * 6);
+    }
+}
+
+// tile: 8 rows (a) x 32 cols (b) per 256-thread CTA; box preparation (fp64 sin/cos) once per box per tile.
+__global__ void iou_matrix_kernel(const float* __restrict__ a, int n, const float* __restrict__ b, int m, int box_dim,
+                                  float* __restrict__ out) {
+    __shared__ ObbPrep sa[8];
+    __shared__ ObbPrep sb[32];
+    __shared__ float ra[8][6];
+    __shared__ float rb[32][6];
+    const int r0 = blockIdx.y * 8, c0 = blockIdx.x * 32;
+    const int t = threadIdx.x;
+    if (box_dim == 7) {
+        if (t < 8 && r0 + t < n) obb_prepare(a + (size_t)(r0 + t) * 7, sa[t]);
+        if (t >= 32 && t < 64 && c0 + (t - 32) < m) obb_prepare(b + (size_t)(c0 + t - 32) * 7, sb[t - 32]);
+    } else {
+        if (t < 48) { const int r = t / 6, k = t % 6; if (r0 + r < n) ra[r][k] = a[(size_t)(r0 + r) * 6 + k]; }
+        if (t >= 64 && t < 64 + 192) { const int c = (t - 64) / 6, k = (t - 64) % 6; if (c0 + c < m) rb[c][k] = b[(size_t)(c0 + c) * 6 + k]; }
+    }
+    __syncthreads();
+    const int r = t / 32, c = t % 32;
+    if (r0 + r >= n || c0 + c >= m) return;
+    float v;
+    if (box_dim == 7) v = iou3d_obb(sa[r], sb[c], true);
+    else v = iou3d_aabb(ra[r], rb[c]);
+    out[(size_t)(r0 + r) * m + c0 + c] = v;
+}
+
+// ------------------------------------------------------------------------------- sort_vertices (K1)
+// One thread per polygon, same contract as sort_vertices_forward (sort_vert.cpp:6-34); restates the
+// selection sort of sort_vert_kernel.cu:42-134 with the polygon held in registers/local memory.
+__global__ void sort_vertices_kernel(const float* __restrict__ vertices, const uint8_t* __restrict__ mask,
+                                     const int32_t* __restrict__ num_valid, long total, int m, int32_t* __restrict__ idx) {
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    float x[32], y[32], q[32];
+    uint32_t mk = 0;
+    for (int k = 0; k < m; ++k) {
+        x[k] = vertices[(p * m + k) * 2];
+        y[k] = vertices[(p * m + k) * 2 + 1];
+        q[k] = pseudo_angle(x[k], y[k]);
+        if (mask[p * m + k]) mk |= 1u << k;
+    }
+    const int nv = num_valid[p];
+    int pad = 0;
+    for (int j = 8; j < m; ++j) if (!((mk >> j) & 1u)) { pad = j; break; }
+    int32_t* o = idx + p * 9;
+    if (nv < 3) { for (int j = 0; j < 9; ++j) o[j] = pad; return; }
+    int tk[9];
+    int first = 0, prev = 0;
+    for (int j = 0; j < nv; ++j) {
+        float bx = 1.0f, by = -eps_f(), bq = 1.0f;
+        int take = 0;
+        for (int k = 0; k < m; ++k) {
+            if (!((mk >> k) & 1u)) continue;
+            bool ok = vert_less(x[k], y[k], q[k], bx, by, bq);
+            if (ok && j > 0) ok = vert_less(x[prev], y[prev], q[prev], x[k], y[k], q[k]);
+            if (ok) { bx = x[k]; by = y[k]; bq = q[k]; take = k; }
+        }
+        if (j == 0) first = take;
+        if (j < 9) tk[j] = take;
+        prev = take;
+    }
+    for (int j = 0; j < 9; ++j) o[j] = pad;
+    for (int j = 0; j < nv && j < 9; ++j) o[j] = tk[j];
+    if (nv < 9) o[nv] = first;
+    if (nv == 8) {
+        int counter = 0;
+        for (int j = 0; j < 4; ++j) for (int k = 4; k < 8; ++k) counter += (tk[k] == tk[j]) ? 1 : 0;
+        if (counter == 4) { o[4] = tk[0]; for (int j = 5; j < 9; ++j) o[j] = pad; }
+    }
+}
+
+// ------------------------------------------------------------------------------------ bitonic sort
+constexpr int kSortTile = 8192;       // elements sorted inside one CTA's shared memory (64 KB)
+constexpr int kSortThreads = 1024;
+
+__device__ __forceinline__ void cmp_swap(unsigned long long& a, unsigned long long& b, bool asc) {
+    if ((a > b) == asc) { const unsigned long long t = a; a = b; b = t; }
+}
+
+// All stages with partner distance < tile, for merge sizes k in [k_lo, k_hi].
+__global__ void __launch_bounds__(kSortThreads) bitonic_local_kernel(unsigned long long* __restrict__ keys, int n_pad,
+                                                                    int tile, int k_lo, int k_hi) {
+    extern __shared__ unsigned long long sk[];
+    const int base = blockIdx.x * tile;
+    for (int i = threadIdx.x; i < tile; i += blockDim.x) sk[i] = keys[base + i];
+    __syncthreads();
+    for (int k = k_lo; k <= k_hi; k <<= 1) {
+        int j0 = k >> 1; if (j0 >= tile) j0 = tile >> 1;
+        for (int j = j0; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (tile >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j cleared
+                const bool asc = (((base + i) & k) == 0);
+                cmp_swap(sk[i], sk[i | j], asc);
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < tile; i += blockDim.x) keys[base + i] = sk[i];
+}
+
+__global__ void bitonic_global_kernel(unsigned long long* __restrict__ keys, int n_pad, int k, int j) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (n_pad >> 1)) return;
+    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    const bool asc = ((i & k) == 0);
+    unsigned long long a = keys[i], b = keys[i | j];
+    if ((a > b) == asc) { keys[i] = b; keys[i | j] = a; }
+}
+
+int bitonic_sort_u64(unsigned long long* keys, int n_pad, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        NRPN_CUDA_TRY(cudaFuncSetAttribute(bitonic_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortTile * 8));
+        attr_set = true;
+    }
+    const int tile = n_pad < kSortTile ? n_pad : kSortTile;
+    const int blocks = n_pad / tile;
+    bitonic_local_kernel<<<blocks, kSortThreads, tile * 8, st>>>(keys, n_pad, tile, 2, tile);
+    NRPN_LAUNCH_CHECK();
+    for (int k = tile << 1; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j >= tile; j >>= 1) {
+            bitonic_global_kernel<<<ceil_div(n_pad >> 1, 256), 256, 0, st>>>(keys, n_pad, k, j);
+            NRPN_LAUNCH_CHECK();
+        }
+        bitonic_local_kernel<<<blocks, kSortThreads, tile * 8, st>>>(keys, n_pad, tile, k, k);
+        NRPN_LAUNCH_CHECK();
+    }
+    return NRPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- NMS
+static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+constexpr int kNmsMaxBoxes = 32768;
+constexpr int kPrepFloats = 16;
+
+struct NmsWs {
+    unsigned long long* keys;     // n_pad
+    unsigned long long* keys2;    // n_pad
+    float* prep;                  // n * 16
+    int* sgroup;                  // n
+    int* seg;                     // 512 (start[256], end[256])
+    unsigned long long* keepbits; // W
+    unsigned long long* mask;     // n * W
+    size_t total;
+};
+
+static NmsWs nms_layout(void* base, int n) {
+    NmsWs w;
+    const int n_pad = next_pow2(n < 2 ? 2 : n);
+    const int W = ceil_div(n, 64);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    char* b = (char*)base;
+    w.keys = (unsigned long long*)(b + take((size_t)n_pad * 8));
+    w.keys2 = (unsigned long long*)(b + take((size_t)n_pad * 8));
+    w.prep = (float*)(b + take((size_t)n * kPrepFloats * 4));
+    w.sgroup = (int*)(b + take((size_t)n * 4));
+    w.seg = (int*)(b + take(512 * 4));
+    w.keepbits = (unsigned long long*)(b + take((size_t)W * 8));
+    w.mask = (unsigned long long*)(b + take((size_t)n * W * 8));
+    w.total = off;
+    return w;
+}
+
+__global__ void nms_keys_kernel(const float* __restrict__ scores, const int32_t* __restrict__ group, int n, int n_pad,
+                                unsigned long long* __restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    unsigned long long k = ~0ull;
+    if (i < n) {
+        const unsigned long long g = group ? (unsigned long long)(group[i] & 0xFF) : 0ull;
+        const unsigned long long s = (unsigned long long)(~float_to_ordered(scores[i]));
+        k = (g << 56) | (s << 24) | (unsigned long long)i;
+    }
+    keys[i] = k;
+}
+
+__global__ void nms_prep_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ boxes, int box_dim,
+                                int n, float* __restrict__ prep, int* __restrict__ sgroup, int* __restrict__ seg) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const unsigned long long k = keys[p];
+    const int idx = (int)(k & 0xFFFFFFull);
+    const int g = (int)(k >> 56);
+    sgroup[p] = g;
+    if (p == 0 || (int)(keys[p - 1] >> 56) != g) seg[g] = p;
+    if (p == n - 1 || (int)(keys[p + 1] >> 56) != g) seg[256 + g] = p + 1;
+    float* o = prep + (size_t)p * kPrepFloats;
+    if (box_dim == 7) {
+        ObbPrep pp;
+        obb_prepare(boxes + (size_t)idx * 7, pp);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = pp.c[i];
+        o[8] = pp.area; o[9] = pp.vol; o[10] = pp.zmin; o[11] = pp.zmax; o[12] = pp.cx; o[13] = pp.cy; o[14] = pp.rad;
+        o[15] = __int_as_float(pp.cullable);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) o[i] = boxes[(size_t)idx * 6 + i];
+    }
+}
+
+__device__ __forceinline__ void load_prep(const float* __restrict__ s, ObbPrep& p) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p.c[i] = s[i];
+    p.area = s[8]; p.vol = s[9]; p.zmin = s[10]; p.zmax = s[11]; p.cx = s[12]; p.cy = s[13]; p.rad = s[14];
+    p.cullable = __float_as_int(s[15]);
+}
+
+// grid (W, W); CTA (cb, rb) with cb >= rb fills mask[rows of chunk rb][word cb]. 64 threads, one row each.
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ prep, const int* __restrict__ sgroup, int n,
+                                                      int W, int box_dim, float thr, int ignore_group,
+                                                      unsigned long long* __restrict__ mask) {
+    const int cb = blockIdx.x, rb = blockIdx.y;
+    if (cb < rb) return;
+    __shared__ __align__(16) float sp[64][kPrepFloats];
+    __shared__ int sg[64];
+    const int t = threadIdx.x;
+    const int row = rb * 64 + t;
+    const int col0 = cb * 64;
+    const int row_last = min(rb * 64 + 63, n - 1);
+    // groups ascend along the sorted order: no common group -> all-zero word
+    const bool tile_live = sgroup[row_last] >= sgroup[col0];
+    if (!tile_live) { if (row < n) mask[(size_t)row * W + cb] = 0ull; return; }
+    {
+        const int c = col0 + t;
+        if (c < n) {
+#pragma unroll
+            for (int i = 0; i < kPrepFloats; i += 4)
+                *reinterpret_cast<float4*>(&sp[t][i]) = *reinterpret_cast<const float4*>(prep + (size_t)c * kPrepFloats + i);
+            sg[t] = sgroup[c];
+        } else sg[t] = -1;
+    }
+    __syncthreads();
+    if (row >= n) return;
+    const int g = sgroup[row];
+    unsigned long long bits = 0ull;
+    if (g != ignore_group) {
+        const bool cull_ok = (0.0f <= thr);
+        if (box_dim == 7) {
+            ObbPrep a; load_prep(prep + (size_t)row * kPrepFloats, a);
+            for (int c = 0; c < 64; ++c) {
+                const int col = col0 + c;
+                if (col <= row || sg[c] != g) continue;
+                ObbPrep b; load_prep(sp[c], b);
+                const float iou = iou3d_obb(a, b, cull_ok);
+                if (!(iou <= thr)) bits |= 1ull << c;
+            }
+        } else {
+            float a[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) a[i] = prep[(size_t)row * kPrepFloats + i];
+            for (int c = 0; c < 64; ++c) {
+                const int col = col0 + c;
+                if (col <= row || sg[c] != g) continue;
+                const float iou = iou3d_aabb(a, sp[c]);
+                if (!(iou <= thr)) bits |= 1ull << c;
+            }
+        }
+    }
+    mask[(size_t)row * W + cb] = bits;
+}
+
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)(v & 0xffffffffull), src);
+    const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// one CTA per group id
+__global__ void __launch_bounds__(256) nms_resolve_kernel(const unsigned long long* __restrict__ mask, int W, int n,
+                                                          const int* __restrict__ seg, int ignore_group,
+                                                          unsigned long long* __restrict__ keepbits) {
+    const int g = blockIdx.x;
+    if (g == ignore_group) return;
+    const int s = seg[g], e = seg[256 + g];
+    if (e <= s) return;
+    __shared__ unsigned long long removed[kNmsMaxBoxes / 64];
+    __shared__ unsigned long long kept_sh;
+    const int c0 = s >> 6, c1 = (e - 1) >> 6;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int w = c0 + tid; w <= c1; w += blockDim.x) removed[w] = 0ull;
+    __syncthreads();
+    for (int c = c0; c <= c1; ++c) {
+        if (warp == 0) {
+            const int r_lo = c * 64 + lane, r_hi = r_lo + 32;
+            const bool v_lo = r_lo >= s && r_lo < e, v_hi = r_hi >= s && r_hi < e;
+            const unsigned long long d_lo = v_lo ? mask[(size_t)r_lo * W + c] : 0ull;
+            const unsigned long long d_hi = v_hi ? mask[(size_t)r_hi * W + c] : 0ull;
+            const unsigned b_lo = __ballot_sync(0xffffffffu, v_lo), b_hi = __ballot_sync(0xffffffffu, v_hi);
+            const unsigned long long valid = ((unsigned long long)b_hi << 32) | b_lo;
+            unsigned long long rem = removed[c] | ~valid;
+            unsigned long long kept = 0ull;
+#pragma unroll 8
+            for (int i = 0; i < 64; ++i) {
+                const unsigned long long rowbits = shfl64(i < 32 ? d_lo : d_hi, i & 31);
+                if (!((rem >> i) & 1ull)) { kept |= 1ull << i; rem |= rowbits; }
+            }
+            if (lane == 0) { kept_sh = kept; if (kept) atomicOr(&keepbits[c], kept); }
+        }
+        __syncthreads();
+        const unsigned long long kept = kept_sh;
+        for (int w = c + 1 + tid; w <= c1; w += blockDim.x) {
+            unsigned long long acc = 0ull, k = kept;
+            while (k) {
+                const int i = __ffsll((long long)k) - 1;
+                k &= k - 1;
+                acc |= mask[(size_t)(c * 64 + i) * W + w];
+            }
+            removed[w] |= acc;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void nms_keys2_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ keepbits,
+                                 int n, int n_pad, unsigned long long* __restrict__ keys2) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pad) return;
+    unsigned long long k = ~0ull;
+    if (p < n && ((keepbits[p >> 6] >> (p & 63)) & 1ull)) k = keys[p] & 0x00FFFFFFFFFFFFFFull;   // drop the group byte
+    keys2[p] = k;
+}
+
+__global__ void nms_emit_kernel(const unsigned long long* __restrict__ keys2, int n, int64_t* __restrict__ keep,
+                                int32_t* __restrict__ n_keep) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const bool v = keys2[p] != ~0ull;
+    if (v) keep[p] = (int64_t)(keys2[p] & 0xFFFFFFull);
+    const bool vn = (p + 1 < n) ? (keys2[p + 1] != ~0ull) : false;
+    if (v && !vn) *n_keep = p + 1;
+    if (p == 0 && !v) *n_keep = 0;
+}
+
+size_t nms_workspace_bytes(int n) {
+    if (n <= 0) return 256;
+    return nms_layout(nullptr, n).total + 256;
+}
+
+int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t* group, int n, float thr, int ignore_group,
+            int64_t* keep, int32_t* n_keep, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (n == 0) { NRPN_CUDA_TRY(cudaMemsetAsync(n_keep, 0, 4, st)); return NRPN_OK; }
+    if (n > kNmsMaxBoxes) return NRPN_ERR_UNSUPPORTED;
+    if (ws_bytes < nms_workspace_bytes(n)) return NRPN_ERR_WORKSPACE;
+    void* base = (void*)align_up((size_t)ws, 256);
+    NmsWs w = nms_layout(base, n);
+    const int n_pad = next_pow2(n < 2 ? 2 : n);
+    const int W = ceil_div(n, 64);
+    NRPN_CUDA_TRY(cudaMemsetAsync(w.seg, 0, 512 * 4, st));
+    NRPN_CUDA_TRY(cudaMemsetAsync(w.keepbits, 0, (size_t)W * 8, st));
+    nms_keys_kernel<<<ceil_div(n_pad, 256), 256, 0, st>>>(scores, group, n, n_pad, w.keys);
+    NRPN_LAUNCH_CHECK();
+    int rc = bitonic_sort_u64(w.keys, n_pad, st);
+    if (rc) return rc;
+    nms_prep_kernel<<<ceil_div(n, 128), 128, 0, st>>>(w.keys, boxes, box_dim, n, w.prep, w.sgroup, w.seg);
+    NRPN_LAUNCH_CHECK();
+    nms_mask_kernel<<<dim3(W, W), 64, 0, st>>>(w.prep, w.sgroup, n, W, box_dim, thr, ignore_group, w.mask);
+    NRPN_LAUNCH_CHECK();
+    nms_resolve_kernel<<<256, 256, 0, st>>>(w.mask, W, n, w.seg, ignore_group, w.keepbits);
+    NRPN_LAUNCH_CHECK();
+    nms_keys2_kernel<<<ceil_div(n_pad, 256), 256, 0, st>>>(w.keys, w.keepbits, n, n_pad, w.keys2);
+    NRPN_LAUNCH_CHECK();
+    rc = bitonic_sort_u64(w.keys2, n_pad, st);
+    if (rc) return rc;
+    nms_emit_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.keys2, n, keep, n_keep);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+}  // namespace nrpn
+
+using namespace nrpn;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int nrpn_iou3d_pairs(const float* a, const float* b, int n, int box_dim, float* iou, nrpn_stream_t stream) {
+    if (n < 0 || (box_dim != 6 && box_dim != 7)) return NRPN_ERR_INVALID;
+    if (n == 0) return NRPN_OK;
+    if (!a || !b || !iou) return NRPN_ERR_INVALID;
+    iou_pairs_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(a, b, n, box_dim, iou);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+int nrpn_iou3d_matrix(const float* a, int n, const float* b, int m, int box_dim, float* out, nrpn_stream_t stream) {
+    if (n < 0 || m < 0 || (box_dim != 6 && box_dim != 7)) return NRPN_ERR_INVALID;
+    if (n == 0 || m == 0) return NRPN_OK;
+    if (!a || !b || !out) return NRPN_ERR_INVALID;
+    dim3 grid(ceil_div(m, 32), ceil_div(n, 8));
+    if (grid.y > 65535) return NRPN_ERR_UNSUPPORTED;
+    iou_matrix_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, n, b, m, box_dim, out);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+int nrpn_sort_vertices(const float* vertices, const uint8_t* mask, const int32_t* num_valid, int b, int n, int m,
+                       int32_t* idx, nrpn_stream_t stream) {
+    if (b < 0 || n < 0 || m < 9 || m > 32) return NRPN_ERR_INVALID;
+    const long total = (long)b * n;
+    if (total == 0) return NRPN_OK;
+    if (!vertices || !mask || !num_valid || !idx) return NRPN_ERR_INVALID;
+    sort_vertices_kernel<<<(unsigned)ceil_div(total, 128L), 128, 0, (cudaStream_t)stream>>>(vertices, mask, num_valid, total, m, idx);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+int nrpn_nms_max_boxes(void) { return kNmsMaxBoxes; }
+
+size_t nrpn_nms_workspace_bytes(int n) { return nms_workspace_bytes(n); }
+
+int nrpn_nms(const float* boxes, int box_dim, const float* scores, const int32_t* group, int n, float thr, int64_t* keep,
+             int32_t* n_keep, void* workspace, size_t workspace_bytes, nrpn_stream_t stream) {
+    if (n < 0 || (box_dim != 6 && box_dim != 7) || !n_keep) return NRPN_ERR_INVALID;
+    if (n > 0 && (!boxes || !scores || !keep || !workspace)) return NRPN_ERR_INVALID;
+    return nms_run(boxes, box_dim, scores, group, n, thr, /*ignore_group=*/-1, keep, n_keep, workspace, workspace_bytes,
+                   (cudaStream_t)stream);
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

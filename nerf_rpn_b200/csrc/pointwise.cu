@@ -1,0 +1,128 @@
+// Bandwidth-bound helpers around the convolutions (HBM roofline kernels; 16-byte coalesced accesses).
+#include "common.cuh"
+
+namespace nrpn {
+
+// fp32 NCDHW grid (N,4,X,Y,Z) -> bf16 (N, X2, Y2, Z2+1, 64), X2 = ceil(X/2) etc.
+// Row (i,j,k) holds two 2x2x2 space-to-depth blocks: channels [0,32) = block (i,j,k-1), [32,64) = block (i,j,k);
+// inside a block channel = ((rx*2+ry)*2+rz)*4 + c for input voxel (2i+rx, 2j+ry, 2k'+rz), zero outside the grid.
+// With this layout the reference's stem Conv3d(4,64,k=7,s=2,p=3) (feature_extractor.py:163) is a stride-1
+// implicit GEMM with 4x4x2 taps of K = 64 (see nerf_rpn_b200/engine.py: pack_stem_weight).
+// One thread writes one 16-byte chunk (8 channels); 8 consecutive lanes cover one 128-byte row.
+__global__ void pack_stem_kernel(const float* __restrict__ grid, int n, int X, int Y, int Z, int X2, int Y2, int Z2,
+                                 __nv_bfloat16* __restrict__ out) {
+    const size_t total = (size_t)n * X2 * Y2 * (Z2 + 1) * 8;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int s = (int)(t & 7);
+        size_t v = t >> 3;
+        const int k = (int)(v % (Z2 + 1)); v /= (Z2 + 1);
+        const int j = (int)(v % Y2); v /= Y2;
+        const int i = (int)(v % X2); const int b = (int)(v / X2);
+        const int half = s >> 2, rx = (s >> 1) & 1, ry = s & 1;
+        const int kk = k - 1 + half;                    // s2d block index along z
+        const int x = 2 * i + rx, y = 2 * j + ry, z = 2 * kk;
+        float val[8];                                   // order: rz major, c minor
+#pragma unroll
+        for (int q = 0; q < 8; ++q) val[q] = 0.f;
+        if (kk >= 0 && kk < Z2 && x < X && y < Y) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float* p = grid + ((((size_t)b * 4 + c) * X + x) * Y + y) * Z + z;
+                val[c] = p[0];
+                if (z + 1 < Z) val[4 + c] = p[1];
+            }
+        }
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(val[2 * q], val[2 * q + 1]);
+        *reinterpret_cast<uint4*>(out + (t << 3)) = *reinterpret_cast<uint4*>(h);
+    }
+}
+
+// F.max_pool3d(k=3, s=2, p=1) on channels-last bf16; one thread per (output voxel, 8 channels).
+__global__ void maxpool_k3s2_kernel(const __nv_bfloat16* __restrict__ in, int n, int X, int Y, int Z, int C, int Xo, int Yo,
+                                    int Zo, __nv_bfloat16* __restrict__ out) {
+    const int cg = C >> 3;
+    const size_t total = (size_t)n * Xo * Yo * Zo * cg;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(t % cg); size_t v = t / cg;
+        const int k = (int)(v % Zo); v /= Zo;
+        const int j = (int)(v % Yo); v /= Yo;
+        const int i = (int)(v % Xo); const int b = (int)(v / Xo);
+        float m[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int x = 2 * i + dx; if (x < 0 || x >= X) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int y = 2 * j + dy; if (y < 0 || y >= Y) continue;
+#pragma unroll
+                for (int dz = -1; dz <= 1; ++dz) {
+                    const int z = 2 * k + dz; if (z < 0 || z >= Z) continue;
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + ((((size_t)b * X + x) * Y + y) * Z + z) * C + g * 8));
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); m[2 * q] = fmaxf(m[2 * q], f.x); m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y); }
+                }
+            }
+        }
+        __nv_bfloat162 o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = __floats2bfloat162_rn(m[2 * q], m[2 * q + 1]);
+        *reinterpret_cast<uint4*>(out + ((((size_t)b * Xo + i) * Yo + j) * Zo + k) * C + g * 8) = *reinterpret_cast<uint4*>(o);
+    }
+}
+
+static inline unsigned grid_for(size_t total, int block) {
+    size_t g = (total + block - 1) / block;
+    const size_t cap = (size_t)num_sms() * 16;
+    return (unsigned)(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace nrpn
+
+using namespace nrpn;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int nrpn_pack_stem_input(const float* grid, int n, int x, int y, int z, void* packed, nrpn_stream_t stream) {
+    if (!grid || !packed || n < 1 || x < 1 || y < 1 || z < 1) return NRPN_ERR_INVALID;
+    const int X2 = (x + 1) / 2, Y2 = (y + 1) / 2, Z2 = (z + 1) / 2;
+    const size_t total = (size_t)n * X2 * Y2 * (Z2 + 1) * 8;
+    pack_stem_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, n, x, y, z, X2, Y2, Z2,
+                                                                            reinterpret_cast<__nv_bfloat16*>(packed));
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+int nrpn_maxpool3d_k3s2(const void* in, int n, int x, int y, int z, int c, void* out, nrpn_stream_t stream) {
+    if (!in || !out || n < 1 || x < 1 || y < 1 || z < 1 || c < 8 || c % 8 != 0) return NRPN_ERR_INVALID;
+    const int Xo = (x - 1) / 2 + 1, Yo = (y - 1) / 2 + 1, Zo = (z - 1) / 2 + 1;
+    const size_t total = (size_t)n * Xo * Yo * Zo * (c / 8);
+    maxpool_k3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(in), n, x, y, z, c, Xo, Yo, Zo, reinterpret_cast<__nv_bfloat16*>(out));
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+int nrpn_version(void) { return 100; }
+
+const char* nrpn_status_string(int status) {
+    switch (status) {
+        case NRPN_OK: return "ok";
+        case NRPN_ERR_INVALID: return "invalid argument";
+        case NRPN_ERR_UNSUPPORTED: return "unsupported shape";
+        case NRPN_ERR_WORKSPACE: return "workspace too small";
+        case NRPN_ERR_CUDA: return "CUDA error";
+        case NRPN_ERR_NO_DEVICE: return "no sm_100 device / driver entry point";
+        default: return "unknown status";
+    }
+}
+
+int nrpn_last_cuda_error(void) { return g_last_cuda_error; }
+
+unsigned long long nrpn_launch_count(void) { return g_launch_count.load(); }
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,207 @@
+"""Torch-tensor front-ends of the C ABI. PyTorch only provides device memory and the current stream here;
+every computation is a kernel of libnerf_rpn_b200.so.  All functions require CUDA tensors and raise otherwise
+(no CPU fallback)."""
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, RpnDesc, check, lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"nerf_rpn_b200: {name} must be a CUDA tensor (this package has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"nerf_rpn_b200: {name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"nerf_rpn_b200: {name} must be contiguous")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+# ------------------------------------------------------------------------------------------------ boxes
+def iou3d_pairs(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    a = _req(a, torch.float32, "a"); b = _req(b, torch.float32, "b")
+    if a.shape != b.shape or a.dim() != 2 or a.shape[1] not in (6, 7):
+        raise ValueError("iou3d_pairs expects two (n,6) or two (n,7) tensors")
+    out = torch.empty(a.shape[0], dtype=torch.float32, device=a.device)
+    check(lib().nrpn_iou3d_pairs(_ptr(a), _ptr(b), a.shape[0], a.shape[1], _ptr(out), _stream()), "iou3d_pairs")
+    return out
+
+
+def iou3d_matrix(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    a = _req(a, torch.float32, "a"); b = _req(b, torch.float32, "b")
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1] or a.shape[1] not in (6, 7):
+        raise ValueError("The second dimension of boxes1 and boxes2 should be the same, both 6 or 7. But get {} and {}."
+                         .format(a.shape[-1], b.shape[-1]))
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    check(lib().nrpn_iou3d_matrix(_ptr(a), a.shape[0], _ptr(b), b.shape[0], a.shape[1], _ptr(out), _stream()), "iou3d_matrix")
+    return out
+
+
+def sort_vertices_forward(vertices: torch.Tensor, mask: torch.Tensor, num_valid: torch.Tensor) -> torch.Tensor:
+    """Same contract as the reference's pybind op (cuda_op/sort_vert.cpp:6-34)."""
+    if not vertices.is_cuda:
+        raise RuntimeError("vertices must be a CUDA tensor")
+    if not mask.is_cuda:
+        raise RuntimeError("mask must be a CUDA tensor")
+    if not num_valid.is_cuda:
+        raise RuntimeError("num_valid must be a CUDA tensor")
+    if not (vertices.is_contiguous() and mask.is_contiguous() and num_valid.is_contiguous()):
+        raise RuntimeError("inputs must be contiguous tensors")
+    if vertices.dtype != torch.float32:
+        raise RuntimeError("vertices must be a float tensor")
+    if mask.dtype != torch.bool:
+        raise RuntimeError("mask must be a bool tensor")
+    if num_valid.dtype != torch.int32:
+        raise RuntimeError("num_valid must be a int tensor")
+    b, n, m = vertices.shape[0], vertices.shape[1], vertices.shape[2]
+    idx = torch.zeros((b, n, 9), dtype=torch.int32, device=vertices.device)
+    with torch.cuda.device(vertices.device):
+        check(lib().nrpn_sort_vertices(_ptr(vertices), _ptr(mask), _ptr(num_valid), b, n, m, _ptr(idx), _stream()),
+              "sort_vertices")
+    return idx
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def nms_device(boxes: torch.Tensor, scores: torch.Tensor, groups: Optional[torch.Tensor], thr: float):
+    """Returns (keep int64 (n,), n_keep int32 (1,)) on the device -- no host synchronisation."""
+    boxes = _req(boxes, torch.float32, "boxes"); scores = _req(scores, torch.float32, "scores")
+    n = boxes.shape[0]
+    if groups is not None:
+        groups = _req(groups, torch.int32, "groups")
+    keep = torch.empty(max(n, 1), dtype=torch.int64, device=boxes.device)
+    n_keep = torch.zeros(1, dtype=torch.int32, device=boxes.device)
+    if n == 0:
+        return keep[:0], n_keep
+    if n > lib().nrpn_nms_max_boxes():
+        raise ValueError(f"nms: at most {lib().nrpn_nms_max_boxes()} boxes per call are supported, got {n}")
+    wsb = lib().nrpn_nms_workspace_bytes(n)
+    ws = _workspace(wsb, boxes.device)
+    check(lib().nrpn_nms(_ptr(boxes), boxes.shape[1], _ptr(scores), _ptr(groups), n, float(thr), _ptr(keep), _ptr(n_keep),
+                         _ptr(ws), ws.numel(), _stream()), "nms")
+    return keep, n_keep
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def conv_block_n(cout: int) -> int:
+    return lib().nrpn_conv3d_block_n(int(cout))
+
+
+class ConvLevelArgs:
+    __slots__ = ("x", "y", "res", "n", "in_dims", "out_dims", "res_dims", "ldy", "ldr")
+
+    def __init__(self, x, y, n, in_dims, out_dims, ldy, res=None, res_dims=None, ldr=0):
+        self.x, self.y, self.res, self.n = x, y, res, n
+        self.in_dims, self.out_dims = tuple(in_dims), tuple(out_dims)
+        self.res_dims = tuple(res_dims) if res_dims is not None else tuple(out_dims)
+        self.ldy, self.ldr = ldy, ldr
+
+
+def conv3d_fprop(levels: Sequence[ConvLevelArgs], w: torch.Tensor, shift: torch.Tensor, cin: int, cout: int,
+                 taps: Sequence[Sequence[int]], stride: int = 1, relu: bool = False, out_fp32: bool = False):
+    """One persistent tcgen05 implicit-GEMM launch over 1..4 levels sharing (w, shift)."""
+    d = ConvDesc()
+    d.cin, d.cout, d.n_taps = int(cin), int(cout), len(taps)
+    for t, off in enumerate(taps):
+        for k in range(3):
+            d.tap_off[t][k] = int(off[k])
+    d.stride, d.relu, d.out_fp32 = int(stride), int(bool(relu)), int(bool(out_fp32))
+    d.w, d.shift = w.data_ptr(), shift.data_ptr()
+    d.n_levels = len(levels)
+    for i, L in enumerate(levels):
+        lv = d.level[i]
+        lv.x, lv.y = L.x.data_ptr(), L.y.data_ptr()
+        lv.res = 0 if L.res is None else L.res.data_ptr()
+        lv.n = int(L.n)
+        lv.xi, lv.yi, lv.zi = (int(v) for v in L.in_dims)
+        lv.xo, lv.yo, lv.zo = (int(v) for v in L.out_dims)
+        lv.xr, lv.yr, lv.zr = (int(v) for v in L.res_dims)
+        lv.ldy, lv.ldr = int(L.ldy), int(L.ldr)
+    check(lib().nrpn_conv3d_fprop(ctypes.byref(d), _stream()), "conv3d_fprop")
+
+
+def pack_stem_input(grid: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,4,X,Y,Z) fp32 -> (N, ceil(X/2), ceil(Y/2), ceil(Z/2)+1, 64) bf16."""
+    grid = _req(grid, torch.float32, "grid")
+    n, c, x, y, z = grid.shape
+    if c != 4:
+        raise ValueError("stem packing expects 4 input channels (RGB + density)")
+    shape = (n, (x + 1) // 2, (y + 1) // 2, (z + 1) // 2 + 1, 64)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.bfloat16, device=grid.device)
+    check(lib().nrpn_pack_stem_input(_ptr(grid), n, x, y, z, _ptr(out), _stream()), "pack_stem_input")
+    return out
+
+
+def maxpool3d_k3s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,X,Y,Z,C) bf16 channels-last -> k3 s2 p1 max pool."""
+    x = _req(x, torch.bfloat16, "x")
+    n, X, Y, Z, C = x.shape
+    shape = (n, (X - 1) // 2 + 1, (Y - 1) // 2 + 1, (Z - 1) // 2 + 1, C)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().nrpn_maxpool3d_k3s2(_ptr(x), n, X, Y, Z, C, _ptr(out), _stream()), "maxpool3d_k3s2")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ rpn post
+def make_rpn_desc(preds: List[torch.Tensor], grids, strides, cells, num_anchors: int, rotated: bool, pre_nms_top_n: int,
+                  post_nms_top_n: int, nms_thresh: float, score_thresh: float, min_size: float, mesh, valid=None) -> RpnDesc:
+    d = RpnDesc()
+    d.n_levels = len(preds)
+    for l, p in enumerate(preds):
+        p = _req(p, torch.float32, f"pred[{l}]")
+        lv = d.level[l]
+        lv.pred = p.data_ptr(); lv.ld = int(p.shape[-1])
+        lv.gx, lv.gy, lv.gz = (int(v) for v in grids[l])
+        lv.sx, lv.sy, lv.sz = (int(v) for v in strides[l])
+        for a in range(num_anchors):
+            for k in range(6):
+                d.cell_anchors[l][a][k] = float(cells[l][a][k])
+    d.num_anchors = int(num_anchors); d.rotated = int(bool(rotated))
+    d.pre_nms_top_n, d.post_nms_top_n = int(pre_nms_top_n), int(post_nms_top_n)
+    d.nms_thresh, d.score_thresh, d.min_size = float(nms_thresh), float(score_thresh), float(min_size)
+    for k in range(3):
+        d.mesh[k] = int(mesh[k]); d.valid[k] = int((valid or mesh)[k])
+    return d
+
+
+def rpn_proposals(desc: RpnDesc, device, out=None, workspace: Optional[torch.Tensor] = None):
+    """Runs the device-side post-processing; returns (boxes, scores, levels, count) device tensors (count int32 (1,))."""
+    box_dim = 7 if desc.rotated else 6
+    k = desc.post_nms_top_n
+    if out is None:
+        boxes = torch.empty((k, box_dim), dtype=torch.float32, device=device)
+        scores = torch.empty((k,), dtype=torch.float32, device=device)
+        levels = torch.empty((k,), dtype=torch.float32, device=device)
+        count = torch.zeros((1,), dtype=torch.int32, device=device)
+    else:
+        boxes, scores, levels, count = out
+    wsb = lib().nrpn_rpn_workspace_bytes(ctypes.byref(desc))
+    if wsb == 0:
+        raise ValueError("nerf_rpn_b200: invalid RPN descriptor")
+    ws = workspace if workspace is not None else _workspace(wsb, device)
+    check(lib().nrpn_rpn_proposals(ctypes.byref(desc), _ptr(boxes), _ptr(scores), _ptr(levels), _ptr(count), _ptr(ws),
+                                   ws.numel(), _stream()), "rpn_proposals")
+    return boxes, scores, levels, count

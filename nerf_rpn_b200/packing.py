@@ -1,0 +1,88 @@
+"""Weight pre-packing for the tcgen05 implicit-GEMM convolution (host-side, runs once per checkpoint).
+
+Reference layouts: nn.Conv3d.weight is (Cout, Cin, kx, ky, kz) fp32 over an NCDHW (N,C,W,L,H) input
+(feature_extractor.py:36-43,163,178,184; anchor.py:190-198).  The kernel wants one K-major (Cout x Cin) bf16
+matrix per filter tap, (taps, CoutPad, Cin), with eval-mode BatchNorm folded in: scale multiplied into the
+weights, shift kept as an fp32 per-channel epilogue add.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+
+
+def fold_bn(bn: torch.nn.modules.batchnorm._BatchNorm) -> Tuple[torch.Tensor, torch.Tensor]:
+    """eval-mode BatchNorm3d (feature_extractor.py:38,41,43) as y = x * scale + shift."""
+    inv = torch.rsqrt(bn.running_var.detach().double() + bn.eps)
+    scale = bn.weight.detach().double() * inv
+    shift = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+    return scale.float(), shift.float()
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def conv_block_n(cout: int) -> int:
+    return 64 if cout <= 64 else (128 if cout <= 128 else 256)
+
+
+def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None, cout_pad_to: Optional[int] = None):
+    """(Cout, Cin, k, k, k) -> (taps, CoutPad, CinPad) bf16 and the tap offset table for 'same' padding (k odd)."""
+    cout, cin, kx, ky, kz = w.shape
+    w = w.detach().float()
+    if scale is not None:
+        w = w * scale.view(-1, 1, 1, 1, 1).to(w)
+    cout8 = _round_up(cout, 8)
+    bn = conv_block_n(cout8)
+    cpad = _round_up(cout8, bn) if cout_pad_to is None else cout_pad_to
+    cin_pad = _round_up(cin, 64)
+    taps: List[Tuple[int, int, int]] = []
+    mats = []
+    for a in range(kx):
+        for b in range(ky):
+            for c in range(kz):
+                taps.append((a - kx // 2, b - ky // 2, c - kz // 2))
+                mats.append(w[:, :, a, b, c])
+    m = torch.stack(mats, 0)                                   # (taps, Cout, Cin)
+    out = torch.zeros((len(taps), cpad, cin_pad), dtype=torch.float32, device=w.device)
+    out[:, :cout, :cin] = m
+    return out.to(torch.bfloat16).contiguous(), taps
+
+
+def pad_shift(shift: torch.Tensor, cpad: int) -> torch.Tensor:
+    out = torch.zeros(cpad, dtype=torch.float32, device=shift.device)
+    out[: shift.numel()] = shift.detach().float()
+    return out
+
+
+def pack_stem_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None):
+    """Stem Conv3d(4, 64, kernel 7, stride 2, padding 3) (feature_extractor.py:163) re-expressed on the packed
+    space-to-depth input of csrc/pointwise.cu: 4 x 4 x 2 taps, K = 64 per tap.
+
+    Packed row (i,j,k) = [s2d block (i,j,k-1) | s2d block (i,j,k)], block channel = ((rx*2+ry)*2+rz)*4 + c.
+    Output voxel o reads input 2*o + kk - 3 (kk = 0..6) = 2*(o + q) + r, q in {-2,-1,0,1}; along z the two blocks of a
+    packed row are q = dz-1 and q = dz for tap offset dz in {-1, +1}.
+    """
+    cout, cin, k, _, _ = w.shape
+    assert (cin, k) == (4, 7), "stem packing is specific to the reference's 7^3 stride-2 stem on 4 channels"
+    w = w.detach().float()
+    if scale is not None:
+        w = w * scale.view(-1, 1, 1, 1, 1).to(w)
+    taps, mats = [], []
+    for qx in (-2, -1, 0, 1):
+        for qy in (-2, -1, 0, 1):
+            for dz in (-1, 1):
+                m = torch.zeros((cout, 64), dtype=torch.float32, device=w.device)
+                for half in (0, 1):
+                    qz = dz - 1 + half
+                    for rx in (0, 1):
+                        for ry in (0, 1):
+                            for rz in (0, 1):
+                                kx, ky, kz = 2 * qx + rx + 3, 2 * qy + ry + 3, 2 * qz + rz + 3
+                                if 0 <= kx < 7 and 0 <= ky < 7 and 0 <= kz < 7:
+                                    ch = half * 32 + ((rx * 2 + ry) * 2 + rz) * 4
+                                    m[:, ch:ch + 4] = w[:, :, kx, ky, kz]
+                taps.append((qx, qy, dz))
+                mats.append(m)
+    out = torch.stack(mats, 0)                                  # (32, 64, 64)
+    return out.to(torch.bfloat16).contiguous(), taps
