@@ -278,8 +278,8 @@ static void choose_brick(int xo, int yo, int zo, int& bx, int& by, int& bz) {
         const int cz = 1 << ez, cy = 1 << ey, cx = 1 << ex;
         if (cz > 256 || cy > 256 || cx > 256) continue;
         const long vol = (long)ceil_div(xo, cx) * cx * ceil_div(yo, cy) * cy * ceil_div(zo, cz) * cz;
-        // prefer less padding, then longer z runs (contiguous in memory), then y
-        const long score = vol * 1024 - ez * 16 - ey;
+        // prefer less padding, then compact bricks (smallest halo => best L2 reuse across the filter taps)
+        const long score = vol * 4096 + (long)(cx + 2) * (cy + 2) * (cz + 2);
         if (best < 0 || score < best) { best = score; bx = cx; by = cy; bz = cz; }
     }
 }

@@ -1,0 +1,316 @@
+"""Inference engine: ResNet50-3D + FPN + anchor RPN head + proposal post-processing as a fixed list of
+libnerf_rpn_b200 kernel launches over pre-allocated channels-last bf16 buffers, captured in a CUDA graph.
+
+Mirrors, layer for layer, the reference forward
+  NeRFRegionProposalNetwork.forward      nerf_rpn/model/nerf_rpn.py:166-217
+  ResNet_FPN_256.forward / Bottleneck    nerf_rpn/model/feature_extractor.py:31-68,215-235
+  RPNHead.forward                        nerf_rpn/model/anchor.py:206-213
+  RegionProposalNetwork.forward (eval)   nerf_rpn/model/rpn.py:458-536
+but: BatchNorm (eval) is folded into the conv weights, ReLU / residual / FPN nearest-upsample-add are conv
+epilogues, the head runs all four pyramid levels in one launch per layer, cls and bbox predictors are one GEMM,
+only the top-k candidates are decoded, and NMS never leaves the device.
+
+PyTorch's role here: owning device buffers, the stream and the CUDA graph object.  Training-mode forward
+(BatchNorm batch statistics, losses) is not implemented in this round and raises.
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops, packing
+
+
+class _Conv:
+    """One pre-packed convolution (+ folded BN / bias, optional ReLU)."""
+
+    def __init__(self, weight, bias=None, bn=None, stride=1, relu=False, stem=False, cout_pad_to=None, device="cuda"):
+        scale = shift = None
+        if bn is not None:
+            scale, shift = packing.fold_bn(bn)
+            if bias is not None:
+                shift = shift + bias.detach().float() * scale
+        elif bias is not None:
+            shift = bias.detach().float()
+        cout = weight.shape[0]
+        if stem:
+            wp, taps = packing.pack_stem_weight(weight, scale)
+        else:
+            wp, taps = packing.pack_conv_weight(weight, scale, cout_pad_to=cout_pad_to)
+        self.w = wp.to(device)
+        self.taps = taps
+        self.cin = wp.shape[2]
+        self.cout = ((cout + 7) // 8) * 8 if cout_pad_to is None else cout_pad_to
+        if shift is None:
+            shift = torch.zeros(cout)
+        self.shift = packing.pad_shift(shift, wp.shape[1]).to(device)
+        self.stride, self.relu = stride, relu
+
+    def flops(self, out_voxels: int, real_cin: Optional[int] = None, real_taps: Optional[int] = None) -> float:
+        return 2.0 * out_voxels * self.cout * (real_cin or self.cin) * (real_taps or len(self.taps))
+
+
+def _down(d: Sequence[int]) -> Tuple[int, int, int]:
+    return tuple((v - 1) // 2 + 1 for v in d)
+
+
+class RPNInferenceEngine:
+    """Executes backbone -> FPN -> head -> proposals for a batch of equally sized scenes."""
+
+    def __init__(self, backbone, head=None, anchor_cells=None, num_anchors: int = 0, rotated: bool = False,
+                 pre_nms_top_n: int = 2500, post_nms_top_n: int = 2500, nms_thresh: float = 0.3, score_thresh: float = 0.0,
+                 min_size: float = 1e-3, use_graph: bool = True):
+        self.backbone, self.head = backbone, head
+        self.cells = anchor_cells          # list (levels) of (A, 6) float arrays
+        self.A, self.rotated = num_anchors, rotated
+        self.code = 8 if rotated else 6
+        self.pre_n, self.post_n = pre_nms_top_n, post_nms_top_n
+        self.nms_thresh, self.score_thresh, self.min_size = nms_thresh, score_thresh, min_size
+        self.use_graph = use_graph
+        self._packed_version = None
+        self._plans: Dict[tuple, "_Plan"] = {}
+        self.layers = None
+
+    # ---------------------------------------------------------------- weights
+    def _param_version(self):
+        v = 0
+        for m in (self.backbone, self.head):
+            if m is None:
+                continue
+            for t in list(m.parameters()) + list(m.buffers()):
+                v += t._version + (t.data_ptr() % 1000003)
+        return v
+
+    def _pack(self, device):
+        bb, hd = self.backbone, self.head
+        L = {}
+        L["stem"] = _Conv(bb.conv1.weight, None, bb.bn1, relu=True, stem=True, device=device)
+        blocks = []
+        for stage in bb.layers:
+            for blk in stage:
+                s = blk.stride
+                e = {
+                    "c1": _Conv(blk.conv1.weight, None, blk.bn1, stride=s, relu=True, device=device),
+                    "c2": _Conv(blk.conv2.weight, None, blk.bn2, relu=True, device=device),
+                    "c3": _Conv(blk.conv3.weight, None, blk.bn3, relu=True, device=device),   # ReLU after the residual add
+                    "ds": None, "stride": s,
+                }
+                if blk.downsample is not None:
+                    e["ds"] = _Conv(blk.downsample[0].weight, None, blk.downsample[1], stride=s, relu=False, device=device)
+                blocks.append(e)
+        L["blocks"] = blocks
+        L["lat"] = [_Conv(m.weight, m.bias, device=device) for m in bb.latlayers]
+        L["smooth"] = [_Conv(m.weight, m.bias, device=device) for m in bb.smooths]
+        if hd is None:
+            self.layers = L
+            self._plans.clear()
+            return
+        convs = [m for m in hd.conv if isinstance(m, torch.nn.Conv3d)]
+        L["head"] = [_Conv(m.weight, m.bias, relu=True, device=device) for m in convs]
+        # cls (A) and bbox (A*code) predictors fused into one 1x1x1 GEMM, zero-padded to 128 output channels
+        w = torch.cat([hd.cls_logits.weight, hd.bbox_pred.weight], 0)
+        b = torch.cat([hd.cls_logits.bias, hd.bbox_pred.bias], 0)
+        if w.shape[0] > 128:
+            raise ValueError("fused predictor supports at most 128 output channels")
+        L["pred"] = _Conv(w, b, device=device, cout_pad_to=128)
+        self.layers = L
+        self._plans.clear()
+
+    # ---------------------------------------------------------------- plan
+    def _get_plan(self, n, dims, device):
+        ver = self._param_version()
+        if self.layers is None or ver != self._packed_version:
+            self._pack(device)
+            self._packed_version = ver
+        key = (n, tuple(dims), str(device))
+        p = self._plans.get(key)
+        if p is None:
+            p = _Plan(self, n, tuple(dims), device)
+            self._plans[key] = p
+        return p
+
+    def check_eval(self):
+        if self.backbone.training or (self.head is not None and self.head.training):
+            raise NotImplementedError(
+                "nerf_rpn_b200: training-mode forward (BatchNorm batch statistics, RPN losses, gradients) is not "
+                "implemented by the B200 engine yet; call .eval() (inference) -- there is no PyTorch fallback")
+
+    def forward_device(self, grids: torch.Tensor, valid_dims: Optional[Sequence[Sequence[int]]] = None):
+        """grids: (N,4,X,Y,Z) fp32 CUDA.  Returns the plan whose output buffers hold the results (no host sync)."""
+        self.check_eval()
+        if not grids.is_cuda or grids.dtype != torch.float32:
+            raise RuntimeError("nerf_rpn_b200: input grids must be fp32 CUDA tensors (no CPU path)")
+        n, c, X, Y, Z = grids.shape
+        plan = self._get_plan(n, (X, Y, Z), grids.device)
+        plan.run(grids, valid_dims)
+        return plan
+
+    def flops_per_scene(self, dims) -> float:
+        """Algorithmic conv FLOPs (2*MAC on the reference's real filter taps / channels) for one scene."""
+        p = self._get_plan(1, tuple(dims), torch.device("cuda"))
+        return p.algorithmic_flops
+
+
+class _Plan:
+    def __init__(self, eng: RPNInferenceEngine, n: int, dims: Tuple[int, int, int], device):
+        self.eng, self.n, self.dims, self.device = eng, n, dims, device
+        L = eng.layers
+        bf = dict(dtype=torch.bfloat16, device=device)
+        X, Y, Z = dims
+        self.launches = []           # backbone stage: list of zero-arg callables
+        self.head_launches = []      # head stage
+        self._cur = self.launches
+        self.algorithmic_flops = 0.0
+
+        def buf(d, c, dtype=torch.bfloat16):
+            return torch.empty((n, *d, c), dtype=dtype, device=device)
+
+        def conv(layer: _Conv, xs, ys, in_dims, out_dims, res=None, res_dims=None, out_fp32=False, real=None):
+            args = []
+            for i in range(len(xs)):
+                r = None if res is None else res[i]
+                args.append(ops.ConvLevelArgs(xs[i], ys[i], n, in_dims[i], out_dims[i], ys[i].shape[-1], res=r,
+                                              res_dims=None if r is None else res_dims[i], ldr=0 if r is None else r.shape[-1]))
+            self._cur.append(lambda a=args, l=layer, f=out_fp32: ops.conv3d_fprop(
+                a, l.w, l.shift, l.cin, l.cout, l.taps, stride=l.stride, relu=l.relu, out_fp32=f))
+            for od in out_dims:
+                vox = n * od[0] * od[1] * od[2]
+                rc, rt, rco = real if real else (layer.cin, len(layer.taps), layer.cout)
+                self.algorithmic_flops += 2.0 * vox * rco * rc * rt / n
+
+        # static input + stem
+        self.input = torch.empty((n, 4, X, Y, Z), dtype=torch.float32, device=device)
+        d1 = _down(dims)
+        self.packed = torch.empty((n, d1[0], d1[1], d1[2] + 1, 64), **bf)
+        self.launches.append(lambda: ops.pack_stem_input(self.input, self.packed))
+        c1 = buf(d1, 64)
+        conv(L["stem"], [self.packed], [c1], [(d1[0], d1[1], d1[2] + 1)], [d1], real=(4, 343, 64))
+        d2 = _down(d1)
+        c1p = buf(d2, 64)
+        self.launches.append(lambda: ops.maxpool3d_k3s2(c1, c1p))
+
+        # bottom-up
+        x, xd = c1p, d2
+        c_out = []
+        bi = 0
+        for si, stage in enumerate(eng.backbone.layers):
+            for _ in stage:
+                e = L["blocks"][bi]; bi += 1
+                s = e["stride"]
+                od = _down(xd) if s == 2 else xd
+                a = buf(od, e["c1"].cout)
+                conv(e["c1"], [x], [a], [xd], [od])
+                b = buf(od, e["c2"].cout)
+                conv(e["c2"], [a], [b], [od], [od])
+                if e["ds"] is not None:
+                    r = buf(od, e["ds"].cout)
+                    conv(e["ds"], [x], [r], [xd], [od])
+                else:
+                    r = x
+                o = buf(od, e["c3"].cout)
+                conv(e["c3"], [b], [o], [od], [od], res=[r], res_dims=[od])
+                x, xd = o, od
+            c_out.append((x, xd))
+
+        # top-down (feature_extractor.py:224-235): p5 = lat0(c5); p_i = up(p_{i+1}) + lat(c_i); smooth all but p5
+        (c5, d5) = c_out[-1]
+        p = buf(d5, 256)
+        conv(L["lat"][0], [c5], [p], [d5], [d5])
+        p_out = [(p, d5)]
+        for i in range(1, len(L["lat"])):
+            (c, cd) = c_out[-1 - i]
+            q = buf(cd, 256)
+            conv(L["lat"][i], [c], [q], [cd], [cd], res=[p_out[-1][0]], res_dims=[p_out[-1][1]])
+            p_out.append((q, cd))
+        feats = [p_out[0]]
+        for i, sm in enumerate(L["smooth"]):
+            (q, qd) = p_out[i + 1]
+            sq = buf(qd, 256)
+            conv(sm, [q], [sq], [qd], [qd])
+            feats.append((sq, qd))
+        feats.reverse()                                   # [P2, P3, P4, P5]
+        self.features = [f for f, _ in feats]
+        self.feat_dims = [d for _, d in feats]
+
+        # head: all levels per launch
+        self.has_head = eng.head is not None
+        if not self.has_head:
+            return
+        self._cur = self.head_launches
+        cur = self.features
+        for layer in L["head"]:
+            nxt = [buf(d, 256) for d in self.feat_dims]
+            conv(layer, cur, nxt, self.feat_dims, self.feat_dims)
+            cur = nxt
+        self.pred = [buf(d, 128, torch.float32) for d in self.feat_dims]
+        conv(L["pred"], cur, self.pred, self.feat_dims, self.feat_dims, out_fp32=True,
+             real=(256, 1, eng.A * (1 + eng.code)))
+
+        # proposals
+        self.strides = [tuple(dims[k] // d[k] for k in range(3)) for d in self.feat_dims]
+        self.out_boxes = torch.zeros((n, eng.post_n, 7 if eng.rotated else 6), dtype=torch.float32, device=device)
+        self.out_scores = torch.zeros((n, eng.post_n), dtype=torch.float32, device=device)
+        self.out_levels = torch.zeros((n, eng.post_n), dtype=torch.float32, device=device)
+        self.out_count = torch.zeros((n,), dtype=torch.int32, device=device)
+        self._rpn_ws = None
+        self._valid = None
+        self._graph = None
+        self._post = []
+        self._build_post(None)
+
+    def _build_post(self, valid_dims):
+        eng = self.eng
+        self._post = []
+        self._descs = []
+        ws_bytes = 0
+        for i in range(self.n):
+            preds = [p[i].reshape(-1, 128) for p in self.pred]
+            v = None if valid_dims is None else valid_dims[i]
+            d = ops.make_rpn_desc(preds, self.feat_dims, self.strides, eng.cells, eng.A, eng.rotated, eng.pre_n, eng.post_n,
+                                  eng.nms_thresh, eng.score_thresh, eng.min_size, self.dims, valid=v)
+            self._descs.append(d)
+            import ctypes
+            from ._lib import lib
+            ws_bytes = max(ws_bytes, lib().nrpn_rpn_workspace_bytes(ctypes.byref(d)))
+        if self._rpn_ws is None or self._rpn_ws.numel() < ws_bytes:
+            self._rpn_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        for i, d in enumerate(self._descs):
+            out = (self.out_boxes[i], self.out_scores[i], self.out_levels[i], self.out_count[i:i + 1])
+            self._post.append(lambda d=d, out=out: ops.rpn_proposals(d, self.device, out=out, workspace=self._rpn_ws))
+        self._valid = valid_dims
+
+    def _run_eager(self):
+        for f in self.launches:
+            f()
+        if self.has_head:
+            for f in self.head_launches:
+                f()
+            for f in self._post:
+                f()
+
+    def run(self, grids: torch.Tensor, valid_dims=None):
+        if valid_dims is not None and all(tuple(v) == tuple(self.dims) for v in valid_dims):
+            valid_dims = None
+        vd = None if valid_dims is None else tuple(tuple(v) for v in valid_dims)
+        if self.has_head and vd != self._valid:
+            self._build_post(vd)
+            self._graph = None
+        if grids.data_ptr() != self.input.data_ptr():
+            self.input.copy_(grids, non_blocking=True)
+        if not self.eng.use_graph:
+            self._run_eager()
+            return
+        if self._graph is None:
+            self._run_eager()                      # warm-up: lazy module state, cudaFuncSetAttribute, allocator
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_eager()
+            self._graph = g
+        self._graph.replay()
+
+    def num_launches(self) -> int:
+        """Kernels per forward (conv / pack / pool launches + the post-processing pipeline), counted, not guessed."""
+        from ._lib import lib
+        before = lib().nrpn_launch_count()
+        self._run_eager()
+        return int(lib().nrpn_launch_count() - before)

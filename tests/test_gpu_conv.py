@@ -1,0 +1,149 @@
+"""GPU numerics tests for the tcgen05 implicit-GEMM convolution and the bandwidth kernels, through the C ABI.
+Reference = plain PyTorch fp32 conv3d on the same bf16-rounded operands (tests/emulate.py).  Tolerance: the
+kernel accumulates in fp32, so with fp32 output the error is accumulation-order only (2e-3 of the output scale
+for K up to 13 824); with bf16 output one extra rounding (2^-8 relative)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.emulate import emulate_conv, emulate_pack_stem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available()
+    from nerf_rpn_b200 import ops as _ops
+    return _ops
+
+
+def _diagnose(got, ref, tag):
+    err = (got - ref).abs()
+    scale = ref.abs().max().item() + 1e-12
+    msg = [f"[{tag}] max abs err {err.max().item():.4g} (scale {scale:.4g}), mean abs err {err.mean().item():.4g}"]
+    bad = err > 0.02 * scale
+    msg.append(f"  bad fraction {bad.float().mean().item():.4f}")
+    if bad.any():
+        idx = bad.nonzero()[:8].tolist()
+        msg.append(f"  first bad idx {idx}")
+        for d in range(got.dim()):
+            other = [i for i in range(got.dim()) if i != d]
+            per = bad.float().mean(dim=other)
+            msg.append(f"  bad fraction along dim {d}: {[round(v, 3) for v in per.tolist()[:40]]}")
+    return "\n".join(msg)
+
+
+def run_conv(ops, x, w, bias=None, stride=1, relu=False, res=None, out_fp32=False, levels=None):
+    from nerf_rpn_b200 import packing
+    cout = w.shape[0]
+    wp, taps = packing.pack_conv_weight(w)
+    cpad = wp.shape[1]
+    shift = packing.pad_shift(bias if bias is not None else torch.zeros(cout, device=w.device), cpad)
+    wp = wp.cuda(); shift = shift.cuda()
+    xs = [x] if levels is None else levels
+    ress = [res] if levels is None else [None] * len(levels)
+    args, outs = [], []
+    ldy = ((cout + 7) // 8) * 8
+    for xi, ri in zip(xs, ress):
+        n, X, Y, Z, cin = xi.shape
+        od = tuple((d - 1) // stride + 1 for d in (X, Y, Z))
+        y = torch.full((n, *od, ldy), float("nan"), dtype=torch.float32 if out_fp32 else torch.bfloat16, device="cuda")
+        outs.append(y)
+        a = ops.ConvLevelArgs(xi, y, n, (X, Y, Z), od, ldy, res=ri, res_dims=None if ri is None else ri.shape[1:4],
+                              ldr=0 if ri is None else ri.shape[-1])
+        args.append(a)
+    ops.conv3d_fprop(args, wp, shift, xs[0].shape[-1], ldy, taps, stride=stride, relu=relu, out_fp32=out_fp32)
+    torch.cuda.synchronize()
+    refs = []
+    for xi, ri in zip(xs, ress):
+        n, X, Y, Z, cin = xi.shape
+        od = tuple((d - 1) // stride + 1 for d in (X, Y, Z))
+        refs.append(emulate_conv(xi.float(), wp.float(), taps, shift, od, stride=stride, relu=relu, res=ri)[..., :ldy])
+    return outs, refs
+
+
+CASES = [
+    # name, dims, cin, cout, k, stride, relu, res mode, out_fp32
+    ("1x1_64_64", (8, 8, 16), 64, 64, 1, 1, False, None, True),
+    ("3x3_64_64", (8, 8, 16), 64, 64, 3, 1, False, None, True),
+    ("3x3_odd_relu", (10, 13, 9), 64, 64, 3, 1, True, None, False),
+    ("3x3_256_256", (9, 12, 17), 256, 256, 3, 1, True, None, False),
+    ("1x1_256_1024_res", (6, 9, 10), 256, 1024, 1, 1, True, "same", False),
+    ("1x1_s2_512_128", (9, 12, 11), 512, 128, 1, 2, False, None, True),
+    ("1x1_upsample_add", (13, 9, 7), 512, 256, 1, 1, False, "up", False),
+    ("pred_1x1_256_120", (7, 8, 9), 256, 120, 1, 1, False, None, True),
+]
+
+
+@pytest.mark.parametrize("name,dims,cin,cout,k,stride,relu,resmode,out_fp32", CASES)
+def test_conv_cases(ops, name, dims, cin, cout, k, stride, relu, resmode, out_fp32):
+    g = torch.Generator(device="cuda").manual_seed(hash(name) % 1000)
+    x = torch.randn((2, *dims, cin), device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn((cout, cin, k, k, k), device="cuda", generator=g) / (cin * k ** 3) ** 0.5
+    bias = torch.randn((cout,), device="cuda", generator=g)
+    res = None
+    od = tuple((d - 1) // stride + 1 for d in dims)
+    if resmode == "same":
+        res = torch.randn((2, *od, cout), device="cuda", generator=g).to(torch.bfloat16)
+    elif resmode == "up":
+        rd = tuple((d + 1) // 2 for d in od)                      # odd sizes: 13 -> 7 etc. (size-based nearest)
+        res = torch.randn((2, *rd, cout), device="cuda", generator=g).to(torch.bfloat16)
+    outs, refs = run_conv(ops, x, w, bias, stride, relu, res, out_fp32)
+    got, ref = outs[0].float(), refs[0]
+    assert not torch.isnan(got).any(), _diagnose(torch.nan_to_num(got, nan=1e9), ref, name + " (NaN = never written)")
+    tol = 2e-3 if out_fp32 else 1e-2
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= tol * scale, _diagnose(got, ref, name)
+
+
+def test_conv_multi_level_shared_weights(ops):
+    """The RPN head shape: one launch over 4 pyramid levels sharing 3^3 256->256 weights (anchor.py:206-213)."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    levels = [torch.randn((1, *d, 256), device="cuda", generator=g).to(torch.bfloat16)
+              for d in [(10, 16, 16), (5, 8, 8), (3, 4, 4), (2, 2, 2)]]
+    w = torch.randn((256, 256, 3, 3, 3), device="cuda", generator=g) / (256 * 27) ** 0.5
+    bias = torch.randn((256,), device="cuda", generator=g)
+    outs, refs = run_conv(ops, None, w, bias, 1, True, None, False, levels=levels)
+    for i, (o, r) in enumerate(zip(outs, refs)):
+        got = o.float()
+        assert not torch.isnan(got).any(), f"level {i}: unwritten outputs"
+        assert (got - r).abs().max().item() <= 1e-2 * r.abs().max().item(), _diagnose(got, r, f"level{i}")
+
+
+def test_conv_large_p2_tile_count(ops):
+    """More tiles than SMs (persistent loop, TMEM double buffering, stage ring wrap-around)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn((1, 24, 32, 40, 128), device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn((256, 128, 3, 3, 3), device="cuda", generator=g) / (128 * 27) ** 0.5
+    outs, refs = run_conv(ops, x, w, None, 1, False, None, True)
+    got, ref = outs[0], refs[0]
+    assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item(), _diagnose(got, ref, "p2like")
+
+
+def test_stem_pack_and_conv(ops):
+    from nerf_rpn_b200 import packing
+    g = torch.Generator(device="cuda").manual_seed(12)
+    for dims in [(24, 20, 28), (21, 19, 27)]:
+        x = torch.rand((1, 4, *dims), device="cuda", generator=g)
+        packed = ops.pack_stem_input(x)
+        torch.testing.assert_close(packed.float(), emulate_pack_stem(x).to(torch.bfloat16).float(), rtol=0, atol=0)
+        w = torch.randn((64, 4, 7, 7, 7), device="cuda", generator=g) * 0.05
+        wp, taps = packing.pack_stem_weight(w)
+        od = tuple((d + 1) // 2 for d in dims)
+        y = torch.empty((1, *od, 64), dtype=torch.float32, device="cuda")
+        shift = torch.zeros(64, device="cuda")
+        a = ops.ConvLevelArgs(packed, y, 1, packed.shape[1:4], od, 64)
+        ops.conv3d_fprop([a], wp.cuda(), shift, 64, 64, taps, out_fp32=True)
+        ref = F.conv3d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), stride=2, padding=3).permute(0, 2, 3, 4, 1)
+        assert (y - ref).abs().max().item() <= 2e-3 * ref.abs().max().item(), _diagnose(y, ref, "stem")
+
+
+def test_maxpool(ops):
+    g = torch.Generator(device="cuda").manual_seed(13)
+    for dims in [(12, 10, 14), (11, 9, 13)]:
+        x = torch.randn((2, *dims, 64), device="cuda", generator=g).to(torch.bfloat16)
+        got = ops.maxpool3d_k3s2(x)
+        ref = F.max_pool3d(x.float().permute(0, 4, 1, 2, 3), kernel_size=3, stride=2, padding=1).permute(0, 2, 3, 4, 1)
+        torch.testing.assert_close(got.float(), ref, rtol=0, atol=0)
