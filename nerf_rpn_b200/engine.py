@@ -156,6 +156,10 @@ class _Plan:
         L = eng.layers
         bf = dict(dtype=torch.bfloat16, device=device)
         X, Y, Z = dims
+        self._rpn_ws = None
+        self._valid = None
+        self._graph = None
+        self._post = []
         self.launches = []           # backbone stage: list of zero-arg callables
         self.head_launches = []      # head stage
         self._cur = self.launches
@@ -251,10 +255,6 @@ class _Plan:
         self.out_scores = torch.zeros((n, eng.post_n), dtype=torch.float32, device=device)
         self.out_levels = torch.zeros((n, eng.post_n), dtype=torch.float32, device=device)
         self.out_count = torch.zeros((n,), dtype=torch.int32, device=device)
-        self._rpn_ws = None
-        self._valid = None
-        self._graph = None
-        self._post = []
         self._build_post(None)
 
     def _build_post(self, valid_dims):

@@ -1,0 +1,103 @@
+"""Backbones. Mirrors nerf_rpn/model/feature_extractor.py for the hot path:
+  Bottleneck        feature_extractor.py:31-68
+  ResNet_FPN_256    feature_extractor.py:145-235   (ResNet50-3D + inline FPN; run_rpn.py:276)
+The modules own ordinary nn.Conv3d / nn.BatchNorm3d parameters, created in the reference's order so that
+torch.manual_seed(s) reproduces the reference's initial weights and state_dict keys are identical
+(conv1.weight, bn1.*, layers.{s}.{b}.conv{1,2,3}.weight, ..., smooths.{i}.*, latlayers.{i}.*).
+forward() never calls those nn modules: it runs the pre-packed tcgen05 engine (nerf_rpn_b200/engine.py).
+VGG_FPN / SwinTransformer_FPN (configs 1 and 3) are not built yet; the names exist so run_rpn.py imports resolve.
+"""
+from typing import List
+
+import torch
+from torch import nn
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv3d(inplanes, planes, kernel_size=1, stride=stride, bias=False)   # stride sits on the 1^3 conv
+        self.bn1 = nn.BatchNorm3d(planes)
+        self.conv2 = nn.Conv3d(planes, planes, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm3d(planes)
+        self.conv3 = nn.Conv3d(planes, planes * self.expansion, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm3d(planes * self.expansion)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        raise RuntimeError("nerf_rpn_b200.Bottleneck is a parameter container; it is executed by ResNet_FPN_256's "
+                           "fused B200 engine, not called on its own")
+
+
+class ResNet_FPN_256(nn.Module):
+    """ResNet-FPN backbone, same constructor / attributes as the reference (feature_extractor.py:159-194)."""
+
+    def __init__(self, block, layers, input_dim=4, is_max_pool=False):
+        super().__init__()
+        if input_dim != 4 or not is_max_pool or block is not Bottleneck:
+            raise NotImplementedError("the B200 engine implements the configuration run_rpn.py builds: "
+                                      "ResNet_FPN_256(Bottleneck, [3,4,6,3], input_dim=4, is_max_pool=True)")
+        self.in_planes = 64
+        self.out_channels = 256
+        self.conv1 = nn.Conv3d(input_dim, self.in_planes, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm3d(self.in_planes)
+        self.layers = nn.ModuleList()
+        self.start_deep = self.in_planes
+        self.is_max_pool = is_max_pool
+        for i in range(len(layers)):
+            self.layers.append(self._make_layer(block, self.start_deep * (2 ** i), layers[i], stride=1 if i == 0 else 2))
+        self.smooths = nn.ModuleList()
+        for i in range(len(layers) - 1):
+            self.smooths.append(nn.Conv3d(256, 256, kernel_size=3, stride=1, padding=1))
+        self.latlayers = nn.ModuleList()
+        for i in range(len(layers) - 1, -1, -1):
+            self.latlayers.append(nn.Conv3d(block.expansion * self.start_deep * (2 ** i), self.out_channels,
+                                            kernel_size=1, stride=1, padding=0))
+        for m in self.modules():             # same init walk as the reference (feature_extractor.py:188-194)
+            if isinstance(m, nn.Conv3d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm3d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        self._engine = None
+
+    def _make_layer(self, block, planes, blocks, stride=1):
+        downsample = None
+        if stride != 1 or self.in_planes != planes * block.expansion:
+            downsample = nn.Sequential(
+                nn.Conv3d(self.in_planes, planes * block.expansion, kernel_size=1, stride=stride, bias=False),
+                nn.BatchNorm3d(planes * block.expansion),
+            )
+        layers = [block(self.in_planes, planes, stride, downsample)]
+        self.in_planes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.in_planes, planes))
+        return nn.Sequential(*layers)
+
+    def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """x: (N,4,W,L,H) fp32 CUDA -> [P2,P3,P4,P5], each (N,256,w,l,h) fp32 (channels_last_3d strides)."""
+        from ..engine import RPNInferenceEngine
+        if self._engine is None:
+            self._engine = RPNInferenceEngine(self)
+        plan = self._engine.forward_device(x.contiguous())
+        return [f.permute(0, 4, 1, 2, 3).float() for f in plan.features]
+
+
+def _not_built(name):
+    class _Missing(nn.Module):
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"nerf_rpn_b200: backbone {name} is not implemented yet (round 1 covers "
+                                      "ResNet_FPN_256; see DESIGN.md 'what comes next')")
+    _Missing.__name__ = name
+    return _Missing
+
+
+VGG_FPN = _not_built("VGG_FPN")
+SwinTransformer_FPN = _not_built("SwinTransformer_FPN")
+ResNet_FPN_64 = _not_built("ResNet_FPN_64")
+ResNetSimplified_64 = _not_built("ResNetSimplified_64")
+ResNetSimplified_256 = _not_built("ResNetSimplified_256")

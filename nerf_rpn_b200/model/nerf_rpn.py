@@ -1,0 +1,93 @@
+"""NeRFRegionProposalNetwork. Mirrors nerf_rpn/model/nerf_rpn.py:22-217: same constructor keywords, same
+forward(meshes, targets=None, objectness_output_paths=None) -> ([features, proposals, level_index], losses, scores).
+"""
+from typing import List, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .anchor import AnchorGenerator3D, RPNHead
+from .rpn import RegionProposalNetwork
+
+
+def _default_anchorgen():
+    anchor_sizes = ((8,), (16,), (32,), (64,),)
+    aspect_ratios = (((1., 1., 1.), (1., 1., 2.), (1., 2., 2.), (1., 1., 3.), (1., 3., 3.)),) * len(anchor_sizes)
+    return AnchorGenerator3D(anchor_sizes, aspect_ratios)
+
+
+class NeRFRegionProposalNetwork(nn.Module):
+    def __init__(self, backbone, rpn_anchor_generator=None, rpn_head=None, rpn_pre_nms_top_n_train=2000,
+                 rpn_pre_nms_top_n_test=1000, rpn_post_nms_top_n_train=2000, rpn_post_nms_top_n_test=1000,
+                 rpn_nms_thresh=0.7, rpn_fg_iou_thresh=0.7, rpn_bg_iou_thresh=0.3, rpn_batch_size_per_image=256,
+                 rpn_positive_fraction=0.5, rpn_score_thresh=0.0, iou_batch_size=16, rotated_bbox=False,
+                 reg_loss_type="smooth_l1", **kwargs):
+        if not hasattr(backbone, "out_channels"):
+            raise ValueError("backbone should contain an attribute out_channels specifying the number of output "
+                             "channels (assumed to be the same for all the levels)")
+        if not isinstance(rpn_anchor_generator, (AnchorGenerator3D, type(None))):
+            raise TypeError(f"rpn_anchor_generator should be of type AnchorGenerator or None instead of {type(rpn_anchor_generator)}")
+        out_channels = backbone.out_channels
+        if rpn_anchor_generator is None:
+            rpn_anchor_generator = _default_anchorgen()
+        if rpn_head is None:
+            rpn_head = RPNHead(out_channels, rpn_anchor_generator.num_anchors_per_location()[0], rotated_bbox)
+        rpn = RegionProposalNetwork(
+            rpn_anchor_generator, rpn_head, rpn_fg_iou_thresh, rpn_bg_iou_thresh, rpn_batch_size_per_image,
+            rpn_positive_fraction, dict(training=rpn_pre_nms_top_n_train, testing=rpn_pre_nms_top_n_test),
+            dict(training=rpn_post_nms_top_n_train, testing=rpn_post_nms_top_n_test), rpn_nms_thresh,
+            score_thresh=rpn_score_thresh, iou_batch_size=iou_batch_size, rotated_bbox=rotated_bbox,
+            reg_loss_type=reg_loss_type)
+        super().__init__()
+        self.backbone = backbone
+        self.rpn = rpn
+        self._engine = None
+        self._engine_key = None
+
+    # nerf_rpn.py:129-146
+    def transform(self, meshes, targets=None):
+        if len(meshes) > 1:
+            shapes = [mesh.shape for mesh in meshes]
+            target_shape = np.max(shapes, axis=0)
+            for i, mesh in enumerate(meshes):
+                meshes[i] = F.pad(mesh, (0, target_shape[-1] - mesh.shape[-1], 0, target_shape[-2] - mesh.shape[-2],
+                                         0, target_shape[-3] - mesh.shape[-3]), mode="constant", value=0)
+        return meshes, targets
+
+    def engine(self):
+        from ..engine import RPNInferenceEngine
+        r = self.rpn
+        key = (r._pre_nms_top_n["testing"], r._post_nms_top_n["testing"], r.nms_thresh, r.score_thresh, r.rotate)
+        if self._engine is None or key != self._engine_key:
+            ag = r.anchor_generator
+            self._engine = RPNInferenceEngine(
+                self.backbone, r.head, ag.cell_anchors_np(), ag.num_anchors_per_location()[0], r.rotate,
+                r._pre_nms_top_n["testing"], r._post_nms_top_n["testing"], r.nms_thresh, r.score_thresh, r.min_size)
+            self._engine_key = key
+        return self._engine
+
+    def forward(self, meshes, targets=None, objectness_output_paths=None):
+        if self.training:
+            raise NotImplementedError("nerf_rpn_b200: training-mode forward is not implemented by the B200 engine yet "
+                                      "(round 1 = inference path); use .eval()")
+        if objectness_output_paths is not None:
+            raise NotImplementedError("nerf_rpn_b200: --output_voxel_scores export (rpn.py:538-549) is not implemented")
+        original_mesh_sizes: List[Tuple[int, int, int]] = []
+        for mesh in meshes:
+            val = mesh.shape[-3:]
+            torch._assert(len(val) == 3, f"expecting the last three dimensions of the Tensor to be W, H and D instead got {mesh.shape[-3:]}")
+            original_mesh_sizes.append((val[0], val[1], val[2]))
+        meshes, targets = self.transform(meshes, targets)
+        mesh_tensors = meshes[0].unsqueeze(0) if len(meshes) == 1 else torch.stack(meshes, dim=0)
+        if not mesh_tensors.is_contiguous():
+            mesh_tensors = mesh_tensors.contiguous()
+        valid = original_mesh_sizes if len(meshes) > 1 else None     # padding masks only when batch > 1 (rpn.py:501)
+        plan = self.engine().forward_device(mesh_tensors, valid)
+        counts = plan.out_count.tolist()                              # the one host sync: data-dependent output sizes
+        features = [f.permute(0, 4, 1, 2, 3).float() for f in plan.features]
+        proposals = [plan.out_boxes[i, :k].clone() for i, k in enumerate(counts)]
+        level_index = [plan.out_levels[i, :k].clone() for i, k in enumerate(counts)]
+        scores = [plan.out_scores[i, :k].clone() for i, k in enumerate(counts)]
+        return [features, proposals, level_index], {}, scores

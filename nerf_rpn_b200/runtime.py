@@ -1,0 +1,83 @@
+"""Scene streaming runtime: host (pinned) RGB-sigma grids -> proposals, with the host->device copy of scene i+1
+overlapped with the compute of scene i on a second CUDA stream, and the small device->host result copy issued
+asynchronously.  This is the end-to-end entry point bench.py times (`e2e`): what run_rpn.py's eval loop does per
+batch (run_rpn.py:470-517: .cuda(), model(...), .cpu()), minus its per-iteration synchronisations.
+
+Scenes shard across ranks by index (rank r takes scenes r, r+world, ...): inference needs no collective
+(SURVEY.md section 8e).
+"""
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+
+
+class ScenePipeline:
+    def __init__(self, model, dims: Tuple[int, int, int], device=None):
+        """model: nerf_rpn_b200.model.nerf_rpn.NeRFRegionProposalNetwork in eval mode; dims: (W, L, H) of every scene."""
+        self.model = model
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.dims = tuple(dims)
+        self.eng = model.engine()
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        # two device staging buffers; the engine's graph reads its own static input, filled by a D2D copy
+        self.stage = [torch.empty((1, 4, *self.dims), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        k = self.eng.post_n
+        bd = 7 if self.eng.rotated else 6
+        self.h_boxes = torch.empty((2, k, bd), dtype=torch.float32).pin_memory()
+        self.h_scores = torch.empty((2, k), dtype=torch.float32).pin_memory()
+        self.h_levels = torch.empty((2, k), dtype=torch.float32).pin_memory()
+        self.h_count = torch.empty((2, 1), dtype=torch.int32).pin_memory()
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.h2d_bytes_per_scene = 4 * self.dims[0] * self.dims[1] * self.dims[2] * 4
+        self.d2h_bytes_per_scene = (k * bd + 2 * k + 1) * 4
+
+    def _prefetch(self, slot: int, host_grid: torch.Tensor):
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[slot])
+            self.stage[slot][0].copy_(host_grid, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+
+    def run(self, host_grids: Iterable[torch.Tensor], collect: bool = True):
+        """host_grids: iterable of pinned fp32 (4,W,L,H) tensors. Returns a list of (boxes, scores, levels) CPU tensors
+        (or only the number of scenes processed when collect=False)."""
+        cur = torch.cuda.current_stream(self.device)
+        it = iter(host_grids)
+        nxt = next(it, None)
+        if nxt is None:
+            return []
+        for e in self.consumed:
+            e.record(cur)
+        self._prefetch(0, nxt)
+        results: List = []
+        pending: Optional[int] = None
+        i = 0
+        while nxt is not None:
+            slot = i & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                self._prefetch(slot ^ 1, nxt)
+            cur.wait_event(self.ready[slot])
+            plan = self.eng.forward_device(self.stage[slot])
+            self.consumed[slot].record(cur)
+            # results of the previous scene were copied out while this one was being enqueued
+            if pending is not None and collect:
+                results.append(self._collect(pending))
+            self.h_boxes[slot].copy_(plan.out_boxes[0], non_blocking=True)
+            self.h_scores[slot].copy_(plan.out_scores[0], non_blocking=True)
+            self.h_levels[slot].copy_(plan.out_levels[0], non_blocking=True)
+            self.h_count[slot].copy_(plan.out_count, non_blocking=True)
+            self.done[slot].record(cur)
+            pending = slot
+            i += 1
+        if pending is not None and collect:
+            results.append(self._collect(pending))
+        else:
+            self.done[(i - 1) & 1].synchronize()
+        return results if collect else i
+
+    def _collect(self, slot: int):
+        self.done[slot].synchronize()
+        k = int(self.h_count[slot, 0])
+        return self.h_boxes[slot, :k].clone(), self.h_scores[slot, :k].clone(), self.h_levels[slot, :k].clone()

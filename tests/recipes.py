@@ -1,0 +1,35 @@
+"""Shared model-construction recipe (TEST helper): rebuilds, from seeds only, exactly the weights that
+tools/make_golden.py gave the reference when it produced tests/golden/rpn_small_*.npz."""
+import numpy as np
+import torch
+
+ANCHOR_SIZES = ((8,), (16,), (32,), (64,),)
+ASPECT = (((1., 1., 1.), (1., 1., 2.), (1., 2., 2.), (1., 1., 3.), (1., 3., 3.)),) * 4
+
+
+def build_small_model(ns, rotated, golden):
+    """ns: namespace providing ResNet_FPN_256, Bottleneck, AnchorGenerator3D, RPNHead (reference or ours)."""
+    torch.manual_seed(0)
+    backbone = ns.ResNet_FPN_256(ns.Bottleneck, [3, 4, 6, 3], input_dim=4, is_max_pool=True)
+    ag = ns.AnchorGenerator3D(ANCHOR_SIZES, ASPECT)
+    head = ns.RPNHead(256, ag.num_anchors_per_location()[0], 4, rotate=rotated)
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        head.cls_logits.weight.copy_(torch.randn(head.cls_logits.weight.shape, generator=g) * 0.2)
+        head.bbox_pred.weight.copy_(torch.randn(head.bbox_pred.weight.shape, generator=g) * 0.05)
+        for m in backbone.modules():
+            if isinstance(m, torch.nn.BatchNorm3d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.5 + 0.75)
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+        # the generator calibrated both predictors on the reference's own forward; take the stored result
+        head.cls_logits.weight.copy_(torch.from_numpy(golden["cls_w"]).view_as(head.cls_logits.weight))
+        head.bbox_pred.weight.copy_(torch.from_numpy(golden["bbox_w"]).view_as(head.bbox_pred.weight))
+    assert abs(backbone.conv1.weight.double().sum().item() - float(golden["conv1_sum"])) < 1e-9, "seeded weights differ"
+    assert abs(head.conv[0].weight.double().sum().item() - float(golden["head_sum"])) < 1e-9, "seeded head weights differ"
+    return backbone, ag, head
+
+
+def golden_input(golden):
+    return torch.from_numpy(golden["grid"]).permute(3, 0, 1, 2).contiguous()       # (4,W,L,H) like datasets.py:55-57

@@ -1,0 +1,143 @@
+"""GPU end-to-end parity: NeRFRegionProposalNetwork (our module mirror -> fused engine -> CUDA kernels) against
+(a) the reference's golden outputs on the same seeded weights/input and (b) the oracle.
+
+Tolerances (stated per north_star, see DESIGN.md "precision"):
+  - feature maps / logits: norm-wise relative error <= 2e-2.  The engine stores activations in bf16 (8-bit mantissa,
+    BASELINE config 2 dtype), so the 1e-3 target of the fp32 reference is not reachable element-wise; measured
+    values are printed.
+  - post-processing: bit-identical to the oracle when fed the SAME head outputs (proposal sets, order, scores).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import box as obox
+from oracle import rpn_post as rp
+from tests import recipes
+
+pytestmark = pytest.mark.gpu
+
+
+class NS:
+    pass
+
+
+def _ns():
+    from nerf_rpn_b200.model import anchor, feature_extractor
+    NS.ResNet_FPN_256 = feature_extractor.ResNet_FPN_256
+    NS.Bottleneck = feature_extractor.Bottleneck
+    NS.AnchorGenerator3D = anchor.AnchorGenerator3D
+    NS.RPNHead = anchor.RPNHead
+    return NS
+
+
+def build(rot, g):
+    from nerf_rpn_b200.model.nerf_rpn import NeRFRegionProposalNetwork
+    backbone, ag, head = recipes.build_small_model(_ns(), rot, g)
+    model = NeRFRegionProposalNetwork(backbone, ag, head, rpn_pre_nms_top_n_test=2500, rpn_post_nms_top_n_test=2500,
+                                      rpn_nms_thresh=0.3, rpn_fg_iou_thresh=0.35, rpn_bg_iou_thresh=0.2,
+                                      rpn_score_thresh=0.0, rotated_bbox=rot)
+    return model.cuda().eval(), ag
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def oracle_post_from_engine(plan, eng, scene=0):
+    code = eng.code
+    logits = [p[scene].reshape(-1, 128)[:, :13].reshape(-1).cpu().numpy() for p in plan.pred]
+    deltas = [p[scene].reshape(-1, 128)[:, 13:13 + 13 * code].reshape(-1, code).cpu().numpy() for p in plan.pred]
+    return rp.rpn_proposals(logits, deltas, plan.feat_dims, plan.strides, eng.cells, plan.dims, eng.rotated,
+                            eng.pre_n, eng.post_n, eng.nms_thresh, eng.score_thresh)
+
+
+@pytest.mark.parametrize("name,rot", [("rpn_small_aabb", False), ("rpn_small_obb", True)])
+def test_small_scene_vs_reference_golden(golden_dir, name, rot):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    model, ag = build(rot, g)
+    x = recipes.golden_input(g).cuda()
+    with torch.no_grad():
+        (features, proposals, level_index), losses, scores = model([x])
+    assert losses == {} and len(proposals) == 1
+    # (a) feature maps, norm-wise
+    for i, f in enumerate(features):
+        assert tuple(f.shape[1:]) == g[f"feat{i}"].shape and f.dtype == torch.float32
+        ref = torch.from_numpy(g[f"feat{i}"].astype(np.float32)).cuda()
+        rel = ((f[0] - ref).norm() / ref.norm()).item()
+        print(f"{name}: feature P{i + 2} norm-wise rel err {rel:.3e}")
+        assert rel < 2e-2
+    plan = model.engine()._plans[next(iter(model.engine()._plans))]
+    for i, p in enumerate(plan.pred):
+        lg = p[0][..., :13].permute(3, 0, 1, 2).cpu()
+        ref = torch.from_numpy(g[f"logits{i}"])
+        rel = ((lg - ref).norm() / ref.norm()).item()
+        print(f"{name}: logits level {i} norm-wise rel err {rel:.3e}")
+        assert rel < 3e-2
+    # (b) post-processing is bit-identical to the oracle on the engine's own head outputs
+    ob, os_, ol = oracle_post_from_engine(plan, model.engine())
+    assert proposals[0].shape[0] == ob.shape[0]
+    np.testing.assert_array_equal(bits(proposals[0].cpu().numpy()), bits(ob))
+    np.testing.assert_array_equal(bits(scores[0].cpu().numpy()), bits(os_))
+    np.testing.assert_array_equal(level_index[0].cpu().numpy(), ol)
+    # (c) proposals agree with the reference's (bf16 perturbs logits, so compare by overlap, not by index)
+    refp, refs = g["proposals"], g["scores"]
+    ours = proposals[0].cpu().numpy()
+    top = np.argsort(-refs, kind="stable")[:100]
+    iou = obox.iou_matrix(refp[top], ours) if ours.shape[0] else np.zeros((len(top), 0), np.float32)
+    hit = (iou.max(axis=1) >= 0.7).mean() if ours.shape[0] else 0.0
+    print(f"{name}: {ours.shape[0]} proposals (reference {refp.shape[0]}); top-100 reference proposals matched at IoU>=0.7: {hit:.2f}")
+    assert hit >= 0.85
+    assert abs(ours.shape[0] - refp.shape[0]) <= 0.15 * refp.shape[0] + 10
+
+
+def test_batch_of_two_padded_scenes(golden_dir):
+    """batch > 1 with different extents: zero padding to the batch max + -inf objectness in padded voxels
+    (nerf_rpn.py:129-146, anchor.py:124-152, rpn.py:321-322); the post-processing must equal the oracle's."""
+    g = np.load(os.path.join(golden_dir, "rpn_small_aabb.npz"))
+    model, ag = build(False, g)
+    x0 = recipes.golden_input(g).cuda()
+    x1 = x0[:, :24, :40, :32].contiguous()
+    with torch.no_grad():
+        (features, proposals, level_index), _, scores = model([x0, x1])
+    eng = model.engine()
+    plan = [p for k, p in eng._plans.items() if k[0] == 2][0]
+    code = eng.code
+    for i, valid in enumerate([(32, 48, 40), (24, 40, 32)]):
+        logits = [p[i].reshape(-1, 128)[:, :13].reshape(-1).cpu().numpy() for p in plan.pred]
+        deltas = [p[i].reshape(-1, 128)[:, 13:13 + 13 * code].reshape(-1, code).cpu().numpy() for p in plan.pred]
+        ob, os_, ol = rp.rpn_proposals(logits, deltas, plan.feat_dims, plan.strides, eng.cells, plan.dims, False,
+                                       eng.pre_n, eng.post_n, eng.nms_thresh, eng.score_thresh, valid=valid)
+        np.testing.assert_array_equal(bits(proposals[i].cpu().numpy()), bits(ob))
+        np.testing.assert_array_equal(bits(scores[i].cpu().numpy()), bits(os_))
+
+
+def test_full_size_scene_runs_and_matches_oracle_post():
+    """BASELINE config 2 size: 160x256x256x4 grid, ResNet50-FPN + anchor head, random-init (seed 0) weights."""
+    from nerf_rpn_b200.model.nerf_rpn import NeRFRegionProposalNetwork
+    ns = _ns()
+    torch.manual_seed(0)
+    backbone = ns.ResNet_FPN_256(ns.Bottleneck, [3, 4, 6, 3], input_dim=4, is_max_pool=True)
+    ag = ns.AnchorGenerator3D(recipes.ANCHOR_SIZES, recipes.ASPECT)
+    head = ns.RPNHead(256, 13, 4, rotate=False)
+    model = NeRFRegionProposalNetwork(backbone, ag, head, rpn_pre_nms_top_n_test=2500, rpn_post_nms_top_n_test=2500,
+                                      rpn_nms_thresh=0.3, rpn_score_thresh=0.0).cuda().eval()
+    gi = torch.Generator().manual_seed(1000)
+    x = torch.rand(160, 256, 256, 4, generator=gi).permute(3, 0, 1, 2).contiguous().cuda()
+    with torch.no_grad():
+        (features, proposals, level_index), _, scores = model([x])
+        (features2, proposals2, _), _, scores2 = model([x])            # graph replay is deterministic
+    assert [tuple(f.shape) for f in features] == [(1, 256, 40, 64, 64), (1, 256, 20, 32, 32), (1, 256, 10, 16, 16), (1, 256, 5, 8, 8)]
+    assert all(torch.isfinite(f).all() for f in features)
+    assert torch.equal(proposals[0], proposals2[0]) and torch.equal(scores[0], scores2[0])
+    eng = model.engine()
+    plan = eng._plans[next(iter(eng._plans))]
+    ob, os_, ol = oracle_post_from_engine(plan, eng)
+    np.testing.assert_array_equal(bits(proposals[0].cpu().numpy()), bits(ob))
+    np.testing.assert_array_equal(bits(scores[0].cpu().numpy()), bits(os_))
+    s = scores[0].cpu().numpy()
+    assert s.shape[0] > 0 and np.all(s[:-1] >= s[1:])
+    print(f"full-size: {s.shape[0]} proposals, {plan.algorithmic_flops / 1e12:.3f} TFLOP/scene algorithmic")
+    assert abs(plan.algorithmic_flops / 1e12 - 3.913) < 0.05

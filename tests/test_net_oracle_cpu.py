@@ -1,0 +1,38 @@
+"""CPU: oracle/net.py (functional fp32 restatement of ResNet50-FPN + RPN head) against the reference's golden
+feature maps / logits / proposals, using weights rebuilt from seeds through OUR module mirror (which also checks
+that nerf_rpn_b200.model reproduces the reference's parameter order, init and state_dict keys)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from nerf_rpn_b200.model import anchor, feature_extractor
+from oracle import net as onet
+from tests import recipes
+
+
+class NS:
+    ResNet_FPN_256 = feature_extractor.ResNet_FPN_256
+    Bottleneck = feature_extractor.Bottleneck
+    AnchorGenerator3D = anchor.AnchorGenerator3D
+    RPNHead = anchor.RPNHead
+
+
+@pytest.mark.parametrize("name,rot", [("rpn_small_aabb", False), ("rpn_small_obb", True)])
+def test_net_oracle_matches_reference(golden_dir, name, rot):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    backbone, ag, head = recipes.build_small_model(NS, rot, g)
+    assert len(backbone.state_dict()) == 332 and len(head.state_dict()) == 12
+    x = recipes.golden_input(g)[None]
+    feats, (b, s, lv) = onet.full_forward(backbone.state_dict(), head.state_dict(), x, ag.cell_anchors_np(), rot)
+    for i, f in enumerate(feats):
+        ref = torch.from_numpy(g[f"feat{i}"].astype(np.float32))
+        rel = (f[0] - ref).norm() / ref.norm()
+        assert rel < 1e-3, f"feature level {i}: rel {rel}"                               # golden stored in fp16
+    logits, deltas = onet.head_forward(head.state_dict(), feats)
+    for i in range(4):
+        np.testing.assert_allclose(logits[i][0].numpy(), g[f"logits{i}"], rtol=1e-3, atol=2e-3)
+    assert b.shape == g["proposals"].shape
+    np.testing.assert_allclose(b, g["proposals"], rtol=1e-3, atol=1e-2)
+    np.testing.assert_array_equal(lv, g["level_index"])
