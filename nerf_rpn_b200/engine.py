@@ -26,12 +26,17 @@ class _Conv:
     def __init__(self, weight, bias=None, bn=None, stride=1, relu=False, stem=False, cout_pad_to=None, device="cuda"):
         scale = shift = None
         if bn is not None:
-            scale, shift = packing.fold_bn(bn)
+            scale, shift = (t.cpu() for t in packing.fold_bn(bn))
             if bias is not None:
-                shift = shift + bias.detach().float() * scale
+                shift = shift + bias.detach().float().cpu() * scale
         elif bias is not None:
-            shift = bias.detach().float()
+            shift = bias.detach().float().cpu()
         cout = weight.shape[0]
+        weight = weight.detach().float().cpu()          # packing is host-side work (once per checkpoint), not GPU launches
+        if scale is not None:
+            scale = scale.cpu()
+        if shift is not None:
+            shift = shift.cpu()
         if stem:
             wp, taps = packing.pack_stem_weight(weight, scale)
         else:
@@ -160,6 +165,7 @@ class _Plan:
         self._valid = None
         self._graph = None
         self._post = []
+        self.names = {}              # id(callable) -> (layer name, algorithmic flops of the launch)
         self.launches = []           # backbone stage: list of zero-arg callables
         self.head_launches = []      # head stage
         self._cur = self.launches
@@ -168,7 +174,7 @@ class _Plan:
         def buf(d, c, dtype=torch.bfloat16):
             return torch.empty((n, *d, c), dtype=dtype, device=device)
 
-        def conv(layer: _Conv, xs, ys, in_dims, out_dims, res=None, res_dims=None, out_fp32=False, real=None):
+        def conv(layer: _Conv, xs, ys, in_dims, out_dims, res=None, res_dims=None, out_fp32=False, real=None, name="conv"):
             args = []
             for i in range(len(xs)):
                 r = None if res is None else res[i]
@@ -176,21 +182,27 @@ class _Plan:
                                               res_dims=None if r is None else res_dims[i], ldr=0 if r is None else r.shape[-1]))
             self._cur.append(lambda a=args, l=layer, f=out_fp32: ops.conv3d_fprop(
                 a, l.w, l.shift, l.cin, l.cout, l.taps, stride=l.stride, relu=l.relu, out_fp32=f))
+            fl = 0.0
             for od in out_dims:
                 vox = n * od[0] * od[1] * od[2]
                 rc, rt, rco = real if real else (layer.cin, len(layer.taps), layer.cout)
-                self.algorithmic_flops += 2.0 * vox * rco * rc * rt / n
+                fl += 2.0 * vox * rco * rc * rt
+            self.algorithmic_flops += fl / n
+            self.names[id(self._cur[-1])] = (f"{name} {layer.cin}->{layer.cout} taps={len(layer.taps)} s={layer.stride} "
+                                             f"out={'+'.join('x'.join(map(str, d)) for d in out_dims)}", fl)
 
         # static input + stem
         self.input = torch.empty((n, 4, X, Y, Z), dtype=torch.float32, device=device)
         d1 = _down(dims)
         self.packed = torch.empty((n, d1[0], d1[1], d1[2] + 1, 64), **bf)
         self.launches.append(lambda: ops.pack_stem_input(self.input, self.packed))
+        self.names[id(self.launches[-1])] = ("pack_stem_input", 0.0)
         c1 = buf(d1, 64)
-        conv(L["stem"], [self.packed], [c1], [(d1[0], d1[1], d1[2] + 1)], [d1], real=(4, 343, 64))
+        conv(L["stem"], [self.packed], [c1], [(d1[0], d1[1], d1[2] + 1)], [d1], real=(4, 343, 64), name="stem7x7x7s2(s2d)")
         d2 = _down(d1)
         c1p = buf(d2, 64)
         self.launches.append(lambda: ops.maxpool3d_k3s2(c1, c1p))
+        self.names[id(self.launches[-1])] = ("maxpool3d_k3s2", 0.0)
 
         # bottom-up
         x, xd = c1p, d2
@@ -202,34 +214,34 @@ class _Plan:
                 s = e["stride"]
                 od = _down(xd) if s == 2 else xd
                 a = buf(od, e["c1"].cout)
-                conv(e["c1"], [x], [a], [xd], [od])
+                conv(e["c1"], [x], [a], [xd], [od], name=f"L{si}.c1")
                 b = buf(od, e["c2"].cout)
-                conv(e["c2"], [a], [b], [od], [od])
+                conv(e["c2"], [a], [b], [od], [od], name=f"L{si}.c2")
                 if e["ds"] is not None:
                     r = buf(od, e["ds"].cout)
-                    conv(e["ds"], [x], [r], [xd], [od])
+                    conv(e["ds"], [x], [r], [xd], [od], name=f"L{si}.ds")
                 else:
                     r = x
                 o = buf(od, e["c3"].cout)
-                conv(e["c3"], [b], [o], [od], [od], res=[r], res_dims=[od])
+                conv(e["c3"], [b], [o], [od], [od], res=[r], res_dims=[od], name=f"L{si}.c3+res")
                 x, xd = o, od
             c_out.append((x, xd))
 
         # top-down (feature_extractor.py:224-235): p5 = lat0(c5); p_i = up(p_{i+1}) + lat(c_i); smooth all but p5
         (c5, d5) = c_out[-1]
         p = buf(d5, 256)
-        conv(L["lat"][0], [c5], [p], [d5], [d5])
+        conv(L["lat"][0], [c5], [p], [d5], [d5], name="lat0")
         p_out = [(p, d5)]
         for i in range(1, len(L["lat"])):
             (c, cd) = c_out[-1 - i]
             q = buf(cd, 256)
-            conv(L["lat"][i], [c], [q], [cd], [cd], res=[p_out[-1][0]], res_dims=[p_out[-1][1]])
+            conv(L["lat"][i], [c], [q], [cd], [cd], res=[p_out[-1][0]], res_dims=[p_out[-1][1]], name=f"lat{i}+up")
             p_out.append((q, cd))
         feats = [p_out[0]]
         for i, sm in enumerate(L["smooth"]):
             (q, qd) = p_out[i + 1]
             sq = buf(qd, 256)
-            conv(sm, [q], [sq], [qd], [qd])
+            conv(sm, [q], [sq], [qd], [qd], name=f"smooth{i}")
             feats.append((sq, qd))
         feats.reverse()                                   # [P2, P3, P4, P5]
         self.features = [f for f, _ in feats]
@@ -243,11 +255,11 @@ class _Plan:
         cur = self.features
         for layer in L["head"]:
             nxt = [buf(d, 256) for d in self.feat_dims]
-            conv(layer, cur, nxt, self.feat_dims, self.feat_dims)
+            conv(layer, cur, nxt, self.feat_dims, self.feat_dims, name="head3x3x3")
             cur = nxt
         self.pred = [buf(d, 128, torch.float32) for d in self.feat_dims]
         conv(L["pred"], cur, self.pred, self.feat_dims, self.feat_dims, out_fp32=True,
-             real=(256, 1, eng.A * (1 + eng.code)))
+             real=(256, 1, eng.A * (1 + eng.code)), name="pred(cls|bbox)")
 
         # proposals
         self.strides = [tuple(dims[k] // d[k] for k in range(3)) for d in self.feat_dims]

@@ -81,3 +81,35 @@ class ScenePipeline:
         self.done[slot].synchronize()
         k = int(self.h_count[slot, 0])
         return self.h_boxes[slot, :k].clone(), self.h_scores[slot, :k].clone(), self.h_levels[slot, :k].clone()
+
+
+# ---------------------------------------------------------------------------------------------- multi-GPU
+def shard_indices(n_scenes: int, rank: int, world: int) -> List[int]:
+    """Scene i is processed by rank i % world (the reference shards the same way through DistributedSampler with
+    batch_size // world_size scenes per rank, run_rpn.py:336-339). No data-path collective is needed at inference."""
+    return list(range(rank, n_scenes, world))
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Elapsed time of a multi-rank job = the slowest rank (bench.py timing rule)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_to_rank0(local: dict):
+    """Collect {scene index: result} dicts on rank 0 (the reference evaluates on rank 0 only, run_rpn.py:359-363)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return dict(local)
+    out = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(local, out, dst=0)
+    if dist.get_rank() != 0:
+        return None
+    merged = {}
+    for d in out:
+        merged.update(d)
+    return merged
