@@ -215,7 +215,7 @@ def run_b200(args):
 
     # ---- device-resident throughput
     with torch.no_grad():
-        for i in range(W):
+        for i in range(max(W, 4)):                            # >= 4: both buffer parities warmed and captured
             plan = eng.forward_device(dev[i % n_pool])
         barrier()
         sampler = ClockSampler(local)
@@ -225,6 +225,7 @@ def run_b200(args):
         e0.record()
         for i in range(K):
             plan = eng.forward_device(dev[i % n_pool])
+        torch.cuda.current_stream().wait_event(plan.done)     # the last scene's post-processing (side stream)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -265,6 +266,7 @@ def run_b200(args):
         value = world * K / (ms * 1e-3)
         cores = os.cpu_count() or 1
         torch.cuda.empty_cache()
+        cpu_port_run(16, cores)                            # warm the CPU libraries (oneDNN JIT, thread pool) on a thin slab
         cpu_t = cpu_port_run(160, cores)[0]
         out = {"metric": "scenes/sec", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -279,7 +281,7 @@ def run_b200(args):
                "gpu_launches": launches_per_step * K,
                "roofline": roofline,
                "cpu_baseline": {"value": 1.0 / cpu_t, "unit": "scenes/s", "cores": cores, "kind": "port",
-                                "sample": "1 scene 160x256x256 (oracle/net.py fp32 CPU port of the reference, single timed run)"}}
+                                "sample": "1 scene 160x256x256 (oracle/net.py fp32 CPU port of the reference; one timed run after a thin warm-up slab)"}}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

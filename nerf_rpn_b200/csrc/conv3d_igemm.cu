@@ -27,7 +27,6 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kABytes = kBlockM * kBlockK * 2;       // 16 KB
-constexpr int kSmemBudget = 200 * 1024;
 
 struct ConvLevelDev {
     int n, xo, yo, zo;
@@ -59,8 +58,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(192, 1) conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvDev P) {
+template <int BLOCK_N, int STAGES, int MIN_BLOCKS>
+__global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvDev P) {
     constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;
@@ -180,6 +179,17 @@ __global__ void __launch_bounds__(192, 1) conv3d_igemm_kernel(const __grid_const
             }
             const int n0 = n_tile * BLOCK_N;
 
+            // residual rows are fetched one 32-channel chunk ahead (4 x 16 B per thread in flight) so that the DRAM
+            // latency of chunk c+1 hides behind the TMEM load + math + stores of chunk c
+            uint4 rv[4];
+            auto load_res = [&](int c, uint4 (&dst)[4]) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int ch = n0 + c * 32 + g * 8;
+                    dst[g] = (rrow != nullptr && ch < P.cout) ? __ldg(reinterpret_cast<const uint4*>(rrow + ch)) : make_uint4(0u, 0u, 0u, 0u);
+                }
+            };
+            load_res(0, rv);
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
@@ -187,6 +197,8 @@ __global__ void __launch_bounds__(192, 1) conv3d_igemm_kernel(const __grid_const
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(t_base + (uint32_t)(c * 32), r);
+                uint4 rn[4];
+                if (c + 1 < BLOCK_N / 32) load_res(c + 1, rn);
                 ptx::tmem_ld_wait();
                 const int ch0 = n0 + c * 32;
                 if (valid && ch0 < P.cout) {
@@ -202,8 +214,7 @@ __global__ void __launch_bounds__(192, 1) conv3d_igemm_kernel(const __grid_const
                         v[4] = __uint_as_float(r[g * 8 + 4]) + s1.x; v[5] = __uint_as_float(r[g * 8 + 5]) + s1.y;
                         v[6] = __uint_as_float(r[g * 8 + 6]) + s1.z; v[7] = __uint_as_float(r[g * 8 + 7]) + s1.w;
                         if (rrow != nullptr) {
-                            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rrow + ch));
-                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv[g]);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(rb[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
                         }
@@ -221,6 +232,10 @@ __global__ void __launch_bounds__(192, 1) conv3d_igemm_kernel(const __grid_const
                                                                       pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                         }
                     }
+                }
+                if (c + 1 < BLOCK_N / 32) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) rv[g] = rn[g];
                 }
             }
             ptx::tc_fence_before();
@@ -253,20 +268,20 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-template <int BLOCK_N>
-constexpr int stages_for() { return kSmemBudget / (kABytes + BLOCK_N * kBlockK * 2) > 8 ? 8 : kSmemBudget / (kABytes + BLOCK_N * kBlockK * 2); }
-
-template <int BLOCK_N>
+template <int BLOCK_N, int STAGES, int MIN_BLOCKS>
 static int launch_conv(const ConvMaps& maps, const ConvDev& P, int total_tiles, cudaStream_t st) {
-    constexpr int STAGES = stages_for<BLOCK_N>();
     constexpr int smem = STAGES * (kABytes + BLOCK_N * kBlockK * 2) + 1024 + 256;
+    static_assert(smem * MIN_BLOCKS <= 227 * 1024, "shared memory budget");
+    static_assert(2 * BLOCK_N * MIN_BLOCKS <= 512, "TMEM budget: 512 columns per SM");
     static bool attr_set = false;
     if (!attr_set) {
-        NRPN_CUDA_TRY(cudaFuncSetAttribute(conv3d_igemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        NRPN_CUDA_TRY(cudaFuncSetAttribute(conv3d_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-    conv3d_igemm_kernel<BLOCK_N, STAGES><<<grid, 192, smem, st>>>(maps, P);
+    const int slots = num_sms() * MIN_BLOCKS;
+    const int grid = total_tiles < slots ? total_tiles : slots;
+    conv3d_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS><<<grid, 192, smem, st>>>(maps, P);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
@@ -306,8 +321,13 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
     EncodeTiledFn encode = get_encode();
     if (!encode) return NRPN_ERR_NO_DEVICE;
 
-    const int block_n = nrpn_conv3d_block_n(d->cout);
-    const int cout_pad = ceil_div(d->cout, block_n) * block_n;
+    // Weights are padded to nrpn_conv3d_block_n(cout) (a multiple of 64). Long reductions (3^3 taps) use the widest N tile
+    // that fits, one CTA per SM, deep smem ring: tensor-pipe bound.  Short reductions (1^3 convs: at most 8 k-blocks) are
+    // HBM / epilogue-latency bound: they run N = 64 tiles with 3 CTAs per SM so that 3x more loads/stores are in flight.
+    const int pad_n = nrpn_conv3d_block_n(d->cout);
+    const int cout_pad = ceil_div(d->cout, pad_n) * pad_n;
+    const bool short_k = d->n_taps * (d->cin / kBlockK) <= 8;
+    const int block_n = short_k ? 64 : pad_n;
     ConvMaps maps;
     ConvDev P;
     memset(&P, 0, sizeof(P));
@@ -359,9 +379,10 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
     P.total_m_tiles = tiles;
     const int total_tiles = tiles * P.n_tiles_n;
     cudaStream_t st = (cudaStream_t)stream;
-    if (block_n == 64) return launch_conv<64>(maps, P, total_tiles, st);
-    if (block_n == 128) return launch_conv<128>(maps, P, total_tiles, st);
-    return launch_conv<256>(maps, P, total_tiles, st);
+    if (short_k) return launch_conv<64, 2, 3>(maps, P, total_tiles, st);
+    if (block_n == 64) return launch_conv<64, 8, 1>(maps, P, total_tiles, st);
+    if (block_n == 128) return launch_conv<128, 6, 1>(maps, P, total_tiles, st);
+    return launch_conv<256, 4, 1>(maps, P, total_tiles, st);
 }
 
 #pragma GCC visibility pop

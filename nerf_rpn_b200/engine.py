@@ -257,68 +257,145 @@ class _Plan:
             nxt = [buf(d, 256) for d in self.feat_dims]
             conv(layer, cur, nxt, self.feat_dims, self.feat_dims, name="head3x3x3")
             cur = nxt
-        self.pred = [buf(d, 128, torch.float32) for d in self.feat_dims]
-        conv(L["pred"], cur, self.pred, self.feat_dims, self.feat_dims, out_fp32=True,
-             real=(256, 1, eng.A * (1 + eng.code)), name="pred(cls|bbox)")
+        # cls|bbox predictor: two output sets (parity) so that the post-processing of scene i, which runs on a side
+        # stream, overlaps the backbone of scene i+1 without a buffer hazard
+        self.pred_sets = [[buf(d, 128, torch.float32) for d in self.feat_dims] for _ in range(2)]
+        self.pred_launch = []
+        for par in range(2):
+            self._cur = []
+            conv(L["pred"], cur, self.pred_sets[par], self.feat_dims, self.feat_dims, out_fp32=True,
+                 real=(256, 1, eng.A * (1 + eng.code)), name="pred(cls|bbox)")
+            self.pred_launch.append(self._cur[0])
+            if par == 1:
+                self.algorithmic_flops -= self.names[id(self._cur[0])][1] / n     # counted once per scene
+        self._cur = self.head_launches
 
         # proposals
         self.strides = [tuple(dims[k] // d[k] for k in range(3)) for d in self.feat_dims]
-        self.out_boxes = torch.zeros((n, eng.post_n, 7 if eng.rotated else 6), dtype=torch.float32, device=device)
-        self.out_scores = torch.zeros((n, eng.post_n), dtype=torch.float32, device=device)
-        self.out_levels = torch.zeros((n, eng.post_n), dtype=torch.float32, device=device)
-        self.out_count = torch.zeros((n,), dtype=torch.int32, device=device)
+        bd = 7 if eng.rotated else 6
+        self._out = [dict(boxes=torch.zeros((n, eng.post_n, bd), dtype=torch.float32, device=device),
+                          scores=torch.zeros((n, eng.post_n), dtype=torch.float32, device=device),
+                          levels=torch.zeros((n, eng.post_n), dtype=torch.float32, device=device),
+                          count=torch.zeros((n,), dtype=torch.int32, device=device)) for _ in range(2)]
+        self.side = torch.cuda.Stream(device=device)
+        self._ev_pred = [torch.cuda.Event() for _ in range(2)]
+        self._ev_done = [torch.cuda.Event() for _ in range(2)]
+        self._parity = 0
+        self._post_graph = [None, None]
         self._build_post(None)
 
+    # results of the most recent run (valid once `done` has completed)
+    @property
+    def pred(self):
+        return self.pred_sets[self._parity]
+
+    @property
+    def out_boxes(self):
+        return self._out[self._parity]["boxes"]
+
+    @property
+    def out_scores(self):
+        return self._out[self._parity]["scores"]
+
+    @property
+    def out_levels(self):
+        return self._out[self._parity]["levels"]
+
+    @property
+    def out_count(self):
+        return self._out[self._parity]["count"]
+
+    @property
+    def done(self):
+        return self._ev_done[self._parity]
+
     def _build_post(self, valid_dims):
+        import ctypes
+        from ._lib import lib
         eng = self.eng
-        self._post = []
+        self._post = [[], []]
         self._descs = []
         ws_bytes = 0
-        for i in range(self.n):
-            preds = [p[i].reshape(-1, 128) for p in self.pred]
-            v = None if valid_dims is None else valid_dims[i]
-            d = ops.make_rpn_desc(preds, self.feat_dims, self.strides, eng.cells, eng.A, eng.rotated, eng.pre_n, eng.post_n,
-                                  eng.nms_thresh, eng.score_thresh, eng.min_size, self.dims, valid=v)
-            self._descs.append(d)
-            import ctypes
-            from ._lib import lib
-            ws_bytes = max(ws_bytes, lib().nrpn_rpn_workspace_bytes(ctypes.byref(d)))
+        for par in range(2):
+            for i in range(self.n):
+                preds = [p[i].reshape(-1, 128) for p in self.pred_sets[par]]
+                v = None if valid_dims is None else valid_dims[i]
+                d = ops.make_rpn_desc(preds, self.feat_dims, self.strides, eng.cells, eng.A, eng.rotated, eng.pre_n, eng.post_n,
+                                      eng.nms_thresh, eng.score_thresh, eng.min_size, self.dims, valid=v)
+                self._descs.append(d)
+                ws_bytes = max(ws_bytes, lib().nrpn_rpn_workspace_bytes(ctypes.byref(d)))
         if self._rpn_ws is None or self._rpn_ws.numel() < ws_bytes:
             self._rpn_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-        for i, d in enumerate(self._descs):
-            out = (self.out_boxes[i], self.out_scores[i], self.out_levels[i], self.out_count[i:i + 1])
-            self._post.append(lambda d=d, out=out: ops.rpn_proposals(d, self.device, out=out, workspace=self._rpn_ws))
+        for par in range(2):
+            o = self._out[par]
+            for i in range(self.n):
+                d = self._descs[par * self.n + i]
+                out = (o["boxes"][i], o["scores"][i], o["levels"][i], o["count"][i:i + 1])
+                self._post[par].append(lambda d=d, out=out: ops.rpn_proposals(d, self.device, out=out, workspace=self._rpn_ws))
         self._valid = valid_dims
+        self._post_graph = [None, None]
 
-    def _run_eager(self):
+    def _run_main_eager(self):
         for f in self.launches:
             f()
         if self.has_head:
             for f in self.head_launches:
                 f()
-            for f in self._post:
-                f()
+
+    def _run_post_eager(self, par):
+        for f in self._post[par]:
+            f()
+
+    def _run_eager(self):
+        """Everything for one batch on the current stream (warm-up, launch counting, profiling)."""
+        self._run_main_eager()
+        if self.has_head:
+            self.pred_launch[self._parity]()
+            self._run_post_eager(self._parity)
 
     def run(self, grids: torch.Tensor, valid_dims=None):
         if valid_dims is not None and all(tuple(v) == tuple(self.dims) for v in valid_dims):
             valid_dims = None
         vd = None if valid_dims is None else tuple(tuple(v) for v in valid_dims)
         if self.has_head and vd != self._valid:
+            torch.cuda.synchronize()
             self._build_post(vd)
-            self._graph = None
         if grids.data_ptr() != self.input.data_ptr():
             self.input.copy_(grids, non_blocking=True)
-        if not self.eng.use_graph:
-            self._run_eager()
-            return
-        if self._graph is None:
-            self._run_eager()                      # warm-up: lazy module state, cudaFuncSetAttribute, allocator
+        use_graph = self.eng.use_graph
+        if use_graph and self._graph is None:
+            self._run_eager()                      # warm-up: cudaFuncSetAttribute, lazy init
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._run_eager()
+                self._run_main_eager()
             self._graph = g
-        self._graph.replay()
+        if use_graph:
+            self._graph.replay()
+        else:
+            self._run_main_eager()
+        if not self.has_head:
+            return
+        cur = torch.cuda.current_stream(self.device)
+        par = self._parity ^ 1
+        cur.wait_event(self._ev_done[par])          # the post-processing that used this buffer set two runs ago
+        self.pred_launch[par]()
+        self._ev_pred[par].record(cur)
+        self.side.wait_event(self._ev_pred[par])
+        with torch.cuda.stream(self.side):
+            if use_graph:
+                if self._post_graph[par] is None:
+                    self._run_post_eager(par)
+                    self.side.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.side):
+                        self._run_post_eager(par)
+                    self._post_graph[par] = g
+                self._post_graph[par].replay()
+            else:
+                self._run_post_eager(par)
+            self._ev_done[par].record(self.side)
+        self._parity = par
 
     def num_launches(self) -> int:
         """Kernels per forward (conv / pack / pool launches + the post-processing pipeline), counted, not guessed."""

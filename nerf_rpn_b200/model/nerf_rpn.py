@@ -85,6 +85,7 @@ class NeRFRegionProposalNetwork(nn.Module):
             mesh_tensors = mesh_tensors.contiguous()
         valid = original_mesh_sizes if len(meshes) > 1 else None     # padding masks only when batch > 1 (rpn.py:501)
         plan = self.engine().forward_device(mesh_tensors, valid)
+        torch.cuda.current_stream().wait_event(plan.done)            # post-processing runs on the engine's side stream
         counts = plan.out_count.tolist()                              # the one host sync: data-dependent output sizes
         features = [f.permute(0, 4, 1, 2, 3).float() for f in plan.features]
         proposals = [plan.out_boxes[i, :k].clone() for i, k in enumerate(counts)]

@@ -64,11 +64,12 @@ class ScenePipeline:
             # results of the previous scene were copied out while this one was being enqueued
             if pending is not None and collect:
                 results.append(self._collect(pending))
-            self.h_boxes[slot].copy_(plan.out_boxes[0], non_blocking=True)
-            self.h_scores[slot].copy_(plan.out_scores[0], non_blocking=True)
-            self.h_levels[slot].copy_(plan.out_levels[0], non_blocking=True)
-            self.h_count[slot].copy_(plan.out_count, non_blocking=True)
-            self.done[slot].record(cur)
+            with torch.cuda.stream(plan.side):                    # ordered after this scene's post-processing
+                self.h_boxes[slot].copy_(plan.out_boxes[0], non_blocking=True)
+                self.h_scores[slot].copy_(plan.out_scores[0], non_blocking=True)
+                self.h_levels[slot].copy_(plan.out_levels[0], non_blocking=True)
+                self.h_count[slot].copy_(plan.out_count, non_blocking=True)
+                self.done[slot].record(plan.side)
             pending = slot
             i += 1
         if pending is not None and collect:

@@ -24,7 +24,7 @@ def main():
     torch.cuda.synchronize()
     rows = []
     reps = 5
-    for stage, fs in (("backbone", plan.launches), ("head", plan.head_launches), ("post", plan._post)):
+    for stage, fs in (("backbone", plan.launches), ("head", plan.head_launches + [plan.pred_launch[0]]), ("post", plan._post[0])):
         for f in fs:
             name, fl = plan.names.get(id(f), ("rpn_proposals (top-k, decode, NMS; ~45 kernels)", 0.0))
             ts = []
