@@ -114,10 +114,17 @@ typedef struct {
     const float *shift;             /* fp32 (CoutPad) */
     int32_t n_levels;
     nrpn_conv_level level[NRPN_CONV_MAX_LEVELS];
+    void *workspace;                /* optional split-K scratch (see nrpn_conv3d_workspace_bytes) or NULL */
+    size_t workspace_bytes;
 } nrpn_conv_desc;
 
-/* N tile the kernel will use for this cout (64, 128 or 256); weights/shift must be padded to a multiple. */
+/* Padding granularity of the output-channel axis for this cout (64, 128 or 256): w / shift must be padded to a multiple. */
 int nrpn_conv3d_block_n(int cout);
+/* Layers with few output tiles and a long reduction are split along K over several CTAs that reduce through an fp32
+ * scratch buffer.  Returns the bytes such a layer wants (0: the layer is not split).  The buffer must be zero-filled
+ * ONCE by the caller; every launch leaves it zero-filled again, so one buffer can serve all layers of a stream.
+ * Passing workspace == NULL (or too small) is legal: the layer then runs unsplit. */
+size_t nrpn_conv3d_workspace_bytes(const nrpn_conv_desc *desc /*host*/);
 int nrpn_conv3d_fprop(const nrpn_conv_desc *desc /*host*/, nrpn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -43,6 +43,9 @@ struct ConvLevelDev {
 struct ConvDev {
     int n_levels, n_taps, kc_blocks, n_tiles_n, cout, relu, out_fp32;
     int total_m_tiles;
+    int splits, cout_pad;      // split-K: `splits` CTAs share one output tile and reduce through `ws`
+    float* ws;                 // fp32 (total_m_tiles*128, cout_pad) partial sums, all zero between launches
+    unsigned* counters;        // one arrival counter per output tile, zero between launches
     signed char tap[NRPN_CONV_MAX_TAPS][4];
     const float* shift;
     ConvLevelDev lv[NRPN_CONV_MAX_LEVELS];
@@ -89,14 +92,17 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_tiles = P.total_m_tiles * P.n_tiles_n;
+    const int total_tiles = P.total_m_tiles * P.n_tiles_n * P.splits;     // work items = (output tile, k-split)
     const int kblocks = P.n_taps * P.kc_blocks;
+    uint32_t* ticket_slot = tmem_slot + 1;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (one thread)
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+                const int split = item % P.splits, tile = item / P.splits;
+                const int kb0 = (kblocks * split) / P.splits, kb1 = (kblocks * (split + 1)) / P.splits;
                 const int n_tile = tile % P.n_tiles_n, m_tile = tile / P.n_tiles_n;
                 int l = 0;
 #pragma unroll
@@ -107,9 +113,10 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                 const int tiy = t % L.ty; t /= L.ty;
                 const int tix = t % L.tx; const int nb = t / L.tx;
                 const int x0 = tix * L.bx, y0 = tiy * L.by, z0 = tiz * L.bz, n0 = n_tile * BLOCK_N;
-                for (int tap = 0; tap < P.n_taps; ++tap) {
-                    const int dx = P.tap[tap][0], dy = P.tap[tap][1], dz = P.tap[tap][2];
-                    for (int kc = 0; kc < P.kc_blocks; ++kc) {
+                {
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        const int tap = kb / P.kc_blocks, kc = kb - tap * P.kc_blocks;
+                        const int dx = P.tap[tap][0], dy = P.tap[tap][1], dz = P.tap[tap][2];
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                         uint8_t* sa = smem + stage * kStageBytes;
                         uint8_t* sb = sa + kABytes;
@@ -126,11 +133,13 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+                const int split = item % P.splits;
+                const int nkb = (kblocks * (split + 1)) / P.splits - (kblocks * split) / P.splits;
                 ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
@@ -153,7 +162,8 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;                   // accumulator row == voxel inside the brick
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+            const int tile = item / P.splits;
             const int n_tile = tile % P.n_tiles_n, m_tile = tile / P.n_tiles_n;
             int l = 0;
 #pragma unroll
@@ -179,6 +189,68 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
             }
             const int n0 = n_tile * BLOCK_N;
 
+            if (P.splits > 1) {
+                // ---- split-K: add this CTA's partial tile into the fp32 workspace; the last CTA to arrive finishes the tile
+                float* wrow = P.ws + ((size_t)m_tile * kBlockM + row) * P.cout_pad + n0;
+                ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+                ptx::tc_fence_after();
+                const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(t_base + (uint32_t)(c * 32), r);
+                    ptx::tmem_ld_wait();
+                    if (valid && n0 + c * 32 < P.cout) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) atomicAdd(wrow + c * 32 + j, __uint_as_float(r[j]));
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (row == 0) *ticket_slot = atomicAdd(P.counters + tile, 1u);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const bool last = (*ticket_slot == (uint32_t)(P.splits - 1));
+                if (last) {
+                    __threadfence();
+                    if (valid) {
+                        for (int ch = n0; ch < n0 + BLOCK_N && ch < P.cout; ch += 8) {
+                            float* wp = wrow + (ch - n0);
+                            const float4 a0 = __ldcg(reinterpret_cast<const float4*>(wp));
+                            const float4 a1 = __ldcg(reinterpret_cast<const float4*>(wp + 4));
+                            *reinterpret_cast<float4*>(wp) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            *reinterpret_cast<float4*>(wp + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.shift + ch));
+                            const float4 s1 = __ldg(reinterpret_cast<const float4*>(P.shift + ch + 4));
+                            float v[8] = {a0.x + s0.x, a0.y + s0.y, a0.z + s0.z, a0.w + s0.w, a1.x + s1.x, a1.y + s1.y, a1.z + s1.z, a1.w + s1.w};
+                            if (rrow != nullptr) {
+                                const uint4 rv4 = __ldg(reinterpret_cast<const uint4*>(rrow + ch));
+                                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv4);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(rb[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
+                            }
+                            if (P.relu) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+                            }
+                            if (P.out_fp32) {
+                                float* o = reinterpret_cast<float*>(L.y) + vox * L.ldy + ch;
+                                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                                *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                            } else {
+                                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(L.y) + vox * L.ldy + ch;
+                                *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                                          pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                            }
+                        }
+                    }
+                    if (row == 0) P.counters[tile] = 0u;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");     // ticket_slot is reused by the next work item
+                continue;
+            }
             // residual rows are fetched one 32-channel chunk ahead (4 x 16 B per thread in flight) so that the DRAM
             // latency of chunk c+1 hides behind the TMEM load + math + stores of chunk c
             uint4 rv[4];
@@ -299,12 +371,54 @@ static void choose_brick(int xo, int yo, int zo, int& bx, int& by, int& bz) {
     }
 }
 
+// Split-K: layers with far fewer output tiles than SMs and a long reduction (late ResNet stages: 5x8x8 .. 10x16x16 voxels,
+// K up to 13 824) are latency bound on streaming their weights through a handful of CTAs. Spread the k-blocks of each
+// tile over `splits` CTAs (>= 4 k-blocks each, about one wave in total).
+static int choose_splits(int total_tiles, int kblocks, bool short_k) {
+    if (short_k || kblocks < 8 || total_tiles * 2 > num_sms()) return 1;
+    int s = num_sms() / total_tiles;
+    if (s > kblocks / 4) s = kblocks / 4;
+    if (s > 32) s = 32;
+    return s < 2 ? 1 : s;
+}
+
+struct ConvGeom { int pad_n, cout_pad, block_n, kblocks, m_tiles, n_tiles_n, splits; bool short_k; size_t ws_bytes, counter_bytes; };
+
+static int conv_geometry(const nrpn_conv_desc* d, ConvGeom& g) {
+    g.pad_n = nrpn_conv3d_block_n(d->cout);
+    g.cout_pad = ceil_div(d->cout, g.pad_n) * g.pad_n;
+    g.kblocks = d->n_taps * (d->cin / kBlockK);
+    g.short_k = g.kblocks <= 8;
+    g.block_n = g.short_k ? 64 : g.pad_n;
+    g.n_tiles_n = g.cout_pad / g.block_n;
+    int tiles = 0;
+    for (int l = 0; l < d->n_levels; ++l) {
+        const nrpn_conv_level& S = d->level[l];
+        if (S.n < 1 || S.xo < 1 || S.yo < 1 || S.zo < 1) return NRPN_ERR_INVALID;
+        int bx, by, bz;
+        choose_brick(S.xo, S.yo, S.zo, bx, by, bz);
+        tiles += S.n * ceil_div(S.xo, bx) * ceil_div(S.yo, by) * ceil_div(S.zo, bz);
+    }
+    g.m_tiles = tiles;
+    g.splits = choose_splits(tiles * g.n_tiles_n, g.kblocks, g.short_k);
+    g.counter_bytes = align_up((size_t)tiles * g.n_tiles_n * 4, 256);
+    g.ws_bytes = g.splits > 1 ? g.counter_bytes + (size_t)tiles * kBlockM * g.cout_pad * 4 : 0;
+    return NRPN_OK;
+}
+
 }  // namespace nrpn
 
 using namespace nrpn;
 
 extern "C" {
 #pragma GCC visibility push(default)
+
+size_t nrpn_conv3d_workspace_bytes(const nrpn_conv_desc* d) {
+    if (!d || d->cin < 64 || d->cin % 64 != 0 || d->n_levels < 1 || d->n_levels > NRPN_CONV_MAX_LEVELS || d->n_taps < 1) return 0;
+    ConvGeom g;
+    if (conv_geometry(d, g) != NRPN_OK) return 0;
+    return g.ws_bytes;
+}
 
 int nrpn_conv3d_block_n(int cout) { return cout <= 64 ? 64 : (cout <= 128 ? 128 : 256); }
 
@@ -324,10 +438,13 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
     // Weights are padded to nrpn_conv3d_block_n(cout) (a multiple of 64). Long reductions (3^3 taps) use the widest N tile
     // that fits, one CTA per SM, deep smem ring: tensor-pipe bound.  Short reductions (1^3 convs: at most 8 k-blocks) are
     // HBM / epilogue-latency bound: they run N = 64 tiles with 3 CTAs per SM so that 3x more loads/stores are in flight.
-    const int pad_n = nrpn_conv3d_block_n(d->cout);
-    const int cout_pad = ceil_div(d->cout, pad_n) * pad_n;
-    const bool short_k = d->n_taps * (d->cin / kBlockK) <= 8;
-    const int block_n = short_k ? 64 : pad_n;
+    ConvGeom geo;
+    { const int rc = conv_geometry(d, geo); if (rc) return rc; }
+    const int cout_pad = geo.cout_pad;
+    const bool short_k = geo.short_k;
+    const int block_n = geo.block_n;
+    int splits = geo.splits;
+    if (splits > 1 && (!d->workspace || d->workspace_bytes < geo.ws_bytes)) splits = 1;      // no (or too small a) workspace: run unsplit
     ConvMaps maps;
     ConvDev P;
     memset(&P, 0, sizeof(P));
@@ -377,7 +494,10 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
         if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return NRPN_ERR_CUDA; }
     }
     P.total_m_tiles = tiles;
-    const int total_tiles = tiles * P.n_tiles_n;
+    P.splits = splits; P.cout_pad = cout_pad;
+    P.counters = reinterpret_cast<unsigned*>(d->workspace);
+    P.ws = splits > 1 ? reinterpret_cast<float*>(reinterpret_cast<char*>(d->workspace) + geo.counter_bytes) : nullptr;
+    const int total_tiles = tiles * P.n_tiles_n * splits;
     cudaStream_t st = (cudaStream_t)stream;
     if (short_k) return launch_conv<64, 2, 3>(maps, P, total_tiles, st);
     if (block_n == 64) return launch_conv<64, 8, 1>(maps, P, total_tiles, st);

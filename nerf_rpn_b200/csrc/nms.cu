@@ -329,15 +329,19 @@ __global__ void __launch_bounds__(256) nms_resolve_kernel(const unsigned long lo
             if (lane == 0) { kept_sh = kept; if (kept) atomicOr(&keepbits[c], kept); }
         }
         __syncthreads();
+        // OR the kept rows into the removed words right of the diagonal: lane <-> word (coalesced), warp <-> 8 of the 64
+        // rows, so up to 8 independent loads per thread are in flight (this loop used to be one thread per word walking
+        // the kept rows serially: 64 dependent L2 round trips per chunk)
         const unsigned long long kept = kept_sh;
-        for (int w = c + 1 + tid; w <= c1; w += blockDim.x) {
-            unsigned long long acc = 0ull, k = kept;
-            while (k) {
-                const int i = __ffsll((long long)k) - 1;
-                k &= k - 1;
-                acc |= mask[(size_t)(c * 64 + i) * W + w];
+        const unsigned long long mine = (kept >> (warp * 8)) & 0xFFull;
+        if (mine) {
+            for (int w = c + 1 + lane; w <= c1; w += 32) {
+                unsigned long long acc = 0ull;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if ((mine >> i) & 1ull) acc |= mask[(size_t)(c * 64 + warp * 8 + i) * W + w];
+                if (acc) atomicOr(&removed[w], acc);
             }
-            removed[w] |= acc;
         }
         __syncthreads();
     }

@@ -165,6 +165,8 @@ class _Plan:
         self._valid = None
         self._graph = None
         self._post = []
+        # split-K scratch shared by every conv of this plan's main stream: zero-filled once, each launch restores the zeros
+        self._splitk_ws = torch.zeros(64 << 20, dtype=torch.uint8, device=device)
         self.names = {}              # id(callable) -> (layer name, algorithmic flops of the launch)
         self.launches = []           # backbone stage: list of zero-arg callables
         self.head_launches = []      # head stage
@@ -180,8 +182,12 @@ class _Plan:
                 r = None if res is None else res[i]
                 args.append(ops.ConvLevelArgs(xs[i], ys[i], n, in_dims[i], out_dims[i], ys[i].shape[-1], res=r,
                                               res_dims=None if r is None else res_dims[i], ldr=0 if r is None else r.shape[-1]))
+            need = ops.conv3d_workspace_bytes(args, layer.w, layer.shift, layer.cin, layer.cout, layer.taps, layer.stride,
+                                              layer.relu, out_fp32)
+            if need > self._splitk_ws.numel():
+                raise RuntimeError(f"split-K workspace too small: need {need} bytes")
             self._cur.append(lambda a=args, l=layer, f=out_fp32: ops.conv3d_fprop(
-                a, l.w, l.shift, l.cin, l.cout, l.taps, stride=l.stride, relu=l.relu, out_fp32=f))
+                a, l.w, l.shift, l.cin, l.cout, l.taps, stride=l.stride, relu=l.relu, out_fp32=f, workspace=self._splitk_ws))
             fl = 0.0
             for od in out_dims:
                 vox = n * od[0] * od[1] * od[2]

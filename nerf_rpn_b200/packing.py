@@ -12,9 +12,10 @@ import torch
 
 def fold_bn(bn: torch.nn.modules.batchnorm._BatchNorm) -> Tuple[torch.Tensor, torch.Tensor]:
     """eval-mode BatchNorm3d (feature_extractor.py:38,41,43) as y = x * scale + shift."""
-    inv = torch.rsqrt(bn.running_var.detach().double() + bn.eps)
-    scale = bn.weight.detach().double() * inv
-    shift = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+    var, mean = bn.running_var.detach().cpu().double(), bn.running_mean.detach().cpu().double()     # host-side, once per checkpoint
+    inv = torch.rsqrt(var + bn.eps)
+    scale = bn.weight.detach().cpu().double() * inv
+    shift = bn.bias.detach().cpu().double() - mean * scale
     return scale.float(), shift.float()
 
 

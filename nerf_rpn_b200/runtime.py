@@ -12,38 +12,45 @@ import torch
 
 
 class ScenePipeline:
-    def __init__(self, model, dims: Tuple[int, int, int], device=None):
-        """model: nerf_rpn_b200.model.nerf_rpn.NeRFRegionProposalNetwork in eval mode; dims: (W, L, H) of every scene."""
+    def __init__(self, model, dims: Tuple[int, int, int], device=None, batch: int = 1):
+        """model: nerf_rpn_b200.model.nerf_rpn.NeRFRegionProposalNetwork in eval mode; dims: (W, L, H) of every scene;
+        batch: scenes per engine launch (weights are read once per batch, small layers get more tiles)."""
         self.model = model
+        self.batch = int(batch)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.dims = tuple(dims)
         self.eng = model.engine()
         self.copy_stream = torch.cuda.Stream(device=self.device)
         # two device staging buffers; the engine's graph reads its own static input, filled by a D2D copy
-        self.stage = [torch.empty((1, 4, *self.dims), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.stage = [torch.empty((self.batch, 4, *self.dims), dtype=torch.float32, device=self.device) for _ in range(2)]
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
         k = self.eng.post_n
         bd = 7 if self.eng.rotated else 6
-        self.h_boxes = torch.empty((2, k, bd), dtype=torch.float32).pin_memory()
-        self.h_scores = torch.empty((2, k), dtype=torch.float32).pin_memory()
-        self.h_levels = torch.empty((2, k), dtype=torch.float32).pin_memory()
-        self.h_count = torch.empty((2, 1), dtype=torch.int32).pin_memory()
+        B = self.batch
+        self.h_boxes = torch.empty((2, B, k, bd), dtype=torch.float32).pin_memory()
+        self.h_scores = torch.empty((2, B, k), dtype=torch.float32).pin_memory()
+        self.h_levels = torch.empty((2, B, k), dtype=torch.float32).pin_memory()
+        self.h_count = torch.empty((2, B), dtype=torch.int32).pin_memory()
         self.done = [torch.cuda.Event() for _ in range(2)]
         self.h2d_bytes_per_scene = 4 * self.dims[0] * self.dims[1] * self.dims[2] * 4
         self.d2h_bytes_per_scene = (k * bd + 2 * k + 1) * 4
 
-    def _prefetch(self, slot: int, host_grid: torch.Tensor):
+    def _prefetch(self, slot: int, host_grids):
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.consumed[slot])
-            self.stage[slot][0].copy_(host_grid, non_blocking=True)
+            for b, g in enumerate(host_grids):
+                self.stage[slot][b].copy_(g, non_blocking=True)
             self.ready[slot].record(self.copy_stream)
 
     def run(self, host_grids: Iterable[torch.Tensor], collect: bool = True):
         """host_grids: iterable of pinned fp32 (4,W,L,H) tensors. Returns a list of (boxes, scores, levels) CPU tensors
         (or only the number of scenes processed when collect=False)."""
         cur = torch.cuda.current_stream(self.device)
-        it = iter(host_grids)
+        grids = list(host_grids)
+        if len(grids) % self.batch:
+            raise ValueError(f"number of scenes ({len(grids)}) must be a multiple of the pipeline batch ({self.batch})")
+        it = iter([grids[i:i + self.batch] for i in range(0, len(grids), self.batch)])
         nxt = next(it, None)
         if nxt is None:
             return []
@@ -63,25 +70,28 @@ class ScenePipeline:
             self.consumed[slot].record(cur)
             # results of the previous scene were copied out while this one was being enqueued
             if pending is not None and collect:
-                results.append(self._collect(pending))
-            with torch.cuda.stream(plan.side):                    # ordered after this scene's post-processing
-                self.h_boxes[slot].copy_(plan.out_boxes[0], non_blocking=True)
-                self.h_scores[slot].copy_(plan.out_scores[0], non_blocking=True)
-                self.h_levels[slot].copy_(plan.out_levels[0], non_blocking=True)
+                results.extend(self._collect(pending))
+            with torch.cuda.stream(plan.side):                    # ordered after this batch's post-processing
+                self.h_boxes[slot].copy_(plan.out_boxes, non_blocking=True)
+                self.h_scores[slot].copy_(plan.out_scores, non_blocking=True)
+                self.h_levels[slot].copy_(plan.out_levels, non_blocking=True)
                 self.h_count[slot].copy_(plan.out_count, non_blocking=True)
                 self.done[slot].record(plan.side)
             pending = slot
             i += 1
         if pending is not None and collect:
-            results.append(self._collect(pending))
+            results.extend(self._collect(pending))
         else:
             self.done[(i - 1) & 1].synchronize()
-        return results if collect else i
+        return results if collect else i * self.batch
 
     def _collect(self, slot: int):
         self.done[slot].synchronize()
-        k = int(self.h_count[slot, 0])
-        return self.h_boxes[slot, :k].clone(), self.h_scores[slot, :k].clone(), self.h_levels[slot, :k].clone()
+        out = []
+        for b in range(self.batch):
+            k = int(self.h_count[slot, b])
+            out.append((self.h_boxes[slot, b, :k].clone(), self.h_scores[slot, b, :k].clone(), self.h_levels[slot, b, :k].clone()))
+        return out
 
 
 # ---------------------------------------------------------------------------------------------- multi-GPU

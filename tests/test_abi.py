@@ -40,7 +40,7 @@ def test_struct_layouts_match_c():
 #include <stddef.h>
 #include "nerf_rpn_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(nrpn_conv_level), sizeof(nrpn_conv_desc), offsetof(nrpn_conv_desc, stride),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", offsetof(nrpn_conv_desc, workspace), sizeof(nrpn_conv_level), sizeof(nrpn_conv_desc), offsetof(nrpn_conv_desc, stride),
          offsetof(nrpn_conv_desc, w), offsetof(nrpn_conv_desc, level), sizeof(nrpn_rpn_level), sizeof(nrpn_rpn_desc),
          offsetof(nrpn_rpn_desc, cell_anchors), offsetof(nrpn_rpn_desc, nms_thresh), offsetof(nrpn_rpn_desc, valid));
   return 0; }'''
@@ -50,7 +50,7 @@ int main(void) {
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         vals = [int(v) for v in subprocess.check_output([exe]).split()]
     C, R = _lib.ConvDesc, _lib.RpnDesc
-    mine = [ctypes.sizeof(_lib.ConvLevel), ctypes.sizeof(C), C.stride.offset, C.w.offset, C.level.offset,
+    mine = [C.workspace.offset, ctypes.sizeof(_lib.ConvLevel), ctypes.sizeof(C), C.stride.offset, C.w.offset, C.level.offset,
             ctypes.sizeof(_lib.RpnLevel), ctypes.sizeof(R), R.cell_anchors.offset, R.nms_thresh.offset, R.valid.offset]
     assert mine == vals
 

@@ -112,6 +112,35 @@ def test_conv_multi_level_shared_weights(ops):
         assert (got - r).abs().max().item() <= 1e-2 * r.abs().max().item(), _diagnose(got, r, f"level{i}")
 
 
+def test_conv_split_k_small_grids(ops):
+    """Late ResNet stages: few output tiles, long reductions -> split-K through the fp32 scratch (atomics + last-CTA
+    fix-up). Run twice on the same zero-initialised scratch: every launch must leave it zero-filled."""
+    from nerf_rpn_b200 import packing
+    g = torch.Generator(device="cuda").manual_seed(21)
+    ws = torch.zeros(64 << 20, dtype=torch.uint8, device="cuda")
+    for dims, cin, cout, k, relu, with_res in [((5, 8, 8), 512, 512, 3, True, False), ((10, 16, 16), 1024, 256, 1, False, True),
+                                                ((5, 8, 8), 2048, 512, 1, True, True), ((10, 16, 16), 256, 256, 3, False, False)]:
+        x = torch.randn((1, *dims, cin), device="cuda", generator=g).to(torch.bfloat16)
+        w = torch.randn((cout, cin, k, k, k), device="cuda", generator=g) / (cin * k ** 3) ** 0.5
+        bias = torch.randn((cout,), device="cuda", generator=g)
+        res = torch.randn((1, *dims, cout), device="cuda", generator=g).to(torch.bfloat16) if with_res else None
+        wp, taps = packing.pack_conv_weight(w.cpu()); wp = wp.cuda()
+        shift = packing.pad_shift(bias, wp.shape[1])
+        ref = emulate_conv(x.float(), wp.float(), taps, shift, dims, relu=relu, res=res)[..., :cout]
+        args_probe = [ops.ConvLevelArgs(x, x, 1, dims, dims, cout)]
+        need = ops.conv3d_workspace_bytes(args_probe, wp, shift, cin, cout, taps)
+        assert need > 0, "this shape is expected to be split along K"
+        for rep in range(2):
+            y = torch.full((1, *dims, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+            a = ops.ConvLevelArgs(x, y, 1, dims, dims, cout, res=res, res_dims=dims if with_res else None, ldr=cout if with_res else 0)
+            ops.conv3d_fprop([a], wp, shift, cin, cout, taps, relu=relu, workspace=ws)
+            torch.cuda.synchronize()
+            got = y.float()
+            assert not torch.isnan(got).any()
+            assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item(), _diagnose(got, ref, f"splitk {dims} {cin}->{cout} rep{rep}")
+        assert int(ws.count_nonzero().item()) == 0, "split-K scratch not restored to zero"
+
+
 def test_conv_large_p2_tile_count(ops):
     """More tiles than SMs (persistent loop, TMEM double buffering, stage ring wrap-around)."""
     g = torch.Generator(device="cuda").manual_seed(11)
