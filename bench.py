@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true", help="exploration runs only: omit the ~40 s CPU port timing")
     ap.add_argument("--scenes-per-step", type=int, default=int(os.environ.get("NRPN_SCENES_PER_STEP", "1")),
                     help="scenes per rank per step (one engine launch); weights are read once per step")
     return ap.parse_args()
@@ -270,8 +271,11 @@ def run_b200(args):
         value = world * K * B / (ms * 1e-3)
         cores = os.cpu_count() or 1
         torch.cuda.empty_cache()
-        cpu_port_run(16, cores)                            # warm the CPU libraries (oneDNN JIT, thread pool) on a thin slab
-        cpu_t = cpu_port_run(160, cores)[0]
+        if args.skip_cpu_baseline:
+            cpu_t = float("nan")
+        else:
+            cpu_port_run(16, cores)                        # warm the CPU libraries (oneDNN JIT, thread pool) on a thin slab
+            cpu_t = cpu_port_run(160, cores)[0]
         out = {"metric": "scenes/sec", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                "data": "synthetic",

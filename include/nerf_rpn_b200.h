@@ -120,10 +120,11 @@ typedef struct {
 
 /* Padding granularity of the output-channel axis for this cout (64, 128 or 256): w / shift must be padded to a multiple. */
 int nrpn_conv3d_block_n(int cout);
-/* Layers with few output tiles and a long reduction are split along K over several CTAs that reduce through an fp32
- * scratch buffer.  Returns the bytes such a layer wants (0: the layer is not split).  The buffer must be zero-filled
- * ONCE by the caller; every launch leaves it zero-filled again, so one buffer can serve all layers of a stream.
- * Passing workspace == NULL (or too small) is legal: the layer then runs unsplit. */
+/* Layers with few output tiles and a long reduction are split along K over several CTAs; each stores its partial tile
+ * into its own fp32 slab and the last CTA to arrive sums the slabs in a fixed order (bit-reproducible).  Returns the
+ * bytes such a layer wants (0: the layer is not split).  The first 256-byte-aligned counters region must be zero-filled
+ * ONCE by the caller (simplest: zero the whole buffer); every launch leaves the counters at zero, so one buffer can serve
+ * all layers of a stream.  Passing workspace == NULL (or too small) is legal: the layer then runs unsplit. */
 size_t nrpn_conv3d_workspace_bytes(const nrpn_conv_desc *desc /*host*/);
 int nrpn_conv3d_fprop(const nrpn_conv_desc *desc /*host*/, nrpn_stream_t stream);
 

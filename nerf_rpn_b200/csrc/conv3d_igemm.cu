@@ -44,7 +44,7 @@ struct ConvDev {
     int n_levels, n_taps, kc_blocks, n_tiles_n, cout, relu, out_fp32;
     int total_m_tiles;
     int splits, cout_pad;      // split-K: `splits` CTAs share one output tile and reduce through `ws`
-    float* ws;                 // fp32 (total_m_tiles*128, cout_pad) partial sums, all zero between launches
+    float* ws;                 // fp32 (tiles, splits, 128, BLOCK_N) partial tiles, rewritten by every launch
     unsigned* counters;        // one arrival counter per output tile, zero between launches
     signed char tap[NRPN_CONV_MAX_TAPS][4];
     const float* shift;
@@ -190,8 +190,11 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
             const int n0 = n_tile * BLOCK_N;
 
             if (P.splits > 1) {
-                // ---- split-K: add this CTA's partial tile into the fp32 workspace; the last CTA to arrive finishes the tile
-                float* wrow = P.ws + ((size_t)m_tile * kBlockM + row) * P.cout_pad + n0;
+                // ---- split-K (deterministic): every CTA stores its partial tile into its own fp32 slab of the workspace with
+                // plain stores; the last CTA to arrive sums the slabs in split order and runs the normal epilogue.
+                const int split = item % P.splits;
+                float* slab0 = P.ws + ((size_t)tile * P.splits) * (kBlockM * BLOCK_N);          // slabs of this output tile
+                float* wrow = slab0 + (size_t)split * (kBlockM * BLOCK_N) + (size_t)row * BLOCK_N;
                 ptx::mbar_wait(&tfull_bar[acc], acc_phase);
                 ptx::tc_fence_after();
                 const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
@@ -200,9 +203,11 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                     uint32_t r[32];
                     ptx::tmem_ld_32x32(t_base + (uint32_t)(c * 32), r);
                     ptx::tmem_ld_wait();
-                    if (valid && n0 + c * 32 < P.cout) {
+                    if (valid) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) atomicAdd(wrow + c * 32 + j, __uint_as_float(r[j]));
+                        for (int j = 0; j < 32; j += 4)
+                            __stcg(reinterpret_cast<float4*>(wrow + c * 32 + j),
+                                   make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
                     }
                 }
                 ptx::tc_fence_before();
@@ -216,12 +221,16 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                 if (last) {
                     __threadfence();
                     if (valid) {
+                        const float* rrow0 = slab0 + (size_t)row * BLOCK_N;
                         for (int ch = n0; ch < n0 + BLOCK_N && ch < P.cout; ch += 8) {
-                            float* wp = wrow + (ch - n0);
-                            const float4 a0 = __ldcg(reinterpret_cast<const float4*>(wp));
-                            const float4 a1 = __ldcg(reinterpret_cast<const float4*>(wp + 4));
-                            *reinterpret_cast<float4*>(wp) = make_float4(0.f, 0.f, 0.f, 0.f);
-                            *reinterpret_cast<float4*>(wp + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+                            for (int sp = 0; sp < P.splits; ++sp) {                                  // fixed order => reproducible
+                                const float* wp = rrow0 + (size_t)sp * (kBlockM * BLOCK_N) + (ch - n0);
+                                const float4 b0 = __ldcg(reinterpret_cast<const float4*>(wp));
+                                const float4 b1 = __ldcg(reinterpret_cast<const float4*>(wp + 4));
+                                a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+                                a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+                            }
                             const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.shift + ch));
                             const float4 s1 = __ldg(reinterpret_cast<const float4*>(P.shift + ch + 4));
                             float v[8] = {a0.x + s0.x, a0.y + s0.y, a0.z + s0.z, a0.w + s0.w, a1.x + s1.x, a1.y + s1.y, a1.z + s1.z, a1.w + s1.w};
@@ -402,7 +411,7 @@ static int conv_geometry(const nrpn_conv_desc* d, ConvGeom& g) {
     g.m_tiles = tiles;
     g.splits = choose_splits(tiles * g.n_tiles_n, g.kblocks, g.short_k);
     g.counter_bytes = align_up((size_t)tiles * g.n_tiles_n * 4, 256);
-    g.ws_bytes = g.splits > 1 ? g.counter_bytes + (size_t)tiles * kBlockM * g.cout_pad * 4 : 0;
+    g.ws_bytes = g.splits > 1 ? g.counter_bytes + (size_t)tiles * g.n_tiles_n * g.splits * kBlockM * g.block_n * 4 : 0;
     return NRPN_OK;
 }
 

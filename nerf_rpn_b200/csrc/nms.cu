@@ -161,7 +161,9 @@ int bitonic_sort_u64(unsigned long long* keys, int n_pad, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------- NMS
 static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-constexpr int kNmsMaxBoxes = 32768;
+constexpr int kNmsMatrixMax = 32768;     // full bit-matrix path (n x n/64 words) up to here
+constexpr int kNmsMaxBoxes = 1 << 21;       // chunked path beyond (index field of the sort key is 24 bits)
+constexpr int kChunk = 4096;                // boxes per chunk of the chunked path (64 words)
 constexpr int kPrepFloats = 16;
 
 struct NmsWs {
@@ -171,7 +173,10 @@ struct NmsWs {
     int* sgroup;                  // n
     int* seg;                     // 512 (start[256], end[256])
     unsigned long long* keepbits; // W
-    unsigned long long* mask;     // n * W
+    unsigned long long* mask;     // n * W (matrix path) or kChunk * 64 (chunked path)
+    unsigned long long* removed0; // 64 words: suppression by earlier chunks (chunked path)
+    int* kept_pos;                // n (chunked path)
+    int* state;                   // [0] kept count, [1..256] first kept index per group
     size_t total;
 };
 
@@ -188,7 +193,11 @@ static NmsWs nms_layout(void* base, int n) {
     w.sgroup = (int*)(b + take((size_t)n * 4));
     w.seg = (int*)(b + take(512 * 4));
     w.keepbits = (unsigned long long*)(b + take((size_t)W * 8));
-    w.mask = (unsigned long long*)(b + take((size_t)n * W * 8));
+    const bool chunked = n > kNmsMatrixMax;
+    w.mask = (unsigned long long*)(b + take(chunked ? (size_t)kChunk * 64 * 8 : (size_t)n * W * 8));
+    w.removed0 = (unsigned long long*)(b + take(64 * 8));
+    w.kept_pos = (int*)(b + take(chunked ? (size_t)n * 4 : 4));
+    w.state = (int*)(b + take(257 * 4));
     w.total = off;
     return w;
 }
@@ -305,7 +314,7 @@ __global__ void __launch_bounds__(256) nms_resolve_kernel(const unsigned long lo
     if (g == ignore_group) return;
     const int s = seg[g], e = seg[256 + g];
     if (e <= s) return;
-    __shared__ unsigned long long removed[kNmsMaxBoxes / 64];
+    __shared__ unsigned long long removed[kNmsMatrixMax / 64];
     __shared__ unsigned long long kept_sh;
     const int c0 = s >> 6, c1 = (e - 1) >> 6;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -345,6 +354,125 @@ __global__ void __launch_bounds__(256) nms_resolve_kernel(const unsigned long lo
         }
         __syncthreads();
     }
+}
+
+// ------------------------------------------------------------------------------ chunked path (n > 32 768)
+// Sorted boxes are processed in chunks of 4096: (a) every box of the chunk is tested against the boxes KEPT so far
+// (one warp per box, lanes stride over the kept list of its group, exact-zero culling first), (b) the 4096 x 4096 bit
+// matrix of the chunk is built with the same tile kernel as the matrix path, (c) one CTA resolves the chunk and appends
+// the survivors to the kept list. Greedy semantics are unchanged: a box is suppressed iff a higher-scored KEPT box of
+// its group overlaps it by more than the threshold.
+__global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict__ prep, const int* __restrict__ sgroup, int box_dim,
+                                                        float thr, int ignore_group, int chunk_begin, int chunk_n,
+                                                        const int* __restrict__ kept_pos, const int* __restrict__ state,
+                                                        unsigned long long* __restrict__ removed0) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= chunk_n) return;
+    const int p = chunk_begin + warp;
+    const int g = sgroup[p];
+    bool sup = false;
+    if (g == ignore_group) {
+        sup = true;
+    } else {
+        const int kc = state[0];
+        const int start = state[1 + g];
+        const bool cull_ok = (0.0f <= thr);
+        if (box_dim == 7) {
+            ObbPrep b; load_prep(prep + (size_t)p * kPrepFloats, b);
+            for (int k0 = start; k0 < kc; k0 += 32) {
+                const int k = k0 + lane;
+                bool hit = false;
+                if (k < kc) {
+                    ObbPrep a; load_prep(prep + (size_t)kept_pos[k] * kPrepFloats, a);
+                    const float iou = iou3d_obb(a, b, cull_ok);
+                    hit = !(iou <= thr);
+                }
+                if (__any_sync(0xffffffffu, hit)) { sup = true; break; }
+            }
+        } else {
+            float b[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) b[i] = prep[(size_t)p * kPrepFloats + i];
+            for (int k0 = start; k0 < kc; k0 += 32) {
+                const int k = k0 + lane;
+                bool hit = false;
+                if (k < kc) {
+                    const float* a = prep + (size_t)kept_pos[k] * kPrepFloats;
+                    float aa[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) aa[i] = a[i];
+                    const float iou = iou3d_aabb(aa, b);
+                    hit = !(iou <= thr);
+                }
+                if (__any_sync(0xffffffffu, hit)) { sup = true; break; }
+            }
+        }
+    }
+    if (sup && lane == 0) atomicOr(&removed0[warp >> 6], 1ull << (warp & 63));
+}
+
+// one CTA: resolve the chunk (all groups at once: mask bits only ever connect boxes of the same group), append survivors
+__global__ void __launch_bounds__(256) nms_chunk_resolve_kernel(const unsigned long long* __restrict__ cmask, int Wc, int chunk_begin,
+                                                                int chunk_n, const int* __restrict__ sgroup,
+                                                                unsigned long long* __restrict__ removed0, int* __restrict__ kept_pos,
+                                                                int* __restrict__ state, unsigned long long* __restrict__ keepbits) {
+    __shared__ unsigned long long removed[64];
+    __shared__ unsigned long long kept_sh;
+    __shared__ int kept_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 64) { removed[tid] = removed0[tid]; removed0[tid] = 0ull; }       // leave the scratch zeroed for the next chunk
+    if (tid == 0) kept_base = state[0];
+    __syncthreads();
+    for (int c = 0; c < Wc; ++c) {
+        if (warp == 0) {
+            const int r_lo = c * 64 + lane, r_hi = r_lo + 32;
+            const bool v_lo = r_lo < chunk_n, v_hi = r_hi < chunk_n;
+            const unsigned long long d_lo = v_lo ? cmask[(size_t)r_lo * Wc + c] : 0ull;
+            const unsigned long long d_hi = v_hi ? cmask[(size_t)r_hi * Wc + c] : 0ull;
+            const unsigned b_lo = __ballot_sync(0xffffffffu, v_lo), b_hi = __ballot_sync(0xffffffffu, v_hi);
+            const unsigned long long valid = ((unsigned long long)b_hi << 32) | b_lo;
+            unsigned long long rem = removed[c] | ~valid;
+            unsigned long long kept = 0ull;
+#pragma unroll 8
+            for (int i = 0; i < 64; ++i) {
+                const unsigned long long rowbits = shfl64(i < 32 ? d_lo : d_hi, i & 31);
+                if (!((rem >> i) & 1ull)) { kept |= 1ull << i; rem |= rowbits; }
+            }
+            // append survivors in order; remember where each group's kept boxes start
+            const int base = kept_base;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane + 32 * h;
+                if ((kept >> i) & 1ull) {
+                    const int pos = chunk_begin + c * 64 + i;
+                    const int ki = base + __popcll(kept & ((1ull << i) - 1ull));
+                    kept_pos[ki] = pos;
+                    atomicMin(&state[1 + sgroup[pos]], ki);
+                }
+            }
+            if (lane == 0) { kept_sh = kept; kept_base = base + __popcll(kept); keepbits[(chunk_begin >> 6) + c] = kept; }
+        }
+        __syncthreads();
+        const unsigned long long kept = kept_sh;
+        const unsigned long long mine = (kept >> (warp * 8)) & 0xFFull;
+        if (mine) {
+            for (int w = c + 1 + lane; w < Wc; w += 32) {
+                unsigned long long acc = 0ull;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if ((mine >> i) & 1ull) acc |= cmask[(size_t)(c * 64 + warp * 8 + i) * Wc + w];
+                if (acc) atomicOr(&removed[w], acc);
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) state[0] = kept_base;
+}
+
+__global__ void nms_state_init_kernel(int* __restrict__ state) {
+    const int t = threadIdx.x;
+    if (t == 0) state[0] = 0;
+    if (t < 256) state[1 + t] = 0x7fffffff;
 }
 
 __global__ void nms_keys2_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ keepbits,
@@ -389,10 +517,28 @@ int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t*
     if (rc) return rc;
     nms_prep_kernel<<<ceil_div(n, 128), 128, 0, st>>>(w.keys, boxes, box_dim, n, w.prep, w.sgroup, w.seg);
     NRPN_LAUNCH_CHECK();
-    nms_mask_kernel<<<dim3(W, W), 64, 0, st>>>(w.prep, w.sgroup, n, W, box_dim, thr, ignore_group, w.mask);
-    NRPN_LAUNCH_CHECK();
-    nms_resolve_kernel<<<256, 256, 0, st>>>(w.mask, W, n, w.seg, ignore_group, w.keepbits);
-    NRPN_LAUNCH_CHECK();
+    if (n <= kNmsMatrixMax) {
+        nms_mask_kernel<<<dim3(W, W), 64, 0, st>>>(w.prep, w.sgroup, n, W, box_dim, thr, ignore_group, w.mask);
+        NRPN_LAUNCH_CHECK();
+        nms_resolve_kernel<<<256, 256, 0, st>>>(w.mask, W, n, w.seg, ignore_group, w.keepbits);
+        NRPN_LAUNCH_CHECK();
+    } else {
+        NRPN_CUDA_TRY(cudaMemsetAsync(w.removed0, 0, 64 * 8, st));
+        nms_state_init_kernel<<<1, 256, 0, st>>>(w.state);
+        NRPN_LAUNCH_CHECK();
+        for (int cb = 0; cb < n; cb += kChunk) {
+            const int cn = n - cb < kChunk ? n - cb : kChunk;
+            const int Wc = ceil_div(cn, 64);
+            nms_cross_kernel<<<ceil_div(cn * 32, 256), 256, 0, st>>>(w.prep, w.sgroup, box_dim, thr, ignore_group, cb, cn,
+                                                                     w.kept_pos, w.state, w.removed0);
+            NRPN_LAUNCH_CHECK();
+            nms_mask_kernel<<<dim3(Wc, Wc), 64, 0, st>>>(w.prep + (size_t)cb * kPrepFloats, w.sgroup + cb, cn, Wc, box_dim, thr,
+                                                        ignore_group, w.mask);
+            NRPN_LAUNCH_CHECK();
+            nms_chunk_resolve_kernel<<<1, 256, 0, st>>>(w.mask, Wc, cb, cn, w.sgroup, w.removed0, w.kept_pos, w.state, w.keepbits);
+            NRPN_LAUNCH_CHECK();
+        }
+    }
     nms_keys2_kernel<<<ceil_div(n_pad, 256), 256, 0, st>>>(w.keys, w.keepbits, n, n_pad, w.keys2);
     NRPN_LAUNCH_CHECK();
     rc = bitonic_sort_u64(w.keys2, n_pad, st);

@@ -254,6 +254,25 @@ static int orc_si_cmp(const void *pa, const void *pb)
     return (a->i > b->i) - (a->i < b->i);
 }
 
+/* Exactness-preserving shortcut for large inputs: 1 when the reference chain is certain to return an IoU of exactly 0
+ * (positive finite extents and either disjoint z ranges or bounding circles / boxes further apart than their radii plus a
+ * 0.1 % + 1e-3 margin). Used by orc_nms only; the IoU functions above never take it. */
+static int orc_surely_zero(const float *a, const float *b, int box_dim)
+{
+    for (int i = 0; i < box_dim; ++i) if (!isfinite(a[i]) || !isfinite(b[i])) return 0;
+    if (box_dim == 7) {
+        if (!(a[3] > 0 && a[4] > 0 && a[5] > 0 && b[3] > 0 && b[4] > 0 && b[5] > 0)) return 0;
+        double za0 = (double)a[2] - 0.5 * a[5], za1 = (double)a[2] + 0.5 * a[5];
+        double zb0 = (double)b[2] - 0.5 * b[5], zb1 = (double)b[2] + 0.5 * b[5];
+        if (za0 > zb1 * 1.0 + 1e-3 + 1e-6 * fabs(zb1) || zb0 > za1 + 1e-3 + 1e-6 * fabs(za1)) return 1;
+        double ra = 0.5 * sqrt((double)a[3] * a[3] + (double)a[4] * a[4]) * 1.001 + 1e-3;
+        double rb = 0.5 * sqrt((double)b[3] * b[3] + (double)b[4] * b[4]) * 1.001 + 1e-3;
+        double dx = (double)a[0] - b[0], dy = (double)a[1] - b[1];
+        return dx * dx + dy * dy > (ra + rb) * (ra + rb);
+    }
+    return 0;
+}
+
 /* nms(), utils.py:215-230. keep[] receives indices in pick order (score-descending). */
 int orc_nms(const float *boxes, int box_dim, const float *scores, int n, float thr, int64_t *keep)
 {
@@ -269,7 +288,9 @@ int orc_nms(const float *boxes, int box_dim, const float *scores, int n, float t
         keep[nk++] = i;
         for (int q = p + 1; q < n; ++q) {
             if (dead[q]) continue;
-            float iou = orc_iou3d(boxes + (long)i * box_dim, boxes + (long)ord[q].i * box_dim, box_dim);
+            const float *bi = boxes + (long)i * box_dim, *bq = boxes + (long)ord[q].i * box_dim;
+            if (thr >= 0.0f && orc_surely_zero(bi, bq, box_dim)) continue;     /* IoU is exactly 0 <= thr: kept */
+            float iou = orc_iou3d(bi, bq, box_dim);
             if (!(iou <= thr)) dead[q] = 1;      /* reference keeps iou <= thr, utils.py:228 */
         }
     }

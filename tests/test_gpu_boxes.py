@@ -114,6 +114,33 @@ def test_nms_vs_oracle_larger_and_edges(ops, G):
     np.testing.assert_array_equal(run_nms(ops, g["o700_boxes"], g["o700_scores"], None, 0.5), g["o700_keep_t5"])
 
 
+def test_nms_chunked_path_large_inputs(ops):
+    """BASELINE config 5 sizes (beyond the 32 768-box bit-matrix path): exact against the oracle at 40k-70k boxes,
+    size-independent properties at 300k (sorted by score, idempotent, kept set pairwise below the threshold)."""
+    rng = np.random.default_rng(17)
+    for n, dim, ext, ngroups in ((40000, 7, 200.0, 1), (50000, 7, 160.0, 4), (70000, 6, 260.0, 1)):
+        boxes = rand_obb(n, rng, ext, 3, 24) if dim == 7 else rand_aabb(n, rng, ext, 3, 28)
+        if dim == 7:
+            boxes[:, 2] = rng.random(n) * ext * 0.625
+        scores = rng.random(n).astype(np.float32)
+        groups = rng.integers(0, ngroups, n).astype(np.int32) if ngroups > 1 else None
+        got = run_nms(ops, boxes, scores, groups, 0.3)
+        ref = obox.batched_nms(boxes, scores, groups, 0.3) if groups is not None else obox.nms(boxes, scores, 0.3)
+        np.testing.assert_array_equal(got, ref)
+    n = 300000
+    boxes = rand_obb(n, rng, 256.0, 4, 48)
+    boxes[:, 2] = rng.random(n) * 160.0
+    scores = rng.random(n).astype(np.float32)
+    keep = run_nms(ops, boxes, scores, None, 0.3)
+    s = scores[keep]
+    assert 1000 < keep.shape[0] < n and np.all(s[:-1] >= s[1:]) and np.unique(keep).shape[0] == keep.shape[0]
+    again = run_nms(ops, boxes[keep], scores[keep], None, 0.3)
+    np.testing.assert_array_equal(again, np.arange(keep.shape[0]))                   # idempotent
+    sub = keep[:: max(1, keep.shape[0] // 1500)]
+    m = obox.iou_matrix(boxes[sub], boxes[sub]); np.fill_diagonal(m, 0)
+    assert np.nanmax(m) <= 0.3                                                        # survivors do not overlap beyond thr
+
+
 def _rpn_inputs_from_golden(r, rot):
     code = 8 if rot else 6
     A = 13
