@@ -142,6 +142,14 @@ int nrpn_pack_stem_input(const float *grid, int n, int x, int y, int z, void *pa
 /* F.max_pool3d(kernel 3, stride 2, padding 1) on (N,X,Y,Z,C) bf16, C % 8 == 0 (feature_extractor.py:219). */
 int nrpn_maxpool3d_k3s2(const void *in, int n, int x, int y, int z, int c, void *out, nrpn_stream_t stream);
 
+/* nn.MaxPool3d(kernel 2, stride 2, ceil_mode=True) (VGG stages, feature_extractor.py:347): output extent ceil(in/2). */
+int nrpn_maxpool3d_k2s2_ceil(const void *in, int n, int x, int y, int z, int c, void *out, nrpn_stream_t stream);
+
+/* Stride-1 stem packing for VGG_FPN on grids smaller than 160 (Conv3d(4,64,kernel 7,stride 1,padding 3),
+ * feature_extractor.py:341): fp32 NCDHW (4,X,Y,Z) -> bf16 (X, Y+1, Z, 64); row (x,yp,z) = the 7 z-neighbours of the two
+ * input rows y = yp-1, yp (56 channels + 8 zero), so that the conv is a 7x4-tap implicit GEMM with K = 64 per tap. */
+int nrpn_pack_stem_input_s1(const float *grid, int n, int x, int y, int z, void *packed, nrpn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * RPN post-processing (rpn.py:292-370, anchor.py:51-122, coder/AABB_coder.py:86-137,
  * coder/midpoint_offset_coder.py:160-223, utils.py:268-367) for ONE scene, fully on device.

@@ -65,6 +65,10 @@ _SIGNATURES = {
                                             ctypes.c_void_p, c_stream]),
     "nrpn_maxpool3d_k3s2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_void_p, c_stream]),
+    "nrpn_maxpool3d_k2s2_ceil": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_void_p, c_stream]),
+    "nrpn_pack_stem_input_s1": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_void_p, c_stream]),
     "nrpn_rpn_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(RpnDesc)]),
     "nrpn_rpn_proposals": (ctypes.c_int, [ctypes.POINTER(RpnDesc), c_f32p, c_f32p, c_f32p, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_size_t, c_stream]),

@@ -18,6 +18,7 @@
 //     span up to 4 pyramid levels sharing the same weights (the RPN head on P2..P5 is ONE launch per layer).
 //   - epilogue (fused): + shift (bias / folded BN), + residual (same shape, or nearest-upsampled coarser level
 //     for the FPN top-down path), ReLU, convert, 16-byte stores.
+#include <cstdlib>
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -381,9 +382,14 @@ static void choose_brick(int xo, int yo, int zo, int& bx, int& by, int& bz) {
 }
 
 // Split-K: layers with far fewer output tiles than SMs and a long reduction (late ResNet stages: 5x8x8 .. 10x16x16 voxels,
-// K up to 13 824) are latency bound on streaming their weights through a handful of CTAs. Spread the k-blocks of each
-// tile over `splits` CTAs (>= 4 k-blocks each, about one wave in total).
+// K up to 13 824) are latency bound on streaming their weights through a handful of CTAs. The kernel can spread the
+// k-blocks of each tile over `splits` CTAs (per-split fp32 slabs, last CTA reduces in a fixed order: bit-reproducible).
+// MEASURED on B200 (profiles/r01_layers_splitk_*.txt): the single-CTA slab reduction costs more than the split saves
+// (L3.c2 512->512 3^3 at 5x8x8: 0.101 ms unsplit, 0.175 ms with 24 splits), so it is OFF unless NRPN_SPLITK=1 is set;
+// batching several scenes per launch (bench.py --scenes-per-step) is what feeds these layers instead.
 static int choose_splits(int total_tiles, int kblocks, bool short_k) {
+    static const bool enabled = [] { const char* e = getenv("NRPN_SPLITK"); return e && e[0] == '1'; }();
+    if (!enabled) return 1;
     if (short_k || kblocks < 8 || total_tiles * 2 > num_sms()) return 1;
     int s = num_sms() / total_tiles;
     if (s > kblocks / 4) s = kblocks / 4;

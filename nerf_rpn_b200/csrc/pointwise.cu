@@ -73,6 +73,74 @@ __global__ void maxpool_k3s2_kernel(const __nv_bfloat16* __restrict__ in, int n,
     }
 }
 
+// nn.MaxPool3d(kernel 2, stride 2, ceil_mode=True) on channels-last bf16 (VGG stages, feature_extractor.py:347):
+// output extent ceil(in/2); the last window is clipped at the border.
+__global__ void maxpool_k2s2_ceil_kernel(const __nv_bfloat16* __restrict__ in, int n, int X, int Y, int Z, int C, int Xo, int Yo,
+                                         int Zo, __nv_bfloat16* __restrict__ out) {
+    const int cg = C >> 3;
+    const size_t total = (size_t)n * Xo * Yo * Zo * cg;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(t % cg); size_t v = t / cg;
+        const int k = (int)(v % Zo); v /= Zo;
+        const int j = (int)(v % Yo); v /= Yo;
+        const int i = (int)(v % Xo); const int b = (int)(v / Xo);
+        float m[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int x = 2 * i + dx; if (x >= X) continue;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const int y = 2 * j + dy; if (y >= Y) continue;
+#pragma unroll
+                for (int dz = 0; dz < 2; ++dz) {
+                    const int z = 2 * k + dz; if (z >= Z) continue;
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + ((((size_t)b * X + x) * Y + y) * Z + z) * C + g * 8));
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); m[2 * q] = fmaxf(m[2 * q], f.x); m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y); }
+                }
+            }
+        }
+        __nv_bfloat162 o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = __floats2bfloat162_rn(m[2 * q], m[2 * q + 1]);
+        *reinterpret_cast<uint4*>(out + ((((size_t)b * Xo + i) * Yo + j) * Zo + k) * C + g * 8) = *reinterpret_cast<uint4*>(o);
+    }
+}
+
+// Stride-1 stem packing (VGG_FPN for grids < 160: Conv3d(4,64,k=7,s=1,p=3), feature_extractor.py:341):
+// fp32 NCDHW (N,4,X,Y,Z) -> bf16 (N, X, Y+1, Z, 64).  Row (x, yp, z) holds, for the two input rows y = yp-1 and yp, the seven
+// z-neighbours z-3..z+3 of all 4 channels: channel = ((yy*7 + zz)*4 + c), 56 used + 8 zero.  The 7^3 conv becomes a
+// 7 (dx) x 4 (y pairs) tap implicit GEMM with K = 64 per tap (packing.pack_stem_s1_weight).
+__global__ void pack_stem_s1_kernel(const float* __restrict__ grid, int n, int X, int Y, int Z, __nv_bfloat16* __restrict__ out) {
+    const size_t total = (size_t)n * X * (Y + 1) * Z * 8;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int s = (int)(t & 7);
+        size_t v = t >> 3;
+        const int z = (int)(v % Z); v /= Z;
+        const int yp = (int)(v % (Y + 1)); v /= (Y + 1);
+        const int x = (int)(v % X); const int b = (int)(v / X);
+        float val[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ch = s * 8 + e;
+            float f = 0.f;
+            if (ch < 56) {
+                const int c = ch & 3, zz = (ch >> 2) % 7, yy = (ch >> 2) / 7;
+                const int y = yp - 1 + yy, zi = z + zz - 3;
+                if (y >= 0 && y < Y && zi >= 0 && zi < Z) f = grid[((((size_t)b * 4 + c) * X + x) * Y + y) * Z + zi];
+            }
+            val[e] = f;
+        }
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(val[2 * q], val[2 * q + 1]);
+        *reinterpret_cast<uint4*>(out + (t << 3)) = *reinterpret_cast<uint4*>(h);
+    }
+}
+
 static inline unsigned grid_for(size_t total, int block) {
     size_t g = (total + block - 1) / block;
     const size_t cap = (size_t)num_sms() * 16;
@@ -102,6 +170,24 @@ int nrpn_maxpool3d_k3s2(const void* in, int n, int x, int y, int z, int c, void*
     const size_t total = (size_t)n * Xo * Yo * Zo * (c / 8);
     maxpool_k3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(in), n, x, y, z, c, Xo, Yo, Zo, reinterpret_cast<__nv_bfloat16*>(out));
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+int nrpn_maxpool3d_k2s2_ceil(const void* in, int n, int x, int y, int z, int c, void* out, nrpn_stream_t stream) {
+    if (!in || !out || n < 1 || x < 1 || y < 1 || z < 1 || c < 8 || c % 8 != 0) return NRPN_ERR_INVALID;
+    const int Xo = (x + 1) / 2, Yo = (y + 1) / 2, Zo = (z + 1) / 2;
+    const size_t total = (size_t)n * Xo * Yo * Zo * (c / 8);
+    maxpool_k2s2_ceil_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(in), n, x, y, z, c, Xo, Yo, Zo, reinterpret_cast<__nv_bfloat16*>(out));
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+int nrpn_pack_stem_input_s1(const float* grid, int n, int x, int y, int z, void* packed, nrpn_stream_t stream) {
+    if (!grid || !packed || n < 1 || x < 1 || y < 1 || z < 1) return NRPN_ERR_INVALID;
+    const size_t total = (size_t)n * x * (y + 1) * z * 8;
+    pack_stem_s1_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, n, x, y, z, reinterpret_cast<__nv_bfloat16*>(packed));
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }

@@ -37,7 +37,9 @@ class _Conv:
             scale = scale.cpu()
         if shift is not None:
             shift = shift.cpu()
-        if stem:
+        if stem == "s1":
+            wp, taps = packing.pack_stem_s1_weight(weight, scale)
+        elif stem:
             wp, taps = packing.pack_stem_weight(weight, scale)
         else:
             wp, taps = packing.pack_conv_weight(weight, scale, cout_pad_to=cout_pad_to)
@@ -88,6 +90,28 @@ class RPNInferenceEngine:
     def _pack(self, device):
         bb, hd = self.backbone, self.head
         L = {}
+        self.kind = "vgg" if type(bb).__name__ == "VGG_FPN" else "resnet"
+        if self.kind == "vgg":
+            self._pack_vgg(L, device)
+        else:
+            self._pack_resnet(L, device)
+        if hd is None:
+            self.layers = L
+            self._plans.clear()
+            return
+        convs = [m for m in hd.conv if isinstance(m, torch.nn.Conv3d)]
+        L["head"] = [_Conv(m.weight, m.bias, relu=True, device=device) for m in convs]
+        # cls (A) and bbox (A*code) predictors fused into one 1x1x1 GEMM, zero-padded to 128 output channels
+        w = torch.cat([hd.cls_logits.weight, hd.bbox_pred.weight], 0)
+        b = torch.cat([hd.cls_logits.bias, hd.bbox_pred.bias], 0)
+        if w.shape[0] > 128:
+            raise ValueError("fused predictor supports at most 128 output channels")
+        L["pred"] = _Conv(w, b, device=device, cout_pad_to=128)
+        self.layers = L
+        self._plans.clear()
+
+    def _pack_resnet(self, L, device):
+        bb = self.backbone
         L["stem"] = _Conv(bb.conv1.weight, None, bb.bn1, relu=True, stem=True, device=device)
         blocks = []
         for stage in bb.layers:
@@ -105,20 +129,34 @@ class RPNInferenceEngine:
         L["blocks"] = blocks
         L["lat"] = [_Conv(m.weight, m.bias, device=device) for m in bb.latlayers]
         L["smooth"] = [_Conv(m.weight, m.bias, device=device) for m in bb.smooths]
-        if hd is None:
-            self.layers = L
-            self._plans.clear()
-            return
-        convs = [m for m in hd.conv if isinstance(m, torch.nn.Conv3d)]
-        L["head"] = [_Conv(m.weight, m.bias, relu=True, device=device) for m in convs]
-        # cls (A) and bbox (A*code) predictors fused into one 1x1x1 GEMM, zero-padded to 128 output channels
-        w = torch.cat([hd.cls_logits.weight, hd.bbox_pred.weight], 0)
-        b = torch.cat([hd.cls_logits.bias, hd.bbox_pred.bias], 0)
-        if w.shape[0] > 128:
-            raise ValueError("fused predictor supports at most 128 output channels")
-        L["pred"] = _Conv(w, b, device=device, cout_pad_to=128)
-        self.layers = L
-        self._plans.clear()
+
+    def _pack_vgg(self, L, device):
+        """VGG_FPN (feature_extractor.py:289-377): stem [conv7 (s2 + max-pool when input_size >= 160, else s1), BN, ReLU], then
+        four stages of (Conv3d 3^3 + BN + ReLU)* [+ MaxPool3d(2,2,ceil)] and the mmdet-style FPN neck (fpn.py:105-161)."""
+        bb = self.backbone
+        mods = list(bb.layers.children())
+        stem_conv, stem_bn = mods[0], mods[1]
+        strided = stem_conv.stride[0] == 2
+        L["vgg_strided"] = strided
+        L["stem"] = _Conv(stem_conv.weight, stem_conv.bias, stem_bn, relu=True, stem=True if strided else "s1", device=device)
+        stages = []
+        for grp in mods[-4:]:
+            seq, items = list(grp.children()), []
+            i = 0
+            while i < len(seq):
+                m = seq[i]
+                if isinstance(m, torch.nn.Conv3d):
+                    bn = seq[i + 1] if i + 1 < len(seq) and isinstance(seq[i + 1], torch.nn.BatchNorm3d) else None
+                    items.append(("conv", _Conv(m.weight, m.bias, bn, relu=True, device=device)))
+                    i += 2 if bn is not None else 1
+                elif isinstance(m, torch.nn.MaxPool3d):
+                    items.append(("pool", None)); i += 1
+                else:
+                    i += 1                      # ReLU is fused into the conv epilogue
+            stages.append(items)
+        L["vgg_stages"] = stages
+        L["lat"] = [_Conv(m.weight, m.bias, device=device) for m in bb.fpn_neck.lateral_convs]
+        L["fpn"] = [_Conv(m.weight, m.bias, device=device) for m in bb.fpn_neck.fpn_convs]
 
     # ---------------------------------------------------------------- plan
     def _get_plan(self, n, dims, device):
@@ -197,8 +235,53 @@ class _Plan:
             self.names[id(self._cur[-1])] = (f"{name} {layer.cin}->{layer.cout} taps={len(layer.taps)} s={layer.stride} "
                                              f"out={'+'.join('x'.join(map(str, d)) for d in out_dims)}", fl)
 
-        # static input + stem
         self.input = torch.empty((n, 4, X, Y, Z), dtype=torch.float32, device=device)
+        self._buf, self._conv = buf, conv
+        feats = self._build_vgg(L, n, dims, bf) if eng.kind == "vgg" else self._build_resnet(L, n, dims, bf)
+        self.features = [f for f, _ in feats]
+        self.feat_dims = [d for _, d in feats]
+
+        # head: all levels per launch
+        self.has_head = eng.head is not None
+        if not self.has_head:
+            return
+        self._cur = self.head_launches
+        cur = self.features
+        for layer in L["head"]:
+            nxt = [buf(d, 256) for d in self.feat_dims]
+            conv(layer, cur, nxt, self.feat_dims, self.feat_dims, name="head3x3x3")
+            cur = nxt
+        # cls|bbox predictor: two output sets (parity) so that the post-processing of scene i, which runs on a side
+        # stream, overlaps the backbone of scene i+1 without a buffer hazard
+        self.pred_sets = [[buf(d, 128, torch.float32) for d in self.feat_dims] for _ in range(2)]
+        self.pred_launch = []
+        for par in range(2):
+            self._cur = []
+            conv(L["pred"], cur, self.pred_sets[par], self.feat_dims, self.feat_dims, out_fp32=True,
+                 real=(256, 1, eng.A * (1 + eng.code)), name="pred(cls|bbox)")
+            self.pred_launch.append(self._cur[0])
+            if par == 1:
+                self.algorithmic_flops -= self.names[id(self._cur[0])][1] / n     # counted once per scene
+        self._cur = self.head_launches
+
+        # proposals
+        self.strides = [tuple(dims[k] // d[k] for k in range(3)) for d in self.feat_dims]
+        bd = 7 if eng.rotated else 6
+        self._out = [dict(boxes=torch.zeros((n, eng.post_n, bd), dtype=torch.float32, device=device),
+                          scores=torch.zeros((n, eng.post_n), dtype=torch.float32, device=device),
+                          levels=torch.zeros((n, eng.post_n), dtype=torch.float32, device=device),
+                          count=torch.zeros((n,), dtype=torch.int32, device=device)) for _ in range(2)]
+        self.side = torch.cuda.Stream(device=device)
+        self._ev_pred = [torch.cuda.Event() for _ in range(2)]
+        self._ev_done = [torch.cuda.Event() for _ in range(2)]
+        self._parity = 0
+        self._post_graph = [None, None]
+        self._build_post(None)
+
+    def _build_resnet(self, L, n, dims, bf):
+        eng, device = self.eng, self.device
+        buf, conv = self._buf, self._conv
+        X, Y, Z = dims
         d1 = _down(dims)
         self.packed = torch.empty((n, d1[0], d1[1], d1[2] + 1, 64), **bf)
         self.launches.append(lambda: ops.pack_stem_input(self.input, self.packed))
@@ -250,45 +333,63 @@ class _Plan:
             conv(sm, [q], [sq], [qd], [qd], name=f"smooth{i}")
             feats.append((sq, qd))
         feats.reverse()                                   # [P2, P3, P4, P5]
-        self.features = [f for f, _ in feats]
-        self.feat_dims = [d for _, d in feats]
+        return feats
 
-        # head: all levels per launch
-        self.has_head = eng.head is not None
-        if not self.has_head:
-            return
-        self._cur = self.head_launches
-        cur = self.features
-        for layer in L["head"]:
-            nxt = [buf(d, 256) for d in self.feat_dims]
-            conv(layer, cur, nxt, self.feat_dims, self.feat_dims, name="head3x3x3")
-            cur = nxt
-        # cls|bbox predictor: two output sets (parity) so that the post-processing of scene i, which runs on a side
-        # stream, overlaps the backbone of scene i+1 without a buffer hazard
-        self.pred_sets = [[buf(d, 128, torch.float32) for d in self.feat_dims] for _ in range(2)]
-        self.pred_launch = []
-        for par in range(2):
-            self._cur = []
-            conv(L["pred"], cur, self.pred_sets[par], self.feat_dims, self.feat_dims, out_fp32=True,
-                 real=(256, 1, eng.A * (1 + eng.code)), name="pred(cls|bbox)")
-            self.pred_launch.append(self._cur[0])
-            if par == 1:
-                self.algorithmic_flops -= self.names[id(self._cur[0])][1] / n     # counted once per scene
-        self._cur = self.head_launches
 
-        # proposals
-        self.strides = [tuple(dims[k] // d[k] for k in range(3)) for d in self.feat_dims]
-        bd = 7 if eng.rotated else 6
-        self._out = [dict(boxes=torch.zeros((n, eng.post_n, bd), dtype=torch.float32, device=device),
-                          scores=torch.zeros((n, eng.post_n), dtype=torch.float32, device=device),
-                          levels=torch.zeros((n, eng.post_n), dtype=torch.float32, device=device),
-                          count=torch.zeros((n,), dtype=torch.int32, device=device)) for _ in range(2)]
-        self.side = torch.cuda.Stream(device=device)
-        self._ev_pred = [torch.cuda.Event() for _ in range(2)]
-        self._ev_done = [torch.cuda.Event() for _ in range(2)]
-        self._parity = 0
-        self._post_graph = [None, None]
-        self._build_post(None)
+    def _build_vgg(self, L, n, dims, bf):
+        """VGG_FPN.forward (feature_extractor.py:362-377) + FPN.forward (fpn.py:134-161)."""
+        device = self.device
+        buf, conv = self._buf, self._conv
+        X, Y, Z = dims
+        if L["vgg_strided"]:
+            d1 = _down(dims)
+            self.packed = torch.empty((n, d1[0], d1[1], d1[2] + 1, 64), **bf)
+            self.launches.append(lambda: ops.pack_stem_input(self.input, self.packed))
+            self.names[id(self.launches[-1])] = ("pack_stem_input", 0.0)
+            c1 = buf(d1, 64)
+            conv(L["stem"], [self.packed], [c1], [(d1[0], d1[1], d1[2] + 1)], [d1], real=(4, 343, 64), name="stem7x7x7s2(s2d)")
+            xd = _down(d1)
+            x = buf(xd, 64)
+            self.launches.append(lambda a=c1, b=x: ops.maxpool3d_k3s2(a, b))
+            self.names[id(self.launches[-1])] = ("maxpool3d_k3s2", 0.0)
+        else:
+            self.packed = torch.empty((n, X, Y + 1, Z, 64), **bf)
+            self.launches.append(lambda: ops.pack_stem_input_s1(self.input, self.packed))
+            self.names[id(self.launches[-1])] = ("pack_stem_input_s1", 0.0)
+            xd = dims
+            x = buf(xd, 64)
+            conv(L["stem"], [self.packed], [x], [(X, Y + 1, Z)], [xd], real=(4, 343, 64), name="stem7x7x7s1(packed)")
+        stage_out = []
+        for si, items in enumerate(L["vgg_stages"]):
+            for kind, layer in items:
+                if kind == "conv":
+                    y = buf(xd, layer.cout)
+                    conv(layer, [x], [y], [xd], [xd], name=f"vgg{si}.conv3x3x3")
+                    x = y
+                else:
+                    od = tuple((v + 1) // 2 for v in xd)
+                    y = buf(od, x.shape[-1])
+                    self.launches.append(lambda a=x, b=y: ops.maxpool3d_k2s2_ceil(a, b))
+                    self.names[id(self.launches[-1])] = ("maxpool3d_k2s2_ceil", 0.0)
+                    x, xd = y, od
+            stage_out.append((x, xd))
+        # FPN: laterals top-down (in-place accumulation in the reference), then a 3^3 conv on every level
+        lat = [None] * 4
+        for i in range(3, -1, -1):
+            f, fd = stage_out[i]
+            q = buf(fd, 256)
+            if i == 3:
+                conv(L["lat"][i], [f], [q], [fd], [fd], name=f"fpn.lateral{i}")
+            else:
+                conv(L["lat"][i], [f], [q], [fd], [fd], res=[lat[i + 1][0]], res_dims=[lat[i + 1][1]], name=f"fpn.lateral{i}+up")
+            lat[i] = (q, fd)
+        feats = []
+        for i in range(4):
+            q, qd = lat[i]
+            o = buf(qd, 256)
+            conv(L["fpn"][i], [q], [o], [qd], [qd], name=f"fpn.conv{i}")
+            feats.append((o, qd))
+        return feats
 
     # results of the most recent run (valid once `done` has completed)
     @property

@@ -96,7 +96,78 @@ def _not_built(name):
     return _Missing
 
 
-VGG_FPN = _not_built("VGG_FPN")
+vgg_cfgs = {     # feature_extractor.py:278-286
+    "A": [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+    "B": [64, 64, "M", 128, 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+    "D": [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"],
+    "E": [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"],
+    "AF": [64, 128, "F", 256, 256, "M", "F", 512, 512, "M", "F", 512, 512, "M", "F"],
+    "DF": [64, 64, 128, 128, "F", 256, 256, 256, "M", "F", 512, 512, 512, "M", "F", 512, 512, 512, "M", "F"],
+    "EF": [64, 64, 128, 128, "F", 256, 256, 256, 256, "M", "F", 512, 512, 512, 512, "M", "F", 512, 512, 512, 512, "M", "F"],
+}
+
+
+class VGG_FPN(nn.Module):
+    """VGG-FPN backbone (feature_extractor.py:289-377), cfgs "AF" / "DF" / "EF" (run_rpn.py:277-280 builds AF and EF):
+    stem Conv3d(4,64,7) [stride 2 + max-pool when input_size >= 160, else stride 1] + BN + ReLU, four stages of
+    (Conv3d 3^3 + BN + ReLU)* [+ MaxPool3d(2,2,ceil_mode=True)], FPN neck on the four stage outputs."""
+
+    def __init__(self, cfg: str = "AF", in_channels: int = 4, batch_norm: bool = True, input_size: int = 256,
+                 conv_at_start: bool = False):
+        super().__init__()
+        if conv_at_start or in_channels != 4 or not cfg.endswith("F"):
+            raise NotImplementedError("the B200 engine implements VGG_FPN(cfg in {AF,DF,EF}, 4, batch_norm, input_size)")
+        from .fpn import FPN
+        self.out_channels = 256
+        self.layers = self.make_layers(vgg_cfgs[cfg], in_channels, batch_norm, input_size)
+        stage_channels = [[v for v in grp if isinstance(v, int)][-1] for grp in self._groups(vgg_cfgs[cfg])]
+        if stage_channels != [128, 256, 512, 512]:
+            raise NotImplementedError("FPN input widths are fixed to [128,256,512,512] in the reference (feature_extractor.py:304)")
+        self.fpn_neck = FPN([128, 256, 512, 512], self.out_channels, 4)
+        self.conv_at_start = conv_at_start
+        self.starting_layers = None
+        self.ds_layers = None
+        self._engine = None
+
+    @staticmethod
+    def _groups(cfg):
+        out, cur = [], []
+        for v in cfg:
+            if v == "F":
+                out.append(cur); cur = []
+            else:
+                cur.append(v)
+        return out
+
+    def make_layers(self, cfg, in_channels, batch_norm, input_size) -> nn.Sequential:
+        layers, curr = [], []
+        if input_size >= 160:
+            layers += [nn.Conv3d(in_channels, 64, kernel_size=7, stride=2, padding=3), nn.BatchNorm3d(64), nn.ReLU(inplace=True),
+                       nn.MaxPool3d(kernel_size=3, stride=2, padding=1)]
+        else:
+            layers += [nn.Conv3d(in_channels, 64, kernel_size=7, stride=1, padding=3), nn.BatchNorm3d(64), nn.ReLU(inplace=True)]
+        c = 64
+        for v in cfg:
+            if v == "M":
+                curr += [nn.MaxPool3d(kernel_size=2, stride=2, ceil_mode=True)]
+            elif v == "F":
+                layers += [nn.Sequential(*curr)]
+                curr = []
+            else:
+                conv3d = nn.Conv3d(c, v, kernel_size=3, padding=1)
+                curr += [conv3d, nn.BatchNorm3d(v), nn.ReLU(inplace=True)] if batch_norm else [conv3d, nn.ReLU(inplace=True)]
+                c = v
+        return nn.Sequential(*layers)
+
+    def forward(self, X):
+        """(N,4,W,L,H) fp32 CUDA -> tuple of 4 (N,256,w,l,h) fp32 feature maps (channels_last_3d strides)."""
+        from ..engine import RPNInferenceEngine
+        if self._engine is None:
+            self._engine = RPNInferenceEngine(self)
+        plan = self._engine.forward_device(X.contiguous())
+        return tuple(f.permute(0, 4, 1, 2, 3).float() for f in plan.features)
+
+
 SwinTransformer_FPN = _not_built("SwinTransformer_FPN")
 ResNet_FPN_64 = _not_built("ResNet_FPN_64")
 ResNetSimplified_64 = _not_built("ResNetSimplified_64")

@@ -181,6 +181,28 @@ def maxpool3d_k3s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
     return out
 
 
+def maxpool3d_k2s2_ceil(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,X,Y,Z,C) bf16 channels-last -> MaxPool3d(2, 2, ceil_mode=True)."""
+    x = _req(x, torch.bfloat16, "x")
+    n, X, Y, Z, C = x.shape
+    if out is None:
+        out = torch.empty((n, (X + 1) // 2, (Y + 1) // 2, (Z + 1) // 2, C), dtype=torch.bfloat16, device=x.device)
+    check(lib().nrpn_maxpool3d_k2s2_ceil(_ptr(x), n, X, Y, Z, C, _ptr(out), _stream()), "maxpool3d_k2s2_ceil")
+    return out
+
+
+def pack_stem_input_s1(grid: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,4,X,Y,Z) fp32 -> (N, X, Y+1, Z, 64) bf16 (stride-1 7^3 stem)."""
+    grid = _req(grid, torch.float32, "grid")
+    n, c, x, y, z = grid.shape
+    if c != 4:
+        raise ValueError("stem packing expects 4 input channels (RGB + density)")
+    if out is None:
+        out = torch.empty((n, x, y + 1, z, 64), dtype=torch.bfloat16, device=grid.device)
+    check(lib().nrpn_pack_stem_input_s1(_ptr(grid), n, x, y, z, _ptr(out), _stream()), "pack_stem_input_s1")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ rpn post
 def make_rpn_desc(preds: List[torch.Tensor], grids, strides, cells, num_anchors: int, rotated: bool, pre_nms_top_n: int,
                   post_nms_top_n: int, nms_thresh: float, score_thresh: float, min_size: float, mesh, valid=None) -> RpnDesc:

@@ -87,3 +87,31 @@ def pack_stem_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None):
                 mats.append(m)
     out = torch.stack(mats, 0)                                  # (32, 64, 64)
     return out.to(torch.bfloat16).contiguous(), taps
+
+
+def pack_stem_s1_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None):
+    """Stride-1 stem Conv3d(4, 64, kernel 7, padding 3) (VGG_FPN on grids < 160, feature_extractor.py:341) on the packed input
+    of csrc/pointwise.cu:pack_stem_s1_kernel: 7 (dx) x 4 (y pairs) taps, K = 64 per tap.
+
+    Packed row (x, yp, z) = rows y = yp-1 and yp, each with its 7 z-neighbours: channel = (yy*7 + zz)*4 + c.
+    Output (x,y,z) reads input rows y-3..y+3 = pairs (y+dyp, y+dyp+1) for dyp in {-3,-1,1,3}; pair (a, a+1) lives in packed row
+    yp = a+1, so the tap offset in packed coordinates is dyp + 1 (the packed Y extent is Y+1)."""
+    cout, cin, k, _, _ = w.shape
+    assert (cin, k) == (4, 7)
+    w = w.detach().float()
+    if scale is not None:
+        w = w * scale.view(-1, 1, 1, 1, 1).to(w)
+    taps, mats = [], []
+    for dx in range(-3, 4):
+        for dyp in (-3, -1, 1, 3):
+            m = torch.zeros((cout, 64), dtype=torch.float32, device=w.device)
+            for yy in (0, 1):
+                ky = dyp + yy + 3
+                if not 0 <= ky < 7:
+                    continue
+                for zz in range(7):
+                    ch = (yy * 7 + zz) * 4
+                    m[:, ch:ch + 4] = w[:, :, dx + 3, ky, zz]
+            taps.append((dx, dyp + 1, 0))
+            mats.append(m)
+    return torch.stack(mats, 0).to(torch.bfloat16).contiguous(), taps

@@ -91,3 +91,32 @@ def full_forward(sd, hsd, x, cells, rotated, pre_nms_top_n=2500, post_nms_top_n=
     strides = [tuple(mesh[i] // g[i] for i in range(3)) for g in grids]
     b, s, lv = rp.rpn_proposals(lg, dl, grids, strides, cells, mesh, rotated, pre_nms_top_n, post_nms_top_n, nms_thresh, score_thresh)
     return feats, (b, s, lv)
+
+
+@torch.no_grad()
+def vgg_fpn_forward(sd, x):
+    """VGG_FPN.forward (nerf_rpn/model/feature_extractor.py:362-377, make_layers :331-360) + FPN.forward (fpn.py:134-161),
+    functional fp32, keyed by the reference's state_dict names (layers.{i}[.{j}].*, fpn_neck.{lateral,fpn}_convs.{i}.*)."""
+    strided = "layers.3.0.weight" not in sd and any(k.startswith("layers.4.") for k in sd)       # stem has a max-pool at index 3
+    h = F.conv3d(x, sd["layers.0.weight"], sd["layers.0.bias"], stride=2 if strided else 1, padding=3)
+    h = F.relu(_bn(h, sd, "layers.1"))
+    if strided:
+        h = F.max_pool3d(h, kernel_size=3, stride=2, padding=1)
+    first = 4 if strided else 3
+    groups = sorted({int(k.split(".")[1]) for k in sd if k.startswith("layers.") and int(k.split(".")[1]) >= first})
+    feats = []
+    for gi in groups:
+        idxs = sorted({int(k.split(".")[2]) for k in sd if k.startswith(f"layers.{gi}.")})
+        convs = [j for j in idxs if f"layers.{gi}.{j}.weight" in sd and sd[f"layers.{gi}.{j}.weight"].dim() == 5]
+        for j in convs:
+            h = F.conv3d(h, sd[f"layers.{gi}.{j}.weight"], sd[f"layers.{gi}.{j}.bias"], padding=1)
+            if f"layers.{gi}.{j + 1}.running_mean" in sd:
+                h = _bn(h, sd, f"layers.{gi}.{j + 1}")
+            h = F.relu(h)
+        if gi != groups[0]:                          # every stage but the first ends with MaxPool3d(2, 2, ceil_mode=True) in the *F cfgs
+            h = F.max_pool3d(h, kernel_size=2, stride=2, ceil_mode=True)
+        feats.append(h)
+    lat = [F.conv3d(f, sd[f"fpn_neck.lateral_convs.{i}.weight"], sd[f"fpn_neck.lateral_convs.{i}.bias"]) for i, f in enumerate(feats)]
+    for i in range(len(lat) - 1, 0, -1):
+        lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], mode="nearest")
+    return [F.conv3d(l, sd[f"fpn_neck.fpn_convs.{i}.weight"], sd[f"fpn_neck.fpn_convs.{i}.bias"], padding=1) for i, l in enumerate(lat)]

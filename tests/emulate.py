@@ -37,3 +37,17 @@ def emulate_conv(x, w_packed, taps, shift, out_dims, stride=1, relu=False, res=N
     if relu:
         out = out.clamp_min(0)
     return out
+
+
+def emulate_pack_stem_s1(grid: torch.Tensor) -> torch.Tensor:
+    """(N,4,X,Y,Z) -> (N,X,Y+1,Z,64) with the layout of csrc/pointwise.cu:pack_stem_s1_kernel."""
+    n, c, X, Y, Z = grid.shape
+    g = F.pad(grid, (3, 3, 1, 1))                       # z by 3, y by 1 on both sides
+    out = torch.zeros((n, X, Y + 1, Z, 64), dtype=grid.dtype, device=grid.device)
+    for yy in range(2):
+        for zz in range(7):
+            # row yp holds input y = yp - 1 + yy  -> padded index yp + yy ; z neighbour z + zz - 3 -> padded z + zz
+            sl = g[:, :, :, yy: yy + Y + 1, zz: zz + Z]                 # (n, c, X, Y+1, Z)
+            ch = (yy * 7 + zz) * 4
+            out[..., ch:ch + 4] = sl.permute(0, 2, 3, 4, 1)
+    return out

@@ -33,3 +33,27 @@ def build_small_model(ns, rotated, golden):
 
 def golden_input(golden):
     return torch.from_numpy(golden["grid"]).permute(3, 0, 1, 2).contiguous()       # (4,W,L,H) like datasets.py:55-57
+
+
+def build_vgg_small(ns, golden):
+    """Config-1 model (VGG19 'EF' + FPN + anchor head, 32^3 grid) with the weights tools/make_golden.py gave the reference."""
+    torch.manual_seed(0)
+    backbone = ns.VGG_FPN("EF", 4, True, 32)
+    ag = ns.AnchorGenerator3D(ANCHOR_SIZES, ASPECT)
+    head = ns.RPNHead(256, ag.num_anchors_per_location()[0], 4, rotate=False)
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        torch.randn(head.cls_logits.weight.shape, generator=g); torch.randn(head.bbox_pred.weight.shape, generator=g)   # same draws
+        for m in backbone.modules():
+            if isinstance(m, torch.nn.BatchNorm3d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.5 + 0.75)
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+        head.cls_logits.weight.copy_(torch.from_numpy(golden["cls_w"]).view_as(head.cls_logits.weight))
+        head.bbox_pred.weight.copy_(torch.from_numpy(golden["bbox_w"]).view_as(head.bbox_pred.weight))
+    stem = list(backbone.layers.children())[0]
+    assert abs(stem.weight.double().sum().item() - float(golden["stem_sum"])) < 1e-9, "seeded VGG weights differ"
+    assert abs(backbone.fpn_neck.fpn_convs[3].weight.double().sum().item() - float(golden["fpn_sum"])) < 1e-9
+    assert abs(head.conv[0].weight.double().sum().item() - float(golden["head_sum"])) < 1e-9
+    return backbone, ag, head

@@ -30,6 +30,7 @@ def _ns():
     NS.Bottleneck = feature_extractor.Bottleneck
     NS.AnchorGenerator3D = anchor.AnchorGenerator3D
     NS.RPNHead = anchor.RPNHead
+    NS.VGG_FPN = feature_extractor.VGG_FPN
     return NS
 
 
@@ -141,3 +142,35 @@ def test_full_size_scene_runs_and_matches_oracle_post():
     assert s.shape[0] > 0 and np.all(s[:-1] >= s[1:])
     print(f"full-size: {s.shape[0]} proposals, {plan.algorithmic_flops / 1e12:.3f} TFLOP/scene algorithmic")
     assert abs(plan.algorithmic_flops / 1e12 - 3.913) < 0.05
+
+
+def test_config1_vgg19_fpn_small_grid(golden_dir):
+    """BASELINE config 1: single 32x32x32 grid, VGG19 ("EF") + FPN backbone, anchor head -- against the reference's golden
+    outputs (the reference ran this exact configuration on CPU, tools/make_golden.py)."""
+    from nerf_rpn_b200.model.nerf_rpn import NeRFRegionProposalNetwork
+    g = np.load(os.path.join(golden_dir, "vgg_small_aabb.npz"))
+    backbone, ag, head = recipes.build_vgg_small(_ns(), g)
+    model = NeRFRegionProposalNetwork(backbone, ag, head, rpn_pre_nms_top_n_test=2500, rpn_post_nms_top_n_test=2500,
+                                      rpn_nms_thresh=0.3, rpn_score_thresh=0.0).cuda().eval()
+    x = recipes.golden_input(g).cuda()
+    with torch.no_grad():
+        (features, proposals, level_index), _, scores = model([x])
+        standalone = backbone(x[None])                                   # the backbone module is also callable on its own
+    assert [tuple(f.shape) for f in features] == [(1, 256, 32, 32, 32), (1, 256, 16, 16, 16), (1, 256, 8, 8, 8), (1, 256, 4, 4, 4)]
+    for i, f in enumerate(features):
+        st = int(g["fstride"][i])
+        ref = torch.from_numpy(g[f"feat{i}"].astype(np.float32)).cuda()
+        rel = ((f[0][:, ::st, ::st, ::st] - ref).norm() / ref.norm()).item()
+        print(f"vgg config 1: feature level {i} norm-wise rel err {rel:.3e}")
+        assert rel < 2e-2
+        assert torch.equal(standalone[i], f)
+    eng = model.engine()
+    plan = eng._plans[next(iter(eng._plans))]
+    ob, os_, ol = oracle_post_from_engine(plan, eng)
+    np.testing.assert_array_equal(bits(proposals[0].cpu().numpy()), bits(ob))
+    refp, refs = g["proposals"], g["scores"]
+    ours = proposals[0].cpu().numpy()
+    top = np.argsort(-refs, kind="stable")[:50]
+    hit = (obox.iou_matrix(refp[top], ours).max(axis=1) >= 0.7).mean()
+    print(f"vgg config 1: {ours.shape[0]} proposals (reference {refp.shape[0]}); top-50 matched at IoU>=0.7: {hit:.2f}")
+    assert hit >= 0.85

@@ -17,6 +17,7 @@ class NS:
     Bottleneck = feature_extractor.Bottleneck
     AnchorGenerator3D = anchor.AnchorGenerator3D
     RPNHead = anchor.RPNHead
+    VGG_FPN = feature_extractor.VGG_FPN
 
 
 @pytest.mark.parametrize("name,rot", [("rpn_small_aabb", False), ("rpn_small_obb", True)])
@@ -33,6 +34,34 @@ def test_net_oracle_matches_reference(golden_dir, name, rot):
     logits, deltas = onet.head_forward(head.state_dict(), feats)
     for i in range(4):
         np.testing.assert_allclose(logits[i][0].numpy(), g[f"logits{i}"], rtol=1e-3, atol=2e-3)
+    assert b.shape == g["proposals"].shape
+    np.testing.assert_allclose(b, g["proposals"], rtol=1e-3, atol=1e-2)
+    np.testing.assert_array_equal(lv, g["level_index"])
+
+
+def test_vgg_fpn_oracle_matches_reference(golden_dir):
+    """BASELINE config 1 (VGG19-FPN + anchor head on a 32^3 grid): module mirror reproduces the reference's seeded weights
+    and state_dict keys (135 backbone tensors); the functional oracle reproduces its features / logits / proposals."""
+    from oracle import rpn_post as rp
+    g = np.load(os.path.join(golden_dir, "vgg_small_aabb.npz"))
+    backbone, ag, head = recipes.build_vgg_small(NS, g)
+    sd = backbone.state_dict()
+    assert len(sd) == 135 and "fpn_neck.lateral_convs.0.weight" in sd and "layers.3.0.weight" in sd
+    x = recipes.golden_input(g)[None]
+    feats = onet.vgg_fpn_forward(sd, x)
+    for i, f in enumerate(feats):
+        st = int(g["fstride"][i])
+        ref = torch.from_numpy(g[f"feat{i}"].astype(np.float32))
+        got = f[0][:, ::st, ::st, ::st]
+        assert ((got - ref).norm() / ref.norm()).item() < 1e-3
+    logits, deltas = onet.head_forward(head.state_dict(), feats)
+    for i in range(4):
+        st = int(g["lstride"][i])
+        np.testing.assert_allclose(logits[i][0][:, ::st, ::st, ::st].numpy(), g[f"logits{i}"], rtol=1e-3, atol=2e-3)
+    lg, dl = onet.flatten_predictions(logits, deltas, 13, 6)
+    grids = [tuple(f.shape[-3:]) for f in feats]
+    strides = [tuple(32 // gr[k] for k in range(3)) for gr in grids]
+    b, s_, lv = rp.rpn_proposals(lg, dl, grids, strides, ag.cell_anchors_np(), (32, 32, 32), False)
     assert b.shape == g["proposals"].shape
     np.testing.assert_allclose(b, g["proposals"], rtol=1e-3, atol=1e-2)
     np.testing.assert_array_equal(lv, g["level_index"])

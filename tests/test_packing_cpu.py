@@ -46,3 +46,15 @@ def test_bn_folding():
     x = torch.randn(2, 8, 3, 3, 3)
     s, b = packing.fold_bn(bn)
     torch.testing.assert_close(x * s.view(1, -1, 1, 1, 1) + b.view(1, -1, 1, 1, 1), bn(x), rtol=1e-5, atol=1e-5)
+
+
+def test_stem_stride1_packing_equals_conv7():
+    from tests.emulate import emulate_pack_stem_s1
+    torch.manual_seed(3)
+    x = torch.randn(1, 4, 9, 8, 10)
+    w = torch.randn(64, 4, 7, 7, 7) * 0.05
+    wp, taps = packing.pack_stem_s1_weight(w)
+    assert wp.shape == (28, 64, 64)
+    got = emulate_conv(emulate_pack_stem_s1(x), wp.float(), taps, torch.zeros(64), (9, 8, 10))
+    ref = F.conv3d(x, w.to(torch.bfloat16).float(), padding=3).permute(0, 2, 3, 4, 1)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)

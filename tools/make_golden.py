@@ -25,7 +25,7 @@ torch.cuda.is_available = lambda: False
 
 from model.anchor import AnchorGenerator3D, RPNHead  # noqa: E402
 from model.coder import AABBCoder, MidpointOffsetCoder  # noqa: E402
-from model.feature_extractor import Bottleneck, ResNet_FPN_256  # noqa: E402
+from model.feature_extractor import Bottleneck, ResNet_FPN_256, VGG_FPN  # noqa: E402
 from model.nerf_rpn import NeRFRegionProposalNetwork  # noqa: E402
 from model.rotated_iou.box_intersection_2d import (box_in_box_th, box_intersection_th,  # noqa: E402
                                                    build_vertices)
@@ -203,7 +203,56 @@ def gen_rpn_small():
         print(name, "proposals", tuple(proposals[0].shape), "score range", float(scores[0].min()), float(scores[0].max()), chk)
 
 
+def gen_vgg_small():
+    """BASELINE config 1: one 32x32x32 grid, VGG19 ("EF") + FPN + anchor head (AABB), reference forward on CPU."""
+    torch.manual_seed(0)
+    backbone = VGG_FPN("EF", 4, True, 32)
+    ag = AnchorGenerator3D(ANCHOR_SIZES, ASPECT)
+    head = RPNHead(256, ag.num_anchors_per_location()[0], 4, rotate=False)
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        head.cls_logits.weight.copy_(torch.randn(head.cls_logits.weight.shape, generator=g) * 0.2)
+        head.bbox_pred.weight.copy_(torch.randn(head.bbox_pred.weight.shape, generator=g) * 0.05)
+        for m in backbone.modules():
+            if isinstance(m, torch.nn.BatchNorm3d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.5 + 0.75)
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    gi = torch.Generator().manual_seed(1000)
+    grid = torch.rand(32, 32, 32, 4, generator=gi)
+    x = grid.permute(3, 0, 1, 2).contiguous()
+    backbone.eval(); head.eval()
+    with torch.no_grad():
+        lg, dl = head(list(backbone(x[None])))
+        head.cls_logits.weight.mul_(2.0 / torch.cat([t.flatten() for t in lg]).std().item())
+        head.bbox_pred.weight.mul_(0.3 / torch.cat([t.flatten() for t in dl]).std().item())
+    model = NeRFRegionProposalNetwork(backbone, ag, head, rpn_pre_nms_top_n_test=2500, rpn_post_nms_top_n_test=2500,
+                                      rpn_nms_thresh=0.3, rpn_score_thresh=0.0, rotated_bbox=False)
+    model.eval()
+    with torch.no_grad():
+        (features, proposals, level_index), _, scores = model([x])
+        logits, deltas = head(features)
+    out = dict(grid=grid.numpy(), proposals=proposals[0].numpy(), scores=scores[0].numpy(), level_index=level_index[0].numpy(),
+               stem_sum=np.float64(list(backbone.layers.children())[0].weight.double().sum().item()),
+               fpn_sum=np.float64(backbone.fpn_neck.fpn_convs[3].weight.double().sum().item()),
+               head_sum=np.float64(head.conv[0].weight.double().sum().item()),
+               cls_w=head.cls_logits.weight.detach().numpy().reshape(13, 256),
+               bbox_w=head.bbox_pred.weight.detach().numpy().reshape(-1, 256))
+    # sub-sampled to keep the fixture small: stride 4 on the 32^3 level, 2 on the 16^3 level (features); logits stride 2 / 1
+    fstride, lstride = (4, 2, 1, 1), (2, 1, 1, 1)
+    for i in range(4):
+        fs, ls = fstride[i], lstride[i]
+        out[f"feat{i}"] = features[i][0][:, ::fs, ::fs, ::fs].numpy().astype(np.float16)
+        out[f"logits{i}"] = logits[i][0][:, ::ls, ::ls, ::ls].numpy()
+    out["fstride"], out["lstride"] = np.array(fstride), np.array(lstride)
+    np.savez_compressed(os.path.join(OUT, "vgg_small_aabb.npz"), **out)
+    print("vgg_small_aabb.npz proposals", tuple(proposals[0].shape), [tuple(f.shape) for f in features], len(backbone.state_dict()))
+
+
 if __name__ == "__main__":
+    gen_vgg_small()
+    sys.exit(0) if "--vgg-only" in sys.argv else None
     gen_iou()
     gen_sort_vertices()
     gen_nms()
