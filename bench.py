@@ -36,11 +36,11 @@ FLOPS_PER_SCENE = 3.913e12        # conv FLOPs (2*MAC) of the re
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="exploration runs only: omit the ~40 s CPU port timing")
-    ap.add_argument("--scenes-per-step", type=int, default=int(os.environ.get("NRPN_SCENES_PER_STEP", "1")),
+    ap.add_argument("--scenes-per-step", type=int, default=int(os.environ.get("NRPN_SCENES_PER_STEP", "4")),
                     help="scenes per rank per step (one engine launch); weights are read once per step")
     return ap.parse_args()
 

@@ -150,6 +150,18 @@ int nrpn_maxpool3d_k2s2_ceil(const void *in, int n, int x, int y, int z, int c, 
  * input rows y = yp-1, yp (56 channels + 8 zero), so that the conv is a 7x4-tap implicit GEMM with K = 64 per tap. */
 int nrpn_pack_stem_input_s1(const float *grid, int n, int x, int y, int z, void *packed, nrpn_stream_t stream);
 
+/* GroupNorm(32 groups, 256 channels) + optional ReLU, in place, on up to NRPN_CONV_MAX_LEVELS channels-last bf16 tensors
+ * (N, voxels, 256) that share gamma/beta (FCOS towers: Conv3d -> GroupNorm -> ReLU, fcos/fcos.py:43-69).  Statistics are
+ * per (sample, level, group); reductions run in a fixed order (bit-reproducible). */
+typedef struct {
+    void *x;          /* bf16 (N, voxels, 256), normalised in place */
+    int32_t voxels;
+} nrpn_gn_level;
+size_t nrpn_groupnorm_workspace_bytes(int n_levels, int n);
+int nrpn_groupnorm_relu(const nrpn_gn_level *levels /*host*/, int n_levels, int n, int c, int groups, const float *gamma,
+                        const float *beta, float eps, int relu, void *workspace, size_t workspace_bytes,
+                        nrpn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * RPN post-processing (rpn.py:292-370, anchor.py:51-122, coder/AABB_coder.py:86-137,
  * coder/midpoint_offset_coder.py:160-223, utils.py:268-367) for ONE scene, fully on device.
@@ -181,6 +193,38 @@ size_t nrpn_rpn_workspace_bytes(const nrpn_rpn_desc *desc /*host*/);
  * (the reference returns the level id as a float column), count (1) i32. */
 int nrpn_rpn_proposals(const nrpn_rpn_desc *desc /*host*/, float *boxes, float *scores, float *levels,
                        int32_t *count, void *workspace, size_t workspace_bytes, nrpn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FCOS (anchor-free) post-processing for ONE scene (fcos/fcos.py:116-126,221-250; fcos/inference.py:48-195;
+ * fcos/utils.py:12-61), fully on device: head transform (Scale, ReLU, x stride), sigmoid, candidate selection, centerness
+ * weighting, per-level top-k, AABB / midpoint-offset OBB decode, clip, min-size, one NMS over all levels, k-th value cap.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float *cls;    /* (X*Y*Z, ld_cls) fp32 rows, channel 0 = raw class logit */
+    const float *reg;    /* (X*Y*Z, ld_reg) fp32 rows, channels [0,6|8) = raw distances (+ alpha, beta), next = raw centerness */
+    int32_t ld_cls, ld_reg;
+    int32_t gx, gy, gz;
+    int32_t stride;      /* FPN stride of the level: locations = idx*stride + stride/2 */
+    float scale;         /* the level's learnable Scale */
+} nrpn_fcos_level;
+
+typedef struct {
+    int32_t n_levels;
+    nrpn_fcos_level level[NRPN_RPN_MAX_LEVELS];
+    int32_t use_obb;
+    int32_t pre_nms_top_n, post_nms_top_n;
+    float pre_nms_thresh, nms_thresh, min_size;
+    int32_t grid_size[3];     /* the scene's own extent (clipping, padding mask) */
+    int32_t padded;           /* 1: batch > 1, mask locations outside grid_size (fcos.py:252-266) */
+} nrpn_fcos_desc;
+
+/* capacity (rows) the outputs must have: sum over levels of min(pre_nms_top_n, locations) -- the k-th value cut keeps ties,
+ * so more than post_nms_top_n rows can come back. */
+int nrpn_fcos_max_proposals(const nrpn_fcos_desc *desc /*host*/);
+size_t nrpn_fcos_workspace_bytes(const nrpn_fcos_desc *desc /*host*/);
+/* boxes (cap, 1+6|7) f32 with the level id in column 0, scores (cap) f32, count (1) i32. */
+int nrpn_fcos_proposals(const nrpn_fcos_desc *desc /*host*/, float *boxes, float *scores, int32_t *count, void *workspace,
+                        size_t workspace_bytes, nrpn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,23 @@ class RpnDesc(ctypes.Structure):
                 ("valid", ctypes.c_int32 * 3)]
 
 
+class GnLevel(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_void_p), ("voxels", ctypes.c_int32)]
+
+
+class FcosLevel(ctypes.Structure):
+    _fields_ = [("cls", ctypes.c_void_p), ("reg", ctypes.c_void_p), ("ld_cls", ctypes.c_int32), ("ld_reg", ctypes.c_int32),
+                ("gx", ctypes.c_int32), ("gy", ctypes.c_int32), ("gz", ctypes.c_int32), ("stride", ctypes.c_int32),
+                ("scale", ctypes.c_float)]
+
+
+class FcosDesc(ctypes.Structure):
+    _fields_ = [("n_levels", ctypes.c_int32), ("level", FcosLevel * MAX_LEVELS), ("use_obb", ctypes.c_int32),
+                ("pre_nms_top_n", ctypes.c_int32), ("post_nms_top_n", ctypes.c_int32), ("pre_nms_thresh", ctypes.c_float),
+                ("nms_thresh", ctypes.c_float), ("min_size", ctypes.c_float), ("grid_size", ctypes.c_int32 * 3),
+                ("padded", ctypes.c_int32)]
+
+
 _SIGNATURES = {
     "nrpn_version": (ctypes.c_int, []),
     "nrpn_status_string": (ctypes.c_char_p, [ctypes.c_int]),
@@ -69,6 +86,13 @@ _SIGNATURES = {
                                                 ctypes.c_int, ctypes.c_void_p, c_stream]),
     "nrpn_pack_stem_input_s1": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_void_p, c_stream]),
+    "nrpn_groupnorm_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "nrpn_groupnorm_relu": (ctypes.c_int, [ctypes.POINTER(GnLevel), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           c_f32p, c_f32p, ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, c_stream]),
+    "nrpn_fcos_max_proposals": (ctypes.c_int, [ctypes.POINTER(FcosDesc)]),
+    "nrpn_fcos_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(FcosDesc)]),
+    "nrpn_fcos_proposals": (ctypes.c_int, [ctypes.POINTER(FcosDesc), c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_size_t, c_stream]),
     "nrpn_rpn_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(RpnDesc)]),
     "nrpn_rpn_proposals": (ctypes.c_int, [ctypes.POINTER(RpnDesc), c_f32p, c_f32p, c_f32p, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_size_t, c_stream]),

@@ -8,14 +8,10 @@
 // with oracle/rpn_post.py (torch.topk leaves ties unspecified).
 #include "rpn_decode.cuh"
 #include "nms_internal.cuh"
+#include "topk.cuh"
 
 namespace nrpn {
 
-constexpr int kDigitBits = 12;
-constexpr int kBins = 1 << kDigitBits;
-constexpr int kPasses = 5;                 // 5 x 12 = 60 >= 56 key bits
-constexpr int kIdxBits = 24;
-constexpr unsigned kIdxMask = (1u << kIdxBits) - 1u;
 constexpr int kIgnoreGroup = 255;
 
 struct LevelDev {
@@ -32,11 +28,6 @@ struct RpnDev {
     int total_cand;
 };
 
-// key: larger = better. [55:24] ordered logit, [23:0] (kIdxMask - flat index)
-__device__ __forceinline__ unsigned long long make_key(float logit, int idx) {
-    return ((unsigned long long)float_to_ordered(logit) << kIdxBits) | (unsigned long long)(kIdxMask - (unsigned)idx);
-}
-
 __device__ __forceinline__ float level_logit(const LevelDev& L, int A, int idx) {
     const int vox = idx / A, a = idx - vox * A;
     const int iz = vox % L.gz; const int t = vox / L.gz; const int iy = t % L.gy; const int ix = t / L.gy;
@@ -45,85 +36,18 @@ __device__ __forceinline__ float level_logit(const LevelDev& L, int A, int idx) 
     return v;
 }
 
-// state per level: prefix (selected high digits), remaining k
-struct SelState { unsigned long long prefix; int remaining; int pad; };
-
-__global__ void topk_hist_kernel(RpnDev P, int pass, const SelState* __restrict__ st, unsigned* __restrict__ hist) {
-    __shared__ unsigned sh[kBins];
-    const int l = blockIdx.y;
-    const LevelDev& L = P.lv[l];
-    for (int i = threadIdx.x; i < kBins; i += blockDim.x) sh[i] = 0u;
-    __syncthreads();
-    const int shift = (kPasses - 1 - pass) * kDigitBits;
-    const unsigned long long prefix = st[l].prefix;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.count; i += gridDim.x * blockDim.x) {
-        const unsigned long long key = make_key(level_logit(L, P.A, i), i);
-        if (pass == 0 || (key >> (shift + kDigitBits)) == prefix)
-            atomicAdd(&sh[(unsigned)(key >> shift) & (kBins - 1)], 1u);
+// top-k source: every anchor is a candidate, key = (ordered raw logit, lower flat index wins ties)
+struct RpnSrc {
+    RpnDev P;
+    __device__ __forceinline__ int levels() const { return P.n_levels; }
+    __device__ __forceinline__ int count(int l) const { return P.lv[l].count; }
+    __device__ __forceinline__ int k(int l) const { return P.lv[l].k; }
+    __device__ __forceinline__ int cand_off(int l) const { return P.lv[l].cand_off; }
+    __device__ __forceinline__ bool key(int l, int i, unsigned long long& key) const {
+        key = make_key56(float_to_ordered(level_logit(P.lv[l], P.A, i)), i);
+        return true;
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kBins; i += blockDim.x) if (sh[i]) atomicAdd(&hist[l * kBins + i], sh[i]);
-}
-
-// one CTA (1024 threads) per level: find the digit that contains the k-th largest key, clear the histogram.
-__global__ void __launch_bounds__(1024) topk_select_kernel(RpnDev P, SelState* __restrict__ st, unsigned* __restrict__ hist) {
-    __shared__ unsigned part[1024];
-    __shared__ int sel_bin, sel_above;
-    const int l = blockIdx.x;
-    unsigned* h = hist + l * kBins;
-    const int t = threadIdx.x;
-    // thread t owns bins [4t, 4t+3], counted from the top: bin index b = kBins-1 - (4t + j)
-    unsigned c[4]; unsigned s = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { c[j] = h[kBins - 1 - (4 * t + j)]; s += c[j]; }
-    part[t] = s;
-    __syncthreads();
-    // inclusive scan over 1024 partial sums (Hillis-Steele)
-    for (int off = 1; off < 1024; off <<= 1) {
-        unsigned v = (t >= off) ? part[t - off] : 0u;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    const unsigned rem = (unsigned)st[l].remaining;
-    const unsigned before = part[t] - s;      // keys in bins above this thread's bins
-    if (before < rem && part[t] >= rem) {
-        unsigned acc = before;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (acc < rem && acc + c[j] >= rem) { sel_bin = kBins - 1 - (4 * t + j); sel_above = (int)acc; }
-            acc += c[j];
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) h[kBins - 1 - (4 * t + j)] = 0u;
-    if (t == 0) {
-        st[l].prefix = (st[l].prefix << kDigitBits) | (unsigned long long)sel_bin;
-        st[l].remaining = (int)rem - sel_above;
-    }
-}
-
-// after the last pass st[l].prefix is the key of the k-th largest element: gather everything >= it
-__global__ void topk_collect_kernel(RpnDev P, const SelState* __restrict__ st, unsigned* __restrict__ counters,
-                                    unsigned long long* __restrict__ cand) {
-    const int l = blockIdx.y;
-    const LevelDev& L = P.lv[l];
-    const unsigned long long thr = st[l].prefix;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.count; i += gridDim.x * blockDim.x) {
-        const unsigned long long key = make_key(level_logit(L, P.A, i), i);
-        if (key >= thr) {
-            const unsigned slot = atomicAdd(&counters[l], 1u);
-            if (slot < (unsigned)L.k)    // keys are unique, so exactly k qualify
-                cand[L.cand_off + slot] = ((unsigned long long)l << 56) | (~key & 0x00FFFFFFFFFFFFFFull);   // ascending sort => best first
-        }
-    }
-}
-
-__global__ void rpn_init_kernel(RpnDev P, SelState* __restrict__ st) {
-    const int l = threadIdx.x;
-    if (l < NRPN_RPN_MAX_LEVELS) { st[l].prefix = 0ull; st[l].remaining = l < P.n_levels ? P.lv[l].k : 0; st[l].pad = 0; }
-}
+};
 
 __global__ void fill_u64_kernel(unsigned long long* p, int n, unsigned long long v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,7 +62,7 @@ __global__ void rpn_decode_kernel(RpnDev P, const unsigned long long* __restrict
     const unsigned long long ck = cand[p];
     const int l = (int)(ck >> 56);
     const unsigned long long key = (~ck) & 0x00FFFFFFFFFFFFFFull;
-    const int idx = (int)(kIdxMask - (unsigned)(key & kIdxMask));
+    const int idx = key56_index(key);
     const LevelDev& L = P.lv[l];
     const int A = P.A;
     const int vox = idx / A, a = idx - vox * A;
@@ -336,7 +260,8 @@ int nrpn_rpn_proposals(const nrpn_rpn_desc* desc, float* boxes, float* scores, f
 
     NRPN_CUDA_TRY(cudaMemsetAsync(w.hist, 0, (size_t)NRPN_RPN_MAX_LEVELS * kBins * 4, st));
     NRPN_CUDA_TRY(cudaMemsetAsync(w.counters, 0, NRPN_RPN_MAX_LEVELS * 4, st));
-    rpn_init_kernel<<<1, 32, 0, st>>>(P, w.st);
+    RpnSrc src{P};
+    topk_init_kernel<RpnSrc><<<1, 32, 0, st>>>(src, w.st);
     NRPN_LAUNCH_CHECK();
 
     int max_count = 0;
@@ -345,14 +270,14 @@ int nrpn_rpn_proposals(const nrpn_rpn_desc* desc, float* boxes, float* scores, f
     if (bx > 2 * num_sms()) bx = 2 * num_sms();
     if (bx < 1) bx = 1;
     for (int pass = 0; pass < kPasses; ++pass) {
-        topk_hist_kernel<<<dim3(bx, L), 256, 0, st>>>(P, pass, w.st, w.hist);
+        topk_hist_kernel<RpnSrc><<<dim3(bx, L), 256, 0, st>>>(src, pass, w.st, w.hist);
         NRPN_LAUNCH_CHECK();
-        topk_select_kernel<<<L, 1024, 0, st>>>(P, w.st, w.hist);
+        topk_select_kernel<<<L, 1024, 0, st>>>(pass, w.st, w.hist);
         NRPN_LAUNCH_CHECK();
     }
     fill_u64_kernel<<<ceil_div(cpad, 256), 256, 0, st>>>(w.cand, cpad, ~0ull);
     NRPN_LAUNCH_CHECK();
-    topk_collect_kernel<<<dim3(bx, L), 256, 0, st>>>(P, w.st, w.counters, w.cand);
+    topk_collect_kernel<RpnSrc><<<dim3(bx, L), 256, 0, st>>>(src, w.st, w.counters, w.cand);
     NRPN_LAUNCH_CHECK();
     rc = bitonic_sort_u64(w.cand, cpad, st);
     if (rc) return rc;

@@ -7,7 +7,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, RpnDesc, check, lib
+from ._lib import ConvDesc, FcosDesc, GnLevel, RpnDesc, check, lib
 
 
 def _stream():
@@ -243,3 +243,57 @@ def rpn_proposals(desc: RpnDesc, device, out=None, workspace: Optional[torch.Ten
     check(lib().nrpn_rpn_proposals(ctypes.byref(desc), _ptr(boxes), _ptr(scores), _ptr(levels), _ptr(count), _ptr(ws),
                                    ws.numel(), _stream()), "rpn_proposals")
     return boxes, scores, levels, count
+
+
+# ------------------------------------------------------------------------------------------------ FCOS
+def groupnorm_relu_(levels: Sequence[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, relu: bool = True,
+                    groups: int = 32, workspace: Optional[torch.Tensor] = None):
+    """In-place GroupNorm(groups, C) (+ReLU) on channels-last bf16 tensors (N, X, Y, Z, C) that share gamma / beta."""
+    n, c = levels[0].shape[0], levels[0].shape[-1]
+    arr = (GnLevel * len(levels))()
+    for i, t in enumerate(levels):
+        _req(t, torch.bfloat16, f"levels[{i}]")
+        arr[i].x = t.data_ptr(); arr[i].voxels = int(t.shape[1] * t.shape[2] * t.shape[3])
+    need = lib().nrpn_groupnorm_workspace_bytes(len(levels), n)
+    ws = workspace if workspace is not None else _workspace(need, levels[0].device)
+    check(lib().nrpn_groupnorm_relu(arr, len(levels), n, c, groups, _ptr(gamma), _ptr(beta), float(eps), int(relu), _ptr(ws),
+                                    ws.numel(), _stream()), "groupnorm_relu")
+
+
+def make_fcos_desc(cls_preds, reg_preds, grids, strides, scales, use_obb, pre_nms_thresh, pre_nms_top_n, nms_thresh,
+                   post_nms_top_n, min_size, grid_size, padded=False) -> FcosDesc:
+    d = FcosDesc()
+    d.n_levels = len(cls_preds)
+    for l, (c, r) in enumerate(zip(cls_preds, reg_preds)):
+        c = _req(c, torch.float32, f"cls[{l}]"); r = _req(r, torch.float32, f"reg[{l}]")
+        lv = d.level[l]
+        lv.cls, lv.reg = c.data_ptr(), r.data_ptr()
+        lv.ld_cls, lv.ld_reg = int(c.shape[-1]), int(r.shape[-1])
+        lv.gx, lv.gy, lv.gz = (int(v) for v in grids[l])
+        lv.stride, lv.scale = int(strides[l]), float(scales[l])
+    d.use_obb = int(bool(use_obb))
+    d.pre_nms_top_n, d.post_nms_top_n = int(pre_nms_top_n), int(post_nms_top_n)
+    d.pre_nms_thresh, d.nms_thresh, d.min_size = float(pre_nms_thresh), float(nms_thresh), float(min_size)
+    for k in range(3):
+        d.grid_size[k] = int(grid_size[k])
+    d.padded = int(bool(padded))
+    return d
+
+
+def fcos_proposals(desc: FcosDesc, device, out=None, workspace: Optional[torch.Tensor] = None):
+    """Returns (boxes (cap, 1+6|7) with the level id in column 0, scores (cap,), count int32 (1,)) device tensors."""
+    cap = lib().nrpn_fcos_max_proposals(ctypes.byref(desc))
+    if cap <= 0:
+        raise ValueError("nerf_rpn_b200: invalid FCOS descriptor")
+    dim = 7 if desc.use_obb else 6
+    if out is None:
+        boxes = torch.empty((cap, 1 + dim), dtype=torch.float32, device=device)
+        scores = torch.empty((cap,), dtype=torch.float32, device=device)
+        count = torch.zeros((1,), dtype=torch.int32, device=device)
+    else:
+        boxes, scores, count = out
+    wsb = lib().nrpn_fcos_workspace_bytes(ctypes.byref(desc))
+    ws = workspace if workspace is not None else _workspace(wsb, device)
+    check(lib().nrpn_fcos_proposals(ctypes.byref(desc), _ptr(boxes), _ptr(scores), _ptr(count), _ptr(ws), ws.numel(), _stream()),
+          "fcos_proposals")
+    return boxes, scores, count

@@ -250,7 +250,63 @@ def gen_vgg_small():
     print("vgg_small_aabb.npz proposals", tuple(proposals[0].shape), [tuple(f.shape) for f in features], len(backbone.state_dict()))
 
 
+def gen_fcos_small():
+    """Anchor-free head (run_fcos.py / test_fcos.sh flags: --norm_reg_targets --centerness_on_reg): reference FCOSOverNeRF
+    forward on CPU, ResNet50-FPN backbone, 32x48x40 grid; AABB and OBB, default and tight top-n settings."""
+    import argparse
+    from model.fcos.fcos import FCOSOverNeRF
+    for rotated in (False, True):
+        for tag, pre_n, post_n in (("", 2500, 2500), ("_tight", 300, 150)):
+            args = argparse.Namespace(num_convs=4, norm_reg_targets=True, centerness_on_reg=True, rotated_bbox=rotated,
+                                      pre_nms_thresh=0.0, pre_nms_top_n=pre_n, nms_thresh=0.3, fpn_post_nms_top_n=post_n,
+                                      min_size=0.0, center_sampling_radius=1.5, iou_loss_type="iou",
+                                      use_additional_l1_loss=False, proj2d_loss_weight=0.0)
+            torch.manual_seed(0)
+            backbone = ResNet_FPN_256(Bottleneck, [3, 4, 6, 3], input_dim=4, is_max_pool=True)
+            model = FCOSOverNeRF(args, backbone, [4, 8, 16, 32])
+            head = model.fcos_module.head
+            g = torch.Generator().manual_seed(7)
+            with torch.no_grad():
+                for m in model.modules():
+                    if isinstance(m, (torch.nn.BatchNorm3d, torch.nn.GroupNorm)):
+                        if isinstance(m, torch.nn.BatchNorm3d):
+                            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.5 + 0.75)
+                        m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+                        m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+                for i, sc in enumerate(head.scales):
+                    sc.scale.fill_(1.0 + 0.1 * i)
+            gi = torch.Generator().manual_seed(1000)
+            grid = torch.rand(32, 48, 40, 4, generator=gi)
+            x = grid.permute(3, 0, 1, 2).contiguous()
+            model.eval()
+            with torch.no_grad():
+                feats = list(backbone(x[None]))
+                # calibrate the three predictors on the towers' outputs: logits std 2, distances ~ a few voxels, centerness std 1
+                ct = [head.cls_tower(f) for f in feats]; bt = [head.bbox_tower(f) for f in feats]
+                s_c = torch.cat([head.cls_logits(t).flatten() for t in ct]).std().item()
+                s_b = torch.cat([head.bbox_pred(t).flatten() for t in bt]).std().item()
+                s_t = torch.cat([head.centerness(t).flatten() for t in bt]).std().item()
+                head.cls_logits.weight.mul_(2.0 / s_c); head.cls_logits.bias.fill_(-1.0)
+                head.bbox_pred.weight.mul_(1.5 / s_b); head.bbox_pred.bias.fill_(1.0)
+                head.centerness.weight.mul_(1.0 / s_t)
+                boxes, losses, scores = model([x])
+                logits, bbox_reg, ctr = head(feats)
+            out = dict(boxes=boxes[0].numpy(), scores=scores[0].numpy(),      # grid = torch.rand(32,48,40,4, seed 1000), not stored
+                       conv1_sum=np.float64(backbone.conv1.weight.double().sum().item()),
+                       tower_sum=np.float64(head.cls_tower[0].weight.double().sum().item()),
+                       cls_w=head.cls_logits.weight.detach().numpy(), bbox_w=head.bbox_pred.weight.detach().numpy(),
+                       ctr_w=head.centerness.weight.detach().numpy())
+            for i in range(4):
+                out[f"logits{i}"] = logits[i][0].numpy(); out[f"reg{i}"] = bbox_reg[i][0].numpy(); out[f"ctr{i}"] = ctr[i][0].numpy()
+            name = f"fcos_small_{'obb' if rotated else 'aabb'}{tag}.npz"
+            np.savez_compressed(os.path.join(OUT, name), **out)
+            print(name, "boxes", tuple(boxes[0].shape), "scores", float(scores[0].min()), float(scores[0].max()))
+
+
 if __name__ == "__main__":
+    if "--fcos-only" in sys.argv:
+        gen_fcos_small(); sys.exit(0)
     gen_vgg_small()
     sys.exit(0) if "--vgg-only" in sys.argv else None
     gen_iou()
@@ -258,3 +314,4 @@ if __name__ == "__main__":
     gen_nms()
     gen_decode_anchors()
     gen_rpn_small()
+    gen_fcos_small()
