@@ -65,8 +65,9 @@ class RPNInferenceEngine:
 
     def __init__(self, backbone, head=None, anchor_cells=None, num_anchors: int = 0, rotated: bool = False,
                  pre_nms_top_n: int = 2500, post_nms_top_n: int = 2500, nms_thresh: float = 0.3, score_thresh: float = 0.0,
-                 min_size: float = 1e-3, use_graph: bool = True):
+                 min_size: float = 1e-3, use_graph: bool = True, fcos: Optional[dict] = None):
         self.backbone, self.head = backbone, head
+        self.fcos = fcos                   # None: anchor head (anchor.py:177-213); dict: FCOS head + post-processing settings
         self.cells = anchor_cells          # list (levels) of (A, 6) float arrays
         self.A, self.rotated = num_anchors, rotated
         self.code = 8 if rotated else 6
@@ -99,6 +100,11 @@ class RPNInferenceEngine:
             self.layers = L
             self._plans.clear()
             return
+        if self.fcos is not None:
+            self._pack_fcos(L, device)
+            self.layers = L
+            self._plans.clear()
+            return
         convs = [m for m in hd.conv if isinstance(m, torch.nn.Conv3d)]
         L["head"] = [_Conv(m.weight, m.bias, relu=True, device=device) for m in convs]
         # cls (A) and bbox (A*code) predictors fused into one 1x1x1 GEMM, zero-padded to 128 output channels
@@ -109,6 +115,25 @@ class RPNInferenceEngine:
         L["pred"] = _Conv(w, b, device=device, cout_pad_to=128)
         self.layers = L
         self._plans.clear()
+
+    def _pack_fcos(self, L, device):
+        """FCOSHead (fcos/fcos.py:43-102): two towers of num_convs x [Conv3d 3^3 + GroupNorm(32) + ReLU] shared over levels,
+        3^3 predictors for class (1), distances (6|8) and centerness (1, from the bbox tower), one Scale per level."""
+        hd = self.head
+        def tower(seq):
+            mods, out = list(seq.children()), []
+            for i in range(0, len(mods), 3):
+                conv, gn = mods[i], mods[i + 1]
+                out.append((_Conv(conv.weight, conv.bias, relu=False, device=device),
+                            gn.weight.detach().float().to(device).contiguous(), gn.bias.detach().float().to(device).contiguous(),
+                            float(gn.eps)))
+            return out
+        L["cls_tower"], L["bbox_tower"] = tower(hd.cls_tower), tower(hd.bbox_tower)
+        L["cls_pred"] = _Conv(hd.cls_logits.weight, hd.cls_logits.bias, device=device, cout_pad_to=None)
+        w = torch.cat([hd.bbox_pred.weight, hd.centerness.weight], 0)
+        b = torch.cat([hd.bbox_pred.bias, hd.centerness.bias], 0)
+        L["reg_pred"] = _Conv(w, b, device=device)
+        L["scales"] = [float(s.scale.detach().item()) for s in hd.scales]
 
     def _pack_resnet(self, L, device):
         bb = self.backbone
@@ -244,6 +269,9 @@ class _Plan:
         # head: all levels per launch
         self.has_head = eng.head is not None
         if not self.has_head:
+            return
+        if eng.fcos is not None:
+            self._build_fcos_head(L, n, buf, conv)
             return
         self._cur = self.head_launches
         cur = self.features
@@ -391,6 +419,84 @@ class _Plan:
             feats.append((o, qd))
         return feats
 
+    def _build_fcos_head(self, L, n, buf, conv):
+        eng, device, dims = self.eng, self.device, self.dims
+        f = eng.fcos
+        self._cur = self.head_launches
+        self._gn_ws = torch.empty(max(1, ops.lib().nrpn_groupnorm_workspace_bytes(len(self.features), n)), dtype=torch.uint8, device=device)
+        ends = {}
+        for name in ("cls_tower", "bbox_tower"):
+            cur = self.features
+            for (layer, gamma, beta, eps) in L[name]:
+                nxt = [buf(d, 256) for d in self.feat_dims]
+                conv(layer, cur, nxt, self.feat_dims, self.feat_dims, name=f"fcos.{name}.conv3x3x3")
+                self.head_launches.append(lambda t=nxt, g=gamma, b=beta, e=eps: ops.groupnorm_relu_(t, g, b, e, True, 32, self._gn_ws))
+                self.names[id(self.head_launches[-1])] = (f"fcos.{name}.groupnorm+relu", 0.0)
+                cur = nxt
+            ends[name] = cur
+        code = 8 if f["use_obb"] else 6
+        cls_c, reg_c = L["cls_pred"].cout, L["reg_pred"].cout
+        self.pred_sets = [dict(cls=[buf(d, cls_c, torch.float32) for d in self.feat_dims],
+                               reg=[buf(d, reg_c, torch.float32) for d in self.feat_dims]) for _ in range(2)]
+        self.pred_launch = []
+        for par in range(2):
+            self._cur = []
+            conv(L["cls_pred"], ends["cls_tower"], self.pred_sets[par]["cls"], self.feat_dims, self.feat_dims, out_fp32=True,
+                 real=(256, 27, 1), name="fcos.cls_logits")
+            conv(L["reg_pred"], ends["bbox_tower"], self.pred_sets[par]["reg"], self.feat_dims, self.feat_dims, out_fp32=True,
+                 real=(256, 27, code + 1), name="fcos.bbox_pred|centerness")
+            fs = list(self._cur)
+            self.pred_launch.append(lambda fs=fs: [g() for g in fs])
+            if par == 1:
+                for g in fs:
+                    self.algorithmic_flops -= self.names[id(g)][1] / n
+        self._cur = self.head_launches
+        self.strides = list(f["fpn_strides"])[: len(self.feat_dims)]
+        self._fcos_desc0 = ops.make_fcos_desc([p[0].reshape(-1, cls_c) for p in self.pred_sets[0]["cls"]],
+                                              [p[0].reshape(-1, reg_c) for p in self.pred_sets[0]["reg"]], self.feat_dims, self.strides,
+                                              L["scales"], f["use_obb"], f["pre_nms_thresh"], f["pre_nms_top_n"], f["nms_thresh"],
+                                              f["post_nms_top_n"], f["min_size"], dims)
+        cap = ops.lib().nrpn_fcos_max_proposals(__import__("ctypes").byref(self._fcos_desc0))
+        dim = 7 if f["use_obb"] else 6
+        self._out = [dict(boxes=torch.zeros((n, cap, 1 + dim), dtype=torch.float32, device=device),
+                          scores=torch.zeros((n, cap), dtype=torch.float32, device=device),
+                          count=torch.zeros((n,), dtype=torch.int32, device=device)) for _ in range(2)]
+        self.side = torch.cuda.Stream(device=device)
+        self._ev_pred = [torch.cuda.Event() for _ in range(2)]
+        self._ev_done = [torch.cuda.Event() for _ in range(2)]
+        self._parity = 0
+        self._post_graph = [None, None]
+        self._valid = "unset"
+        self._build_post(None)
+
+    def _build_post_fcos(self, valid_dims):
+        import ctypes
+        eng, L, f = self.eng, self.eng.layers, self.eng.fcos
+        cls_c, reg_c = L["cls_pred"].cout, L["reg_pred"].cout
+        self._post = [[], []]
+        ws_bytes = 0
+        descs = []
+        for par in range(2):
+            for i in range(self.n):
+                gs = self.dims if valid_dims is None else valid_dims[i]
+                d = ops.make_fcos_desc([p[i].reshape(-1, cls_c) for p in self.pred_sets[par]["cls"]],
+                                       [p[i].reshape(-1, reg_c) for p in self.pred_sets[par]["reg"]], self.feat_dims, self.strides,
+                                       L["scales"], f["use_obb"], f["pre_nms_thresh"], f["pre_nms_top_n"], f["nms_thresh"],
+                                       f["post_nms_top_n"], f["min_size"], gs, padded=self.n > 1)
+                descs.append(d)
+                ws_bytes = max(ws_bytes, ops.lib().nrpn_fcos_workspace_bytes(ctypes.byref(d)))
+        if self._rpn_ws is None or self._rpn_ws.numel() < ws_bytes:
+            self._rpn_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        for par in range(2):
+            o = self._out[par]
+            for i in range(self.n):
+                d = descs[par * self.n + i]
+                out = (o["boxes"][i], o["scores"][i], o["count"][i:i + 1])
+                self._post[par].append(lambda d=d, out=out: ops.fcos_proposals(d, self.device, out=out, workspace=self._rpn_ws))
+        self._descs = descs
+        self._valid = valid_dims
+        self._post_graph = [None, None]
+
     # results of the most recent run (valid once `done` has completed)
     @property
     def pred(self):
@@ -420,6 +526,8 @@ class _Plan:
         import ctypes
         from ._lib import lib
         eng = self.eng
+        if eng.fcos is not None:
+            return self._build_post_fcos(valid_dims)
         self._post = [[], []]
         self._descs = []
         ws_bytes = 0

@@ -57,3 +57,40 @@ def build_vgg_small(ns, golden):
     assert abs(backbone.fpn_neck.fpn_convs[3].weight.double().sum().item() - float(golden["fpn_sum"])) < 1e-9
     assert abs(head.conv[0].weight.double().sum().item() - float(golden["head_sum"])) < 1e-9
     return backbone, ag, head
+
+
+def fcos_args(rotated, pre_n=2500, post_n=2500):
+    import argparse
+    return argparse.Namespace(num_convs=4, norm_reg_targets=True, centerness_on_reg=True, rotated_bbox=rotated, pre_nms_thresh=0.0,
+                              pre_nms_top_n=pre_n, nms_thresh=0.3, fpn_post_nms_top_n=post_n, min_size=0.0,
+                              center_sampling_radius=1.5, iou_loss_type="iou", use_additional_l1_loss=False, proj2d_loss_weight=0.0)
+
+
+def build_fcos_small(ns, rotated, golden, pre_n=2500, post_n=2500):
+    """FCOSOverNeRF(ResNet50-FPN) with the weights tools/make_golden.py:gen_fcos_small gave the reference."""
+    torch.manual_seed(0)
+    backbone = ns.ResNet_FPN_256(ns.Bottleneck, [3, 4, 6, 3], input_dim=4, is_max_pool=True)
+    model = ns.FCOSOverNeRF(fcos_args(rotated, pre_n, post_n), backbone, [4, 8, 16, 32])
+    head = model.fcos_module.head
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, (torch.nn.BatchNorm3d, torch.nn.GroupNorm)):
+                if isinstance(m, torch.nn.BatchNorm3d):
+                    m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                    m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.5 + 0.75)
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+        for i, sc in enumerate(head.scales):
+            sc.scale.fill_(1.0 + 0.1 * i)
+        head.cls_logits.weight.copy_(torch.from_numpy(golden["cls_w"])); head.cls_logits.bias.fill_(-1.0)
+        head.bbox_pred.weight.copy_(torch.from_numpy(golden["bbox_w"])); head.bbox_pred.bias.fill_(1.0)
+        head.centerness.weight.copy_(torch.from_numpy(golden["ctr_w"]))
+    assert abs(backbone.conv1.weight.double().sum().item() - float(golden["conv1_sum"])) < 1e-9
+    assert abs(head.cls_tower[0].weight.double().sum().item() - float(golden["tower_sum"])) < 1e-9, "seeded FCOS tower weights differ"
+    return model
+
+
+def seed1000_input(dims=(32, 48, 40)):
+    gi = torch.Generator().manual_seed(1000)
+    return torch.rand(*dims, 4, generator=gi).permute(3, 0, 1, 2).contiguous()
