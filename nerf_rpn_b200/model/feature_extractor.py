@@ -168,7 +168,113 @@ class VGG_FPN(nn.Module):
         return tuple(f.permute(0, 4, 1, 2, 3).float() for f in plan.features)
 
 
-SwinTransformer_FPN = _not_built("SwinTransformer_FPN")
+class ShiftedWindowAttention(nn.Module):
+    """Parameter container for 3-D shifted-window attention (feature_extractor.py:504-590): qkv / proj Linear layers, the
+    (2w-1)^3 x heads relative-position bias table and its index buffer, created and initialised in the reference's order."""
+
+    def __init__(self, dim, window_size, shift_size, num_heads, qkv_bias=True, proj_bias=True, attention_dropout=0.0, dropout=0.0):
+        super().__init__()
+        if len(window_size) != 3 or len(shift_size) != 3:
+            raise ValueError("window_size and shift_size must be of length 3")
+        self.window_size, self.shift_size, self.num_heads = window_size, shift_size, num_heads
+        self.attention_dropout, self.dropout = attention_dropout, dropout
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim, bias=proj_bias)
+        w = window_size
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * w[0] - 1) * (2 * w[1] - 1) * (2 * w[2] - 1), num_heads))
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
+        coords = torch.stack(torch.meshgrid(torch.arange(w[0]), torch.arange(w[1]), torch.arange(w[2]), indexing="ij"))
+        flat = torch.flatten(coords, 1)
+        rel = (flat[:, :, None] - flat[:, None, :]).permute(1, 2, 0).contiguous()
+        rel[:, :, 0] += w[0] - 1; rel[:, :, 1] += w[1] - 1; rel[:, :, 2] += w[2] - 1
+        rel[:, :, 0] *= (2 * w[2] - 1) * (2 * w[1] - 1)
+        rel[:, :, 1] *= (2 * w[2] - 1)
+        self.register_buffer("relative_position_index", rel.sum(-1).flatten())
+
+
+class SwinTransformerBlock(nn.Module):
+    """feature_extractor.py:593-644: x + attn(norm1 x); x + mlp(norm2 x), MLP = Linear(C,4C) -> GELU -> Linear(4C,C)."""
+
+    def __init__(self, dim, num_heads, window_size, shift_size, mlp_ratio=4.0, dropout=0.0, attention_dropout=0.0,
+                 stochastic_depth_prob=0.0, norm_layer=nn.LayerNorm, attn_layer=ShiftedWindowAttention):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = attn_layer(dim, window_size, shift_size, num_heads, attention_dropout=attention_dropout, dropout=dropout)
+        self.stochastic_depth = nn.Identity()          # StochasticDepth("row") is the identity in eval mode
+        self.norm2 = norm_layer(dim)
+        hidden = int(dim * mlp_ratio)
+        # torchvision.ops.misc.MLP(dim, [hidden, dim], activation_layer=nn.GELU, inplace=None): indices 0 and 3 carry parameters
+        self.mlp = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Dropout(dropout), nn.Linear(hidden, dim), nn.Dropout(dropout))
+        for m in self.mlp.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.normal_(m.bias, std=1e-6)
+
+
+class PatchMerging(nn.Module):
+    """feature_extractor.py:647-686: 2x2x2 gather (parity order 000,100,010,110,001,101,011,111 over H,W,D) -> LN(8C) -> Linear."""
+
+    def __init__(self, dim, norm_layer=nn.LayerNorm, expand_dim=True):
+        super().__init__()
+        self.dim = dim
+        self.reduction = nn.Linear(8 * dim, dim * 2 if expand_dim else dim, bias=False)
+        self.norm = norm_layer(8 * dim)
+
+
+class SwinTransformer_FPN(nn.Module):
+    """3-D Swin Transformer + FPN (feature_extractor.py:689-789), same constructor as the reference; run_rpn.py:281-292 builds
+    Swin-T/S/B/L with patch 4^3, window 4^3."""
+
+    def __init__(self, patch_size, embed_dim, depths, num_heads, window_size, mlp_ratio=4.0, dropout=0.0, attention_dropout=0.0,
+                 stochastic_depth_prob=0.1, norm_layer=None, block=None, downsample_layer=None, expand_dim=True,
+                 out_channels=256, input_dim=4):
+        super().__init__()
+        from functools import partial
+        from .fpn import FPN
+        if list(patch_size) != [4, 4, 4] or list(window_size) != [4, 4, 4] or input_dim != 4 or not expand_dim or dropout or attention_dropout:
+            raise NotImplementedError("the B200 engine implements patch 4^3 / window 4^3 / 4 input channels (run_rpn.py:286-292)")
+        norm_layer = norm_layer or partial(nn.LayerNorm, eps=1e-5)
+        block = block or SwinTransformerBlock
+        downsample_layer = downsample_layer or PatchMerging
+        self.out_channels = out_channels
+        self.patch_size, self.window_size, self.depths, self.num_heads, self.embed_dim = list(patch_size), list(window_size), list(depths), list(num_heads), embed_dim
+        self.patch_partition = nn.Sequential(
+            nn.Conv3d(input_dim, embed_dim, kernel_size=tuple(patch_size), stride=tuple(patch_size)),
+            nn.Identity(),                                  # Permute([0,2,3,4,1]) in the reference: no parameters, index 1
+            norm_layer(embed_dim),
+        )
+        self.stages = nn.ModuleList()
+        total, bid, fpn_in = sum(depths), 0, []
+        for i_stage in range(len(depths)):
+            stage = []
+            dim = embed_dim * 2 ** i_stage
+            fpn_in.append(dim)
+            if i_stage > 0:
+                stage.append(downsample_layer(fpn_in[-2], norm_layer, expand_dim))
+            for i_layer in range(depths[i_stage]):
+                sd = stochastic_depth_prob * float(bid) / (total - 1)
+                stage.append(block(dim, num_heads[i_stage], window_size=list(window_size),
+                                   shift_size=[0 if i_layer % 2 == 0 else w // 2 for w in window_size], mlp_ratio=mlp_ratio,
+                                   dropout=dropout, attention_dropout=attention_dropout, stochastic_depth_prob=sd, norm_layer=norm_layer))
+                bid += 1
+            self.stages.append(nn.Sequential(*stage))
+        self.fpn_neck = FPN(fpn_in, out_channels, len(fpn_in))
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+        self._engine = None
+
+    def forward(self, x):
+        from ..engine import RPNInferenceEngine
+        if self._engine is None:
+            self._engine = RPNInferenceEngine(self)
+        plan = self._engine.forward_device(x.contiguous())
+        return tuple(f.permute(0, 4, 1, 2, 3).float() for f in plan.features)
+
+
 ResNet_FPN_64 = _not_built("ResNet_FPN_64")
 ResNetSimplified_64 = _not_built("ResNetSimplified_64")
 ResNetSimplified_256 = _not_built("ResNetSimplified_256")

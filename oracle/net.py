@@ -120,3 +120,77 @@ def vgg_fpn_forward(sd, x):
     for i in range(len(lat) - 1, 0, -1):
         lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], mode="nearest")
     return [F.conv3d(l, sd[f"fpn_neck.fpn_convs.{i}.weight"], sd[f"fpn_neck.fpn_convs.{i}.bias"], padding=1) for i, l in enumerate(lat)]
+
+
+# ------------------------------------------------------------------------------------------------ Swin
+def _window_attention(x, sd, p, heads, shift, win=4):
+    """shifted_window_attention (nerf_rpn/model/feature_extractor.py:382-497) for window = 4^3, restated:
+    zero-pad to multiples of the window AFTER norm1 (padded tokens take part), cyclic shift by -shift when shifted,
+    per-window multi-head attention with q scaled by head_dim^-0.5, relative-position bias, -100 mask between the 27
+    shift regions, softmax, projection, un-shift, crop."""
+    B, H, W, D, C = x.shape
+    ph, pw, pd = (-H) % win, (-W) % win, (-D) % win
+    xp = F.pad(x, (0, 0, 0, pd, 0, pw, 0, ph))
+    PH, PW, PD = H + ph, W + pw, D + pd
+    sh = [0 if win >= e else shift for e in (PH, PW, PD)]
+    if sum(sh) > 0:
+        xp = torch.roll(xp, shifts=(-sh[0], -sh[1], -sh[2]), dims=(1, 2, 3))
+    nh, nw, nd = PH // win, PW // win, PD // win
+    t = xp.view(B, nh, win, nw, win, nd, win, C).permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(B * nh * nw * nd, win ** 3, C)
+    qkv = F.linear(t, sd[p + ".qkv.weight"], sd[p + ".qkv.bias"]).reshape(t.shape[0], win ** 3, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0] * (C // heads) ** -0.5, qkv[1], qkv[2]
+    attn = q @ k.transpose(-2, -1)
+    bias = sd[p + ".relative_position_bias_table"][sd[p + ".relative_position_index"]].view(win ** 3, win ** 3, -1).permute(2, 0, 1)
+    attn = attn + bias.unsqueeze(0)
+    if sum(sh) > 0:
+        region = x.new_zeros((PH, PW, PD))
+        cnt = 0
+        for hs in ((0, -win), (-win, -sh[0]), (-sh[0], None)):
+            for ws in ((0, -win), (-win, -sh[1]), (-sh[1], None)):
+                for ds in ((0, -win), (-win, -sh[2]), (-sh[2], None)):
+                    region[hs[0]:hs[1], ws[0]:ws[1], ds[0]:ds[1]] = cnt
+                    cnt += 1
+        region = region.view(nh, win, nw, win, nd, win).permute(0, 2, 4, 1, 3, 5).reshape(nh * nw * nd, win ** 3)
+        diff = region.unsqueeze(1) - region.unsqueeze(2)
+        mask = torch.where(diff != 0, torch.full_like(diff, -100.0), torch.zeros_like(diff))
+        attn = (attn.view(B, nh * nw * nd, heads, win ** 3, win ** 3) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, win ** 3, win ** 3)
+    attn = F.softmax(attn, dim=-1)
+    o = (attn @ v).transpose(1, 2).reshape(t.shape[0], win ** 3, C)
+    o = F.linear(o, sd[p + ".proj.weight"], sd[p + ".proj.bias"])
+    o = o.view(B, nh, nw, nd, win, win, win, C).permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(B, PH, PW, PD, C)
+    if sum(sh) > 0:
+        o = torch.roll(o, shifts=(sh[0], sh[1], sh[2]), dims=(1, 2, 3))
+    return o[:, :H, :W, :D, :].contiguous()
+
+
+def _ln(x, sd, p, eps=1e-5):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], eps)
+
+
+@torch.no_grad()
+def swin_fpn_forward(sd, x, depths, num_heads):
+    """SwinTransformer_FPN.forward (feature_extractor.py:781-789): patch embed (Conv3d k4 s4 + LN), stages of
+    [PatchMerging] + SwinTransformerBlocks (:593-686), FPN neck (fpn.py:134-161). Channels-last (B,H,W,D,C) inside."""
+    h = F.conv3d(x, sd["patch_partition.0.weight"], sd["patch_partition.0.bias"], stride=4).permute(0, 2, 3, 4, 1)
+    h = _ln(h, sd, "patch_partition.2")
+    feats = []
+    for s, depth in enumerate(depths):
+        idx = 0
+        if s > 0:
+            p = f"stages.{s}.0"
+            H, W, D = h.shape[1:4]
+            hp = F.pad(h, (0, 0, 0, D % 2, 0, W % 2, 0, H % 2))
+            parts = [hp[:, i::2, j::2, k::2, :] for (i, j, k) in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0), (0, 0, 1), (1, 0, 1), (0, 1, 1), (1, 1, 1))]
+            h = F.linear(_ln(torch.cat(parts, -1), sd, p + ".norm"), sd[p + ".reduction.weight"])
+            idx = 1
+        for b in range(depth):
+            p = f"stages.{s}.{idx + b}"
+            h = h + _window_attention(_ln(h, sd, p + ".norm1"), sd, p + ".attn", num_heads[s], 0 if b % 2 == 0 else 2)
+            m = F.linear(F.gelu(F.linear(_ln(h, sd, p + ".norm2"), sd[p + ".mlp.0.weight"], sd[p + ".mlp.0.bias"])),
+                         sd[p + ".mlp.3.weight"], sd[p + ".mlp.3.bias"])
+            h = h + m
+        feats.append(h.permute(0, 4, 1, 2, 3).contiguous())
+    lat = [F.conv3d(f, sd[f"fpn_neck.lateral_convs.{i}.weight"], sd[f"fpn_neck.lateral_convs.{i}.bias"]) for i, f in enumerate(feats)]
+    for i in range(len(lat) - 1, 0, -1):
+        lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], mode="nearest")
+    return [F.conv3d(l, sd[f"fpn_neck.fpn_convs.{i}.weight"], sd[f"fpn_neck.fpn_convs.{i}.bias"], padding=1) for i, l in enumerate(lat)]
