@@ -108,7 +108,7 @@ typedef struct {
     int32_t n_taps;                 /* 1 .. NRPN_CONV_MAX_TAPS */
     int8_t tap_off[NRPN_CONV_MAX_TAPS][3]; /* per tap (dx,dy,dz) input offset */
     int32_t stride;                 /* 1 or 2 (same on all axes) */
-    int32_t relu;                   /* apply max(.,0) last */
+    int32_t relu;                   /* final activation: 0 none, 1 ReLU, 2 exact (erf) GELU */
     int32_t out_fp32;               /* y is fp32 */
     const void *w;                  /* bf16 (taps, CoutPad, cin) */
     const float *shift;             /* fp32 (CoutPad) */
@@ -193,6 +193,24 @@ size_t nrpn_rpn_workspace_bytes(const nrpn_rpn_desc *desc /*host*/);
  * (the reference returns the level id as a float column), count (1) i32. */
 int nrpn_rpn_proposals(const nrpn_rpn_desc *desc /*host*/, float *boxes, float *scores, float *levels,
                        int32_t *count, void *workspace, size_t workspace_bytes, nrpn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Swin-3D support (SwinTransformer_FPN, feature_extractor.py:382-789). Token grids are channels-last bf16 (N,H,W,D,ld) with
+ * C real channels, ld >= C; the Linear layers run through nrpn_conv3d_fprop as 1x1x1 convolutions.
+ * ---------------------------------------------------------------------------------------------- */
+/* fp32 NCDHW grid (N,4,X,Y,Z) -> bf16 (N, X/4, Y/4, Z/4, 256) patch rows, channel ((c*4+px)*4+py)*4+pz: the patch embedding
+ * Conv3d(4, C, kernel 4, stride 4) becomes a 256 -> C GEMM. */
+int nrpn_patch_embed_pack(const float *grid, int n, int x, int y, int z, void *out, nrpn_stream_t stream);
+/* per-token LayerNorm over the first c channels of each row; rows are ld_in / ld_out elements apart. */
+int nrpn_layernorm(const void *in, int ld_in, void *out, int ld_out, long tokens, int c, const float *gamma, const float *beta,
+                   float eps, nrpn_stream_t stream);
+/* PatchMerging front half: 2x2x2 gather (zero past odd extents) + LayerNorm(8c) -> (N, ceil(h/2), ceil(w/2), ceil(d/2), 8c). */
+int nrpn_patch_merge_ln(const void *in, int ld_in, int n, int h, int w, int d, int c, void *out, const float *gamma,
+                        const float *beta, float eps, nrpn_stream_t stream);
+/* 4x4x4 (shifted) window multi-head attention, head_dim 32: qkv (N,h,w,d, 3c) -> out (N,h,w,d, ld_out). shift in {0, 2};
+ * table = (343, heads) relative position bias table; qkv_bias (3c) stands in for zero-padded tokens. */
+int nrpn_window_attention(const void *qkv, int ld_qkv, void *out, int ld_out, const float *qkv_bias, const float *table, int n,
+                          int h, int w, int d, int c, int heads, int shift, nrpn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * FCOS (anchor-free) post-processing for ONE scene (fcos/fcos.py:116-126,221-250; fcos/inference.py:48-195;

@@ -241,9 +241,12 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(rb[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
                             }
-                            if (P.relu) {
+                            if (P.relu == 1) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+                            } else if (P.relu == 2) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
                             }
                             if (P.out_fp32) {
                                 float* o = reinterpret_cast<float*>(L.y) + vox * L.ldy + ch;
@@ -300,9 +303,12 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
 #pragma unroll
                             for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(rb[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
                         }
-                        if (P.relu) {
+                        if (P.relu == 1) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+                        } else if (P.relu == 2) {            // exact (erf) GELU: Swin MLP, feature_extractor.py:635
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
                         }
                         if (P.out_fp32) {
                             float* o = reinterpret_cast<float*>(L.y) + vox * L.ldy + ch;

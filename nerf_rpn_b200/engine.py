@@ -91,9 +91,11 @@ class RPNInferenceEngine:
     def _pack(self, device):
         bb, hd = self.backbone, self.head
         L = {}
-        self.kind = "vgg" if type(bb).__name__ == "VGG_FPN" else "resnet"
+        self.kind = {"VGG_FPN": "vgg", "SwinTransformer_FPN": "swin"}.get(type(bb).__name__, "resnet")
         if self.kind == "vgg":
             self._pack_vgg(L, device)
+        elif self.kind == "swin":
+            self._pack_swin(L, device)
         else:
             self._pack_resnet(L, device)
         if hd is None:
@@ -115,6 +117,38 @@ class RPNInferenceEngine:
         L["pred"] = _Conv(w, b, device=device, cout_pad_to=128)
         self.layers = L
         self._plans.clear()
+
+    def _pack_swin(self, L, device):
+        """SwinTransformer_FPN (feature_extractor.py:689-789). Every Linear becomes a 1x1x1 conv of the tcgen05 kernel; widths
+        that are not multiples of 64 (96 at stage 0) live in rows padded with zero channels."""
+        bb = self.backbone
+        f32 = lambda t: t.detach().float().to(device).contiguous()
+        pe_conv, pe_ln = bb.patch_partition[0], bb.patch_partition[2]
+        C0 = pe_conv.weight.shape[0]
+        L["pe"] = _Conv(pe_conv.weight.reshape(C0, -1, 1, 1, 1), pe_conv.bias, device=device)
+        L["pe_ln"] = (f32(pe_ln.weight), f32(pe_ln.bias), float(pe_ln.eps))
+        stages = []
+        for si, stage in enumerate(bb.stages):
+            mods = list(stage.children())
+            st = {"merge": None, "blocks": []}
+            if si > 0:
+                pm = mods[0]; mods = mods[1:]
+                st["merge"] = dict(ln=(f32(pm.norm.weight), f32(pm.norm.bias), float(pm.norm.eps)), c_in=pm.dim,
+                                   red=_Conv(pm.reduction.weight.reshape(pm.reduction.weight.shape[0], -1, 1, 1, 1), None, device=device))
+            for blk in mods:
+                a = blk.attn
+                C = a.qkv.weight.shape[1]
+                lin = lambda m, act=0: _Conv(m.weight.reshape(m.weight.shape[0], -1, 1, 1, 1), m.bias, relu=act, device=device)
+                st["blocks"].append(dict(
+                    C=C, heads=a.num_heads, shift=int(a.shift_size[0]),
+                    ln1=(f32(blk.norm1.weight), f32(blk.norm1.bias), float(blk.norm1.eps)),
+                    ln2=(f32(blk.norm2.weight), f32(blk.norm2.bias), float(blk.norm2.eps)),
+                    qkv=lin(a.qkv), qkv_bias=f32(a.qkv.bias), table=f32(a.relative_position_bias_table),
+                    proj=lin(a.proj), mlp0=lin(blk.mlp[0], 2), mlp3=lin(blk.mlp[3])))
+            stages.append(st)
+        L["swin_stages"] = stages
+        L["lat"] = [_Conv(m.weight, m.bias, device=device) for m in bb.fpn_neck.lateral_convs]
+        L["fpn"] = [_Conv(m.weight, m.bias, device=device) for m in bb.fpn_neck.fpn_convs]
 
     def _pack_fcos(self, L, device):
         """FCOSHead (fcos/fcos.py:43-102): two towers of num_convs x [Conv3d 3^3 + GroupNorm(32) + ReLU] shared over levels,
@@ -262,7 +296,7 @@ class _Plan:
 
         self.input = torch.empty((n, 4, X, Y, Z), dtype=torch.float32, device=device)
         self._buf, self._conv = buf, conv
-        feats = self._build_vgg(L, n, dims, bf) if eng.kind == "vgg" else self._build_resnet(L, n, dims, bf)
+        feats = {"vgg": self._build_vgg, "swin": self._build_swin}.get(eng.kind, self._build_resnet)(L, n, dims, bf)
         self.features = [f for f, _ in feats]
         self.feat_dims = [d for _, d in feats]
 
@@ -402,6 +436,78 @@ class _Plan:
                     x, xd = y, od
             stage_out.append((x, xd))
         # FPN: laterals top-down (in-place accumulation in the reference), then a 3^3 conv on every level
+        lat = [None] * 4
+        for i in range(3, -1, -1):
+            f, fd = stage_out[i]
+            q = buf(fd, 256)
+            if i == 3:
+                conv(L["lat"][i], [f], [q], [fd], [fd], name=f"fpn.lateral{i}")
+            else:
+                conv(L["lat"][i], [f], [q], [fd], [fd], res=[lat[i + 1][0]], res_dims=[lat[i + 1][1]], name=f"fpn.lateral{i}+up")
+            lat[i] = (q, fd)
+        feats = []
+        for i in range(4):
+            q, qd = lat[i]
+            o = buf(qd, 256)
+            conv(L["fpn"][i], [q], [o], [qd], [qd], name=f"fpn.conv{i}")
+            feats.append((o, qd))
+        return feats
+
+    def _build_swin(self, L, n, dims, bf):
+        """SwinTransformer_FPN.forward (feature_extractor.py:781-789): patch embedding, 4 stages of [PatchMerging] + blocks
+        (x + attn(LN x); x + MLP(LN x)), FPN neck. Token grids are (n, H, W, D, ld) with ld = C rounded up to 64."""
+        device = self.device
+        buf, conv = self._buf, self._conv
+        pad64 = lambda c: (c + 63) // 64 * 64
+        zbuf = lambda d, c: torch.zeros((n, *d, c), dtype=torch.bfloat16, device=device)      # pad channels must stay zero
+        def add(fn, name):
+            self.launches.append(fn); self.names[id(fn)] = (name, 0.0)
+        X, Y, Z = dims
+        td = (X // 4, Y // 4, Z // 4)
+        self.packed = torch.empty((n, *td, 256), **bf)
+        add(lambda: ops.patch_embed_pack(self.input, self.packed), "swin.patch_embed_pack")
+        C = L["pe"].cout
+        e = zbuf(td, pad64(C))
+        conv(L["pe"], [self.packed], [e], [td], [td], name="swin.patch_embed(4x4x4 s4 as GEMM)")
+        x = zbuf(td, pad64(C))
+        g, b, eps = L["pe_ln"]
+        add(lambda i=e, o=x, c=C, g=g, b=b, eps=eps: ops.layernorm(i, o, c, g, b, eps), "swin.patch_embed.ln")
+        stage_out = []
+        for si, st in enumerate(L["swin_stages"]):
+            if st["merge"] is not None:
+                m = st["merge"]
+                od = tuple((v + 1) // 2 for v in td)
+                gathered = torch.empty((n, *od, 8 * m["c_in"]), **bf)
+                g, b, eps = m["ln"]
+                add(lambda i=x, o=gathered, c=m["c_in"], g=g, b=b, eps=eps: ops.patch_merge_ln(i, o, c, g, b, eps), f"swin{si}.patch_merge.gather+ln")
+                C = m["red"].cout
+                x = zbuf(od, pad64(C))
+                conv(m["red"], [gathered], [x], [od], [od], name=f"swin{si}.patch_merge.reduction")
+                td = od
+            Cp = pad64(C)
+            t = zbuf(td, Cp)                                   # LayerNorm output (scratch, reused by every block of the stage)
+            qkv = torch.empty((n, *td, 3 * C), **bf)
+            att = zbuf(td, Cp)
+            hid = torch.empty((n, *td, 4 * C), **bf)
+            ring = [zbuf(td, Cp), zbuf(td, Cp), x]             # residual stream rotates through three buffers
+            ri = 0
+            for bi, blk in enumerate(st["blocks"]):
+                g1, b1, e1 = blk["ln1"]; g2, b2, e2 = blk["ln2"]
+                add(lambda i=x, o=t, c=C, g=g1, b=b1, eps=e1: ops.layernorm(i, o, c, g, b, eps), f"swin{si}.ln1")
+                conv(blk["qkv"], [t], [qkv], [td], [td], name=f"swin{si}.qkv")
+                add(lambda q=qkv, o=att, bb_=blk["qkv_bias"], tb=blk["table"], c=C, h=blk["heads"], s=blk["shift"]:
+                    ops.window_attention(q, o, bb_, tb, c, h, s), f"swin{si}.window_attention(shift={blk['shift']})")
+                x2 = ring[ri % 3]; ri += 1
+                if x2 is x:
+                    x2 = ring[ri % 3]; ri += 1
+                conv(blk["proj"], [att], [x2], [td], [td], res=[x], res_dims=[td], name=f"swin{si}.proj+res")
+                add(lambda i=x2, o=t, c=C, g=g2, b=b2, eps=e2: ops.layernorm(i, o, c, g, b, eps), f"swin{si}.ln2")
+                conv(blk["mlp0"], [t], [hid], [td], [td], name=f"swin{si}.mlp.fc1+gelu")
+                x3 = [r for r in ring if r is not x and r is not x2][0]
+                conv(blk["mlp3"], [hid], [x3], [td], [td], res=[x2], res_dims=[td], name=f"swin{si}.mlp.fc2+res")
+                x = x3
+            # the stage output must survive the next stage's scratch: it is only read (by patch merging and the FPN lateral)
+            stage_out.append((x, td))
         lat = [None] * 4
         for i in range(3, -1, -1):
             f, fd = stage_out[i]

@@ -124,7 +124,7 @@ def _conv_desc(levels, w, shift, cin, cout, taps, stride, relu, out_fp32) -> Con
     for t, off in enumerate(taps):
         for k in range(3):
             d.tap_off[t][k] = int(off[k])
-    d.stride, d.relu, d.out_fp32 = int(stride), int(bool(relu)), int(bool(out_fp32))
+    d.stride, d.relu, d.out_fp32 = int(stride), int(relu), int(bool(out_fp32))      # relu: 0 none, 1 ReLU, 2 GELU
     d.w, d.shift = w.data_ptr(), shift.data_ptr()
     d.n_levels = len(levels)
     for i, L in enumerate(levels):
@@ -297,3 +297,33 @@ def fcos_proposals(desc: FcosDesc, device, out=None, workspace: Optional[torch.T
     check(lib().nrpn_fcos_proposals(ctypes.byref(desc), _ptr(boxes), _ptr(scores), _ptr(count), _ptr(ws), ws.numel(), _stream()),
           "fcos_proposals")
     return boxes, scores, count
+
+
+# ------------------------------------------------------------------------------------------------ Swin
+def patch_embed_pack(grid: torch.Tensor, out: torch.Tensor):
+    grid = _req(grid, torch.float32, "grid")
+    n, c, x, y, z = grid.shape
+    check(lib().nrpn_patch_embed_pack(_ptr(grid), n, x, y, z, _ptr(out), _stream()), "patch_embed_pack")
+    return out
+
+
+def layernorm(x: torch.Tensor, out: torch.Tensor, c: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5):
+    """x, out: (..., ld) bf16 channels-last; normalises the first c channels of every row."""
+    tokens = x.numel() // x.shape[-1]
+    check(lib().nrpn_layernorm(_ptr(x), int(x.shape[-1]), _ptr(out), int(out.shape[-1]), tokens, int(c), _ptr(gamma), _ptr(beta),
+                               float(eps), _stream()), "layernorm")
+    return out
+
+
+def patch_merge_ln(x: torch.Tensor, out: torch.Tensor, c: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5):
+    n, h, w, d, ld = x.shape
+    check(lib().nrpn_patch_merge_ln(_ptr(x), int(ld), n, h, w, d, int(c), _ptr(out), _ptr(gamma), _ptr(beta), float(eps), _stream()),
+          "patch_merge_ln")
+    return out
+
+
+def window_attention(qkv: torch.Tensor, out: torch.Tensor, qkv_bias: torch.Tensor, table: torch.Tensor, c: int, heads: int, shift: int):
+    n, h, w, d, ld = qkv.shape
+    check(lib().nrpn_window_attention(_ptr(qkv), int(ld), _ptr(out), int(out.shape[-1]), _ptr(qkv_bias), _ptr(table), n, h, w, d, int(c),
+                                      int(heads), int(shift), _stream()), "window_attention")
+    return out

@@ -94,3 +94,35 @@ def build_fcos_small(ns, rotated, golden, pre_n=2500, post_n=2500):
 def seed1000_input(dims=(32, 48, 40)):
     gi = torch.Generator().manual_seed(1000)
     return torch.rand(*dims, 4, generator=gi).permute(3, 0, 1, 2).contiguous()
+
+
+SWIN_S = dict(patch_size=[4, 4, 4], embed_dim=96, depths=[2, 2, 18, 2], num_heads=[3, 6, 12, 24], window_size=[4, 4, 4],
+              stochastic_depth_prob=0.1, expand_dim=True)
+
+
+def build_swin_fcos_small(ns, golden):
+    """FCOSOverNeRF(Swin-S + FPN), OBB, with the weights tools/make_golden.py:gen_swin_small gave the reference."""
+    torch.manual_seed(0)
+    backbone = ns.SwinTransformer_FPN(**SWIN_S)
+    model = ns.FCOSOverNeRF(fcos_args(True), backbone, [4, 8, 16, 32])
+    head = model.fcos_module.head
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, (torch.nn.LayerNorm, torch.nn.GroupNorm)):
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+        for name, p in backbone.named_parameters():
+            if name.endswith("relative_position_bias_table"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+            if name.endswith("qkv.bias") or name.endswith("proj.bias") or name.endswith("mlp.0.bias") or name.endswith("mlp.3.bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+        for i, sc in enumerate(head.scales):
+            sc.scale.fill_(1.0 + 0.1 * i)
+        head.cls_logits.weight.copy_(torch.from_numpy(golden["cls_w"])); head.cls_logits.bias.fill_(-1.0)
+        head.bbox_pred.weight.copy_(torch.from_numpy(golden["bbox_w"])); head.bbox_pred.bias.fill_(1.0)
+        head.centerness.weight.copy_(torch.from_numpy(golden["ctr_w"]))
+    assert abs(backbone.patch_partition[0].weight.double().sum().item() - float(golden["pe_sum"])) < 1e-9
+    assert abs(backbone.stages[2][5].attn.qkv.weight.double().sum().item() - float(golden["qkv_sum"])) < 1e-9, "seeded Swin weights differ"
+    assert abs(head.cls_tower[0].weight.double().sum().item() - float(golden["tower_sum"])) < 1e-9
+    return model

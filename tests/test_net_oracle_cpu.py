@@ -65,3 +65,22 @@ def test_vgg_fpn_oracle_matches_reference(golden_dir):
     assert b.shape == g["proposals"].shape
     np.testing.assert_allclose(b, g["proposals"], rtol=1e-3, atol=1e-2)
     np.testing.assert_array_equal(lv, g["level_index"])
+
+
+def test_swin_fpn_oracle_matches_reference(golden_dir):
+    """BASELINE config 3 backbone (Swin-S 3-D shifted-window attention + FPN) on a 40x52x34 grid: the module mirror reproduces
+    the reference's 365 seeded tensors, the functional oracle its feature maps."""
+    from nerf_rpn_b200.model.fcos import fcos as fcos_mod
+
+    class NSW(NS):
+        SwinTransformer_FPN = feature_extractor.SwinTransformer_FPN
+        FCOSOverNeRF = fcos_mod.FCOSOverNeRF
+    g = np.load(os.path.join(golden_dir, "swin_small_fcos_obb.npz"))
+    model = recipes.build_swin_fcos_small(NSW, g)
+    sd = model.backbone.state_dict()
+    assert len(sd) == 365
+    x = recipes.seed1000_input((40, 52, 34))[None]
+    feats = onet.swin_fpn_forward(sd, x, recipes.SWIN_S["depths"], recipes.SWIN_S["num_heads"])
+    for i, f in enumerate(feats):
+        ref = torch.from_numpy(g[f"feat{i}"].astype(np.float32))
+        assert ((f[0] - ref).norm() / ref.norm()).item() < 1e-3

@@ -25,7 +25,7 @@ torch.cuda.is_available = lambda: False
 
 from model.anchor import AnchorGenerator3D, RPNHead  # noqa: E402
 from model.coder import AABBCoder, MidpointOffsetCoder  # noqa: E402
-from model.feature_extractor import Bottleneck, ResNet_FPN_256, VGG_FPN  # noqa: E402
+from model.feature_extractor import Bottleneck, ResNet_FPN_256, SwinTransformer_FPN, VGG_FPN  # noqa: E402
 from model.nerf_rpn import NeRFRegionProposalNetwork  # noqa: E402
 from model.rotated_iou.box_intersection_2d import (box_in_box_th, box_intersection_th,  # noqa: E402
                                                    build_vertices)
@@ -304,7 +304,66 @@ def gen_fcos_small():
             print(name, "boxes", tuple(boxes[0].shape), "scores", float(scores[0].min()), float(scores[0].max()))
 
 
+SWIN_S = dict(patch_size=[4, 4, 4], embed_dim=96, depths=[2, 2, 18, 2], num_heads=[3, 6, 12, 24], window_size=[4, 4, 4],
+              stochastic_depth_prob=0.1, expand_dim=True)
+
+
+def gen_swin_small():
+    """BASELINE config 3 at a small size: Swin-S 3-D window-attention backbone + FPN + FCOS head (OBB), reference forward on CPU.
+    Grid 40x52x34 -> token grid 10x13x8 (padded to 12x16x8 inside the attention: exercises padding, shift and masks)."""
+    import argparse
+    from model.fcos.fcos import FCOSOverNeRF
+    args = argparse.Namespace(num_convs=4, norm_reg_targets=True, centerness_on_reg=True, rotated_bbox=True, pre_nms_thresh=0.0,
+                              pre_nms_top_n=2500, nms_thresh=0.3, fpn_post_nms_top_n=2500, min_size=0.0, center_sampling_radius=1.5,
+                              iou_loss_type="iou", use_additional_l1_loss=False, proj2d_loss_weight=0.0)
+    torch.manual_seed(0)
+    backbone = SwinTransformer_FPN(**SWIN_S)
+    model = FCOSOverNeRF(args, backbone, [4, 8, 16, 32])
+    head = model.fcos_module.head
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, (torch.nn.LayerNorm, torch.nn.GroupNorm)):
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+        for name, p in backbone.named_parameters():
+            if name.endswith("relative_position_bias_table"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+            if name.endswith("qkv.bias") or name.endswith("proj.bias") or name.endswith("mlp.0.bias") or name.endswith("mlp.3.bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+        for i, sc in enumerate(head.scales):
+            sc.scale.fill_(1.0 + 0.1 * i)
+    gi = torch.Generator().manual_seed(1000)
+    grid = torch.rand(40, 52, 34, 4, generator=gi)
+    x = grid.permute(3, 0, 1, 2).contiguous()
+    model.eval()
+    with torch.no_grad():
+        feats = list(backbone(x[None]))
+        ct = [head.cls_tower(f) for f in feats]; bt = [head.bbox_tower(f) for f in feats]
+        s_c = torch.cat([head.cls_logits(t).flatten() for t in ct]).std().item()
+        s_b = torch.cat([head.bbox_pred(t).flatten() for t in bt]).std().item()
+        s_t = torch.cat([head.centerness(t).flatten() for t in bt]).std().item()
+        head.cls_logits.weight.mul_(2.0 / s_c); head.cls_logits.bias.fill_(-1.0)
+        head.bbox_pred.weight.mul_(1.5 / s_b); head.bbox_pred.bias.fill_(1.0)
+        head.centerness.weight.mul_(1.0 / s_t)
+        boxes, _, scores = model([x])
+        logits, bbox_reg, ctr = head(feats)
+    out = dict(boxes=boxes[0].numpy(), scores=scores[0].numpy(),
+               pe_sum=np.float64(backbone.patch_partition[0].weight.double().sum().item()),
+               qkv_sum=np.float64(backbone.stages[2][5].attn.qkv.weight.double().sum().item()),
+               tower_sum=np.float64(head.cls_tower[0].weight.double().sum().item()),
+               cls_w=head.cls_logits.weight.detach().numpy(), bbox_w=head.bbox_pred.weight.detach().numpy(),
+               ctr_w=head.centerness.weight.detach().numpy())
+    for i in range(4):
+        out[f"feat{i}"] = feats[i][0].numpy().astype(np.float16)
+        out[f"logits{i}"] = logits[i][0].numpy()
+    np.savez_compressed(os.path.join(OUT, "swin_small_fcos_obb.npz"), **out)
+    print("swin_small_fcos_obb.npz boxes", tuple(boxes[0].shape), [tuple(f.shape) for f in feats], len(backbone.state_dict()))
+
+
 if __name__ == "__main__":
+    if "--swin-only" in sys.argv:
+        gen_swin_small(); sys.exit(0)
     if "--fcos-only" in sys.argv:
         gen_fcos_small(); sys.exit(0)
     gen_vgg_small()
@@ -315,3 +374,4 @@ if __name__ == "__main__":
     gen_decode_anchors()
     gen_rpn_small()
     gen_fcos_small()
+    gen_swin_small()
