@@ -9,6 +9,8 @@ import nerf_rpn_b200.model.nerf_rpn  # noqa: F401
 import nerf_rpn_b200.model.rpn  # noqa: F401
 import nerf_rpn_b200.model.utils  # noqa: F401
 import nerf_rpn_b200.model.rotated_iou.oriented_iou_loss  # noqa: F401
+import nerf_rpn_b200.model.fpn  # noqa: F401
+import nerf_rpn_b200.model.fcos.fcos  # noqa: F401
 
 sys.modules["model"] = _m
 for _name, _mod in list(sys.modules.items()):

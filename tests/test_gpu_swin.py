@@ -29,7 +29,7 @@ def test_layernorm_and_patch_merge_kernels():
         out = torch.zeros_like(x)
         ops.layernorm(x, out, C, gamma, beta, 1e-5)
         ref = F.layer_norm(x[..., :C].float(), (C,), gamma, beta, 1e-5)
-        assert (out[..., :C].float() - ref).abs().max().item() < 3e-2 and out[..., C:].abs().max().item() == 0
+        assert (out[..., :C].float() - ref).abs().max().item() < 3e-2 and (ld == C or out[..., C:].abs().max().item() == 0)
         gamma8 = torch.rand(8 * C, device="cuda", generator=g) + 0.5; beta8 = torch.randn(8 * C, device="cuda", generator=g)
         merged = torch.empty((2, 3, 4, 2, 8 * C), device="cuda", dtype=torch.bfloat16)
         ops.patch_merge_ln(x, merged, C, gamma8, beta8, 1e-5)
