@@ -8,7 +8,7 @@
 
 namespace nrpn {
 
-constexpr int kGnBlocks = 64;        // CTAs per (level, sample)
+constexpr int kGnMaxBlocks = 512;    // CTAs per (level, sample): ceil(voxels / 64), at most this many
 constexpr int kGnGroups = 32;
 
 struct GnDev {
@@ -16,19 +16,41 @@ struct GnDev {
     float eps;
     __nv_bfloat16* x[NRPN_CONV_MAX_LEVELS];
     int voxels[NRPN_CONV_MAX_LEVELS];
+    int blocks[NRPN_CONV_MAX_LEVELS];      // CTAs per sample for this level
+    int block_begin[NRPN_CONV_MAX_LEVELS]; // first CTA index of the level (levels are laid out back to back, samples inside)
     const float* gamma; const float* beta;
-    double* partial;                 // [level][sample][block][group][2]
+    double* partial;                 // [global CTA][group][2]
 };
 
+__device__ __forceinline__ void gn_locate(const GnDev& P, int cta, int& l, int& smp, int& blk) {
+    l = 0;
+#pragma unroll
+    for (int i = 1; i < NRPN_CONV_MAX_LEVELS; ++i) if (i < P.n_levels && cta >= P.block_begin[i]) l = i;
+    const int r = cta - P.block_begin[l];
+    smp = r / P.blocks[l]; blk = r - smp * P.blocks[l];
+}
+
 __global__ void __launch_bounds__(256) gn_stats_kernel(GnDev P) {
-    const int blk = blockIdx.x % kGnBlocks;
-    const int ls = blockIdx.x / kGnBlocks;
-    const int smp = ls % P.n, l = ls / P.n;
-    const int V = P.voxels[l];
+    int l, smp, blk;
+    gn_locate(P, blockIdx.x, l, smp, blk);
+    const int V = P.voxels[l], nb = P.blocks[l];
     const __nv_bfloat16* x = P.x[l] + (size_t)smp * V * 256;
     const int g = threadIdx.x & 31, r = threadIdx.x >> 5;       // 32 groups x 8 rows per CTA step
     float s = 0.f, q = 0.f;
-    for (int v = blk * 8 + r; v < V; v += kGnBlocks * 8) {
+    const int step = nb * 8;
+    int v = blk * 8 + r;
+    for (; v + 3 * step < V; v += 4 * step) {                  // four independent 16-byte loads in flight per thread
+        uint4 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) raw[u] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)(v + u * step) * 256 + g * 8));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); s += f.x + f.y; q += f.x * f.x + f.y * f.y; }
+        }
+    }
+    for (; v < V; v += step) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + (size_t)v * 256 + g * 8));
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
@@ -41,38 +63,44 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnDev P) {
         double a = 0.0, b = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { a += ss[i][g]; b += sq[i][g]; }
-        double* o = P.partial + ((((size_t)l * P.n + smp) * kGnBlocks + blk) * kGnGroups + g) * 2;
+        double* o = P.partial + ((size_t)blockIdx.x * kGnGroups + g) * 2;
         o[0] = a; o[1] = b;
     }
 }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnDev P) {
-    const int blk = blockIdx.x % kGnBlocks;
-    const int ls = blockIdx.x / kGnBlocks;
-    const int smp = ls % P.n, l = ls / P.n;
-    const int V = P.voxels[l];
+    int l, smp, blk;
+    gn_locate(P, blockIdx.x, l, smp, blk);
+    const int V = P.voxels[l], nb = P.blocks[l];
     __nv_bfloat16* x = P.x[l] + (size_t)smp * V * 256;
     const int g = threadIdx.x & 31, r = threadIdx.x >> 5;
+    __shared__ double red[8][32][2];
     __shared__ float mean_s[32], rstd_s[32];
-    if (threadIdx.x < 32) {
-        const double* p = P.partial + (((size_t)l * P.n + smp) * kGnBlocks) * kGnGroups * 2;
+    {   // every CTA reduces the partial sums of its (level, sample) in the same fixed order: bit-reproducible
+        const double* p = P.partial + ((size_t)(P.block_begin[l] + smp * nb) * kGnGroups) * 2;
         double a = 0.0, b = 0.0;
-        for (int i = 0; i < kGnBlocks; ++i) { a += p[((size_t)i * kGnGroups + threadIdx.x) * 2]; b += p[((size_t)i * kGnGroups + threadIdx.x) * 2 + 1]; }
+        for (int i = r; i < nb; i += 8) { a += p[((size_t)i * kGnGroups + g) * 2]; b += p[((size_t)i * kGnGroups + g) * 2 + 1]; }
+        red[r][g][0] = a; red[r][g][1] = b;
+    }
+    __syncthreads();
+    if (r == 0) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a += red[i][g][0]; b += red[i][g][1]; }
         const double cnt = (double)V * 8.0;
         const double m = a / cnt;
         double var = b / cnt - m * m;                      // biased variance, as torch.nn.GroupNorm
         if (var < 0.0) var = 0.0;
-        mean_s[threadIdx.x] = (float)m;
-        rstd_s[threadIdx.x] = (float)(1.0 / sqrt(var + (double)P.eps));
+        mean_s[g] = (float)m;
+        rstd_s[g] = (float)(1.0 / sqrt(var + (double)P.eps));
     }
     __syncthreads();
     const float mean = mean_s[g], rstd = rstd_s[g];
     float ga[8], be[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ga[i] = __ldg(P.gamma + g * 8 + i) * rstd; be[i] = __ldg(P.beta + g * 8 + i) - mean * ga[i]; }
-    for (int v = blk * 8 + r; v < V; v += kGnBlocks * 8) {
-        uint4* ptr = reinterpret_cast<uint4*>(x + (size_t)v * 256 + g * 8);
-        uint4 raw = *ptr;
+    const int step = nb * 8;
+    auto apply = [&](uint4 raw) {
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -81,7 +109,19 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnDev P) {
             if (P.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
             h[i] = __floats2bfloat162_rn(f.x, f.y);
         }
-        *ptr = raw;
+        return raw;
+    };
+    int v = blk * 8 + r;
+    for (; v + 3 * step < V; v += 4 * step) {
+        uint4 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) raw[u] = *reinterpret_cast<const uint4*>(x + (size_t)(v + u * step) * 256 + g * 8);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(x + (size_t)(v + u * step) * 256 + g * 8) = apply(raw[u]);
+    }
+    for (; v < V; v += step) {
+        uint4* ptr = reinterpret_cast<uint4*>(x + (size_t)v * 256 + g * 8);
+        *ptr = apply(*ptr);
     }
 }
 
@@ -94,7 +134,7 @@ extern "C" {
 
 size_t nrpn_groupnorm_workspace_bytes(int n_levels, int n) {
     if (n_levels < 1 || n_levels > NRPN_CONV_MAX_LEVELS || n < 1) return 0;
-    return (size_t)n_levels * n * kGnBlocks * kGnGroups * 2 * sizeof(double);
+    return (size_t)n_levels * n * kGnMaxBlocks * kGnGroups * 2 * sizeof(double);
 }
 
 int nrpn_groupnorm_relu(const nrpn_gn_level* levels, int n_levels, int n, int c, int groups, const float* gamma,
@@ -105,11 +145,15 @@ int nrpn_groupnorm_relu(const nrpn_gn_level* levels, int n_levels, int n, int c,
     GnDev P;
     P.n_levels = n_levels; P.n = n; P.relu = relu; P.eps = eps; P.gamma = gamma; P.beta = beta;
     P.partial = reinterpret_cast<double*>(workspace);
+    int grid = 0;
     for (int l = 0; l < n_levels; ++l) {
         if (!levels[l].x || levels[l].voxels < 1) return NRPN_ERR_INVALID;
         P.x[l] = reinterpret_cast<__nv_bfloat16*>(levels[l].x); P.voxels[l] = levels[l].voxels;
+        int nb = ceil_div(levels[l].voxels, 64);
+        if (nb > kGnMaxBlocks) nb = kGnMaxBlocks;
+        P.blocks[l] = nb; P.block_begin[l] = grid;
+        grid += nb * n;
     }
-    const int grid = n_levels * n * kGnBlocks;
     gn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
     NRPN_LAUNCH_CHECK();
     gn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);

@@ -29,14 +29,15 @@ def test_layernorm_and_patch_merge_kernels():
         out = torch.zeros_like(x)
         ops.layernorm(x, out, C, gamma, beta, 1e-5)
         ref = F.layer_norm(x[..., :C].float(), (C,), gamma, beta, 1e-5)
-        assert (out[..., :C].float() - ref).abs().max().item() < 3e-2 and (ld == C or out[..., C:].abs().max().item() == 0)
+        assert (out[..., :C].float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item()) + 1e-2, 'layernorm'
+        assert ld == C or out[..., C:].abs().max().item() == 0, 'pad channels must stay zero'
         gamma8 = torch.rand(8 * C, device="cuda", generator=g) + 0.5; beta8 = torch.randn(8 * C, device="cuda", generator=g)
         merged = torch.empty((2, 3, 4, 2, 8 * C), device="cuda", dtype=torch.bfloat16)
         ops.patch_merge_ln(x, merged, C, gamma8, beta8, 1e-5)
         xp = F.pad(x[..., :C].float(), (0, 0, 0, 1, 0, 1, 0, 1))
         parts = [xp[:, i::2, j::2, k::2, :] for (i, j, k) in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0), (0, 0, 1), (1, 0, 1), (0, 1, 1), (1, 1, 1))]
         refm = F.layer_norm(torch.cat(parts, -1), (8 * C,), gamma8, beta8, 1e-5)
-        assert (merged.float() - refm).abs().max().item() < 3e-2
+        assert (merged.float() - refm).abs().max().item() < 1e-2 * max(1.0, refm.abs().max().item()) + 1e-2, 'patch merge'
 
 
 def test_patch_embed_pack_and_gelu_gemm():
