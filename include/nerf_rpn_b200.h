@@ -120,6 +120,9 @@ typedef struct {
 
 /* Padding granularity of the output-channel axis for this cout (64, 128 or 256): w / shift must be padded to a multiple. */
 int nrpn_conv3d_block_n(int cout);
+/* Name of the kernel variant nrpn_conv3d_fprop would launch for this descriptor ("slab<4x16x8,N64>", "igemm<256,4,1>", ...;
+ * "invalid" / "unsupported" when it would be rejected).  Pure host logic: pointers inside the descriptor are not dereferenced. */
+const char *nrpn_conv3d_variant(const nrpn_conv_desc *desc);
 /* Layers with few output tiles and a long reduction are split along K over several CTAs; each stores its partial tile
  * into its own fp32 slab and the last CTA to arrive sums the slabs in a fixed order (bit-reproducible).  Returns the
  * bytes such a layer wants (0: the layer is not split).  The first 256-byte-aligned counters region must be zero-filled

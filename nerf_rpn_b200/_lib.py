@@ -76,6 +76,7 @@ _SIGNATURES = {
     "nrpn_nms": (ctypes.c_int, [c_f32p, ctypes.c_int, c_f32p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, c_stream]),
     "nrpn_conv3d_block_n": (ctypes.c_int, [ctypes.c_int]),
+    "nrpn_conv3d_variant": (ctypes.c_char_p, [ctypes.POINTER(ConvDesc)]),
     "nrpn_conv3d_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvDesc)]),
     "nrpn_conv3d_fprop": (ctypes.c_int, [ctypes.POINTER(ConvDesc), c_stream]),
     "nrpn_pack_stem_input": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

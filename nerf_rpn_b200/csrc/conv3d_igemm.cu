@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "tcgen05.cuh"
+#include "conv_internal.cuh"
 
 namespace nrpn {
 
@@ -98,8 +99,9 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
     uint32_t* ticket_slot = tmem_slot + 1;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (one thread)
-        if (lane == 0) {
+        // ------------------------------------------------------------------ TMA producer (whole warp walks, one elected lane issues)
+        {
+            const bool leader = ptx::elect_one();
             int stage = 0; uint32_t phase = 0;
             for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
                 const int split = item % P.splits, tile = item / P.splits;
@@ -114,24 +116,29 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                 const int tiy = t % L.ty; t /= L.ty;
                 const int tix = t % L.tx; const int nb = t / L.tx;
                 const int x0 = tix * L.bx, y0 = tiy * L.by, z0 = tiz * L.bz, n0 = n_tile * BLOCK_N;
-                {
-                    for (int kb = kb0; kb < kb1; ++kb) {
-                        const int tap = kb / P.kc_blocks, kc = kb - tap * P.kc_blocks;
-                        const int dx = P.tap[tap][0], dy = P.tap[tap][1], dz = P.tap[tap][2];
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int tap = kb / P.kc_blocks, kc = kb - tap * P.kc_blocks;
+                    const int dx = P.tap[tap][0], dy = P.tap[tap][1], dz = P.tap[tap][2];
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (leader) {
                         uint8_t* sa = smem + stage * kStageBytes;
                         uint8_t* sb = sa + kABytes;
                         ptx::mbar_expect_tx(&full_bar[stage], kStageBytes);
                         ptx::tma_load_5d(sa, &maps.x[l], &full_bar[stage], kc * kBlockK, z0 + dz, y0 + dy, x0 + dx, nb);
                         ptx::tma_load_3d(sb, &maps.w, &full_bar[stage], kc * kBlockK, n0, tap);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer
+        // The whole warp walks the warp-uniform loops and waits; one elected lane (elect.sync) issues tcgen05.mma and
+        // tcgen05.commit, which keeps descriptors in uniform registers (no per-instruction waterfall loop: at N = 64 an
+        // MMA lasts 48 clk and a divergent `if (lane == 0)` issue path costs more than that, profiles/r01_ncu_slab_*.md).
+        {
+            const bool leader = ptx::elect_one();
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
@@ -146,15 +153,19 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                     const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
                     const uint64_t da = ptx::make_desc_sw128(sa);
                     const uint64_t db = ptx::make_desc_sw128(sa + kABytes);
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in the >>4 address field
-                        ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in the >>4 address field
+                            ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | k) ? 1u : 0u);
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);        // frees the smem slot once the MMAs have read it
                     }
-                    ptx::umma_commit(&empty_bar[stage]);        // frees the smem slot once the MMAs have read it
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                ptx::umma_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
+                if (leader) ptx::umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -338,24 +349,6 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
 }
 
 // ------------------------------------------------------------------------------------------------ host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 template <int BLOCK_N, int STAGES, int MIN_BLOCKS>
 static int launch_conv(const ConvMaps& maps, const ConvDev& P, int total_tiles, cudaStream_t st) {
     constexpr int smem = STAGES * (kABytes + BLOCK_N * kBlockK * 2) + 1024 + 256;
@@ -443,6 +436,16 @@ size_t nrpn_conv3d_workspace_bytes(const nrpn_conv_desc* d) {
 
 int nrpn_conv3d_block_n(int cout) { return cout <= 64 ? 64 : (cout <= 128 ? 128 : 256); }
 
+const char* nrpn_conv3d_variant(const nrpn_conv_desc* d) {
+    if (!d || d->n_taps < 1 || d->n_taps > NRPN_CONV_MAX_TAPS || d->n_levels < 1 || d->n_levels > NRPN_CONV_MAX_LEVELS) return "invalid";
+    if (d->cin < 64 || d->cin % 64 != 0 || d->cout < 8 || d->cout % 8 != 0 || (d->stride != 1 && d->stride != 2)) return "unsupported";
+    if (conv3d_slab_eligible(d)) return "slab<4x16x8,N64>";
+    ConvGeom g;
+    if (conv_geometry(d, g) != NRPN_OK) return "invalid";
+    if (g.short_k) return "igemm<64,2,3>";
+    return g.block_n == 64 ? "igemm<64,8,1>" : (g.block_n == 128 ? "igemm<128,6,1>" : "igemm<256,4,1>");
+}
+
 int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
     if (!d || !d->w || !d->shift) return NRPN_ERR_INVALID;
     if (d->cin < 64 || d->cin % 64 != 0 || d->cout < 8 || d->cout % 8 != 0) return NRPN_ERR_UNSUPPORTED;
@@ -455,6 +458,7 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
     }
     EncodeTiledFn encode = get_encode();
     if (!encode) return NRPN_ERR_NO_DEVICE;
+    if (conv3d_slab_eligible(d)) return conv3d_slab_launch(d, (cudaStream_t)stream);
 
     // Weights are padded to nrpn_conv3d_block_n(cout) (a multiple of 64). Long reductions (3^3 taps) use the widest N tile
     // that fits, one CTA per SM, deep smem ring: tensor-pipe bound.  Short reductions (1^3 convs: at most 8 k-blocks) are

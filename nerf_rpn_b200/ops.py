@@ -146,6 +146,12 @@ def conv3d_workspace_bytes(levels, w, shift, cin, cout, taps, stride=1, relu=Fal
     return int(lib().nrpn_conv3d_workspace_bytes(ctypes.byref(d)))
 
 
+def conv3d_variant(levels, w, shift, cin, cout, taps, stride=1, relu=False, out_fp32=False) -> str:
+    """Which kernel variant nrpn_conv3d_fprop launches for this layer (host-side query, no launch)."""
+    d = _conv_desc(levels, w, shift, cin, cout, taps, stride, relu, out_fp32)
+    return lib().nrpn_conv3d_variant(ctypes.byref(d)).decode()
+
+
 def conv3d_fprop(levels: Sequence[ConvLevelArgs], w: torch.Tensor, shift: torch.Tensor, cin: int, cout: int,
                  taps: Sequence[Sequence[int]], stride: int = 1, relu: bool = False, out_fp32: bool = False,
                  workspace: Optional[torch.Tensor] = None):

@@ -182,3 +182,74 @@ def test_maxpool(ops):
         got = ops.maxpool3d_k3s2(x)
         ref = F.max_pool3d(x.float().permute(0, 4, 1, 2, 3), kernel_size=3, stride=2, padding=1).permute(0, 2, 3, 4, 1)
         torch.testing.assert_close(got.float(), ref, rtol=0, atol=0)
+
+
+def _stem_case(ops, dims, n, seed):
+    from nerf_rpn_b200 import packing
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.rand((n, 4, *dims), device="cuda", generator=g)
+    packed = ops.pack_stem_input(x)
+    w = torch.randn((64, 4, 7, 7, 7), device="cuda", generator=g) * 0.05
+    bias = torch.randn((64,), device="cuda", generator=g) * 0.1
+    wp, taps = packing.pack_stem_weight(w)
+    od = tuple((d + 1) // 2 for d in dims)
+    ref = F.relu(F.conv3d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias, stride=2, padding=3)).permute(0, 2, 3, 4, 1)
+    return packed, wp.cuda(), taps, bias, od, ref
+
+
+@pytest.mark.parametrize("dims,n", [((48, 64, 40), 1), ((42, 38, 54), 2), ((80, 96, 64), 2)])
+def test_slab_kernel_stem(ops, monkeypatch, dims, n):
+    """csrc/conv3d_slab.cu on the packed stem (4 x 4 x 2 taps, z offsets {-1, +1}): bf16 output routes to the halo-slab
+    kernel; it must agree with fp32 PyTorch on the bf16-rounded operands and with the brick kernel (NRPN_CONV_SLAB=0)."""
+    packed, wp, taps, bias, od, ref = _stem_case(ops, dims, n, 31)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NRPN_CONV_SLAB", mode)
+        y = torch.full((n, *od, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+        a = ops.ConvLevelArgs(packed, y, n, packed.shape[1:4], od, 64)
+        ops.conv3d_fprop([a], wp, bias, 64, 64, taps, relu=True)
+        torch.cuda.synchronize()
+        got = y.float()
+        assert not torch.isnan(got).any(), _diagnose(torch.nan_to_num(got, nan=1e9), ref, f"stem slab={mode}: unwritten outputs")
+        assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item(), _diagnose(got, ref, f"stem slab={mode}")
+        outs[mode] = got
+    # same products, different fp32 summation order, one bf16 rounding each
+    assert (outs["1"] - outs["0"]).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("dims,n", [((40, 64, 64), 1), ((13, 21, 11), 2), ((4, 16, 8), 1)])
+def test_slab_kernel_3x3x3(ops, monkeypatch, dims, n):
+    """ResNet layer1 conv2 shape (64 -> 64, 3^3, BN shift + ReLU): three z phases, ring wrap-around over > 148 tiles."""
+    g = torch.Generator(device="cuda").manual_seed(32)
+    x = torch.randn((n, *dims, 64), device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn((64, 64, 3, 3, 3), device="cuda", generator=g) / (64 * 27) ** 0.5
+    bias = torch.randn((64,), device="cuda", generator=g)
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NRPN_CONV_SLAB", mode)
+        outs, refs = run_conv(ops, x, w, bias, 1, True, None, False)
+        got[mode] = outs[0].float()
+        assert not torch.isnan(got[mode]).any(), f"slab={mode}: unwritten outputs"
+        assert (got[mode] - refs[0]).abs().max().item() <= 1e-2 * refs[0].abs().max().item(), _diagnose(got[mode], refs[0], f"3x3x3 slab={mode}")
+    assert (got["1"] - got["0"]).abs().max().item() <= 2 ** -7 * refs[0].abs().max().item()
+
+
+def test_slab_kernel_is_faster_than_brick(ops, monkeypatch):
+    """Not a timing gate (no thresholds on a shared box) -- prints both timings so the run log records the A/B."""
+    packed, wp, taps, bias, od, ref = _stem_case(ops, (160, 256, 256), 1, 33)
+    y = torch.empty((1, *od, 64), dtype=torch.bfloat16, device="cuda")
+    a = ops.ConvLevelArgs(packed, y, 1, packed.shape[1:4], od, 64)
+    ms = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NRPN_CONV_SLAB", mode)
+        for _ in range(3):
+            ops.conv3d_fprop([a], wp, bias, 64, 64, taps, relu=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.conv3d_fprop([a], wp, bias, 64, 64, taps, relu=True)
+        e1.record(); torch.cuda.synchronize()
+        ms[mode] = e0.elapsed_time(e1) / 10
+        got = y.float()
+        assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item(), _diagnose(got, ref, f"full-size stem slab={mode}")
+    print(f"\n[stem 160x256x256] slab {ms['1']:.3f} ms, brick {ms['0']:.3f} ms")

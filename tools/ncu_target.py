@@ -23,6 +23,10 @@ which = os.environ.get("NCU_TARGET", "head")
 torch.cuda.nvtx.range_push("target")
 if which == "head":
     plan.head_launches[1]()
+elif which == "stem":
+    plan.launches[1]()                                                    # stem conv (halo-slab kernel)
+elif which == "l0c2":
+    [f for f in plan.launches if "L0.c2" in plan.names.get(id(f), ("",))[0]][0]()
 elif which == "misc":
     plan.launches[0](); plan.launches[1](); plan.launches[2]()          # pack, stem conv, maxpool
     for f in plan._post[0]:
