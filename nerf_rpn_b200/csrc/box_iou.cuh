@@ -213,13 +213,18 @@ __device__ __forceinline__ float rect_inter_area(const float* __restrict__ c1, c
     return __fdiv_rn(fabsf(total), 2.0f);
 }
 
-// cal_iou_3d for one pair (oriented_iou_loss.py:82-107). a = "box1" (the picked box in NMS).
-__device__ __forceinline__ float iou3d_obb(const ObbPrep& a, const ObbPrep& b, bool allow_cull) {
-    if (allow_cull && a.cullable && b.cullable) {
-        const float dx = a.cx - b.cx, dy = a.cy - b.cy, rr = a.rad + b.rad;
-        if (dx * dx + dy * dy > rr * rr) return 0.0f;           // footprints cannot touch -> reference yields exactly 0
-        if (a.zmin > b.zmax || b.zmin > a.zmax) return 0.0f;     // z_overlap clamps to 0
-    }
+// Exact-zero test on the tail of a prepared record (floats 8..15: area, vol, zmin, zmax, cx, cy, rad, cullable): true only
+// when the reference arithmetic yields exactly 0 for the pair (disjoint bounding circles -> no vertex of the intersection
+// polygon; disjoint z ranges -> z_overlap clamps to 0).  Cheap enough to run on every pair before the full clip.
+__device__ __forceinline__ bool obb_surely_zero(const float* __restrict__ ta, const float* __restrict__ tb) {
+    if (!(__float_as_int(ta[7]) && __float_as_int(tb[7]))) return false;
+    const float dx = ta[4] - tb[4], dy = ta[5] - tb[5], rr = ta[6] + tb[6];
+    if (dx * dx + dy * dy > rr * rr) return true;
+    return ta[2] > tb[3] || tb[2] > ta[3];
+}
+
+// cal_iou_3d for one pair without the shortcut (oriented_iou_loss.py:82-107). a = "box1" (the picked box in NMS).
+__device__ __forceinline__ float iou3d_obb_full(const ObbPrep& a, const ObbPrep& b) {
     float zo = __fsub_rn(fminf(a.zmax, b.zmax), fmaxf(a.zmin, b.zmin));
     if (!(zo >= 0.0f)) zo = (zo != zo) ? zo : 0.0f;
     const float inter = rect_inter_area(a.c, b.c);
@@ -228,6 +233,15 @@ __device__ __forceinline__ float iou3d_obb(const ObbPrep& a, const ObbPrep& b, b
     const float i3 = __fmul_rn(__fmul_rn(iou2d, u), zo);
     const float u3 = __fsub_rn(__fadd_rn(a.vol, b.vol), i3);
     return __fdiv_rn(i3, u3);
+}
+
+__device__ __forceinline__ float iou3d_obb(const ObbPrep& a, const ObbPrep& b, bool allow_cull) {
+    if (allow_cull && a.cullable && b.cullable) {
+        const float dx = a.cx - b.cx, dy = a.cy - b.cy, rr = a.rad + b.rad;
+        if (dx * dx + dy * dy > rr * rr) return 0.0f;           // footprints cannot touch -> reference yields exactly 0
+        if (a.zmin > b.zmax || b.zmin > a.zmax) return 0.0f;     // z_overlap clamps to 0
+    }
+    return iou3d_obb_full(a, b);
 }
 
 // box_iou_3d AABB branch for one pair (utils.py:418-458).

@@ -290,7 +290,8 @@ int nrpn_rpn_proposals(const nrpn_rpn_desc* desc, float* boxes, float* scores, f
         rpn_compact_obb_kernel<<<1, 1024, 0, st>>>(M, P.min_size, P.score_thresh, w.clevel, w.cflag, w.cscore, w.cbox, w.fbox, w.group);
     }
     NRPN_LAUNCH_CHECK();
-    rc = nms_run(w.fbox, box_dim, w.cscore, w.group, M, desc->nms_thresh, kIgnoreGroup, w.keep, w.n_keep, w.nms_ws, w.nms_bytes, st);
+    rc = nms_run(w.fbox, box_dim, w.cscore, w.group, M, desc->nms_thresh, kIgnoreGroup, w.keep, w.n_keep, w.nms_ws, w.nms_bytes, st,
+                 /*max_group=*/desc->pre_nms_top_n);      // one group per pyramid level, each at most pre_nms_top_n candidates
     if (rc) return rc;
     rpn_emit_kernel<<<ceil_div(desc->post_nms_top_n, 256), 256, 0, st>>>(w.keep, w.n_keep, desc->post_nms_top_n, box_dim, w.fbox,
                                                                        w.cscore, w.clevel, boxes, scores, levels, count);

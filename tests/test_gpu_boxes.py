@@ -101,7 +101,8 @@ def test_nms_golden_sets(ops, G, name):
 
 def test_nms_vs_oracle_larger_and_edges(ops, G):
     rng = np.random.default_rng(7)
-    for n, dim, ext in ((5000, 7, 60.0), (10000, 6, 90.0), (9999, 7, 40.0), (65, 7, 5.0), (64, 6, 5.0), (1, 7, 5.0)):
+    for n, dim, ext in ((5000, 7, 60.0), (10000, 6, 90.0), (9999, 7, 40.0), (6000, 7, 12.0), (3072, 7, 30.0), (3073, 7, 30.0),
+                        (65, 7, 5.0), (64, 6, 5.0), (1, 7, 5.0)):      # 6000 @ 12: heavy suppression (few survivors, long kept-list scans)
         boxes = rand_obb(n, rng, ext, 2, 14) if dim == 7 else rand_aabb(n, rng, ext, 2, 16)
         scores = rng.random(n).astype(np.float32)
         scores[: n // 10] = scores[n // 10: 2 * (n // 10)]           # exact score ties
