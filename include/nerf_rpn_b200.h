@@ -247,6 +247,14 @@ size_t nrpn_fcos_workspace_bytes(const nrpn_fcos_desc *desc /*host*/);
 int nrpn_fcos_proposals(const nrpn_fcos_desc *desc /*host*/, float *boxes, float *scores, int32_t *count, void *workspace,
                         size_t workspace_bytes, nrpn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------ recall metric
+ * Greedy proposal <-> ground-truth matching of evaluate_box_proposals_recall (eval.py:33-52) on device.
+ * overlaps: (n_proposals, n_gt) fp32 IoU matrix (nrpn_iou3d_matrix of the score-sorted, limit-truncated proposals against the
+ * ground truth); gt_overlaps: min(n_proposals, n_gt) fp32, the IoU recorded at each step of the reference loop (the rest of
+ * the reference's zero-initialised vector is left to the caller).  Ties: lowest ground-truth index, then lowest proposal
+ * index, as torch.max on CPU.  n_proposals <= 32 768, n_gt <= 4 096. */
+int nrpn_recall_match(const float *overlaps, int n_proposals, int n_gt, float *gt_overlaps, nrpn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ struct ConvLevelDev {
     int xr, yr, zr;          // residual extent
     float rsx, rsy, rsz;     // nearest-neighbour scale = in / out
     int ldy, ldr;
+    int wide_y, wide_r;      // rows of y / res are 32-byte aligned: 256-bit stores / loads
     void* y;
     const __nv_bfloat16* res;
 };
@@ -275,17 +276,24 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                 asm volatile("bar.sync 1, 128;" ::: "memory");     // ticket_slot is reused by the next work item
                 continue;
             }
-            // residual rows are fetched one 32-channel chunk ahead (4 x 16 B per thread in flight) so that the DRAM
+            // residual rows are fetched one 32-channel chunk ahead (2 x 32 B or 4 x 16 B per thread in flight) so that the DRAM
             // latency of chunk c+1 hides behind the TMEM load + math + stores of chunk c
             uint4 rv[4];
             auto load_res = [&](int c, uint4 (&dst)[4]) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int ch = n0 + c * 32 + g * 8;
-                    dst[g] = (rrow != nullptr && ch < P.cout) ? __ldg(reinterpret_cast<const uint4*>(rrow + ch)) : make_uint4(0u, 0u, 0u, 0u);
+                for (int h = 0; h < 2; ++h) {
+                    const int ch = n0 + c * 32 + h * 16;
+                    if (rrow != nullptr && L.wide_r && ch + 16 <= P.cout) {
+                        ptx::ld_global_nc_v8(rrow + ch, dst[2 * h], dst[2 * h + 1]);
+                    } else {
+                        dst[2 * h] = (rrow != nullptr && ch < P.cout) ? __ldg(reinterpret_cast<const uint4*>(rrow + ch)) : make_uint4(0u, 0u, 0u, 0u);
+                        dst[2 * h + 1] = (rrow != nullptr && ch + 8 < P.cout) ? __ldg(reinterpret_cast<const uint4*>(rrow + ch + 8)) : make_uint4(0u, 0u, 0u, 0u);
+                    }
                 }
             };
             load_res(0, rv);
+            uint4 rn[4];
+            if (BLOCK_N == 64) load_res(1, rn);          // N = 64 (HBM-bound 1^3 layers): the whole residual row is in flight before the wait
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
             const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
@@ -293,42 +301,61 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 uint32_t r[32];
                 ptx::tmem_ld_32x32(t_base + (uint32_t)(c * 32), r);
-                uint4 rn[4];
-                if (c + 1 < BLOCK_N / 32) load_res(c + 1, rn);
+                if (BLOCK_N != 64 && c + 1 < BLOCK_N / 32) load_res(c + 1, rn);
                 ptx::tmem_ld_wait();
                 const int ch0 = n0 + c * 32;
                 if (valid && ch0 < P.cout) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {            // 4 groups of 8 channels
-                        const int ch = ch0 + g * 8;
-                        if (ch >= P.cout) break;
-                        float v[8];
-                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.shift + ch));
-                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(P.shift + ch + 4));
-                        v[0] = __uint_as_float(r[g * 8 + 0]) + s0.x; v[1] = __uint_as_float(r[g * 8 + 1]) + s0.y;
-                        v[2] = __uint_as_float(r[g * 8 + 2]) + s0.z; v[3] = __uint_as_float(r[g * 8 + 3]) + s0.w;
-                        v[4] = __uint_as_float(r[g * 8 + 4]) + s1.x; v[5] = __uint_as_float(r[g * 8 + 5]) + s1.y;
-                        v[6] = __uint_as_float(r[g * 8 + 6]) + s1.z; v[7] = __uint_as_float(r[g * 8 + 7]) + s1.w;
-                        if (rrow != nullptr) {
-                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv[g]);
+                    for (int h = 0; h < 2; ++h) {            // 2 halves of 16 channels = 32 bytes of bf16
+                        const int chh = ch0 + h * 16;
+                        if (chh >= P.cout) break;
+                        float v[16];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(rb[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
+                        for (int g = 0; g < 2; ++g) {
+                            const int ch = chh + g * 8;
+                            if (ch < P.cout) {
+                                const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.shift + ch));
+                                const float4 s1 = __ldg(reinterpret_cast<const float4*>(P.shift + ch + 4));
+                                const uint32_t* rr = r + h * 16 + g * 8;
+                                float* vv = v + g * 8;
+                                vv[0] = __uint_as_float(rr[0]) + s0.x; vv[1] = __uint_as_float(rr[1]) + s0.y;
+                                vv[2] = __uint_as_float(rr[2]) + s0.z; vv[3] = __uint_as_float(rr[3]) + s0.w;
+                                vv[4] = __uint_as_float(rr[4]) + s1.x; vv[5] = __uint_as_float(rr[5]) + s1.y;
+                                vv[6] = __uint_as_float(rr[6]) + s1.z; vv[7] = __uint_as_float(rr[7]) + s1.w;
+                                if (rrow != nullptr) {
+                                    const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv[2 * h + g]);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(rb[i]); vv[2 * i] += f.x; vv[2 * i + 1] += f.y; }
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[g * 8 + i] = 0.0f;
+                            }
                         }
                         if (P.relu == 1) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+                            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
                         } else if (P.relu == 2) {            // exact (erf) GELU: Swin MLP, feature_extractor.py:635
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
+                            for (int i = 0; i < 16; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
                         }
+                        const bool both = chh + 16 <= P.cout;
                         if (P.out_fp32) {
-                            float* o = reinterpret_cast<float*>(L.y) + vox * L.ldy + ch;
-                            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                            float* o = reinterpret_cast<float*>(L.y) + vox * L.ldy + chh;
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+                                if (chh + g * 8 >= P.cout) break;
+                                const uint4 lo = make_uint4(__float_as_uint(v[g * 8 + 0]), __float_as_uint(v[g * 8 + 1]), __float_as_uint(v[g * 8 + 2]), __float_as_uint(v[g * 8 + 3]));
+                                const uint4 hi = make_uint4(__float_as_uint(v[g * 8 + 4]), __float_as_uint(v[g * 8 + 5]), __float_as_uint(v[g * 8 + 6]), __float_as_uint(v[g * 8 + 7]));
+                                if (L.wide_y) ptx::st_global_v8(o + g * 8, lo, hi);
+                                else { *reinterpret_cast<uint4*>(o + g * 8) = lo; *reinterpret_cast<uint4*>(o + g * 8 + 4) = hi; }
+                            }
                         } else {
-                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(L.y) + vox * L.ldy + ch;
-                            *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                                                      pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(L.y) + vox * L.ldy + chh;
+                            const uint4 lo = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                            const uint4 hi = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                            if (both && L.wide_y) ptx::st_global_v8(o, lo, hi);
+                            else { *reinterpret_cast<uint4*>(o) = lo; if (both) *reinterpret_cast<uint4*>(o + 8) = hi; }
                         }
                     }
                 }
@@ -494,6 +521,9 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
         L.xr = S.res ? S.xr : S.xo; L.yr = S.res ? S.yr : S.yo; L.zr = S.res ? S.zr : S.zo;
         L.rsx = (float)L.xr / (float)S.xo; L.rsy = (float)L.yr / (float)S.yo; L.rsz = (float)L.zr / (float)S.zo;
         L.ldy = S.ldy; L.ldr = S.ldr; L.y = S.y; L.res = reinterpret_cast<const __nv_bfloat16*>(S.res);
+        const size_t ybytes = (size_t)S.ldy * (d->out_fp32 ? 4 : 2);
+        L.wide_y = (ybytes % 32 == 0 && reinterpret_cast<uintptr_t>(S.y) % 32 == 0) ? 1 : 0;
+        L.wide_r = (S.res && ((size_t)S.ldr * 2) % 32 == 0 && reinterpret_cast<uintptr_t>(S.res) % 32 == 0) ? 1 : 0;
 
         // activation tensor map: (C, Z, Y, X, N), optionally sub-sampled by `stride` on the three spatial axes
         const cuuint64_t cin = (cuuint64_t)d->cin;

@@ -41,7 +41,7 @@ struct SlabDev {
     int n_phases, ndx, ndy;
     int dx0, dy0;
     int planes, slots, plane_bytes;
-    int cout, relu, ldy;
+    int cout, relu, ldy, wide_y;
     signed char dz[kSlabMaxAxis];
     unsigned char dyrel[kSlabMaxAxis];
     unsigned char widx[kSlabMaxAxis][kSlabMaxAxis][kSlabMaxAxis];     // [phase][dx index][dy index] -> tap index of the packed weights
@@ -224,24 +224,37 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv3d_slab_kernel(const __gr
                 if (valid_yz && gx < P.xo) {
                     __nv_bfloat16* o = P.y + ((((size_t)nb * P.xo + gx) * P.yo + gy) * P.zo + gz) * P.ldy;
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const int ch = g * 8;
-                        if (ch >= P.cout) break;
-                        const uint32_t* r = (g < 4) ? (r0 + g * 8) : (r1 + (g - 4) * 8);
-                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.shift + ch));
-                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(P.shift + ch + 4));
-                        float v[8] = {__uint_as_float(r[0]) + s0.x, __uint_as_float(r[1]) + s0.y, __uint_as_float(r[2]) + s0.z,
-                                      __uint_as_float(r[3]) + s0.w, __uint_as_float(r[4]) + s1.x, __uint_as_float(r[5]) + s1.y,
-                                      __uint_as_float(r[6]) + s1.z, __uint_as_float(r[7]) + s1.w};
-                        if (P.relu == 1) {
+                    for (int h = 0; h < 4; ++h) {                       // 16 channels = 32 bytes per step
+                        const int chh = h * 16;
+                        if (chh >= P.cout) break;
+                        uint4 pk[2];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
-                        } else if (P.relu == 2) {
+                        for (int gg = 0; gg < 2; ++gg) {
+                            const int g = h * 2 + gg, ch = g * 8;
+                            const uint32_t* r = (g < 4) ? (r0 + g * 8) : (r1 + (g - 4) * 8);
+                            float v[8];
+                            if (ch < P.cout) {
+                                const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.shift + ch));
+                                const float4 s1 = __ldg(reinterpret_cast<const float4*>(P.shift + ch + 4));
+                                v[0] = __uint_as_float(r[0]) + s0.x; v[1] = __uint_as_float(r[1]) + s0.y; v[2] = __uint_as_float(r[2]) + s0.z;
+                                v[3] = __uint_as_float(r[3]) + s0.w; v[4] = __uint_as_float(r[4]) + s1.x; v[5] = __uint_as_float(r[5]) + s1.y;
+                                v[6] = __uint_as_float(r[6]) + s1.z; v[7] = __uint_as_float(r[7]) + s1.w;
+                            } else {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
+                                for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+                            }
+                            if (P.relu == 1) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+                            } else if (P.relu == 2) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
+                            }
+                            pk[gg] = make_uint4(slab_pack_bf16(v[0], v[1]), slab_pack_bf16(v[2], v[3]), slab_pack_bf16(v[4], v[5]), slab_pack_bf16(v[6], v[7]));
                         }
-                        *reinterpret_cast<uint4*>(o + ch) = make_uint4(slab_pack_bf16(v[0], v[1]), slab_pack_bf16(v[2], v[3]),
-                                                                       slab_pack_bf16(v[4], v[5]), slab_pack_bf16(v[6], v[7]));
+                        const bool both = chh + 16 <= P.cout;
+                        if (both && P.wide_y) ptx::st_global_v8(o + chh, pk[0], pk[1]);
+                        else { *reinterpret_cast<uint4*>(o + chh) = pk[0]; if (both) *reinterpret_cast<uint4*>(o + chh + 8) = pk[1]; }
                     }
                 }
             }
@@ -321,6 +334,7 @@ int conv3d_slab_launch(const nrpn_conv_desc* d, cudaStream_t st) {
     P.tx = ceil_div(S.xo, kSlabAcc); P.ty = ceil_div(S.yo, kSlabTileY); P.tz = ceil_div(S.zo, kSlabTileZ);
     P.total_tiles = S.n * P.tx * P.ty * P.tz;
     P.cout = d->cout; P.relu = d->relu; P.ldy = S.ldy; P.shift = d->shift; P.y = reinterpret_cast<__nv_bfloat16*>(S.y);
+    P.wide_y = (((size_t)S.ldy * 2) % 32 == 0 && reinterpret_cast<uintptr_t>(S.y) % 32 == 0) ? 1 : 0;
 
     SlabMaps maps;
     {   // activations (C, Z, Y, X, N): one box = one x-plane of the slab, {64 ch, 8 z, Ys y}

@@ -56,6 +56,17 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.256): one full 32-byte sector per lane and instruction. The epilogues use them so
+// that a row written as 16-byte pieces does not reach L2 as two partial-sector writes (ncu: 2x the sectors of the tensor).
+__device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
 // One lane of a fully converged warp (elect.sync): the idiom ptxas recognises as "exactly one thread", so the
 // uniform-datapath instructions it guards (UTCHMMA, UTCBAR, UTMALDG) need no per-instruction waterfall loop.
 __device__ __forceinline__ bool elect_one() {

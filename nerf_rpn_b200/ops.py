@@ -48,6 +48,15 @@ def iou3d_matrix(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def recall_match(overlaps: torch.Tensor) -> torch.Tensor:
+    """(P, G) fp32 IoU matrix -> the min(P, G) IoUs recorded by the greedy loop of eval.py:33-52 (device resident)."""
+    overlaps = _req(overlaps, torch.float32, "overlaps")
+    p, g = overlaps.shape
+    out = torch.zeros((min(p, g),), dtype=torch.float32, device=overlaps.device)
+    check(lib().nrpn_recall_match(_ptr(overlaps), p, g, _ptr(out), _stream()), "recall_match")
+    return out
+
+
 def sort_vertices_forward(vertices: torch.Tensor, mask: torch.Tensor, num_valid: torch.Tensor) -> torch.Tensor:
     """Same contract as the reference's pybind op (cuda_op/sort_vert.cpp:6-34)."""
     if not vertices.is_cuda:

@@ -361,7 +361,67 @@ def gen_swin_small():
     print("swin_small_fcos_obb.npz boxes", tuple(boxes[0].shape), [tuple(f.shape) for f in feats], len(backbone.state_dict()))
 
 
+def recall_scene(i, dims=(32, 48, 40), n_gt=24):
+    """Scene i of the recall fixture: U[0,1) grid (seed 2000+i) and n_gt random OBB ground-truth boxes inside it."""
+    gi = torch.Generator().manual_seed(2000 + i)
+    grid = torch.rand(*dims, 4, generator=gi)
+    d = torch.tensor(dims, dtype=torch.float32)
+    size = torch.rand(n_gt, 3, generator=gi) * 16.0 + 4.0
+    ctr = torch.rand(n_gt, 3, generator=gi) * (d - 4.0) + 2.0
+    theta = (torch.rand(n_gt, 1, generator=gi) - 0.5) * math.pi
+    return grid.permute(3, 0, 1, 2).contiguous(), torch.cat([ctr, size, theta], 1)
+
+
+def gen_recall(n_scenes=12):
+    """recall@{0.25,0.5} (eval.py:14-81, limits 300/1000/2500) of the reference's OBB proposals on 12 small scenes with
+    planted ground truth; weights = the rpn_small_obb model. Also pins the greedy matching itself on random IoU matrices."""
+    import eval as ref_eval
+    import types
+    from tests import recipes
+    g = np.load(os.path.join(OUT, "rpn_small_obb.npz"))
+    ns = types.SimpleNamespace(ResNet_FPN_256=ResNet_FPN_256, Bottleneck=Bottleneck, AnchorGenerator3D=AnchorGenerator3D, RPNHead=RPNHead)
+    backbone, ag, head = recipes.build_small_model(ns, True, g)
+    model = NeRFRegionProposalNetwork(backbone, ag, head, rpn_pre_nms_top_n_test=2500, rpn_post_nms_top_n_test=2500,
+                                      rpn_nms_thresh=0.3, rpn_fg_iou_thresh=0.35, rpn_bg_iou_thresh=0.2,
+                                      rpn_score_thresh=0.0, rotated_bbox=True)
+    model.eval()
+    props, scores, gts = [], [], []
+    for i in range(n_scenes):
+        x, gt = recall_scene(i)
+        with torch.no_grad():
+            (_, proposals, _), _, sc = model([x])
+        props.append(proposals[0]); scores.append(sc[0]); gts.append(gt)
+        print("recall scene", i, tuple(proposals[0].shape))
+    out = dict(n_scenes=np.int64(n_scenes), gt=torch.stack(gts).numpy(), n_props=np.array([p.shape[0] for p in props]))
+    thr = torch.tensor([0.25, 0.5])
+    for limit in (300, 1000, 2500):
+        r = ref_eval.evaluate_box_proposals_recall(props, scores, gts, thresholds=thr, limit=limit)
+        out[f"recalls_{limit}"] = r["recalls"].numpy()
+        out[f"gt_overlaps_{limit}"] = r["gt_overlaps"].numpy()
+        print("limit", limit, "recall@0.25/0.5", r["recalls"].tolist(), "num_pos", r["num_pos"])
+    # the matching loop alone, on random matrices (ties included), through the reference function with a patched IoU
+    gen = torch.Generator().manual_seed(5)
+    mats, outs = [], []
+    orig = ref_eval.box_iou_3d
+    try:
+        for (p, q) in ((40, 7), (5, 9), (300, 24), (1, 1)):
+            m = torch.rand(p, q, generator=gen)
+            m[m < 0.3] = 0.0
+            m = (m * 8).round() / 8                    # many exact ties
+            ref_eval.box_iou_3d = lambda a, b, m=m: m.clone()
+            r = ref_eval.evaluate_box_proposals_recall([torch.zeros(p, 7)], [torch.arange(p, 0, -1).float()], [torch.zeros(q, 7)],
+                                                       thresholds=thr, limit=None)
+            mats.append(m.numpy()); outs.append(r["gt_overlaps"].numpy())
+    finally:
+        ref_eval.box_iou_3d = orig
+    for k, (m, o) in enumerate(zip(mats, outs)):
+        out[f"match_m{k}"] = m; out[f"match_o{k}"] = o
+    np.savez_compressed(os.path.join(OUT, "recall_small_obb.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--recall-only" in sys.argv:
+        sys.path.insert(0, ROOT); gen_recall(); sys.exit(0)
     if "--swin-only" in sys.argv:
         gen_swin_small(); sys.exit(0)
     if "--fcos-only" in sys.argv:
@@ -375,3 +435,4 @@ if __name__ == "__main__":
     gen_rpn_small()
     gen_fcos_small()
     gen_swin_small()
+    sys.path.insert(0, ROOT); gen_recall()

@@ -27,6 +27,9 @@ elif which == "stem":
     plan.launches[1]()                                                    # stem conv (halo-slab kernel)
 elif which == "l0c2":
     [f for f in plan.launches if "L0.c2" in plan.names.get(id(f), ("",))[0]][0]()
+elif which in ("l0c3", "l0c1", "l1c3", "lat3"):
+    key = {"l0c3": "L0.c3+res", "l0c1": "L0.c1", "l1c3": "L1.c3+res", "lat3": "lat3+up"}[which]
+    [f for f in plan.launches if key in plan.names.get(id(f), ("",))[0]][-1]()
 elif which == "misc":
     plan.launches[0](); plan.launches[1](); plan.launches[2]()          # pack, stem conv, maxpool
     for f in plan._post[0]:
