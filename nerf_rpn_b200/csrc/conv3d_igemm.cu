@@ -39,6 +39,7 @@ struct ConvLevelDev {
     float rsx, rsy, rsz;     // nearest-neighbour scale = in / out
     int ldy, ldr;
     int wide_y, wide_r;      // rows of y / res are 32-byte aligned: 256-bit stores / loads
+    int res_tma;             // TMA-epilogue variant: the residual has the output's extent and arrives through maps.r
     void* y;
     const __nv_bfloat16* res;
 };
@@ -57,6 +58,8 @@ struct ConvDev {
 struct ConvMaps {
     CUtensorMap x[NRPN_CONV_MAX_LEVELS];
     CUtensorMap w;
+    CUtensorMap y[NRPN_CONV_MAX_LEVELS];      // TMA-epilogue variant only: output tiles are stored with cp.async.bulk.tensor
+    CUtensorMap r[NRPN_CONV_MAX_LEVELS];      // ... and same-shape residual tiles are prefetched by the producer warp
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -64,29 +67,45 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BLOCK_N, int STAGES, int MIN_BLOCKS>
+constexpr int kEpiTileBytes = kBlockM * 64 * 2;      // one 128 x 64 bf16 tile (residual in / output out of the TMA epilogue)
+
+// TMA_EPI (N = 64 tiles of the HBM-bound 1^3 layers, bf16 output, Cout % 64 == 0): the epilogue never touches global memory
+// from a register.  The producer warp prefetches the residual tile of a same-shape skip connection into shared memory
+// (2-deep ring) together with the operands; the epilogue warps add it from shared memory, write the bf16 tile into a
+// swizzled staging buffer and one elected thread stores it with cp.async.bulk.tensor (hardware clips partial bricks).
+// With per-thread 16/32-byte global loads and stores the same layers sat at ~45 % of the HBM rate (ncu: lts 45 %, 2-3x the
+// compulsory L2 sectors, a DRAM-latency chain per tile).
+template <int BLOCK_N, int STAGES, int MIN_BLOCKS, bool TMA_EPI = false>
 __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvDev P) {
+    static_assert(!TMA_EPI || BLOCK_N == 64, "the TMA epilogue stages 128 x 64 tiles");
     constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
+    constexpr int kEpiBytes = TMA_EPI ? 3 * kEpiTileBytes : 0;      // residual ring (2) + output staging (1)
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;
     constexpr uint32_t kIdesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+    uint8_t* smem_res = smem + STAGES * kStageBytes;                 // [2][128 rows][128 B], 128B-swizzled (TMA_EPI)
+    uint8_t* smem_out = smem_res + 2 * kEpiTileBytes;                // [128 rows][128 B], 128B-swizzled (TMA_EPI)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes + kEpiBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* tfull_bar = bars + 2 * STAGES;
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* rfull_bar = bars + 2 * STAGES + 4;
+    uint64_t* rempty_bar = bars + 2 * STAGES + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 128); }
+        for (int a = 0; a < 2; ++a) { ptx::mbar_init(&rfull_bar[a], 1); ptx::mbar_init(&rempty_bar[a], 128); }
         ptx::fence_barrier_init();
         for (int l = 0; l < P.n_levels; ++l) ptx::prefetch_tmap(&maps.x[l]);
+        if (TMA_EPI) for (int l = 0; l < P.n_levels; ++l) { ptx::prefetch_tmap(&maps.y[l]); ptx::prefetch_tmap(&maps.r[l]); }
         ptx::prefetch_tmap(&maps.w);
     }
     if (warp == 1) { ptx::tmem_alloc(tmem_slot, kTmemCols); ptx::tmem_relinquish(); }
@@ -104,6 +123,7 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
         {
             const bool leader = ptx::elect_one();
             int stage = 0; uint32_t phase = 0;
+            int rslot = 0; uint32_t rphase = 0;
             for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
                 const int split = item % P.splits, tile = item / P.splits;
                 const int kb0 = (kblocks * split) / P.splits, kb1 = (kblocks * (split + 1)) / P.splits;
@@ -130,6 +150,15 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                if (TMA_EPI && L.res_tma) {                          // residual tile of this output tile, two tiles ahead of its use
+                    ptx::mbar_wait(&rempty_bar[rslot], rphase ^ 1u);
+                    if (leader) {
+                        ptx::mbar_expect_tx(&rfull_bar[rslot], kEpiTileBytes);
+                        ptx::tma_load_5d(smem_res + rslot * kEpiTileBytes, &maps.r[l], &rfull_bar[rslot], n0, z0, y0, x0, nb);
+                    }
+                    __syncwarp();
+                    if (++rslot == 2) { rslot = 0; rphase ^= 1u; }
                 }
             }
         }
@@ -175,6 +204,7 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;                   // accumulator row == voxel inside the brick
         int acc = 0; uint32_t acc_phase = 0;
+        int rslot = 0; uint32_t rphase = 0;
         for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
             const int tile = item / P.splits;
             const int n_tile = tile % P.n_tiles_n, m_tile = tile / P.n_tiles_n;
@@ -276,6 +306,64 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                 asm volatile("bar.sync 1, 128;" ::: "memory");     // ticket_slot is reused by the next work item
                 continue;
             }
+            if constexpr (TMA_EPI) {
+                // ---- shared-memory epilogue: residual from the TMA-fed ring, output through a swizzled staging tile + TMA store
+                const bool res_smem = L.res_tma != 0;
+                ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+                if (res_smem) ptx::mbar_wait(&rfull_bar[rslot], rphase);
+                ptx::tc_fence_after();
+                // the staging tile is free once the previous tile's bulk store has finished READING it
+                if (threadIdx.x == 64) ptx::bulk_wait_read0();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+                const uint8_t* rsm = smem_res + rslot * kEpiTileBytes + row * 128;
+                uint8_t* osm = smem_out + row * 128;
+                const int sw = row & 7;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(t_base + (uint32_t)(c * 32), r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int j = c * 4 + g;                     // 16-byte chunk (8 channels) inside the 128-byte row
+                        const int ch = n0 + j * 8;
+                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.shift + ch));
+                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(P.shift + ch + 4));
+                        float v[8] = {__uint_as_float(r[g * 8 + 0]) + s0.x, __uint_as_float(r[g * 8 + 1]) + s0.y,
+                                      __uint_as_float(r[g * 8 + 2]) + s0.z, __uint_as_float(r[g * 8 + 3]) + s0.w,
+                                      __uint_as_float(r[g * 8 + 4]) + s1.x, __uint_as_float(r[g * 8 + 5]) + s1.y,
+                                      __uint_as_float(r[g * 8 + 6]) + s1.z, __uint_as_float(r[g * 8 + 7]) + s1.w};
+                        if (res_smem || rrow != nullptr) {
+                            const uint4 rv4 = res_smem ? *reinterpret_cast<const uint4*>(rsm + ((j ^ sw) << 4))
+                                                       : __ldg(reinterpret_cast<const uint4*>(rrow + ch));
+                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv4);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(rb[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
+                        }
+                        if (P.relu == 1) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+                        } else if (P.relu == 2) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
+                        }
+                        *reinterpret_cast<uint4*>(osm + ((j ^ sw) << 4)) =
+                            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tempty_bar[acc]);
+                if (res_smem) { ptx::mbar_arrive(&rempty_bar[rslot]); if (++rslot == 2) { rslot = 0; rphase ^= 1u; } }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                ptx::fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA engine
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 64) {
+                    ptx::tma_store_5d(&maps.y[l], smem_out, n0, tiz * L.bz, tiy * L.by, tix * L.bx, nb);
+                    ptx::bulk_commit();
+                }
+                continue;
+            }
             // residual rows are fetched one 32-channel chunk ahead (2 x 32 B or 4 x 16 B per thread in flight) so that the DRAM
             // latency of chunk c+1 hides behind the TMEM load + math + stores of chunk c
             uint4 rv[4];
@@ -370,26 +458,27 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
         }
     }
 
+    if (TMA_EPI && threadIdx.x == 64) ptx::bulk_wait_all();          // the staging tile must outlive its last bulk store
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, kTmemCols); }
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <int BLOCK_N, int STAGES, int MIN_BLOCKS>
+template <int BLOCK_N, int STAGES, int MIN_BLOCKS, bool TMA_EPI = false>
 static int launch_conv(const ConvMaps& maps, const ConvDev& P, int total_tiles, cudaStream_t st) {
-    constexpr int smem = STAGES * (kABytes + BLOCK_N * kBlockK * 2) + 1024 + 256;
-    static_assert(smem * MIN_BLOCKS <= 227 * 1024, "shared memory budget");
+    constexpr int smem = STAGES * (kABytes + BLOCK_N * kBlockK * 2) + (TMA_EPI ? 3 * kEpiTileBytes : 0) + 1024 + 256;
+    static_assert((smem + 1024) * MIN_BLOCKS <= 228 * 1024, "shared memory budget");
     static_assert(2 * BLOCK_N * MIN_BLOCKS <= 512, "TMEM budget: 512 columns per SM");
     static bool attr_set = false;
     if (!attr_set) {
-        NRPN_CUDA_TRY(cudaFuncSetAttribute(conv3d_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS>,
+        NRPN_CUDA_TRY(cudaFuncSetAttribute(conv3d_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS, TMA_EPI>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const int slots = num_sms() * MIN_BLOCKS;
     const int grid = total_tiles < slots ? total_tiles : slots;
-    conv3d_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS><<<grid, 192, smem, st>>>(maps, P);
+    conv3d_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS, TMA_EPI><<<grid, 192, smem, st>>>(maps, P);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
@@ -423,7 +512,7 @@ static int choose_splits(int total_tiles, int kblocks, bool short_k) {
     return s < 2 ? 1 : s;
 }
 
-struct ConvGeom { int pad_n, cout_pad, block_n, kblocks, m_tiles, n_tiles_n, splits; bool short_k; size_t ws_bytes, counter_bytes; };
+struct ConvGeom { int pad_n, cout_pad, block_n, kblocks, m_tiles, n_tiles_n, splits; bool short_k, tma_epi; size_t ws_bytes, counter_bytes; };
 
 static int conv_geometry(const nrpn_conv_desc* d, ConvGeom& g) {
     g.pad_n = nrpn_conv3d_block_n(d->cout);
@@ -444,6 +533,16 @@ static int conv_geometry(const nrpn_conv_desc* d, ConvGeom& g) {
     g.splits = choose_splits(tiles * g.n_tiles_n, g.kblocks, g.short_k);
     g.counter_bytes = align_up((size_t)tiles * g.n_tiles_n * 4, 256);
     g.ws_bytes = g.splits > 1 ? g.counter_bytes + (size_t)tiles * g.n_tiles_n * g.splits * kBlockM * g.block_n * 4 : 0;
+    // shared-memory (TMA) epilogue: the HBM-bound short reductions with whole 64-channel bf16 output tiles
+    { const char* e = getenv("NRPN_CONV_TMA_EPI"); g.tma_epi = !(e && e[0] == '0'); }       // A/B switch for tests and profiling
+    g.tma_epi = g.tma_epi && g.short_k && g.splits == 1 && !d->out_fp32 && d->cout % 64 == 0;
+    for (int l = 0; l < d->n_levels && g.tma_epi; ++l) {
+        const nrpn_conv_level& S = d->level[l];
+        if (reinterpret_cast<uintptr_t>(S.y) % 16 != 0 || (S.res && reinterpret_cast<uintptr_t>(S.res) % 16 != 0)) g.tma_epi = false;
+        // a nearest-upsampled residual (FPN top-down) is gathered per row from registers: the pipelined register epilogue
+        // with 3 CTAs per SM is faster for it (measured: lat3+up 0.207 ms vs 0.275 ms)
+        if (S.res && (S.xr != S.xo || S.yr != S.yo || S.zr != S.zo)) g.tma_epi = false;
+    }
     return NRPN_OK;
 }
 
@@ -469,7 +568,7 @@ const char* nrpn_conv3d_variant(const nrpn_conv_desc* d) {
     if (conv3d_slab_eligible(d)) return "slab<4x16x8,N64>";
     ConvGeom g;
     if (conv_geometry(d, g) != NRPN_OK) return "invalid";
-    if (g.short_k) return "igemm<64,2,3>";
+    if (g.short_k) return g.tma_epi ? "igemm<64,2,2,tma-epilogue>" : "igemm<64,2,3>";
     return g.block_n == 64 ? "igemm<64,8,1>" : (g.block_n == 128 ? "igemm<128,6,1>" : "igemm<256,4,1>");
 }
 
@@ -521,6 +620,26 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
         L.xr = S.res ? S.xr : S.xo; L.yr = S.res ? S.yr : S.yo; L.zr = S.res ? S.zr : S.zo;
         L.rsx = (float)L.xr / (float)S.xo; L.rsy = (float)L.yr / (float)S.yo; L.rsz = (float)L.zr / (float)S.zo;
         L.ldy = S.ldy; L.ldr = S.ldr; L.y = S.y; L.res = reinterpret_cast<const __nv_bfloat16*>(S.res);
+        L.res_tma = (geo.tma_epi && S.res && S.xr == S.xo && S.yr == S.yo && S.zr == S.zo) ? 1 : 0;
+        if (geo.tma_epi) {
+            // output / residual tensors (C, Z, Y, X, N) with the row pitch ldy / ldr; one box = one 64-channel brick tile
+            cuuint32_t ebox[5] = {64, (cuuint32_t)L.bz, (cuuint32_t)L.by, (cuuint32_t)L.bx, 1};
+            cuuint32_t eone[5] = {1, 1, 1, 1, 1};
+            cuuint64_t ydim[5] = {(cuuint64_t)d->cout, (cuuint64_t)S.zo, (cuuint64_t)S.yo, (cuuint64_t)S.xo, (cuuint64_t)S.n};
+            cuuint64_t ystr[4] = {(cuuint64_t)S.ldy * 2, (cuuint64_t)S.zo * S.ldy * 2, (cuuint64_t)S.yo * S.zo * S.ldy * 2,
+                                  (cuuint64_t)S.xo * S.yo * S.zo * S.ldy * 2};
+            CUresult ry = encode(&maps.y[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, S.y, ydim, ystr, ebox, eone, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (ry != CUDA_SUCCESS) { g_last_cuda_error = (int)ry; return NRPN_ERR_CUDA; }
+            if (L.res_tma) {
+                cuuint64_t rstr[4] = {(cuuint64_t)S.ldr * 2, (cuuint64_t)S.zo * S.ldr * 2, (cuuint64_t)S.yo * S.zo * S.ldr * 2,
+                                      (cuuint64_t)S.xo * S.yo * S.zo * S.ldr * 2};
+                CUresult rr = encode(&maps.r[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(S.res), ydim, rstr, ebox, eone,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (rr != CUDA_SUCCESS) { g_last_cuda_error = (int)rr; return NRPN_ERR_CUDA; }
+            } else maps.r[l] = maps.y[l];
+        }
         const size_t ybytes = (size_t)S.ldy * (d->out_fp32 ? 4 : 2);
         L.wide_y = (ybytes % 32 == 0 && reinterpret_cast<uintptr_t>(S.y) % 32 == 0) ? 1 : 0;
         L.wide_r = (S.res && ((size_t)S.ldr * 2) % 32 == 0 && reinterpret_cast<uintptr_t>(S.res) % 32 == 0) ? 1 : 0;
@@ -537,7 +656,8 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return NRPN_ERR_CUDA; }
     }
-    for (int l = d->n_levels; l < NRPN_CONV_MAX_LEVELS; ++l) maps.x[l] = maps.x[0];
+    for (int l = d->n_levels; l < NRPN_CONV_MAX_LEVELS; ++l) { maps.x[l] = maps.x[0]; maps.y[l] = maps.y[0]; maps.r[l] = maps.r[0]; }
+    if (!geo.tma_epi) for (int l = 0; l < NRPN_CONV_MAX_LEVELS; ++l) { maps.y[l] = maps.x[0]; maps.r[l] = maps.x[0]; }
     {
         cuuint64_t gdim[3] = {(cuuint64_t)d->cin, (cuuint64_t)cout_pad, (cuuint64_t)d->n_taps};
         cuuint64_t gstr[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)cout_pad * d->cin * 2};
@@ -554,6 +674,7 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
     P.ws = splits > 1 ? reinterpret_cast<float*>(reinterpret_cast<char*>(d->workspace) + geo.counter_bytes) : nullptr;
     const int total_tiles = tiles * P.n_tiles_n * splits;
     cudaStream_t st = (cudaStream_t)stream;
+    if (short_k && geo.tma_epi && splits == 1) return launch_conv<64, 2, 2, true>(maps, P, total_tiles, st);
     if (short_k) return launch_conv<64, 2, 3>(maps, P, total_tiles, st);
     if (block_n == 64) return launch_conv<64, 8, 1>(maps, P, total_tiles, st);
     if (block_n == 128) return launch_conv<128, 6, 1>(maps, P, total_tiles, st);

@@ -253,3 +253,32 @@ def test_slab_kernel_is_faster_than_brick(ops, monkeypatch):
         got = y.float()
         assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item(), _diagnose(got, ref, f"full-size stem slab={mode}")
     print(f"\n[stem 160x256x256] slab {ms['1']:.3f} ms, brick {ms['0']:.3f} ms")
+
+
+@pytest.mark.parametrize("dims,cin,cout,stride,resmode,relu", [
+    ((13, 9, 7), 64, 256, 1, "same", True),        # ResNet c3 + residual, ragged bricks (TMA store clips)
+    ((40, 32, 24), 256, 64, 1, None, True),        # c1, > 148 tiles
+    ((9, 12, 11), 512, 128, 2, None, False),       # stride-2 1^3 through the sub-sampled tensor map
+    ((13, 9, 7), 512, 256, 1, "up", False),        # FPN lateral + nearest-upsampled coarser level: stays on the register epilogue
+])
+def test_tma_epilogue_matches_register_epilogue(ops, monkeypatch, dims, cin, cout, stride, resmode, relu):
+    """The shared-memory / cp.async.bulk.tensor epilogue of the 1^3 layers performs the same fp32 operations in the same order
+    as the register epilogue: outputs must be bit-identical, and both within tolerance of fp32 PyTorch."""
+    g = torch.Generator(device="cuda").manual_seed(41)
+    x = torch.randn((2, *dims, cin), device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn((cout, cin, 1, 1, 1), device="cuda", generator=g) / cin ** 0.5
+    bias = torch.randn((cout,), device="cuda", generator=g)
+    od = tuple((d - 1) // stride + 1 for d in dims)
+    res = None
+    if resmode == "same":
+        res = torch.randn((2, *od, cout), device="cuda", generator=g).to(torch.bfloat16)
+    elif resmode == "up":
+        res = torch.randn((2, *tuple((d + 1) // 2 for d in od), cout), device="cuda", generator=g).to(torch.bfloat16)
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NRPN_CONV_TMA_EPI", mode)
+        outs, refs = run_conv(ops, x, w, bias, stride, relu, res, False)
+        assert not torch.isnan(outs[0].float()).any(), f"tma_epi={mode}: unwritten outputs"
+        assert (outs[0].float() - refs[0]).abs().max().item() <= 1e-2 * refs[0].abs().max().item(), _diagnose(outs[0].float(), refs[0], f"tma_epi={mode}")
+        got[mode] = outs[0]
+    assert torch.equal(got["1"], got["0"])
