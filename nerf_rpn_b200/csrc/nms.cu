@@ -254,7 +254,8 @@ __device__ __forceinline__ void load_prep(const float* __restrict__ s, ObbPrep& 
     p.cullable = __float_as_int(s[15]);
 }
 
-// grid (W, W); CTA (cb, rb) with cb >= rb fills mask[rows of chunk rb][word cb]: a 64 x 64 tile of pairs, 64 threads.
+// grid (W, W); CTA (cb, rb) with cb >= rb fills mask[rows of chunk rb][word cb]: a 64 x 64 tile of pairs, 256 threads
+// (64-thread CTAs left the 136-tile matrices of the chunked path with 2 warps per SM: 0.8 ms per 1024-box chunk under ncu).
 // Oriented boxes take two phases so that the expensive polygon clip never runs on a half-empty warp:
 //   1. thread <-> row: the cheap tests (column right of the row, same group, not provably zero) give a 64-bit candidate
 //      word per row; the candidates of the whole tile are compacted into a list in shared memory;
@@ -262,84 +263,83 @@ __device__ __forceinline__ void load_prep(const float* __restrict__ s, ObbPrep& 
 //      the row's word with a shared-memory atomic.
 // (One row per thread with the test inline ran the full clip whenever ANY of the 32 rows of a warp needed it:
 //  measured 0.4 ns per pair regardless of how many pairs overlapped.)
-__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ prep, const int* __restrict__ sgroup, int n,
-                                                      int W, int box_dim, float thr, int ignore_group,
-                                                      unsigned long long* __restrict__ mask) {
+constexpr int kMaskThreads = 256;
+
+__global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float* __restrict__ prep, const int* __restrict__ sgroup, int n,
+                                                                int W, int box_dim, float thr, int ignore_group,
+                                                                unsigned long long* __restrict__ mask) {
     const int cb = blockIdx.x, rb = blockIdx.y;
     if (cb < rb) return;
     __shared__ __align__(16) float sp[64][kPrepFloats];      // columns
     __shared__ __align__(16) float sr[64][kPrepFloats];      // rows
-    __shared__ int sg[64];
+    __shared__ int sg[64], sgr[64];
     __shared__ unsigned long long sbits[64];
     __shared__ unsigned short list[4096];
-    __shared__ int warp_total[2];
+    __shared__ int warp_total[kMaskThreads / 32];
     const int t = threadIdx.x;
-    const int row = rb * 64 + t;
-    const int col0 = cb * 64;
-    const int row_last = min(rb * 64 + 63, n - 1);
+    const int col0 = cb * 64, row0 = rb * 64;
+    const int row_last = min(row0 + 63, n - 1);
     // groups ascend along the sorted order: no common group -> all-zero word
     const bool tile_live = sgroup[row_last] >= sgroup[col0];
-    if (!tile_live) { if (row < n) mask[(size_t)row * W + cb] = 0ull; return; }
-    {
-        const int c = col0 + t;
-        if (c < n) {
-#pragma unroll
-            for (int i = 0; i < kPrepFloats; i += 4)
-                *reinterpret_cast<float4*>(&sp[t][i]) = *reinterpret_cast<const float4*>(prep + (size_t)c * kPrepFloats + i);
-            sg[t] = sgroup[c];
-        } else sg[t] = -1;
-        if (row < n) {
-#pragma unroll
-            for (int i = 0; i < kPrepFloats; i += 4)
-                *reinterpret_cast<float4*>(&sr[t][i]) = *reinterpret_cast<const float4*>(prep + (size_t)row * kPrepFloats + i);
-        }
-        sbits[t] = 0ull;
+    if (!tile_live) { if (t < 64 && row0 + t < n) mask[(size_t)(row0 + t) * W + cb] = 0ull; return; }
+    {   // 64 column records + 64 row records, one float4 per thread (4 float4 per record)
+        const int rec = t >> 2, part = t & 3;
+        const int c = col0 + rec, r = row0 + rec;
+        if (c < n) *reinterpret_cast<float4*>(&sp[rec][part * 4]) = *reinterpret_cast<const float4*>(prep + (size_t)c * kPrepFloats + part * 4);
+        if (r < n) *reinterpret_cast<float4*>(&sr[rec][part * 4]) = *reinterpret_cast<const float4*>(prep + (size_t)r * kPrepFloats + part * 4);
+        if (t < 64) { sg[t] = (col0 + t < n) ? sgroup[col0 + t] : -1; sgr[t] = (row0 + t < n) ? sgroup[row0 + t] : -2; sbits[t] = 0ull; }
     }
     __syncthreads();
-    const int g = row < n ? sgroup[row] : -1;
+    // thread <-> (row, 16-column quarter)
+    const int rl = t & 63, quarter = t >> 6;
+    const int row = row0 + rl;
+    const int g = sgr[rl];
     const bool row_live = row < n && g != ignore_group;
     if (box_dim != 7) {
         unsigned long long bits = 0ull;
         if (row_live) {
-            for (int c = 0; c < 64; ++c) {
+            for (int c = quarter * 16; c < quarter * 16 + 16; ++c) {
                 const int col = col0 + c;
                 if (col <= row || sg[c] != g) continue;
-                const float iou = iou3d_aabb(sr[t], sp[c]);
+                const float iou = iou3d_aabb(sr[rl], sp[c]);
                 if (!(iou <= thr)) bits |= 1ull << c;
             }
         }
-        if (row < n) mask[(size_t)row * W + cb] = bits;
+        if (bits) atomicOr(&sbits[rl], bits);
+        __syncthreads();
+        if (t < 64 && row0 + t < n) mask[(size_t)(row0 + t) * W + cb] = sbits[t];
         return;
     }
-    // ---- phase 1: candidate word per row
+    // ---- phase 1: candidate bits of this thread's 16 columns
     const bool cull_ok = (0.0f <= thr);
-    unsigned long long cand = 0ull;
+    unsigned cand = 0u;
     if (row_live) {
-        for (int c = 0; c < 64; ++c) {
-            const int col = col0 + c;
+        for (int k = 0; k < 16; ++k) {
+            const int c = quarter * 16 + k, col = col0 + c;
             if (col <= row || sg[c] != g) continue;
-            if (cull_ok && obb_surely_zero(&sr[t][8], &sp[c][8])) continue;
-            cand |= 1ull << c;
+            if (cull_ok && obb_surely_zero(&sr[rl][8], &sp[c][8])) continue;
+            cand |= 1u << k;
         }
     }
-    // exclusive prefix sum of the candidate counts over the 64 threads
-    const int cnt = __popcll(cand);
+    // exclusive prefix sum of the candidate counts over the CTA
+    const int cnt = __popc(cand);
     const int lane = t & 31, wid = t >> 5;
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
     if (lane == 31) warp_total[wid] = incl;
     __syncthreads();
-    int base = incl - cnt + (wid ? warp_total[0] : 0);
-    const int total = warp_total[0] + warp_total[1];
+    int base = incl - cnt, total = 0;
+#pragma unroll
+    for (int w = 0; w < kMaskThreads / 32; ++w) { if (w < wid) base += warp_total[w]; total += warp_total[w]; }
     while (cand) {
-        const int c = __ffsll((long long)cand) - 1;
-        cand &= cand - 1ull;
-        list[base++] = (unsigned short)((t << 6) | c);
+        const int k = __ffs((int)cand) - 1;
+        cand &= cand - 1u;
+        list[base++] = (unsigned short)((rl << 6) | (quarter * 16 + k));
     }
     __syncthreads();
     // ---- phase 2: one candidate pair per thread
-    for (int i = t; i < total; i += 64) {
+    for (int i = t; i < total; i += kMaskThreads) {
         const int e = list[i], r = e >> 6, c = e & 63;
         ObbPrep a, b;
         load_prep(sr[r], a);
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
         if (!(iou <= thr)) atomicOr(&sbits[r], 1ull << c);
     }
     __syncthreads();
-    if (row < n) mask[(size_t)row * W + cb] = sbits[t];
+    if (t < 64 && row0 + t < n) mask[(size_t)(row0 + t) * W + cb] = sbits[t];
 }
 
 __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
@@ -630,7 +630,7 @@ int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t*
     nms_prep_kernel<<<ceil_div(n, 128), 128, 0, st>>>(w.keys, boxes, box_dim, n, w.prep, w.sgroup, w.seg);
     NRPN_LAUNCH_CHECK();
     if (nms_use_matrix(n, max_group)) {
-        nms_mask_kernel<<<dim3(W, W), 64, 0, st>>>(w.prep, w.sgroup, n, W, box_dim, thr, ignore_group, w.mask);
+        nms_mask_kernel<<<dim3(W, W), kMaskThreads, 0, st>>>(w.prep, w.sgroup, n, W, box_dim, thr, ignore_group, w.mask);
         NRPN_LAUNCH_CHECK();
         nms_resolve_kernel<<<256, 256, 0, st>>>(w.mask, W, n, w.seg, ignore_group, w.keepbits);
         NRPN_LAUNCH_CHECK();
@@ -645,7 +645,7 @@ int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t*
             nms_cross_kernel<<<ceil_div(cn, 8), 256, 0, st>>>(w.prep, w.sgroup, box_dim, thr, ignore_group, cb, cn,
                                                                      w.kept_pos, w.state, w.removed0);
             NRPN_LAUNCH_CHECK();
-            nms_mask_kernel<<<dim3(Wc, Wc), 64, 0, st>>>(w.prep + (size_t)cb * kPrepFloats, w.sgroup + cb, cn, Wc, box_dim, thr,
+            nms_mask_kernel<<<dim3(Wc, Wc), kMaskThreads, 0, st>>>(w.prep + (size_t)cb * kPrepFloats, w.sgroup + cb, cn, Wc, box_dim, thr,
                                                         ignore_group, w.mask);
             NRPN_LAUNCH_CHECK();
             nms_chunk_resolve_kernel<<<1, 256, 0, st>>>(w.mask, Wc, cb, cn, w.sgroup, w.removed0, w.kept_pos, w.state, w.keepbits);
