@@ -6,7 +6,9 @@
 //   patch_merge_ln        2x2x2 gather (zero pad on odd extents) + LayerNorm(8C)     (:661-685)
 //   window_attention      4^3 shifted-window multi-head attention, head_dim 32        (:382-497)
 // Activations are (N, H, W, D, ld) bf16 with C real channels and ld >= C (ld a multiple of 64; channels [C, ld) stay zero).
+#include <cstdlib>
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace nrpn {
 
@@ -175,6 +177,194 @@ __global__ void __launch_bounds__(64) window_attention_kernel(AttnDev P) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------- window attention on tcgen05
+// Two 64-token windows of the same head are stacked into ONE M = 128 problem: S = Q K^T is a 128 x 128 tcgen05.mma whose two
+// diagonal 64 x 64 blocks are the windows' score matrices (the off-diagonal blocks are never read); softmax runs from TMEM
+// (thread r <-> query row r: scale, relative-position bias, -100 region mask, exp); the un-normalised probabilities go back to
+// shared memory as bf16 with the other window's block zeroed, and O = P V is a second MMA (M 128, N 32, K 128) against V^T.
+// The 1/sum normalisation is applied to the fp32 accumulator.  Operands are written to shared memory by the threads
+// themselves (a token's q/k/v are 64 contiguous bytes each) in the 128B-swizzled K-major layout; V is transposed on the way.
+constexpr int kAttnThreads = 128;
+constexpr int kAttnSmem = 16384 /*Q*/ + 16384 /*K*/ + 2 * 4096 /*V^T*/ + 2 * 16384 /*P*/ + 1024 /*align*/ + 2048 /*table, regions, barriers*/;
+
+__device__ __forceinline__ uint32_t attn_sw(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+__global__ void __launch_bounds__(kAttnThreads) window_attention_tc_kernel(AttnDev P, int n_windows) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* Qs = smem;
+    uint8_t* Ks = smem + 16384;
+    uint8_t* Vt = smem + 32768;                 // [2 tiles][32 rows (d)][64 tokens]
+    uint8_t* Ps = smem + 40960;                 // [2 tiles (key halves)][128 rows][64 keys]
+    float* tbl = reinterpret_cast<float*>(smem + 73728);          // 343 relative-position biases of this head
+    int* region = reinterpret_cast<int*>(smem + 73728 + 1408);    // 128
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 73728 + 1408 + 512);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int head = blockIdx.y;
+    const int t = threadIdx.x, warp = t >> 5;
+    const int hc = head * 32;
+    for (int i = t; i < 343; i += kAttnThreads) tbl[i] = P.table[i * P.heads + head];
+    if (t == 0) { ptx::mbar_init(&bars[0], 1); ptx::mbar_init(&bars[1], 1); ptx::fence_barrier_init(); }
+    if (warp == 0) { ptx::tmem_alloc(tmem_slot, 128); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const bool shifted = (P.sh + P.sw + P.sd) > 0;
+    const int half = t >> 6, tw = t & 63;                          // stacked window (0/1), token inside it
+    const int ti = tw >> 4, tj = (tw >> 2) & 3, tk = tw & 3;
+    constexpr uint32_t kIdescS = ptx::make_idesc_bf16(128, 128);
+    constexpr uint32_t kIdescO = ptx::make_idesc_bf16(128, 32);
+    uint32_t phase = 0;
+    for (int pair = blockIdx.x; pair * 2 < n_windows; pair += gridDim.x) {
+        int w = pair * 2 + half;
+        const bool have = w < n_windows;
+        const int wd = w % P.nwd; w /= P.nwd;
+        const int ww = w % P.nww; w /= P.nww;
+        const int wh = w % P.nwh; const int b = w / P.nwh;
+        const int ph = wh * 4 + ti, pw = ww * 4 + tj, pd = wd * 4 + tk;   // position in the padded, shifted grid
+        const int sh_ = (ph + P.sh) % P.PH, sw_ = (pw + P.sw) % P.PW, sd_ = (pd + P.sd) % P.PD;
+        const bool real = have && sh_ < P.H && sw_ < P.W && sd_ < P.D;
+        const size_t tok = have ? ((((size_t)b * P.H + sh_) * P.W + sw_) * P.D + sd_) : 0;
+        {   // ---- stage q, k (row t of the K-major tiles) and v (column t of V^T)
+            uint4 qv[4], kv[4], vv[4];
+            if (real) {
+                const __nv_bfloat16* row = P.qkv + tok * P.ld_qkv;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    qv[i] = __ldg(reinterpret_cast<const uint4*>(row + hc) + i);
+                    kv[i] = __ldg(reinterpret_cast<const uint4*>(row + P.C + hc) + i);
+                    vv[i] = __ldg(reinterpret_cast<const uint4*>(row + 2 * P.C + hc) + i);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    __nv_bfloat162 a[4], c[4], e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int d = i * 8 + u * 2;
+                        a[u] = have ? __floats2bfloat162_rn(P.qkv_bias[hc + d], P.qkv_bias[hc + d + 1]) : __floats2bfloat162_rn(0.f, 0.f);
+                        c[u] = have ? __floats2bfloat162_rn(P.qkv_bias[P.C + hc + d], P.qkv_bias[P.C + hc + d + 1]) : __floats2bfloat162_rn(0.f, 0.f);
+                        e[u] = have ? __floats2bfloat162_rn(P.qkv_bias[2 * P.C + hc + d], P.qkv_bias[2 * P.C + hc + d + 1]) : __floats2bfloat162_rn(0.f, 0.f);
+                    }
+                    qv[i] = *reinterpret_cast<uint4*>(a); kv[i] = *reinterpret_cast<uint4*>(c); vv[i] = *reinterpret_cast<uint4*>(e);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                *reinterpret_cast<uint4*>(Qs + attn_sw(t, i)) = qv[i];
+                *reinterpret_cast<uint4*>(Ks + attn_sw(t, i)) = kv[i];
+            }
+            uint8_t* vt = Vt + half * 4096;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&vv[i]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int d = i * 8 + u;
+                    *reinterpret_cast<__nv_bfloat16*>(vt + attn_sw(d, tw >> 3) + (tw & 7) * 2) = e[u];
+                }
+            }
+            auto reg1 = [](int p, int Pext, int s) { return s == 0 ? 2 : (p < Pext - 4 ? 0 : (p < Pext - s ? 1 : 2)); };
+            region[t] = shifted ? (reg1(ph, P.PH, P.sh) * 9 + reg1(pw, P.PW, P.sw) * 3 + reg1(pd, P.PD, P.sd)) : 0;
+        }
+        ptx::fence_proxy_async();
+        ptx::tc_fence_before();
+        __syncthreads();
+        if (warp == 0) {
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t da = ptx::make_desc_sw128(ptx::smem_u32(Qs)), db = ptx::make_desc_sw128(ptx::smem_u32(Ks));
+#pragma unroll
+                for (int k = 0; k < 2; ++k)                                   // head_dim 32 = two K-steps of 16
+                    ptx::umma_bf16(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdescS, k ? 1u : 0u);
+                ptx::umma_commit(&bars[0]);
+            }
+            __syncwarp();
+        }
+        ptx::mbar_wait(&bars[0], phase);
+        ptx::tc_fence_after();
+        // ---- softmax of row t over its own window's 64 keys
+        float sc[64];
+        {
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 64);
+            ptx::tmem_ld_32x32(taddr, r0);
+            ptx::tmem_ld_32x32(taddr + 32, r1);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { sc[j] = __uint_as_float(r0[j]); sc[32 + j] = __uint_as_float(r1[j]); }
+        }
+        const int myreg = region[t];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            const int ji = j >> 4, jj = (j >> 2) & 3, jk = j & 3;
+            float a = sc[j] * 0.17677669529663687f + tbl[(ti - ji + 3) * 49 + (tj - jj + 3) * 7 + (tk - jk + 3)];
+            if (shifted && region[half * 64 + j] != myreg) a += -100.0f;
+            sc[j] = a; mx = fmaxf(mx, a);
+        }
+        float sum = 0.f;
+        {
+            uint8_t* mine = Ps + half * 16384;
+            uint8_t* other = Ps + (1 - half) * 16384;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float e[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { e[u] = __expf(sc[c * 8 + u] - mx); sum += e[u]; }
+                __nv_bfloat162 pk[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pk[u] = __floats2bfloat162_rn(e[2 * u], e[2 * u + 1]);
+                *reinterpret_cast<uint4*>(mine + attn_sw(t, c)) = *reinterpret_cast<uint4*>(pk);
+                *reinterpret_cast<uint4*>(other + attn_sw(t, c)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        ptx::fence_proxy_async();
+        ptx::tc_fence_before();
+        __syncthreads();                                   // every S row has been read: its TMEM columns may be overwritten by O
+        if (warp == 0) {
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint64_t da = ptx::make_desc_sw128(ptx::smem_u32(Ps + h * 16384));
+                    const uint64_t db = ptx::make_desc_sw128(ptx::smem_u32(Vt + h * 4096));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_bf16(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdescO, (h | k) ? 1u : 0u);
+                }
+                ptx::umma_commit(&bars[1]);
+            }
+            __syncwarp();
+        }
+        ptx::mbar_wait(&bars[1], phase);
+        ptx::tc_fence_after();
+        {
+            uint32_t o[32];
+            ptx::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16), o);
+            ptx::tmem_ld_wait();
+            if (real) {
+                const float inv = 1.0f / sum;
+                __nv_bfloat16* orow = P.out + tok * P.ld_out + hc;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    __nv_bfloat162 pk[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        pk[u] = __floats2bfloat162_rn(__uint_as_float(o[i * 8 + 2 * u]) * inv, __uint_as_float(o[i * 8 + 2 * u + 1]) * inv);
+                    *(reinterpret_cast<uint4*>(orow) + i) = *reinterpret_cast<uint4*>(pk);
+                }
+            }
+        }
+        ptx::tc_fence_before();
+        __syncthreads();                                   // O has been read, the operand tiles may be rewritten
+        ptx::tc_fence_after();
+        phase ^= 1u;
+    }
+    if (warp == 0) ptx::tmem_dealloc(tmem, 128);
+}
+
 static inline unsigned grid_for(size_t total, int block) {
     size_t g = (total + block - 1) / block;
     const size_t cap = (size_t)num_sms() * 16;
@@ -228,6 +418,24 @@ int nrpn_window_attention(const void* qkv, int ld_qkv, void* out, int ld_out, co
     P.nwh = P.PH / 4; P.nww = P.PW / 4; P.nwd = P.PD / 4;
     const long windows = (long)n * P.nwh * P.nww * P.nwd;
     if (windows > 0x7fffffffL || heads > 65535) return NRPN_ERR_UNSUPPORTED;
+    // tcgen05 path: needs 16-byte aligned 64-byte q/k/v segments; NRPN_ATTN_TC=0 selects the CUDA-core kernel (A/B testing)
+    const char* e = getenv("NRPN_ATTN_TC");
+    const bool tc = !(e && e[0] == '0') && ld_qkv % 8 == 0 && ld_out % 8 == 0 && c % 8 == 0 &&
+                    reinterpret_cast<uintptr_t>(qkv) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+    if (tc) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            NRPN_CUDA_TRY(cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+            attr_set = true;
+        }
+        const long pairs = (windows + 1) / 2;
+        long gx = (long)num_sms() * 3 / heads;              // ~3 resident CTAs per SM in total, each looping over window pairs
+        if (gx < 1) gx = 1;
+        if (gx > pairs) gx = pairs;
+        window_attention_tc_kernel<<<dim3((unsigned)gx, heads), kAttnThreads, kAttnSmem, (cudaStream_t)stream>>>(P, (int)windows);
+        NRPN_LAUNCH_CHECK();
+        return NRPN_OK;
+    }
     window_attention_kernel<<<dim3((unsigned)windows, heads), 64, 0, (cudaStream_t)stream>>>(P);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
