@@ -255,6 +255,18 @@ int nrpn_fcos_proposals(const nrpn_fcos_desc *desc /*host*/, float *boxes, float
  * index, as torch.max on CPU.  n_proposals <= 32 768, n_gt <= 4 096. */
 int nrpn_recall_match(const float *overlaps, int n_proposals, int n_gt, float *gt_overlaps, nrpn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------ training targets
+ * RegionProposalNetwork.assign_targets_to_anchors (rpn.py:240-290): IoU of every anchor with every (rectified, obb2hbb_3d)
+ * ground-truth box, Matcher(high, low, allow_low_quality_matches) (utils.py:98-212) and the label mapping, without the
+ * (G, N) matrix.  anchors (N,6) f32 [x1,y1,z1,x2,y2,z2]; gt (G,6) AABB or (G,7) OBB; valid: optional (N) u8 padding mask
+ * (0 = anchor in a padded voxel: enters the matcher as -1.0, label -1).  labels (N) f32 in {1, 0, -1}; matched_idxs (N) i64:
+ * the matcher's output (GT index, -1 below low, -2 between thresholds); gather gt[clamp(idx, 0)] for the matched boxes.
+ * G <= 1024.  G == 0 is the caller's "background mesh" case (rpn.py:246-250) and is rejected here. */
+size_t nrpn_assign_targets_workspace_bytes(int n_anchors, int n_gt);
+int nrpn_assign_targets(const float *anchors, int n_anchors, const float *gt, int n_gt, int gt_dim, const uint8_t *valid,
+                        float high_threshold, float low_threshold, int allow_low_quality_matches, float *labels,
+                        int64_t *matched_idxs, void *workspace, size_t workspace_bytes, nrpn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

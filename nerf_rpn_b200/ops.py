@@ -48,6 +48,24 @@ def iou3d_matrix(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def assign_targets(anchors: torch.Tensor, gt: torch.Tensor, valid: Optional[torch.Tensor], high: float, low: float,
+                   allow_low_quality_matches: bool = True):
+    """anchors (N,6), gt (G,6|7), valid (N) bool or None -> labels (N) f32 in {1,0,-1}, matched_idxs (N) i64 (rpn.py:240-290)."""
+    anchors = _req(anchors, torch.float32, "anchors")
+    gt = _req(gt, torch.float32, "gt")
+    n, g = anchors.shape[0], gt.shape[0]
+    v = None
+    if valid is not None:
+        v = valid.to(torch.uint8).contiguous()
+    labels = torch.empty((n,), dtype=torch.float32, device=anchors.device)
+    matched = torch.empty((n,), dtype=torch.int64, device=anchors.device)
+    ws = _workspace(lib().nrpn_assign_targets_workspace_bytes(n, g), anchors.device)
+    check(lib().nrpn_assign_targets(_ptr(anchors), n, _ptr(gt), g, int(gt.shape[1]), _ptr(v), float(high), float(low),
+                                    int(bool(allow_low_quality_matches)), _ptr(labels), _ptr(matched), _ptr(ws), ws.numel(), _stream()),
+          "assign_targets")
+    return labels, matched
+
+
 def recall_match(overlaps: torch.Tensor) -> torch.Tensor:
     """(P, G) fp32 IoU matrix -> the min(P, G) IoUs recorded by the greedy loop of eval.py:33-52 (device resident)."""
     overlaps = _req(overlaps, torch.float32, "overlaps")

@@ -1,0 +1,77 @@
+"""GPU: nrpn_assign_targets (anchor <-> ground-truth assignment, rpn.py:240-290) against the reference's own outputs and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import targets_oracle as T
+from tests.test_targets_cpu import small_anchors
+
+pytestmark = pytest.mark.gpu
+
+
+def test_assign_targets_vs_reference_golden(golden_dir):
+    from nerf_rpn_b200 import ops
+    g = np.load(os.path.join(golden_dir, "targets_small.npz"))
+    anchors = small_anchors().cuda()
+    mask = torch.from_numpy(g["mask"]).cuda()
+    for tag in ("a", "b"):
+        for kind in ("obb", "aabb"):
+            for use_mask in (0, 1):
+                key = f"{tag}_{kind}_{use_mask}"
+                gt = torch.from_numpy(g["gt_" + key]).cuda()
+                labels, idx = ops.assign_targets(anchors, gt, mask if use_mask else None, 0.35, 0.2, True)
+                np.testing.assert_array_equal(labels.cpu().numpy().astype(np.int8), g["labels_" + key], err_msg=key)
+                np.testing.assert_array_equal(idx.cpu().numpy().astype(np.int16), g["matched_" + key], err_msg=key)
+
+
+def test_assign_targets_module_api_and_full_size():
+    """The module-level mirror (same signature as the reference method) and the BASELINE-size anchor set (2 433 600 anchors)
+    against the oracle on a sub-sample of anchors... the per-GT maxima need ALL anchors, so compare on a 1/16 scene instead and
+    check size-independent properties at full size."""
+    from nerf_rpn_b200 import ops
+    from nerf_rpn_b200.model.anchor import AnchorGenerator3D, RPNHead
+    from nerf_rpn_b200.model.rpn import RegionProposalNetwork
+    from tests import recipes
+    ag = AnchorGenerator3D(recipes.ANCHOR_SIZES, recipes.ASPECT)
+    rng = np.random.default_rng(5)
+
+    def scene(dims, n_gt):
+        feats = [torch.zeros(1, 1, *[(d + s - 1) // s for d in dims]) for s in (4, 8, 16, 32)]
+        anchors = ag(torch.zeros(1, 4, *dims), feats)[0][0]
+        d = np.array(dims, np.float32)
+        gt = np.concatenate([rng.random((n_gt, 3)).astype(np.float32) * d, rng.random((n_gt, 3)).astype(np.float32) * 40 + 6,
+                             (rng.random((n_gt, 1)).astype(np.float32) - 0.5) * np.pi], 1).astype(np.float32)
+        return anchors, torch.from_numpy(gt)
+
+    rpn = RegionProposalNetwork(ag, RPNHead(256, 13, 1), 0.35, 0.2, 256, 0.5, dict(training=2500, testing=2500),
+                                dict(training=2500, testing=2500), 0.3)
+    anchors, gt = scene((64, 96, 80), 40)
+    labels, boxes = rpn.assign_targets_to_anchors([anchors], [gt])
+    ol, oi = T.assign(anchors.numpy(), gt.numpy(), None, 0.35, 0.2)
+    np.testing.assert_array_equal(labels[0].numpy(), ol)
+    np.testing.assert_array_equal(boxes[0].numpy(), gt.numpy()[np.clip(oi, 0, None)])
+    # full size
+    anchors, gt = scene((160, 256, 256), 64)
+    assert anchors.shape[0] == 2433600
+    a = anchors.cuda()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lab, idx = ops.assign_targets(a, gt.cuda(), None, 0.35, 0.2, True)
+    ev0.record()
+    lab, idx = ops.assign_targets(a, gt.cuda(), None, 0.35, 0.2, True)
+    ev1.record(); torch.cuda.synchronize()
+    print(f"\nassign_targets: 2 433 600 anchors x 64 GT in {ev0.elapsed_time(ev1):.3f} ms (the reference materialises a 623 MB IoU matrix)")
+    lab_c, idx_c = lab.cpu().numpy(), idx.cpu().numpy()
+    assert set(np.unique(lab_c)).issubset({-1.0, 0.0, 1.0}) and idx_c.min() >= -2 and idx_c.max() < 64
+    assert np.all((lab_c == 1) == (idx_c >= 0)) and np.all((lab_c == 0) == (idx_c == -1))
+    # every ground-truth box owns at least one positive anchor (low-quality matches), and a random sub-sample agrees with the oracle
+    # on the threshold part of the rule (IoU of the matched pair recomputed on the CPU)
+    pos_gt = np.unique(idx_c[idx_c >= 0])
+    assert pos_gt.shape[0] == 64
+    sel = rng.choice(anchors.shape[0], 20000, replace=False)
+    m = T.aabb_iou(T.obb2hbb_3d(gt.numpy()), anchors.numpy()[sel])
+    vals = m.max(axis=0)
+    strong = vals >= np.float32(0.35)
+    assert np.all(lab_c[sel][strong] == 1) and np.all(idx_c[sel][strong] == m.argmax(axis=0)[strong])
+    assert np.all(lab_c[sel][vals < np.float32(0.2)] != -1)          # below the low threshold: background, or a low-quality positive

@@ -419,7 +419,48 @@ def gen_recall(n_scenes=12):
     np.savez_compressed(os.path.join(OUT, "recall_small_obb.npz"), **out)
 
 
+def gen_targets():
+    """assign_targets_to_anchors (rpn.py:240-290) pieces run through the reference's own functions on CPU: obb2hbb_3d,
+    batched_box_iou (chunks of 16 GT), Matcher(0.35, 0.2, allow_low_quality_matches=True) and the label mapping."""
+    from model.coder.misc import obb2hbb_3d
+    from model.utils import Matcher, batched_box_iou
+    dims = (32, 48, 40)
+    ag = AnchorGenerator3D(ANCHOR_SIZES, ASPECT)
+    feats = [torch.zeros(1, 1, *[(d + s - 1) // s for d in dims]) for s in (4, 8, 16, 32)]
+    anchors = ag(torch.zeros(1, 4, *dims), feats)[0][0]
+    matcher = Matcher(0.35, 0.2, allow_low_quality_matches=True)
+    out = dict(anchors_sum=np.float64(anchors.double().sum().item()), n_anchors=np.int64(anchors.shape[0]))
+    gen = torch.Generator().manual_seed(11)
+    mask = torch.rand(anchors.shape[0], generator=gen) > 0.1            # stands in for get_padding_masks (anchor.py:124-152)
+    for tag, n_gt in (("a", 24), ("b", 3)):
+        _, gt = recall_scene(7 if tag == "a" else 8, dims, n_gt)
+        if tag == "b":
+            gt[2, :3] = torch.tensor([500.0, 500.0, 500.0])              # a ground-truth box no anchor touches: the IoU == max == 0 tie quirk
+        for kind in ("obb", "aabb"):
+            g = gt if kind == "obb" else obb2hbb_3d(gt)
+            gq = obb2hbb_3d(g) if kind == "obb" else g
+            for use_mask in (False, True):
+                m = batched_box_iou(gq, anchors, 16)
+                if use_mask:
+                    m[:, ~mask] = -1.0
+                idx = matcher(m)
+                labels = (idx >= 0).float()
+                labels[idx == -1] = 0.0
+                labels[idx == -2] = -1.0
+                if use_mask:
+                    labels[~mask] = -1.0
+                key = f"{tag}_{kind}_{int(use_mask)}"
+                out["gt_" + key] = g.numpy()
+                out["labels_" + key] = labels.numpy().astype(np.int8)
+                out["matched_" + key] = idx.numpy().astype(np.int16)
+                print(key, "pos", int((labels == 1).sum()), "neg", int((labels == 0).sum()), "ignored", int((labels == -1).sum()))
+    out["mask"] = mask.numpy()
+    np.savez_compressed(os.path.join(OUT, "targets_small.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--targets-only" in sys.argv:
+        sys.path.insert(0, ROOT); gen_targets(); sys.exit(0)
     if "--recall-only" in sys.argv:
         sys.path.insert(0, ROOT); gen_recall(); sys.exit(0)
     if "--swin-only" in sys.argv:
@@ -436,3 +477,4 @@ if __name__ == "__main__":
     gen_fcos_small()
     gen_swin_small()
     sys.path.insert(0, ROOT); gen_recall()
+    gen_targets()
