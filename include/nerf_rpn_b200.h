@@ -116,6 +116,7 @@ typedef struct {
     nrpn_conv_level level[NRPN_CONV_MAX_LEVELS];
     void *workspace;                /* optional split-K scratch (see nrpn_conv3d_workspace_bytes) or NULL */
     size_t workspace_bytes;
+    int32_t act_fp16;               /* 16-bit format of x / w / res / 16-bit y: 0 = bf16, 1 = fp16 (IEEE half) */
 } nrpn_conv_desc;
 
 /* Padding granularity of the output-channel axis for this cout (64, 128 or 256): w / shift must be padded to a multiple. */
@@ -140,10 +141,10 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc *desc /*host*/, nrpn_stream_t stream)
  * of voxel (i,j,k-1) followed by the block of voxel (i,j,k), k in [0, ceil(Z/2)] (so the packed Z extent is
  * ceil(Z/2)+1); turns the 7^3 stride-2 stem conv (feature_extractor.py:163) into a 4x4x2-tap stride-1
  * implicit GEMM with K = 64 per tap. */
-int nrpn_pack_stem_input(const float *grid, int n, int x, int y, int z, void *packed, nrpn_stream_t stream);
+int nrpn_pack_stem_input(const float *grid, int n, int x, int y, int z, void *packed, int act_fp16, nrpn_stream_t stream);
 
 /* F.max_pool3d(kernel 3, stride 2, padding 1) on (N,X,Y,Z,C) bf16, C % 8 == 0 (feature_extractor.py:219). */
-int nrpn_maxpool3d_k3s2(const void *in, int n, int x, int y, int z, int c, void *out, nrpn_stream_t stream);
+int nrpn_maxpool3d_k3s2(const void *in, int n, int x, int y, int z, int c, void *out, int act_fp16, nrpn_stream_t stream);
 
 /* nn.MaxPool3d(kernel 2, stride 2, ceil_mode=True) (VGG stages, feature_extractor.py:347): output extent ceil(in/2). */
 int nrpn_maxpool3d_k2s2_ceil(const void *in, int n, int x, int y, int z, int c, void *out, nrpn_stream_t stream);

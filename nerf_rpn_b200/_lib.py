@@ -29,7 +29,7 @@ class ConvDesc(ctypes.Structure):
                 ("tap_off", (ctypes.c_int8 * 3) * MAX_TAPS), ("stride", ctypes.c_int32), ("relu", ctypes.c_int32),
                 ("out_fp32", ctypes.c_int32), ("w", ctypes.c_void_p), ("shift", ctypes.c_void_p),
                 ("n_levels", ctypes.c_int32), ("level", ConvLevel * MAX_LEVELS), ("workspace", ctypes.c_void_p),
-                ("workspace_bytes", ctypes.c_size_t)]
+                ("workspace_bytes", ctypes.c_size_t), ("act_fp16", ctypes.c_int32)]
 
 
 class RpnLevel(ctypes.Structure):
@@ -80,9 +80,9 @@ _SIGNATURES = {
     "nrpn_conv3d_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvDesc)]),
     "nrpn_conv3d_fprop": (ctypes.c_int, [ctypes.POINTER(ConvDesc), c_stream]),
     "nrpn_pack_stem_input": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                            ctypes.c_void_p, c_stream]),
+                                            ctypes.c_void_p, ctypes.c_int, c_stream]),
     "nrpn_maxpool3d_k3s2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                           ctypes.c_int, ctypes.c_void_p, c_stream]),
+                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_int, c_stream]),
     "nrpn_maxpool3d_k2s2_ceil": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_int, ctypes.c_void_p, c_stream]),
     "nrpn_pack_stem_input_s1": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

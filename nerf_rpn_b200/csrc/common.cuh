@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <atomic>
 #include "../../include/nerf_rpn_b200.h"
@@ -39,6 +40,20 @@ inline int num_sms() {
     }
     return sms;
 }
+
+// 16-bit activation format of a launch: 0 = bf16 (default, BASELINE config 2), 1 = fp16 (same tensor-core rate, 11-bit
+// significand: the higher-parity mode of DESIGN.md section 4).  Storage is 2 bytes either way; only conversions differ.
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t pack_act2(float a, float b, int fp16) {
+    if (fp16) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_act2(uint32_t u, int fp16) {
+    if (fp16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+#endif
 
 template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }

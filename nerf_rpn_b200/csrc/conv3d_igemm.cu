@@ -45,7 +45,7 @@ struct ConvLevelDev {
 };
 
 struct ConvDev {
-    int n_levels, n_taps, kc_blocks, n_tiles_n, cout, relu, out_fp32;
+    int n_levels, n_taps, kc_blocks, n_tiles_n, cout, relu, out_fp32, fp16;
     int total_m_tiles;
     int splits, cout_pad;      // split-K: `splits` CTAs share one output tile and reduce through `ws`
     float* ws;                 // fp32 (tiles, splits, 128, BLOCK_N) partial tiles, rewritten by every launch
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
     constexpr int kStageBytes = kABytes + kBBytes;
     constexpr int kEpiBytes = TMA_EPI ? 3 * kEpiTileBytes : 0;      // residual ring (2) + output staging (1)
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;
-    constexpr uint32_t kIdesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
+    const uint32_t kIdesc = P.fp16 ? ptx::make_idesc_f16(kBlockM, BLOCK_N) : ptx::make_idesc_bf16(kBlockM, BLOCK_N);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -279,9 +279,9 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                             float v[8] = {a0.x + s0.x, a0.y + s0.y, a0.z + s0.z, a0.w + s0.w, a1.x + s1.x, a1.y + s1.y, a1.z + s1.z, a1.w + s1.w};
                             if (rrow != nullptr) {
                                 const uint4 rv4 = __ldg(reinterpret_cast<const uint4*>(rrow + ch));
-                                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv4);
+                                const uint32_t* rb = reinterpret_cast<const uint32_t*>(&rv4);
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(rb[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
+                                for (int i = 0; i < 4; ++i) { const float2 f = unpack_act2(rb[i], P.fp16); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
                             }
                             if (P.relu == 1) {
 #pragma unroll
@@ -296,8 +296,8 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                                 *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
                             } else {
                                 __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(L.y) + vox * L.ldy + ch;
-                                *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                                                          pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                                *reinterpret_cast<uint4*>(o) = make_uint4(pack_act2(v[0], v[1], P.fp16), pack_act2(v[2], v[3], P.fp16),
+                                                                          pack_act2(v[4], v[5], P.fp16), pack_act2(v[6], v[7], P.fp16));
                             }
                         }
                     }
@@ -337,9 +337,9 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                         if (res_smem || rrow != nullptr) {
                             const uint4 rv4 = res_smem ? *reinterpret_cast<const uint4*>(rsm + ((j ^ sw) << 4))
                                                        : __ldg(reinterpret_cast<const uint4*>(rrow + ch));
-                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv4);
+                            const uint32_t* rb = reinterpret_cast<const uint32_t*>(&rv4);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(rb[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
+                            for (int i = 0; i < 4; ++i) { const float2 f = unpack_act2(rb[i], P.fp16); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
                         }
                         if (P.relu == 1) {
 #pragma unroll
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                             for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
                         }
                         *reinterpret_cast<uint4*>(osm + ((j ^ sw) << 4)) =
-                            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                            make_uint4(pack_act2(v[0], v[1], P.fp16), pack_act2(v[2], v[3], P.fp16), pack_act2(v[4], v[5], P.fp16), pack_act2(v[6], v[7], P.fp16));
                     }
                 }
                 ptx::tc_fence_before();
@@ -411,9 +411,9 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                                 vv[4] = __uint_as_float(rr[4]) + s1.x; vv[5] = __uint_as_float(rr[5]) + s1.y;
                                 vv[6] = __uint_as_float(rr[6]) + s1.z; vv[7] = __uint_as_float(rr[7]) + s1.w;
                                 if (rrow != nullptr) {
-                                    const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv[2 * h + g]);
+                                    const uint32_t* rb = reinterpret_cast<const uint32_t*>(&rv[2 * h + g]);
 #pragma unroll
-                                    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(rb[i]); vv[2 * i] += f.x; vv[2 * i + 1] += f.y; }
+                                    for (int i = 0; i < 4; ++i) { const float2 f = unpack_act2(rb[i], P.fp16); vv[2 * i] += f.x; vv[2 * i + 1] += f.y; }
                                 }
                             } else {
 #pragma unroll
@@ -440,8 +440,8 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                             }
                         } else {
                             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(L.y) + vox * L.ldy + chh;
-                            const uint4 lo = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                            const uint4 hi = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                            const uint4 lo = make_uint4(pack_act2(v[0], v[1], P.fp16), pack_act2(v[2], v[3], P.fp16), pack_act2(v[4], v[5], P.fp16), pack_act2(v[6], v[7], P.fp16));
+                            const uint4 hi = make_uint4(pack_act2(v[8], v[9], P.fp16), pack_act2(v[10], v[11], P.fp16), pack_act2(v[12], v[13], P.fp16), pack_act2(v[14], v[15], P.fp16));
                             if (both && L.wide_y) ptx::st_global_v8(o, lo, hi);
                             else { *reinterpret_cast<uint4*>(o) = lo; if (both) *reinterpret_cast<uint4*>(o + 8) = hi; }
                         }
@@ -600,7 +600,7 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
     ConvDev P;
     memset(&P, 0, sizeof(P));
     P.n_levels = d->n_levels; P.n_taps = d->n_taps; P.kc_blocks = d->cin / kBlockK; P.n_tiles_n = cout_pad / block_n;
-    P.cout = d->cout; P.relu = d->relu; P.out_fp32 = d->out_fp32; P.shift = d->shift;
+    P.cout = d->cout; P.relu = d->relu; P.out_fp32 = d->out_fp32; P.shift = d->shift; P.fp16 = d->act_fp16 ? 1 : 0;
     for (int t = 0; t < d->n_taps; ++t) { P.tap[t][0] = d->tap_off[t][0]; P.tap[t][1] = d->tap_off[t][1]; P.tap[t][2] = d->tap_off[t][2]; P.tap[t][3] = 0; }
 
     int tiles = 0;

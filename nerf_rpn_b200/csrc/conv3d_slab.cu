@@ -41,7 +41,7 @@ struct SlabDev {
     int n_phases, ndx, ndy;
     int dx0, dy0;
     int planes, slots, plane_bytes;
-    int cout, relu, ldy, wide_y;
+    int cout, relu, ldy, wide_y, fp16;
     signed char dz[kSlabMaxAxis];
     unsigned char dyrel[kSlabMaxAxis];
     unsigned char widx[kSlabMaxAxis][kSlabMaxAxis][kSlabMaxAxis];     // [phase][dx index][dy index] -> tap index of the packed weights
@@ -57,7 +57,7 @@ __device__ __forceinline__ uint32_t slab_pack_bf16(float a, float b) {
 }
 
 __global__ void __launch_bounds__(kSlabThreads, 1) conv3d_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabDev P) {
-    constexpr uint32_t kIdesc = ptx::make_idesc_bf16(128, 64);
+    const uint32_t kIdesc = P.fp16 ? ptx::make_idesc_f16(128, 64) : ptx::make_idesc_bf16(128, 64);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv3d_slab_kernel(const __gr
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
                             }
-                            pk[gg] = make_uint4(slab_pack_bf16(v[0], v[1]), slab_pack_bf16(v[2], v[3]), slab_pack_bf16(v[4], v[5]), slab_pack_bf16(v[6], v[7]));
+                            pk[gg] = make_uint4(pack_act2(v[0], v[1], P.fp16), pack_act2(v[2], v[3], P.fp16), pack_act2(v[4], v[5], P.fp16), pack_act2(v[6], v[7], P.fp16));
                         }
                         const bool both = chh + 16 <= P.cout;
                         if (both && P.wide_y) ptx::st_global_v8(o + chh, pk[0], pk[1]);
@@ -333,6 +333,7 @@ int conv3d_slab_launch(const nrpn_conv_desc* d, cudaStream_t st) {
     P.n = S.n; P.xo = S.xo; P.yo = S.yo; P.zo = S.zo;
     P.tx = ceil_div(S.xo, kSlabAcc); P.ty = ceil_div(S.yo, kSlabTileY); P.tz = ceil_div(S.zo, kSlabTileZ);
     P.total_tiles = S.n * P.tx * P.ty * P.tz;
+    P.fp16 = d->act_fp16 ? 1 : 0;
     P.cout = d->cout; P.relu = d->relu; P.ldy = S.ldy; P.shift = d->shift; P.y = reinterpret_cast<__nv_bfloat16*>(S.y);
     P.wide_y = (((size_t)S.ldy * 2) % 32 == 0 && reinterpret_cast<uintptr_t>(S.y) % 32 == 0) ? 1 : 0;
 

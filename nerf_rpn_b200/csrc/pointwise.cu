@@ -10,7 +10,7 @@ namespace nrpn {
 // implicit GEMM with 4x4x2 taps of K = 64 (see nerf_rpn_b200/engine.py: pack_stem_weight).
 // One thread writes one 16-byte chunk (8 channels); 8 consecutive lanes cover one 128-byte row.
 __global__ void pack_stem_kernel(const float* __restrict__ grid, int n, int X, int Y, int Z, int X2, int Y2, int Z2,
-                                 __nv_bfloat16* __restrict__ out) {
+                                 __nv_bfloat16* __restrict__ out, int fp16) {
     const size_t total = (size_t)n * X2 * Y2 * (Z2 + 1) * 8;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int s = (int)(t & 7);
@@ -32,16 +32,16 @@ __global__ void pack_stem_kernel(const float* __restrict__ grid, int n, int X, i
                 if (z + 1 < Z) val[4 + c] = p[1];
             }
         }
-        __nv_bfloat162 h[4];
+        uint32_t h[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(val[2 * q], val[2 * q + 1]);
-        *reinterpret_cast<uint4*>(out + (t << 3)) = *reinterpret_cast<uint4*>(h);
+        for (int q = 0; q < 4; ++q) h[q] = pack_act2(val[2 * q], val[2 * q + 1], fp16);
+        *reinterpret_cast<uint4*>(out + (t << 3)) = make_uint4(h[0], h[1], h[2], h[3]);
     }
 }
 
 // F.max_pool3d(k=3, s=2, p=1) on channels-last bf16; one thread per (output voxel, 8 channels).
 __global__ void maxpool_k3s2_kernel(const __nv_bfloat16* __restrict__ in, int n, int X, int Y, int Z, int C, int Xo, int Yo,
-                                    int Zo, __nv_bfloat16* __restrict__ out) {
+                                    int Zo, __nv_bfloat16* __restrict__ out, int fp16) {
     const int cg = C >> 3;
     const size_t total = (size_t)n * Xo * Yo * Zo * cg;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
@@ -60,16 +60,16 @@ __global__ void maxpool_k3s2_kernel(const __nv_bfloat16* __restrict__ in, int n,
                 for (int dz = -1; dz <= 1; ++dz) {
                     const int z = 2 * k + dz; if (z < 0 || z >= Z) continue;
                     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + ((((size_t)b * X + x) * Y + y) * Z + z) * C + g * 8));
-                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+                    const uint32_t* h = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); m[2 * q] = fmaxf(m[2 * q], f.x); m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y); }
+                    for (int q = 0; q < 4; ++q) { const float2 f = unpack_act2(h[q], fp16); m[2 * q] = fmaxf(m[2 * q], f.x); m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y); }
                 }
             }
         }
-        __nv_bfloat162 o[4];
+        uint32_t o[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = __floats2bfloat162_rn(m[2 * q], m[2 * q + 1]);
-        *reinterpret_cast<uint4*>(out + ((((size_t)b * Xo + i) * Yo + j) * Zo + k) * C + g * 8) = *reinterpret_cast<uint4*>(o);
+        for (int q = 0; q < 4; ++q) o[q] = pack_act2(m[2 * q], m[2 * q + 1], fp16);
+        *reinterpret_cast<uint4*>(out + ((((size_t)b * Xo + i) * Yo + j) * Zo + k) * C + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -77,6 +77,7 @@ __global__ void maxpool_k3s2_kernel(const __nv_bfloat16* __restrict__ in, int n,
 // output extent ceil(in/2); the last window is clipped at the border.
 __global__ void maxpool_k2s2_ceil_kernel(const __nv_bfloat16* __restrict__ in, int n, int X, int Y, int Z, int C, int Xo, int Yo,
                                          int Zo, __nv_bfloat16* __restrict__ out) {
+    constexpr int fp16 = 0;                       // the VGG path stores bf16 only
     const int cg = C >> 3;
     const size_t total = (size_t)n * Xo * Yo * Zo * cg;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
@@ -97,16 +98,16 @@ __global__ void maxpool_k2s2_ceil_kernel(const __nv_bfloat16* __restrict__ in, i
                 for (int dz = 0; dz < 2; ++dz) {
                     const int z = 2 * k + dz; if (z >= Z) continue;
                     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + ((((size_t)b * X + x) * Y + y) * Z + z) * C + g * 8));
-                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+                    const uint32_t* h = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); m[2 * q] = fmaxf(m[2 * q], f.x); m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y); }
+                    for (int q = 0; q < 4; ++q) { const float2 f = unpack_act2(h[q], fp16); m[2 * q] = fmaxf(m[2 * q], f.x); m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y); }
                 }
             }
         }
-        __nv_bfloat162 o[4];
+        uint32_t o[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = __floats2bfloat162_rn(m[2 * q], m[2 * q + 1]);
-        *reinterpret_cast<uint4*>(out + ((((size_t)b * Xo + i) * Yo + j) * Zo + k) * C + g * 8) = *reinterpret_cast<uint4*>(o);
+        for (int q = 0; q < 4; ++q) o[q] = pack_act2(m[2 * q], m[2 * q + 1], fp16);
+        *reinterpret_cast<uint4*>(out + ((((size_t)b * Xo + i) * Yo + j) * Zo + k) * C + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -154,22 +155,22 @@ using namespace nrpn;
 extern "C" {
 #pragma GCC visibility push(default)
 
-int nrpn_pack_stem_input(const float* grid, int n, int x, int y, int z, void* packed, nrpn_stream_t stream) {
+int nrpn_pack_stem_input(const float* grid, int n, int x, int y, int z, void* packed, int act_fp16, nrpn_stream_t stream) {
     if (!grid || !packed || n < 1 || x < 1 || y < 1 || z < 1) return NRPN_ERR_INVALID;
     const int X2 = (x + 1) / 2, Y2 = (y + 1) / 2, Z2 = (z + 1) / 2;
     const size_t total = (size_t)n * X2 * Y2 * (Z2 + 1) * 8;
     pack_stem_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, n, x, y, z, X2, Y2, Z2,
-                                                                            reinterpret_cast<__nv_bfloat16*>(packed));
+                                                                            reinterpret_cast<__nv_bfloat16*>(packed), act_fp16 ? 1 : 0);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
 
-int nrpn_maxpool3d_k3s2(const void* in, int n, int x, int y, int z, int c, void* out, nrpn_stream_t stream) {
+int nrpn_maxpool3d_k3s2(const void* in, int n, int x, int y, int z, int c, void* out, int act_fp16, nrpn_stream_t stream) {
     if (!in || !out || n < 1 || x < 1 || y < 1 || z < 1 || c < 8 || c % 8 != 0) return NRPN_ERR_INVALID;
     const int Xo = (x - 1) / 2 + 1, Yo = (y - 1) / 2 + 1, Zo = (z - 1) / 2 + 1;
     const size_t total = (size_t)n * Xo * Yo * Zo * (c / 8);
     maxpool_k3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(in), n, x, y, z, c, Xo, Yo, Zo, reinterpret_cast<__nv_bfloat16*>(out));
+        reinterpret_cast<const __nv_bfloat16*>(in), n, x, y, z, c, Xo, Yo, Zo, reinterpret_cast<__nv_bfloat16*>(out), act_fp16 ? 1 : 0);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }

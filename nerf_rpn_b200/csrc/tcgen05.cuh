@@ -140,6 +140,10 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// same with fp16 A and B (format code 0 in both operand fields)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 }  // namespace ptx
 }  // namespace nrpn

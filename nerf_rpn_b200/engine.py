@@ -23,6 +23,8 @@ from . import ops, packing
 class _Conv:
     """One pre-packed convolution (+ folded BN / bias, optional ReLU)."""
 
+    dtype = torch.bfloat16      # 16-bit storage format of the weights being packed (set by the engine around _pack)
+
     def __init__(self, weight, bias=None, bn=None, stride=1, relu=False, stem=False, cout_pad_to=None, device="cuda"):
         scale = shift = None
         if bn is not None:
@@ -38,11 +40,11 @@ class _Conv:
         if shift is not None:
             shift = shift.cpu()
         if stem == "s1":
-            wp, taps = packing.pack_stem_s1_weight(weight, scale)
+            wp, taps = packing.pack_stem_s1_weight(weight, scale, dtype=_Conv.dtype)
         elif stem:
-            wp, taps = packing.pack_stem_weight(weight, scale)
+            wp, taps = packing.pack_stem_weight(weight, scale, dtype=_Conv.dtype)
         else:
-            wp, taps = packing.pack_conv_weight(weight, scale, cout_pad_to=cout_pad_to)
+            wp, taps = packing.pack_conv_weight(weight, scale, cout_pad_to=cout_pad_to, dtype=_Conv.dtype)
         self.w = wp.to(device)
         self.taps = taps
         self.cin = wp.shape[2]
@@ -65,7 +67,11 @@ class RPNInferenceEngine:
 
     def __init__(self, backbone, head=None, anchor_cells=None, num_anchors: int = 0, rotated: bool = False,
                  pre_nms_top_n: int = 2500, post_nms_top_n: int = 2500, nms_thresh: float = 0.3, score_thresh: float = 0.0,
-                 min_size: float = 1e-3, use_graph: bool = True, fcos: Optional[dict] = None):
+                 min_size: float = 1e-3, use_graph: bool = True, fcos: Optional[dict] = None, precision: str = "bf16"):
+        if precision not in ("bf16", "fp16"):
+            raise ValueError("precision must be 'bf16' (default, BASELINE config 2) or 'fp16' (11-bit significand activations)")
+        self.precision = precision
+        self.act_dtype = torch.float16 if precision == "fp16" else torch.bfloat16
         self.backbone, self.head = backbone, head
         self.fcos = fcos                   # None: anchor head (anchor.py:177-213); dict: FCOS head + post-processing settings
         self.cells = anchor_cells          # list (levels) of (A, 6) float arrays
@@ -92,6 +98,9 @@ class RPNInferenceEngine:
         bb, hd = self.backbone, self.head
         L = {}
         self.kind = {"VGG_FPN": "vgg", "SwinTransformer_FPN": "swin"}.get(type(bb).__name__, "resnet")
+        if self.precision == "fp16" and (self.kind != "resnet" or self.fcos is not None):
+            raise NotImplementedError("precision='fp16' is implemented for the ResNet-FPN + anchor-head path only")
+        _Conv.dtype = self.act_dtype
         if self.kind == "vgg":
             self._pack_vgg(L, device)
         elif self.kind == "swin":
@@ -256,7 +265,7 @@ class _Plan:
     def __init__(self, eng: RPNInferenceEngine, n: int, dims: Tuple[int, int, int], device):
         self.eng, self.n, self.dims, self.device = eng, n, dims, device
         L = eng.layers
-        bf = dict(dtype=torch.bfloat16, device=device)
+        bf = dict(dtype=eng.act_dtype, device=device)
         X, Y, Z = dims
         self._rpn_ws = None
         self._valid = None
@@ -270,7 +279,7 @@ class _Plan:
         self._cur = self.launches
         self.algorithmic_flops = 0.0
 
-        def buf(d, c, dtype=torch.bfloat16):
+        def buf(d, c, dtype=eng.act_dtype):
             return torch.empty((n, *d, c), dtype=dtype, device=device)
 
         def conv(layer: _Conv, xs, ys, in_dims, out_dims, res=None, res_dims=None, out_fp32=False, real=None, name="conv"):

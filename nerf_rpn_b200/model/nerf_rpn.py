@@ -59,12 +59,14 @@ class NeRFRegionProposalNetwork(nn.Module):
     def engine(self):
         from ..engine import RPNInferenceEngine
         r = self.rpn
-        key = (r._pre_nms_top_n["testing"], r._post_nms_top_n["testing"], r.nms_thresh, r.score_thresh, r.rotate)
+        precision = getattr(self, "precision", "bf16")      # "fp16": 11-bit-significand activations
+        key = (r._pre_nms_top_n["testing"], r._post_nms_top_n["testing"], r.nms_thresh, r.score_thresh, r.rotate, precision)
         if self._engine is None or key != self._engine_key:
             ag = r.anchor_generator
             self._engine = RPNInferenceEngine(
                 self.backbone, r.head, ag.cell_anchors_np(), ag.num_anchors_per_location()[0], r.rotate,
-                r._pre_nms_top_n["testing"], r._post_nms_top_n["testing"], r.nms_thresh, r.score_thresh, r.min_size)
+                r._pre_nms_top_n["testing"], r._post_nms_top_n["testing"], r.nms_thresh, r.score_thresh, r.min_size,
+                precision=precision)
             self._engine_key = key
         return self._engine
 

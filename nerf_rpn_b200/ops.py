@@ -164,6 +164,9 @@ def _conv_desc(levels, w, shift, cin, cout, taps, stride, relu, out_fp32) -> Con
         lv.xr, lv.yr, lv.zr = (int(v) for v in L.res_dims)
         lv.ldy, lv.ldr = int(L.ldy), int(L.ldr)
     d.workspace, d.workspace_bytes = 0, 0
+    d.act_fp16 = 1 if levels[0].x.dtype == torch.float16 else 0
+    if w.dtype != levels[0].x.dtype:
+        raise TypeError(f"conv3d: weights are {w.dtype} but activations are {levels[0].x.dtype}")
     return d
 
 
@@ -190,27 +193,40 @@ def conv3d_fprop(levels: Sequence[ConvLevelArgs], w: torch.Tensor, shift: torch.
     check(lib().nrpn_conv3d_fprop(ctypes.byref(d), _stream()), "conv3d_fprop")
 
 
-def pack_stem_input(grid: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """(N,4,X,Y,Z) fp32 -> (N, ceil(X/2), ceil(Y/2), ceil(Z/2)+1, 64) bf16."""
+def _act16(t: torch.Tensor, name: str) -> int:
+    """16-bit activation tensors are bf16 (default) or fp16 (higher-parity mode); returns the C ABI's act_fp16 flag."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"nerf_rpn_b200: {name} must be a CUDA tensor (this package has no CPU path)")
+    if t.dtype not in (torch.bfloat16, torch.float16):
+        raise TypeError(f"nerf_rpn_b200: {name} must be bfloat16 or float16, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"nerf_rpn_b200: {name} must be contiguous")
+    return 1 if t.dtype == torch.float16 else 0
+
+
+def pack_stem_input(grid: torch.Tensor, out: Optional[torch.Tensor] = None, dtype=torch.bfloat16) -> torch.Tensor:
+    """(N,4,X,Y,Z) fp32 -> (N, ceil(X/2), ceil(Y/2), ceil(Z/2)+1, 64) bf16 (or fp16: dtype of `out`)."""
     grid = _req(grid, torch.float32, "grid")
     n, c, x, y, z = grid.shape
     if c != 4:
         raise ValueError("stem packing expects 4 input channels (RGB + density)")
     shape = (n, (x + 1) // 2, (y + 1) // 2, (z + 1) // 2 + 1, 64)
     if out is None:
-        out = torch.empty(shape, dtype=torch.bfloat16, device=grid.device)
-    check(lib().nrpn_pack_stem_input(_ptr(grid), n, x, y, z, _ptr(out), _stream()), "pack_stem_input")
+        out = torch.empty(shape, dtype=dtype, device=grid.device)
+    check(lib().nrpn_pack_stem_input(_ptr(grid), n, x, y, z, _ptr(out), _act16(out, "out"), _stream()), "pack_stem_input")
     return out
 
 
 def maxpool3d_k3s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """(N,X,Y,Z,C) bf16 channels-last -> k3 s2 p1 max pool."""
-    x = _req(x, torch.bfloat16, "x")
+    """(N,X,Y,Z,C) bf16 / fp16 channels-last -> k3 s2 p1 max pool."""
+    f16 = _act16(x, "x")
     n, X, Y, Z, C = x.shape
     shape = (n, (X - 1) // 2 + 1, (Y - 1) // 2 + 1, (Z - 1) // 2 + 1, C)
     if out is None:
-        out = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
-    check(lib().nrpn_maxpool3d_k3s2(_ptr(x), n, X, Y, Z, C, _ptr(out), _stream()), "maxpool3d_k3s2")
+        out = torch.empty(shape, dtype=x.dtype, device=x.device)
+    if out.dtype != x.dtype:
+        raise TypeError("maxpool3d_k3s2: out must have the dtype of x")
+    check(lib().nrpn_maxpool3d_k3s2(_ptr(x), n, X, Y, Z, C, _ptr(out), f16, _stream()), "maxpool3d_k3s2")
     return out
 
 

@@ -27,7 +27,7 @@ def conv_block_n(cout: int) -> int:
     return 64 if cout <= 64 else (128 if cout <= 128 else 256)
 
 
-def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None, cout_pad_to: Optional[int] = None):
+def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None, cout_pad_to: Optional[int] = None, dtype=torch.bfloat16):
     """(Cout, Cin, k, k, k) -> (taps, CoutPad, CinPad) bf16 and the tap offset table for 'same' padding (k odd)."""
     cout, cin, kx, ky, kz = w.shape
     w = w.detach().float()
@@ -47,7 +47,7 @@ def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None, cout
     m = torch.stack(mats, 0)                                   # (taps, Cout, Cin)
     out = torch.zeros((len(taps), cpad, cin_pad), dtype=torch.float32, device=w.device)
     out[:, :cout, :cin] = m
-    return out.to(torch.bfloat16).contiguous(), taps
+    return out.to(dtype).contiguous(), taps
 
 
 def pad_shift(shift: torch.Tensor, cpad: int) -> torch.Tensor:
@@ -56,7 +56,7 @@ def pad_shift(shift: torch.Tensor, cpad: int) -> torch.Tensor:
     return out
 
 
-def pack_stem_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None):
+def pack_stem_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None, dtype=torch.bfloat16):
     """Stem Conv3d(4, 64, kernel 7, stride 2, padding 3) (feature_extractor.py:163) re-expressed on the packed
     space-to-depth input of csrc/pointwise.cu: 4 x 4 x 2 taps, K = 64 per tap.
 
@@ -86,10 +86,10 @@ def pack_stem_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None):
                 taps.append((qx, qy, dz))
                 mats.append(m)
     out = torch.stack(mats, 0)                                  # (32, 64, 64)
-    return out.to(torch.bfloat16).contiguous(), taps
+    return out.to(dtype).contiguous(), taps
 
 
-def pack_stem_s1_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None):
+def pack_stem_s1_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None, dtype=torch.bfloat16):
     """Stride-1 stem Conv3d(4, 64, kernel 7, padding 3) (VGG_FPN on grids < 160, feature_extractor.py:341) on the packed input
     of csrc/pointwise.cu:pack_stem_s1_kernel: 7 (dx) x 4 (y pairs) taps, K = 64 per tap.
 
@@ -114,4 +114,4 @@ def pack_stem_s1_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None):
                     m[:, ch:ch + 4] = w[:, :, dx + 3, ky, zz]
             taps.append((dx, dyp + 1, 0))
             mats.append(m)
-    return torch.stack(mats, 0).to(torch.bfloat16).contiguous(), taps
+    return torch.stack(mats, 0).to(dtype).contiguous(), taps
