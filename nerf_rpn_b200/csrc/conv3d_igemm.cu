@@ -109,10 +109,12 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
         ptx::prefetch_tmap(&maps.w);
     }
     if (warp == 1) { ptx::tmem_alloc(tmem_slot, kTmemCols); ptx::tmem_relinquish(); }
+    ptx::pdl_trigger();                 // the next layer may start its own prologue as our CTAs retire
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();                    // everything above overlapped the previous layer's tail; its outputs are visible from here
 
     const int total_tiles = P.total_m_tiles * P.n_tiles_n * P.splits;     // work items = (output tile, k-split)
     const int kblocks = P.n_taps * P.kc_blocks;
@@ -478,7 +480,7 @@ static int launch_conv(const ConvMaps& maps, const ConvDev& P, int total_tiles, 
     }
     const int slots = num_sms() * MIN_BLOCKS;
     const int grid = total_tiles < slots ? total_tiles : slots;
-    conv3d_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS, TMA_EPI><<<grid, 192, smem, st>>>(maps, P);
+    NRPN_CUDA_TRY(launch_pdl(conv3d_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS, TMA_EPI>, dim3(grid), dim3(192), smem, st, total_tiles <= 2 * slots, maps, P));
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }

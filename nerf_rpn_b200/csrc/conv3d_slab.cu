@@ -81,10 +81,12 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv3d_slab_kernel(const __gr
         ptx::prefetch_tmap(&maps.w);
     }
     if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    ptx::pdl_trigger();
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();                    // prologue overlapped the previous kernel's tail; its outputs are visible from here
 
     if (warp == 0) {
         // ---------------------------------------------------------------- slab producer: one x-plane per TMA
@@ -365,7 +367,7 @@ int conv3d_slab_launch(const nrpn_conv_desc* d, cudaStream_t st) {
         smem_set = smem;
     }
     const int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-    conv3d_slab_kernel<<<grid, kSlabThreads, smem, st>>>(maps, P);
+    NRPN_CUDA_TRY(launch_pdl(conv3d_slab_kernel, dim3(grid), dim3(kSlabThreads), smem, st, P.total_tiles <= 2 * num_sms(), maps, P));
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }

@@ -52,15 +52,24 @@ __global__ void maxpool_k3s2_kernel(const __nv_bfloat16* __restrict__ in, int n,
         float m[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+        // out-of-range taps are clamped onto the border voxel instead of skipped: a maximum ignores duplicates, and the 27
+        // loads become branch-free and independent (all in flight at once)
+        const __nv_bfloat16* base = in + (size_t)b * X * Y * Z * C + g * 8;
+#pragma unroll
         for (int dx = -1; dx <= 1; ++dx) {
-            const int x = 2 * i + dx; if (x < 0 || x >= X) continue;
+            const int x = min(max(2 * i + dx, 0), X - 1);
+#pragma unroll
             for (int dy = -1; dy <= 1; ++dy) {
-                const int y = 2 * j + dy; if (y < 0 || y >= Y) continue;
+                const int y = min(max(2 * j + dy, 0), Y - 1);
+                uint4 raw[3];
 #pragma unroll
                 for (int dz = -1; dz <= 1; ++dz) {
-                    const int z = 2 * k + dz; if (z < 0 || z >= Z) continue;
-                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(in + ((((size_t)b * X + x) * Y + y) * Z + z) * C + g * 8));
-                    const uint32_t* h = reinterpret_cast<const uint32_t*>(&raw);
+                    const int z = min(max(2 * k + dz, 0), Z - 1);
+                    raw[dz + 1] = __ldg(reinterpret_cast<const uint4*>(base + (((size_t)x * Y + y) * Z + z) * C));
+                }
+#pragma unroll
+                for (int dz = 0; dz < 3; ++dz) {
+                    const uint32_t* h = reinterpret_cast<const uint32_t*>(&raw[dz]);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { const float2 f = unpack_act2(h[q], fp16); m[2 * q] = fmaxf(m[2 * q], f.x); m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y); }
                 }

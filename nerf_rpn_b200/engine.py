@@ -13,6 +13,7 @@ only the top-k candidates are decoded, and NMS never leaves the device.
 PyTorch's role here: owning device buffers, the stream and the CUDA graph object.  Training-mode forward
 (BatchNorm batch statistics, losses) is not implemented in this round and raises.
 """
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -342,7 +343,9 @@ class _Plan:
                           scores=torch.zeros((n, eng.post_n), dtype=torch.float32, device=device),
                           levels=torch.zeros((n, eng.post_n), dtype=torch.float32, device=device),
                           count=torch.zeros((n,), dtype=torch.int32, device=device)) for _ in range(2)]
-        self.side = torch.cuda.Stream(device=device)
+        # post-processing = ~45 tiny kernels per scene: high priority so that they slip into the SMs as conv CTAs retire instead of
+        # queueing behind whole layers (the main stream depends on them two steps later through the double-buffered predictions)
+        self.side = torch.cuda.Stream(device=device, priority=-1 if os.environ.get("NRPN_SIDE_PRIORITY", "1") != "0" else 0)
         self._ev_pred = [torch.cuda.Event() for _ in range(2)]
         self._ev_done = [torch.cuda.Event() for _ in range(2)]
         self._parity = 0
@@ -576,7 +579,9 @@ class _Plan:
         self._out = [dict(boxes=torch.zeros((n, cap, 1 + dim), dtype=torch.float32, device=device),
                           scores=torch.zeros((n, cap), dtype=torch.float32, device=device),
                           count=torch.zeros((n,), dtype=torch.int32, device=device)) for _ in range(2)]
-        self.side = torch.cuda.Stream(device=device)
+        # post-processing = ~45 tiny kernels per scene: high priority so that they slip into the SMs as conv CTAs retire instead of
+        # queueing behind whole layers (the main stream depends on them two steps later through the double-buffered predictions)
+        self.side = torch.cuda.Stream(device=device, priority=-1 if os.environ.get("NRPN_SIDE_PRIORITY", "1") != "0" else 0)
         self._ev_pred = [torch.cuda.Event() for _ in range(2)]
         self._ev_done = [torch.cuda.Event() for _ in range(2)]
         self._parity = 0
