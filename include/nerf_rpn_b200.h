@@ -255,6 +255,9 @@ int nrpn_fcos_proposals(const nrpn_fcos_desc *desc /*host*/, float *boxes, float
  * the reference's zero-initialised vector is left to the caller).  Ties: lowest ground-truth index, then lowest proposal
  * index, as torch.max on CPU.  n_proposals <= 32 768, n_gt <= 4 096. */
 int nrpn_recall_match(const float *overlaps, int n_proposals, int n_gt, float *gt_overlaps, nrpn_stream_t stream);
+/* Row-wise maximum and first arg-max of a (rows, cols) fp32 matrix (torch.max(dim=1) tie rule): the per-detection step of
+ * evaluate_box_proposals_ap (eval.py:355-358) for a whole scene's IoU matrix. */
+int nrpn_rowmax_f32(const float *m, int rows, int cols, float *maxv, int32_t *argmax, nrpn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ training targets
  * RegionProposalNetwork.assign_targets_to_anchors (rpn.py:240-290): IoU of every anchor with every (rectified, obb2hbb_3d)

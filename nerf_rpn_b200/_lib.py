@@ -104,6 +104,7 @@ _SIGNATURES = {
     "nrpn_assign_targets_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "nrpn_assign_targets": (ctypes.c_int, [c_f32p, ctypes.c_int, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_float,
                                            ctypes.c_float, ctypes.c_int, c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, c_stream]),
+    "nrpn_rowmax_f32": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, c_f32p, ctypes.c_void_p, c_stream]),
     "nrpn_recall_match": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, c_f32p, c_stream]),
     "nrpn_rpn_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(RpnDesc)]),
     "nrpn_rpn_proposals": (ctypes.c_int, [ctypes.POINTER(RpnDesc), c_f32p, c_f32p, c_f32p, ctypes.c_void_p,

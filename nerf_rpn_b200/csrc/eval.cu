@@ -58,6 +58,24 @@ __global__ void __launch_bounds__(kMatchThreads) recall_match_kernel(const float
     }
 }
 
+// Per-row maximum and its first index (torch.max(dim=1) on CPU), one warp per row: the detection -> best ground truth step of
+// the VOC-style AP (eval.py:355-358), for all detections of a scene at once instead of one box_iou_3d call per detection.
+__global__ void __launch_bounds__(256) rowmax_kernel(const float* __restrict__ m, int rows, int cols, float* __restrict__ maxv,
+                                                     int* __restrict__ argmax) {
+    const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    unsigned long long best = 0ull;
+    for (int c = lane; c < cols; c += 32)
+        best = max(best, ((unsigned long long)float_to_ordered(m[(size_t)row * cols + c]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)c));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); best = other > best ? other : best; }
+    if (lane == 0) {
+        const int c = (int)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull));
+        argmax[row] = c;
+        maxv[row] = m[(size_t)row * cols + c];
+    }
+}
+
 }  // namespace nrpn
 
 using namespace nrpn;
@@ -71,6 +89,15 @@ int nrpn_recall_match(const float* overlaps, int n_proposals, int n_gt, float* g
     if (!overlaps || !gt_overlaps) return NRPN_ERR_INVALID;
     if (n_gt > kMatchMaxGt || n_proposals > 32768) return NRPN_ERR_UNSUPPORTED;
     recall_match_kernel<<<1, kMatchThreads, 0, (cudaStream_t)stream>>>(overlaps, n_proposals, n_gt, gt_overlaps);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+int nrpn_rowmax_f32(const float* m, int rows, int cols, float* maxv, int32_t* argmax, nrpn_stream_t stream) {
+    if (rows < 0 || cols < 1) return NRPN_ERR_INVALID;
+    if (rows == 0) return NRPN_OK;
+    if (!m || !maxv || !argmax) return NRPN_ERR_INVALID;
+    rowmax_kernel<<<(unsigned)ceil_div((long)rows * 32, 256L), 256, 0, (cudaStream_t)stream>>>(m, rows, cols, maxv, argmax);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }

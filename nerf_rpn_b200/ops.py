@@ -66,6 +66,16 @@ def assign_targets(anchors: torch.Tensor, gt: torch.Tensor, valid: Optional[torc
     return labels, matched
 
 
+def rowmax(m: torch.Tensor):
+    """(rows, cols) fp32 -> (max, first argmax) per row, on the device."""
+    m = _req(m, torch.float32, "m")
+    rows, cols = m.shape
+    mv = torch.empty((rows,), dtype=torch.float32, device=m.device)
+    am = torch.empty((rows,), dtype=torch.int32, device=m.device)
+    check(lib().nrpn_rowmax_f32(_ptr(m), rows, cols, _ptr(mv), _ptr(am), _stream()), "rowmax")
+    return mv, am
+
+
 def recall_match(overlaps: torch.Tensor) -> torch.Tensor:
     """(P, G) fp32 IoU matrix -> the min(P, G) IoUs recorded by the greedy loop of eval.py:33-52 (device resident)."""
     overlaps = _req(overlaps, torch.float32, "overlaps")

@@ -399,6 +399,15 @@ def gen_recall(n_scenes=12):
         out[f"recalls_{limit}"] = r["recalls"].numpy()
         out[f"gt_overlaps_{limit}"] = r["gt_overlaps"].numpy()
         print("limit", limit, "recall@0.25/0.5", r["recalls"].tolist(), "num_pos", r["num_pos"])
+    # VOC-style AP (eval.py:319-395) on the same proposals; the proposals themselves are stored so that the device metric can be
+    # checked on identical inputs
+    for thr_iou in (0.25, 0.5):
+        for top_k in (None, 300):
+            r = ref_eval.evaluate_box_proposals_ap(props, scores, gts, iou_thresh=thr_iou, top_k=top_k)
+            out[f"ap_{int(thr_iou * 100)}_{top_k or 0}"] = np.float64(float(r["ap"]))
+            print("AP", thr_iou, top_k, float(r["ap"]))
+    out["ref_props"] = np.concatenate([p.numpy() for p in props]).astype(np.float32)
+    out["ref_scores"] = np.concatenate([s_.numpy() for s_ in scores]).astype(np.float32)
     # the matching loop alone, on random matrices (ties included), through the reference function with a patched IoU
     gen = torch.Generator().manual_seed(5)
     mats, outs = [], []
