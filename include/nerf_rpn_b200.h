@@ -141,7 +141,9 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc *desc /*host*/, nrpn_stream_t stream)
  * of voxel (i,j,k-1) followed by the block of voxel (i,j,k), k in [0, ceil(Z/2)] (so the packed Z extent is
  * ceil(Z/2)+1); turns the 7^3 stride-2 stem conv (feature_extractor.py:163) into a 4x4x2-tap stride-1
  * implicit GEMM with K = 64 per tap. */
-int nrpn_pack_stem_input(const float *grid, int n, int x, int y, int z, void *packed, int act_fp16, nrpn_stream_t stream);
+int nrpn_pack_stem_input(const float *grid, int n, int x, int y, int z, void *packed, int act_fp16,
+                         int channels_last /* 0: grid is (N,4,X,Y,Z); 1: (N,X,Y,Z,4) as stored on disk, datasets.py:49-57 */,
+                         nrpn_stream_t stream);
 
 /* F.max_pool3d(kernel 3, stride 2, padding 1) on (N,X,Y,Z,C) bf16, C % 8 == 0 (feature_extractor.py:219). */
 int nrpn_maxpool3d_k3s2(const void *in, int n, int x, int y, int z, int c, void *out, int act_fp16, nrpn_stream_t stream);

@@ -80,7 +80,7 @@ _SIGNATURES = {
     "nrpn_conv3d_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvDesc)]),
     "nrpn_conv3d_fprop": (ctypes.c_int, [ctypes.POINTER(ConvDesc), c_stream]),
     "nrpn_pack_stem_input": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                            ctypes.c_void_p, ctypes.c_int, c_stream]),
+                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_stream]),
     "nrpn_maxpool3d_k3s2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_int, c_stream]),
     "nrpn_maxpool3d_k2s2_ceil": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

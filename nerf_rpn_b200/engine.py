@@ -228,15 +228,18 @@ class RPNInferenceEngine:
         L["fpn"] = [_Conv(m.weight, m.bias, device=device) for m in bb.fpn_neck.fpn_convs]
 
     # ---------------------------------------------------------------- plan
-    def _get_plan(self, n, dims, device):
+    def _get_plan(self, n, dims, device, channels_last: bool = False):
         ver = self._param_version()
         if self.layers is None or ver != self._packed_version:
             self._pack(device)
             self._packed_version = ver
-        key = (n, tuple(dims), str(device))
+        # a grid handed over as the dataset's (4,W,L,H) VIEW of the on-disk (W,L,H,4) array is consumed in place by the
+        # ResNet stem packing (128-bit loads); the other backbones take a copy into NCDHW first
+        cl = bool(channels_last) and self.kind == "resnet" and max(dims) >= 0
+        key = (n, tuple(dims), str(device), cl)
         p = self._plans.get(key)
         if p is None:
-            p = _Plan(self, n, tuple(dims), device)
+            p = _Plan(self, n, tuple(dims), device, cl)
             self._plans[key] = p
         return p
 
@@ -252,7 +255,7 @@ class RPNInferenceEngine:
         if not grids.is_cuda or grids.dtype != torch.float32:
             raise RuntimeError("nerf_rpn_b200: input grids must be fp32 CUDA tensors (no CPU path)")
         n, c, X, Y, Z = grids.shape
-        plan = self._get_plan(n, (X, Y, Z), grids.device)
+        plan = self._get_plan(n, (X, Y, Z), grids.device, channels_last=ops.is_channels_last_grid(grids))
         plan.run(grids, valid_dims)
         return plan
 
@@ -263,8 +266,9 @@ class RPNInferenceEngine:
 
 
 class _Plan:
-    def __init__(self, eng: RPNInferenceEngine, n: int, dims: Tuple[int, int, int], device):
+    def __init__(self, eng: RPNInferenceEngine, n: int, dims: Tuple[int, int, int], device, channels_last: bool = False):
         self.eng, self.n, self.dims, self.device = eng, n, dims, device
+        self.channels_last = channels_last
         L = eng.layers
         bf = dict(dtype=eng.act_dtype, device=device)
         X, Y, Z = dims
@@ -304,7 +308,10 @@ class _Plan:
             self.names[id(self._cur[-1])] = (f"{name} {layer.cin}->{layer.cout} taps={len(layer.taps)} s={layer.stride} "
                                              f"out={'+'.join('x'.join(map(str, d)) for d in out_dims)}", fl)
 
-        self.input = torch.empty((n, 4, X, Y, Z), dtype=torch.float32, device=device)
+        if channels_last:            # memory (n,X,Y,Z,4), logical (n,4,X,Y,Z): same strides as the dataset's view, copies stay memcpys
+            self.input = torch.empty((n, X, Y, Z, 4), dtype=torch.float32, device=device).permute(0, 4, 1, 2, 3)
+        else:
+            self.input = torch.empty((n, 4, X, Y, Z), dtype=torch.float32, device=device)
         self._buf, self._conv = buf, conv
         feats = {"vgg": self._build_vgg, "swin": self._build_swin}.get(eng.kind, self._build_resnet)(L, n, dims, bf)
         self.features = [f for f, _ in feats]

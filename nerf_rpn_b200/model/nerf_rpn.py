@@ -82,9 +82,15 @@ class NeRFRegionProposalNetwork(nn.Module):
             torch._assert(len(val) == 3, f"expecting the last three dimensions of the Tensor to be W, H and D instead got {mesh.shape[-3:]}")
             original_mesh_sizes.append((val[0], val[1], val[2]))
         meshes, targets = self.transform(meshes, targets)
-        mesh_tensors = meshes[0].unsqueeze(0) if len(meshes) == 1 else torch.stack(meshes, dim=0)
-        if not mesh_tensors.is_contiguous():
-            mesh_tensors = mesh_tensors.contiguous()
+        # The reference's dataset yields each mesh as a (4,W,L,H) VIEW of the on-disk (W,L,H,4) array (datasets.py:55-56). Such
+        # meshes are kept in that memory order (the stem packing reads it with one 128-bit load per voxel); anything else is
+        # made contiguous NCDHW like the reference's torch.stack does.
+        if all(m.dim() == 4 and not m.is_contiguous() and m.permute(1, 2, 3, 0).is_contiguous() for m in meshes):
+            mesh_tensors = torch.stack([m.permute(1, 2, 3, 0) for m in meshes], dim=0).permute(0, 4, 1, 2, 3)
+        else:
+            mesh_tensors = meshes[0].unsqueeze(0) if len(meshes) == 1 else torch.stack(meshes, dim=0)
+            if not mesh_tensors.is_contiguous():
+                mesh_tensors = mesh_tensors.contiguous()
         valid = original_mesh_sizes if len(meshes) > 1 else None     # padding masks only when batch > 1 (rpn.py:501)
         plan = self.engine().forward_device(mesh_tensors, valid)
         torch.cuda.current_stream().wait_event(plan.done)            # post-processing runs on the engine's side stream

@@ -214,16 +214,26 @@ def _act16(t: torch.Tensor, name: str) -> int:
     return 1 if t.dtype == torch.float16 else 0
 
 
+def is_channels_last_grid(grid: torch.Tensor) -> bool:
+    """True for an (N,4,X,Y,Z) tensor whose memory is (N,X,Y,Z,4): what datasets.py:55-56 produces (np.transpose view)."""
+    return grid.dim() == 5 and not grid.is_contiguous() and grid.permute(0, 2, 3, 4, 1).is_contiguous()
+
+
 def pack_stem_input(grid: torch.Tensor, out: Optional[torch.Tensor] = None, dtype=torch.bfloat16) -> torch.Tensor:
-    """(N,4,X,Y,Z) fp32 -> (N, ceil(X/2), ceil(Y/2), ceil(Z/2)+1, 64) bf16 (or fp16: dtype of `out`)."""
-    grid = _req(grid, torch.float32, "grid")
+    """(N,4,X,Y,Z) fp32 -> (N, ceil(X/2), ceil(Y/2), ceil(Z/2)+1, 64) bf16 (or fp16: dtype of `out`).
+    `grid` may be contiguous NCDHW or the channels-last view the reference's dataset yields (memory (N,X,Y,Z,4))."""
+    if not isinstance(grid, torch.Tensor) or not grid.is_cuda or grid.dtype != torch.float32 or grid.dim() != 5:
+        raise RuntimeError("nerf_rpn_b200: grid must be a 5-D fp32 CUDA tensor")
+    cl = is_channels_last_grid(grid)
+    if not cl and not grid.is_contiguous():
+        raise ValueError("nerf_rpn_b200: grid must be contiguous (N,4,X,Y,Z) or a permuted view of a contiguous (N,X,Y,Z,4) array")
     n, c, x, y, z = grid.shape
     if c != 4:
         raise ValueError("stem packing expects 4 input channels (RGB + density)")
     shape = (n, (x + 1) // 2, (y + 1) // 2, (z + 1) // 2 + 1, 64)
     if out is None:
         out = torch.empty(shape, dtype=dtype, device=grid.device)
-    check(lib().nrpn_pack_stem_input(_ptr(grid), n, x, y, z, _ptr(out), _act16(out, "out"), _stream()), "pack_stem_input")
+    check(lib().nrpn_pack_stem_input(_ptr(grid), n, x, y, z, _ptr(out), _act16(out, "out"), int(cl), _stream()), "pack_stem_input")
     return out
 
 

@@ -21,8 +21,9 @@ class ScenePipeline:
         self.dims = tuple(dims)
         self.eng = model.engine()
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        # two device staging buffers; the engine's graph reads its own static input, filled by a D2D copy
-        self.stage = [torch.empty((self.batch, 4, *self.dims), dtype=torch.float32, device=self.device) for _ in range(2)]
+        # two device staging buffers; the engine's graph reads its own static input, filled by a D2D copy.  Allocated on the
+        # first run() in the memory order of the host grids (contiguous (4,W,L,H), or the dataset's channels-last view).
+        self.stage = None
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
         k = self.eng.post_n
@@ -36,6 +37,15 @@ class ScenePipeline:
         self.h2d_bytes_per_scene = 4 * self.dims[0] * self.dims[1] * self.dims[2] * 4
         self.d2h_bytes_per_scene = (k * bd + 2 * k + 1) * 4
 
+    def _alloc_stage(self, sample: torch.Tensor):
+        cl = sample.dim() == 4 and not sample.is_contiguous() and sample.permute(1, 2, 3, 0).is_contiguous()
+        if cl:
+            self.stage = [torch.empty((self.batch, *self.dims, 4), dtype=torch.float32, device=self.device).permute(0, 4, 1, 2, 3)
+                          for _ in range(2)]
+        else:
+            self.stage = [torch.empty((self.batch, 4, *self.dims), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.stage_channels_last = cl
+
     def _prefetch(self, slot: int, host_grids):
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.consumed[slot])
@@ -44,7 +54,8 @@ class ScenePipeline:
             self.ready[slot].record(self.copy_stream)
 
     def run(self, host_grids: Iterable[torch.Tensor], collect: bool = True):
-        """host_grids: iterable of pinned fp32 (4,W,L,H) tensors. Returns a list of (boxes, scores, levels) CPU tensors
+        """host_grids: iterable of pinned fp32 (4,W,L,H) tensors -- contiguous, or the dataset's views of (W,L,H,4) arrays (then the
+        H2D copy is a plain memcpy of the on-disk layout and the stem packing reads it channels-last). Returns a list of (boxes, scores, levels) CPU tensors
         (or only the number of scenes processed when collect=False)."""
         cur = torch.cuda.current_stream(self.device)
         grids = list(host_grids)
@@ -54,6 +65,9 @@ class ScenePipeline:
         nxt = next(it, None)
         if nxt is None:
             return []
+        cl = grids[0].dim() == 4 and not grids[0].is_contiguous() and grids[0].permute(1, 2, 3, 0).is_contiguous()
+        if self.stage is None or cl != self.stage_channels_last:
+            self._alloc_stage(grids[0])
         for e in self.consumed:
             e.record(cur)
         self._prefetch(0, nxt)

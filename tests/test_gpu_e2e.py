@@ -218,3 +218,31 @@ def test_fp16_activation_mode_reaches_the_north_star_tolerance(golden_dir, name,
     hit = (obox.iou_matrix(refp[top], ours).max(axis=1) >= 0.7).mean()
     print(f"{name} fp16 mode: {ours.shape[0]} proposals (reference {refp.shape[0]}); top-100 matched at IoU>=0.7: {hit:.2f}")
     assert hit >= 0.9
+
+
+def test_dataset_channels_last_view_is_consumed_in_place(golden_dir):
+    """datasets.py:55-56 hands the model a (4,W,L,H) VIEW of the (W,L,H,4) array. The stem packing must read that memory order
+    directly (bit-identical packed rows), and model / ScenePipeline results must not depend on the memory order."""
+    from nerf_rpn_b200 import ops
+    from nerf_rpn_b200.runtime import ScenePipeline
+    g = np.load(os.path.join(golden_dir, "rpn_small_aabb.npz"))
+    model, ag = build(False, g)
+    wlhc = torch.from_numpy(g["grid"]).cuda()                              # (W,L,H,4) as on disk
+    view = wlhc.permute(3, 0, 1, 2)                                        # what the dataset yields
+    dense = view.contiguous()
+    assert ops.is_channels_last_grid(view[None]) and not ops.is_channels_last_grid(dense[None])
+    assert torch.equal(ops.pack_stem_input(view[None]), ops.pack_stem_input(dense[None]))
+    odd = torch.rand((2, 21, 19, 27, 4), device="cuda").permute(0, 4, 1, 2, 3)          # odd extents, batch 2
+    assert torch.equal(ops.pack_stem_input(odd), ops.pack_stem_input(odd.contiguous()))
+    with torch.no_grad():
+        (_, p_view, _), _, s_view = model([view])
+        (_, p_dense, _), _, s_dense = model([dense])
+    assert torch.equal(p_view[0], p_dense[0]) and torch.equal(s_view[0], s_dense[0])
+    eng = model.engine()
+    assert any(k[3] for k in eng._plans) and any(not k[3] for k in eng._plans)          # both plan kinds were built
+    pipe = ScenePipeline(model, tuple(dense.shape[1:]), batch=1)
+    host_view = wlhc.cpu().pin_memory().permute(3, 0, 1, 2)
+    out = pipe.run([host_view, host_view])
+    assert pipe.stage_channels_last
+    for boxes, scores, levels in out:
+        assert torch.equal(boxes, p_dense[0].cpu()) and torch.equal(scores, s_dense[0].cpu())
