@@ -295,7 +295,7 @@ def run_b200(args):
         value = world * K * B / (ms * 1e-3)
         cores = os.cpu_count() or 1
         torch.cuda.empty_cache()
-        if args.skip_cpu_baseline:
+        if args.skip_cpu_baseline or world > 1:            # the CPU baseline is timed on rank 0 of the single-GPU run only
             cpu_t = float("nan")
         else:
             cpu_port_run(16, cores)                        # warm the CPU libraries (oneDNN JIT, thread pool) on a thin slab
@@ -314,8 +314,9 @@ def run_b200(args):
                        "api": "nerf_rpn_b200.runtime.ScenePipeline.run (pinned host fp32 grids -> host proposals)"},
                "gpu_launches": launches_per_step * K,
                "roofline": roofline,
-               "cpu_baseline": {"value": 1.0 / cpu_t, "unit": "scenes/s", "cores": cores, "kind": "port",
-                                "sample": "1 scene 160x256x256 (oracle/net.py fp32 CPU port of the reference; one timed run after a thin warm-up slab)"}}
+               "cpu_baseline": {"value": (1.0 / cpu_t) if cpu_t == cpu_t else None, "unit": "scenes/s", "cores": cores, "kind": "port",
+                                "sample": "1 scene 160x256x256 (oracle/net.py fp32 CPU port of the reference; one timed run after a thin warm-up slab)"
+                                if cpu_t == cpu_t else "not timed in this run (N > 1 or --skip-cpu-baseline)"}}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
