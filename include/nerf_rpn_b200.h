@@ -149,12 +149,12 @@ int nrpn_pack_stem_input(const float *grid, int n, int x, int y, int z, void *pa
 int nrpn_maxpool3d_k3s2(const void *in, int n, int x, int y, int z, int c, void *out, int act_fp16, nrpn_stream_t stream);
 
 /* nn.MaxPool3d(kernel 2, stride 2, ceil_mode=True) (VGG stages, feature_extractor.py:347): output extent ceil(in/2). */
-int nrpn_maxpool3d_k2s2_ceil(const void *in, int n, int x, int y, int z, int c, void *out, nrpn_stream_t stream);
+int nrpn_maxpool3d_k2s2_ceil(const void *in, int n, int x, int y, int z, int c, void *out, int act_fp16, nrpn_stream_t stream);
 
 /* Stride-1 stem packing for VGG_FPN on grids smaller than 160 (Conv3d(4,64,kernel 7,stride 1,padding 3),
  * feature_extractor.py:341): fp32 NCDHW (4,X,Y,Z) -> bf16 (X, Y+1, Z, 64); row (x,yp,z) = the 7 z-neighbours of the two
  * input rows y = yp-1, yp (56 channels + 8 zero), so that the conv is a 7x4-tap implicit GEMM with K = 64 per tap. */
-int nrpn_pack_stem_input_s1(const float *grid, int n, int x, int y, int z, void *packed, nrpn_stream_t stream);
+int nrpn_pack_stem_input_s1(const float *grid, int n, int x, int y, int z, void *packed, int act_fp16, nrpn_stream_t stream);
 
 /* GroupNorm(32 groups, 256 channels) + optional ReLU, in place, on up to NRPN_CONV_MAX_LEVELS channels-last bf16 tensors
  * (N, voxels, 256) that share gamma/beta (FCOS towers: Conv3d -> GroupNorm -> ReLU, fcos/fcos.py:43-69).  Statistics are
@@ -165,7 +165,7 @@ typedef struct {
 } nrpn_gn_level;
 size_t nrpn_groupnorm_workspace_bytes(int n_levels, int n);
 int nrpn_groupnorm_relu(const nrpn_gn_level *levels /*host*/, int n_levels, int n, int c, int groups, const float *gamma,
-                        const float *beta, float eps, int relu, void *workspace, size_t workspace_bytes,
+                        const float *beta, float eps, int relu, int act_fp16, void *workspace, size_t workspace_bytes,
                         nrpn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -206,17 +206,17 @@ int nrpn_rpn_proposals(const nrpn_rpn_desc *desc /*host*/, float *boxes, float *
  * ---------------------------------------------------------------------------------------------- */
 /* fp32 NCDHW grid (N,4,X,Y,Z) -> bf16 (N, X/4, Y/4, Z/4, 256) patch rows, channel ((c*4+px)*4+py)*4+pz: the patch embedding
  * Conv3d(4, C, kernel 4, stride 4) becomes a 256 -> C GEMM. */
-int nrpn_patch_embed_pack(const float *grid, int n, int x, int y, int z, void *out, nrpn_stream_t stream);
+int nrpn_patch_embed_pack(const float *grid, int n, int x, int y, int z, void *out, int act_fp16, nrpn_stream_t stream);
 /* per-token LayerNorm over the first c channels of each row; rows are ld_in / ld_out elements apart. */
 int nrpn_layernorm(const void *in, int ld_in, void *out, int ld_out, long tokens, int c, const float *gamma, const float *beta,
-                   float eps, nrpn_stream_t stream);
+                   float eps, int act_fp16, nrpn_stream_t stream);
 /* PatchMerging front half: 2x2x2 gather (zero past odd extents) + LayerNorm(8c) -> (N, ceil(h/2), ceil(w/2), ceil(d/2), 8c). */
 int nrpn_patch_merge_ln(const void *in, int ld_in, int n, int h, int w, int d, int c, void *out, const float *gamma,
-                        const float *beta, float eps, nrpn_stream_t stream);
+                        const float *beta, float eps, int act_fp16, nrpn_stream_t stream);
 /* 4x4x4 (shifted) window multi-head attention, head_dim 32: qkv (N,h,w,d, 3c) -> out (N,h,w,d, ld_out). shift in {0, 2};
  * table = (343, heads) relative position bias table; qkv_bias (3c) stands in for zero-padded tokens. */
 int nrpn_window_attention(const void *qkv, int ld_qkv, void *out, int ld_out, const float *qkv_bias, const float *table, int n,
-                          int h, int w, int d, int c, int heads, int shift, nrpn_stream_t stream);
+                          int h, int w, int d, int c, int heads, int shift, int act_fp16, nrpn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * FCOS (anchor-free) post-processing for ONE scene (fcos/fcos.py:116-126,221-250; fcos/inference.py:48-195;

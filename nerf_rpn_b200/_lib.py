@@ -84,19 +84,19 @@ _SIGNATURES = {
     "nrpn_maxpool3d_k3s2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_int, c_stream]),
     "nrpn_maxpool3d_k2s2_ceil": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                                ctypes.c_int, ctypes.c_void_p, c_stream]),
+                                                ctypes.c_int, ctypes.c_void_p, ctypes.c_int, c_stream]),
     "nrpn_pack_stem_input_s1": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                               ctypes.c_void_p, c_stream]),
+                                               ctypes.c_void_p, ctypes.c_int, c_stream]),
     "nrpn_groupnorm_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "nrpn_groupnorm_relu": (ctypes.c_int, [ctypes.POINTER(GnLevel), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                           c_f32p, c_f32p, ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, c_stream]),
-    "nrpn_patch_embed_pack": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, c_stream]),
+                                           c_f32p, c_f32p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, c_stream]),
+    "nrpn_patch_embed_pack": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, c_stream]),
     "nrpn_layernorm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_int,
-                                      c_f32p, c_f32p, ctypes.c_float, c_stream]),
+                                      c_f32p, c_f32p, ctypes.c_float, ctypes.c_int, c_stream]),
     "nrpn_patch_merge_ln": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                           ctypes.c_int, ctypes.c_void_p, c_f32p, c_f32p, ctypes.c_float, c_stream]),
+                                           ctypes.c_int, ctypes.c_void_p, c_f32p, c_f32p, ctypes.c_float, ctypes.c_int, c_stream]),
     "nrpn_window_attention": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, c_f32p, c_f32p, ctypes.c_int,
-                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_stream]),
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_stream]),
     "nrpn_fcos_max_proposals": (ctypes.c_int, [ctypes.POINTER(FcosDesc)]),
     "nrpn_fcos_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(FcosDesc)]),
     "nrpn_fcos_proposals": (ctypes.c_int, [ctypes.POINTER(FcosDesc), c_f32p, c_f32p, ctypes.c_void_p, ctypes.c_void_p,

@@ -49,6 +49,13 @@ __device__ __forceinline__ uint32_t pack_act2(float a, float b, int fp16) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ float load_act(const __nv_bfloat16* p, int fp16) {
+    return fp16 ? __half2float(*reinterpret_cast<const __half*>(p)) : __bfloat162float(*p);
+}
+__device__ __forceinline__ void store_act(__nv_bfloat16* p, float v, int fp16) {
+    if (fp16) *reinterpret_cast<__half*>(p) = __float2half_rn(v);
+    else *p = __float2bfloat16(v);
+}
 __device__ __forceinline__ float2 unpack_act2(uint32_t u, int fp16) {
     if (fp16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
     return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));

@@ -12,7 +12,7 @@ constexpr int kGnMaxBlocks = 512;    // CTAs per (level, sample): ceil(voxels / 
 constexpr int kGnGroups = 32;
 
 struct GnDev {
-    int n_levels, n, relu;
+    int n_levels, n, relu, fp16;
     float eps;
     __nv_bfloat16* x[NRPN_CONV_MAX_LEVELS];
     int voxels[NRPN_CONV_MAX_LEVELS];
@@ -45,16 +45,16 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnDev P) {
         for (int u = 0; u < 4; ++u) raw[u] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)(v + u * step) * 256 + g * 8));
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+            const uint32_t* h = reinterpret_cast<const uint32_t*>(&raw[u]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); s += f.x + f.y; q += f.x * f.x + f.y * f.y; }
+            for (int i = 0; i < 4; ++i) { const float2 f = unpack_act2(h[i], P.fp16); s += f.x + f.y; q += f.x * f.x + f.y * f.y; }
         }
     }
     for (; v < V; v += step) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + (size_t)v * 256 + g * 8));
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const uint32_t* h = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); s += f.x + f.y; q += f.x * f.x + f.y * f.y; }
+        for (int i = 0; i < 4; ++i) { const float2 f = unpack_act2(h[i], P.fp16); s += f.x + f.y; q += f.x * f.x + f.y * f.y; }
     }
     __shared__ double ss[8][32], sq[8][32];
     ss[r][g] = (double)s; sq[r][g] = (double)q;
@@ -101,13 +101,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnDev P) {
     for (int i = 0; i < 8; ++i) { ga[i] = __ldg(P.gamma + g * 8 + i) * rstd; be[i] = __ldg(P.beta + g * 8 + i) - mean * ga[i]; }
     const int step = nb * 8;
     auto apply = [&](uint4 raw) {
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+        uint32_t* h = reinterpret_cast<uint32_t*>(&raw);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float2 f = __bfloat1622float2(h[i]);
+            float2 f = unpack_act2(h[i], P.fp16);
             f.x = f.x * ga[2 * i] + be[2 * i]; f.y = f.y * ga[2 * i + 1] + be[2 * i + 1];
             if (P.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
-            h[i] = __floats2bfloat162_rn(f.x, f.y);
+            h[i] = pack_act2(f.x, f.y, P.fp16);
         }
         return raw;
     };
@@ -138,12 +138,12 @@ size_t nrpn_groupnorm_workspace_bytes(int n_levels, int n) {
 }
 
 int nrpn_groupnorm_relu(const nrpn_gn_level* levels, int n_levels, int n, int c, int groups, const float* gamma,
-                        const float* beta, float eps, int relu, void* workspace, size_t workspace_bytes, nrpn_stream_t stream) {
+                        const float* beta, float eps, int relu, int act_fp16, void* workspace, size_t workspace_bytes, nrpn_stream_t stream) {
     if (!levels || !gamma || !beta || !workspace || n_levels < 1 || n_levels > NRPN_CONV_MAX_LEVELS || n < 1) return NRPN_ERR_INVALID;
     if (c != 256 || groups != 32) return NRPN_ERR_UNSUPPORTED;       // 8 channels per group = one 16-byte chunk per thread
     if (workspace_bytes < nrpn_groupnorm_workspace_bytes(n_levels, n)) return NRPN_ERR_WORKSPACE;
     GnDev P;
-    P.n_levels = n_levels; P.n = n; P.relu = relu; P.eps = eps; P.gamma = gamma; P.beta = beta;
+    P.n_levels = n_levels; P.n = n; P.relu = relu; P.fp16 = act_fp16 ? 1 : 0; P.eps = eps; P.gamma = gamma; P.beta = beta;
     P.partial = reinterpret_cast<double*>(workspace);
     int grid = 0;
     for (int l = 0; l < n_levels; ++l) {

@@ -111,8 +111,7 @@ __global__ void maxpool_k3s2_kernel(const __nv_bfloat16* __restrict__ in, int n,
 // nn.MaxPool3d(kernel 2, stride 2, ceil_mode=True) on channels-last bf16 (VGG stages, feature_extractor.py:347):
 // output extent ceil(in/2); the last window is clipped at the border.
 __global__ void maxpool_k2s2_ceil_kernel(const __nv_bfloat16* __restrict__ in, int n, int X, int Y, int Z, int C, int Xo, int Yo,
-                                         int Zo, __nv_bfloat16* __restrict__ out) {
-    constexpr int fp16 = 0;                       // the VGG path stores bf16 only
+                                         int Zo, __nv_bfloat16* __restrict__ out, int fp16) {
     const int cg = C >> 3;
     const size_t total = (size_t)n * Xo * Yo * Zo * cg;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
@@ -150,7 +149,7 @@ __global__ void maxpool_k2s2_ceil_kernel(const __nv_bfloat16* __restrict__ in, i
 // fp32 NCDHW (N,4,X,Y,Z) -> bf16 (N, X, Y+1, Z, 64).  Row (x, yp, z) holds, for the two input rows y = yp-1 and yp, the seven
 // z-neighbours z-3..z+3 of all 4 channels: channel = ((yy*7 + zz)*4 + c), 56 used + 8 zero.  The 7^3 conv becomes a
 // 7 (dx) x 4 (y pairs) tap implicit GEMM with K = 64 per tap (packing.pack_stem_s1_weight).
-__global__ void pack_stem_s1_kernel(const float* __restrict__ grid, int n, int X, int Y, int Z, __nv_bfloat16* __restrict__ out) {
+__global__ void pack_stem_s1_kernel(const float* __restrict__ grid, int n, int X, int Y, int Z, __nv_bfloat16* __restrict__ out, int fp16) {
     const size_t total = (size_t)n * X * (Y + 1) * Z * 8;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int s = (int)(t & 7);
@@ -170,10 +169,10 @@ __global__ void pack_stem_s1_kernel(const float* __restrict__ grid, int n, int X
             }
             val[e] = f;
         }
-        __nv_bfloat162 h[4];
+        uint32_t h[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(val[2 * q], val[2 * q + 1]);
-        *reinterpret_cast<uint4*>(out + (t << 3)) = *reinterpret_cast<uint4*>(h);
+        for (int q = 0; q < 4; ++q) h[q] = pack_act2(val[2 * q], val[2 * q + 1], fp16);
+        *reinterpret_cast<uint4*>(out + (t << 3)) = make_uint4(h[0], h[1], h[2], h[3]);
     }
 }
 
@@ -218,20 +217,20 @@ int nrpn_maxpool3d_k3s2(const void* in, int n, int x, int y, int z, int c, void*
     return NRPN_OK;
 }
 
-int nrpn_maxpool3d_k2s2_ceil(const void* in, int n, int x, int y, int z, int c, void* out, nrpn_stream_t stream) {
+int nrpn_maxpool3d_k2s2_ceil(const void* in, int n, int x, int y, int z, int c, void* out, int act_fp16, nrpn_stream_t stream) {
     if (!in || !out || n < 1 || x < 1 || y < 1 || z < 1 || c < 8 || c % 8 != 0) return NRPN_ERR_INVALID;
     const int Xo = (x + 1) / 2, Yo = (y + 1) / 2, Zo = (z + 1) / 2;
     const size_t total = (size_t)n * Xo * Yo * Zo * (c / 8);
     maxpool_k2s2_ceil_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(in), n, x, y, z, c, Xo, Yo, Zo, reinterpret_cast<__nv_bfloat16*>(out));
+        reinterpret_cast<const __nv_bfloat16*>(in), n, x, y, z, c, Xo, Yo, Zo, reinterpret_cast<__nv_bfloat16*>(out), act_fp16 ? 1 : 0);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
 
-int nrpn_pack_stem_input_s1(const float* grid, int n, int x, int y, int z, void* packed, nrpn_stream_t stream) {
+int nrpn_pack_stem_input_s1(const float* grid, int n, int x, int y, int z, void* packed, int act_fp16, nrpn_stream_t stream) {
     if (!grid || !packed || n < 1 || x < 1 || y < 1 || z < 1) return NRPN_ERR_INVALID;
     const size_t total = (size_t)n * x * (y + 1) * z * 8;
-    pack_stem_s1_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, n, x, y, z, reinterpret_cast<__nv_bfloat16*>(packed));
+    pack_stem_s1_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, n, x, y, z, reinterpret_cast<__nv_bfloat16*>(packed), act_fp16 ? 1 : 0);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }

@@ -22,7 +22,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // row (i,j,k) channel ((c*4+px)*4+py)*4+pz = grid[c][4i+px][4j+py][4k+pz]; one thread per 16-byte chunk (8 channels =
 // fixed c,px,py half of pz... 8 consecutive channels = pz 0..3 for py and py+1).
 __global__ void patch_embed_pack_kernel(const float* __restrict__ grid, int n, int X, int Y, int Z, int H, int W, int D,
-                                        __nv_bfloat16* __restrict__ out) {
+                                        __nv_bfloat16* __restrict__ out, int fp16) {
     const size_t total = (size_t)n * H * W * D * 32;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int s = (int)(t & 31);
@@ -38,10 +38,10 @@ __global__ void patch_embed_pack_kernel(const float* __restrict__ grid, int n, i
             const int py = py0 + (e >> 2), pz = e & 3;
             val[e] = grid[((((size_t)b * 4 + c) * X + 4 * i + px) * Y + 4 * j + py) * Z + 4 * k + pz];
         }
-        __nv_bfloat162 h[4];
+        uint32_t h[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(val[2 * q], val[2 * q + 1]);
-        *reinterpret_cast<uint4*>(out + (t << 3)) = *reinterpret_cast<uint4*>(h);
+        for (int q = 0; q < 4; ++q) h[q] = pack_act2(val[2 * q], val[2 * q + 1], fp16);
+        *reinterpret_cast<uint4*>(out + (t << 3)) = make_uint4(h[0], h[1], h[2], h[3]);
     }
 }
 
@@ -49,19 +49,19 @@ __global__ void patch_embed_pack_kernel(const float* __restrict__ grid, int n, i
 // one warp per token; two passes over the row held in registers (C <= 3072 -> <= 96 values per lane)
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, __nv_bfloat16* __restrict__ out,
                                                         int ld_out, long tokens, int C, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, float eps) {
+                                                        const float* __restrict__ beta, float eps, int fp16) {
     const long tok = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (tok >= tokens) return;
     const __nv_bfloat16* x = in + tok * ld_in;
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += __bfloat162float(x[c]);
+    for (int c = lane; c < C; c += 32) s += load_act(x + c, fp16);
     const float mean = warp_sum(s) / (float)C;
     float q = 0.f;
-    for (int c = lane; c < C; c += 32) { const float d = __bfloat162float(x[c]) - mean; q += d * d; }
+    for (int c = lane; c < C; c += 32) { const float d = load_act(x + c, fp16) - mean; q += d * d; }
     const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
     __nv_bfloat16* y = out + tok * ld_out;
-    for (int c = lane; c < C; c += 32) y[c] = __float2bfloat16((__bfloat162float(x[c]) - mean) * rstd * gamma[c] + beta[c]);
+    for (int c = lane; c < C; c += 32) store_act(y + c, (load_act(x + c, fp16) - mean) * rstd * gamma[c] + beta[c], fp16);
 }
 
 // ---------------------------------------------------------------------------------------------- patch merging
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 // parity order 000,100,010,110,001,101,011,111 over (H,W,D), zero for positions past an odd extent.
 __global__ void __launch_bounds__(256) patch_merge_ln_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int n, int H, int W, int D, int C,
                                                              __nv_bfloat16* __restrict__ out, const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float eps) {
+                                                             const float* __restrict__ beta, float eps, int fp16) {
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, Do = (D + 1) / 2;
     const long tokens = (long)n * Ho * Wo * Do;
     const long tok = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) patch_merge_ln_kernel(const __nv_bfloat16
         const int a = part & 1, bb = (part >> 1) & 1, cc = (part >> 2) & 1;
         const int h = 2 * i + a, w = 2 * j + bb, d = 2 * k + cc;
         if (h >= H || w >= W || d >= D) return 0.f;
-        return __bfloat162float(in[((((size_t)b * H + h) * W + w) * D + d) * ld_in + c]);
+        return load_act(in + ((((size_t)b * H + h) * W + w) * D + d) * ld_in + c, fp16);
     };
     float s = 0.f;
     for (int c = lane; c < C8; c += 32) s += src(c);
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) patch_merge_ln_kernel(const __nv_bfloat16
     for (int c = lane; c < C8; c += 32) { const float d = src(c) - mean; q += d * d; }
     const float rstd = rsqrtf(warp_sum(q) / (float)C8 + eps);
     __nv_bfloat16* y = out + tok * C8;
-    for (int c = lane; c < C8; c += 32) y[c] = __float2bfloat16((src(c) - mean) * rstd * gamma[c] + beta[c]);
+    for (int c = lane; c < C8; c += 32) store_act(y + c, (src(c) - mean) * rstd * gamma[c] + beta[c], fp16);
 }
 
 // ---------------------------------------------------------------------------------------------- window attention
@@ -110,6 +110,7 @@ struct AttnDev {
     int n, H, W, D, C, heads;
     int PH, PW, PD, sh, sw, sd;                // padded extents, effective shifts
     int nwh, nww, nwd;
+    int fp16;                                  // 16-bit format of qkv / out: 0 bf16, 1 fp16
 };
 
 __global__ void __launch_bounds__(64) window_attention_kernel(AttnDev P) {
@@ -133,9 +134,9 @@ __global__ void __launch_bounds__(64) window_attention_kernel(AttnDev P) {
     const float scale = 0.17677669529663687f;                          // 32^-0.5
 #pragma unroll
     for (int d = 0; d < 32; ++d) {
-        const float qv = real ? __bfloat162float(row[hc + d]) : P.qkv_bias[hc + d];
-        const float kv = real ? __bfloat162float(row[P.C + hc + d]) : P.qkv_bias[P.C + hc + d];
-        const float vv = real ? __bfloat162float(row[2 * P.C + hc + d]) : P.qkv_bias[2 * P.C + hc + d];
+        const float qv = real ? load_act(row + hc + d, P.fp16) : P.qkv_bias[hc + d];
+        const float kv = real ? load_act(row + P.C + hc + d, P.fp16) : P.qkv_bias[P.C + hc + d];
+        const float vv = real ? load_act(row + 2 * P.C + hc + d, P.fp16) : P.qkv_bias[2 * P.C + hc + d];
         q[d] = qv * scale; Ks[t][d] = kv; Vs[t][d] = vv;
     }
     // shift-mask region of this token (ids as built by the reference: per axis 0 / 1 / 2, an unshifted axis contributes one id)
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(64) window_attention_kernel(AttnDev P) {
     if (real) {
         __nv_bfloat16* orow = P.out + tok * P.ld_out + hc;
 #pragma unroll
-        for (int d = 0; d < 32; d += 2) *reinterpret_cast<__nv_bfloat162*>(orow + d) = __floats2bfloat162_rn(o[d], o[d + 1]);
+        for (int d = 0; d < 32; d += 2) *reinterpret_cast<uint32_t*>(orow + d) = pack_act2(o[d], o[d + 1], P.fp16);
     }
 }
 
@@ -213,8 +214,8 @@ __global__ void __launch_bounds__(kAttnThreads) window_attention_tc_kernel(AttnD
     const bool shifted = (P.sh + P.sw + P.sd) > 0;
     const int half = t >> 6, tw = t & 63;                          // stacked window (0/1), token inside it
     const int ti = tw >> 4, tj = (tw >> 2) & 3, tk = tw & 3;
-    constexpr uint32_t kIdescS = ptx::make_idesc_bf16(128, 128);
-    constexpr uint32_t kIdescO = ptx::make_idesc_bf16(128, 32);
+    const uint32_t kIdescS = P.fp16 ? ptx::make_idesc_f16(128, 128) : ptx::make_idesc_bf16(128, 128);
+    const uint32_t kIdescO = P.fp16 ? ptx::make_idesc_f16(128, 32) : ptx::make_idesc_bf16(128, 32);
     uint32_t phase = 0;
     for (int pair = blockIdx.x; pair * 2 < n_windows; pair += gridDim.x) {
         int w = pair * 2 + half;
@@ -239,15 +240,15 @@ __global__ void __launch_bounds__(kAttnThreads) window_attention_tc_kernel(AttnD
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    __nv_bfloat162 a[4], c[4], e[4];
+                    uint32_t a[4], c[4], e[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int d = i * 8 + u * 2;
-                        a[u] = have ? __floats2bfloat162_rn(P.qkv_bias[hc + d], P.qkv_bias[hc + d + 1]) : __floats2bfloat162_rn(0.f, 0.f);
-                        c[u] = have ? __floats2bfloat162_rn(P.qkv_bias[P.C + hc + d], P.qkv_bias[P.C + hc + d + 1]) : __floats2bfloat162_rn(0.f, 0.f);
-                        e[u] = have ? __floats2bfloat162_rn(P.qkv_bias[2 * P.C + hc + d], P.qkv_bias[2 * P.C + hc + d + 1]) : __floats2bfloat162_rn(0.f, 0.f);
+                        a[u] = have ? pack_act2(P.qkv_bias[hc + d], P.qkv_bias[hc + d + 1], P.fp16) : 0u;
+                        c[u] = have ? pack_act2(P.qkv_bias[P.C + hc + d], P.qkv_bias[P.C + hc + d + 1], P.fp16) : 0u;
+                        e[u] = have ? pack_act2(P.qkv_bias[2 * P.C + hc + d], P.qkv_bias[2 * P.C + hc + d + 1], P.fp16) : 0u;
                     }
-                    qv[i] = *reinterpret_cast<uint4*>(a); kv[i] = *reinterpret_cast<uint4*>(c); vv[i] = *reinterpret_cast<uint4*>(e);
+                    qv[i] = make_uint4(a[0], a[1], a[2], a[3]); kv[i] = make_uint4(c[0], c[1], c[2], c[3]); vv[i] = make_uint4(e[0], e[1], e[2], e[3]);
                 }
             }
 #pragma unroll
@@ -313,10 +314,10 @@ __global__ void __launch_bounds__(kAttnThreads) window_attention_tc_kernel(AttnD
                 float e[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) { e[u] = __expf(sc[c * 8 + u] - mx); sum += e[u]; }
-                __nv_bfloat162 pk[4];
+                uint32_t pk[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) pk[u] = __floats2bfloat162_rn(e[2 * u], e[2 * u + 1]);
-                *reinterpret_cast<uint4*>(mine + attn_sw(t, c)) = *reinterpret_cast<uint4*>(pk);
+                for (int u = 0; u < 4; ++u) pk[u] = pack_act2(e[2 * u], e[2 * u + 1], P.fp16);
+                *reinterpret_cast<uint4*>(mine + attn_sw(t, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 *reinterpret_cast<uint4*>(other + attn_sw(t, c)) = make_uint4(0u, 0u, 0u, 0u);
             }
         }
@@ -349,11 +350,11 @@ __global__ void __launch_bounds__(kAttnThreads) window_attention_tc_kernel(AttnD
                 __nv_bfloat16* orow = P.out + tok * P.ld_out + hc;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    __nv_bfloat162 pk[4];
+                    uint32_t pk[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        pk[u] = __floats2bfloat162_rn(__uint_as_float(o[i * 8 + 2 * u]) * inv, __uint_as_float(o[i * 8 + 2 * u + 1]) * inv);
-                    *(reinterpret_cast<uint4*>(orow) + i) = *reinterpret_cast<uint4*>(pk);
+                        pk[u] = pack_act2(__uint_as_float(o[i * 8 + 2 * u]) * inv, __uint_as_float(o[i * 8 + 2 * u + 1]) * inv, P.fp16);
+                    *(reinterpret_cast<uint4*>(orow) + i) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
         }
@@ -378,40 +379,41 @@ using namespace nrpn;
 extern "C" {
 #pragma GCC visibility push(default)
 
-int nrpn_patch_embed_pack(const float* grid, int n, int x, int y, int z, void* out, nrpn_stream_t stream) {
+int nrpn_patch_embed_pack(const float* grid, int n, int x, int y, int z, void* out, int act_fp16, nrpn_stream_t stream) {
     if (!grid || !out || n < 1 || x < 4 || y < 4 || z < 4) return NRPN_ERR_INVALID;
     const int H = x / 4, W = y / 4, D = z / 4;
     const size_t total = (size_t)n * H * W * D * 32;
-    patch_embed_pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, n, x, y, z, H, W, D, reinterpret_cast<__nv_bfloat16*>(out));
+    patch_embed_pack_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, n, x, y, z, H, W, D, reinterpret_cast<__nv_bfloat16*>(out), act_fp16 ? 1 : 0);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
 
 int nrpn_layernorm(const void* in, int ld_in, void* out, int ld_out, long tokens, int c, const float* gamma, const float* beta,
-                   float eps, nrpn_stream_t stream) {
+                   float eps, int act_fp16, nrpn_stream_t stream) {
     if (!in || !out || !gamma || !beta || tokens < 1 || c < 1 || ld_in < c || ld_out < c) return NRPN_ERR_INVALID;
     layernorm_kernel<<<(unsigned)ceil_div(tokens, 8L), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(in), ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out, tokens, c, gamma, beta, eps);
+        reinterpret_cast<const __nv_bfloat16*>(in), ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out, tokens, c, gamma, beta, eps, act_fp16 ? 1 : 0);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
 
 int nrpn_patch_merge_ln(const void* in, int ld_in, int n, int h, int w, int d, int c, void* out, const float* gamma, const float* beta,
-                        float eps, nrpn_stream_t stream) {
+                        float eps, int act_fp16, nrpn_stream_t stream) {
     if (!in || !out || !gamma || !beta || n < 1 || h < 1 || w < 1 || d < 1 || c < 1 || ld_in < c) return NRPN_ERR_INVALID;
     const long tokens = (long)n * ((h + 1) / 2) * ((w + 1) / 2) * ((d + 1) / 2);
     patch_merge_ln_kernel<<<(unsigned)ceil_div(tokens, 8L), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(in), ld_in, n, h, w, d, c, reinterpret_cast<__nv_bfloat16*>(out), gamma, beta, eps);
+        reinterpret_cast<const __nv_bfloat16*>(in), ld_in, n, h, w, d, c, reinterpret_cast<__nv_bfloat16*>(out), gamma, beta, eps, act_fp16 ? 1 : 0);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
 
 int nrpn_window_attention(const void* qkv, int ld_qkv, void* out, int ld_out, const float* qkv_bias, const float* table, int n, int h,
-                          int w, int d, int c, int heads, int shift, nrpn_stream_t stream) {
+                          int w, int d, int c, int heads, int shift, int act_fp16, nrpn_stream_t stream) {
     if (!qkv || !out || !qkv_bias || !table || n < 1 || h < 1 || w < 1 || d < 1 || heads < 1 || c != heads * 32) return NRPN_ERR_INVALID;
     if (ld_qkv < 3 * c || ld_out < c || (shift != 0 && shift != 2)) return NRPN_ERR_INVALID;
     AttnDev P;
     P.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv); P.ld_qkv = ld_qkv; P.out = reinterpret_cast<__nv_bfloat16*>(out); P.ld_out = ld_out;
+    P.fp16 = act_fp16 ? 1 : 0;
     P.qkv_bias = qkv_bias; P.table = table; P.n = n; P.H = h; P.W = w; P.D = d; P.C = c; P.heads = heads;
     P.PH = (h + 3) / 4 * 4; P.PW = (w + 3) / 4 * 4; P.PD = (d + 3) / 4 * 4;
     P.sh = (4 >= P.PH) ? 0 : shift; P.sw = (4 >= P.PW) ? 0 : shift; P.sd = (4 >= P.PD) ? 0 : shift;   // no shift along an axis one window wide

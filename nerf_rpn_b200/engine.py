@@ -99,8 +99,6 @@ class RPNInferenceEngine:
         bb, hd = self.backbone, self.head
         L = {}
         self.kind = {"VGG_FPN": "vgg", "SwinTransformer_FPN": "swin"}.get(type(bb).__name__, "resnet")
-        if self.precision == "fp16" and (self.kind != "resnet" or self.fcos is not None):
-            raise NotImplementedError("precision='fp16' is implemented for the ResNet-FPN + anchor-head path only")
         _Conv.dtype = self.act_dtype
         if self.kind == "vgg":
             self._pack_vgg(L, device)
@@ -478,7 +476,7 @@ class _Plan:
         device = self.device
         buf, conv = self._buf, self._conv
         pad64 = lambda c: (c + 63) // 64 * 64
-        zbuf = lambda d, c: torch.zeros((n, *d, c), dtype=torch.bfloat16, device=device)      # pad channels must stay zero
+        zbuf = lambda d, c: torch.zeros((n, *d, c), dtype=eng.act_dtype, device=device)      # pad channels must stay zero
         def add(fn, name):
             self.launches.append(fn); self.names[id(fn)] = (name, 0.0)
         X, Y, Z = dims

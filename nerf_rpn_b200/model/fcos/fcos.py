@@ -105,12 +105,13 @@ class FCOSOverNeRF(nn.Module):
 
     def engine(self):
         from ...engine import RPNInferenceEngine
-        if self._engine is None:
+        precision = getattr(self, "precision", "bf16")      # "fp16": IEEE-half activations / weights
+        if self._engine is None or self._engine.precision != precision:
             m, sel = self.fcos_module, self.fcos_module.box_selector_test
             self._engine = RPNInferenceEngine(self.backbone, m.head, fcos=dict(
                 use_obb=sel.use_obb, pre_nms_thresh=sel.pre_nms_thresh, pre_nms_top_n=sel.pre_nms_top_n,
                 nms_thresh=sel.nms_thresh, post_nms_top_n=sel.fpn_post_nms_top_n, min_size=sel.min_size,
-                fpn_strides=list(m.fpn_strides)))
+                fpn_strides=list(m.fpn_strides)), precision=precision)
         return self._engine
 
     def forward(self, meshes, targets=None, objectness_output_paths=None):

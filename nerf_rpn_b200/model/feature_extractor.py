@@ -81,8 +81,9 @@ class ResNet_FPN_256(nn.Module):
     def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
         """x: (N,4,W,L,H) fp32 CUDA -> [P2,P3,P4,P5], each (N,256,w,l,h) fp32 (channels_last_3d strides)."""
         from ..engine import RPNInferenceEngine
-        if self._engine is None:
-            self._engine = RPNInferenceEngine(self)
+        precision = getattr(self, "precision", "bf16")
+        if self._engine is None or self._engine.precision != precision:
+            self._engine = RPNInferenceEngine(self, precision=precision)
         plan = self._engine.forward_device(x.contiguous())
         return [f.permute(0, 4, 1, 2, 3).float() for f in plan.features]
 
@@ -162,8 +163,9 @@ class VGG_FPN(nn.Module):
     def forward(self, X):
         """(N,4,W,L,H) fp32 CUDA -> tuple of 4 (N,256,w,l,h) fp32 feature maps (channels_last_3d strides)."""
         from ..engine import RPNInferenceEngine
-        if self._engine is None:
-            self._engine = RPNInferenceEngine(self)
+        precision = getattr(self, "precision", "bf16")
+        if self._engine is None or self._engine.precision != precision:
+            self._engine = RPNInferenceEngine(self, precision=precision)
         plan = self._engine.forward_device(X.contiguous())
         return tuple(f.permute(0, 4, 1, 2, 3).float() for f in plan.features)
 
@@ -269,8 +271,9 @@ class SwinTransformer_FPN(nn.Module):
 
     def forward(self, x):
         from ..engine import RPNInferenceEngine
-        if self._engine is None:
-            self._engine = RPNInferenceEngine(self)
+        precision = getattr(self, "precision", "bf16")
+        if self._engine is None or self._engine.precision != precision:
+            self._engine = RPNInferenceEngine(self, precision=precision)
         plan = self._engine.forward_device(x.contiguous())
         return tuple(f.permute(0, 4, 1, 2, 3).float() for f in plan.features)
 

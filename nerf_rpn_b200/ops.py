@@ -251,24 +251,24 @@ def maxpool3d_k3s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
 
 
 def maxpool3d_k2s2_ceil(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """(N,X,Y,Z,C) bf16 channels-last -> MaxPool3d(2, 2, ceil_mode=True)."""
-    x = _req(x, torch.bfloat16, "x")
+    """(N,X,Y,Z,C) bf16 / fp16 channels-last -> MaxPool3d(2, 2, ceil_mode=True)."""
+    f16 = _act16(x, "x")
     n, X, Y, Z, C = x.shape
     if out is None:
-        out = torch.empty((n, (X + 1) // 2, (Y + 1) // 2, (Z + 1) // 2, C), dtype=torch.bfloat16, device=x.device)
-    check(lib().nrpn_maxpool3d_k2s2_ceil(_ptr(x), n, X, Y, Z, C, _ptr(out), _stream()), "maxpool3d_k2s2_ceil")
+        out = torch.empty((n, (X + 1) // 2, (Y + 1) // 2, (Z + 1) // 2, C), dtype=x.dtype, device=x.device)
+    check(lib().nrpn_maxpool3d_k2s2_ceil(_ptr(x), n, X, Y, Z, C, _ptr(out), f16, _stream()), "maxpool3d_k2s2_ceil")
     return out
 
 
-def pack_stem_input_s1(grid: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """(N,4,X,Y,Z) fp32 -> (N, X, Y+1, Z, 64) bf16 (stride-1 7^3 stem)."""
+def pack_stem_input_s1(grid: torch.Tensor, out: Optional[torch.Tensor] = None, dtype=torch.bfloat16) -> torch.Tensor:
+    """(N,4,X,Y,Z) fp32 -> (N, X, Y+1, Z, 64) bf16 / fp16 (stride-1 7^3 stem)."""
     grid = _req(grid, torch.float32, "grid")
     n, c, x, y, z = grid.shape
     if c != 4:
         raise ValueError("stem packing expects 4 input channels (RGB + density)")
     if out is None:
-        out = torch.empty((n, x, y + 1, z, 64), dtype=torch.bfloat16, device=grid.device)
-    check(lib().nrpn_pack_stem_input_s1(_ptr(grid), n, x, y, z, _ptr(out), _stream()), "pack_stem_input_s1")
+        out = torch.empty((n, x, y + 1, z, 64), dtype=dtype, device=grid.device)
+    check(lib().nrpn_pack_stem_input_s1(_ptr(grid), n, x, y, z, _ptr(out), _act16(out, "out"), _stream()), "pack_stem_input_s1")
     return out
 
 
@@ -321,11 +321,11 @@ def groupnorm_relu_(levels: Sequence[torch.Tensor], gamma: torch.Tensor, beta: t
     n, c = levels[0].shape[0], levels[0].shape[-1]
     arr = (GnLevel * len(levels))()
     for i, t in enumerate(levels):
-        _req(t, torch.bfloat16, f"levels[{i}]")
+        f16 = _act16(t, f"levels[{i}]")
         arr[i].x = t.data_ptr(); arr[i].voxels = int(t.shape[1] * t.shape[2] * t.shape[3])
     need = lib().nrpn_groupnorm_workspace_bytes(len(levels), n)
     ws = workspace if workspace is not None else _workspace(need, levels[0].device)
-    check(lib().nrpn_groupnorm_relu(arr, len(levels), n, c, groups, _ptr(gamma), _ptr(beta), float(eps), int(relu), _ptr(ws),
+    check(lib().nrpn_groupnorm_relu(arr, len(levels), n, c, groups, _ptr(gamma), _ptr(beta), float(eps), int(relu), f16, _ptr(ws),
                                     ws.numel(), _stream()), "groupnorm_relu")
 
 
@@ -372,7 +372,7 @@ def fcos_proposals(desc: FcosDesc, device, out=None, workspace: Optional[torch.T
 def patch_embed_pack(grid: torch.Tensor, out: torch.Tensor):
     grid = _req(grid, torch.float32, "grid")
     n, c, x, y, z = grid.shape
-    check(lib().nrpn_patch_embed_pack(_ptr(grid), n, x, y, z, _ptr(out), _stream()), "patch_embed_pack")
+    check(lib().nrpn_patch_embed_pack(_ptr(grid), n, x, y, z, _ptr(out), _act16(out, "out"), _stream()), "patch_embed_pack")
     return out
 
 
@@ -380,19 +380,19 @@ def layernorm(x: torch.Tensor, out: torch.Tensor, c: int, gamma: torch.Tensor, b
     """x, out: (..., ld) bf16 channels-last; normalises the first c channels of every row."""
     tokens = x.numel() // x.shape[-1]
     check(lib().nrpn_layernorm(_ptr(x), int(x.shape[-1]), _ptr(out), int(out.shape[-1]), tokens, int(c), _ptr(gamma), _ptr(beta),
-                               float(eps), _stream()), "layernorm")
+                               float(eps), _act16(x, "x"), _stream()), "layernorm")
     return out
 
 
 def patch_merge_ln(x: torch.Tensor, out: torch.Tensor, c: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5):
     n, h, w, d, ld = x.shape
-    check(lib().nrpn_patch_merge_ln(_ptr(x), int(ld), n, h, w, d, int(c), _ptr(out), _ptr(gamma), _ptr(beta), float(eps), _stream()),
-          "patch_merge_ln")
+    check(lib().nrpn_patch_merge_ln(_ptr(x), int(ld), n, h, w, d, int(c), _ptr(out), _ptr(gamma), _ptr(beta), float(eps),
+                                    _act16(x, "x"), _stream()), "patch_merge_ln")
     return out
 
 
 def window_attention(qkv: torch.Tensor, out: torch.Tensor, qkv_bias: torch.Tensor, table: torch.Tensor, c: int, heads: int, shift: int):
     n, h, w, d, ld = qkv.shape
     check(lib().nrpn_window_attention(_ptr(qkv), int(ld), _ptr(out), int(out.shape[-1]), _ptr(qkv_bias), _ptr(table), n, h, w, d, int(c),
-                                      int(heads), int(shift), _stream()), "window_attention")
+                                      int(heads), int(shift), _act16(qkv, "qkv"), _stream()), "window_attention")
     return out

@@ -79,9 +79,11 @@ def _ns():
 
 @pytest.mark.parametrize("name,obb,pre,post", [("fcos_small_aabb", False, 2500, 2500), ("fcos_small_obb", True, 2500, 2500),
                                                ("fcos_small_obb_tight", True, 300, 150)])
-def test_fcos_end_to_end_vs_reference_golden(golden_dir, name, obb, pre, post):
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_fcos_end_to_end_vs_reference_golden(golden_dir, name, obb, pre, post, precision):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     model = recipes.build_fcos_small(_ns(), obb, g, pre, post).cuda().eval()
+    model.precision = precision
     x = recipes.seed1000_input().cuda()
     with torch.no_grad():
         boxes, losses, scores = model([x])
@@ -94,8 +96,8 @@ def test_fcos_end_to_end_vs_reference_golden(golden_dir, name, obb, pre, post):
         lg = plan.pred["cls"][l][0][..., 0].cpu()
         ref = torch.from_numpy(g[f"logits{l}"][0])
         rel = ((lg - ref).norm() / ref.norm()).item()
-        print(f"{name}: cls logits level {l} norm-wise rel err {rel:.3e}")
-        assert rel < 5e-2
+        print(f"{name} [{precision}]: cls logits level {l} norm-wise rel err {rel:.3e}")
+        assert rel < (5e-2 if precision == "bf16" else 6e-3)
     # (b) post-processing bit-identical to the oracle on the engine's own head outputs
     L = eng.layers
     ob, os_ = fp.fcos_proposals([p[0].reshape(-1, p.shape[-1])[:, 0].cpu().numpy() for p in plan.pred["cls"]],
