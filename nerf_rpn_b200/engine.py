@@ -476,7 +476,7 @@ class _Plan:
         device = self.device
         buf, conv = self._buf, self._conv
         pad64 = lambda c: (c + 63) // 64 * 64
-        zbuf = lambda d, c: torch.zeros((n, *d, c), dtype=eng.act_dtype, device=device)      # pad channels must stay zero
+        zbuf = lambda d, c: torch.zeros((n, *d, c), dtype=self.eng.act_dtype, device=device)      # pad channels must stay zero
         def add(fn, name):
             self.launches.append(fn); self.names[id(fn)] = (name, 0.0)
         X, Y, Z = dims
