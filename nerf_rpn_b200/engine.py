@@ -310,6 +310,7 @@ class _Plan:
             self.input = torch.empty((n, X, Y, Z, 4), dtype=torch.float32, device=device).permute(0, 4, 1, 2, 3)
         else:
             self.input = torch.empty((n, 4, X, Y, Z), dtype=torch.float32, device=device)
+        self._src = self.input
         self._buf, self._conv = buf, conv
         feats = {"vgg": self._build_vgg, "swin": self._build_swin}.get(eng.kind, self._build_resnet)(L, n, dims, bf)
         self.features = [f for f, _ in feats]
@@ -363,7 +364,7 @@ class _Plan:
         X, Y, Z = dims
         d1 = _down(dims)
         self.packed = torch.empty((n, d1[0], d1[1], d1[2] + 1, 64), **bf)
-        self.launches.append(lambda: ops.pack_stem_input(self.input, self.packed))
+        self.launches.append(lambda: ops.pack_stem_input(self._src, self.packed))
         self.names[id(self.launches[-1])] = ("pack_stem_input", 0.0)
         c1 = buf(d1, 64)
         conv(L["stem"], [self.packed], [c1], [(d1[0], d1[1], d1[2] + 1)], [d1], real=(4, 343, 64), name="stem7x7x7s2(s2d)")
@@ -423,7 +424,7 @@ class _Plan:
         if L["vgg_strided"]:
             d1 = _down(dims)
             self.packed = torch.empty((n, d1[0], d1[1], d1[2] + 1, 64), **bf)
-            self.launches.append(lambda: ops.pack_stem_input(self.input, self.packed))
+            self.launches.append(lambda: ops.pack_stem_input(self._src, self.packed))
             self.names[id(self.launches[-1])] = ("pack_stem_input", 0.0)
             c1 = buf(d1, 64)
             conv(L["stem"], [self.packed], [c1], [(d1[0], d1[1], d1[2] + 1)], [d1], real=(4, 343, 64), name="stem7x7x7s2(s2d)")
@@ -433,7 +434,7 @@ class _Plan:
             self.names[id(self.launches[-1])] = ("maxpool3d_k3s2", 0.0)
         else:
             self.packed = torch.empty((n, X, Y + 1, Z, 64), **bf)
-            self.launches.append(lambda: ops.pack_stem_input_s1(self.input, self.packed))
+            self.launches.append(lambda: ops.pack_stem_input_s1(self._src, self.packed))
             self.names[id(self.launches[-1])] = ("pack_stem_input_s1", 0.0)
             xd = dims
             x = buf(xd, 64)
@@ -482,7 +483,7 @@ class _Plan:
         X, Y, Z = dims
         td = (X // 4, Y // 4, Z // 4)
         self.packed = torch.empty((n, *td, 256), **bf)
-        add(lambda: ops.patch_embed_pack(self.input, self.packed), "swin.patch_embed_pack")
+        add(lambda: ops.patch_embed_pack(self._src, self.packed), "swin.patch_embed_pack")
         C = L["pe"].cout
         e = zbuf(td, pad64(C))
         conv(L["pe"], [self.packed], [e], [td], [td], name="swin.patch_embed(4x4x4 s4 as GEMM)")
@@ -675,8 +676,10 @@ class _Plan:
         self._valid = valid_dims
         self._post_graph = [None, None]
 
-    def _run_main_eager(self):
-        for f in self.launches:
+    def _run_main_eager(self, skip_pack: bool = False):
+        # launches[0] is always the kernel that consumes the fp32 input grid (stem packing / patch-embedding packing); it reads
+        # self._src, the caller's tensor, so no staging copy of the 168 MB grid is needed.  The captured graph starts after it.
+        for f in self.launches[1:] if skip_pack else self.launches:
             f()
         if self.has_head:
             for f in self.head_launches:
@@ -700,17 +703,20 @@ class _Plan:
         if self.has_head and vd != self._valid:
             torch.cuda.synchronize()
             self._build_post(vd)
-        if grids.data_ptr() != self.input.data_ptr():
-            self.input.copy_(grids, non_blocking=True)
+        if self.channels_last != ops.is_channels_last_grid(grids) or (not self.channels_last and not grids.is_contiguous()):
+            self.input.copy_(grids, non_blocking=True)      # foreign memory order: one conversion copy into the plan's own buffer
+            grids = self.input
+        self._src = grids
         use_graph = self.eng.use_graph
         if use_graph and self._graph is None:
             self._run_eager()                      # warm-up: cudaFuncSetAttribute, lazy init
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._run_main_eager()
+                self._run_main_eager(skip_pack=True)
             self._graph = g
         if use_graph:
+            self.launches[0]()                     # input packing, eager: the only kernel whose source pointer changes per call
             self._graph.replay()
         else:
             self._run_main_eager()
