@@ -532,6 +532,13 @@ static int conv_geometry(const nrpn_conv_desc* d, ConvGeom& g) {
         tiles += S.n * ceil_div(S.xo, bx) * ceil_div(S.yo, by) * ceil_div(S.zo, bz);
     }
     g.m_tiles = tiles;
+    // Late ResNet stages (5x8x8 .. 10x16x16 voxels, K up to 13 824): a handful of 128 x 256 tiles leaves most SMs idle while each
+    // tile runs a long reduction.  When even 64-wide tiles fit in one wave, use them: 4x the CTAs, each 128 x 64 MMA lasts 48 clk
+    // instead of 128 (same reduction order per output element, bit-identical results).
+    if (!g.short_k && g.block_n > 64 && tiles * (g.cout_pad / 64) <= num_sms()) {
+        const char* e = getenv("NRPN_CONV_NARROW");
+        if (!(e && e[0] == '0')) { g.block_n = 64; g.n_tiles_n = g.cout_pad / 64; }
+    }
     g.splits = choose_splits(tiles * g.n_tiles_n, g.kblocks, g.short_k);
     g.counter_bytes = align_up((size_t)tiles * g.n_tiles_n * 4, 256);
     g.ws_bytes = g.splits > 1 ? g.counter_bytes + (size_t)tiles * g.n_tiles_n * g.splits * kBlockM * g.block_n * 4 : 0;
