@@ -113,3 +113,30 @@ def test_fcos_end_to_end_vs_reference_golden(golden_dir, name, obb, pre, post, p
     hit = (obox.iou_matrix(refb[top], ours).max(axis=1) >= 0.7).mean()
     print(f"{name}: {ours.shape[0]} proposals (reference {refb.shape[0]}); top-100 matched at IoU>=0.7: {hit:.2f}")
     assert hit >= 0.8 and abs(ours.shape[0] - refb.shape[0]) <= 0.2 * refb.shape[0] + 10
+
+
+@pytest.mark.parametrize("obb", [False, True])
+def test_fcos_batch_of_two_padded_scenes(golden_dir, obb):
+    """batch > 1 with different extents (fcos.py:252-266 compute_padding_masks): scenes are zero-padded to the batch maximum,
+    locations outside a scene's own extent are masked, boxes are clipped to the scene's own size. Post-processing of every scene
+    must equal the oracle's on the engine's head outputs."""
+    name = "fcos_small_obb" if obb else "fcos_small_aabb"
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    model = recipes.build_fcos_small(_ns(), obb, g, 2500, 2500).cuda().eval()
+    x0 = recipes.seed1000_input().cuda()
+    x1 = x0[:, :24, :40, :32].contiguous()
+    with torch.no_grad():
+        boxes, losses, scores = model([x0, x1])
+    assert len(boxes) == 2 and losses == {}
+    eng = model.engine()
+    plan = [p for k, p in eng._plans.items() if k[0] == 2][0]
+    code = 8 if obb else 6
+    L = eng.layers
+    for i, own in enumerate([(32, 48, 40), (24, 40, 32)]):
+        ob, os_ = fp.fcos_proposals([p[i].reshape(-1, p.shape[-1])[:, 0].cpu().numpy() for p in plan.pred["cls"]],
+                                    [p[i].reshape(-1, p.shape[-1])[:, :code].cpu().numpy() for p in plan.pred["reg"]],
+                                    [p[i].reshape(-1, p.shape[-1])[:, code].cpu().numpy() for p in plan.pred["reg"]],
+                                    L["scales"], GRIDS, STRIDES, own, obb, 0.0, 2500, 0.3, 2500, 0.0, padded=True)
+        np.testing.assert_array_equal(bits(boxes[i].cpu().numpy()), bits(ob))
+        np.testing.assert_array_equal(bits(scores[i].cpu().numpy()), bits(os_))
+    assert boxes[1].shape[0] > 0 and boxes[0].shape[0] != boxes[1].shape[0]
