@@ -145,6 +145,10 @@ int nrpn_pack_stem_input(const float *grid, int n, int x, int y, int z, void *pa
                          int channels_last /* 0: grid is (N,4,X,Y,Z); 1: (N,X,Y,Z,4) as stored on disk, datasets.py:49-57 */,
                          nrpn_stream_t stream);
 
+/* Same packing from a raw uint8 grid in its on-disk order (N,X,Y,Z,4): bytes are normalised by / 255 on the device, as
+ * datasets.py:59-61 does on the host (.float() / 255.0); a quarter of the fp32 host-to-device traffic. */
+int nrpn_pack_stem_input_u8(const uint8_t *grid_xyzc, int n, int x, int y, int z, void *packed, int act_fp16, nrpn_stream_t stream);
+
 /* F.max_pool3d(kernel 3, stride 2, padding 1) on (N,X,Y,Z,C) bf16, C % 8 == 0 (feature_extractor.py:219). */
 int nrpn_maxpool3d_k3s2(const void *in, int n, int x, int y, int z, int c, void *out, int act_fp16, nrpn_stream_t stream);
 

@@ -65,6 +65,34 @@ __global__ void pack_stem_cl_kernel(const float4* __restrict__ grid, int n, int 
     }
 }
 
+// uint8 grids (datasets.py:59-61 normalises them with .float() / 255.0 on the host): the raw (N,X,Y,Z,4) bytes are copied to the
+// device (a quarter of the fp32 H2D traffic) and normalised here, one 32-bit load per voxel; the division is the same correctly
+// rounded fp32 x / 255 the reference performs.
+__global__ void pack_stem_cl_u8_kernel(const uint32_t* __restrict__ grid, int n, int X, int Y, int Z, int X2, int Y2, int Z2,
+                                       __nv_bfloat16* __restrict__ out, int fp16) {
+    const size_t total = (size_t)n * X2 * Y2 * (Z2 + 1) * 8;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int s = (int)(t & 7);
+        size_t v = t >> 3;
+        const int k = (int)(v % (Z2 + 1)); v /= (Z2 + 1);
+        const int j = (int)(v % Y2); v /= Y2;
+        const int i = (int)(v % X2); const int b = (int)(v / X2);
+        const int half = s >> 2, rx = (s >> 1) & 1, ry = s & 1;
+        const int kk = k - 1 + half;
+        const int x = 2 * i + rx, y = 2 * j + ry, z = 2 * kk;
+        uint32_t a = 0u, c = 0u;
+        if (kk >= 0 && kk < Z2 && x < X && y < Y) {
+            const uint32_t* p = grid + (((size_t)b * X + x) * Y + y) * Z + z;
+            a = __ldg(p);
+            if (z + 1 < Z) c = __ldg(p + 1);
+        }
+        auto f = [](uint32_t w, int byte) { return __fdiv_rn((float)((w >> (8 * byte)) & 0xFFu), 255.0f); };
+        const uint32_t h0 = pack_act2(f(a, 0), f(a, 1), fp16), h1 = pack_act2(f(a, 2), f(a, 3), fp16);
+        const uint32_t h2 = pack_act2(f(c, 0), f(c, 1), fp16), h3 = pack_act2(f(c, 2), f(c, 3), fp16);
+        *reinterpret_cast<uint4*>(out + (t << 3)) = make_uint4(h0, h1, h2, h3);
+    }
+}
+
 // F.max_pool3d(k=3, s=2, p=1) on channels-last bf16; one thread per (output voxel, 8 channels).
 __global__ void maxpool_k3s2_kernel(const __nv_bfloat16* __restrict__ in, int n, int X, int Y, int Z, int C, int Xo, int Yo,
                                     int Zo, __nv_bfloat16* __restrict__ out, int fp16) {
@@ -203,6 +231,17 @@ int nrpn_pack_stem_input(const float* grid, int n, int x, int y, int z, void* pa
     }
     pack_stem_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, n, x, y, z, X2, Y2, Z2,
                                                                             reinterpret_cast<__nv_bfloat16*>(packed), act_fp16 ? 1 : 0);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+int nrpn_pack_stem_input_u8(const uint8_t* grid, int n, int x, int y, int z, void* packed, int act_fp16, nrpn_stream_t stream) {
+    if (!grid || !packed || n < 1 || x < 1 || y < 1 || z < 1) return NRPN_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(grid) % 4 != 0) return NRPN_ERR_INVALID;
+    const int X2 = (x + 1) / 2, Y2 = (y + 1) / 2, Z2 = (z + 1) / 2;
+    const size_t total = (size_t)n * X2 * Y2 * (Z2 + 1) * 8;
+    pack_stem_cl_u8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(grid), n, x, y, z, X2, Y2, Z2,
+                                                                                  reinterpret_cast<__nv_bfloat16*>(packed), act_fp16 ? 1 : 0);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }

@@ -226,7 +226,7 @@ class RPNInferenceEngine:
         L["fpn"] = [_Conv(m.weight, m.bias, device=device) for m in bb.fpn_neck.fpn_convs]
 
     # ---------------------------------------------------------------- plan
-    def _get_plan(self, n, dims, device, channels_last: bool = False):
+    def _get_plan(self, n, dims, device, channels_last: bool = False, u8: bool = False):
         ver = self._param_version()
         if self.layers is None or ver != self._packed_version:
             self._pack(device)
@@ -234,10 +234,12 @@ class RPNInferenceEngine:
         # a grid handed over as the dataset's (4,W,L,H) VIEW of the on-disk (W,L,H,4) array is consumed in place by the
         # ResNet stem packing (128-bit loads); the other backbones take a copy into NCDHW first
         cl = bool(channels_last) and self.kind == "resnet" and max(dims) >= 0
-        key = (n, tuple(dims), str(device), cl)
+        if u8 and not cl:
+            raise NotImplementedError("raw uint8 grids are consumed by the ResNet stem packing only; normalise to fp32 for the other backbones")
+        key = (n, tuple(dims), str(device), cl, bool(u8))
         p = self._plans.get(key)
         if p is None:
-            p = _Plan(self, n, tuple(dims), device, cl)
+            p = _Plan(self, n, tuple(dims), device, cl, bool(u8))
             self._plans[key] = p
         return p
 
@@ -250,10 +252,13 @@ class RPNInferenceEngine:
     def forward_device(self, grids: torch.Tensor, valid_dims: Optional[Sequence[Sequence[int]]] = None):
         """grids: (N,4,X,Y,Z) fp32 CUDA.  Returns the plan whose output buffers hold the results (no host sync)."""
         self.check_eval()
-        if not grids.is_cuda or grids.dtype != torch.float32:
-            raise RuntimeError("nerf_rpn_b200: input grids must be fp32 CUDA tensors (no CPU path)")
+        if not grids.is_cuda or grids.dtype not in (torch.float32, torch.uint8):
+            raise RuntimeError("nerf_rpn_b200: input grids must be fp32 (or raw uint8, channels-last) CUDA tensors (no CPU path)")
         n, c, X, Y, Z = grids.shape
-        plan = self._get_plan(n, (X, Y, Z), grids.device, channels_last=ops.is_channels_last_grid(grids))
+        u8 = grids.dtype == torch.uint8
+        if u8 and not ops.is_channels_last_grid(grids):
+            raise ValueError("nerf_rpn_b200: uint8 grids must be (4,W,L,H) views of the on-disk (W,L,H,4) arrays")
+        plan = self._get_plan(n, (X, Y, Z), grids.device, channels_last=ops.is_channels_last_grid(grids), u8=u8)
         plan.run(grids, valid_dims)
         return plan
 
@@ -264,9 +269,11 @@ class RPNInferenceEngine:
 
 
 class _Plan:
-    def __init__(self, eng: RPNInferenceEngine, n: int, dims: Tuple[int, int, int], device, channels_last: bool = False):
+    def __init__(self, eng: RPNInferenceEngine, n: int, dims: Tuple[int, int, int], device, channels_last: bool = False,
+                 u8: bool = False):
         self.eng, self.n, self.dims, self.device = eng, n, dims, device
         self.channels_last = channels_last
+        self.input_u8 = u8
         L = eng.layers
         bf = dict(dtype=eng.act_dtype, device=device)
         X, Y, Z = dims
@@ -307,7 +314,7 @@ class _Plan:
                                              f"out={'+'.join('x'.join(map(str, d)) for d in out_dims)}", fl)
 
         if channels_last:            # memory (n,X,Y,Z,4), logical (n,4,X,Y,Z): same strides as the dataset's view, copies stay memcpys
-            self.input = torch.empty((n, X, Y, Z, 4), dtype=torch.float32, device=device).permute(0, 4, 1, 2, 3)
+            self.input = torch.empty((n, X, Y, Z, 4), dtype=torch.uint8 if u8 else torch.float32, device=device).permute(0, 4, 1, 2, 3)
         else:
             self.input = torch.empty((n, 4, X, Y, Z), dtype=torch.float32, device=device)
         self._src = self.input

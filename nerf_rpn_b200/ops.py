@@ -222,8 +222,18 @@ def is_channels_last_grid(grid: torch.Tensor) -> bool:
 def pack_stem_input(grid: torch.Tensor, out: Optional[torch.Tensor] = None, dtype=torch.bfloat16) -> torch.Tensor:
     """(N,4,X,Y,Z) fp32 -> (N, ceil(X/2), ceil(Y/2), ceil(Z/2)+1, 64) bf16 (or fp16: dtype of `out`).
     `grid` may be contiguous NCDHW or the channels-last view the reference's dataset yields (memory (N,X,Y,Z,4))."""
+    if isinstance(grid, torch.Tensor) and grid.is_cuda and grid.dtype == torch.uint8 and grid.dim() == 5:
+        # raw uint8 grid in its on-disk order: normalised (/ 255) on the device
+        if not is_channels_last_grid(grid):
+            raise ValueError("nerf_rpn_b200: uint8 grids must be the (N,4,X,Y,Z) view of a contiguous (N,X,Y,Z,4) array")
+        n, c, x, y, z = grid.shape
+        shape = (n, (x + 1) // 2, (y + 1) // 2, (z + 1) // 2 + 1, 64)
+        if out is None:
+            out = torch.empty(shape, dtype=dtype, device=grid.device)
+        check(lib().nrpn_pack_stem_input_u8(_ptr(grid), n, x, y, z, _ptr(out), _act16(out, "out"), _stream()), "pack_stem_input_u8")
+        return out
     if not isinstance(grid, torch.Tensor) or not grid.is_cuda or grid.dtype != torch.float32 or grid.dim() != 5:
-        raise RuntimeError("nerf_rpn_b200: grid must be a 5-D fp32 CUDA tensor")
+        raise RuntimeError("nerf_rpn_b200: grid must be a 5-D fp32 (or channels-last uint8) CUDA tensor")
     cl = is_channels_last_grid(grid)
     if not cl and not grid.is_contiguous():
         raise ValueError("nerf_rpn_b200: grid must be contiguous (N,4,X,Y,Z) or a permuted view of a contiguous (N,X,Y,Z,4) array")

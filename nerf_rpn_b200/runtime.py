@@ -39,12 +39,15 @@ class ScenePipeline:
 
     def _alloc_stage(self, sample: torch.Tensor):
         cl = sample.dim() == 4 and not sample.is_contiguous() and sample.permute(1, 2, 3, 0).is_contiguous()
+        dt = sample.dtype                   # fp32, or raw uint8 (normalised by the stem packing kernel on the device)
         if cl:
-            self.stage = [torch.empty((self.batch, *self.dims, 4), dtype=torch.float32, device=self.device).permute(0, 4, 1, 2, 3)
+            self.stage = [torch.empty((self.batch, *self.dims, 4), dtype=dt, device=self.device).permute(0, 4, 1, 2, 3)
                           for _ in range(2)]
         else:
-            self.stage = [torch.empty((self.batch, 4, *self.dims), dtype=torch.float32, device=self.device) for _ in range(2)]
+            self.stage = [torch.empty((self.batch, 4, *self.dims), dtype=dt, device=self.device) for _ in range(2)]
         self.stage_channels_last = cl
+        self.stage_dtype = dt
+        self.h2d_bytes_per_scene = 4 * self.dims[0] * self.dims[1] * self.dims[2] * sample.element_size()
 
     def _prefetch(self, slot: int, host_grids):
         with torch.cuda.stream(self.copy_stream):
@@ -66,7 +69,7 @@ class ScenePipeline:
         if nxt is None:
             return []
         cl = grids[0].dim() == 4 and not grids[0].is_contiguous() and grids[0].permute(1, 2, 3, 0).is_contiguous()
-        if self.stage is None or cl != self.stage_channels_last:
+        if self.stage is None or cl != self.stage_channels_last or grids[0].dtype != self.stage_dtype:
             self._alloc_stage(grids[0])
         for e in self.consumed:
             e.record(cur)

@@ -249,3 +249,27 @@ def test_dataset_channels_last_view_is_consumed_in_place(golden_dir):
     assert pipe.stage_channels_last
     for boxes, scores, levels in out:
         assert torch.equal(boxes, p_dense[0].cpu()) and torch.equal(scores, s_dense[0].cpu())
+
+
+def test_raw_uint8_grid_is_normalised_on_the_device(golden_dir):
+    """datasets.py:59-61: uint8 grids are normalised with .float() / 255.0 on the host. Handing the raw (4,W,L,H) uint8 view to the
+    model must give exactly the result of the host-normalised fp32 grid (same correctly rounded x / 255), through model and pipeline."""
+    from nerf_rpn_b200 import ops
+    from nerf_rpn_b200.runtime import ScenePipeline
+    g = np.load(os.path.join(golden_dir, "rpn_small_aabb.npz"))
+    model, ag = build(False, g)
+    gen = torch.Generator().manual_seed(77)
+    raw = torch.randint(0, 256, (32, 48, 40, 4), generator=gen, dtype=torch.uint8)        # (W,L,H,4) as on disk
+    view_u8 = raw.permute(3, 0, 1, 2)                                                       # what the dataset's transpose yields
+    ref_f32 = view_u8.float() / 255.0                                                       # datasets.py:59-61
+    assert torch.equal(ops.pack_stem_input(view_u8.cuda()[None]), ops.pack_stem_input(ref_f32.cuda()[None]))
+    with torch.no_grad():
+        (_, p_u8, _), _, s_u8 = model([view_u8.cuda()])
+        (_, p_f, _), _, s_f = model([ref_f32.cuda()])
+    assert torch.equal(p_u8[0], p_f[0]) and torch.equal(s_u8[0], s_f[0]) and p_u8[0].shape[0] > 0
+    pipe = ScenePipeline(model, (32, 48, 40), batch=1)
+    host = raw.pin_memory().permute(3, 0, 1, 2)
+    out = pipe.run([host, host])
+    assert pipe.stage_dtype == torch.uint8 and pipe.h2d_bytes_per_scene == 32 * 48 * 40 * 4
+    for boxes, scores, levels in out:
+        assert torch.equal(boxes, p_f[0].cpu()) and torch.equal(scores, s_f[0].cpu())
