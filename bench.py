@@ -41,8 +41,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"],
                     help="16-bit activation / weight storage; bf16 is BASELINE config 2's dtype (default), fp16 the higher-parity mode")
-    ap.add_argument("--input-layout", default="dataset", choices=["dataset", "ncdhw"],
-                    help="memory order of the fp32 input grids: the dataset's channels-last view (default) or contiguous (4,W,L,H)")
+    ap.add_argument("--input-layout", default="dataset", choices=["dataset", "ncdhw", "dataset_u8"],
+                    help="input grids: the dataset's fp32 channels-last view (default), contiguous fp32 (4,W,L,H), or the raw uint8 "
+                         "channels-last view (uint8 npz files; normalised on the device instead of by datasets.py:59-61 on the host)")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="exploration runs only: omit the ~40 s CPU port timing")
     ap.add_argument("--scenes-per-step", type=int, default=int(os.environ.get("NRPN_SCENES_PER_STEP", "4")),
                     help="scenes per rank per step (one engine launch); weights are read once per step")
@@ -248,12 +249,15 @@ def run_b200(args):
     eng = model.engine()
     B = max(1, args.scenes_per_step)
     n_pool = 4                                             # 4 x 168 MB of distinct inputs (> 126 MB L2)
-    if args.input_layout == "dataset":      # pinned (W,L,H,4) arrays, handed over as (4,W,L,H) views like the reference's dataset does
+    if args.input_layout == "dataset_u8":   # raw uint8 (W,L,H,4) arrays as stored in uint8 npz files
+        host = [(synth_scene(rank * 1000 + i, "dataset").permute(1, 2, 3, 0) * 255.0).round().to(torch.uint8).contiguous().pin_memory()
+                .permute(3, 0, 1, 2) for i in range(n_pool)]
+    elif args.input_layout == "dataset":    # pinned (W,L,H,4) arrays, handed over as (4,W,L,H) views like the reference's dataset does
         host = [synth_scene(rank * 1000 + i, "dataset").permute(1, 2, 3, 0).contiguous().pin_memory().permute(3, 0, 1, 2) for i in range(n_pool)]
     else:
         host = [synth_scene(rank * 1000 + i).pin_memory() for i in range(n_pool)]
     hdev = [h.cuda() for h in host]
-    if args.input_layout == "dataset":      # keep the (B,X,Y,Z,4) memory order: logical (B,4,X,Y,Z) views
+    if args.input_layout in ("dataset", "dataset_u8"):      # keep the (B,X,Y,Z,4) memory order: logical (B,4,X,Y,Z) views
         dev = [torch.stack([hdev[(i + b) % n_pool].permute(1, 2, 3, 0) for b in range(B)], 0).permute(0, 4, 1, 2, 3) for i in range(n_pool)]
     else:
         dev = [torch.stack([hdev[(i + b) % n_pool] for b in range(B)], 0) for i in range(n_pool)]   # (B,4,X,Y,Z) batches
@@ -340,8 +344,9 @@ def run_b200(args):
                "config": {"workload": WORKLOAD, "scenes_per_step_per_gpu": B, "parallelism": f"dp{world} (one scene per rank, no collective)",
                           "l2": "4 distinct 168 MB input grids per rank cycled (> 126 MB L2); activations stream ~1.5 GB/scene",
                           "weights": "reference init, torch.manual_seed(0)", "proposals_last_scene": count,
-                          "input_layout": "fp32 (4,W,L,H) views of (W,L,H,4) arrays, as datasets.py:55-56 yields" if args.input_layout == "dataset"
-                          else "fp32 contiguous (4,W,L,H)"},
+                          "input_layout": {"dataset": "fp32 (4,W,L,H) views of (W,L,H,4) arrays, as datasets.py:55-56 yields",
+                                           "dataset_u8": "raw uint8 (4,W,L,H) views of (W,L,H,4) arrays, normalised on the device",
+                                           "ncdhw": "fp32 contiguous (4,W,L,H)"}[args.input_layout]},
                "clocks": clocks,
                "e2e": {"value": world * K * B / (ms_e2e * 1e-3), "unit": "scenes/s", "h2d_bytes_per_step": pipe.h2d_bytes_per_scene * B,
                        "d2h_bytes_per_step": pipe.d2h_bytes_per_scene * B, "ms_per_step": ms_e2e / K,
