@@ -350,7 +350,7 @@ def run_b200(args):
                "clocks": clocks,
                "e2e": {"value": world * K * B / (ms_e2e * 1e-3), "unit": "scenes/s", "h2d_bytes_per_step": pipe.h2d_bytes_per_scene * B,
                        "d2h_bytes_per_step": pipe.d2h_bytes_per_scene * B, "ms_per_step": ms_e2e / K,
-                       "api": "nerf_rpn_b200.runtime.ScenePipeline.run (pinned host fp32 grids -> host proposals)"},
+                       "api": "nerf_rpn_b200.runtime.ScenePipeline.run (pinned host grids -> host proposals)"},
                "gpu_launches": launches_per_step * K,
                "roofline": roofline,
                "cpu_baseline": {"value": (1.0 / cpu_t) if cpu_t == cpu_t else None, "unit": "scenes/s", "cores": cores, "kind": "port",
