@@ -115,3 +115,12 @@ def pack_stem_s1_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None, d
             taps.append((dx, dyp + 1, 0))
             mats.append(m)
     return torch.stack(mats, 0).to(dtype).contiguous(), taps
+
+
+def pack_conv_weight_dgrad(w: torch.Tensor, dtype=torch.bfloat16):
+    """Data-gradient weights of a stride-1 'same' Conv3d: dL/dx = conv(dL/dy, W') with W'[ci, co, a, b, c] = W[co, ci, k-1-a, k-1-b, k-1-c]
+    (taps mirrored, matrices transposed), so the backward-data pass of every stride-1 layer runs on the SAME tcgen05 implicit-GEMM
+    kernel as the forward pass (row a18: first building block of the training path; weight gradients need a voxel-major GEMM and
+    are not built).  Returns (packed (taps, CinPad, CoutPad... as the kernel's (taps, N, K)), taps)."""
+    wt = w.detach().float().permute(1, 0, 2, 3, 4).flip(2, 3, 4).contiguous()
+    return pack_conv_weight(wt, None, dtype=dtype)

@@ -282,3 +282,25 @@ def test_tma_epilogue_matches_register_epilogue(ops, monkeypatch, dims, cin, cou
         assert (outs[0].float() - refs[0]).abs().max().item() <= 1e-2 * refs[0].abs().max().item(), _diagnose(outs[0].float(), refs[0], f"tma_epi={mode}")
         got[mode] = outs[0]
     assert torch.equal(got["1"], got["0"])
+
+
+@pytest.mark.parametrize("dims,cin,cout,k", [((9, 12, 10), 64, 128, 3), ((8, 8, 16), 256, 64, 1), ((10, 13, 9), 128, 128, 3)])
+def test_conv_data_gradient_runs_on_the_forward_kernel(ops, dims, cin, cout, k):
+    """dL/dx of a stride-1 'same' Conv3d = the same implicit GEMM with mirrored taps and transposed matrices
+    (packing.pack_conv_weight_dgrad); checked against torch.autograd on the bf16-rounded operands."""
+    from nerf_rpn_b200 import packing
+    g = torch.Generator(device="cuda").manual_seed(51)
+    w = (torch.randn((cout, cin, k, k, k), device="cuda", generator=g) / (cout * k ** 3) ** 0.5).to(torch.bfloat16).float()
+    dy = torch.randn((2, *dims, cout), device="cuda", generator=g).to(torch.bfloat16)
+    x = torch.zeros((2, cin, *dims), device="cuda", requires_grad=True)
+    y = F.conv3d(x, w, padding=k // 2)
+    (ref,) = torch.autograd.grad(y, x, dy.float().permute(0, 4, 1, 2, 3))
+    ref = ref.permute(0, 2, 3, 4, 1)
+    wp, taps = packing.pack_conv_weight_dgrad(w.cpu())
+    shift = torch.zeros(wp.shape[1], device="cuda")
+    dx = torch.full((2, *dims, cin), float("nan"), dtype=torch.float32, device="cuda")
+    a = ops.ConvLevelArgs(dy, dx, 2, dims, dims, cin)
+    ops.conv3d_fprop([a], wp.cuda(), shift, cout, cin, taps, out_fp32=True)
+    torch.cuda.synchronize()
+    assert not torch.isnan(dx).any()
+    assert (dx - ref).abs().max().item() <= 2e-3 * ref.abs().max().item(), _diagnose(dx, ref, "dgrad")
