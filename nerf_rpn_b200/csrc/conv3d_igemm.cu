@@ -12,12 +12,16 @@
 //     no im2col buffer, no index arithmetic on the SM.
 //   - N tile  = 64 / 128 / 256 output channels; W is pre-packed (tap, Cout, Cin) so a k-block of weights is a
 //     3-D TMA box {64, N, 1}.
-//   - warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one thread), warps 2-5 = epilogue.  smem ring of
-//     4-8 stages (full/empty mbarriers), accumulators double-buffered in TMEM (2 x N columns) so the epilogue of
-//     tile i overlaps the main loop of tile i+1.  Persistent CTAs (grid = #SMs) walk a static tile list that may
-//     span up to 4 pyramid levels sharing the same weights (the RPN head on P2..P5 is ONE launch per layer).
-//   - epilogue (fused): + shift (bias / folded BN), + residual (same shape, or nearest-upsampled coarser level
-//     for the FPN top-down path), ReLU, convert, 16-byte stores.
+//   - warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (converged warps, one elect.sync lane issues the async
+//     instructions), warps 2-5 = epilogue.  smem ring of 2-8 stages (full/empty mbarriers), accumulators double-buffered
+//     in TMEM (2 x N columns) so the epilogue of tile i overlaps the main loop of tile i+1.  Persistent CTAs walk a static
+//     tile list that may span up to 4 pyramid levels sharing the same weights (the RPN head on P2..P5 is ONE launch per
+//     layer).  Prologue (barriers, TMEM, tensor-map prefetch) runs ahead of griddepcontrol.wait (programmatic dependent launch).
+//   - epilogue (fused): + shift (bias / folded BN), + residual (same shape, or nearest-upsampled coarser level for the FPN
+//     top-down path), ReLU / GELU, convert to bf16 / fp16 / fp32; 256-bit register stores, or -- TMA_EPI variant of the 1^3
+//     layers -- residual tiles prefetched by TMA into shared memory and output tiles stored with cp.async.bulk.tensor.
+//   - variants: <256,4,1> <128,6,1> <64,8,1> (long reductions; <64,8,1> also for layers with fewer tiles than SMs),
+//     <64,2,3> / <64,2,2,TMA_EPI> (reductions of at most 8 k-blocks), optional split-K (NRPN_SPLITK=1, measured slower).
 #include <cstdlib>
 #include "common.cuh"
 #include "tcgen05.cuh"
