@@ -45,6 +45,18 @@ class RpnDesc(ctypes.Structure):
                 ("valid", ctypes.c_int32 * 3)]
 
 
+class WgradLevel(ctypes.Structure):
+    _fields_ = [("dy_planar", ctypes.c_void_p), ("x_planar", ctypes.c_void_p), ("n", ctypes.c_int32), ("x", ctypes.c_int32),
+                ("y", ctypes.c_int32), ("z", ctypes.c_int32)]
+
+
+class WgradDesc(ctypes.Structure):
+    _fields_ = [("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("n_taps", ctypes.c_int32),
+                ("tap_off", (ctypes.c_int8 * 3) * MAX_TAPS), ("n_levels", ctypes.c_int32), ("level", WgradLevel * MAX_LEVELS),
+                ("dw", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+                ("act_fp16", ctypes.c_int32)]
+
+
 class GnLevel(ctypes.Structure):
     _fields_ = [("x", ctypes.c_void_p), ("voxels", ctypes.c_int32)]
 
@@ -79,6 +91,10 @@ _SIGNATURES = {
     "nrpn_conv3d_variant": (ctypes.c_char_p, [ctypes.POINTER(ConvDesc)]),
     "nrpn_conv3d_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvDesc)]),
     "nrpn_conv3d_fprop": (ctypes.c_int, [ctypes.POINTER(ConvDesc), c_stream]),
+    "nrpn_conv3d_wgrad_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(WgradDesc)]),
+    "nrpn_conv3d_wgrad": (ctypes.c_int, [ctypes.POINTER(WgradDesc), c_stream]),
+    "nrpn_transpose_to_planar": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_void_p, c_stream]),
     "nrpn_pack_stem_input": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_stream]),
     "nrpn_pack_stem_input_u8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

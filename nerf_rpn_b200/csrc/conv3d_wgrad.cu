@@ -1,0 +1,281 @@
+// Weight gradient of a stride-1 'same' 3-D convolution on tcgen05 (training building block):
+//     dW[tap][co][ci] = sum over voxels v   dY[v][co] * X[v + tap_offset][ci]
+// The contraction runs over VOXELS, but activations are channels-last (a voxel's channels are contiguous), i.e. both operands
+// would be MN-major.  Instead of MN-major descriptors the two tensors are first transposed to a planar (N, C, X, Y, Z) layout
+// by a bandwidth kernel; then one 5-D TMA box {bz, by, bx, channels, 1} of 64 voxels lands in shared memory as `channels` rows
+// of 128 bytes in exactly the 128B-swizzled K-major layout every other kernel of this library feeds to tcgen05.mma:
+//     A = dY^T brick (128 output channels x 64 voxels),  B = X^T brick shifted by the tap (N_T input channels x 64 voxels),
+//     D (128 x N_T, fp32 in TMEM) += A * B^T      -- out-of-range voxels are zero-filled by TMA (= the convolution padding).
+// Work item = (tap, 128-channel slice of Cout, K-split); every item streams its share of the voxel bricks of all pyramid
+// levels (levels that share the weights, e.g. the RPN head on P2..P5) and writes one fp32 partial tile; a second kernel sums
+// the partial tiles in a fixed order (bit-reproducible) into dW (taps, Cout, Cin) fp32.
+#include <cstdlib>
+#include <cstring>
+#include "common.cuh"
+#include "tcgen05.cuh"
+#include "conv_internal.cuh"
+
+namespace nrpn {
+
+constexpr int kWgStages = 4;
+constexpr int kWgABytes = 128 * 128;            // 128 output channels x 64 voxels x 2 B
+constexpr int kWgThreads = 192;
+
+struct WgLevelDev { int n, tx, ty, tz, bx, by, bz, brick_begin; };
+
+struct WgDev {
+    int n_levels, n_taps, cin, cout, n_t, m_tiles, splits, total_bricks, fp16;
+    signed char tap[NRPN_CONV_MAX_TAPS][4];
+    WgLevelDev lv[NRPN_CONV_MAX_LEVELS];
+    float* partial;                            // [tap][m_tile][split][128][n_t]
+};
+
+struct WgMaps { CUtensorMap dy[NRPN_CONV_MAX_LEVELS]; CUtensorMap x[NRPN_CONV_MAX_LEVELS]; };
+
+__global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgDev P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_bytes = P.n_t * 128;
+    const int stage_bytes = kWgABytes + b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kWgStages;
+    uint64_t* tfull_bar = bars + 2 * kWgStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWgStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::fence_barrier_init();
+        for (int l = 0; l < P.n_levels; ++l) { ptx::prefetch_tmap(&maps.dy[l]); ptx::prefetch_tmap(&maps.x[l]); }
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t idesc = P.fp16 ? ptx::make_idesc_f16(128, P.n_t) : ptx::make_idesc_bf16(128, P.n_t);
+    const int items = P.n_taps * P.m_tiles * P.splits;
+    uint32_t tphase = 0;
+    int stage_p = 0, stage_c = 0; uint32_t phase_p = 0, phase_c = 0;          // producer / consumer ring positions (persist over items)
+
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int split = item % P.splits;
+        const int mt = (item / P.splits) % P.m_tiles;
+        const int tap = item / (P.splits * P.m_tiles);
+        const int b0 = (int)(((long)P.total_bricks * split) / P.splits), b1 = (int)(((long)P.total_bricks * (split + 1)) / P.splits);
+        if (warp == 0) {
+            const bool leader = ptx::elect_one();
+            const int dx = P.tap[tap][0], dy = P.tap[tap][1], dz = P.tap[tap][2];
+            for (int b = b0; b < b1; ++b) {
+                int l = 0;
+#pragma unroll
+                for (int i = 1; i < NRPN_CONV_MAX_LEVELS; ++i) if (i < P.n_levels && b >= P.lv[i].brick_begin) l = i;
+                const WgLevelDev& L = P.lv[l];
+                int t = b - L.brick_begin;
+                const int tiz = t % L.tz; t /= L.tz;
+                const int tiy = t % L.ty; t /= L.ty;
+                const int tix = t % L.tx; const int nb = t / L.tx;
+                const int x0 = tix * L.bx, y0 = tiy * L.by, z0 = tiz * L.bz;
+                ptx::mbar_wait(&empty_bar[stage_p], phase_p ^ 1u);
+                if (leader) {
+                    uint8_t* sa = smem + stage_p * stage_bytes;
+                    ptx::mbar_expect_tx(&full_bar[stage_p], (uint32_t)stage_bytes);
+                    ptx::tma_load_5d(sa, &maps.dy[l], &full_bar[stage_p], z0, y0, x0, mt * 128, nb);
+                    ptx::tma_load_5d(sa + kWgABytes, &maps.x[l], &full_bar[stage_p], z0 + dz, y0 + dy, x0 + dx, 0, nb);
+                }
+                __syncwarp();
+                if (++stage_p == kWgStages) { stage_p = 0; phase_p ^= 1u; }
+            }
+        } else if (warp == 1) {
+            const bool leader = ptx::elect_one();
+            for (int b = b0; b < b1; ++b) {
+                ptx::mbar_wait(&full_bar[stage_c], phase_c);
+                ptx::tc_fence_after();
+                const uint32_t sa = ptx::smem_u32(smem + stage_c * stage_bytes);
+                const uint64_t da = ptx::make_desc_sw128(sa), db = ptx::make_desc_sw128(sa + kWgABytes);
+                if (leader) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_bf16(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, ((b - b0) | k) ? 1u : 0u);
+                    ptx::umma_commit(&empty_bar[stage_c]);
+                }
+                __syncwarp();
+                if (++stage_c == kWgStages) { stage_c = 0; phase_c ^= 1u; }
+            }
+            if (leader) ptx::umma_commit(tfull_bar);
+            __syncwarp();
+        } else {
+            // epilogue warps 2..5: row = output channel of the slice, columns = input channels
+            const int q = warp & 3, row = q * 32 + lane;
+            float* out = P.partial + ((((size_t)tap * P.m_tiles + mt) * P.splits + split) * 128 + row) * P.n_t;
+            ptx::mbar_wait(tfull_bar, tphase);
+            ptx::tc_fence_after();
+            const bool empty = (b1 <= b0);                               // nothing accumulated: the TMEM contents are stale
+            for (int c = 0; c < P.n_t; c += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(out + c + j) = empty ? make_float4(0.f, 0.f, 0.f, 0.f)
+                        : make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+            ptx::tc_fence_before();
+        }
+        tphase ^= 1u;
+        __syncthreads();            // the accumulator is drained before the next item's first MMA overwrites it
+        ptx::tc_fence_after();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
+}
+
+// dW[tap][co][ci] = sum over splits (fixed order) of the partial tiles
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_taps, int m_tiles, int splits, int n_t, int cout, int cin,
+                                    float* __restrict__ dw) {
+    const size_t total = (size_t)n_taps * cout * cin;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(t % cin); size_t v = t / cin;
+        const int co = (int)(v % cout); const int tap = (int)(v / cout);
+        const int mt = co >> 7, row = co & 127;
+        const float* p = partial + ((((size_t)tap * m_tiles + mt) * splits) * 128 + row) * n_t + ci;
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += p[(size_t)sp * 128 * n_t];
+        dw[t] = s;
+    }
+}
+
+// channels-last (N, V, C) -> planar (N, C, V), 16-bit elements, 64 x 64 tiles through shared memory
+__global__ void __launch_bounds__(256) cl_to_planar_kernel(const uint16_t* __restrict__ in, int ld, int C, long V, uint16_t* __restrict__ out) {
+    __shared__ uint16_t tile[64][66];
+    const long v0 = (long)blockIdx.x * 64;
+    const int c0 = blockIdx.y * 64, nb = blockIdx.z;
+    const uint16_t* src = in + (size_t)nb * V * ld;
+    uint16_t* dst = out + (size_t)nb * C * V;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int v = i >> 6, c = i & 63;
+        tile[v][c] = (v0 + v < V && c0 + c < C) ? src[(size_t)(v0 + v) * ld + c0 + c] : (uint16_t)0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int c = i >> 6, v = i & 63;
+        if (v0 + v < V && c0 + c < C) dst[(size_t)(c0 + c) * V + v0 + v] = tile[v][c];
+    }
+}
+
+static void wg_brick(int X, int Y, int Z, int& bx, int& by, int& bz) {
+    // 64 voxels with at least 8 along z (the TMA inner dimension must span >= 16 bytes)
+    bz = Z >= 16 && Z % 16 == 0 ? 16 : 8;
+    const int rest = 64 / bz;
+    by = 1;
+    while (by * 2 <= rest && by * 2 <= (Y > 1 ? Y : 1) * 2 && by < 4) by *= 2;
+    bx = rest / by;
+    (void)X;
+}
+
+}  // namespace nrpn
+
+using namespace nrpn;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int nrpn_transpose_to_planar(const void* in_cl, int n, long voxels, int c, int ld, void* out_planar, nrpn_stream_t stream) {
+    if (!in_cl || !out_planar || n < 1 || voxels < 1 || c < 1 || ld < c) return NRPN_ERR_INVALID;
+    dim3 grid((unsigned)ceil_div(voxels, 64L), (unsigned)ceil_div(c, 64), (unsigned)n);
+    if (grid.y > 65535 || grid.z > 65535) return NRPN_ERR_UNSUPPORTED;
+    cl_to_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint16_t*>(in_cl), ld, c, voxels,
+                                                               reinterpret_cast<uint16_t*>(out_planar));
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+static int wgrad_plan(const nrpn_wgrad_desc* d, WgDev& P) {
+    if (!d || d->n_levels < 1 || d->n_levels > NRPN_CONV_MAX_LEVELS || d->n_taps < 1 || d->n_taps > NRPN_CONV_MAX_TAPS) return NRPN_ERR_INVALID;
+    if (d->cout < 128 || d->cout % 128 != 0 || d->cin < 32 || d->cin > 256 || d->cin % 32 != 0) return NRPN_ERR_UNSUPPORTED;
+    memset(&P, 0, sizeof(P));
+    P.n_levels = d->n_levels; P.n_taps = d->n_taps; P.cin = d->cin; P.cout = d->cout; P.n_t = d->cin; P.m_tiles = d->cout / 128;
+    P.fp16 = d->act_fp16 ? 1 : 0;
+    for (int t = 0; t < d->n_taps; ++t) { P.tap[t][0] = d->tap_off[t][0]; P.tap[t][1] = d->tap_off[t][1]; P.tap[t][2] = d->tap_off[t][2]; P.tap[t][3] = 0; }
+    int bricks = 0;
+    for (int l = 0; l < d->n_levels; ++l) {
+        const nrpn_wgrad_level& S = d->level[l];
+        if (S.n < 1 || S.x < 1 || S.y < 1 || S.z < 1) return NRPN_ERR_INVALID;
+        WgLevelDev& L = P.lv[l];
+        wg_brick(S.x, S.y, S.z, L.bx, L.by, L.bz);
+        L.n = S.n; L.tx = ceil_div(S.x, L.bx); L.ty = ceil_div(S.y, L.by); L.tz = ceil_div(S.z, L.bz);
+        L.brick_begin = bricks;
+        bricks += S.n * L.tx * L.ty * L.tz;
+    }
+    P.total_bricks = bricks;
+    const int base = d->n_taps * P.m_tiles;
+    int splits = ceil_div(num_sms(), base);
+    if (splits > bricks) splits = bricks;
+    if (splits < 1) splits = 1;
+    P.splits = splits;
+    return NRPN_OK;
+}
+
+size_t nrpn_conv3d_wgrad_workspace_bytes(const nrpn_wgrad_desc* d) {
+    WgDev P;
+    if (wgrad_plan(d, P) != NRPN_OK) return 0;
+    return (size_t)P.n_taps * P.m_tiles * P.splits * 128 * P.n_t * sizeof(float) + 256;
+}
+
+int nrpn_conv3d_wgrad(const nrpn_wgrad_desc* d, nrpn_stream_t stream) {
+    WgDev P;
+    { const int rc = wgrad_plan(d, P); if (rc) return rc; }
+    if (!d->dw || !d->workspace || d->workspace_bytes < nrpn_conv3d_wgrad_workspace_bytes(d)) return NRPN_ERR_WORKSPACE;
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return NRPN_ERR_NO_DEVICE;
+    WgMaps maps;
+    for (int l = 0; l < d->n_levels; ++l) {
+        const nrpn_wgrad_level& S = d->level[l];
+        if (!S.dy_planar || !S.x_planar) return NRPN_ERR_INVALID;
+        const WgLevelDev& L = P.lv[l];
+        const cuuint64_t X = S.x, Y = S.y, Z = S.z;
+        cuuint32_t one[5] = {1, 1, 1, 1, 1};
+        {
+            cuuint64_t gdim[5] = {Z, Y, X, (cuuint64_t)d->cout, (cuuint64_t)S.n};
+            cuuint64_t gstr[4] = {Z * 2, Y * Z * 2, X * Y * Z * 2, X * Y * Z * 2 * (cuuint64_t)d->cout};
+            cuuint32_t box[5] = {(cuuint32_t)L.bz, (cuuint32_t)L.by, (cuuint32_t)L.bx, 128, 1};
+            CUresult r = encode(&maps.dy[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(S.dy_planar), gdim, gstr, box, one,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return NRPN_ERR_CUDA; }
+        }
+        {
+            cuuint64_t gdim[5] = {Z, Y, X, (cuuint64_t)d->cin, (cuuint64_t)S.n};
+            cuuint64_t gstr[4] = {Z * 2, Y * Z * 2, X * Y * Z * 2, X * Y * Z * 2 * (cuuint64_t)d->cin};
+            cuuint32_t box[5] = {(cuuint32_t)L.bz, (cuuint32_t)L.by, (cuuint32_t)L.bx, (cuuint32_t)P.n_t, 1};
+            CUresult r = encode(&maps.x[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(S.x_planar), gdim, gstr, box, one,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return NRPN_ERR_CUDA; }
+        }
+    }
+    for (int l = d->n_levels; l < NRPN_CONV_MAX_LEVELS; ++l) { maps.dy[l] = maps.dy[0]; maps.x[l] = maps.x[0]; }
+    P.partial = reinterpret_cast<float*>(align_up((size_t)d->workspace, 256));
+    const int smem = kWgStages * (kWgABytes + P.n_t * 128) + 1024 + 256;
+    static int smem_set = 0;
+    if (smem > smem_set) {
+        NRPN_CUDA_TRY(cudaFuncSetAttribute(conv3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set = smem;
+    }
+    const int items = P.n_taps * P.m_tiles * P.splits;
+    const int grid = items < num_sms() ? items : num_sms();
+    cudaStream_t st = (cudaStream_t)stream;
+    conv3d_wgrad_kernel<<<grid, kWgThreads, smem, st>>>(maps, P);
+    NRPN_LAUNCH_CHECK();
+    const size_t total = (size_t)P.n_taps * P.cout * P.cin;
+    size_t blocks = ceil_div(total, (size_t)256);
+    if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
+    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(P.partial, P.n_taps, P.m_tiles, P.splits, P.n_t, P.cout, P.cin, d->dw);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -7,7 +7,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, FcosDesc, GnLevel, RpnDesc, check, lib
+from ._lib import WgradDesc, ConvDesc, FcosDesc, GnLevel, RpnDesc, check, lib
 
 
 def _stream():
@@ -217,6 +217,42 @@ def _act16(t: torch.Tensor, name: str) -> int:
 def is_channels_last_grid(grid: torch.Tensor) -> bool:
     """True for an (N,4,X,Y,Z) tensor whose memory is (N,X,Y,Z,4): what datasets.py:55-56 produces (np.transpose view)."""
     return grid.dim() == 5 and not grid.is_contiguous() and grid.permute(0, 2, 3, 4, 1).is_contiguous()
+
+
+def to_planar(x: torch.Tensor) -> torch.Tensor:
+    """(N, X, Y, Z, ld) 16-bit channels-last -> (N, ld, X, Y, Z) planar (the operand layout of conv3d_wgrad)."""
+    _act16(x, "x")
+    n, X, Y, Z, c = x.shape
+    out = torch.empty((n, c, X, Y, Z), dtype=x.dtype, device=x.device)
+    check(lib().nrpn_transpose_to_planar(_ptr(x), n, X * Y * Z, c, c, _ptr(out), _stream()), "transpose_to_planar")
+    return out
+
+
+def conv3d_wgrad(dys: Sequence[torch.Tensor], xs: Sequence[torch.Tensor], taps: Sequence[Sequence[int]]) -> torch.Tensor:
+    """dW (taps, Cout, Cin) fp32 of a stride-1 conv from planar (N,C,X,Y,Z) 16-bit dY / X tensors, one pair per pyramid level
+    that shares the weights."""
+    d = WgradDesc()
+    d.cout, d.cin, d.n_taps = int(dys[0].shape[1]), int(xs[0].shape[1]), len(taps)
+    for t, off in enumerate(taps):
+        for k in range(3):
+            d.tap_off[t][k] = int(off[k])
+    d.n_levels = len(dys)
+    for i, (dy, x) in enumerate(zip(dys, xs)):
+        f16 = _act16(dy, "dy"); _act16(x, "x")
+        if dy.dtype != x.dtype or dy.shape[0] != x.shape[0] or dy.shape[2:] != x.shape[2:]:
+            raise ValueError("conv3d_wgrad: dy and x must share dtype, batch and spatial extent (stride-1 'same' convolution)")
+        lv = d.level[i]
+        lv.dy_planar, lv.x_planar = dy.data_ptr(), x.data_ptr()
+        lv.n, lv.x, lv.y, lv.z = int(dy.shape[0]), int(dy.shape[2]), int(dy.shape[3]), int(dy.shape[4])
+    d.act_fp16 = f16
+    dw = torch.empty((len(taps), d.cout, d.cin), dtype=torch.float32, device=dys[0].device)
+    need = lib().nrpn_conv3d_wgrad_workspace_bytes(ctypes.byref(d))
+    if need == 0:
+        raise ValueError("conv3d_wgrad: unsupported shape (cout % 128 == 0, cin % 32 == 0, cin <= 256)")
+    ws = _workspace(need, dys[0].device)
+    d.dw, d.workspace, d.workspace_bytes = dw.data_ptr(), ws.data_ptr(), ws.numel()
+    check(lib().nrpn_conv3d_wgrad(ctypes.byref(d), _stream()), "conv3d_wgrad")
+    return dw
 
 
 def pack_stem_input(grid: torch.Tensor, out: Optional[torch.Tensor] = None, dtype=torch.bfloat16) -> torch.Tensor:
