@@ -279,13 +279,14 @@ int nrpn_assign_targets(const float *anchors, int n_anchors, const float *gt, in
 
 /* ------------------------------------------------------------------------------------------------ weight gradient
  * dW[tap][co][ci] = sum_v dY[v][co] * X[v + tap_off][ci] of a stride-1 convolution (training) on tcgen05.
- * Both operands are read in PLANAR layout (N, C, X, Y, Z), 16-bit (nrpn_transpose_to_planar converts a channels-last tensor);
+ * Both operands are read in PLANAR layout (N, C, X, Y, z_pitch), 16-bit (nrpn_transpose_to_planar converts a channels-last tensor);
  * levels that share the weights (RPN head on P2..P5) accumulate into the same dW.  dw: fp32 (taps, cout, cin), overwritten.
  * cout % 128 == 0; cin % 32 == 0, cin <= 256.  Deterministic (fixed-order reduction of the K-split partial tiles). */
 typedef struct {
-    const void *dy_planar;   /* (N, cout, X, Y, Z) bf16 / fp16 */
-    const void *x_planar;    /* (N, cin,  X, Y, Z) bf16 / fp16 */
+    const void *dy_planar;   /* (N, cout, X, Y, z_pitch) bf16 / fp16 */
+    const void *x_planar;    /* (N, cin,  X, Y, z_pitch) bf16 / fp16 */
     int32_t n, x, y, z;
+    int32_t z_pitch;         /* >= z, multiple of 8 (16-byte TMA strides); the pad is never read */
 } nrpn_wgrad_level;
 
 typedef struct {
@@ -301,8 +302,9 @@ typedef struct {
 
 size_t nrpn_conv3d_wgrad_workspace_bytes(const nrpn_wgrad_desc *desc /*host*/);
 int nrpn_conv3d_wgrad(const nrpn_wgrad_desc *desc /*host*/, nrpn_stream_t stream);
-/* channels-last (N, voxels, ld >= c) 16-bit -> planar (N, c, voxels) */
-int nrpn_transpose_to_planar(const void *in_cl, int n, long voxels, int c, int ld, void *out_planar, nrpn_stream_t stream);
+/* channels-last (N, X, Y, Z, ld >= c) 16-bit -> planar (N, c, X, Y, z_pitch >= Z) */
+int nrpn_transpose_to_planar(const void *in_cl, int n, int x, int y, int z, int c, int ld, void *out_planar, int z_pitch,
+                             nrpn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -147,13 +147,16 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_tap
     }
 }
 
-// channels-last (N, V, C) -> planar (N, C, V), 16-bit elements, 64 x 64 tiles through shared memory
-__global__ void __launch_bounds__(256) cl_to_planar_kernel(const uint16_t* __restrict__ in, int ld, int C, long V, uint16_t* __restrict__ out) {
+// channels-last (N, X*Y*Z, ld) -> planar (N, C, X*Y, Zp) with Zp = z pitch >= Z (a multiple of 8 so that every TMA stride is a
+// multiple of 16 bytes; the pad is never read: the tensor maps carry the logical Z), 16-bit elements, 64 x 64 tiles through smem
+__global__ void __launch_bounds__(256) cl_to_planar_kernel(const uint16_t* __restrict__ in, int ld, int C, long V, int Z, int Zp,
+                                                           uint16_t* __restrict__ out) {
     __shared__ uint16_t tile[64][66];
     const long v0 = (long)blockIdx.x * 64;
     const int c0 = blockIdx.y * 64, nb = blockIdx.z;
     const uint16_t* src = in + (size_t)nb * V * ld;
-    uint16_t* dst = out + (size_t)nb * C * V;
+    const size_t plane = (size_t)(V / Z) * Zp;
+    uint16_t* dst = out + (size_t)nb * C * plane;
     for (int i = threadIdx.x; i < 64 * 64; i += 256) {
         const int v = i >> 6, c = i & 63;
         tile[v][c] = (v0 + v < V && c0 + c < C) ? src[(size_t)(v0 + v) * ld + c0 + c] : (uint16_t)0;
@@ -161,7 +164,10 @@ __global__ void __launch_bounds__(256) cl_to_planar_kernel(const uint16_t* __res
     __syncthreads();
     for (int i = threadIdx.x; i < 64 * 64; i += 256) {
         const int c = i >> 6, v = i & 63;
-        if (v0 + v < V && c0 + c < C) dst[(size_t)(c0 + c) * V + v0 + v] = tile[v][c];
+        if (v0 + v < V && c0 + c < C) {
+            const long vv = v0 + v;
+            dst[(size_t)(c0 + c) * plane + (size_t)(vv / Z) * Zp + (vv % Z)] = tile[v][c];
+        }
     }
 }
 
@@ -182,11 +188,13 @@ using namespace nrpn;
 extern "C" {
 #pragma GCC visibility push(default)
 
-int nrpn_transpose_to_planar(const void* in_cl, int n, long voxels, int c, int ld, void* out_planar, nrpn_stream_t stream) {
-    if (!in_cl || !out_planar || n < 1 || voxels < 1 || c < 1 || ld < c) return NRPN_ERR_INVALID;
+int nrpn_transpose_to_planar(const void* in_cl, int n, int x, int y, int z, int c, int ld, void* out_planar, int z_pitch,
+                             nrpn_stream_t stream) {
+    if (!in_cl || !out_planar || n < 1 || x < 1 || y < 1 || z < 1 || c < 1 || ld < c || z_pitch < z) return NRPN_ERR_INVALID;
+    const long voxels = (long)x * y * z;
     dim3 grid((unsigned)ceil_div(voxels, 64L), (unsigned)ceil_div(c, 64), (unsigned)n);
     if (grid.y > 65535 || grid.z > 65535) return NRPN_ERR_UNSUPPORTED;
-    cl_to_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint16_t*>(in_cl), ld, c, voxels,
+    cl_to_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint16_t*>(in_cl), ld, c, voxels, z, z_pitch,
                                                                reinterpret_cast<uint16_t*>(out_planar));
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
@@ -202,7 +210,7 @@ static int wgrad_plan(const nrpn_wgrad_desc* d, WgDev& P) {
     int bricks = 0;
     for (int l = 0; l < d->n_levels; ++l) {
         const nrpn_wgrad_level& S = d->level[l];
-        if (S.n < 1 || S.x < 1 || S.y < 1 || S.z < 1) return NRPN_ERR_INVALID;
+        if (S.n < 1 || S.x < 1 || S.y < 1 || S.z < 1 || S.z_pitch < S.z || S.z_pitch % 8 != 0) return NRPN_ERR_INVALID;
         WgLevelDev& L = P.lv[l];
         wg_brick(S.x, S.y, S.z, L.bx, L.by, L.bz);
         L.n = S.n; L.tx = ceil_div(S.x, L.bx); L.ty = ceil_div(S.y, L.by); L.tz = ceil_div(S.z, L.bz);
@@ -211,7 +219,7 @@ static int wgrad_plan(const nrpn_wgrad_desc* d, WgDev& P) {
     }
     P.total_bricks = bricks;
     const int base = d->n_taps * P.m_tiles;
-    int splits = ceil_div(num_sms(), base);
+    int splits = num_sms() / base;                      // one wave of work items: (taps x Cout slices x splits) <= SMs
     if (splits > bricks) splits = bricks;
     if (splits < 1) splits = 1;
     P.splits = splits;
@@ -235,11 +243,11 @@ int nrpn_conv3d_wgrad(const nrpn_wgrad_desc* d, nrpn_stream_t stream) {
         const nrpn_wgrad_level& S = d->level[l];
         if (!S.dy_planar || !S.x_planar) return NRPN_ERR_INVALID;
         const WgLevelDev& L = P.lv[l];
-        const cuuint64_t X = S.x, Y = S.y, Z = S.z;
+        const cuuint64_t X = S.x, Y = S.y, Z = S.z, Zp = S.z_pitch;
         cuuint32_t one[5] = {1, 1, 1, 1, 1};
         {
             cuuint64_t gdim[5] = {Z, Y, X, (cuuint64_t)d->cout, (cuuint64_t)S.n};
-            cuuint64_t gstr[4] = {Z * 2, Y * Z * 2, X * Y * Z * 2, X * Y * Z * 2 * (cuuint64_t)d->cout};
+            cuuint64_t gstr[4] = {Zp * 2, Y * Zp * 2, X * Y * Zp * 2, X * Y * Zp * 2 * (cuuint64_t)d->cout};
             cuuint32_t box[5] = {(cuuint32_t)L.bz, (cuuint32_t)L.by, (cuuint32_t)L.bx, 128, 1};
             CUresult r = encode(&maps.dy[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(S.dy_planar), gdim, gstr, box, one,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -248,7 +256,7 @@ int nrpn_conv3d_wgrad(const nrpn_wgrad_desc* d, nrpn_stream_t stream) {
         }
         {
             cuuint64_t gdim[5] = {Z, Y, X, (cuuint64_t)d->cin, (cuuint64_t)S.n};
-            cuuint64_t gstr[4] = {Z * 2, Y * Z * 2, X * Y * Z * 2, X * Y * Z * 2 * (cuuint64_t)d->cin};
+            cuuint64_t gstr[4] = {Zp * 2, Y * Zp * 2, X * Y * Zp * 2, X * Y * Zp * 2 * (cuuint64_t)d->cin};
             cuuint32_t box[5] = {(cuuint32_t)L.bz, (cuuint32_t)L.by, (cuuint32_t)L.bx, (cuuint32_t)P.n_t, 1};
             CUresult r = encode(&maps.x[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(S.x_planar), gdim, gstr, box, one,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -220,12 +220,14 @@ def is_channels_last_grid(grid: torch.Tensor) -> bool:
 
 
 def to_planar(x: torch.Tensor) -> torch.Tensor:
-    """(N, X, Y, Z, ld) 16-bit channels-last -> (N, ld, X, Y, Z) planar (the operand layout of conv3d_wgrad)."""
+    """(N, X, Y, Z, ld) 16-bit channels-last -> planar (N, ld, X, Y, Z) VIEW of a buffer whose z pitch is rounded up to a multiple
+    of 8 (16-byte TMA strides): the operand layout of conv3d_wgrad."""
     _act16(x, "x")
     n, X, Y, Z, c = x.shape
-    out = torch.empty((n, c, X, Y, Z), dtype=x.dtype, device=x.device)
-    check(lib().nrpn_transpose_to_planar(_ptr(x), n, X * Y * Z, c, c, _ptr(out), _stream()), "transpose_to_planar")
-    return out
+    zp = (Z + 7) // 8 * 8
+    buf = torch.zeros((n, c, X, Y, zp), dtype=x.dtype, device=x.device)
+    check(lib().nrpn_transpose_to_planar(_ptr(x), n, X, Y, Z, c, c, _ptr(buf), zp, _stream()), "transpose_to_planar")
+    return buf[..., :Z]
 
 
 def conv3d_wgrad(dys: Sequence[torch.Tensor], xs: Sequence[torch.Tensor], taps: Sequence[Sequence[int]]) -> torch.Tensor:
@@ -242,8 +244,11 @@ def conv3d_wgrad(dys: Sequence[torch.Tensor], xs: Sequence[torch.Tensor], taps: 
         if dy.dtype != x.dtype or dy.shape[0] != x.shape[0] or dy.shape[2:] != x.shape[2:]:
             raise ValueError("conv3d_wgrad: dy and x must share dtype, batch and spatial extent (stride-1 'same' convolution)")
         lv = d.level[i]
+        if dy.stride(-1) != 1 or x.stride(-1) != 1 or dy.stride(3) != x.stride(3) or dy.stride(3) % 8 != 0:
+            raise ValueError("conv3d_wgrad: operands must come from ops.to_planar (z pitch a multiple of 8)")
         lv.dy_planar, lv.x_planar = dy.data_ptr(), x.data_ptr()
         lv.n, lv.x, lv.y, lv.z = int(dy.shape[0]), int(dy.shape[2]), int(dy.shape[3]), int(dy.shape[4])
+        lv.z_pitch = int(dy.stride(3))
     d.act_fp16 = f16
     dw = torch.empty((len(taps), d.cout, d.cin), dtype=torch.float32, device=dys[0].device)
     need = lib().nrpn_conv3d_wgrad_workspace_bytes(ctypes.byref(d))
