@@ -240,7 +240,9 @@ def conv3d_wgrad(dys: Sequence[torch.Tensor], xs: Sequence[torch.Tensor], taps: 
             d.tap_off[t][k] = int(off[k])
     d.n_levels = len(dys)
     for i, (dy, x) in enumerate(zip(dys, xs)):
-        f16 = _act16(dy, "dy"); _act16(x, "x")
+        if not (dy.is_cuda and x.is_cuda) or dy.dtype not in (torch.bfloat16, torch.float16):
+            raise TypeError("conv3d_wgrad: operands must be bf16 / fp16 CUDA tensors")
+        f16 = 1 if dy.dtype == torch.float16 else 0
         if dy.dtype != x.dtype or dy.shape[0] != x.shape[0] or dy.shape[2:] != x.shape[2:]:
             raise ValueError("conv3d_wgrad: dy and x must share dtype, batch and spatial extent (stride-1 'same' convolution)")
         lv = d.level[i]
