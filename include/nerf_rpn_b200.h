@@ -286,7 +286,7 @@ typedef struct {
     const void *dy_planar;   /* (N, cout, X, Y, z_pitch) bf16 / fp16 */
     const void *x_planar;    /* (N, cin,  X, Y, z_pitch) bf16 / fp16 */
     int32_t n, x, y, z;
-    int32_t z_pitch;         /* >= z, multiple of 8 (16-byte TMA strides); the pad is never read */
+    int32_t z_pitch;         /* >= z + 1, multiple of 8; the pad columns MUST be zero (they are the convolution's z padding) */
 } nrpn_wgrad_level;
 
 typedef struct {
@@ -302,7 +302,8 @@ typedef struct {
 
 size_t nrpn_conv3d_wgrad_workspace_bytes(const nrpn_wgrad_desc *desc /*host*/);
 int nrpn_conv3d_wgrad(const nrpn_wgrad_desc *desc /*host*/, nrpn_stream_t stream);
-/* channels-last (N, X, Y, Z, ld >= c) 16-bit -> planar (N, c, X, Y, z_pitch >= Z) */
+/* channels-last (N, X, Y, Z, ld >= c) 16-bit -> planar (N, c, X, Y, z_pitch >= Z); columns [Z, z_pitch) are left untouched
+ * (pre-zero the buffer once) */
 int nrpn_transpose_to_planar(const void *in_cl, int n, int x, int y, int z, int c, int ld, void *out_planar, int z_pitch,
                              nrpn_stream_t stream);
 

@@ -2,8 +2,11 @@
 //     dW[tap][co][ci] = sum over voxels v   dY[v][co] * X[v + tap_offset][ci]
 // The contraction runs over VOXELS, but activations are channels-last (a voxel's channels are contiguous), i.e. both operands
 // would be MN-major.  Instead of MN-major descriptors the two tensors are first transposed to a planar (N, C, X, Y, Z) layout
-// by a bandwidth kernel; then one 5-D TMA box {bz, by, bx, channels, 1} of 64 voxels lands in shared memory as `channels` rows
-// of 128 bytes in exactly the 128B-swizzled K-major layout every other kernel of this library feeds to tcgen05.mma:
+// (z pitch padded with at least one ZERO column) by a bandwidth kernel.  The (y, z) plane is then addressed as ONE flattened axis
+// of Y * z_pitch elements: a TMA box {64 flattened voxels, 1 x, channels, 1} lands in shared memory as `channels` rows of exactly
+// 128 bytes -- the 128B-swizzled K-major layout every other kernel of this library feeds to tcgen05.mma (an inner box narrower
+// than the swizzle span is NOT laid out densely by TMA, hence 64 contiguous elements).  A tap shift (dy, dz) is the flattened
+// offset dy * z_pitch + dz; stepping off a row's end lands in the zero pad column, stepping off the plane is TMA's zero fill:
 //     A = dY^T brick (128 output channels x 64 voxels),  B = X^T brick shifted by the tap (N_T input channels x 64 voxels),
 //     D (128 x N_T, fp32 in TMEM) += A * B^T      -- out-of-range voxels are zero-filled by TMA (= the convolution padding).
 // Work item = (tap, 128-channel slice of Cout, K-split); every item streams its share of the voxel bricks of all pyramid
@@ -21,7 +24,7 @@ constexpr int kWgStages = 4;
 constexpr int kWgABytes = 128 * 128;            // 128 output channels x 64 voxels x 2 B
 constexpr int kWgThreads = 192;
 
-struct WgLevelDev { int n, tx, ty, tz, bx, by, bz, brick_begin; };
+struct WgLevelDev { int n, X, chunks, zp, brick_begin; };      // chunks = ceil(Y * zp / 64) K-blocks per x-plane
 
 struct WgDev {
     int n_levels, n_taps, cin, cout, n_t, m_tiles, splits, total_bricks, fp16;
@@ -73,16 +76,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_kernel(const __gri
                 for (int i = 1; i < NRPN_CONV_MAX_LEVELS; ++i) if (i < P.n_levels && b >= P.lv[i].brick_begin) l = i;
                 const WgLevelDev& L = P.lv[l];
                 int t = b - L.brick_begin;
-                const int tiz = t % L.tz; t /= L.tz;
-                const int tiy = t % L.ty; t /= L.ty;
-                const int tix = t % L.tx; const int nb = t / L.tx;
-                const int x0 = tix * L.bx, y0 = tiy * L.by, z0 = tiz * L.bz;
+                const int ck = t % L.chunks; t /= L.chunks;
+                const int x0 = t % L.X; const int nb = t / L.X;
+                const int f0 = ck * 64;                                      // position on the flattened (y, z-with-pad) axis
                 ptx::mbar_wait(&empty_bar[stage_p], phase_p ^ 1u);
                 if (leader) {
                     uint8_t* sa = smem + stage_p * stage_bytes;
                     ptx::mbar_expect_tx(&full_bar[stage_p], (uint32_t)stage_bytes);
-                    ptx::tma_load_5d(sa, &maps.dy[l], &full_bar[stage_p], z0, y0, x0, mt * 128, nb);
-                    ptx::tma_load_5d(sa + kWgABytes, &maps.x[l], &full_bar[stage_p], z0 + dz, y0 + dy, x0 + dx, 0, nb);
+                    ptx::tma_load_4d(sa, &maps.dy[l], &full_bar[stage_p], f0, x0, mt * 128, nb);
+                    ptx::tma_load_4d(sa + kWgABytes, &maps.x[l], &full_bar[stage_p], f0 + dy * L.zp + dz, x0 + dx, 0, nb);
                 }
                 __syncwarp();
                 if (++stage_p == kWgStages) { stage_p = 0; phase_p ^= 1u; }
@@ -171,16 +173,6 @@ __global__ void __launch_bounds__(256) cl_to_planar_kernel(const uint16_t* __res
     }
 }
 
-static void wg_brick(int X, int Y, int Z, int& bx, int& by, int& bz) {
-    // 64 voxels with at least 8 along z (the TMA inner dimension must span >= 16 bytes)
-    bz = Z >= 16 && Z % 16 == 0 ? 16 : 8;
-    const int rest = 64 / bz;
-    by = 1;
-    while (by * 2 <= rest && by * 2 <= (Y > 1 ? Y : 1) * 2 && by < 4) by *= 2;
-    bx = rest / by;
-    (void)X;
-}
-
 }  // namespace nrpn
 
 using namespace nrpn;
@@ -207,15 +199,16 @@ static int wgrad_plan(const nrpn_wgrad_desc* d, WgDev& P) {
     P.n_levels = d->n_levels; P.n_taps = d->n_taps; P.cin = d->cin; P.cout = d->cout; P.n_t = d->cin; P.m_tiles = d->cout / 128;
     P.fp16 = d->act_fp16 ? 1 : 0;
     for (int t = 0; t < d->n_taps; ++t) { P.tap[t][0] = d->tap_off[t][0]; P.tap[t][1] = d->tap_off[t][1]; P.tap[t][2] = d->tap_off[t][2]; P.tap[t][3] = 0; }
+    int max_dz = 1;
+    for (int t = 0; t < d->n_taps; ++t) { const int a = d->tap_off[t][2] < 0 ? -d->tap_off[t][2] : d->tap_off[t][2]; if (a > max_dz) max_dz = a; }
     int bricks = 0;
     for (int l = 0; l < d->n_levels; ++l) {
         const nrpn_wgrad_level& S = d->level[l];
-        if (S.n < 1 || S.x < 1 || S.y < 1 || S.z < 1 || S.z_pitch < S.z || S.z_pitch % 8 != 0) return NRPN_ERR_INVALID;
+        if (S.n < 1 || S.x < 1 || S.y < 1 || S.z < 1 || S.z_pitch < S.z + max_dz || S.z_pitch % 8 != 0) return NRPN_ERR_INVALID;   // zero pad columns >= the largest z offset
         WgLevelDev& L = P.lv[l];
-        wg_brick(S.x, S.y, S.z, L.bx, L.by, L.bz);
-        L.n = S.n; L.tx = ceil_div(S.x, L.bx); L.ty = ceil_div(S.y, L.by); L.tz = ceil_div(S.z, L.bz);
+        L.n = S.n; L.X = S.x; L.zp = S.z_pitch; L.chunks = ceil_div(S.y * S.z_pitch, 64);
         L.brick_begin = bricks;
-        bricks += S.n * L.tx * L.ty * L.tz;
+        bricks += S.n * S.x * L.chunks;
     }
     P.total_bricks = bricks;
     const int base = d->n_taps * P.m_tiles;
@@ -242,23 +235,22 @@ int nrpn_conv3d_wgrad(const nrpn_wgrad_desc* d, nrpn_stream_t stream) {
     for (int l = 0; l < d->n_levels; ++l) {
         const nrpn_wgrad_level& S = d->level[l];
         if (!S.dy_planar || !S.x_planar) return NRPN_ERR_INVALID;
-        const WgLevelDev& L = P.lv[l];
-        const cuuint64_t X = S.x, Y = S.y, Z = S.z, Zp = S.z_pitch;
-        cuuint32_t one[5] = {1, 1, 1, 1, 1};
+        const cuuint64_t X = S.x, F = (cuuint64_t)S.y * S.z_pitch;            // flattened (y, z-with-pad) extent
+        cuuint32_t one[4] = {1, 1, 1, 1};
         {
-            cuuint64_t gdim[5] = {Z, Y, X, (cuuint64_t)d->cout, (cuuint64_t)S.n};
-            cuuint64_t gstr[4] = {Zp * 2, Y * Zp * 2, X * Y * Zp * 2, X * Y * Zp * 2 * (cuuint64_t)d->cout};
-            cuuint32_t box[5] = {(cuuint32_t)L.bz, (cuuint32_t)L.by, (cuuint32_t)L.bx, 128, 1};
-            CUresult r = encode(&maps.dy[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(S.dy_planar), gdim, gstr, box, one,
+            cuuint64_t gdim[4] = {F, X, (cuuint64_t)d->cout, (cuuint64_t)S.n};
+            cuuint64_t gstr[3] = {F * 2, X * F * 2, X * F * 2 * (cuuint64_t)d->cout};
+            cuuint32_t box[4] = {64, 1, 128, 1};
+            CUresult r = encode(&maps.dy[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(S.dy_planar), gdim, gstr, box, one,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return NRPN_ERR_CUDA; }
         }
         {
-            cuuint64_t gdim[5] = {Z, Y, X, (cuuint64_t)d->cin, (cuuint64_t)S.n};
-            cuuint64_t gstr[4] = {Zp * 2, Y * Zp * 2, X * Y * Zp * 2, X * Y * Zp * 2 * (cuuint64_t)d->cin};
-            cuuint32_t box[5] = {(cuuint32_t)L.bz, (cuuint32_t)L.by, (cuuint32_t)L.bx, (cuuint32_t)P.n_t, 1};
-            CUresult r = encode(&maps.x[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(S.x_planar), gdim, gstr, box, one,
+            cuuint64_t gdim[4] = {F, X, (cuuint64_t)d->cin, (cuuint64_t)S.n};
+            cuuint64_t gstr[3] = {F * 2, X * F * 2, X * F * 2 * (cuuint64_t)d->cin};
+            cuuint32_t box[4] = {64, 1, (cuuint32_t)P.n_t, 1};
+            CUresult r = encode(&maps.x[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(S.x_planar), gdim, gstr, box, one,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return NRPN_ERR_CUDA; }

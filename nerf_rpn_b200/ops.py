@@ -220,11 +220,11 @@ def is_channels_last_grid(grid: torch.Tensor) -> bool:
 
 
 def to_planar(x: torch.Tensor) -> torch.Tensor:
-    """(N, X, Y, Z, ld) 16-bit channels-last -> planar (N, ld, X, Y, Z) VIEW of a buffer whose z pitch is rounded up to a multiple
-    of 8 (16-byte TMA strides): the operand layout of conv3d_wgrad."""
+    """(N, X, Y, Z, ld) 16-bit channels-last -> planar (N, ld, X, Y, Z) VIEW of a zero-filled buffer whose z pitch is Z + 1 rounded up
+    to a multiple of 8 (at least one zero pad column per row = the z padding of the convolution): the operand layout of conv3d_wgrad."""
     _act16(x, "x")
     n, X, Y, Z, c = x.shape
-    zp = (Z + 7) // 8 * 8
+    zp = (Z + 1 + 7) // 8 * 8
     buf = torch.zeros((n, c, X, Y, zp), dtype=x.dtype, device=x.device)
     check(lib().nrpn_transpose_to_planar(_ptr(x), n, X, Y, Z, c, c, _ptr(buf), zp, _stream()), "transpose_to_planar")
     return buf[..., :Z]
