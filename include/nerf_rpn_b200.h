@@ -281,12 +281,12 @@ int nrpn_assign_targets(const float *anchors, int n_anchors, const float *gt, in
  * dW[tap][co][ci] = sum_v dY[v][co] * X[v + tap_off][ci] of a stride-1 convolution (training) on tcgen05.
  * Both operands are read in PLANAR layout (N, C, X, Y, z_pitch), 16-bit (nrpn_transpose_to_planar converts a channels-last tensor);
  * levels that share the weights (RPN head on P2..P5) accumulate into the same dW.  dw: fp32 (taps, cout, cin), overwritten.
- * cout % 128 == 0; cin % 32 == 0, cin <= 256.  Deterministic (fixed-order reduction of the K-split partial tiles). */
+ * cout % 128 == 0; cin % 32 == 0, cin <= 256; tap z offsets in {-1, 0, +1}.  Deterministic (fixed-order reduction of the K-split partial tiles). */
 typedef struct {
     const void *dy_planar;   /* (N, cout, X, Y, z_pitch) bf16 / fp16 */
-    const void *x_planar;    /* (N, cin,  X, Y, z_pitch) bf16 / fp16 */
+    const void *x_planar[3]; /* (N, cin,  X, Y, z_pitch): copies shifted along z, [k][z] = x[z + (k - 1)], zero outside; NULL if no tap has dz = k - 1 */
     int32_t n, x, y, z;
-    int32_t z_pitch;         /* >= z + 1, multiple of 8; the pad columns MUST be zero (they are the convolution's z padding) */
+    int32_t z_pitch;         /* >= z + 1, multiple of 8; positions without a source MUST be zero (pre-zeroed buffers) */
 } nrpn_wgrad_level;
 
 typedef struct {
@@ -305,7 +305,7 @@ int nrpn_conv3d_wgrad(const nrpn_wgrad_desc *desc /*host*/, nrpn_stream_t stream
 /* channels-last (N, X, Y, Z, ld >= c) 16-bit -> planar (N, c, X, Y, z_pitch >= Z); columns [Z, z_pitch) are left untouched
  * (pre-zero the buffer once) */
 int nrpn_transpose_to_planar(const void *in_cl, int n, int x, int y, int z, int c, int ld, void *out_planar, int z_pitch,
-                             nrpn_stream_t stream);
+                             int z_shift /* out[z'] = in[z' + z_shift] */, nrpn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -46,7 +46,7 @@ class RpnDesc(ctypes.Structure):
 
 
 class WgradLevel(ctypes.Structure):
-    _fields_ = [("dy_planar", ctypes.c_void_p), ("x_planar", ctypes.c_void_p), ("n", ctypes.c_int32), ("x", ctypes.c_int32),
+    _fields_ = [("dy_planar", ctypes.c_void_p), ("x_planar", ctypes.c_void_p * 3), ("n", ctypes.c_int32), ("x", ctypes.c_int32),
                 ("y", ctypes.c_int32), ("z", ctypes.c_int32), ("z_pitch", ctypes.c_int32)]
 
 
@@ -94,7 +94,7 @@ _SIGNATURES = {
     "nrpn_conv3d_wgrad_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(WgradDesc)]),
     "nrpn_conv3d_wgrad": (ctypes.c_int, [ctypes.POINTER(WgradDesc), c_stream]),
     "nrpn_transpose_to_planar": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                                ctypes.c_int, ctypes.c_void_p, ctypes.c_int, c_stream]),
+                                                ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_stream]),
     "nrpn_pack_stem_input": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_stream]),
     "nrpn_pack_stem_input_u8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

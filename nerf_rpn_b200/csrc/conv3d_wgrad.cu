@@ -5,8 +5,9 @@
 // (z pitch padded with at least one ZERO column) by a bandwidth kernel.  The (y, z) plane is then addressed as ONE flattened axis
 // of Y * z_pitch elements: a TMA box {64 flattened voxels, 1 x, channels, 1} lands in shared memory as `channels` rows of exactly
 // 128 bytes -- the 128B-swizzled K-major layout every other kernel of this library feeds to tcgen05.mma (an inner box narrower
-// than the swizzle span is NOT laid out densely by TMA, hence 64 contiguous elements).  A tap shift (dy, dz) is the flattened
-// offset dy * z_pitch + dz; stepping off a row's end lands in the zero pad column, stepping off the plane is TMA's zero fill:
+// than the swizzle span is NOT laid out densely by TMA, hence 64 contiguous elements).  TMA needs 16-byte aligned inner
+// coordinates, so a y shift is the flattened offset dy * z_pitch (z_pitch % 8 == 0) and a z shift of -1 / +1 reads a z-SHIFTED
+// COPY of X^T written by the transpose kernel (zero where the source falls outside); stepping off the plane is TMA's zero fill:
 //     A = dY^T brick (128 output channels x 64 voxels),  B = X^T brick shifted by the tap (N_T input channels x 64 voxels),
 //     D (128 x N_T, fp32 in TMEM) += A * B^T      -- out-of-range voxels are zero-filled by TMA (= the convolution padding).
 // Work item = (tap, 128-channel slice of Cout, K-split); every item streams its share of the voxel bricks of all pyramid
@@ -33,7 +34,7 @@ struct WgDev {
     float* partial;                            // [tap][m_tile][split][128][n_t]
 };
 
-struct WgMaps { CUtensorMap dy[NRPN_CONV_MAX_LEVELS]; CUtensorMap x[NRPN_CONV_MAX_LEVELS]; };
+struct WgMaps { CUtensorMap dy[NRPN_CONV_MAX_LEVELS]; CUtensorMap x[NRPN_CONV_MAX_LEVELS][3]; };      // x[level][dz + 1]: z-shifted copies
 
 __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgDev P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_kernel(const __gri
         for (int s = 0; s < kWgStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
         ptx::mbar_init(tfull_bar, 1);
         ptx::fence_barrier_init();
-        for (int l = 0; l < P.n_levels; ++l) { ptx::prefetch_tmap(&maps.dy[l]); ptx::prefetch_tmap(&maps.x[l]); }
+        for (int l = 0; l < P.n_levels; ++l) { ptx::prefetch_tmap(&maps.dy[l]); for (int k = 0; k < 3; ++k) ptx::prefetch_tmap(&maps.x[l][k]); }
     }
     if (warp == 1) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
     ptx::tc_fence_before();
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_kernel(const __gri
                     uint8_t* sa = smem + stage_p * stage_bytes;
                     ptx::mbar_expect_tx(&full_bar[stage_p], (uint32_t)stage_bytes);
                     ptx::tma_load_4d(sa, &maps.dy[l], &full_bar[stage_p], f0, x0, mt * 128, nb);
-                    ptx::tma_load_4d(sa + kWgABytes, &maps.x[l], &full_bar[stage_p], f0 + dy * L.zp + dz, x0 + dx, 0, nb);
+                    ptx::tma_load_4d(sa + kWgABytes, &maps.x[l][dz + 1], &full_bar[stage_p], f0 + dy * L.zp, x0 + dx, 0, nb);   // z shift lives in the copy
                 }
                 __syncwarp();
                 if (++stage_p == kWgStages) { stage_p = 0; phase_p ^= 1u; }
@@ -152,7 +153,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_tap
 // channels-last (N, X*Y*Z, ld) -> planar (N, C, X*Y, Zp) with Zp = z pitch >= Z (a multiple of 8 so that every TMA stride is a
 // multiple of 16 bytes; the pad is never read: the tensor maps carry the logical Z), 16-bit elements, 64 x 64 tiles through smem
 __global__ void __launch_bounds__(256) cl_to_planar_kernel(const uint16_t* __restrict__ in, int ld, int C, long V, int Z, int Zp,
-                                                           uint16_t* __restrict__ out) {
+                                                           int z_shift, uint16_t* __restrict__ out) {
     __shared__ uint16_t tile[64][66];
     const long v0 = (long)blockIdx.x * 64;
     const int c0 = blockIdx.y * 64, nb = blockIdx.z;
@@ -168,7 +169,8 @@ __global__ void __launch_bounds__(256) cl_to_planar_kernel(const uint16_t* __res
         const int c = i >> 6, v = i & 63;
         if (v0 + v < V && c0 + c < C) {
             const long vv = v0 + v;
-            dst[(size_t)(c0 + c) * plane + (size_t)(vv / Z) * Zp + (vv % Z)] = tile[v][c];
+            const int zo = (int)(vv % Z) - z_shift;          // out[z'] = in[z' + z_shift]: a z-shifted copy keeps TMA coordinates 16-byte aligned
+            if (zo >= 0 && zo < Zp) dst[(size_t)(c0 + c) * plane + (size_t)(vv / Z) * Zp + zo] = tile[v][c];
         }
     }
 }
@@ -180,13 +182,13 @@ using namespace nrpn;
 extern "C" {
 #pragma GCC visibility push(default)
 
-int nrpn_transpose_to_planar(const void* in_cl, int n, int x, int y, int z, int c, int ld, void* out_planar, int z_pitch,
+int nrpn_transpose_to_planar(const void* in_cl, int n, int x, int y, int z, int c, int ld, void* out_planar, int z_pitch, int z_shift,
                              nrpn_stream_t stream) {
     if (!in_cl || !out_planar || n < 1 || x < 1 || y < 1 || z < 1 || c < 1 || ld < c || z_pitch < z) return NRPN_ERR_INVALID;
     const long voxels = (long)x * y * z;
     dim3 grid((unsigned)ceil_div(voxels, 64L), (unsigned)ceil_div(c, 64), (unsigned)n);
     if (grid.y > 65535 || grid.z > 65535) return NRPN_ERR_UNSUPPORTED;
-    cl_to_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint16_t*>(in_cl), ld, c, voxels, z, z_pitch,
+    cl_to_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint16_t*>(in_cl), ld, c, voxels, z, z_pitch, z_shift,
                                                                reinterpret_cast<uint16_t*>(out_planar));
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
@@ -201,6 +203,7 @@ static int wgrad_plan(const nrpn_wgrad_desc* d, WgDev& P) {
     for (int t = 0; t < d->n_taps; ++t) { P.tap[t][0] = d->tap_off[t][0]; P.tap[t][1] = d->tap_off[t][1]; P.tap[t][2] = d->tap_off[t][2]; P.tap[t][3] = 0; }
     int max_dz = 1;
     for (int t = 0; t < d->n_taps; ++t) { const int a = d->tap_off[t][2] < 0 ? -d->tap_off[t][2] : d->tap_off[t][2]; if (a > max_dz) max_dz = a; }
+    if (max_dz > 1) return NRPN_ERR_UNSUPPORTED;                       // z-shifted operand copies exist for dz in {-1, 0, +1}
     int bricks = 0;
     for (int l = 0; l < d->n_levels; ++l) {
         const nrpn_wgrad_level& S = d->level[l];
@@ -234,7 +237,8 @@ int nrpn_conv3d_wgrad(const nrpn_wgrad_desc* d, nrpn_stream_t stream) {
     WgMaps maps;
     for (int l = 0; l < d->n_levels; ++l) {
         const nrpn_wgrad_level& S = d->level[l];
-        if (!S.dy_planar || !S.x_planar) return NRPN_ERR_INVALID;
+        if (!S.dy_planar) return NRPN_ERR_INVALID;
+        for (int t = 0; t < d->n_taps; ++t) if (!S.x_planar[d->tap_off[t][2] + 1]) return NRPN_ERR_INVALID;
         const cuuint64_t X = S.x, F = (cuuint64_t)S.y * S.z_pitch;            // flattened (y, z-with-pad) extent
         cuuint32_t one[4] = {1, 1, 1, 1};
         {
@@ -246,17 +250,19 @@ int nrpn_conv3d_wgrad(const nrpn_wgrad_desc* d, nrpn_stream_t stream) {
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return NRPN_ERR_CUDA; }
         }
-        {
-            cuuint64_t gdim[4] = {F, X, (cuuint64_t)d->cin, (cuuint64_t)S.n};
-            cuuint64_t gstr[3] = {F * 2, X * F * 2, X * F * 2 * (cuuint64_t)d->cin};
-            cuuint32_t box[4] = {64, 1, (cuuint32_t)P.n_t, 1};
-            CUresult r = encode(&maps.x[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(S.x_planar), gdim, gstr, box, one,
+        for (int k = 0; k < 3; ++k) {
+            const void* src = S.x_planar[k] ? S.x_planar[k] : S.dy_planar;        // unused slots get any valid map
+            const cuuint64_t ch = S.x_planar[k] ? (cuuint64_t)d->cin : (cuuint64_t)d->cout;
+            cuuint64_t gdim[4] = {F, X, ch, (cuuint64_t)S.n};
+            cuuint64_t gstr[3] = {F * 2, X * F * 2, X * F * 2 * ch};
+            cuuint32_t box[4] = {64, 1, (cuuint32_t)(S.x_planar[k] ? P.n_t : 128), 1};
+            CUresult r = encode(&maps.x[l][k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, one,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return NRPN_ERR_CUDA; }
         }
     }
-    for (int l = d->n_levels; l < NRPN_CONV_MAX_LEVELS; ++l) { maps.dy[l] = maps.dy[0]; maps.x[l] = maps.x[0]; }
+    for (int l = d->n_levels; l < NRPN_CONV_MAX_LEVELS; ++l) { maps.dy[l] = maps.dy[0]; for (int k = 0; k < 3; ++k) maps.x[l][k] = maps.x[0][k]; }
     P.partial = reinterpret_cast<float*>(align_up((size_t)d->workspace, 256));
     const int smem = kWgStages * (kWgABytes + P.n_t * 128) + 1024 + 256;
     static int smem_set = 0;

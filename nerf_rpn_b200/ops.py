@@ -219,38 +219,45 @@ def is_channels_last_grid(grid: torch.Tensor) -> bool:
     return grid.dim() == 5 and not grid.is_contiguous() and grid.permute(0, 2, 3, 4, 1).is_contiguous()
 
 
-def to_planar(x: torch.Tensor) -> torch.Tensor:
+def to_planar(x: torch.Tensor, z_shift: int = 0) -> torch.Tensor:
     """(N, X, Y, Z, ld) 16-bit channels-last -> planar (N, ld, X, Y, Z) VIEW of a zero-filled buffer whose z pitch is Z + 1 rounded up
-    to a multiple of 8 (at least one zero pad column per row = the z padding of the convolution): the operand layout of conv3d_wgrad."""
+    to a multiple of 8; z_shift = s writes out[z'] = x[z' + s] (zero where the source falls outside): the operand layout of
+    conv3d_wgrad (TMA wants 16-byte aligned inner coordinates, so z offsets live in shifted copies)."""
     _act16(x, "x")
     n, X, Y, Z, c = x.shape
     zp = (Z + 1 + 7) // 8 * 8
     buf = torch.zeros((n, c, X, Y, zp), dtype=x.dtype, device=x.device)
-    check(lib().nrpn_transpose_to_planar(_ptr(x), n, X, Y, Z, c, c, _ptr(buf), zp, _stream()), "transpose_to_planar")
+    check(lib().nrpn_transpose_to_planar(_ptr(x), n, X, Y, Z, c, c, _ptr(buf), zp, int(z_shift), _stream()), "transpose_to_planar")
     return buf[..., :Z]
 
 
 def conv3d_wgrad(dys: Sequence[torch.Tensor], xs: Sequence[torch.Tensor], taps: Sequence[Sequence[int]]) -> torch.Tensor:
-    """dW (taps, Cout, Cin) fp32 of a stride-1 conv from planar (N,C,X,Y,Z) 16-bit dY / X tensors, one pair per pyramid level
-    that shares the weights."""
+    """dW (taps, Cout, Cin) fp32 of a stride-1 'same' conv from channels-last 16-bit dY (N,X,Y,Z,Cout) and X (N,X,Y,Z,Cin), one pair per
+    pyramid level that shares the weights (tap z offsets in {-1, 0, +1})."""
     d = WgradDesc()
-    d.cout, d.cin, d.n_taps = int(dys[0].shape[1]), int(xs[0].shape[1]), len(taps)
+    d.cout, d.cin, d.n_taps = int(dys[0].shape[-1]), int(xs[0].shape[-1]), len(taps)
     for t, off in enumerate(taps):
         for k in range(3):
             d.tap_off[t][k] = int(off[k])
+    dzs = sorted({int(off[2]) for off in taps})
+    if any(abs(z) > 1 for z in dzs):
+        raise ValueError("conv3d_wgrad: tap z offsets must be in {-1, 0, +1}")
     d.n_levels = len(dys)
+    keep = []
     for i, (dy, x) in enumerate(zip(dys, xs)):
-        if not (dy.is_cuda and x.is_cuda) or dy.dtype not in (torch.bfloat16, torch.float16):
-            raise TypeError("conv3d_wgrad: operands must be bf16 / fp16 CUDA tensors")
-        f16 = 1 if dy.dtype == torch.float16 else 0
-        if dy.dtype != x.dtype or dy.shape[0] != x.shape[0] or dy.shape[2:] != x.shape[2:]:
+        f16 = _act16(dy, "dy")
+        if _act16(x, "x") != f16 or dy.shape[:4] != x.shape[:4]:
             raise ValueError("conv3d_wgrad: dy and x must share dtype, batch and spatial extent (stride-1 'same' convolution)")
+        pdy = to_planar(dy)
+        keep.append(pdy)
         lv = d.level[i]
-        if dy.stride(-1) != 1 or x.stride(-1) != 1 or dy.stride(3) != x.stride(3) or dy.stride(3) % 8 != 0:
-            raise ValueError("conv3d_wgrad: operands must come from ops.to_planar (z pitch a multiple of 8)")
-        lv.dy_planar, lv.x_planar = dy.data_ptr(), x.data_ptr()
-        lv.n, lv.x, lv.y, lv.z = int(dy.shape[0]), int(dy.shape[2]), int(dy.shape[3]), int(dy.shape[4])
-        lv.z_pitch = int(dy.stride(3))
+        lv.dy_planar = pdy.data_ptr()
+        for z in dzs:
+            px = to_planar(x, z)
+            keep.append(px)
+            lv.x_planar[z + 1] = px.data_ptr()
+        lv.n, lv.x, lv.y, lv.z = int(dy.shape[0]), int(dy.shape[1]), int(dy.shape[2]), int(dy.shape[3])
+        lv.z_pitch = int(pdy.stride(3))
     d.act_fp16 = f16
     dw = torch.empty((len(taps), d.cout, d.cin), dtype=torch.float32, device=dys[0].device)
     need = lib().nrpn_conv3d_wgrad_workspace_bytes(ctypes.byref(d))

@@ -322,9 +322,10 @@ def test_conv_weight_gradient_vs_autograd(ops, level_dims, cin, cout, k, dtype):
         y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w, padding=k // 2)
         (gw,) = torch.autograd.grad(y, w, dy.float().permute(0, 4, 1, 2, 3))
         ref += gw
-        px, pdy = ops.to_planar(x), ops.to_planar(dy)
-        assert torch.equal(px, x.permute(0, 4, 1, 2, 3)) and torch.equal(pdy, dy.permute(0, 4, 1, 2, 3))
-        xs.append(px); dys.append(pdy)
+        assert torch.equal(ops.to_planar(x), x.permute(0, 4, 1, 2, 3))
+        sh = ops.to_planar(x, 1)                                        # out[z'] = x[z' + 1]
+        assert torch.equal(sh[..., :-1], x.permute(0, 4, 1, 2, 3)[..., 1:]) and sh[..., -1].abs().max().item() == 0
+        xs.append(x); dys.append(dy)
     taps = [(a - k // 2, b - k // 2, c - k // 2) for a in range(k) for b in range(k) for c in range(k)]
     dw = ops.conv3d_wgrad(dys, xs, taps)
     torch.cuda.synchronize()
