@@ -307,6 +307,13 @@ int nrpn_conv3d_wgrad(const nrpn_wgrad_desc *desc /*host*/, nrpn_stream_t stream
 int nrpn_transpose_to_planar(const void *in_cl, int n, int x, int y, int z, int c, int ld, void *out_planar, int z_pitch,
                              int z_shift /* out[z'] = in[z' + z_shift] */, nrpn_stream_t stream);
 
+/* Pointwise pieces of a conv + bias + ReLU layer's backward pass (training building blocks):
+ * db[c] = sum over rows of dY[row][c] (fixed-order two-stage reduction, bit-reproducible); dY *= (act > 0) in place. */
+size_t nrpn_bias_grad_workspace_bytes(int c);
+int nrpn_bias_grad(const void *dy_cl /* (rows, ld >= c) 16-bit */, long rows, int c, int ld, int act_fp16, float *db, void *workspace,
+                   size_t workspace_bytes, nrpn_stream_t stream);
+int nrpn_relu_backward(void *dy_cl, const void *act_cl, size_t elements /* % 8 == 0 */, int act_fp16, nrpn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

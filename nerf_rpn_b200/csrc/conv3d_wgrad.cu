@@ -285,3 +285,82 @@ int nrpn_conv3d_wgrad(const nrpn_wgrad_desc* d, nrpn_stream_t stream) {
 
 #pragma GCC visibility pop
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ bias gradient, ReLU backward
+// The two pointwise pieces of a conv + bias + ReLU layer's backward pass (training building blocks next to dgrad / wgrad):
+//   db[c]  = sum over voxels of dY[v][c]           (two-stage, fixed-order reduction: bit-reproducible)
+//   dY[v][c] *= (act[v][c] > 0)                     (in place, 16-bit channels-last tensors)
+namespace nrpn {
+
+constexpr int kBgBlocks = 256;
+
+__global__ void __launch_bounds__(256) bias_grad_partial_kernel(const __nv_bfloat16* __restrict__ dy, long rows, int c, int ld, int fp16,
+                                                                float* __restrict__ partial) {
+    // block b sums rows b, b + gridDim.x, ...; thread t owns channels t, t + 256, ...
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float s = 0.f;
+        for (long r = blockIdx.x; r < rows; r += gridDim.x) s += load_act(dy + (size_t)r * ld + ch, fp16);
+        partial[(size_t)blockIdx.x * c + ch] = s;
+    }
+}
+
+__global__ void bias_grad_final_kernel(const float* __restrict__ partial, int blocks, int c, float* __restrict__ db) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    float s = 0.f;
+    for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * c + ch];
+    db[ch] = s;
+}
+
+__global__ void relu_backward_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ act, size_t chunks, int fp16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 g = reinterpret_cast<const uint4*>(dy)[i];
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(act) + i);
+        uint32_t* gw = reinterpret_cast<uint32_t*>(&g);
+        const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 av = unpack_act2(aw[k], fp16);
+            if (!(av.x > 0.f)) gw[k] &= 0xFFFF0000u;
+            if (!(av.y > 0.f)) gw[k] &= 0x0000FFFFu;
+        }
+        reinterpret_cast<uint4*>(dy)[i] = g;
+    }
+}
+
+}  // namespace nrpn
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+size_t nrpn_bias_grad_workspace_bytes(int c) { return c < 1 ? 0 : (size_t)nrpn::kBgBlocks * c * sizeof(float) + 256; }
+
+int nrpn_bias_grad(const void* dy_cl, long rows, int c, int ld, int act_fp16, float* db, void* workspace, size_t workspace_bytes,
+                   nrpn_stream_t stream) {
+    if (!dy_cl || !db || !workspace || rows < 1 || c < 1 || ld < c) return NRPN_ERR_INVALID;
+    if (workspace_bytes < nrpn_bias_grad_workspace_bytes(c)) return NRPN_ERR_WORKSPACE;
+    float* partial = reinterpret_cast<float*>(nrpn::align_up((size_t)workspace, 256));
+    const int blocks = rows < nrpn::kBgBlocks ? (int)rows : nrpn::kBgBlocks;
+    nrpn::bias_grad_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_cl), rows, c, ld,
+                                                                          act_fp16 ? 1 : 0, partial);
+    NRPN_LAUNCH_CHECK();
+    nrpn::bias_grad_final_kernel<<<nrpn::ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(partial, blocks, c, db);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+int nrpn_relu_backward(void* dy_cl, const void* act_cl, size_t elements, int act_fp16, nrpn_stream_t stream) {
+    if (!dy_cl || !act_cl || elements < 8 || elements % 8 != 0) return NRPN_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(dy_cl) % 16 != 0 || reinterpret_cast<uintptr_t>(act_cl) % 16 != 0) return NRPN_ERR_INVALID;
+    const size_t chunks = elements / 8;
+    size_t blocks = nrpn::ceil_div(chunks, (size_t)256);
+    if (blocks > (size_t)nrpn::num_sms() * 16) blocks = (size_t)nrpn::num_sms() * 16;
+    nrpn::relu_backward_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16*>(dy_cl),
+                                                                                  reinterpret_cast<const __nv_bfloat16*>(act_cl), chunks,
+                                                                                  act_fp16 ? 1 : 0);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -269,6 +269,26 @@ def conv3d_wgrad(dys: Sequence[torch.Tensor], xs: Sequence[torch.Tensor], taps: 
     return dw
 
 
+def bias_grad(dy: torch.Tensor) -> torch.Tensor:
+    """(..., C) 16-bit channels-last dY -> db (C) fp32 = sum over every row (bit-reproducible two-stage reduction)."""
+    f16 = _act16(dy, "dy")
+    c = int(dy.shape[-1])
+    rows = dy.numel() // c
+    db = torch.empty((c,), dtype=torch.float32, device=dy.device)
+    ws = _workspace(lib().nrpn_bias_grad_workspace_bytes(c), dy.device)
+    check(lib().nrpn_bias_grad(_ptr(dy), rows, c, c, f16, _ptr(db), _ptr(ws), ws.numel(), _stream()), "bias_grad")
+    return db
+
+
+def relu_backward_(dy: torch.Tensor, act: torch.Tensor) -> torch.Tensor:
+    """dy *= (act > 0) in place (16-bit tensors of equal shape): the ReLU of a conv + bias + ReLU layer, backwards."""
+    f16 = _act16(dy, "dy")
+    if _act16(act, "act") != f16 or act.shape != dy.shape:
+        raise ValueError("relu_backward_: dy and act must have the same dtype and shape")
+    check(lib().nrpn_relu_backward(_ptr(dy), _ptr(act), dy.numel(), f16, _stream()), "relu_backward")
+    return dy
+
+
 def pack_stem_input(grid: torch.Tensor, out: Optional[torch.Tensor] = None, dtype=torch.bfloat16) -> torch.Tensor:
     """(N,4,X,Y,Z) fp32 -> (N, ceil(X/2), ceil(Y/2), ceil(Z/2)+1, 64) bf16 (or fp16: dtype of `out`).
     `grid` may be contiguous NCDHW or the channels-last view the reference's dataset yields (memory (N,X,Y,Z,4))."""

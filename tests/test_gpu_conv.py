@@ -333,3 +333,18 @@ def test_conv_weight_gradient_vs_autograd(ops, level_dims, cin, cout, k, dtype):
     assert not torch.isnan(dw).any()
     assert (dw - refp).abs().max().item() <= 2e-3 * refp.abs().max().item(), _diagnose(dw, refp, "wgrad")
     assert torch.equal(dw, ops.conv3d_wgrad(dys, xs, taps)), "weight gradients must be bit-reproducible"
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_bias_grad_and_relu_backward(ops, dtype):
+    g = torch.Generator(device="cuda").manual_seed(71)
+    dy = torch.randn((2, 9, 11, 10, 256), device="cuda", generator=g).to(dtype)
+    act = torch.randn((2, 9, 11, 10, 256), device="cuda", generator=g).to(dtype)
+    act[0, 0, 0, 0, :8] = 0                                                   # exactly zero activations: gradient must be cut
+    db = ops.bias_grad(dy)
+    ref = dy.float().sum(dim=(0, 1, 2, 3))
+    assert (db - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    assert torch.equal(db, ops.bias_grad(dy))
+    want = torch.where(act.float() > 0, dy, torch.zeros_like(dy))
+    got = ops.relu_backward_(dy.clone(), act)
+    assert torch.equal(got, want)
