@@ -467,7 +467,53 @@ def gen_targets():
     np.savez_compressed(os.path.join(OUT, "targets_small.npz"), **out)
 
 
+def gen_losses():
+    """Loss side of the RPN training step through the reference's own functions (CPU): sampler with recorded randperm draws,
+    AABB / midpoint-offset encoders on the matched pairs, smooth-L1 + BCE as combined in compute_loss (rpn.py:394-417)."""
+    import torch.nn.functional as F
+    from model.coder.AABB_coder import encode_boxes_3d
+    from model.coder.midpoint_offset_coder import bbox2delta_sp
+    from model.coder.misc import obb2hbb_3d
+    from model.utils import BalancedPositiveNegativeSampler
+    t = np.load(os.path.join(OUT, "targets_small.npz"))
+    dims = (32, 48, 40)
+    ag = AnchorGenerator3D(ANCHOR_SIZES, ASPECT)
+    feats = [torch.zeros(1, 1, *[(d + s - 1) // s for d in dims]) for s in (4, 8, 16, 32)]
+    anchors = ag(torch.zeros(1, 4, *dims), feats)[0][0]
+    out = {}
+    gen = torch.Generator().manual_seed(21)
+    for kind, code in (("aabb", 6), ("obb", 8)):
+        gt = torch.from_numpy(t[f"gt_a_{kind}_0"])
+        labels = torch.from_numpy(t[f"labels_a_{kind}_0"].astype(np.float32))
+        matched = torch.from_numpy(t[f"matched_a_{kind}_0"].astype(np.int64))
+        mgt = gt[matched.clamp(min=0)]
+        targets = encode_boxes_3d(mgt, anchors) if kind == "aabb" else bbox2delta_sp(anchors, mgt)
+        # the sampler draws two randperms from the global RNG: record them
+        torch.manual_seed(5)
+        n_pos, n_neg = int((labels >= 1).sum()), int((labels == 0).sum())
+        perm_pos, perm_neg = torch.randperm(n_pos), torch.randperm(n_neg)
+        torch.manual_seed(5)
+        pos_m, neg_m = BalancedPositiveNegativeSampler(256, 0.5)([labels])
+        pos_m, neg_m = pos_m[0].bool(), neg_m[0].bool()
+        objectness = torch.randn(anchors.shape[0], generator=gen)
+        deltas = torch.randn(anchors.shape[0], code, generator=gen) * 0.3
+        pos, neg = torch.where(pos_m)[0], torch.where(neg_m)[0]
+        sampled = torch.cat([pos, neg])
+        box = F.smooth_l1_loss(deltas[pos], targets[pos], beta=1 / 9, reduction="sum") / sampled.numel()
+        obj = F.binary_cross_entropy_with_logits(objectness[sampled], labels[sampled])
+        finite = torch.isfinite(targets).all(dim=1)
+        out.update({f"{kind}_perm_pos": perm_pos.numpy(), f"{kind}_perm_neg": perm_neg.numpy(), f"{kind}_pos_mask": pos_m.numpy(),
+                    f"{kind}_neg_mask": neg_m.numpy(), f"{kind}_targets_pos": targets[pos].numpy(), f"{kind}_pos_idx": pos.numpy(),
+                    f"{kind}_objectness_sampled": objectness[sampled].numpy(), f"{kind}_deltas_pos": deltas[pos].numpy(),
+                    f"{kind}_neg_idx": neg.numpy(),
+                    f"{kind}_loss_obj": np.float64(float(obj)), f"{kind}_loss_box": np.float64(float(box))})
+        print(kind, "sampled", int(pos_m.sum()), int(neg_m.sum()), "losses", float(obj), float(box), "finite targets", int(finite.sum()))
+    np.savez_compressed(os.path.join(OUT, "loss_small.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--losses-only" in sys.argv:
+        sys.path.insert(0, ROOT); gen_losses(); sys.exit(0)
     if "--targets-only" in sys.argv:
         sys.path.insert(0, ROOT); gen_targets(); sys.exit(0)
     if "--recall-only" in sys.argv:
@@ -487,3 +533,4 @@ if __name__ == "__main__":
     gen_swin_small()
     sys.path.insert(0, ROOT); gen_recall()
     gen_targets()
+    gen_losses()
