@@ -117,6 +117,9 @@ typedef struct {
     void *workspace;                /* optional split-K scratch (see nrpn_conv3d_workspace_bytes) or NULL */
     size_t workspace_bytes;
     int32_t act_fp16;               /* 16-bit format of x / w / res / 16-bit y: 0 = bf16, 1 = fp16 (IEEE half) */
+    int32_t wsplit;                 /* 1: w is (taps, 2, CoutPad, cin) = every weight as the sum hi + lo of two 16-bit numbers (both
+                                     * planes are multiplied with the same activation tile into one fp32 accumulator): the weights
+                                     * then contribute no 16-bit rounding error -- the <= 1e-3 feature-map parity mode */
 } nrpn_conv_desc;
 
 /* Padding granularity of the output-channel axis for this cout (64, 128 or 256): w / shift must be padded to a multiple. */

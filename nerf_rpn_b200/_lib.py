@@ -29,7 +29,7 @@ class ConvDesc(ctypes.Structure):
                 ("tap_off", (ctypes.c_int8 * 3) * MAX_TAPS), ("stride", ctypes.c_int32), ("relu", ctypes.c_int32),
                 ("out_fp32", ctypes.c_int32), ("w", ctypes.c_void_p), ("shift", ctypes.c_void_p),
                 ("n_levels", ctypes.c_int32), ("level", ConvLevel * MAX_LEVELS), ("workspace", ctypes.c_void_p),
-                ("workspace_bytes", ctypes.c_size_t), ("act_fp16", ctypes.c_int32)]
+                ("workspace_bytes", ctypes.c_size_t), ("act_fp16", ctypes.c_int32), ("wsplit", ctypes.c_int32)]
 
 
 class RpnLevel(ctypes.Structure):

@@ -79,19 +79,26 @@ constexpr int kEpiTileBytes = kBlockM * 64 * 2;      // one 128 x 64 bf16 tile (
 // swizzled staging buffer and one elected thread stores it with cp.async.bulk.tensor (hardware clips partial bricks).
 // With per-thread 16/32-byte global loads and stores the same layers sat at ~45 % of the HBM rate (ncu: lts 45 %, 2-3x the
 // compulsory L2 sectors, a DRAM-latency chain per tile).
-template <int BLOCK_N, int STAGES, int MIN_BLOCKS, bool TMA_EPI = false>
+//
+// WS (weight split, the <=1e-3 parity mode of the backbone): every weight is the sum of TWO 16-bit numbers, w = hi + lo with
+// lo = round16(w - hi), packed as (taps, 2, CoutPad, Cin).  One TMA box {64, BLOCK_N, 2} brings both planes of a k-block; the
+// issuer runs the k-block's MMAs twice on the SAME activation tile (B = hi, then B = lo) into the same accumulator, so the
+// weights enter the fp32 accumulation with ~22 significant bits and only the activations carry 16-bit rounding error.
+template <int BLOCK_N, int STAGES, int MIN_BLOCKS, bool TMA_EPI = false, bool WS = false>
 __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvDev P) {
     static_assert(!TMA_EPI || BLOCK_N == 64, "the TMA epilogue stages 128 x 64 tiles");
-    constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    constexpr int kBPlane = BLOCK_N * kBlockK * 2;
+    constexpr int kBBytes = kBPlane * (WS ? 2 : 1);
     constexpr int kStageBytes = kABytes + kBBytes;
-    constexpr int kEpiBytes = TMA_EPI ? 3 * kEpiTileBytes : 0;      // residual ring (2) + output staging (1)
+    constexpr int RES_SLOTS = (TMA_EPI && WS) ? 1 : 2;              // residual prefetch depth (shared-memory budget of 2 CTAs / SM)
+    constexpr int kEpiBytes = TMA_EPI ? (RES_SLOTS + 1) * kEpiTileBytes : 0;      // residual ring + output staging (1)
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;
     const uint32_t kIdesc = P.fp16 ? ptx::make_idesc_f16(kBlockM, BLOCK_N) : ptx::make_idesc_bf16(kBlockM, BLOCK_N);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_res = smem + STAGES * kStageBytes;                 // [2][128 rows][128 B], 128B-swizzled (TMA_EPI)
-    uint8_t* smem_out = smem_res + 2 * kEpiTileBytes;                // [128 rows][128 B], 128B-swizzled (TMA_EPI)
+    uint8_t* smem_out = smem_res + RES_SLOTS * kEpiTileBytes;        // [128 rows][128 B], 128B-swizzled (TMA_EPI)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes + kEpiBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + STAGES;
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                         uint8_t* sb = sa + kABytes;
                         ptx::mbar_expect_tx(&full_bar[stage], kStageBytes);
                         ptx::tma_load_5d(sa, &maps.x[l], &full_bar[stage], kc * kBlockK, z0 + dz, y0 + dy, x0 + dx, nb);
-                        ptx::tma_load_3d(sb, &maps.w, &full_bar[stage], kc * kBlockK, n0, tap);
+                        ptx::tma_load_3d(sb, &maps.w, &full_bar[stage], kc * kBlockK, n0, WS ? 2 * tap : tap);   // WS: box depth 2 = hi, lo
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                         ptx::tma_load_5d(smem_res + rslot * kEpiTileBytes, &maps.r[l], &rfull_bar[rslot], n0, z0, y0, x0, nb);
                     }
                     __syncwarp();
-                    if (++rslot == 2) { rslot = 0; rphase ^= 1u; }
+                    if (++rslot == RES_SLOTS) { rslot = 0; rphase ^= 1u; }
                 }
             }
         }
@@ -191,9 +198,12 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                     const uint64_t db = ptx::make_desc_sw128(sa + kABytes);
                     if (leader) {
 #pragma unroll
-                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in the >>4 address field
-                            ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | k) ? 1u : 0u);
+                        for (int h = 0; h < (WS ? 2 : 1); ++h) {
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in the >>4 address field
+                                ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(h * (kBPlane >> 4) + 2 * k), kIdesc, (kb | k | h) ? 1u : 0u);
+                            }
                         }
                         ptx::umma_commit(&empty_bar[stage]);        // frees the smem slot once the MMAs have read it
                     }
@@ -360,7 +370,7 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
                 }
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&tempty_bar[acc]);
-                if (res_smem) { ptx::mbar_arrive(&rempty_bar[rslot]); if (++rslot == 2) { rslot = 0; rphase ^= 1u; } }
+                if (res_smem) { ptx::mbar_arrive(&rempty_bar[rslot]); if (++rslot == RES_SLOTS) { rslot = 0; rphase ^= 1u; } }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
                 ptx::fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA engine
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -471,20 +481,20 @@ __global__ void __launch_bounds__(192, MIN_BLOCKS) conv3d_igemm_kernel(const __g
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <int BLOCK_N, int STAGES, int MIN_BLOCKS, bool TMA_EPI = false>
+template <int BLOCK_N, int STAGES, int MIN_BLOCKS, bool TMA_EPI = false, bool WS = false>
 static int launch_conv(const ConvMaps& maps, const ConvDev& P, int total_tiles, cudaStream_t st) {
-    constexpr int smem = STAGES * (kABytes + BLOCK_N * kBlockK * 2) + (TMA_EPI ? 3 * kEpiTileBytes : 0) + 1024 + 256;
+    constexpr int smem = STAGES * (kABytes + BLOCK_N * kBlockK * 2 * (WS ? 2 : 1)) + (TMA_EPI ? ((WS ? 1 : 2) + 1) * kEpiTileBytes : 0) + 1024 + 256;
     static_assert((smem + 1024) * MIN_BLOCKS <= 228 * 1024, "shared memory budget");
     static_assert(2 * BLOCK_N * MIN_BLOCKS <= 512, "TMEM budget: 512 columns per SM");
     static bool attr_set = false;
     if (!attr_set) {
-        NRPN_CUDA_TRY(cudaFuncSetAttribute(conv3d_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS, TMA_EPI>,
+        NRPN_CUDA_TRY(cudaFuncSetAttribute(conv3d_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS, TMA_EPI, WS>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const int slots = num_sms() * MIN_BLOCKS;
     const int grid = total_tiles < slots ? total_tiles : slots;
-    NRPN_CUDA_TRY(launch_pdl(conv3d_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS, TMA_EPI>, dim3(grid), dim3(192), smem, st, total_tiles <= 2 * slots, maps, P));
+    NRPN_CUDA_TRY(launch_pdl(conv3d_igemm_kernel<BLOCK_N, STAGES, MIN_BLOCKS, TMA_EPI, WS>, dim3(grid), dim3(192), smem, st, total_tiles <= 2 * slots, maps, P));
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
@@ -543,7 +553,7 @@ static int conv_geometry(const nrpn_conv_desc* d, ConvGeom& g) {
         const char* e = getenv("NRPN_CONV_NARROW");
         if (!(e && e[0] == '0')) { g.block_n = 64; g.n_tiles_n = g.cout_pad / 64; }
     }
-    g.splits = choose_splits(tiles * g.n_tiles_n, g.kblocks, g.short_k);
+    g.splits = d->wsplit ? 1 : choose_splits(tiles * g.n_tiles_n, g.kblocks, g.short_k);
     g.counter_bytes = align_up((size_t)tiles * g.n_tiles_n * 4, 256);
     g.ws_bytes = g.splits > 1 ? g.counter_bytes + (size_t)tiles * g.n_tiles_n * g.splits * kBlockM * g.block_n * 4 : 0;
     // shared-memory (TMA) epilogue: the HBM-bound short reductions with whole 64-channel bf16 output tiles
@@ -578,9 +588,13 @@ int nrpn_conv3d_block_n(int cout) { return cout <= 64 ? 64 : (cout <= 128 ? 128 
 const char* nrpn_conv3d_variant(const nrpn_conv_desc* d) {
     if (!d || d->n_taps < 1 || d->n_taps > NRPN_CONV_MAX_TAPS || d->n_levels < 1 || d->n_levels > NRPN_CONV_MAX_LEVELS) return "invalid";
     if (d->cin < 64 || d->cin % 64 != 0 || d->cout < 8 || d->cout % 8 != 0 || (d->stride != 1 && d->stride != 2)) return "unsupported";
-    if (conv3d_slab_eligible(d)) return "slab<4x16x8,N64>";
+    if (!d->wsplit && conv3d_slab_eligible(d)) return "slab<4x16x8,N64>";
     ConvGeom g;
     if (conv_geometry(d, g) != NRPN_OK) return "invalid";
+    if (d->wsplit) {
+        if (g.short_k) return g.tma_epi ? "igemm<64,2,2,tma-epilogue,wsplit>" : "igemm<64,2,3,wsplit>";
+        return g.block_n == 64 ? "igemm<64,6,1,wsplit>" : (g.block_n == 128 ? "igemm<128,4,1,wsplit>" : "igemm<256,2,1,wsplit>");
+    }
     if (g.short_k) return g.tma_epi ? "igemm<64,2,2,tma-epilogue>" : "igemm<64,2,3>";
     return g.block_n == 64 ? "igemm<64,8,1>" : (g.block_n == 128 ? "igemm<128,6,1>" : "igemm<256,4,1>");
 }
@@ -597,7 +611,7 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
     }
     EncodeTiledFn encode = get_encode();
     if (!encode) return NRPN_ERR_NO_DEVICE;
-    if (conv3d_slab_eligible(d)) return conv3d_slab_launch(d, (cudaStream_t)stream);
+    if (!d->wsplit && conv3d_slab_eligible(d)) return conv3d_slab_launch(d, (cudaStream_t)stream);
 
     // Weights are padded to nrpn_conv3d_block_n(cout) (a multiple of 64). Long reductions (3^3 taps) use the widest N tile
     // that fits, one CTA per SM, deep smem ring: tensor-pipe bound.  Short reductions (1^3 convs: at most 8 k-blocks) are
@@ -672,9 +686,11 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
     for (int l = d->n_levels; l < NRPN_CONV_MAX_LEVELS; ++l) { maps.x[l] = maps.x[0]; maps.y[l] = maps.y[0]; maps.r[l] = maps.r[0]; }
     if (!geo.tma_epi) for (int l = 0; l < NRPN_CONV_MAX_LEVELS; ++l) { maps.y[l] = maps.x[0]; maps.r[l] = maps.x[0]; }
     {
-        cuuint64_t gdim[3] = {(cuuint64_t)d->cin, (cuuint64_t)cout_pad, (cuuint64_t)d->n_taps};
+        // wsplit: (taps, 2, CoutPad, cin) -- the hi and lo planes of a tap are consecutive slices, one box of depth 2 fetches both
+        const int planes = d->wsplit ? 2 : 1;
+        cuuint64_t gdim[3] = {(cuuint64_t)d->cin, (cuuint64_t)cout_pad, (cuuint64_t)d->n_taps * planes};
         cuuint64_t gstr[2] = {(cuuint64_t)d->cin * 2, (cuuint64_t)cout_pad * d->cin * 2};
-        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n, 1};
+        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n, (cuuint32_t)planes};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&maps.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->w), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -687,6 +703,14 @@ int nrpn_conv3d_fprop(const nrpn_conv_desc* d, nrpn_stream_t stream) {
     P.ws = splits > 1 ? reinterpret_cast<float*>(reinterpret_cast<char*>(d->workspace) + geo.counter_bytes) : nullptr;
     const int total_tiles = tiles * P.n_tiles_n * splits;
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->wsplit) {
+        if (splits != 1) return NRPN_ERR_UNSUPPORTED;
+        if (short_k && geo.tma_epi) return launch_conv<64, 2, 2, true, true>(maps, P, total_tiles, st);
+        if (short_k) return launch_conv<64, 2, 3, false, true>(maps, P, total_tiles, st);
+        if (block_n == 64) return launch_conv<64, 6, 1, false, true>(maps, P, total_tiles, st);
+        if (block_n == 128) return launch_conv<128, 4, 1, false, true>(maps, P, total_tiles, st);
+        return launch_conv<256, 2, 1, false, true>(maps, P, total_tiles, st);
+    }
     if (short_k && geo.tma_epi && splits == 1) return launch_conv<64, 2, 2, true>(maps, P, total_tiles, st);
     if (short_k) return launch_conv<64, 2, 3>(maps, P, total_tiles, st);
     if (block_n == 64) return launch_conv<64, 8, 1>(maps, P, total_tiles, st);

@@ -19,6 +19,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops, packing
+from .precision import resolve as _resolve_precision
 
 
 class _Conv:
@@ -26,7 +27,7 @@ class _Conv:
 
     dtype = torch.bfloat16      # 16-bit storage format of the weights being packed (set by the engine around _pack)
 
-    def __init__(self, weight, bias=None, bn=None, stride=1, relu=False, stem=False, cout_pad_to=None, device="cuda"):
+    def __init__(self, weight, bias=None, bn=None, stride=1, relu=False, stem=False, cout_pad_to=None, device="cuda", wsplit=False):
         scale = shift = None
         if bn is not None:
             scale, shift = (t.cpu() for t in packing.fold_bn(bn))
@@ -45,14 +46,14 @@ class _Conv:
         elif stem:
             wp, taps = packing.pack_stem_weight(weight, scale, dtype=_Conv.dtype)
         else:
-            wp, taps = packing.pack_conv_weight(weight, scale, cout_pad_to=cout_pad_to, dtype=_Conv.dtype)
+            wp, taps = packing.pack_conv_weight(weight, scale, cout_pad_to=cout_pad_to, dtype=_Conv.dtype, split=bool(wsplit))
         self.w = wp.to(device)
         self.taps = taps
-        self.cin = wp.shape[2]
+        self.cin = wp.shape[-1]
         self.cout = ((cout + 7) // 8) * 8 if cout_pad_to is None else cout_pad_to
         if shift is None:
             shift = torch.zeros(cout)
-        self.shift = packing.pad_shift(shift, wp.shape[1]).to(device)
+        self.shift = packing.pad_shift(shift, wp.shape[-2]).to(device)
         self.stride, self.relu = stride, relu
 
     def flops(self, out_voxels: int, real_cin: Optional[int] = None, real_taps: Optional[int] = None) -> float:
@@ -68,11 +69,11 @@ class RPNInferenceEngine:
 
     def __init__(self, backbone, head=None, anchor_cells=None, num_anchors: int = 0, rotated: bool = False,
                  pre_nms_top_n: int = 2500, post_nms_top_n: int = 2500, nms_thresh: float = 0.3, score_thresh: float = 0.0,
-                 min_size: float = 1e-3, use_graph: bool = True, fcos: Optional[dict] = None, precision: str = "bf16"):
-        if precision not in ("bf16", "fp16"):
-            raise ValueError("precision must be 'bf16' (default, BASELINE config 2) or 'fp16' (11-bit significand activations)")
+                 min_size: float = 1e-3, use_graph: bool = True, fcos: Optional[dict] = None, precision: Optional[str] = None):
+        precision = _resolve_precision(precision)            # "bf16" | "fp16" | "fp16_w2" (nerf_rpn_b200/precision.py)
         self.precision = precision
-        self.act_dtype = torch.float16 if precision == "fp16" else torch.bfloat16
+        self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float16
+        self.wsplit = precision == "fp16_w2"                 # backbone / FPN weights as hi + lo halves
         self.backbone, self.head = backbone, head
         self.fcos = fcos                   # None: anchor head (anchor.py:177-213); dict: FCOS head + post-processing settings
         self.cells = anchor_cells          # list (levels) of (A, 6) float arrays
@@ -133,7 +134,7 @@ class RPNInferenceEngine:
         f32 = lambda t: t.detach().float().to(device).contiguous()
         pe_conv, pe_ln = bb.patch_partition[0], bb.patch_partition[2]
         C0 = pe_conv.weight.shape[0]
-        L["pe"] = _Conv(pe_conv.weight.reshape(C0, -1, 1, 1, 1), pe_conv.bias, device=device)
+        L["pe"] = _Conv(pe_conv.weight.reshape(C0, -1, 1, 1, 1), pe_conv.bias, device=device, wsplit=self.wsplit)
         L["pe_ln"] = (f32(pe_ln.weight), f32(pe_ln.bias), float(pe_ln.eps))
         stages = []
         for si, stage in enumerate(bb.stages):
@@ -142,11 +143,13 @@ class RPNInferenceEngine:
             if si > 0:
                 pm = mods[0]; mods = mods[1:]
                 st["merge"] = dict(ln=(f32(pm.norm.weight), f32(pm.norm.bias), float(pm.norm.eps)), c_in=pm.dim,
-                                   red=_Conv(pm.reduction.weight.reshape(pm.reduction.weight.shape[0], -1, 1, 1, 1), None, device=device))
+                                   red=_Conv(pm.reduction.weight.reshape(pm.reduction.weight.shape[0], -1, 1, 1, 1), None, device=device,
+                                             wsplit=self.wsplit))
             for blk in mods:
                 a = blk.attn
                 C = a.qkv.weight.shape[1]
-                lin = lambda m, act=0: _Conv(m.weight.reshape(m.weight.shape[0], -1, 1, 1, 1), m.bias, relu=act, device=device)
+                lin = lambda m, act=0: _Conv(m.weight.reshape(m.weight.shape[0], -1, 1, 1, 1), m.bias, relu=act, device=device,
+                                             wsplit=self.wsplit)
                 st["blocks"].append(dict(
                     C=C, heads=a.num_heads, shift=int(a.shift_size[0]),
                     ln1=(f32(blk.norm1.weight), f32(blk.norm1.bias), float(blk.norm1.eps)),
@@ -155,8 +158,8 @@ class RPNInferenceEngine:
                     proj=lin(a.proj), mlp0=lin(blk.mlp[0], 2), mlp3=lin(blk.mlp[3])))
             stages.append(st)
         L["swin_stages"] = stages
-        L["lat"] = [_Conv(m.weight, m.bias, device=device) for m in bb.fpn_neck.lateral_convs]
-        L["fpn"] = [_Conv(m.weight, m.bias, device=device) for m in bb.fpn_neck.fpn_convs]
+        L["lat"] = [_Conv(m.weight, m.bias, device=device, wsplit=self.wsplit) for m in bb.fpn_neck.lateral_convs]
+        L["fpn"] = [_Conv(m.weight, m.bias, device=device, wsplit=self.wsplit and i > 0) for i, m in enumerate(bb.fpn_neck.fpn_convs)]
 
     def _pack_fcos(self, L, device):
         """FCOSHead (fcos/fcos.py:43-102): two towers of num_convs x [Conv3d 3^3 + GroupNorm(32) + ReLU] shared over levels,
@@ -179,23 +182,28 @@ class RPNInferenceEngine:
 
     def _pack_resnet(self, L, device):
         bb = self.backbone
+        ws = self.wsplit
         L["stem"] = _Conv(bb.conv1.weight, None, bb.bn1, relu=True, stem=True, device=device)
         blocks = []
         for stage in bb.layers:
             for blk in stage:
                 s = blk.stride
+                slab = blk.conv2.weight.shape[0] <= 64 and blk.conv2.weight.shape[1] == 64     # 64-channel 3^3 layers stay on the slab kernel
                 e = {
-                    "c1": _Conv(blk.conv1.weight, None, blk.bn1, stride=s, relu=True, device=device),
-                    "c2": _Conv(blk.conv2.weight, None, blk.bn2, relu=True, device=device),
-                    "c3": _Conv(blk.conv3.weight, None, blk.bn3, relu=True, device=device),   # ReLU after the residual add
+                    "c1": _Conv(blk.conv1.weight, None, blk.bn1, stride=s, relu=True, device=device, wsplit=ws),
+                    "c2": _Conv(blk.conv2.weight, None, blk.bn2, relu=True, device=device, wsplit=ws and not slab),
+                    "c3": _Conv(blk.conv3.weight, None, blk.bn3, relu=True, device=device, wsplit=ws),   # ReLU after the residual add
                     "ds": None, "stride": s,
                 }
                 if blk.downsample is not None:
-                    e["ds"] = _Conv(blk.downsample[0].weight, None, blk.downsample[1], stride=s, relu=False, device=device)
+                    e["ds"] = _Conv(blk.downsample[0].weight, None, blk.downsample[1], stride=s, relu=False, device=device, wsplit=ws)
                 blocks.append(e)
         L["blocks"] = blocks
-        L["lat"] = [_Conv(m.weight, m.bias, device=device) for m in bb.latlayers]
-        L["smooth"] = [_Conv(m.weight, m.bias, device=device) for m in bb.smooths]
+        L["lat"] = [_Conv(m.weight, m.bias, device=device, wsplit=ws) for m in bb.latlayers]
+        # smooth convs: P4 and P3 carry split weights; the P2 smooth (15 % of the scene's FLOPs, tensor-pipe bound) keeps single
+        # halves -- its weight rounding alone contributes ~2e-4 to P2 (measured by emulation)
+        nsm = len(bb.smooths)
+        L["smooth"] = [_Conv(m.weight, m.bias, device=device, wsplit=ws and i < nsm - 1) for i, m in enumerate(bb.smooths)]
 
     def _pack_vgg(self, L, device):
         """VGG_FPN (feature_extractor.py:289-377): stem [conv7 (s2 + max-pool when input_size >= 160, else s1), BN, ReLU], then
@@ -214,7 +222,8 @@ class RPNInferenceEngine:
                 m = seq[i]
                 if isinstance(m, torch.nn.Conv3d):
                     bn = seq[i + 1] if i + 1 < len(seq) and isinstance(seq[i + 1], torch.nn.BatchNorm3d) else None
-                    items.append(("conv", _Conv(m.weight, m.bias, bn, relu=True, device=device)))
+                    slab = m.weight.shape[0] <= 64 and m.weight.shape[1] == 64
+                    items.append(("conv", _Conv(m.weight, m.bias, bn, relu=True, device=device, wsplit=self.wsplit and not slab)))
                     i += 2 if bn is not None else 1
                 elif isinstance(m, torch.nn.MaxPool3d):
                     items.append(("pool", None)); i += 1
@@ -222,8 +231,8 @@ class RPNInferenceEngine:
                     i += 1                      # ReLU is fused into the conv epilogue
             stages.append(items)
         L["vgg_stages"] = stages
-        L["lat"] = [_Conv(m.weight, m.bias, device=device) for m in bb.fpn_neck.lateral_convs]
-        L["fpn"] = [_Conv(m.weight, m.bias, device=device) for m in bb.fpn_neck.fpn_convs]
+        L["lat"] = [_Conv(m.weight, m.bias, device=device, wsplit=self.wsplit) for m in bb.fpn_neck.lateral_convs]
+        L["fpn"] = [_Conv(m.weight, m.bias, device=device, wsplit=self.wsplit and i > 0) for i, m in enumerate(bb.fpn_neck.fpn_convs)]
 
     # ---------------------------------------------------------------- plan
     def _get_plan(self, n, dims, device, channels_last: bool = False, u8: bool = False):

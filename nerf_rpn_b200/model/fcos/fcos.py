@@ -12,6 +12,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from ...precision import resolve as _resolve_precision
+
 
 class Scale(nn.Module):
     def __init__(self, init_value=1.0):
@@ -84,7 +86,7 @@ class FCOSModule(nn.Module):
 
 
 class FCOSOverNeRF(nn.Module):
-    def __init__(self, args, backbone, fpn_strides, world_size=1) -> None:
+    def __init__(self, args, backbone, fpn_strides, world_size=1, precision=None) -> None:
         if not hasattr(backbone, "out_channels"):
             raise ValueError("backbone should contain an attribute out_channels specifying the number of output "
                              "channels (assumed to be the same for all the levels)")
@@ -93,6 +95,7 @@ class FCOSOverNeRF(nn.Module):
         self.world_size = world_size
         self.backbone = backbone
         self.fcos_module = FCOSModule(args, backbone.out_channels, fpn_strides, world_size=world_size)
+        self.precision = _resolve_precision(precision)
         self._engine = None
 
     def transform(self, meshes):
@@ -105,7 +108,7 @@ class FCOSOverNeRF(nn.Module):
 
     def engine(self):
         from ...engine import RPNInferenceEngine
-        precision = getattr(self, "precision", "bf16")      # "fp16": IEEE-half activations / weights
+        precision = _resolve_precision(getattr(self, "precision", None))
         if self._engine is None or self._engine.precision != precision:
             m, sel = self.fcos_module, self.fcos_module.box_selector_test
             self._engine = RPNInferenceEngine(self.backbone, m.head, fcos=dict(

@@ -5,12 +5,14 @@ The modules own ordinary nn.Conv3d / nn.BatchNorm3d parameters, created in the r
 torch.manual_seed(s) reproduces the reference's initial weights and state_dict keys are identical
 (conv1.weight, bn1.*, layers.{s}.{b}.conv{1,2,3}.weight, ..., smooths.{i}.*, latlayers.{i}.*).
 forward() never calls those nn modules: it runs the pre-packed tcgen05 engine (nerf_rpn_b200/engine.py).
-VGG_FPN / SwinTransformer_FPN (configs 1 and 3) are not built yet; the names exist so run_rpn.py imports resolve.
+VGG_FPN (config 1) and SwinTransformer_FPN (config 3) follow below on the same engine.
 """
 from typing import List
 
 import torch
 from torch import nn
+
+from ..precision import resolve as _resolve_precision
 
 
 class Bottleneck(nn.Module):
@@ -36,8 +38,9 @@ class Bottleneck(nn.Module):
 class ResNet_FPN_256(nn.Module):
     """ResNet-FPN backbone, same constructor / attributes as the reference (feature_extractor.py:159-194)."""
 
-    def __init__(self, block, layers, input_dim=4, is_max_pool=False):
+    def __init__(self, block, layers, input_dim=4, is_max_pool=False, precision=None):
         super().__init__()
+        self.precision = _resolve_precision(precision)
         if input_dim != 4 or not is_max_pool or block is not Bottleneck:
             raise NotImplementedError("the B200 engine implements the configuration run_rpn.py builds: "
                                       "ResNet_FPN_256(Bottleneck, [3,4,6,3], input_dim=4, is_max_pool=True)")
@@ -81,7 +84,7 @@ class ResNet_FPN_256(nn.Module):
     def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
         """x: (N,4,W,L,H) fp32 CUDA -> [P2,P3,P4,P5], each (N,256,w,l,h) fp32 (channels_last_3d strides)."""
         from ..engine import RPNInferenceEngine
-        precision = getattr(self, "precision", "bf16")
+        precision = _resolve_precision(getattr(self, "precision", None))
         if self._engine is None or self._engine.precision != precision:
             self._engine = RPNInferenceEngine(self, precision=precision)
         plan = self._engine.forward_device(x.contiguous())
@@ -114,8 +117,9 @@ class VGG_FPN(nn.Module):
     (Conv3d 3^3 + BN + ReLU)* [+ MaxPool3d(2,2,ceil_mode=True)], FPN neck on the four stage outputs."""
 
     def __init__(self, cfg: str = "AF", in_channels: int = 4, batch_norm: bool = True, input_size: int = 256,
-                 conv_at_start: bool = False):
+                 conv_at_start: bool = False, precision=None):
         super().__init__()
+        self.precision = _resolve_precision(precision)
         if conv_at_start or in_channels != 4 or not cfg.endswith("F"):
             raise NotImplementedError("the B200 engine implements VGG_FPN(cfg in {AF,DF,EF}, 4, batch_norm, input_size)")
         from .fpn import FPN
@@ -163,7 +167,7 @@ class VGG_FPN(nn.Module):
     def forward(self, X):
         """(N,4,W,L,H) fp32 CUDA -> tuple of 4 (N,256,w,l,h) fp32 feature maps (channels_last_3d strides)."""
         from ..engine import RPNInferenceEngine
-        precision = getattr(self, "precision", "bf16")
+        precision = _resolve_precision(getattr(self, "precision", None))
         if self._engine is None or self._engine.precision != precision:
             self._engine = RPNInferenceEngine(self, precision=precision)
         plan = self._engine.forward_device(X.contiguous())
@@ -230,8 +234,9 @@ class SwinTransformer_FPN(nn.Module):
 
     def __init__(self, patch_size, embed_dim, depths, num_heads, window_size, mlp_ratio=4.0, dropout=0.0, attention_dropout=0.0,
                  stochastic_depth_prob=0.1, norm_layer=None, block=None, downsample_layer=None, expand_dim=True,
-                 out_channels=256, input_dim=4):
+                 out_channels=256, input_dim=4, precision=None):
         super().__init__()
+        self.precision = _resolve_precision(precision)
         from functools import partial
         from .fpn import FPN
         if list(patch_size) != [4, 4, 4] or list(window_size) != [4, 4, 4] or input_dim != 4 or not expand_dim or dropout or attention_dropout:
@@ -271,7 +276,7 @@ class SwinTransformer_FPN(nn.Module):
 
     def forward(self, x):
         from ..engine import RPNInferenceEngine
-        precision = getattr(self, "precision", "bf16")
+        precision = _resolve_precision(getattr(self, "precision", None))
         if self._engine is None or self._engine.precision != precision:
             self._engine = RPNInferenceEngine(self, precision=precision)
         plan = self._engine.forward_device(x.contiguous())

@@ -8,6 +8,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from ..precision import resolve as _resolve_precision
 from .anchor import AnchorGenerator3D, RPNHead
 from .rpn import RegionProposalNetwork
 
@@ -23,7 +24,7 @@ class NeRFRegionProposalNetwork(nn.Module):
                  rpn_pre_nms_top_n_test=1000, rpn_post_nms_top_n_train=2000, rpn_post_nms_top_n_test=1000,
                  rpn_nms_thresh=0.7, rpn_fg_iou_thresh=0.7, rpn_bg_iou_thresh=0.3, rpn_batch_size_per_image=256,
                  rpn_positive_fraction=0.5, rpn_score_thresh=0.0, iou_batch_size=16, rotated_bbox=False,
-                 reg_loss_type="smooth_l1", **kwargs):
+                 reg_loss_type="smooth_l1", precision=None, **kwargs):
         if not hasattr(backbone, "out_channels"):
             raise ValueError("backbone should contain an attribute out_channels specifying the number of output "
                              "channels (assumed to be the same for all the levels)")
@@ -43,8 +44,12 @@ class NeRFRegionProposalNetwork(nn.Module):
         super().__init__()
         self.backbone = backbone
         self.rpn = rpn
+        self.precision = _resolve_precision(precision)     # "bf16" | "fp16" | "fp16_w2" (nerf_rpn_b200/precision.py); explicit, in repr
         self._engine = None
         self._engine_key = None
+
+    def extra_repr(self):
+        return f"precision={self.precision!r}"
 
     # nerf_rpn.py:129-146
     def transform(self, meshes, targets=None):
@@ -59,7 +64,7 @@ class NeRFRegionProposalNetwork(nn.Module):
     def engine(self):
         from ..engine import RPNInferenceEngine
         r = self.rpn
-        precision = getattr(self, "precision", "bf16")      # "fp16": 11-bit-significand activations
+        precision = _resolve_precision(self.precision)
         key = (r._pre_nms_top_n["testing"], r._post_nms_top_n["testing"], r.nms_thresh, r.score_thresh, r.rotate, precision)
         if self._engine is None or key != self._engine_key:
             ag = r.anchor_generator

@@ -163,6 +163,7 @@ def _conv_desc(levels, w, shift, cin, cout, taps, stride, relu, out_fp32) -> Con
             d.tap_off[t][k] = int(off[k])
     d.stride, d.relu, d.out_fp32 = int(stride), int(relu), int(bool(out_fp32))      # relu: 0 none, 1 ReLU, 2 GELU
     d.w, d.shift = w.data_ptr(), shift.data_ptr()
+    d.wsplit = 1 if w.dim() == 4 else 0          # (taps, 2, CoutPad, Cin): hi / lo weight planes (packing.split_hi_lo)
     d.n_levels = len(levels)
     for i, L in enumerate(levels):
         lv = d.level[i]

@@ -27,8 +27,18 @@ def conv_block_n(cout: int) -> int:
     return 64 if cout <= 64 else (128 if cout <= 128 else 256)
 
 
-def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None, cout_pad_to: Optional[int] = None, dtype=torch.bfloat16):
-    """(Cout, Cin, k, k, k) -> (taps, CoutPad, CinPad) bf16 and the tap offset table for 'same' padding (k odd)."""
+def split_hi_lo(w32: torch.Tensor, dtype) -> torch.Tensor:
+    """fp32 (..., Cout, Cin) -> 16-bit (..., 2, Cout, Cin): w ~= hi + lo with hi = round16(w), lo = round16(w - hi).  The two planes
+    are multiplied with the same activations into one fp32 accumulator (nrpn_conv_desc.wsplit), so the weights keep ~22 bits."""
+    hi = w32.to(dtype)
+    lo = (w32 - hi.float()).to(dtype)
+    return torch.stack([hi, lo], dim=-3).contiguous()
+
+
+def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None, cout_pad_to: Optional[int] = None, dtype=torch.bfloat16,
+                     split: bool = False):
+    """(Cout, Cin, k, k, k) -> (taps, CoutPad, CinPad) bf16 and the tap offset table for 'same' padding (k odd);
+    split=True: (taps, 2, CoutPad, CinPad) hi / lo planes (see split_hi_lo)."""
     cout, cin, kx, ky, kz = w.shape
     w = w.detach().float()
     if scale is not None:
@@ -47,6 +57,8 @@ def pack_conv_weight(w: torch.Tensor, scale: Optional[torch.Tensor] = None, cout
     m = torch.stack(mats, 0)                                   # (taps, Cout, Cin)
     out = torch.zeros((len(taps), cpad, cin_pad), dtype=torch.float32, device=w.device)
     out[:, :cout, :cin] = m
+    if split:
+        return split_hi_lo(out, dtype), taps
     return out.to(dtype).contiguous(), taps
 
 

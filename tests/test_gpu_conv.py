@@ -348,3 +348,50 @@ def test_bias_grad_and_relu_backward(ops, dtype):
     want = torch.where(act.float() > 0, dy, torch.zeros_like(dy))
     got = ops.relu_backward_(dy.clone(), act)
     assert torch.equal(got, want)
+
+
+WSPLIT_CASES = [
+    # name, dims, cin, cout, k, stride, relu, res mode  -> kernel variant exercised
+    ("ws_1x1_256_64_res", (8, 12, 16), 256, 64, 1, 1, True, "same"),       # igemm<64,2,2,tma-epilogue,wsplit>
+    ("ws_1x1_s2_256_128", (9, 12, 11), 256, 128, 1, 2, True, None),        # igemm<64,2,3,wsplit> path (stride-2 1^3)
+    ("ws_1x1_up_512_256", (13, 9, 7), 512, 256, 1, 1, False, "up"),        # igemm<64,2,3,wsplit> with up-sampled residual
+    ("ws_3x3_128_128", (20, 32, 32), 128, 128, 3, 1, True, None),          # igemm<128,4,1,wsplit>
+    ("ws_3x3_256_256", (10, 16, 16), 256, 256, 3, 1, True, None),          # igemm<256,2,1,wsplit> or <64,6,1,wsplit> (narrow)
+    ("ws_3x3_512_512_narrow", (5, 8, 8), 512, 512, 3, 1, True, None),      # igemm<64,6,1,wsplit>
+]
+
+
+@pytest.mark.parametrize("name,dims,cin,cout,k,stride,relu,resmode", WSPLIT_CASES)
+def test_conv_weight_split_cases(ops, name, dims, cin, cout, k, stride, relu, resmode):
+    """nrpn_conv_desc.wsplit: weights as hi + lo fp16 planes.  Against an fp32 conv on the UNROUNDED weights (fp16 activations)
+    the error must be accumulation-order only -- an order of magnitude below what single-fp16 weights give -- and the launch
+    must hit the wsplit variant of every igemm template."""
+    from nerf_rpn_b200 import packing
+    g = torch.Generator(device="cuda").manual_seed(hash(name) % 1000)
+    x = torch.randn((2, *dims, cin), device="cuda", generator=g).to(torch.float16)
+    w = torch.randn((cout, cin, k, k, k), device="cuda", generator=g) / (cin * k ** 3) ** 0.5
+    bias = torch.randn((cout,), device="cuda", generator=g)
+    od = tuple((d - 1) // stride + 1 for d in dims)
+    res = None
+    if resmode == "same":
+        res = torch.randn((2, *od, cout), device="cuda", generator=g).to(torch.float16)
+    elif resmode == "up":
+        res = torch.randn((2, *tuple((d + 1) // 2 for d in od), cout), device="cuda", generator=g).to(torch.float16)
+    errs = {}
+    for split in (False, True):
+        wp, taps = packing.pack_conv_weight(w, dtype=torch.float16, split=split)
+        shift = packing.pad_shift(bias, wp.shape[-2]).cuda()
+        y = torch.full((2, *od, cout), float("nan"), dtype=torch.float32, device="cuda")
+        a = [ops.ConvLevelArgs(x, y, 2, dims, od, cout, res=res, res_dims=None if res is None else res.shape[1:4],
+                               ldr=0 if res is None else res.shape[-1])]
+        variant = ops.conv3d_variant(a, wp, shift, cin, cout, taps, stride=stride, relu=relu, out_fp32=True)
+        assert ("wsplit" in variant) == split, variant
+        ops.conv3d_fprop(a, wp, shift, cin, cout, taps, stride=stride, relu=relu, out_fp32=True)
+        torch.cuda.synchronize()
+        w_exact, _ = packing.pack_conv_weight(w, dtype=torch.float32)
+        ref = emulate_conv(x.float(), w_exact.cuda(), taps, shift, od, stride=stride, relu=relu, res=res)[..., :cout]
+        assert not torch.isnan(y).any(), f"{name} [{variant}]: unwritten outputs"
+        errs[split] = ((y - ref).norm() / ref.norm()).item()
+        print(f"{name} [{variant}]: norm-wise rel err vs exact-weight fp32 conv {errs[split]:.3e}")
+    assert errs[True] < 1e-5, errs          # fp32 accumulation order + the lo plane's fp16-subnormal step only (K up to 13 824)
+    assert errs[False] > 10 * errs[True]    # single fp16 weights: ~1.4e-4 rounding error per weight

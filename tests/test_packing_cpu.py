@@ -58,3 +58,20 @@ def test_stem_stride1_packing_equals_conv7():
     got = emulate_conv(emulate_pack_stem_s1(x), wp.float(), taps, torch.zeros(64), (9, 8, 10))
     ref = F.conv3d(x, w.to(torch.bfloat16).float(), padding=3).permute(0, 2, 3, 4, 1)
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_weight_split_hi_lo_reconstructs_fp32():
+    """packing.split_hi_lo (nrpn_conv_desc.wsplit): hi + lo == w to ~2^-22 relative for fp16, layout (taps, 2, CoutPad, Cin)."""
+    import torch
+    from nerf_rpn_b200 import packing
+    torch.manual_seed(3)
+    w = torch.randn(72, 128, 3, 3, 3) * 0.05
+    wp, taps = packing.pack_conv_weight(w, dtype=torch.float16, split=True)
+    single, taps1 = packing.pack_conv_weight(w, dtype=torch.float16)
+    assert taps == taps1 and wp.shape == (27, 2, 128, 128) and single.shape == (27, 128, 128)
+    assert torch.equal(wp[:, 0], single)                                   # plane 0 = the ordinary rounded weights
+    exact, _ = packing.pack_conv_weight(w, dtype=torch.float32)
+    rec = wp[:, 0].float() + wp[:, 1].float()
+    # lo lands in fp16's subnormal range for weights this small: absolute error <= half a subnormal step (2^-25) + fp32 rounding
+    assert (rec - exact).abs().max().item() <= 2 ** -25 + 1e-9
+    assert (single.float() - exact).abs().max() > 100 * (rec - exact).abs().max()

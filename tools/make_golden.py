@@ -428,6 +428,35 @@ def gen_recall(n_scenes=12):
     np.savez_compressed(os.path.join(OUT, "recall_small_obb.npz"), **out)
 
 
+def gen_recall_large(n_scenes=32, n_gt=64):
+    """The recall fixture at a size that resolves north_star's 0.5 pt: 32 scenes x 64 planted OBBs = 2048 ground-truth boxes
+    (one box = 0.05 pt), same model / scene recipe as gen_recall (scene seeds 2000+i, n_gt boxes each)."""
+    import eval as ref_eval
+    import types
+    from tests import recipes
+    g = np.load(os.path.join(OUT, "rpn_small_obb.npz"))
+    ns = types.SimpleNamespace(ResNet_FPN_256=ResNet_FPN_256, Bottleneck=Bottleneck, AnchorGenerator3D=AnchorGenerator3D, RPNHead=RPNHead)
+    backbone, ag, head = recipes.build_small_model(ns, True, g)
+    model = NeRFRegionProposalNetwork(backbone, ag, head, rpn_pre_nms_top_n_test=2500, rpn_post_nms_top_n_test=2500,
+                                      rpn_nms_thresh=0.3, rpn_fg_iou_thresh=0.35, rpn_bg_iou_thresh=0.2,
+                                      rpn_score_thresh=0.0, rotated_bbox=True)
+    model.eval()
+    props, scores, gts = [], [], []
+    for i in range(n_scenes):
+        x, gt = recall_scene(i, n_gt=n_gt)
+        with torch.no_grad():
+            (_, proposals, _), _, sc = model([x])
+        props.append(proposals[0]); scores.append(sc[0]); gts.append(gt)
+        print("recall-large scene", i, tuple(proposals[0].shape), flush=True)
+    out = dict(n_scenes=np.int64(n_scenes), n_gt=np.int64(n_gt), n_props=np.array([p.shape[0] for p in props]))
+    thr = torch.tensor([0.25, 0.5])
+    for limit in (300, 1000, 2500):
+        r = ref_eval.evaluate_box_proposals_recall(props, scores, gts, thresholds=thr, limit=limit)
+        out[f"recalls_{limit}"] = r["recalls"].numpy()
+        print("limit", limit, "recall@0.25/0.5", r["recalls"].tolist(), "num_pos", r["num_pos"], flush=True)
+    np.savez_compressed(os.path.join(OUT, "recall_large_obb.npz"), **out)
+
+
 def gen_targets():
     """assign_targets_to_anchors (rpn.py:240-290) pieces run through the reference's own functions on CPU: obb2hbb_3d,
     batched_box_iou (chunks of 16 GT), Matcher(0.35, 0.2, allow_low_quality_matches=True) and the label mapping."""
@@ -516,6 +545,8 @@ if __name__ == "__main__":
         sys.path.insert(0, ROOT); gen_losses(); sys.exit(0)
     if "--targets-only" in sys.argv:
         sys.path.insert(0, ROOT); gen_targets(); sys.exit(0)
+    if "--recall-large-only" in sys.argv:
+        sys.path.insert(0, ROOT); gen_recall_large(); sys.exit(0)
     if "--recall-only" in sys.argv:
         sys.path.insert(0, ROOT); gen_recall(); sys.exit(0)
     if "--swin-only" in sys.argv:
