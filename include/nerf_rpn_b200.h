@@ -60,6 +60,14 @@ int nrpn_iou3d_matrix(const float *a, int n, const float *b, int m, int box_dim,
 int nrpn_sort_vertices(const float *vertices, const uint8_t *mask, const int32_t *num_valid, int b, int n, int m,
                        int32_t *idx, nrpn_stream_t stream);
 
+/* Rounding order of the oriented-IoU chain (csrc/box_iou.cuh).  The reference runs it as ~40 ATen kernels whose libm and reduction
+ * orders differ between its CPU and CUDA builds: bit 0 = operation order of the torch-CUDA kernels (bmm as fma, 4-accumulator /
+ * tree sums), bit 1 = CUDA sinf / cosf instead of fp64-rounded sin / cos.  Default 3: bit-identical to the reference running on
+ * the same GPU (tests/test_gpu_reference.py); 0: bit-identical to oracle/box_oracle.c's default (the reference's CPU build).
+ * Process-wide; takes effect for launches issued after the call (synchronous 4-byte copy to the device). */
+int nrpn_set_iou_mode(int mode);
+int nrpn_get_iou_mode(void);
+
 /* Greedy NMS, per group, fully on device (no host round trip per kept box as in utils.py:215-230).
  *   boxes  (n, box_dim) f32, scores (n) f32, group (n) i32 in [0,255] or NULL (single group)
  *   keep   (n) i64 out: indices kept, sorted by score descending (ties: lower index first)
@@ -301,6 +309,8 @@ typedef struct {
     void *workspace;
     size_t workspace_bytes;
     int32_t act_fp16;
+    int32_t dw_layout;       /* 0: dw is (taps, Cout, Cin); 1: dw is (Cout, Cin, taps) = nn.Conv3d.weight's own memory order */
+    int32_t accumulate;      /* 1: dw += result (a weight shared by several launches) */
 } nrpn_wgrad_desc;
 
 size_t nrpn_conv3d_wgrad_workspace_bytes(const nrpn_wgrad_desc *desc /*host*/);
@@ -316,6 +326,63 @@ size_t nrpn_bias_grad_workspace_bytes(int c);
 int nrpn_bias_grad(const void *dy_cl /* (rows, ld >= c) 16-bit */, long rows, int c, int ld, int act_fp16, float *db, void *workspace,
                    size_t workspace_bytes, nrpn_stream_t stream);
 int nrpn_relu_backward(void *dy_cl, const void *act_cl, size_t elements /* % 8 == 0 */, int act_fp16, nrpn_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Training step (row a18, BASELINE config 4): everything of the reference's `loss.backward(); clip_grad_norm_; optimizer.step()`
+ * (run_rpn.py:384-395) that is not one of the three GEMMs above.  Channels-last 16-bit activations / gradients (rows, c),
+ * c % 8 == 0; all reductions run in a fixed order (bit-reproducible).
+ * ---------------------------------------------------------------------------------------------- */
+size_t nrpn_chan_reduce_workspace_bytes(int c);
+/* nn.BatchNorm3d in train mode, statistics half (feature_extractor.py:38-43 under model.train()): stats = {mean[c], rstd[c],
+ * biased var[c]} over `rows`; when running_mean/var are given they are updated with `momentum` (unbiased variance) like torch. */
+int nrpn_bn_stats(const void *y, long rows, int c, int act_fp16, float eps, float *stats /*3c*/, float *running_mean,
+                  float *running_var, float momentum, void *workspace, size_t workspace_bytes, nrpn_stream_t stream);
+/* out = act(gamma * (y - mean) * rstd + beta (+ res)): normalise (+ residual, Bottleneck.forward :61-66) (+ ReLU) */
+int nrpn_bn_apply(const void *y, const void *res, void *out, long rows, int c, const float *stats, const float *gamma,
+                  const float *beta, int relu, int act_fp16, nrpn_stream_t stream);
+/* Backward of [BatchNorm (+ residual) (+ ReLU)]: g = dout * (act > 0 when relu); sums = {sum g * xhat = dgamma [c], sum g = dbeta [c]};
+ * dy = gamma * rstd * (g - sum g / rows - xhat * sum(g xhat) / rows); dres (optional) = g, the gradient of the skip branch. */
+int nrpn_bn_backward(const void *dout, const void *act, const void *y, void *dy, void *dres, long rows, int c, const float *stats,
+                     const float *gamma, float *sums /*2c*/, int relu, int act_fp16, void *workspace, size_t workspace_bytes,
+                     nrpn_stream_t stream);
+/* F.max_pool3d(3, 2, 1) with the recorded argmax (one byte per output element: window position of the first maximum) and its
+ * backward as a deterministic gather over the <= 8 windows that contain an input voxel (feature_extractor.py:219). */
+int nrpn_maxpool3d_k3s2_argmax(const void *in, int n, int x, int y, int z, int c, void *out, uint8_t *idx, int act_fp16, nrpn_stream_t stream);
+int nrpn_maxpool3d_k3s2_backward(const void *dy, const uint8_t *idx, int n, int x, int y, int z, int c, void *dx, int act_fp16, nrpn_stream_t stream);
+/* Backward of the FPN top-down merge fine += nearest_upsample(coarse) (feature_extractor.py:211-213): dcoarse (+)= sum of dfine over
+ * the fine voxels whose source index floor(f * coarse / fine) is the coarse voxel (same float expression as the forward epilogue). */
+int nrpn_upsample_nearest_backward(const void *dfine, int n, int xf, int yf, int zf, int xc, int yc, int zc, int c, void *dcoarse,
+                                   int accumulate, int act_fp16, nrpn_stream_t stream);
+/* Stride-2 1^3 convolutions (first block of ResNet stages 2-4): scatter = 0: dst (ceil/2 extents) = src sub-sampled at even
+ * voxels (the wgrad operand); scatter = 1: dst (x,y,z) = src (ceil/2 extents) zero-stuffed (the data gradient). */
+int nrpn_stride2(const void *src, void *dst, int n, int x, int y, int z, int c, int scatter, nrpn_stream_t stream);
+int nrpn_add_inplace(void *a, const void *b, size_t elements, int act_fp16, nrpn_stream_t stream);
+/* RPN losses of one mesh on its sampled anchors (rpn.py:372-417, smooth-L1 branch) and their gradient w.r.t. the predictor output.
+ * desc: level geometry as for nrpn_rpn_proposals (pred = fp32 (voxels, 128) rows [A logits | A*code deltas]); dpred[l]: 16-bit
+ * (voxels, 128) tensors, ZERO-FILLED by the caller; pos_idx / neg_idx: flat anchor indices (rpn.py:20-27 order) of the sampled
+ * positives / negatives; gt_pos (n_pos, 6|7): their matched ground-truth boxes (encoded on the fly: AABB_coder.py:14-56 /
+ * midpoint_offset_coder.py:106-158); norm = sampled anchors of the whole batch.  losses[0] += BCE sum / norm, losses[1] +=
+ * smooth-L1(beta 1/9) sum / norm; dpred = grad_scale * d(w_obj * L_obj + w_reg * L_reg)/dpred.  targets_out (optional, (n_pos,
+ * code)): the encoded regression targets (for tests). */
+int nrpn_rpn_loss(const nrpn_rpn_desc *desc /*host*/, void *const *dpred /*host array*/, const int64_t *pos_idx, int n_pos,
+                  const int64_t *neg_idx, int n_neg, const float *gt_pos, float norm, float w_obj, float w_reg, float grad_scale,
+                  float *losses /*2, accumulated*/, float *targets_out, int act_fp16, nrpn_stream_t stream);
+/* fp32 master weights (Cout, Cin, taps) -> 16-bit GEMM operands: fwd (taps, fwd_rows >= Cout, fwd_cols >= Cin) and, optionally,
+ * the data-gradient operand with mirrored taps and transposed matrices (taps, bwd_rows >= Cin, bwd_cols >= Cout).  Pad regions are
+ * not written (zero-fill the buffers once). */
+int nrpn_pack_weights(const float *w, int cout, int cin, int taps, void *fwd, int fwd_rows, int fwd_cols, void *bwd, int bwd_rows,
+                      int bwd_cols, int act_fp16, nrpn_stream_t stream);
+/* out[i] = idx[i] >= 0 ? src[idx[i]] * scale : 0 -- 16-bit (out16) or fp32 (out32): layouts given by a host-built index table
+ * (the space-to-depth stem weights and their gradient). */
+int nrpn_gather_pack(const float *src, const int32_t *idx, size_t n, void *out16, float *out32, float scale, int act_fp16, nrpn_stream_t stream);
+/* norm_out[0] = ||g||_2 * inv_scale (fp64 two-stage reduction) */
+size_t nrpn_grad_norm_workspace_bytes(void);
+int nrpn_grad_norm(const float *g, size_t n, float inv_scale, float *norm_out, void *workspace, size_t workspace_bytes, nrpn_stream_t stream);
+/* torch.nn.utils.clip_grad_norm_(max_norm) (coefficient read from the device: no host sync) fused with torch.optim.AdamW's update
+ * on flat fp32 buffers; gradients are multiplied by inv_scale first (loss scaling / world size). */
+int nrpn_adamw_step(float *p, const float *g, float *m, float *v, size_t n, const float *norm, float max_norm, float inv_scale, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, nrpn_stream_t stream);
 
 #ifdef __cplusplus
 }

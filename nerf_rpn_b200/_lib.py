@@ -54,7 +54,7 @@ class WgradDesc(ctypes.Structure):
     _fields_ = [("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("n_taps", ctypes.c_int32),
                 ("tap_off", (ctypes.c_int8 * 3) * MAX_TAPS), ("n_levels", ctypes.c_int32), ("level", WgradLevel * MAX_LEVELS),
                 ("dw", ctypes.c_void_p), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
-                ("act_fp16", ctypes.c_int32)]
+                ("act_fp16", ctypes.c_int32), ("dw_layout", ctypes.c_int32), ("accumulate", ctypes.c_int32)]
 
 
 class GnLevel(ctypes.Structure):
@@ -83,6 +83,8 @@ _SIGNATURES = {
     "nrpn_iou3d_matrix": (ctypes.c_int, [c_f32p, ctypes.c_int, c_f32p, ctypes.c_int, ctypes.c_int, c_f32p, c_stream]),
     "nrpn_sort_vertices": (ctypes.c_int, [c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_void_p, c_stream]),
+    "nrpn_set_iou_mode": (ctypes.c_int, [ctypes.c_int]),
+    "nrpn_get_iou_mode": (ctypes.c_int, []),
     "nrpn_nms_max_boxes": (ctypes.c_int, []),
     "nrpn_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "nrpn_nms": (ctypes.c_int, [c_f32p, ctypes.c_int, c_f32p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
@@ -128,6 +130,33 @@ _SIGNATURES = {
                                            ctypes.c_float, ctypes.c_int, c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, c_stream]),
     "nrpn_rowmax_f32": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, c_f32p, ctypes.c_void_p, c_stream]),
     "nrpn_recall_match": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, c_f32p, c_stream]),
+    # ---- training step (csrc/train.cu)
+    "nrpn_chan_reduce_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "nrpn_bn_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_float, c_f32p, c_f32p, c_f32p,
+                                     ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t, c_stream]),
+    "nrpn_bn_apply": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, c_f32p, c_f32p, c_f32p,
+                                     ctypes.c_int, ctypes.c_int, c_stream]),
+    "nrpn_bn_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long,
+                                        ctypes.c_int, c_f32p, c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, c_stream]),
+    "nrpn_maxpool3d_k3s2_argmax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_stream]),
+    "nrpn_maxpool3d_k3s2_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_int, ctypes.c_void_p, ctypes.c_int, c_stream]),
+    "nrpn_upsample_nearest_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_stream]),
+    "nrpn_stride2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_int, c_stream]),
+    "nrpn_add_inplace": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, c_stream]),
+    "nrpn_rpn_loss": (ctypes.c_int, [ctypes.POINTER(RpnDesc), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_int, c_f32p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_f32p, c_f32p,
+                                     ctypes.c_int, c_stream]),
+    "nrpn_pack_weights": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_stream]),
+    "nrpn_gather_pack": (ctypes.c_int, [c_f32p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, c_f32p, ctypes.c_float, ctypes.c_int, c_stream]),
+    "nrpn_grad_norm_workspace_bytes": (ctypes.c_size_t, []),
+    "nrpn_grad_norm": (ctypes.c_int, [c_f32p, ctypes.c_size_t, ctypes.c_float, c_f32p, ctypes.c_void_p, ctypes.c_size_t, c_stream]),
+    "nrpn_adamw_step": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_size_t, c_f32p, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                       ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, c_stream]),
     "nrpn_rpn_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(RpnDesc)]),
     "nrpn_rpn_proposals": (ctypes.c_int, [ctypes.POINTER(RpnDesc), c_f32p, c_f32p, c_f32p, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_size_t, c_stream]),

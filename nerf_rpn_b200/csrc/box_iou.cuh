@@ -5,12 +5,23 @@
 // One thread evaluates one pair entirely in registers; nothing (24-vertex arrays, masks, sort indices)
 // is materialised in HBM.
 //
-// Arithmetic contract (identical to oracle/box_oracle.c, so results are bit-identical to the oracle):
-// every fp32 operation is an explicitly rounded __f*_rn intrinsic (never contracted into FMA), sin/cos are
-// evaluated in fp64 and rounded once, sums run left to right.
+// Arithmetic contract: every fp32 operation is an explicitly rounded intrinsic in the reference's operation order.  Three steps
+// of the reference chain round differently on its CPU and CUDA builds; NRPN_IOU_MODE selects which build is reproduced
+// (measured on the B200 against the unmodified reference + its own K1 binary: tools/ref_gpu_probe.py, profiles/r02_ref_gpu_probe.json):
+//   bit 0 (operation order of the torch-CUDA kernels): box2corners_th's 4x2 * 2x2 torch.bmm = fma(y4, r1, x4 * r0); torch.sum over
+//         the 24 masked vertices = four interleaved accumulators, ((a0 + a1) + a2) + a3; torch.sum over the 8 shoelace terms =
+//         (t0+t4 + t2+t6) + (t1+t5 + t3+t7).  Mode bit clear: separately rounded mul/mul/add and left-to-right sums, the order of
+//         oracle/box_oracle.c's default (== the reference's CPU build on the golden vectors).
+//   bit 1 (libm): sin / cos through CUDA's sinf / cosf like ATen's CUDA kernels; clear: fp64 sin / cos rounded once (oracle).
+// The library default is 3 = "what the reference computes on this GPU" (nrpn_set_iou_mode); tests against the CPU oracle use 0.
+// Independent of the mode, K1's pseudo-angle denominator is fma(x, x, y * y): that is what nvcc makes of `x1*x1 + y1*y1` in the
+// reference's sort_vert_kernel.cu:25 (SASS of its own build: FMUL y*y; FFMA x*x + .).
 #pragma once
 #ifndef NRPN_SKIP_COMMON
 #include "common.cuh"
+#endif
+#ifndef NRPN_IOU_MODE
+#define NRPN_IOU_MODE 3
 #endif
 
 namespace nrpn {
@@ -31,8 +42,10 @@ struct ObbPrep {          // per-box derived data, computed once per box
 
 __device__ __forceinline__ void obb_prepare(const float* __restrict__ b, ObbPrep& p) {
     const float x = b[0], y = b[1], z = b[2], w = b[3], h = b[4], d = b[5], alpha = b[6];
-    const float s = (float)sin((double)alpha);
-    const float co = (float)cos((double)alpha);
+    const int mode = NRPN_IOU_MODE;
+    float s, co;
+    if (mode & 2) { s = sinf(alpha); co = cosf(alpha); }
+    else { s = (float)sin((double)alpha); co = (float)cos((double)alpha); }
     const float ns = -s;
     const float sx[4] = {0.5f, -0.5f, -0.5f, 0.5f};
     const float sy[4] = {0.5f, 0.5f, -0.5f, -0.5f};
@@ -40,8 +53,9 @@ __device__ __forceinline__ void obb_prepare(const float* __restrict__ b, ObbPrep
     for (int i = 0; i < 4; ++i) {
         const float x4 = __fmul_rn(sx[i], w);
         const float y4 = __fmul_rn(sy[i], h);
-        const float rx = __fadd_rn(__fmul_rn(x4, co), __fmul_rn(y4, ns));
-        const float ry = __fadd_rn(__fmul_rn(x4, s), __fmul_rn(y4, co));
+        float rx, ry;
+        if (mode & 1) { rx = __fmaf_rn(y4, ns, __fmul_rn(x4, co)); ry = __fmaf_rn(y4, co, __fmul_rn(x4, s)); }
+        else { rx = __fadd_rn(__fmul_rn(x4, co), __fmul_rn(y4, ns)); ry = __fadd_rn(__fmul_rn(x4, s), __fmul_rn(y4, co)); }
         p.c[2 * i] = __fadd_rn(rx, x);
         p.c[2 * i + 1] = __fadd_rn(ry, y);
     }
@@ -69,7 +83,7 @@ __device__ __forceinline__ bool vert_less(float x1, float y1, float q1, float x2
 }
 
 __device__ __forceinline__ float pseudo_angle(float x, float y) {
-    const float n = (float)((double)__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)) + 1e-8);
+    const float n = (float)((double)__fmaf_rn(x, x, __fmul_rn(y, y)) + 1e-8);       // nvcc contracts x1*x1 + y1*y1 in K1 (see header)
     return __fdiv_rn(__fmul_rn(fabsf(x), x), n);
 }
 
@@ -134,12 +148,25 @@ __device__ __forceinline__ float rect_inter_area(const float* __restrict__ c1, c
     }
     // mean of the valid vertices (sort_indices, :121-141)
     int nv = __popc(mk);
+    const int mode = NRPN_IOU_MODE;
     float sxm = 0.f, sym = 0.f;
+    if (mode & 1) {                             // ATen CUDA reduce: 4 interleaved accumulators, combined left to right
+        float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < 24; ++k) {
-        const float mf = ((mk >> k) & 1u) ? 1.0f : 0.0f;
-        sxm = __fadd_rn(sxm, __fmul_rn(vx[k], mf));
-        sym = __fadd_rn(sym, __fmul_rn(vy[k], mf));
+        for (int k = 0; k < 24; ++k) {
+            const float mf = ((mk >> k) & 1u) ? 1.0f : 0.0f;
+            ax[k & 3] = __fadd_rn(ax[k & 3], __fmul_rn(vx[k], mf));
+            ay[k & 3] = __fadd_rn(ay[k & 3], __fmul_rn(vy[k], mf));
+        }
+        sxm = __fadd_rn(__fadd_rn(__fadd_rn(ax[0], ax[1]), ax[2]), ax[3]);
+        sym = __fadd_rn(__fadd_rn(__fadd_rn(ay[0], ay[1]), ay[2]), ay[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 24; ++k) {
+            const float mf = ((mk >> k) & 1u) ? 1.0f : 0.0f;
+            sxm = __fadd_rn(sxm, __fmul_rn(vx[k], mf));
+            sym = __fadd_rn(sym, __fmul_rn(vy[k], mf));
+        }
     }
     const float mx = __fdiv_rn(sxm, (float)nv), my = __fdiv_rn(sym, (float)nv);
     // pad vertex: first masked-out intersection point
@@ -150,65 +177,81 @@ __device__ __forceinline__ float rect_inter_area(const float* __restrict__ c1, c
     for (int k = 0; k < 24; ++k) if (k == pad) { padx = vx[k]; pady = vy[k]; }
     const float tpp = __fsub_rn(__fmul_rn(padx, pady), __fmul_rn(pady, padx));   // pad x pad term
 
-    float total = 0.f;
-    if (nv < 3) {
+    // the 8 shoelace terms t[i] = sel[i] x sel[i+1] of the gathered 9-vertex list (calculate_area, :143-159)
+    float t[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) total = __fadd_rn(total, tpp);
-        return __fdiv_rn(fabsf(total), 2.0f);
-    }
-    // normalised coordinates and pseudo-angles of the valid vertices
-    float nx[24], ny[24], qq[24];
-#pragma unroll
-    for (int k = 0; k < 24; ++k) {
-        nx[k] = __fsub_rn(vx[k], mx); ny[k] = __fsub_rn(vy[k], my);
-        qq[k] = (((mk >> k) & 1u) || k == 0) ? pseudo_angle(nx[k], ny[k]) : 0.f;   // vertex 0 is the default pick
-    }
-    // selection sort by angle (sort_vertices_kernel, :70-106), shoelace accumulated on the fly
-    const int nsel = nv < 9 ? nv : 9;
-    float pnx = 0.f, pny = 0.f, pq = 0.f;       // previous pick, normalised
-    float fx = 0.f, fy = 0.f;                   // first pick, raw
-    float lx = 0.f, ly = 0.f;                   // last pick, raw
-    float total3 = 0.f, s3x = 0.f, s3y = 0.f;   // state after 4 picks (identical-box special case)
-    unsigned long long takes = 0ull;
-    for (int j = 0; j < nsel; ++j) {
-        float bx = 1.0f, by = -eps_f(), bq = 1.0f;   // "big" start value (1, -EPSILON): q = 1*1/(1+1e-16+1e-8) -> 1.0f
-        int take = 0;
-        float rx = vx[0], ry = vy[0], tnx = nx[0], tny = ny[0], tq = qq[0];   // default pick is vertex 0
+    for (int i = 0; i < 8; ++i) t[i] = tpp;     // nv < 3: every index is the pad vertex
+    if (nv >= 3) {
+        // normalised coordinates and pseudo-angles of the valid vertices
+        float nx[24], ny[24], qq[24];
 #pragma unroll
         for (int k = 0; k < 24; ++k) {
-            if ((mk >> k) & 1u) {
-                bool ok = vert_less(nx[k], ny[k], qq[k], bx, by, bq);
-                if (ok && j > 0) ok = vert_less(pnx, pny, pq, nx[k], ny[k], qq[k]);
-                if (ok) { bx = nx[k]; by = ny[k]; bq = qq[k]; take = k; rx = vx[k]; ry = vy[k]; tnx = nx[k]; tny = ny[k]; tq = qq[k]; }
+            nx[k] = __fsub_rn(vx[k], mx); ny[k] = __fsub_rn(vy[k], my);
+            qq[k] = (((mk >> k) & 1u) || k == 0) ? pseudo_angle(nx[k], ny[k]) : 0.f;   // vertex 0 is the default pick
+        }
+        // selection sort by angle (sort_vertices_kernel, :70-106), shoelace terms recorded on the fly
+        const int nsel = nv < 9 ? nv : 9;
+        float pnx = 0.f, pny = 0.f, pq = 0.f;       // previous pick, normalised
+        float fx = 0.f, fy = 0.f;                   // first pick, raw
+        float lx = 0.f, ly = 0.f;                   // last pick, raw
+        float s3x = 0.f, s3y = 0.f;                 // fourth pick (identical-box special case)
+        unsigned long long takes = 0ull;
+        for (int j = 0; j < nsel; ++j) {
+            float bx = 1.0f, by = -eps_f(), bq = 1.0f;   // "big" start value (1, -EPSILON): q = 1*1/(1+1e-16+1e-8) -> 1.0f
+            int take = 0;
+            float rx = vx[0], ry = vy[0], tnx = nx[0], tny = ny[0], tq = qq[0];   // default pick is vertex 0
+#pragma unroll
+            for (int k = 0; k < 24; ++k) {
+                if ((mk >> k) & 1u) {
+                    bool ok = vert_less(nx[k], ny[k], qq[k], bx, by, bq);
+                    if (ok && j > 0) ok = vert_less(pnx, pny, pq, nx[k], ny[k], qq[k]);
+                    if (ok) { bx = nx[k]; by = ny[k]; bq = qq[k]; take = k; rx = vx[k]; ry = vy[k]; tnx = nx[k]; tny = ny[k]; tq = qq[k]; }
+                }
+            }
+            // (when nothing qualified the reference leaves idx = 0 and reads vertex 0, valid or not, next round)
+            takes |= (unsigned long long)take << (8 * (j & 7));
+            if (j == 0) { fx = rx; fy = ry; }
+            else {
+                const float term = __fsub_rn(__fmul_rn(lx, ry), __fmul_rn(ly, rx));
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (q == j - 1) t[q] = term;
+            }
+            if (j == 3) { s3x = rx; s3y = ry; }
+            lx = rx; ly = ry; pnx = tnx; pny = tny; pq = tq;
+        }
+        bool special = false;
+        if (nv == 8) {                              // identical boxes (:114-129)
+            int counter = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int check = (int)((takes >> (8 * j)) & 0xFF);
+#pragma unroll
+                for (int k = 4; k < 8; ++k) counter += ((int)((takes >> (8 * k)) & 0xFF) == check) ? 1 : 0;
+            }
+            special = counter == 4;
+        }
+        const float t_first_pad = __fsub_rn(__fmul_rn(fx, pady), __fmul_rn(fy, padx));          // first pick -> pad
+        if (special) {                              // idx = p0 p1 p2 p3 p0 pad pad pad pad
+            t[3] = __fsub_rn(__fmul_rn(s3x, fy), __fmul_rn(s3y, fx));
+            t[4] = t_first_pad;
+            t[5] = tpp; t[6] = tpp; t[7] = tpp;
+        } else if (nv < 9) {                        // idx = p0 .. p(nv-1) p0 pad ...
+            const float t_close = __fsub_rn(__fmul_rn(lx, fy), __fmul_rn(ly, fx));
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q == nv - 1) t[q] = t_close;
+                else if (q == nv) t[q] = t_first_pad;
+                else if (q > nv) t[q] = tpp;
             }
         }
-        // (when nothing qualified the reference leaves idx = 0 and reads vertex 0, valid or not, next round)
-        takes |= (unsigned long long)take << (8 * (j & 7));
-        if (j == 0) { fx = rx; fy = ry; }
-        else total = __fadd_rn(total, __fsub_rn(__fmul_rn(lx, ry), __fmul_rn(ly, rx)));
-        if (j == 3) { total3 = total; s3x = rx; s3y = ry; }
-        lx = rx; ly = ry; pnx = tnx; pny = tny; pq = tq;
     }
-    bool special = false;
-    if (nv == 8) {                              // identical boxes (:114-129)
-        int counter = 0;
+    float total;
+    if (mode & 1) {                                 // ATen CUDA reduce over 8 contiguous elements: (t0+t4 + t2+t6) + (t1+t5 + t3+t7)
+        total = __fadd_rn(__fadd_rn(__fadd_rn(t[0], t[4]), __fadd_rn(t[2], t[6])), __fadd_rn(__fadd_rn(t[1], t[5]), __fadd_rn(t[3], t[7])));
+    } else {
+        total = t[0];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int check = (int)((takes >> (8 * j)) & 0xFF);
-#pragma unroll
-            for (int k = 4; k < 8; ++k) counter += ((int)((takes >> (8 * k)) & 0xFF) == check) ? 1 : 0;
-        }
-        special = counter == 4;
-    }
-    if (special) {
-        total = __fadd_rn(total3, __fsub_rn(__fmul_rn(s3x, fy), __fmul_rn(s3y, fx)));   // s3 -> s0
-        total = __fadd_rn(total, __fsub_rn(__fmul_rn(fx, pady), __fmul_rn(fy, padx)));  // s0 -> pad
-        total = __fadd_rn(total, tpp); total = __fadd_rn(total, tpp); total = __fadd_rn(total, tpp);
-    } else if (nv < 9) {
-        total = __fadd_rn(total, __fsub_rn(__fmul_rn(lx, fy), __fmul_rn(ly, fx)));      // close the polygon
-        int terms = nv;                                                                 // terms so far: nv
-        if (terms < 8) { total = __fadd_rn(total, __fsub_rn(__fmul_rn(fx, pady), __fmul_rn(fy, padx))); ++terms; }
-        for (; terms < 8; ++terms) total = __fadd_rn(total, tpp);
+        for (int i = 1; i < 8; ++i) total = __fadd_rn(total, t[i]);
     }
     return __fdiv_rn(fabsf(total), 2.0f);
 }

@@ -28,10 +28,10 @@ constexpr int kWgThreads = 192;
 struct WgLevelDev { int n, X, chunks, zp, brick_begin; };      // chunks = ceil(Y * zp / 64) K-blocks per x-plane
 
 struct WgDev {
-    int n_levels, n_taps, cin, cout, n_t, m_tiles, splits, total_bricks, fp16;
+    int n_levels, n_taps, cin, cout, n_t, m_tiles, n_tiles, splits, total_bricks, fp16, dw_layout, accumulate;
     signed char tap[NRPN_CONV_MAX_TAPS][4];
     WgLevelDev lv[NRPN_CONV_MAX_LEVELS];
-    float* partial;                            // [tap][m_tile][split][128][n_t]
+    float* partial;                            // [tap][m_tile][n_tile][split][128][n_t]
 };
 
 struct WgMaps { CUtensorMap dy[NRPN_CONV_MAX_LEVELS]; CUtensorMap x[NRPN_CONV_MAX_LEVELS][3]; };      // x[level][dz + 1]: z-shifted copies
@@ -59,14 +59,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_kernel(const __gri
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t idesc = P.fp16 ? ptx::make_idesc_f16(128, P.n_t) : ptx::make_idesc_bf16(128, P.n_t);
-    const int items = P.n_taps * P.m_tiles * P.splits;
+    const int items = P.n_taps * P.m_tiles * P.n_tiles * P.splits;
     uint32_t tphase = 0;
     int stage_p = 0, stage_c = 0; uint32_t phase_p = 0, phase_c = 0;          // producer / consumer ring positions (persist over items)
 
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int split = item % P.splits;
-        const int mt = (item / P.splits) % P.m_tiles;
-        const int tap = item / (P.splits * P.m_tiles);
+        const int nt = (item / P.splits) % P.n_tiles;
+        const int mt = (item / (P.splits * P.n_tiles)) % P.m_tiles;
+        const int tap = item / (P.splits * P.n_tiles * P.m_tiles);
         const int b0 = (int)(((long)P.total_bricks * split) / P.splits), b1 = (int)(((long)P.total_bricks * (split + 1)) / P.splits);
         if (warp == 0) {
             const bool leader = ptx::elect_one();
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_kernel(const __gri
                     uint8_t* sa = smem + stage_p * stage_bytes;
                     ptx::mbar_expect_tx(&full_bar[stage_p], (uint32_t)stage_bytes);
                     ptx::tma_load_4d(sa, &maps.dy[l], &full_bar[stage_p], f0, x0, mt * 128, nb);
-                    ptx::tma_load_4d(sa + kWgABytes, &maps.x[l][dz + 1], &full_bar[stage_p], f0 + dy * L.zp, x0 + dx, 0, nb);   // z shift lives in the copy
+                    ptx::tma_load_4d(sa + kWgABytes, &maps.x[l][dz + 1], &full_bar[stage_p], f0 + dy * L.zp, x0 + dx, nt * P.n_t, nb);   // z shift lives in the copy
                 }
                 __syncwarp();
                 if (++stage_p == kWgStages) { stage_p = 0; phase_p ^= 1u; }
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_kernel(const __gri
         } else {
             // epilogue warps 2..5: row = output channel of the slice, columns = input channels
             const int q = warp & 3, row = q * 32 + lane;
-            float* out = P.partial + ((((size_t)tap * P.m_tiles + mt) * P.splits + split) * 128 + row) * P.n_t;
+            float* out = P.partial + (((((size_t)tap * P.m_tiles + mt) * P.n_tiles + nt) * P.splits + split) * 128 + row) * P.n_t;
             ptx::mbar_wait(tfull_bar, tphase);
             ptx::tc_fence_after();
             const bool empty = (b1 <= b0);                               // nothing accumulated: the TMEM contents are stale
@@ -136,17 +137,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_kernel(const __gri
 }
 
 // dW[tap][co][ci] = sum over splits (fixed order) of the partial tiles
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_taps, int m_tiles, int splits, int n_t, int cout, int cin,
-                                    float* __restrict__ dw) {
+// layout 0: dw (taps, Cout, Cin);  layout 1: dw (Cout, Cin, taps) = nn.Conv3d.weight's own memory order (taps = kx*ky*kz row-major);
+// accumulate: dw += (gradient accumulation of a shared weight over separate launches)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_taps, int m_tiles, int n_tiles, int splits, int n_t, int cout, int cin,
+                                    float* __restrict__ dw, int layout, int accumulate) {
     const size_t total = (size_t)n_taps * cout * cin;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int ci = (int)(t % cin); size_t v = t / cin;
         const int co = (int)(v % cout); const int tap = (int)(v / cout);
-        const int mt = co >> 7, row = co & 127;
-        const float* p = partial + ((((size_t)tap * m_tiles + mt) * splits) * 128 + row) * n_t + ci;
+        const int mt = co >> 7, row = co & 127, nt = ci / n_t, col = ci - nt * n_t;
+        const float* p = partial + (((((size_t)tap * m_tiles + mt) * n_tiles + nt) * splits) * 128 + row) * n_t + col;
         float s = 0.f;
         for (int sp = 0; sp < splits; ++sp) s += p[(size_t)sp * 128 * n_t];
-        dw[t] = s;
+        const size_t o = layout ? ((size_t)co * cin + ci) * n_taps + tap : t;
+        dw[o] = accumulate ? dw[o] + s : s;
     }
 }
 
@@ -196,10 +200,13 @@ int nrpn_transpose_to_planar(const void* in_cl, int n, int x, int y, int z, int 
 
 static int wgrad_plan(const nrpn_wgrad_desc* d, WgDev& P) {
     if (!d || d->n_levels < 1 || d->n_levels > NRPN_CONV_MAX_LEVELS || d->n_taps < 1 || d->n_taps > NRPN_CONV_MAX_TAPS) return NRPN_ERR_INVALID;
-    if (d->cout < 128 || d->cout % 128 != 0 || d->cin < 32 || d->cin > 256 || d->cin % 32 != 0) return NRPN_ERR_UNSUPPORTED;
+    // Cout: any multiple of 8 (a last slice narrower than 128 rows is zero-filled by TMA: the box exceeds the tensor's channel
+    // extent); Cin: a multiple of 32 up to 256, or a multiple of 256 (N tiles of 256 input channels)
+    if (d->cout < 8 || d->cout % 8 != 0 || d->cin < 32 || d->cin % 32 != 0 || (d->cin > 256 && d->cin % 256 != 0)) return NRPN_ERR_UNSUPPORTED;
     memset(&P, 0, sizeof(P));
-    P.n_levels = d->n_levels; P.n_taps = d->n_taps; P.cin = d->cin; P.cout = d->cout; P.n_t = d->cin; P.m_tiles = d->cout / 128;
-    P.fp16 = d->act_fp16 ? 1 : 0;
+    P.n_levels = d->n_levels; P.n_taps = d->n_taps; P.cin = d->cin; P.cout = d->cout;
+    P.n_t = d->cin > 256 ? 256 : d->cin; P.n_tiles = d->cin / P.n_t; P.m_tiles = ceil_div(d->cout, 128);
+    P.fp16 = d->act_fp16 ? 1 : 0; P.dw_layout = d->dw_layout ? 1 : 0; P.accumulate = d->accumulate ? 1 : 0;
     for (int t = 0; t < d->n_taps; ++t) { P.tap[t][0] = d->tap_off[t][0]; P.tap[t][1] = d->tap_off[t][1]; P.tap[t][2] = d->tap_off[t][2]; P.tap[t][3] = 0; }
     int max_dz = 1;
     for (int t = 0; t < d->n_taps; ++t) { const int a = d->tap_off[t][2] < 0 ? -d->tap_off[t][2] : d->tap_off[t][2]; if (a > max_dz) max_dz = a; }
@@ -214,7 +221,7 @@ static int wgrad_plan(const nrpn_wgrad_desc* d, WgDev& P) {
         bricks += S.n * S.x * L.chunks;
     }
     P.total_bricks = bricks;
-    const int base = d->n_taps * P.m_tiles;
+    const int base = d->n_taps * P.m_tiles * P.n_tiles;
     int splits = num_sms() / base;                      // one wave of work items: (taps x Cout slices x splits) <= SMs
     if (splits > bricks) splits = bricks;
     if (splits < 1) splits = 1;
@@ -225,7 +232,7 @@ static int wgrad_plan(const nrpn_wgrad_desc* d, WgDev& P) {
 size_t nrpn_conv3d_wgrad_workspace_bytes(const nrpn_wgrad_desc* d) {
     WgDev P;
     if (wgrad_plan(d, P) != NRPN_OK) return 0;
-    return (size_t)P.n_taps * P.m_tiles * P.splits * 128 * P.n_t * sizeof(float) + 256;
+    return (size_t)P.n_taps * P.m_tiles * P.n_tiles * P.splits * 128 * P.n_t * sizeof(float) + 256;
 }
 
 int nrpn_conv3d_wgrad(const nrpn_wgrad_desc* d, nrpn_stream_t stream) {
@@ -270,7 +277,7 @@ int nrpn_conv3d_wgrad(const nrpn_wgrad_desc* d, nrpn_stream_t stream) {
         NRPN_CUDA_TRY(cudaFuncSetAttribute(conv3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         smem_set = smem;
     }
-    const int items = P.n_taps * P.m_tiles * P.splits;
+    const int items = P.n_taps * P.m_tiles * P.n_tiles * P.splits;
     const int grid = items < num_sms() ? items : num_sms();
     cudaStream_t st = (cudaStream_t)stream;
     conv3d_wgrad_kernel<<<grid, kWgThreads, smem, st>>>(maps, P);
@@ -278,7 +285,7 @@ int nrpn_conv3d_wgrad(const nrpn_wgrad_desc* d, nrpn_stream_t stream) {
     const size_t total = (size_t)P.n_taps * P.cout * P.cin;
     size_t blocks = ceil_div(total, (size_t)256);
     if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
-    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(P.partial, P.n_taps, P.m_tiles, P.splits, P.n_t, P.cout, P.cin, d->dw);
+    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(P.partial, P.n_taps, P.m_tiles, P.n_tiles, P.splits, P.n_t, P.cout, P.cin, d->dw, P.dw_layout, P.accumulate);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }

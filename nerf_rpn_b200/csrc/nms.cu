@@ -6,6 +6,8 @@
 // exact-zero culling by bounding circle / z range), resolve each group with one CTA that walks the matrix
 // 64 rows at a time (warp-shuffle resolve of the diagonal word, coalesced OR of the kept rows), then sort
 // the survivors by score.  No host round trips; everything is stream-ordered.
+namespace nrpn { static __device__ int g_iou_mode = 3; }      // see box_iou.cuh: which build of the reference chain is reproduced
+#define NRPN_IOU_MODE (::nrpn::g_iou_mode)
 #include "box_iou.cuh"
 #include "nms_internal.cuh"
 
@@ -698,6 +700,15 @@ int nrpn_sort_vertices(const float* vertices, const uint8_t* mask, const int32_t
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
+
+static int g_iou_mode_host = 3;
+int nrpn_set_iou_mode(int mode) {
+    if (mode < 0 || mode > 3) return NRPN_ERR_INVALID;
+    NRPN_CUDA_TRY(cudaMemcpyToSymbol(nrpn::g_iou_mode, &mode, sizeof(int)));
+    g_iou_mode_host = mode;
+    return NRPN_OK;
+}
+int nrpn_get_iou_mode(void) { return g_iou_mode_host; }
 
 int nrpn_nms_max_boxes(void) { return kNmsMaxBoxes; }
 

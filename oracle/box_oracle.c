@@ -32,6 +32,19 @@
 #include <string.h>
 
 #define ORC_EPS_D 1e-8          /* EPSILON, box_intersection_2d.py:9 / sort_vert_kernel.cu:8 */
+
+/* Arithmetic mode (orc_set_mode), mirrors NRPN_IOU_MODE of csrc/box_iou.cuh:
+ *   0 (default)  the conventions above == the reference's CPU build on the golden vectors;
+ *   bit 0        operation ORDER of the reference's torch-CUDA build, measured on the B200 by tools/ref_gpu_probe.py against the
+ *                unmodified reference: box2corners_th's bmm = fma(y4, r1, x4*r0); torch.sum over the 24 masked vertices = four
+ *                interleaved accumulators ((a0+a1)+a2)+a3; torch.sum over the 8 shoelace terms = (t0+t4 + t2+t6) + (t1+t5 + t3+t7);
+ *   bit 1        sin / cos through float sinf / cosf (the CUDA build calls CUDA's; a CPU libm can only approximate that, so
+ *                this bit exists for structural cross-checks of the kernel logic, not for bit-parity with a GPU).
+ * K1's pseudo-angle denominator is fma(x, x, y*y) in every mode: nvcc contracts `x1*x1 + y1*y1` (sort_vert_kernel.cu:25) -- SASS
+ * of the reference's own build (FMUL y*y; FFMA x*x + .), confirmed bit-for-bit against that binary on 600 000 polygons. */
+static int orc_mode = 0;
+void orc_set_mode(int m) { orc_mode = m; }
+int orc_get_mode(void) { return orc_mode; }
 #define ORC_MAXV 24
 #define ORC_NIDX 9
 
@@ -42,14 +55,20 @@ static void orc_corners(float x, float y, float w, float h, float alpha, float c
 {
     static const float sx[4] = {0.5f, -0.5f, -0.5f, 0.5f};
     static const float sy[4] = {0.5f, 0.5f, -0.5f, -0.5f};
-    float s = (float)sin((double)alpha);
-    float co = (float)cos((double)alpha);
+    float s = (orc_mode & 2) ? sinf(alpha) : (float)sin((double)alpha);
+    float co = (orc_mode & 2) ? cosf(alpha) : (float)cos((double)alpha);
     float ns = -s;
     for (int i = 0; i < 4; ++i) {
         float x4 = sx[i] * w;
         float y4 = sy[i] * h;
-        float rx = x4 * co;  float t = y4 * ns;  rx = rx + t;   /* row . rot_T[:,0] */
-        float ry = x4 * s;   t = y4 * co;        ry = ry + t;   /* row . rot_T[:,1] */
+        float rx, ry;
+        if (orc_mode & 1) {
+            float t = x4 * co; rx = fmaf(y4, ns, t);
+            t = x4 * s;        ry = fmaf(y4, co, t);
+        } else {
+            rx = x4 * co;  float t = y4 * ns;  rx = rx + t;   /* row . rot_T[:,0] */
+            ry = x4 * s;   t = y4 * co;        ry = ry + t;   /* row . rot_T[:,1] */
+        }
         c[2 * i + 0] = rx + x;
         c[2 * i + 1] = ry + y;
     }
@@ -61,8 +80,8 @@ static int orc_cmp(float x1, float y1, float x2, float y2)
     if ((double)fabsf(x1 - x2) < ORC_EPS_D && (double)fabsf(y2 - y1) < ORC_EPS_D) return 0;
     if (y1 > 0 && y2 < 0) return 1;
     if (y1 < 0 && y2 > 0) return 0;
-    float n1 = (float)((double)(x1 * x1 + y1 * y1) + ORC_EPS_D);
-    float n2 = (float)((double)(x2 * x2 + y2 * y2) + ORC_EPS_D);
+    float n1 = (float)((double)fmaf(x1, x1, y1 * y1) + ORC_EPS_D);     /* nvcc's contraction of x1*x1 + y1*y1 (see orc_mode note) */
+    float n2 = (float)((double)fmaf(x2, x2, y2 * y2) + ORC_EPS_D);
     float q1 = fabsf(x1) * x1 / n1;
     float q2 = fabsf(x2) * x2 / n2;
     float d = q1 - q2;
@@ -169,11 +188,24 @@ static float orc_inter_area(const float c1[8], const float c2[8])
     }
     /* sort_indices, :121-141 */
     int nv = 0; float sxm = 0.f, sym = 0.f;
-    for (int k = 0; k < ORC_MAXV; ++k) {
-        float mf = mk[k] ? 1.0f : 0.0f;
-        nv += mk[k];
-        sxm = sxm + vx[k] * mf;
-        sym = sym + vy[k] * mf;
+    if (orc_mode & 1) {
+        float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < ORC_MAXV; ++k) {
+            float mf = mk[k] ? 1.0f : 0.0f;
+            nv += mk[k];
+            float px = vx[k] * mf, py = vy[k] * mf;
+            ax[k & 3] = ax[k & 3] + px;
+            ay[k & 3] = ay[k & 3] + py;
+        }
+        sxm = ax[0] + ax[1]; sxm = sxm + ax[2]; sxm = sxm + ax[3];
+        sym = ay[0] + ay[1]; sym = sym + ay[2]; sym = sym + ay[3];
+    } else {
+        for (int k = 0; k < ORC_MAXV; ++k) {
+            float mf = mk[k] ? 1.0f : 0.0f;
+            nv += mk[k];
+            sxm = sxm + vx[k] * mf;
+            sym = sym + vy[k] * mf;
+        }
     }
     float mx = sxm / (float)nv, my = sym / (float)nv;
     float vn[2 * ORC_MAXV];
@@ -181,11 +213,20 @@ static float orc_inter_area(const float c1[8], const float c2[8])
     int32_t idx[ORC_NIDX];
     orc_sort_one(vn, mk, nv, ORC_MAXV, idx);
     /* calculate_area, :143-159 (gathers the un-normalised vertices) */
-    float total = 0.f;
+    float t[8];
     for (int i = 0; i < 8; ++i) {
         float a = vx[idx[i]] * vy[idx[i + 1]];
         float bb = vy[idx[i]] * vx[idx[i + 1]];
-        total = total + (a - bb);
+        t[i] = a - bb;
+    }
+    float total;
+    if (orc_mode & 1) {
+        float a0 = t[0] + t[4], a1 = t[1] + t[5], a2 = t[2] + t[6], a3 = t[3] + t[7];
+        float l = a0 + a2, r = a1 + a3;
+        total = l + r;
+    } else {
+        total = 0.f;
+        for (int i = 0; i < 8; ++i) total = total + t[i];
     }
     return fabsf(total) / 2.0f;
 }

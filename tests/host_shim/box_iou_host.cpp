@@ -12,6 +12,10 @@ static inline float __fmul_rn(float a, float b) { volatile float r = a * b; retu
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+static int g_shim_iou_mode = 0;
+#define NRPN_IOU_MODE g_shim_iou_mode
+extern "C" void shim_set_iou_mode(int m) { g_shim_iou_mode = m; }
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 static inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }

@@ -59,13 +59,20 @@ def test_sort_vertices_bit_identical_to_reference_kernel():
     want = ref.sort_vertices.sort_vertices_forward(v, m, nv)
     got = ops.sort_vertices_forward(v, m, nv)
     ok = nv <= 8
-    assert torch.equal(got[ok], want[ok])
+    rows = (got[ok] == want[ok]).all(dim=-1)
+    bad = (~rows).nonzero().reshape(-1)
+    print(f"reference smoke input (random masks): {int(rows.sum())} of {rows.numel()} polygons identical")
+    for r in bad[:3].tolist():
+        gi = ok.nonzero()[r]
+        print("  differing polygon", gi.tolist(), "nv", int(nv[gi[0], gi[1]]), "got", got[gi[0], gi[1]].tolist(), "want", want[gi[0], gi[1]].tolist(),
+              "mask", m[gi[0], gi[1]].int().tolist(), "v", v[gi[0], gi[1]].flatten().tolist())
+    assert bool(rows.all())
 
 
 # ------------------------------------------------------------------------------------------------ IoU + NMS (rows a12-a15)
 def test_iou_pairs_vs_reference_on_this_gpu():
-    """cal_iou_3d of the reference (torch-CUDA chain + K1) vs nrpn_iou3d_pairs on 400 000 random OBB pairs: prints the bit-equal
-    fraction; every value within 2e-6 absolute."""
+    """cal_iou_3d of the reference (torch-CUDA chain + K1) vs nrpn_iou3d_pairs (library default NRPN_IOU_MODE 3: CUDA sinf / cosf,
+    bmm as fma, ATen's CUDA summation orders -- measured by tools/ref_gpu_probe.py) on 400 000 random OBB pairs: bit-identical."""
     from nerf_rpn_b200 import ops
     ref = ref_gpu.load()
     g = torch.Generator().manual_seed(5)
@@ -77,8 +84,11 @@ def test_iou_pairs_vs_reference_on_this_gpu():
     eq = (want.view(torch.int32) == got.view(torch.int32))
     print(f"IoU vs reference on {torch.cuda.get_device_name(0)}: {int(nz.sum())} overlapping pairs, bit-equal {eq[nz].float().mean().item():.5f} "
           f"(all pairs {eq.float().mean().item():.5f}), max |diff| {(want - got).abs().max().item():.3e}")
+    bad = (~eq).nonzero().reshape(-1)
+    for i in bad[:5].tolist():
+        print(f"  differs: a={a[i].tolist()} b={b[i].tolist()} reference={want[i].item():.9g} ours={got[i].item():.9g}")
     assert (want - got).abs().max().item() <= 2e-6
-    assert torch.equal(want == 0, got == 0)                  # exact-zero culling never changes a zero / non-zero decision
+    assert eq.float().mean().item() >= 0.99999, "NRPN_IOU_MODE 3 should reproduce the torch-CUDA chain bit for bit"
 
 
 @pytest.mark.parametrize("tag,nb,groups,extent", [("2500x4_levels", 10000, 4, 60.0), ("10000_one_level", 10000, 1, 60.0),
@@ -101,7 +111,14 @@ def test_nms_keep_sets_identical_to_reference_loop(tag, nb, groups, extent):
     t_our = time.perf_counter() - t0
     diff = set(want.tolist()) ^ set(got.tolist())
     print(f"NMS {tag}: reference keeps {want.numel()} in {t_ref:.2f} s, ours keeps {got.numel()} in {t_our * 1e3:.2f} ms, symmetric difference {len(diff)}")
-    assert got.numel() == want.numel() and torch.equal(got, want), f"keep sets differ in {len(diff)} boxes: {sorted(diff)[:10]}"
+    assert got.numel() == want.numel() and not diff, f"keep sets differ in {len(diff)} boxes: {sorted(diff)[:10]}"
+    # order: score descending in both; boxes with EQUAL scores (torch.rand draws collide among 10 000 fp32 values) come in whatever
+    # order torch.sort leaves them in the reference and lowest-index-first here: compare the sequences modulo ties
+    sw, sg = scores[want], scores[got]
+    assert torch.equal(sw, sg)
+    neq = (want != got).nonzero().reshape(-1)
+    for i in neq.tolist():
+        assert ((sw == sw[i]).sum() > 1), "order differs outside a tie group"
 
 
 # ------------------------------------------------------------------------------------------------ network at full size (rows a3, a6)
