@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- scenes/sec of the NeRF-RPN hot path (BASELINE.json config 2: ResNet50-3D + FPN + anchor head,
-160x256x256 RGB-sigma grids, bf16, 13 anchors/location, top-2500 per level, NMS 0.3).
+"""bench.py -- scenes/sec of the NeRF-RPN hot path (BASELINE.json config 2: ResNet50-3D + FPN + anchor head, 160x256x256 RGB-sigma
+grids, 13 anchors/location, top-2500 per level, NMS 0.3) plus, in the same JSON line, the legs that explain it.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one scene through backbone -> FPN -> head -> decode/top-k -> NMS -> proposals on each rank (weak scaling:
-scenes are independent, no collective on the data path).  Prints ONE JSON line (contract in the task
-statement): `value` = whole-job scenes/s with inputs resident in HBM (device-timed, max over ranks), `e2e` = the same
-metric through the public pipeline with pinned HOST grids (H2D + D2H inside the timed region), `roofline` for the
-dominant kernel (tcgen05 implicit-GEMM conv, RPN-head layer over P2..P5) measured live with CUDA events,
-`cpu_baseline` = the oracle's fp32 CPU port of the reference on this box's host cores.
+One "step" = `scenes_per_step` scenes per rank through backbone -> FPN -> head -> decode / top-k -> NMS -> proposals (weak scaling:
+scenes are independent, no collective on the inference path).  ONE JSON line (contract in the task statement):
+  value          whole-job scenes/s, inputs resident in HBM, device-timed, max over ranks
+  e2e            the same metric through the public pipeline with pinned HOST grids (H2D + D2H inside the timed region); `forward_api`
+                 inside it = NeRFRegionProposalNetwork.forward itself with the reference's own methodology (run_rpn.py:594-617)
+  roofline       dominant kernel (tcgen05 implicit-GEMM conv, one RPN-head layer over P2..P5) timed live with CUDA events
+  variants       other loads on the same box: seed-0 weights (round-1 line), rotated boxes (--rotated_bbox: polygon-clip NMS), one scene per
+                 launch, bf16 (BASELINE's dtype, 8e-3 feature parity)
+  train          BASELINE config 4: one training step (forward + losses + backward + clip + AdamW) per rank on one 160x256x256 scene with
+                 rotated boxes, the flat gradient bucket all-reduced over NCCL and overlapped with the backward pass
+  reference_gpu  the INCUMBENT: the unmodified reference (oracle/_ref: cuDNN + ATen + Python NMS + its own K1) on this GPU (rank 0, N = 1)
+  cpu_baseline   the reference on this box's host cores (N = 1): its own modules when oracle/_ref is staged, else the oracle's port
 
-`--impl reference` times that CPU port only (the reference is pure Python/PyTorch and cannot travel to the GPU box
-together with /root/reference; the port under oracle/net.py restates it and is pinned by its golden vectors).
+`--impl reference` times the reference on the host CPU only: the unmodified reference modules from oracle/_ref when staged
+(cpu_baseline.kind "reference"), else the fp32 port oracle/net.py ("port").
 """
 import argparse
 import json
@@ -29,7 +35,9 @@ sys.path.insert(0, ROOT)
 DIMS = (160, 256, 256)
 ANCHOR_SIZES = ((8,), (16,), (32,), (64,),)
 ASPECT = (((1., 1., 1.), (1., 1., 2.), (1., 2., 2.), (1., 1., 3.), (1., 3., 3.)),) * 4
-WORKLOAD = "ResNet50-3D+FPN+anchor-head(AABB) 160x256x256x4 RGBsigma, 13 anchors/loc, pre/post-NMS top 2500, NMS 0.3"
+SPREAD = 30.0                     # cls_logits.weight multiplier of the score-spread variant (seed-0 init gives ~0.5 everywhere)
+WORKLOAD = ("ResNet50-3D+FPN+anchor-head(AABB) 160x256x256x4 RGBsigma, 13 anchors/loc, pre/post-NMS top 2500, NMS 0.3, "
+            f"reference init seed 0 with cls_logits.weight x{SPREAD:g} (spread objectness)")
 FLOPS_PER_SCENE = 3.913e12        # conv FLOPs (2*MAC) of the reference's layers
 
 
@@ -44,9 +52,12 @@ def parse():
     ap.add_argument("--input-layout", default="dataset", choices=["dataset", "ncdhw", "dataset_u8"],
                     help="input grids: the dataset's fp32 channels-last view (default), contiguous fp32 (4,W,L,H), or the raw uint8 "
                          "channels-last view (uint8 npz files; normalised on the device instead of by datasets.py:59-61 on the host)")
-    ap.add_argument("--skip-cpu-baseline", action="store_true", help="exploration runs only: omit the ~40 s CPU port timing")
+    ap.add_argument("--skip-cpu-baseline", action="store_true", help="exploration runs only: omit the CPU timing")
+    ap.add_argument("--skip-extras", action="store_true", help="exploration runs only: omit variants / train / reference_gpu legs")
     ap.add_argument("--scenes-per-step", type=int, default=int(os.environ.get("NRPN_SCENES_PER_STEP", "4")),
                     help="scenes per rank per step (one engine launch); weights are read once per step")
+    ap.add_argument("--weights", default="spread", choices=["spread", "seed0"], help="headline weights: spread objectness (default) or plain seed-0 init")
+    ap.add_argument("--rotated", action="store_true", help="headline with --rotated_bbox (8 deltas, OBB decode, polygon-clip NMS)")
     return ap.parse_args()
 
 
@@ -60,15 +71,38 @@ def synth_scene(i, layout="ncdhw"):
     return grid.permute(3, 0, 1, 2) if layout == "dataset" else grid.permute(3, 0, 1, 2).contiguous()
 
 
-def build_modules():
+def planted_boxes(i, n_gt=16, rotated=True):
+    """Ground truth of scene i for the training leg: n_gt cuboids, sizes U[8,64], yaw U[-pi/2, pi/2)."""
+    import math
+    import torch
+    g = torch.Generator().manual_seed(5000 + i)
+    d = torch.tensor(DIMS, dtype=torch.float32)
+    size = torch.rand(n_gt, 3, generator=g) * 56.0 + 8.0
+    ctr = torch.rand(n_gt, 3, generator=g) * (d - 16.0) + 8.0
+    if rotated:
+        return torch.cat([ctr, size, (torch.rand(n_gt, 1, generator=g) - 0.5) * math.pi], 1)
+    return torch.cat([ctr - size / 2, ctr + size / 2], 1)
+
+
+def build_modules(rotated=False, spread=SPREAD):
     import torch
     from nerf_rpn_b200.model.anchor import AnchorGenerator3D, RPNHead
     from nerf_rpn_b200.model.feature_extractor import Bottleneck, ResNet_FPN_256
     torch.manual_seed(0)
     backbone = ResNet_FPN_256(Bottleneck, [3, 4, 6, 3], input_dim=4, is_max_pool=True)
     ag = AnchorGenerator3D(ANCHOR_SIZES, ASPECT)
-    head = RPNHead(256, ag.num_anchors_per_location()[0], 4, rotate=False)
+    head = RPNHead(256, ag.num_anchors_per_location()[0], 4, rotate=rotated)
+    if spread:
+        with torch.no_grad():
+            head.cls_logits.weight.mul_(spread)
     return backbone, ag, head
+
+
+def build_model(rotated=False, spread=SPREAD, precision=None):
+    from nerf_rpn_b200.model.nerf_rpn import NeRFRegionProposalNetwork
+    backbone, ag, head = build_modules(rotated, spread)
+    return NeRFRegionProposalNetwork(backbone, ag, head, rpn_pre_nms_top_n_test=2500, rpn_post_nms_top_n_test=2500, rpn_nms_thresh=0.3,
+                                     rpn_score_thresh=0.0, rpn_fg_iou_thresh=0.35, rpn_bg_iou_thresh=0.2, rotated_bbox=rotated, precision=precision)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -115,55 +149,80 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------------------------------ CPU port
-_CPU_PORT = {}
+# ------------------------------------------------------------------------------------------------ the reference on the host CPU
+_CPU = {}
 
 
-def _cpu_port_state():
-    """Weights, anchors and the synthetic scene of the CPU port, built once per process."""
-    if not _CPU_PORT:
-        backbone, ag, head = build_modules()
-        _CPU_PORT["sd"] = {k: v.detach() for k, v in backbone.state_dict().items()}
-        _CPU_PORT["hsd"] = {k: v.detach() for k, v in head.state_dict().items()}
-        _CPU_PORT["cells"] = ag.cell_anchors_np()
-        _CPU_PORT["scene"] = synth_scene(0)
-    return _CPU_PORT
-
-
-def cpu_port_run(x_extent, n_threads, repeats=1, y_extent=None):
-    """Time the oracle's CPU port on an (x_extent x y_extent x 256) block of the scene (x_extent*y_extent/(160*256) of a scene).
-    Returns seconds per run."""
+def _cpu_state():
+    """The reference on the host: its own modules (oracle/_ref, eval mode, AABB head: no native op on that path) when staged, else the
+    oracle's fp32 port.  Same seed-0 + spread weights and scene as the B200 arm."""
+    if _CPU:
+        return _CPU
     import torch
-    from oracle import net as onet
+    backbone, ag, head = build_modules()
+    _CPU["scene"] = synth_scene(0)
+    _CPU["kind"] = "port"
+    _CPU["sd"] = {k: v.detach() for k, v in backbone.state_dict().items()}
+    _CPU["hsd"] = {k: v.detach() for k, v in head.state_dict().items()}
+    _CPU["cells"] = ag.cell_anchors_np()
+    try:
+        from oracle import ref_gpu
+        if ref_gpu.available():
+            sys.path.insert(0, os.path.join(ROOT, "tools", "ref_stub"))      # import-time stand-in for the native op; the AABB path never calls it
+            try:
+                ref = ref_gpu.load(need_k1=False)
+            finally:
+                sys.path.remove(os.path.join(ROOT, "tools", "ref_stub"))
+            m = ref_gpu.build_reference_model(rotated=False, seed=0, spread=SPREAD).eval()
+            _CPU["model"], _CPU["kind"] = m, "reference"
+    except Exception as e:                                                   # noqa: BLE001 -- fall back to the port, say why
+        _CPU["why_port"] = repr(e)
+    return _CPU
+
+
+def cpu_run(x_extent, n_threads, repeats=1, y_extent=None):
+    """Time the reference on an (x_extent x y_extent x 256) block of the scene (x_extent*y_extent/(160*256) of a scene). Seconds per run."""
+    import torch
     torch.set_num_threads(n_threads)
-    st = _cpu_port_state()
+    st = _cpu_state()
     y_extent = DIMS[1] if y_extent is None else y_extent
-    x = st["scene"][:, :x_extent, :y_extent].contiguous()[None]
+    x = st["scene"][:, :x_extent, :y_extent].contiguous()
     times = []
     for _ in range(repeats):
         t0 = time.perf_counter()
-        onet.full_forward(st["sd"], st["hsd"], x, st["cells"], False)
+        with torch.no_grad():
+            if st["kind"] == "reference":
+                st["model"]([x.clone()])
+            else:
+                from oracle import net as onet
+                onet.full_forward(st["sd"], st["hsd"], x[None], st["cells"], False)
         times.append(time.perf_counter() - t0)
     return times
 
 
 def best_cpu_threads():
-    """Intra-op thread count that makes the CPU port fastest on this host: all cores is NOT it on a 128-thread box (measured on
-    the B200 host: 32x128x256 block 0.37 s with 16 threads, 0.43 s with 32, 0.80 s with 64, 5.6 s with 128; full scene 4.2 s
-    with 32 threads vs 33 s with 128 -- profiles/r01_cpu_port_threads.txt). Sweeps {all, 64, 32, 16, 8} on a small block and
-    returns (threads, {threads: seconds})."""
+    """Intra-op thread count that makes the CPU run fastest on this host: all cores is NOT it on a 128-thread box (measured on the B200 host:
+    full scene 4.2 s with 32 threads vs 33 s with 128 -- profiles/r01_cpu_port_threads.txt). Sweeps {all, 64, 32, 16, 8} on a small block."""
     cores = os.cpu_count() or 1
     cands = sorted({c for c in (cores, 64, 32, 16, 8) if 1 <= c <= cores}, reverse=True)
-    cpu_port_run(32, min(cands), y_extent=64)                  # library warm-up (oneDNN JIT, thread pool), not timed
+    cpu_run(32, min(cands), y_extent=64)                       # library warm-up (oneDNN JIT, thread pool), not timed
     sweep = {}
     for th in cands:
-        sweep[th] = min(cpu_port_run(32, th, y_extent=128, repeats=2))
+        sweep[th] = min(cpu_run(32, th, y_extent=128, repeats=2))
     best = min(sweep, key=sweep.get)
     return best, {k: round(v, 2) for k, v in sweep.items()}
 
 
+def _cpu_desc(cores, sweep):
+    import torch
+    st = _cpu_state()
+    what = ("the UNMODIFIED reference modules (oracle/_ref: NeRFRegionProposalNetwork.forward incl. its Python NMS loop) on the host CPU"
+            if st["kind"] == "reference" else "oracle/net.py fp32 port of the reference")
+    return f"{what}, torch {torch.__version__}, {cores} of {os.cpu_count()} threads = the fastest of the sweep {sweep}"
+
+
 def run_reference(args):
-    """--impl reference: the CPU port on all host cores; each step = a bounded block of the workload, sized so that the whole
+    """--impl reference: the reference on the host cores; each step = a bounded block of the workload, sized so that the whole
     (warmup + steps) run stays within a few minutes whatever K is."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -171,10 +230,9 @@ def run_reference(args):
     import torch
     cores, sweep = best_cpu_threads()
     torch.set_num_threads(cores)
-    per_full = cpu_port_run(160, cores)[0]                     # one full scene with the chosen thread count
+    per_full = cpu_run(160, cores)[0]                          # one full scene with the chosen thread count
     budget = 150.0
     frac = budget / (per_full * (args.steps + args.warmup))
-    # candidate blocks (x extent multiple of 32 for the 5 stride-2 stages, y extent 64/128/256), largest one within the budget
     cands = sorted(((ex * ey) / float(DIMS[0] * DIMS[1]), ex, ey) for ex in (32, 64, 96, 128, 160) for ey in (64, 128, 256))
     pick = cands[0]
     for c in cands:
@@ -182,19 +240,17 @@ def run_reference(args):
             pick = c
     share, ex, ey = pick
     for _ in range(args.warmup):
-        cpu_port_run(ex, cores, y_extent=ey)
+        cpu_run(ex, cores, y_extent=ey)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_port_run(ex, cores, y_extent=ey)
+        cpu_run(ex, cores, y_extent=ey)
     dt = time.perf_counter() - t0
-    scenes = args.steps * share
-    value = scenes / dt
-    sample = (f"{ex}x{ey}x{DIMS[2]} block per step = {share:.3f} scene (oracle/net.py fp32 port of the reference, torch {torch.__version__}, "
-              f"{cores} of {os.cpu_count()} threads = the fastest of the sweep {sweep})")
+    value = args.steps * share / dt
+    sample = f"{ex}x{ey}x{DIMS[2]} block per step = {share:.3f} scene; full scene {per_full:.2f} s ({_cpu_desc(cores, sweep)})"
     out = {"impl": "reference", "metric": "scenes/sec", "value": value, "unit": "scenes/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-           "cpu_baseline": {"value": value, "unit": "scenes/s", "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": value, "unit": "scenes/s", "cores": cores, "kind": _cpu_state()["kind"], "sample": sample},
            "e2e": {"value": value, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
@@ -227,6 +283,85 @@ def time_dominant_kernel(plan, reps=10):
     return statistics.mean(times), min(times), flops
 
 
+def device_throughput(model, dev_batches, K, W, barrier):
+    """K engine steps over resident input batches; returns (ms, plan, proposals of the last scene)."""
+    import torch
+    eng = model.engine()
+    with torch.no_grad():
+        for i in range(max(W, 4)):                            # >= 4: both buffer parities warmed and captured
+            plan = eng.forward_device(dev_batches[i % len(dev_batches)])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            plan = eng.forward_device(dev_batches[i % len(dev_batches)])
+        torch.cuda.current_stream().wait_event(plan.done)     # the last scene's post-processing (side stream)
+        e1.record()
+        barrier()
+    return e0.elapsed_time(e1), plan, int(plan.out_count[0].item())
+
+
+def train_leg(rank, local, world, barrier, steps=5, warm=2):
+    """BASELINE config 4: ResNet50-FPN + anchor head, --rotated_bbox, one 160x256x256 scene per rank per step, data parallel: forward,
+    target assignment + sampling + losses, backward (dgrad / wgrad on tcgen05), NCCL all-reduce of the flat gradient bucket overlapped
+    with the backward pass, clip_grad_norm_(0.1) + AdamW.  bf16 activations / gradients, fp32 master weights and accumulation."""
+    import torch
+    import torch.distributed as dist
+    model = build_model(rotated=True, spread=0.0).cuda().train()
+    eng = model.train_engine(precision="bf16", lr=1e-4, weight_decay=0.01, clip_grad_norm=0.1, reg_loss_weight=5.0,
+                             process_group=dist.group.WORLD if world > 1 else None)
+    grids = [synth_scene(rank * 1000 + i, "dataset").permute(1, 2, 3, 0).contiguous().cuda().permute(3, 0, 1, 2)[None] for i in range(2)]
+    gts = [[planted_boxes(rank * 1000 + i).cuda()] for i in range(2)]
+    for i in range(warm):
+        eng.train_step(grids[i % 2], gts[i % 2])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        losses = eng.train_step(grids[i % 2], gts[i % 2])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    plan = eng.plan(1, DIMS)
+    out = {"metric": "training scenes/sec", "value": world * steps / (ms * 1e-3), "unit": "scenes/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warm,
+           "scaling": "weak", "dtype": "bf16 activations / gradients, fp32 master weights + accumulation",
+           "config": "ResNet50-3D+FPN+anchor head --rotated_bbox, 1 scene (160x256x256) per rank per step, 16 planted OBBs, sample 256 anchors, "
+                     "smooth-L1 + BCE, clip 0.1, AdamW (BASELINE config 4)",
+           "collective": (f"NCCL all-reduce (sum) of the flat fp32 gradient bucket, {eng.n_params} parameters = {eng.n_params * 4 / 1e6:.0f} MB per step, "
+                          f"{getattr(plan, 'allreduce_calls', 0)} chunks launched as the backward pass finalises them (head -> FPN -> stages -> stem)")
+                         if world > 1 else "none at N = 1 (the all-reduce is skipped)",
+           "losses_last_step": [round(v, 5) for v in losses.tolist()], "params": eng.n_params}
+    del eng, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def forward_api_leg(model, host_grid, reps=100, warm=10):
+    """NeRFRegionProposalNetwork.forward through the reference's own benchmark methodology (run_rpn.py:594-617: eval mode, warm-up, CUDA events
+    around model([grid]), synchronize per repetition), one scene per call, grid copied from pinned host memory inside the timed region like
+    run_rpn.py:473 (`item.cuda()`), proposals copied back like :507."""
+    import torch
+    times = []
+    with torch.no_grad():
+        for i in range(warm + reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            x = host_grid.cuda(non_blocking=True)
+            (feats, props, lv), _, scores = model([x])
+            _ = props[0].cpu()
+            b.record()
+            torch.cuda.synchronize()
+            if i >= warm:
+                times.append(a.elapsed_time(b))
+    return {"ms_per_scene": statistics.mean(times), "std_ms": statistics.pstdev(times), "scenes_per_s": 1000.0 / statistics.mean(times), "reps": reps,
+            "warmup": warm, "api": "NeRFRegionProposalNetwork.forward([grid]) (features returned as fp32 NCDHW views), run_rpn.py:594-617 methodology",
+            "h2d_bytes_per_step": host_grid.numel() * host_grid.element_size(), "d2h_bytes_per_step": int(props[0].numel() * 4)}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -234,20 +369,15 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
-        raise RuntimeError("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU port)")
+        raise RuntimeError("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU reference)")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    from nerf_rpn_b200._lib import lib
-    from nerf_rpn_b200.model.nerf_rpn import NeRFRegionProposalNetwork
-    from nerf_rpn_b200.runtime import ScenePipeline
-
-    backbone, ag, head = build_modules()
-    model = NeRFRegionProposalNetwork(backbone, ag, head, rpn_pre_nms_top_n_test=2500, rpn_post_nms_top_n_test=2500,
-                                      rpn_nms_thresh=0.3, rpn_score_thresh=0.0).cuda().eval()
     from nerf_rpn_b200 import precision as nprec
+    from nerf_rpn_b200.runtime import ScenePipeline
     args.precision = nprec.resolve(args.precision)
-    model.precision = args.precision
+    spread = SPREAD if args.weights == "spread" else 0.0
+    model = build_model(rotated=args.rotated, spread=spread, precision=args.precision).cuda().eval()
     eng = model.engine()
     B = max(1, args.scenes_per_step)
     n_pool = 4                                             # 4 x 168 MB of distinct inputs (> 126 MB L2)
@@ -259,10 +389,12 @@ def run_b200(args):
     else:
         host = [synth_scene(rank * 1000 + i).pin_memory() for i in range(n_pool)]
     hdev = [h.cuda() for h in host]
-    if args.input_layout in ("dataset", "dataset_u8"):      # keep the (B,X,Y,Z,4) memory order: logical (B,4,X,Y,Z) views
-        dev = [torch.stack([hdev[(i + b) % n_pool].permute(1, 2, 3, 0) for b in range(B)], 0).permute(0, 4, 1, 2, 3) for i in range(n_pool)]
-    else:
-        dev = [torch.stack([hdev[(i + b) % n_pool] for b in range(B)], 0) for i in range(n_pool)]   # (B,4,X,Y,Z) batches
+
+    def batches(b):
+        if args.input_layout in ("dataset", "dataset_u8"):      # keep the (B,X,Y,Z,4) memory order: logical (B,4,X,Y,Z) views
+            return [torch.stack([hdev[(i + k) % n_pool].permute(1, 2, 3, 0) for k in range(b)], 0).permute(0, 4, 1, 2, 3) for i in range(n_pool)]
+        return [torch.stack([hdev[(i + k) % n_pool] for k in range(b)], 0) for i in range(n_pool)]
+    dev = batches(B)
     K, W = args.steps, max(args.warmup, 3)
 
     def barrier():
@@ -270,26 +402,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput
-    with torch.no_grad():
-        for i in range(max(W, 4)):                            # >= 4: both buffer parities warmed and captured
-            plan = eng.forward_device(dev[i % n_pool])
-        barrier()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(K):
-            plan = eng.forward_device(dev[i % n_pool])
-        torch.cuda.current_stream().wait_event(plan.done)     # the last scene's post-processing (side stream)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if rank == 0 else None
-        count = int(plan.out_count[0].item())
+    # ---- device-resident throughput (headline)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, plan, count = device_throughput(model, dev, K, W, barrier)
+    clocks = sampler.stop() if rank == 0 else None
 
-        # ---- end to end through the streaming pipeline (pinned host grids in, proposals out on the host)
+    # ---- end to end through the streaming pipeline (pinned host grids in, proposals out on the host)
+    with torch.no_grad():
         pipe = ScenePipeline(model, DIMS, batch=B)
         pipe.run([host[i % n_pool] for i in range(W * B)], collect=True)
         barrier()
@@ -302,21 +423,19 @@ def run_b200(args):
         wall_ms = 1000.0 * (time.perf_counter() - t0)
         ms_e2e = max(e2.elapsed_time(e3), wall_ms)         # host-side collection included
         assert len(res) == K * B
-
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
-    out = None
+    launches_per_step = plan.num_launches() if rank == 0 else 0
+    torch.cuda.synchronize()
+    roofline = None
+    fwd_api = None
     if rank == 0:
-        launches_per_step = plan.num_launches()
-        torch.cuda.synchronize()
         k_mean, k_min, k_flops = time_dominant_kernel(plan)
         burst, sustained, how = measured_peaks()
         achieved = k_flops / (k_mean * 1e-3) / 1e12
-        # DRAM traffic of that kernel from the committed `ncu --set full` capture (one scene per launch), scaled to this run's
-        # scenes per launch; None when the summary is absent.  It is a profile number, not measured in this (unprofiled) run.
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")) as f:
@@ -327,38 +446,80 @@ def run_b200(args):
             traffic = None
         roofline = {"bound": "tensor", "kernel": "conv3d_igemm_kernel<256,4> (RPN head layer, 3x3x3 256->256 + bias + ReLU over P2..P5)",
                     "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic,
-                    "traffic_source": "profiles/r01_ncu_full_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, 1 scene/launch) x scenes per launch",
+                    "traffic_source": "profiles/r01_ncu_full_summary.json (dram__bytes_read.sum + dram__bytes_write.sum of an ncu --set full capture, 1 scene/launch) x scenes per launch; a profile number, not measured in this run",
                     "peak_source": how + ", burst figure (kernel timed alone, L2 flushed between launches)",
                     "launch_ms": k_mean, "flops_per_launch": k_flops,
                     "whole_step_frac_of_sustained": (FLOPS_PER_SCENE * world * K * B / (ms * 1e-3) / 1e12) / (sustained * world)}
-        value = world * K * B / (ms * 1e-3)
+        if world == 1 and not args.skip_extras:
+            fwd_api = forward_api_leg(model, host[0])
+    del pipe
+    value = world * K * B / (ms * 1e-3)
+
+    # ---- other loads on the same box (device-resident, same method)
+    variants = {}
+    train = None
+    ref_gpu_out = None
+    if not args.skip_extras:
+        del model, eng, plan
+        torch.cuda.empty_cache()
+        Kv = max(8, K // 4)
+        specs = [("seed0_weights", dict(rotated=False, spread=0.0, precision=args.precision), B),
+                 ("rotated_bbox", dict(rotated=True, spread=SPREAD, precision=args.precision), B),
+                 ("one_scene_per_step", dict(rotated=False, spread=SPREAD, precision=args.precision), 1),
+                 ("bf16", dict(rotated=False, spread=SPREAD, precision="bf16"), B)]
+        for name, kw, b in specs:
+            m = build_model(**kw).cuda().eval()
+            vms, vplan, vcount = device_throughput(m, dev if b == B else batches(b), Kv, W, barrier)
+            tt = torch.tensor([vms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            variants[name] = {"value": world * Kv * b / (float(tt.item()) * 1e-3), "unit": "scenes/s", "ms_per_step": float(tt.item()) / Kv, "scenes_per_step_per_gpu": b,
+                              "steps": Kv, "proposals_last_scene": vcount, "precision": kw["precision"]}
+            del m, vplan
+            torch.cuda.empty_cache()
+        train = train_leg(rank, local, world, barrier)
+        if rank == 0 and world == 1:
+            try:
+                from oracle import incumbent
+                ref_gpu_out = {"tf32_default": incumbent.time_reference_gpu(DIMS, rotated=False, spread=SPREAD, tf32=True, warmup=1, reps=3, budget_s=25.0),
+                               "fp32": incumbent.time_reference_gpu(DIMS, rotated=False, spread=SPREAD, tf32=False, warmup=1, reps=2, budget_s=15.0)}
+            except Exception as e:                           # noqa: BLE001
+                ref_gpu_out = {"unavailable": repr(e)}
+
+    out = None
+    if rank == 0:
         cores = os.cpu_count() or 1
         sweep = {}
         torch.cuda.empty_cache()
         if args.skip_cpu_baseline or world > 1:            # the CPU baseline is timed on rank 0 of the single-GPU run only
-            cpu_t = float("nan")
+            cpu_t, cpu_sample, cpu_kind = float("nan"), "not timed in this run (N > 1 or --skip-cpu-baseline)", "port"
         else:
             cores, sweep = best_cpu_threads()              # all 128 hardware threads are 8x SLOWER than 32 on the B200 host
-            cpu_t = statistics.mean(cpu_port_run(160, cores, repeats=3))
+            cpu_t = statistics.mean(cpu_run(160, cores, repeats=2))
+            cpu_kind = _cpu_state()["kind"]
+            cpu_sample = f"2 full scenes 160x256x256, mean ({_cpu_desc(cores, sweep)})"
         out = {"metric": "scenes/sec", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": nprec.bench_dtype(args.precision),
                "data": "synthetic",
-               "config": {"workload": WORKLOAD, "scenes_per_step_per_gpu": B, "parallelism": f"dp{world} (one scene per rank, no collective)",
+               "config": {"workload": WORKLOAD if (args.weights == "spread" and not args.rotated) else WORKLOAD + f" [weights={args.weights}, rotated={args.rotated}]",
+                          "precision": args.precision, "feature_map_parity": "<= 1e-3 norm-wise vs the reference's fp32 on this GPU at 160x256x256 "
+                          "(tests/test_gpu_reference.py)" if args.precision == "fp16_w2" else "see DESIGN.md section 4",
+                          "scenes_per_step_per_gpu": B, "parallelism": f"dp{world} (scenes shard over ranks, no collective on the inference path)",
                           "l2": "4 distinct 168 MB input grids per rank cycled (> 126 MB L2); activations stream ~1.5 GB/scene",
-                          "weights": "reference init, torch.manual_seed(0)", "proposals_last_scene": count,
+                          "proposals_last_scene": count,
                           "input_layout": {"dataset": "fp32 (4,W,L,H) views of (W,L,H,4) arrays, as datasets.py:55-56 yields",
                                            "dataset_u8": "raw uint8 (4,W,L,H) views of (W,L,H,4) arrays, normalised on the device",
                                            "ncdhw": "fp32 contiguous (4,W,L,H)"}[args.input_layout]},
                "clocks": clocks,
-               "e2e": {"value": world * K * B / (ms_e2e * 1e-3), "unit": "scenes/s", "h2d_bytes_per_step": pipe.h2d_bytes_per_scene * B,
-                       "d2h_bytes_per_step": pipe.d2h_bytes_per_scene * B, "ms_per_step": ms_e2e / K,
-                       "api": "nerf_rpn_b200.runtime.ScenePipeline.run (pinned host grids -> host proposals)"},
+               "e2e": {"value": world * K * B / (ms_e2e * 1e-3), "unit": "scenes/s", "h2d_bytes_per_step": int(4 * DIMS[0] * DIMS[1] * DIMS[2] * host[0].element_size() * B),
+                       "d2h_bytes_per_step": int((2500 * (7 if args.rotated else 6) + 2 * 2500 + 1) * 4 * B), "ms_per_step": ms_e2e / K,
+                       "api": "nerf_rpn_b200.runtime.ScenePipeline.run (pinned host grids -> host proposals)", "forward_api": fwd_api},
                "gpu_launches": launches_per_step * K,
                "roofline": roofline,
-               "cpu_baseline": {"value": (1.0 / cpu_t) if cpu_t == cpu_t else None, "unit": "scenes/s", "cores": cores, "kind": "port",
-                                "sample": f"3 scenes 160x256x256, mean (oracle/net.py fp32 CPU port of the reference; {cores} of {os.cpu_count()} threads = "
-                                          f"the fastest of the sweep {sweep})"
-                                if cpu_t == cpu_t else "not timed in this run (N > 1 or --skip-cpu-baseline)"}}
+               "variants": variants,
+               "train": train,
+               "reference_gpu": ref_gpu_out,
+               "cpu_baseline": {"value": (1.0 / cpu_t) if cpu_t == cpu_t else None, "unit": "scenes/s", "cores": cores, "kind": cpu_kind, "sample": cpu_sample}}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -88,18 +88,35 @@ class RPNInferenceEngine:
 
     # ---------------------------------------------------------------- weights
     def _param_version(self):
-        v = 0
+        """(storage, version) of every parameter / buffer: any in-place update, load_state_dict or re-materialisation changes it
+        (a tuple, not a sum: nothing can cancel)."""
+        out = []
         for m in (self.backbone, self.head):
-            if m is None:
-                continue
-            for t in list(m.parameters()) + list(m.buffers()):
-                v += t._version + (t.data_ptr() % 1000003)
-        return v
+            if m is not None:
+                out.extend((t.data_ptr(), t._version) for t in m.parameters())
+                out.extend((t.data_ptr(), t._version) for t in m.buffers())
+        return tuple(out)
+
+    def invalidate(self):
+        """Force re-packing of the weights (and re-capture of the graphs) at the next forward."""
+        self._packed_version = None
 
     def _pack(self, device):
         bb, hd = self.backbone, self.head
         L = {}
-        self.kind = {"VGG_FPN": "vgg", "SwinTransformer_FPN": "swin"}.get(type(bb).__name__, "resnet")
+        kinds = {"ResNet_FPN_256": "resnet", "VGG_FPN": "vgg", "SwinTransformer_FPN": "swin"}
+        if type(bb).__name__ not in kinds:
+            raise NotImplementedError(f"nerf_rpn_b200: backbone {type(bb).__name__} is not implemented by the B200 engine "
+                                      "(ResNet_FPN_256, VGG_FPN, SwinTransformer_FPN are)")
+        self.kind = kinds[type(bb).__name__]
+        if self.kind == "resnet":          # the layer plan below is the configuration run_rpn.py:276 builds; anything else would run silently wrong
+            c1 = getattr(bb, "conv1", None)
+            ok = (getattr(bb, "is_max_pool", False) and c1 is not None and tuple(c1.kernel_size) == (7, 7, 7) and tuple(c1.stride) == (2, 2, 2)
+                  and c1.in_channels == 4 and c1.out_channels == 64 and [len(s) for s in bb.layers] == [3, 4, 6, 3]
+                  and all(type(b).__name__ == "Bottleneck" for s in bb.layers for b in s))
+            if not ok:
+                raise NotImplementedError("nerf_rpn_b200: the ResNet engine implements ResNet_FPN_256(Bottleneck, [3,4,6,3], input_dim=4, "
+                                          "is_max_pool=True) (7^3 stride-2 stem on 4 channels + max-pool), the configuration run_rpn.py:276 builds")
         _Conv.dtype = self.act_dtype
         if self.kind == "vgg":
             self._pack_vgg(L, device)
@@ -627,14 +644,14 @@ class _Plan:
                                        f["post_nms_top_n"], f["min_size"], gs, padded=self.n > 1)
                 descs.append(d)
                 ws_bytes = max(ws_bytes, ops.lib().nrpn_fcos_workspace_bytes(ctypes.byref(d)))
-        if self._rpn_ws is None or self._rpn_ws.numel() < ws_bytes:
-            self._rpn_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        if self._rpn_ws is None or self._rpn_ws[0].numel() < ws_bytes or len(self._rpn_ws) != self.n:
+            self._rpn_ws = [torch.empty(ws_bytes, dtype=torch.uint8, device=self.device) for _ in range(self.n)]
         for par in range(2):
             o = self._out[par]
             for i in range(self.n):
                 d = descs[par * self.n + i]
                 out = (o["boxes"][i], o["scores"][i], o["count"][i:i + 1])
-                self._post[par].append(lambda d=d, out=out: ops.fcos_proposals(d, self.device, out=out, workspace=self._rpn_ws))
+                self._post[par].append(lambda d=d, out=out, i=i: ops.fcos_proposals(d, self.device, out=out, workspace=self._rpn_ws[i]))
         self._descs = descs
         self._valid = valid_dims
         self._post_graph = [None, None]
@@ -681,14 +698,15 @@ class _Plan:
                                       eng.nms_thresh, eng.score_thresh, eng.min_size, self.dims, valid=v)
                 self._descs.append(d)
                 ws_bytes = max(ws_bytes, lib().nrpn_rpn_workspace_bytes(ctypes.byref(d)))
-        if self._rpn_ws is None or self._rpn_ws.numel() < ws_bytes:
-            self._rpn_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        # one workspace per scene: the scenes of a batch are post-processed concurrently (parallel branches of the side-stream graph)
+        if self._rpn_ws is None or self._rpn_ws[0].numel() < ws_bytes or len(self._rpn_ws) != self.n:
+            self._rpn_ws = [torch.empty(ws_bytes, dtype=torch.uint8, device=self.device) for _ in range(self.n)]
         for par in range(2):
             o = self._out[par]
             for i in range(self.n):
                 d = self._descs[par * self.n + i]
                 out = (o["boxes"][i], o["scores"][i], o["levels"][i], o["count"][i:i + 1])
-                self._post[par].append(lambda d=d, out=out: ops.rpn_proposals(d, self.device, out=out, workspace=self._rpn_ws))
+                self._post[par].append(lambda d=d, out=out, i=i: ops.rpn_proposals(d, self.device, out=out, workspace=self._rpn_ws[i]))
         self._valid = valid_dims
         self._post_graph = [None, None]
 
@@ -702,8 +720,27 @@ class _Plan:
                 f()
 
     def _run_post_eager(self, par):
-        for f in self._post[par]:
-            f()
+        """Post-processing of every scene of the batch.  The scenes are independent chains of ~45 small kernels (top-k, decode, NMS): scene 0
+        runs on the current stream, the others on branch streams forked from / joined to it -- eagerly, or as parallel branches of the
+        captured side-stream graph -- so the chain's critical path is one scene long, not n."""
+        fs = self._post[par]
+        if len(fs) == 1 or os.environ.get("NRPN_POST_PARALLEL", "1") == "0":
+            for f in fs:
+                f()
+            return
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_branch", None) is None or len(self._branch) < len(fs) - 1:
+            self._branch = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(len(fs) - 1)]
+        for i, f in enumerate(fs):
+            if i == 0:
+                continue
+            b = self._branch[i - 1]
+            b.wait_stream(cur)
+            with torch.cuda.stream(b):
+                f()
+        fs[0]()
+        for i in range(1, len(fs)):
+            cur.wait_stream(self._branch[i - 1])
 
     def _run_eager(self):
         """Everything for one batch on the current stream (warm-up, launch counting, profiling)."""

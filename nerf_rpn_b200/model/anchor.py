@@ -88,5 +88,7 @@ class RPNHead(nn.Module):
                     torch.nn.init.constant_(layer.bias, 0)
 
     def forward(self, x: List[Tensor]):
-        raise RuntimeError("nerf_rpn_b200.RPNHead is executed inside NeRFRegionProposalNetwork's fused B200 engine "
-                           "(all pyramid levels per launch); it is not called on its own")
+        """anchor.py:206-213 stand-alone: list of (N,256,w,l,h) fp32 CUDA -> (logits [(N,A,w,l,h)], bbox_reg [(N,A*6|8,w,l,h)]).
+        One launch per layer over all levels; inside NeRFRegionProposalNetwork the same layers are part of the captured engine."""
+        from ._eager import rpn_head_forward
+        return rpn_head_forward(self, x, getattr(self, "precision", None))

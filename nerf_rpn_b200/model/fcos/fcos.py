@@ -12,7 +12,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ...precision import resolve as _resolve_precision
+from ...precision import EngineHolder, resolve as _resolve_precision
 
 
 class Scale(nn.Module):
@@ -56,7 +56,9 @@ class FCOSHead(nn.Module):
         self.scales = nn.ModuleList([Scale(init_value=1.0) for _ in range(5)])
 
     def forward(self, x):
-        raise RuntimeError("nerf_rpn_b200.FCOSHead is executed inside FCOSOverNeRF's fused B200 engine")
+        """fcos/fcos.py:104-130 stand-alone (eval): list of (N,256,w,l,h) fp32 CUDA -> (logits, bbox_reg, centerness) lists."""
+        from .._eager import fcos_head_forward
+        return fcos_head_forward(self, x, getattr(self, "precision", None))
 
 
 class FCOSPostProcessor(nn.Module):
@@ -85,7 +87,7 @@ class FCOSModule(nn.Module):
         raise RuntimeError("nerf_rpn_b200.FCOSModule runs inside FCOSOverNeRF.forward (one captured launch sequence)")
 
 
-class FCOSOverNeRF(nn.Module):
+class FCOSOverNeRF(EngineHolder, nn.Module):
     def __init__(self, args, backbone, fpn_strides, world_size=1, precision=None) -> None:
         if not hasattr(backbone, "out_channels"):
             raise ValueError("backbone should contain an attribute out_channels specifying the number of output "

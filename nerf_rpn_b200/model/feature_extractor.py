@@ -12,7 +12,7 @@ from typing import List
 import torch
 from torch import nn
 
-from ..precision import resolve as _resolve_precision
+from ..precision import EngineHolder, resolve as _resolve_precision
 
 
 class Bottleneck(nn.Module):
@@ -31,11 +31,13 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        raise RuntimeError("nerf_rpn_b200.Bottleneck is a parameter container; it is executed by ResNet_FPN_256's "
-                           "fused B200 engine, not called on its own")
+        """(N, inplanes, W, L, H) fp32 CUDA -> (N, 4*planes, w, l, h): feature_extractor.py:48-68 on the tcgen05 kernels (eval mode).
+        Inside ResNet_FPN_256 the same layers run as part of the captured engine; this is the stand-alone entry point."""
+        from ._eager import bottleneck_forward
+        return bottleneck_forward(self, x, getattr(self, "precision", None))
 
 
-class ResNet_FPN_256(nn.Module):
+class ResNet_FPN_256(EngineHolder, nn.Module):
     """ResNet-FPN backbone, same constructor / attributes as the reference (feature_extractor.py:159-194)."""
 
     def __init__(self, block, layers, input_dim=4, is_max_pool=False, precision=None):
@@ -111,7 +113,7 @@ vgg_cfgs = {     # feature_extractor.py:278-286
 }
 
 
-class VGG_FPN(nn.Module):
+class VGG_FPN(EngineHolder, nn.Module):
     """VGG-FPN backbone (feature_extractor.py:289-377), cfgs "AF" / "DF" / "EF" (run_rpn.py:277-280 builds AF and EF):
     stem Conv3d(4,64,7) [stride 2 + max-pool when input_size >= 160, else stride 1] + BN + ReLU, four stages of
     (Conv3d 3^3 + BN + ReLU)* [+ MaxPool3d(2,2,ceil_mode=True)], FPN neck on the four stage outputs."""
@@ -228,7 +230,7 @@ class PatchMerging(nn.Module):
         self.norm = norm_layer(8 * dim)
 
 
-class SwinTransformer_FPN(nn.Module):
+class SwinTransformer_FPN(EngineHolder, nn.Module):
     """3-D Swin Transformer + FPN (feature_extractor.py:689-789), same constructor as the reference; run_rpn.py:281-292 builds
     Swin-T/S/B/L with patch 4^3, window 4^3."""
 

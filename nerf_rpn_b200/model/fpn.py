@@ -1,7 +1,8 @@
 """FPN neck. Mirrors nerf_rpn/model/fpn.py:59-132 for the configuration the reference uses
 (FPN([128,256,512,512], 256, 4), feature_extractor.py:304): per level a 1^3 lateral conv and a 3^3 output conv, created in
 the reference's order (lateral_i, fpn_i alternating) so seeds and state_dict keys (lateral_convs.{i}.*, fpn_convs.{i}.*)
-match.  forward (fpn.py:134-161: top-down nearest-upsample accumulation, then the 3^3 convs) is executed by the engine."""
+match.  forward (fpn.py:134-161: top-down nearest-upsample accumulation, then the 3^3 convs) runs inside the backbone's captured
+engine; called on its own it launches the same kernels eagerly (model/_eager.py)."""
 from torch import nn
 
 
@@ -29,4 +30,6 @@ class FPN(nn.Module):
                 nn.init.constant_(m.bias, 0)
 
     def forward(self, inputs):
-        raise RuntimeError("nerf_rpn_b200.FPN is executed inside its backbone's fused B200 engine")
+        """fpn.py:134-161 stand-alone: tuple of (N, C_i, w, l, h) fp32 CUDA -> tuple of (N, out_channels, w, l, h)."""
+        from ._eager import fpn_forward
+        return fpn_forward(self, inputs, getattr(self, "precision", None))

@@ -19,6 +19,31 @@ def _default_anchorgen():
     return AnchorGenerator3D(anchor_sizes, aspect_ratios)
 
 
+class _RPNTrainStep(torch.autograd.Function):
+    """One autograd node around the engine's forward / backward launch lists (see NeRFRegionProposalNetwork._forward_train)."""
+
+    @staticmethod
+    def forward(ctx, eng, grids, targets, *params):
+        n, c, X, Y, Z = grids.shape
+        plan = eng.plan(n, (X, Y, Z))
+        plan.forward_loss(grids, targets, 1.0, 1.0)
+        ctx.eng, ctx.plan = eng, plan
+        losses = eng.losses.clone()
+        return losses[0].clone(), losses[1].clone()          # fresh 0-dim tensors (run_rpn.py:385 scales them in place)
+
+    @staticmethod
+    def backward(ctx, g_obj, g_reg):
+        eng, plan = ctx.eng, ctx.plan
+        plan.loss_grad(float(g_obj), float(g_reg))          # the loss weights arrive as the upstream gradients (run_rpn.py:385-387)
+        plan.backward()
+        inv = 1.0 / eng.loss_scale
+        grads = []
+        for p in list(eng.bb.parameters()) + list(eng.head.parameters()):
+            g = eng.grad_of(p).view(p.shape)
+            grads.append(g * inv if inv != 1.0 else g.clone())
+        return (None, None, None, *grads)
+
+
 class NeRFRegionProposalNetwork(nn.Module):
     def __init__(self, backbone, rpn_anchor_generator=None, rpn_head=None, rpn_pre_nms_top_n_train=2000,
                  rpn_pre_nms_top_n_test=1000, rpn_post_nms_top_n_train=2000, rpn_post_nms_top_n_test=1000,
@@ -47,6 +72,25 @@ class NeRFRegionProposalNetwork(nn.Module):
         self.precision = _resolve_precision(precision)     # "bf16" | "fp16" | "fp16_w2" (nerf_rpn_b200/precision.py); explicit, in repr
         self._engine = None
         self._engine_key = None
+        self._train_engine = None
+
+    # engines hold CUDA graphs, streams and ctypes objects: keep them out of pickles / deep copies (torch.save(model), spawn-based DDP)
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d["_engine"], d["_engine_key"], d["_train_engine"] = None, None, None
+        return d
+
+    def _output_objectness(self, plan, ori_sizes, output_paths):
+        """--output_voxel_scores (rpn.py:538-549): per scene, per level, the maximum objectness logit over the anchors cropped to the
+        un-padded extent ceil(size / 2^(level+2)); npz with keys '0'..'3'."""
+        A = self.rpn.anchor_generator.num_anchors_per_location()[0]
+        for i in range(len(ori_sizes)):
+            all_levels = {}
+            for level, p in enumerate(plan.pred):
+                score = p[i][..., :A].max(dim=-1)[0]
+                w, l, h = np.ceil(np.array(ori_sizes[i]) / 2 ** (level + 2)).astype(int)
+                all_levels[str(level)] = score[:w, :l, :h].cpu().numpy()
+            np.savez_compressed(output_paths[i], **all_levels)
 
     def extra_repr(self):
         return f"precision={self.precision!r}"
@@ -75,12 +119,37 @@ class NeRFRegionProposalNetwork(nn.Module):
             self._engine_key = key
         return self._engine
 
+    # ------------------------------------------------------------------------------------------------ training
+    def train_engine(self, **kw):
+        """The B200 training engine bound to this model (nerf_rpn_b200/train.py).  Created on first use; keyword arguments (precision,
+        lr, weight_decay, clip_grad_norm, reg_loss_weight, process_group ...) configure a NEW engine."""
+        from ..train import RPNTrainEngine
+        if self._train_engine is None or kw:
+            self._train_engine = RPNTrainEngine(self, **kw)
+        return self._train_engine
+
+    def _forward_train(self, meshes, targets):
+        """Training-mode forward as the reference defines it (nerf_rpn.py:166-217 + rpn.py:514-534): returns losses that carry a
+        grad_fn, so the UNMODIFIED loop of run_rpn.py:384-395 (`loss.backward(); clip_grad_norm_; optimizer.step()`) and a DDP
+        wrapper drive the B200 forward / backward kernels: torch.autograd only sees ONE node whose backward runs the engine's launch
+        list and hands every parameter its gradient."""
+        if targets is None:
+            raise ValueError("targets should not be None")
+        if len({tuple(m.shape) for m in meshes}) != 1:
+            raise NotImplementedError("nerf_rpn_b200: a training batch must hold equally sized meshes (the reference trains with one "
+                                      "scene per rank, train.sh: batch 8 over 8 GPUs)")
+        eng = self.train_engine()
+        eng.overlap_allreduce = False               # gradients are returned to autograd; a DDP wrapper all-reduces them itself
+        eng.sync_parameters()
+        grids = torch.stack([m if m.is_cuda else m.cuda() for m in meshes], 0).float()
+        params = list(self.backbone.parameters()) + list(self.rpn.head.parameters())
+        l_obj, l_reg = _RPNTrainStep.apply(eng, grids, [t for t in targets], *params)
+        zero = torch.zeros((), dtype=torch.float32, device=grids.device)    # 2-D projection loss: weight 0 in every shipped recipe, not evaluated
+        return [None, None, None], {"loss_objectness": l_obj, "loss_rpn_box_reg": l_reg, "loss_rpn_box_reg_2d": zero}, None
+
     def forward(self, meshes, targets=None, objectness_output_paths=None):
         if self.training:
-            raise NotImplementedError("nerf_rpn_b200: training-mode forward is not implemented by the B200 engine yet "
-                                      "(round 1 = inference path); use .eval()")
-        if objectness_output_paths is not None:
-            raise NotImplementedError("nerf_rpn_b200: --output_voxel_scores export (rpn.py:538-549) is not implemented")
+            return self._forward_train(meshes, targets)
         original_mesh_sizes: List[Tuple[int, int, int]] = []
         for mesh in meshes:
             val = mesh.shape[-3:]
@@ -101,6 +170,8 @@ class NeRFRegionProposalNetwork(nn.Module):
         torch.cuda.current_stream().wait_event(plan.done)            # post-processing runs on the engine's side stream
         counts = plan.out_count.tolist()                              # the one host sync: data-dependent output sizes
         features = [f.permute(0, 4, 1, 2, 3).float() for f in plan.features]
+        if objectness_output_paths is not None:
+            self._output_objectness(plan, original_mesh_sizes, objectness_output_paths)
         proposals = [plan.out_boxes[i, :k].clone() for i, k in enumerate(counts)]
         level_index = [plan.out_levels[i, :k].clone() for i, k in enumerate(counts)]
         scores = [plan.out_scores[i, :k].clone() for i, k in enumerate(counts)]

@@ -64,5 +64,43 @@ class RegionProposalNetwork(nn.Module):
         return labels, matched_gt_boxes
 
     def forward(self, meshes, features, original_mesh_sizes, targets=None, objectness_output_paths=None):
-        raise RuntimeError("nerf_rpn_b200.RegionProposalNetwork runs inside NeRFRegionProposalNetwork.forward "
-                           "(backbone, head and post-processing are one captured launch sequence)")
+        """rpn.py:458-536, eval branch, stand-alone: meshes (N,4,W,L,H), features = 4 x (N,256,w,l,h) fp32 CUDA ->
+        (boxes [K_i x 6|7], level_indexes [K_i], losses {}, scores [K_i]).  Head = model/_eager.py (one launch per layer over all
+        levels), then the fused device post-processing (anchors, decode, per-level top-k, clip / filter, per-level NMS, top
+        post_nms_top_n) -- the same kernels NeRFRegionProposalNetwork.forward runs inside its captured engine."""
+        if self.training:
+            raise NotImplementedError("nerf_rpn_b200: RegionProposalNetwork.forward in training mode is not a stand-alone path; the losses "
+                                      "are computed by the whole-model training engine (NeRFRegionProposalNetwork.forward / train.py)")
+        if objectness_output_paths is not None:
+            self.output_objectness_from(features, original_mesh_sizes, objectness_output_paths)
+        from ._eager import rpn_head_pred
+        pred = rpn_head_pred(self.head, features, getattr(self, "precision", None))
+        n = pred[0].shape[0]
+        mesh = tuple(int(v) for v in meshes.shape[-3:])
+        fdims = [tuple(p.shape[1:4]) for p in pred]
+        strides = [tuple(mesh[k] // d[k] for k in range(3)) for d in fdims]
+        ag = self.anchor_generator
+        cells, A = ag.cell_anchors_np(), ag.num_anchors_per_location()[0]
+        boxes, levels, scores = [], [], []
+        for i in range(n):
+            valid = tuple(int(v) for v in original_mesh_sizes[i]) if n > 1 else None       # padding masks only when batch > 1 (rpn.py:501)
+            desc = ops.make_rpn_desc([p[i].reshape(-1, 128) for p in pred], fdims, strides, cells, A, self.rotate, self.pre_nms_top_n(),
+                                     self.post_nms_top_n(), self.nms_thresh, self.score_thresh, self.min_size, mesh, valid=valid)
+            b, s, lv, cnt = ops.rpn_proposals(desc, pred[0].device)
+            k = int(cnt.item())
+            boxes.append(b[:k]); scores.append(s[:k]); levels.append(lv[:k])
+        return boxes, levels, {}, scores
+
+    def output_objectness_from(self, features, ori_sizes, output_paths):
+        """--output_voxel_scores (rpn.py:538-549): per scene and level the maximum objectness LOGIT over the anchors, cropped to the
+        un-padded extent ceil(size / 2^(level+2)), written as npz with keys '0'..'3'."""
+        import numpy as np
+        from ._eager import rpn_head_forward
+        logits, _ = rpn_head_forward(self.head, features, getattr(self, "precision", None))
+        for i in range(len(ori_sizes)):
+            all_levels = {}
+            for level, lg in enumerate(logits):
+                score = lg[i].max(dim=0)[0]
+                w, l, h = np.ceil(np.array(ori_sizes[i]) / 2 ** (level + 2)).astype(int)
+                all_levels[str(level)] = score[:w, :l, :h].cpu().numpy()
+            np.savez_compressed(output_paths[i], **all_levels)

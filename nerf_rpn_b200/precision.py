@@ -29,3 +29,15 @@ def resolve(precision=None) -> str:
 
 def bench_dtype(precision: str) -> str:
     return {"bf16": "bf16", "fp16": "f16", "fp16_w2": "f16 (backbone weights as hi+lo f16 pairs)"}[precision]
+
+
+class EngineHolder:
+    """Mixin of the module mirrors that cache an engine (CUDA graphs, streams, ctypes objects): keeps it out of pickles and deep copies
+    (torch.save(model), copy.deepcopy, spawn-based DDP), like the reference's plain nn.Modules support."""
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        for k in ("_engine", "_engine_key", "_train_engine"):
+            if k in d:
+                d[k] = None
+        return d

@@ -154,6 +154,7 @@ class RPNTrainEngine:
         self._norm_ws = torch.empty(lib().nrpn_grad_norm_workspace_bytes(), dtype=torch.uint8, device=self.device)
         self._red_ws = torch.empty(lib().nrpn_chan_reduce_workspace_bytes(2048), dtype=torch.uint8, device=self.device)
         self.losses = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self.overlap_allreduce = True       # False: leave the gradient all-reduce to the caller (DDP wrapping the autograd compat path)
         self.gen = None
         if seed is not None:
             self.gen = torch.Generator(device=self.device); self.gen.manual_seed(seed)
@@ -175,10 +176,23 @@ class RPNTrainEngine:
             n = p.numel()
             self.flat_p[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + n].view(p.shape)
-            p.grad = self.flat_g[off:off + n].view(p.shape)
             self.offsets[id(p)] = (off, n)
             off += n
         self.n_params = total
+        self._params = params
+        self._packed_ver = None
+
+    def sync_parameters(self):
+        """Drop-in path (torch optimiser / load_state_dict between steps): re-point parameters that were re-materialised back into the flat
+        buffer and re-pack the 16-bit operands when any master weight changed since the last packing."""
+        ver = tuple(p._version for p in self._params)
+        moved = False
+        for p in self._params:
+            off, n = self.offsets[id(p)]
+            if p.data.data_ptr() != self.flat_p.data_ptr() + 4 * off:
+                self.flat_p[off:off + n].copy_(p.data.reshape(-1)); p.data = self.flat_p[off:off + n].view(p.shape); moved = True
+        if moved or ver != self._packed_ver:
+            self.repack()
 
     def grad_of(self, p):
         off, n = self.offsets[id(p)]
@@ -215,6 +229,7 @@ class RPNTrainEngine:
 
     def repack(self):
         """fp32 master weights -> 16-bit GEMM operands (after every optimiser step / checkpoint load)."""
+        self._packed_ver = tuple(p._version for p in self._params)
         for c in self.all_convs:
             c.repack()
         hd, A = self.head, self.A
@@ -604,50 +619,56 @@ class _TrainPlan:
         perm2 = torch.randperm(negative.numel(), device=negative.device, generator=g)[:num_neg]
         return positive[perm1].contiguous(), negative[perm2].contiguous()
 
-    def run(self, grids, targets, backward=True):
-        eng, L, n = self.eng, lib(), self.n
+    def forward_loss(self, grids, targets, w_obj=1.0, w_reg=None):
+        """Forward launches, target assignment, sampling, losses; fills d(pred) for the weighted sum w_obj * L_obj + w_reg * L_reg."""
+        eng, n = self.eng, self.n
         if ops.is_channels_last_grid(grids) or grids.is_contiguous():
             self._src = grids
         else:
             self._src = grids.contiguous()
         for f in self.fwd:
             f()
-        # ---- targets, sampling, losses and d(pred)
         anchors = self._anchors()
-        per_mesh = self.pred.shape[0] // n
         samples = []
+        forced = getattr(self, "forced_samples", None)         # tests: (pos, neg) index tensors per mesh instead of the sampler's draw
         for i in range(n):
             gt = targets[i].to(device=eng.device, dtype=torch.float32).contiguous()
-            if gt.numel() == 0:
+            if gt.numel() == 0:                                     # background mesh (rpn.py:246-250): every anchor is a negative
                 labels = torch.zeros(anchors.shape[0], dtype=torch.float32, device=eng.device)
-                matched = torch.zeros((anchors.shape[0], gt.shape[1] if gt.dim() == 2 else 6), dtype=torch.float32, device=eng.device)
                 pos, neg = self._sample(labels)
-                samples.append((pos, neg, matched[:0]))
+                samples.append((pos, neg, torch.zeros((0, 7 if eng.rotated else 6), dtype=torch.float32, device=eng.device)))
                 continue
             labels, idx = ops.assign_targets(anchors, gt, None, eng.rpn.fg_iou_thresh, eng.rpn.bg_iou_thresh, True)
-            pos, neg = self._sample(labels)
+            pos, neg = self._sample(labels) if forced is None else (forced[i][0].contiguous(), forced[i][1].contiguous())
             samples.append((pos, neg, gt[idx[pos].clamp(min=0)].contiguous()))
+        self.last_samples = samples
+        self.loss_grad(w_obj, eng.w_reg if w_reg is None else w_reg)
+
+    def loss_grad(self, w_obj, w_reg):
+        """(Re)computes the two losses and d(w_obj * L_obj + w_reg * L_reg)/d(pred) * loss_scale for the samples of the last forward."""
+        eng, L, n = self.eng, lib(), self.n
+        samples = self.last_samples
         norm = float(sum(p.numel() + q.numel() for p, q, _ in samples))
         eng.losses.zero_()
         self.dpred.zero_()
-        self.last_samples = samples
         for i, (pos, neg, gtp) in enumerate(samples):
             preds = [p[i].reshape(-1, 128) for p in self.pred_levels]
             dpreds = [p[i].reshape(-1, 128) for p in self.dpred_levels]
             desc = ops.make_rpn_desc(preds, self.feat_dims, self.strides, eng.cells, eng.A, eng.rotated, 1, 1, 0.5, 0.0, 1e-3, self.dims)
             arr = (ctypes.c_void_p * len(dpreds))(*[t.data_ptr() for t in dpreds])
-            check(L.nrpn_rpn_loss(ctypes.byref(desc), arr, _p(pos), int(pos.numel()), _p(neg), int(neg.numel()), _p(gtp), norm, 1.0, float(eng.w_reg),
-                                  float(eng.loss_scale), _p(eng.losses), None, self.f16, _stream()), "rpn_loss")
-        if not backward:
-            return
-        # ---- backward (reverse construction order).  Gradients become final from the END of the flat bucket (head, FPN) towards its
-        # start (stem): every time >= bucket_elems new elements are final their all-reduce is launched on the comm stream, overlapping
-        # the dgrad / wgrad of the layers below (run_rpn.py:235-236: DDP's bucketed all-reduce during loss.backward()).
+            check(L.nrpn_rpn_loss(ctypes.byref(desc), arr, _p(pos), int(pos.numel()), _p(neg), int(neg.numel()), _p(gtp), max(norm, 1.0), float(w_obj),
+                                  float(w_reg), float(eng.loss_scale), _p(eng.losses), None, self.f16, _stream()), "rpn_loss")
+
+    def backward(self):
+        """Backward launches in reverse construction order.  Gradients become final from the END of the flat bucket (head, FPN) towards
+        its start (stem): every time >= bucket_elems new elements are final their all-reduce is launched on the comm stream, overlapping
+        the dgrad / wgrad of the layers below (run_rpn.py:235-236: DDP's bucketed all-reduce during loss.backward())."""
+        eng = self.eng
         hi = eng.n_params
         self.allreduce_calls = 0
         for f, lo in zip(reversed(self.bwd), reversed(self.bwd_lo)):
             f()
-            if eng.world > 1 and (hi - lo >= eng.bucket_elems or lo == 0) and hi > lo:
+            if eng.world > 1 and eng.overlap_allreduce and (hi - lo >= eng.bucket_elems or lo == 0) and hi > lo:
                 ev = torch.cuda.Event()
                 ev.record()
                 eng.comm_stream.wait_event(ev)
@@ -655,3 +676,8 @@ class _TrainPlan:
                     torch.distributed.all_reduce(eng.flat_g[lo:hi], group=eng.pg)
                 self.allreduce_calls += 1
                 hi = lo
+
+    def run(self, grids, targets, backward=True):
+        self.forward_loss(grids, targets)
+        if backward:
+            self.backward()

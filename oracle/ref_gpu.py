@@ -57,6 +57,7 @@ def load(need_k1: bool = True):
         ns.oriented_iou_loss = importlib.import_module("model.rotated_iou.oriented_iou_loss")
         ns.box_intersection_2d = importlib.import_module("model.rotated_iou.box_intersection_2d")
         ns.fcos = importlib.import_module("model.fcos.fcos")
+        ns.fpn = importlib.import_module("model.fpn")
         ns.eval = importlib.import_module("eval")
         ns.sort_vertices = sys.modules.get("sort_vertices")
     finally:

@@ -54,7 +54,12 @@ def test_sort_vertices_bit_identical_to_reference_kernel():
     g2 = torch.Generator().manual_seed(22)
     v = torch.rand(8, 1024, 24, 2, generator=g2).cuda()
     v = (v - v.mean(dim=2, keepdim=True)).contiguous()
-    m = (torch.rand(8, 1024, 24, generator=g2) > 0.8).cuda()
+    m = torch.rand(8, 1024, 24, generator=g2) > 0.8
+    # a polygon with more than 8 valid vertices makes the reference write PAST its 9 output slots into the next polygon's first slot
+    # (:103-106: observed on the B200 as 3 % of rows with a foreign first index): keep every polygon at <= 8 so the comparison is defined
+    over = m.int().sum(-1) > 8
+    m[over] = False
+    m = m.cuda()
     nv = m.int().sum(-1).int()
     want = ref.sort_vertices.sort_vertices_forward(v, m, nv)
     got = ops.sort_vertices_forward(v, m, nv)
