@@ -156,6 +156,11 @@ int nrpn_pack_stem_input(const float *grid, int n, int x, int y, int z, void *pa
                          int channels_last /* 0: grid is (N,4,X,Y,Z); 1: (N,X,Y,Z,4) as stored on disk, datasets.py:49-57 */,
                          nrpn_stream_t stream);
 
+/* Same, with density_to_alpha = 1 applying the reference dataset's --normalize_density map to the last channel on the device:
+ * alpha = clip(1 - exp(-exp(sigma) / 100), 0, 1) (datasets.py:50-52,165-167), fused into the read of the grid. */
+int nrpn_pack_stem_input_ex(const float *grid, int n, int x, int y, int z, void *packed, int act_fp16, int channels_last,
+                            int density_to_alpha, nrpn_stream_t stream);
+
 /* Same packing from a raw uint8 grid in its on-disk order (N,X,Y,Z,4): bytes are normalised by / 255 on the device, as
  * datasets.py:59-61 does on the host (.float() / 255.0); a quarter of the fp32 host-to-device traffic. */
 int nrpn_pack_stem_input_u8(const uint8_t *grid_xyzc, int n, int x, int y, int z, void *packed, int act_fp16, nrpn_stream_t stream);

@@ -9,8 +9,15 @@ namespace nrpn {
 // With this layout the reference's stem Conv3d(4,64,k=7,s=2,p=3) (feature_extractor.py:163) is a stride-1
 // implicit GEMM with 4x4x2 taps of K = 64 (see nerf_rpn_b200/engine.py: pack_stem_weight).
 // One thread writes one 16-byte chunk (8 channels); 8 consecutive lanes cover one 128-byte row.
+// density_to_alpha (datasets.py:165-167, applied by the reference's dataset on the host when --normalize_density is set):
+// alpha = clip(1 - exp(-exp(sigma) / 100), 0, 1) on the last channel, fp32 like numpy computes it on a float32 array.
+__device__ __forceinline__ float density_to_alpha(float sigma) {
+    const float a = 1.0f - expf(-__fdiv_rn(expf(sigma), 100.0f));
+    return fminf(fmaxf(a, 0.0f), 1.0f);
+}
+
 __global__ void pack_stem_kernel(const float* __restrict__ grid, int n, int X, int Y, int Z, int X2, int Y2, int Z2,
-                                 __nv_bfloat16* __restrict__ out, int fp16) {
+                                 __nv_bfloat16* __restrict__ out, int fp16, int alpha) {
     const size_t total = (size_t)n * X2 * Y2 * (Z2 + 1) * 8;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int s = (int)(t & 7);
@@ -31,6 +38,7 @@ __global__ void pack_stem_kernel(const float* __restrict__ grid, int n, int X, i
                 val[c] = p[0];
                 if (z + 1 < Z) val[4 + c] = p[1];
             }
+            if (alpha) { val[3] = density_to_alpha(val[3]); if (z + 1 < Z) val[7] = density_to_alpha(val[7]); }
         }
         uint32_t h[4];
 #pragma unroll
@@ -42,7 +50,7 @@ __global__ void pack_stem_kernel(const float* __restrict__ grid, int n, int X, i
 // Same packing from the grid as it is stored on disk and handed over by the reference's dataset (datasets.py:49-57: a
 // (4,W,L,H) VIEW of the (W,L,H,4) array): one 128-bit load per voxel instead of four scalar loads from four channel planes.
 __global__ void pack_stem_cl_kernel(const float4* __restrict__ grid, int n, int X, int Y, int Z, int X2, int Y2, int Z2,
-                                    __nv_bfloat16* __restrict__ out, int fp16) {
+                                    __nv_bfloat16* __restrict__ out, int fp16, int alpha) {
     const size_t total = (size_t)n * X2 * Y2 * (Z2 + 1) * 8;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int s = (int)(t & 7);
@@ -58,6 +66,7 @@ __global__ void pack_stem_cl_kernel(const float4* __restrict__ grid, int n, int 
             const float4* p = grid + (((size_t)b * X + x) * Y + y) * Z + z;
             a = __ldg(p);
             if (z + 1 < Z) c = __ldg(p + 1);
+            if (alpha) { a.w = density_to_alpha(a.w); if (z + 1 < Z) c.w = density_to_alpha(c.w); }
         }
         const uint32_t h0 = pack_act2(a.x, a.y, fp16), h1 = pack_act2(a.z, a.w, fp16);
         const uint32_t h2 = pack_act2(c.x, c.y, fp16), h3 = pack_act2(c.z, c.w, fp16);
@@ -217,22 +226,27 @@ using namespace nrpn;
 extern "C" {
 #pragma GCC visibility push(default)
 
-int nrpn_pack_stem_input(const float* grid, int n, int x, int y, int z, void* packed, int act_fp16, int channels_last,
-                         nrpn_stream_t stream) {
+int nrpn_pack_stem_input_ex(const float* grid, int n, int x, int y, int z, void* packed, int act_fp16, int channels_last, int density_to_alpha,
+                            nrpn_stream_t stream) {
+    const int alpha = density_to_alpha ? 1 : 0;
     if (!grid || !packed || n < 1 || x < 1 || y < 1 || z < 1) return NRPN_ERR_INVALID;
     const int X2 = (x + 1) / 2, Y2 = (y + 1) / 2, Z2 = (z + 1) / 2;
     const size_t total = (size_t)n * X2 * Y2 * (Z2 + 1) * 8;
     if (channels_last) {
         if (reinterpret_cast<uintptr_t>(grid) % 16 != 0) return NRPN_ERR_INVALID;
         pack_stem_cl_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(grid), n, x, y, z, X2, Y2, Z2,
-                                                                                   reinterpret_cast<__nv_bfloat16*>(packed), act_fp16 ? 1 : 0);
+                                                                                   reinterpret_cast<__nv_bfloat16*>(packed), act_fp16 ? 1 : 0, alpha);
         NRPN_LAUNCH_CHECK();
         return NRPN_OK;
     }
     pack_stem_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grid, n, x, y, z, X2, Y2, Z2,
-                                                                            reinterpret_cast<__nv_bfloat16*>(packed), act_fp16 ? 1 : 0);
+                                                                            reinterpret_cast<__nv_bfloat16*>(packed), act_fp16 ? 1 : 0, alpha);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
+}
+
+int nrpn_pack_stem_input(const float* grid, int n, int x, int y, int z, void* packed, int act_fp16, int channels_last, nrpn_stream_t stream) {
+    return nrpn_pack_stem_input_ex(grid, n, x, y, z, packed, act_fp16, channels_last, 0, stream);
 }
 
 int nrpn_pack_stem_input_u8(const uint8_t* grid, int n, int x, int y, int z, void* packed, int act_fp16, nrpn_stream_t stream) {

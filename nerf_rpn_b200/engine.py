@@ -69,11 +69,14 @@ class RPNInferenceEngine:
 
     def __init__(self, backbone, head=None, anchor_cells=None, num_anchors: int = 0, rotated: bool = False,
                  pre_nms_top_n: int = 2500, post_nms_top_n: int = 2500, nms_thresh: float = 0.3, score_thresh: float = 0.0,
-                 min_size: float = 1e-3, use_graph: bool = True, fcos: Optional[dict] = None, precision: Optional[str] = None):
+                 min_size: float = 1e-3, use_graph: bool = True, fcos: Optional[dict] = None, precision: Optional[str] = None,
+                 density_to_alpha: bool = False):
         precision = _resolve_precision(precision)            # "bf16" | "fp16" | "fp16_w2" (nerf_rpn_b200/precision.py)
         self.precision = precision
         self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float16
         self.wsplit = precision == "fp16_w2"                 # backbone / FPN weights as hi + lo halves
+        # datasets.py:50-52 (--normalize_density) applied by the stem packing kernel instead of numpy on the host (ResNet / VGG strided stems)
+        self.density_to_alpha = bool(density_to_alpha)
         self.backbone, self.head = backbone, head
         self.fcos = fcos                   # None: anchor head (anchor.py:177-213); dict: FCOS head + post-processing settings
         self.cells = anchor_cells          # list (levels) of (A, 6) float arrays
@@ -260,6 +263,8 @@ class RPNInferenceEngine:
         # a grid handed over as the dataset's (4,W,L,H) VIEW of the on-disk (W,L,H,4) array is consumed in place by the
         # ResNet stem packing (128-bit loads); the other backbones take a copy into NCDHW first
         cl = bool(channels_last) and self.kind == "resnet" and max(dims) >= 0
+        if self.density_to_alpha and (u8 or self.kind == "swin" or (self.kind == "vgg" and not self.layers.get("vgg_strided", False))):
+            raise NotImplementedError("density_to_alpha on the device is fused into the fp32 stride-2 stem packing (ResNet_FPN_256, VGG_FPN at >= 160)")
         if u8 and not cl:
             raise NotImplementedError("raw uint8 grids are consumed by the ResNet stem packing only; normalise to fp32 for the other backbones")
         key = (n, tuple(dims), str(device), cl, bool(u8))
@@ -397,7 +402,7 @@ class _Plan:
         X, Y, Z = dims
         d1 = _down(dims)
         self.packed = torch.empty((n, d1[0], d1[1], d1[2] + 1, 64), **bf)
-        self.launches.append(lambda: ops.pack_stem_input(self._src, self.packed))
+        self.launches.append(lambda: ops.pack_stem_input(self._src, self.packed, density_to_alpha=self.eng.density_to_alpha))
         self.names[id(self.launches[-1])] = ("pack_stem_input", 0.0)
         c1 = buf(d1, 64)
         conv(L["stem"], [self.packed], [c1], [(d1[0], d1[1], d1[2] + 1)], [d1], real=(4, 343, 64), name="stem7x7x7s2(s2d)")
@@ -457,7 +462,7 @@ class _Plan:
         if L["vgg_strided"]:
             d1 = _down(dims)
             self.packed = torch.empty((n, d1[0], d1[1], d1[2] + 1, 64), **bf)
-            self.launches.append(lambda: ops.pack_stem_input(self._src, self.packed))
+            self.launches.append(lambda: ops.pack_stem_input(self._src, self.packed, density_to_alpha=self.eng.density_to_alpha))
             self.names[id(self.launches[-1])] = ("pack_stem_input", 0.0)
             c1 = buf(d1, 64)
             conv(L["stem"], [self.packed], [c1], [(d1[0], d1[1], d1[2] + 1)], [d1], real=(4, 343, 64), name="stem7x7x7s2(s2d)")

@@ -49,7 +49,7 @@ class NeRFRegionProposalNetwork(nn.Module):
                  rpn_pre_nms_top_n_test=1000, rpn_post_nms_top_n_train=2000, rpn_post_nms_top_n_test=1000,
                  rpn_nms_thresh=0.7, rpn_fg_iou_thresh=0.7, rpn_bg_iou_thresh=0.3, rpn_batch_size_per_image=256,
                  rpn_positive_fraction=0.5, rpn_score_thresh=0.0, iou_batch_size=16, rotated_bbox=False,
-                 reg_loss_type="smooth_l1", precision=None, **kwargs):
+                 reg_loss_type="smooth_l1", precision=None, density_to_alpha_on_device=False, **kwargs):
         if not hasattr(backbone, "out_channels"):
             raise ValueError("backbone should contain an attribute out_channels specifying the number of output "
                              "channels (assumed to be the same for all the levels)")
@@ -70,6 +70,8 @@ class NeRFRegionProposalNetwork(nn.Module):
         self.backbone = backbone
         self.rpn = rpn
         self.precision = _resolve_precision(precision)     # "bf16" | "fp16" | "fp16_w2" (nerf_rpn_b200/precision.py); explicit, in repr
+        # True: feed RAW densities (dataset built with normalize_density=False) and let the stem packing kernel apply datasets.py:165-167
+        self.density_to_alpha_on_device = bool(density_to_alpha_on_device)
         self._engine = None
         self._engine_key = None
         self._train_engine = None
@@ -109,13 +111,14 @@ class NeRFRegionProposalNetwork(nn.Module):
         from ..engine import RPNInferenceEngine
         r = self.rpn
         precision = _resolve_precision(self.precision)
-        key = (r._pre_nms_top_n["testing"], r._post_nms_top_n["testing"], r.nms_thresh, r.score_thresh, r.rotate, precision)
+        key = (r._pre_nms_top_n["testing"], r._post_nms_top_n["testing"], r.nms_thresh, r.score_thresh, r.rotate, precision,
+               self.density_to_alpha_on_device)
         if self._engine is None or key != self._engine_key:
             ag = r.anchor_generator
             self._engine = RPNInferenceEngine(
                 self.backbone, r.head, ag.cell_anchors_np(), ag.num_anchors_per_location()[0], r.rotate,
                 r._pre_nms_top_n["testing"], r._post_nms_top_n["testing"], r.nms_thresh, r.score_thresh, r.min_size,
-                precision=precision)
+                precision=precision, density_to_alpha=self.density_to_alpha_on_device)
             self._engine_key = key
         return self._engine
 

@@ -290,7 +290,7 @@ def relu_backward_(dy: torch.Tensor, act: torch.Tensor) -> torch.Tensor:
     return dy
 
 
-def pack_stem_input(grid: torch.Tensor, out: Optional[torch.Tensor] = None, dtype=torch.bfloat16) -> torch.Tensor:
+def pack_stem_input(grid: torch.Tensor, out: Optional[torch.Tensor] = None, dtype=torch.bfloat16, density_to_alpha: bool = False) -> torch.Tensor:
     """(N,4,X,Y,Z) fp32 -> (N, ceil(X/2), ceil(Y/2), ceil(Z/2)+1, 64) bf16 (or fp16: dtype of `out`).
     `grid` may be contiguous NCDHW or the channels-last view the reference's dataset yields (memory (N,X,Y,Z,4))."""
     if isinstance(grid, torch.Tensor) and grid.is_cuda and grid.dtype == torch.uint8 and grid.dim() == 5:
@@ -314,7 +314,8 @@ def pack_stem_input(grid: torch.Tensor, out: Optional[torch.Tensor] = None, dtyp
     shape = (n, (x + 1) // 2, (y + 1) // 2, (z + 1) // 2 + 1, 64)
     if out is None:
         out = torch.empty(shape, dtype=dtype, device=grid.device)
-    check(lib().nrpn_pack_stem_input(_ptr(grid), n, x, y, z, _ptr(out), _act16(out, "out"), int(cl), _stream()), "pack_stem_input")
+    check(lib().nrpn_pack_stem_input_ex(_ptr(grid), n, x, y, z, _ptr(out), _act16(out, "out"), int(cl), int(bool(density_to_alpha)), _stream()),
+          "pack_stem_input")
     return out
 
 

@@ -395,3 +395,25 @@ def test_conv_weight_split_cases(ops, name, dims, cin, cout, k, stride, relu, re
         print(f"{name} [{variant}]: norm-wise rel err vs exact-weight fp32 conv {errs[split]:.3e}")
     assert errs[True] < 5e-5, errs          # fp32 accumulation order + the lo plane's fp16-subnormal step only (measured 1.8e-5 at K = 13 824)
     assert errs[False] > 5 * errs[True]     # single fp16 weights: ~1.4e-4 rounding error per weight
+
+
+@pytest.mark.parametrize("layout", ["dataset", "ncdhw"])
+def test_pack_stem_density_to_alpha_fused(ops, layout, tmp_path):
+    """datasets.py:50-52,165-167 (--normalize_density: alpha = clip(1 - exp(-exp(sigma)/100), 0, 1)) applied by the stem
+    packing kernel on a RAW-density grid == packing the grid numpy already converted on the host; the scene comes from an .npz through
+    nerf_rpn_b200.io.read_rgbsigma (pinned, on-disk order)."""
+    from nerf_rpn_b200 import io
+    rng = np.random.default_rng(3)
+    raw = rng.random((10, 12, 9, 4)).astype(np.float32)
+    raw[..., 3] = rng.normal(2.0, 3.0, raw.shape[:3]).astype(np.float32)                 # densities: any real number
+    np.savez(str(tmp_path / "s.npz"), rgbsigma=raw)
+    host = io.read_rgbsigma(str(tmp_path / "s.npz"))
+    assert host.is_pinned() and host.shape == (4, 10, 12, 9) and not host.is_contiguous()
+    ref = raw.copy()
+    ref[..., 3] = np.clip(1.0 - np.exp(-np.exp(ref[..., 3]) / 100.0), 0.0, 1.0)        # BaseDataset.density_to_alpha, verbatim
+    g_raw = host.cuda()[None] if layout == "dataset" else host.cuda().contiguous()[None]
+    g_ref = torch.from_numpy(ref).permute(3, 0, 1, 2).contiguous().cuda()[None]
+    got = ops.pack_stem_input(g_raw, dtype=torch.float16, density_to_alpha=True)
+    want = ops.pack_stem_input(g_ref, dtype=torch.float16)
+    torch.cuda.synchronize()
+    assert (got.float() - want.float()).abs().max().item() <= 2.0 ** -10                  # expf vs numpy's exp: <= 1 fp16 ulp of values in [0, 1]
