@@ -116,7 +116,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
         except OSError:
             return
         self.thread = threading.Thread(target=self._read, daemon=True)
@@ -129,7 +129,6 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -204,7 +203,8 @@ def best_cpu_threads():
     """Intra-op thread count that makes the CPU run fastest on this host: all cores is NOT it on a 128-thread box (measured on the B200 host:
     full scene 4.2 s with 32 threads vs 33 s with 128 -- profiles/r01_cpu_port_threads.txt). Sweeps {all, 64, 32, 16, 8} on a small block."""
     cores = os.cpu_count() or 1
-    cands = sorted({c for c in (cores, 64, 32, 16, 8) if 1 <= c <= cores}, reverse=True)
+    # more than 64 intra-op threads only ever lost on the B200 host (128 threads: 45 s per block vs 0.5 s with 16): not swept
+    cands = sorted({c for c in (min(cores, 64), 32, 16, 8) if 1 <= c <= cores}, reverse=True)
     cpu_run(32, min(cands), y_extent=64)                       # library warm-up (oneDNN JIT, thread pool), not timed
     sweep = {}
     for th in cands:
@@ -283,14 +283,17 @@ def time_dominant_kernel(plan, reps=10):
     return statistics.mean(times), min(times), flops
 
 
-def device_throughput(model, dev_batches, K, W, barrier):
-    """K engine steps over resident input batches; returns (ms, plan, proposals of the last scene)."""
+def device_throughput(model, dev_batches, K, W, barrier, sampler=None):
+    """K engine steps over resident input batches; returns (ms, plan, proposals of the last scene).  `sampler`: clock sampler started
+    right before the timed region (after the warm-up), so that its median is the clock UNDER LOAD."""
     import torch
     eng = model.engine()
     with torch.no_grad():
         for i in range(max(W, 4)):                            # >= 4: both buffer parities warmed and captured
             plan = eng.forward_device(dev_batches[i % len(dev_batches)])
         barrier()
+        if sampler is not None:
+            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(K):
@@ -404,9 +407,7 @@ def run_b200(args):
 
     # ---- device-resident throughput (headline)
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms, plan, count = device_throughput(model, dev, K, W, barrier)
+    ms, plan, count = device_throughput(model, dev, K, W, barrier, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the streaming pipeline (pinned host grids in, proposals out on the host)

@@ -266,6 +266,26 @@ __device__ __forceinline__ bool obb_surely_zero(const float* __restrict__ ta, co
     return ta[2] > tb[3] || tb[2] > ta[3];
 }
 
+// NMS-only shortcut: true only when IoU(a, b) <= thr is CERTAIN, so that the suppression test `!(iou <= thr)` is false without
+// evaluating the polygon clip.  On top of the exact-zero tests:  IoU = I / U with I <= min(V_a, V_b), U >= max(V_a, V_b) and
+// I = A_int * z_overlap <= A_i * z_overlap, hence
+//     IoU <= min(V) / max(V)          (boxes of very different volume cannot suppress each other)
+//     IoU <= z_overlap / max(depth)   (a thin slab of z overlap cannot either).
+// thr_m = thr - 1e-3: the margin dwarfs every rounding error of the reference's fp32 chain (its value never exceeds the exact IoU by
+// more than ~1e-5: mis-sorted or missing vertices only ever SHRINK the polygon), so the skipped decisions are the reference's.
+__device__ __forceinline__ bool obb_surely_not_above(const float* __restrict__ ta, const float* __restrict__ tb, float thr_m) {
+    if (!(__float_as_int(ta[7]) && __float_as_int(tb[7]))) return false;
+    const float dx = ta[4] - tb[4], dy = ta[5] - tb[5], rr = ta[6] + tb[6];
+    if (dx * dx + dy * dy > rr * rr) return true;
+    const float oz = fminf(ta[3], tb[3]) - fmaxf(ta[2], tb[2]);
+    if (!(oz >= 0.0f)) return true;                                           // disjoint z ranges (ta[2] > tb[3] || tb[2] > ta[3])
+    if (thr_m > 0.0f) {
+        if (fminf(ta[1], tb[1]) <= thr_m * fmaxf(ta[1], tb[1])) return true;
+        if (oz <= thr_m * fmaxf(ta[3] - ta[2], tb[3] - tb[2])) return true;
+    }
+    return false;
+}
+
 // cal_iou_3d for one pair without the shortcut (oriented_iou_loss.py:82-107). a = "box1" (the picked box in NMS).
 __device__ __forceinline__ float iou3d_obb_full(const ObbPrep& a, const ObbPrep& b) {
     float zo = __fsub_rn(fminf(a.zmax, b.zmax), fmaxf(a.zmin, b.zmin));

@@ -176,6 +176,27 @@ static inline bool nms_use_matrix(int n, int max_group) { return n <= kNmsMatrix
 static inline int nms_chunk_size(int n) { return n <= 65536 ? 1024 : kChunk; }
 constexpr int kPrepFloats = 16;
 
+// ---- binned chunked path ------------------------------------------------------------------------------------------------------
+// With n in the hundreds of thousands the chunk-against-kept-list scan is O(n * kept): 1 M boxes spent 3.7 s in it.  Whether box j
+// can be suppressed by kept box k is decided by two necessary conditions that can be INDEXED: (a) their volumes are within a factor
+// 1 / thr_m of each other (IoU <= min V / max V), (b) their bounding circles and z ranges intersect.  Kept boxes are therefore filed in
+// a uniform grid per volume class -- class width log2(1 / thr_m), so partners sit in the same or an adjacent class; cell size >= the
+// class's largest diameter / depth -- and a box only visits the cells its circle and z range can reach in its three classes.
+// Every candidate still goes through the same cull + exact polygon clip: the keep set is the sequential greedy loop's, bit for bit.
+constexpr int kBinMinBoxes = 65536;
+constexpr int kBinClasses = 16;
+constexpr int kBinMaxXY = 32, kBinMaxZ = 16;
+constexpr int kBinCellsPerClass = kBinMaxXY * kBinMaxXY * kBinMaxZ;
+constexpr int kBinCells = kBinClasses * kBinCellsPerClass + 1;      // + one cell for boxes the culls cannot reason about (visited by everyone)
+constexpr int kBinStatWords = 8 + 2 * kBinClasses;
+
+struct BinGrid {
+    float x0, y0, z0, lv0, inv_lw;       // origin of the box centres, log2-volume origin, 1 / class width
+    int n_cls;
+    float S[kBinClasses], Sz[kBinClasses], rmax[kBinClasses], dmax[kBinClasses];
+    int nx[kBinClasses], ny[kBinClasses], nz[kBinClasses];
+};
+
 struct NmsWs {
     unsigned long long* keys;     // n_pad
     unsigned long long* keys2;    // n_pad
@@ -187,6 +208,13 @@ struct NmsWs {
     unsigned long long* removed0; // 64 words: suppression by earlier chunks (chunked path)
     int* kept_pos;                // n (chunked path)
     int* state;                   // [0] kept count, [1..256] first kept index per group
+    // binned chunked path (n >= kBinMinBoxes): kept boxes filed by (volume class, x, y, z) cell
+    struct BinGrid* grid;         // grid parameters (device)
+    unsigned* bstats;             // reduction scratch of the grid (ordered-uint min / max)
+    int* box_cell;                // n: cell of every box
+    int* cell_start;              // kBinCells + 1: exclusive scan of the per-cell box counts (capacity of the cell's segment)
+    int* cell_fill;               // kBinCells: kept boxes filed so far
+    int* cell_items;              // n: sorted positions of the kept boxes, cell by cell
     size_t total;
 };
 
@@ -207,7 +235,14 @@ static NmsWs nms_layout(void* base, int n) {
     w.mask = (unsigned long long*)(b + take(chunked ? (size_t)kChunk * 64 * 8 : (size_t)n * W * 8));
     w.removed0 = (unsigned long long*)(b + take(64 * 8));
     w.kept_pos = (int*)(b + take((size_t)n * 4));
-    w.state = (int*)(b + take(257 * 4));
+    w.state = (int*)(b + take(258 * 4));          // [0] kept count, [1..256] per-group starts, [257] kept boxes already filed in the grid
+    const bool binned = n >= kBinMinBoxes;
+    w.grid = (BinGrid*)(b + take(sizeof(BinGrid)));
+    w.bstats = (unsigned*)(b + take(kBinStatWords * 4));
+    w.box_cell = (int*)(b + take(binned ? (size_t)n * 4 : 4));
+    w.cell_start = (int*)(b + take(binned ? (size_t)(kBinCells + 1) * 4 : 4));
+    w.cell_fill = (int*)(b + take(binned ? (size_t)kBinCells * 4 : 4));
+    w.cell_items = (int*)(b + take(binned ? (size_t)n * 4 : 4));
     w.total = off;
     return w;
 }
@@ -244,8 +279,18 @@ __global__ void nms_prep_kernel(const unsigned long long* __restrict__ keys, con
         o[8] = pp.area; o[9] = pp.vol; o[10] = pp.zmin; o[11] = pp.zmax; o[12] = pp.cx; o[13] = pp.cy; o[14] = pp.rad;
         o[15] = __int_as_float(pp.cullable);
     } else {
+        float b[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) o[i] = boxes[(size_t)idx * 6 + i];
+        for (int i = 0; i < 6; ++i) { b[i] = boxes[(size_t)idx * 6 + i]; o[i] = b[i]; }
+        // cull record of an axis-aligned box (binned path only): volume, z range, bounding circle of the footprint
+        const float w = b[3] - b[0], h = b[4] - b[1], d = b[5] - b[2];
+        bool fin = true;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) fin = fin && isfinite(b[i]);
+        o[6] = 0.f; o[7] = 0.f;
+        o[8] = w * h; o[9] = w * h * d; o[10] = b[2]; o[11] = b[5]; o[12] = 0.5f * (b[0] + b[3]); o[13] = 0.5f * (b[1] + b[4]);
+        o[14] = 0.5f * sqrtf(w * w + h * h) * 1.001f + 1e-3f;
+        o[15] = __int_as_float((fin && w > 0.f && h > 0.f && d > 0.f) ? 1 : 0);
     }
 }
 
@@ -314,12 +359,13 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float* __r
     }
     // ---- phase 1: candidate bits of this thread's 16 columns
     const bool cull_ok = (0.0f <= thr);
+    const float thr_m = thr - 1e-3f;                          // margin of the certain-below-threshold tests (box_iou.cuh)
     unsigned cand = 0u;
     if (row_live) {
         for (int k = 0; k < 16; ++k) {
             const int c = quarter * 16 + k, col = col0 + c;
             if (col <= row || sg[c] != g) continue;
-            if (cull_ok && obb_surely_zero(&sr[rl][8], &sp[c][8])) continue;
+            if (cull_ok && obb_surely_not_above(&sr[rl][8], &sp[c][8], thr_m)) continue;
             cand |= 1u << k;
         }
     }
@@ -444,6 +490,7 @@ __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict_
     if (lane == 0 && !done) atomicMin(&min_start, start);
     __syncthreads();
     const bool cull_ok = (0.0f <= thr);
+    const float thr_m = thr - 1e-3f;                          // margin of the certain-below-threshold tests (box_iou.cuh)
     const float* bp = prep + (size_t)p * kPrepFloats;
     if (box_dim != 7) {
         // axis-aligned boxes: the IoU itself is a dozen instructions, no staging needed
@@ -489,7 +536,7 @@ __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict_
             for (int s0 = 0; s0 < kCrossTile; s0 += 32) {
                 const int kk = k0 + s0 + lane;
                 if (k0 + s0 >= kc) break;
-                const bool c = kk < kc && kk >= start && !(cull_ok && obb_surely_zero(tile[s0 + lane], btail));
+                const bool c = kk < kc && kk >= start && !(cull_ok && obb_surely_not_above(tile[s0 + lane], btail, thr_m));
                 const unsigned m = __ballot_sync(0xffffffffu, c);
                 if (m) {
                     if (c) queue[wid][qn + __popc(m & ((1u << lane) - 1u))] = tile_pos[s0 + lane];
@@ -582,6 +629,235 @@ __global__ void __launch_bounds__(256) nms_chunk_resolve_kernel(const unsigned l
     if (tid == 0) state[0] = kept_base;
 }
 
+
+// ------------------------------------------------------------------------------ binned chunked path (n >= kBinMinBoxes)
+__device__ __forceinline__ float ordered_to_float(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+// pass 0 (pass == 0): min / max of centre x, y, z and of log2(volume) over the cullable boxes.  pass 1: per-class max radius / depth.
+__global__ void nms_bin_stats_kernel(const float* __restrict__ prep, int n, int pass, const BinGrid* __restrict__ grid, unsigned* __restrict__ st) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float* t = prep + (size_t)p * kPrepFloats + 8;
+    if (!__float_as_int(t[7])) return;
+    const float zc = 0.5f * (t[2] + t[3]), lv = log2f(t[1]);
+    if (pass == 0) {
+        atomicMin(&st[0], float_to_ordered(t[4])); atomicMax(&st[1], float_to_ordered(t[4]));
+        atomicMin(&st[2], float_to_ordered(t[5])); atomicMax(&st[3], float_to_ordered(t[5]));
+        atomicMin(&st[4], float_to_ordered(zc)); atomicMax(&st[5], float_to_ordered(zc));
+        atomicMin(&st[6], float_to_ordered(lv)); atomicMax(&st[7], float_to_ordered(lv));
+    } else {
+        int c = (int)floorf((lv - grid->lv0) * grid->inv_lw);
+        c = c < 0 ? 0 : (c >= grid->n_cls ? grid->n_cls - 1 : c);
+        atomicMax(&st[8 + c], float_to_ordered(t[6]));
+        atomicMax(&st[8 + kBinClasses + c], float_to_ordered(t[3] - t[2]));
+    }
+}
+
+__global__ void nms_bin_stats_init_kernel(unsigned* __restrict__ st) {
+    const int t = threadIdx.x;
+    if (t < kBinStatWords) st[t] = (t < 8 && !(t & 1)) ? 0xFFFFFFFFu : 0u;          // mins start at +max, maxes at the lowest key
+}
+
+// stage 0: class mapping from the global extents; stage 1: per-class cell sizes / counts from the per-class maxima
+__global__ void nms_bin_grid_kernel(const unsigned* __restrict__ st, float thr_m, int stage, BinGrid* __restrict__ g) {
+    if (threadIdx.x != 0) return;
+    if (stage == 0) {
+        const bool any = st[0] != 0xFFFFFFFFu;
+        g->x0 = any ? ordered_to_float(st[0]) : 0.f; g->y0 = any ? ordered_to_float(st[2]) : 0.f; g->z0 = any ? ordered_to_float(st[4]) : 0.f;
+        g->lv0 = any ? ordered_to_float(st[6]) : 0.f;
+        const float span = any ? ordered_to_float(st[7]) - g->lv0 : 0.f;
+        float width = (thr_m > 0.f && thr_m < 1.f) ? log2f(1.0f / thr_m) : 1e30f;        // no ratio cull: a single class
+        if (span / width > (float)(kBinClasses - 1)) width = span / (float)(kBinClasses - 1) * 1.0001f;   // wider classes stay conservative
+        g->inv_lw = 1.0f / width;
+        int nc = (int)floorf(span * g->inv_lw) + 1;
+        g->n_cls = nc < 1 ? 1 : (nc > kBinClasses ? kBinClasses : nc);
+        return;
+    }
+    const float ex = ordered_to_float(st[1]) - g->x0, ey = ordered_to_float(st[3]) - g->y0, ez = ordered_to_float(st[5]) - g->z0;
+    for (int c = 0; c < kBinClasses; ++c) {
+        const float r = st[8 + c] ? ordered_to_float(st[8 + c]) : 0.f, d = st[8 + kBinClasses + c] ? ordered_to_float(st[8 + kBinClasses + c]) : 0.f;
+        g->rmax[c] = r; g->dmax[c] = d;
+        // cells a quarter of the class's largest diameter / depth wide: a query window of +-(r_j + r_c) / S cells then hugs the circle of
+        // possible partners (a window of 3 x 3 cells of size 2 r_c would cover 3x the area that can hold one)
+        float S = fmaxf(0.5f * r, fmaxf(ex, ey) / (float)kBinMaxXY * 1.0001f);
+        float Sz = fmaxf(0.25f * d, ez / (float)kBinMaxZ * 1.0001f);
+        if (!(S > 0.f)) S = 1.0f;
+        if (!(Sz > 0.f)) Sz = 1.0f;
+        g->S[c] = S; g->Sz[c] = Sz;
+        int nx = (int)floorf(ex / S) + 1, ny = (int)floorf(ey / S) + 1, nz = (int)floorf(ez / Sz) + 1;
+        g->nx[c] = nx < 1 ? 1 : (nx > kBinMaxXY ? kBinMaxXY : nx);
+        g->ny[c] = ny < 1 ? 1 : (ny > kBinMaxXY ? kBinMaxXY : ny);
+        g->nz[c] = nz < 1 ? 1 : (nz > kBinMaxZ ? kBinMaxZ : nz);
+    }
+}
+
+__device__ __forceinline__ int bin_clampi(int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }
+
+// cell of every box (kBinCells - 1 = the "everywhere" cell of boxes without a usable cull record) + per-cell counts
+__global__ void nms_bin_assign_kernel(const float* __restrict__ prep, int n, const BinGrid* __restrict__ g, int* __restrict__ box_cell,
+                                      int* __restrict__ cell_count) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float* t = prep + (size_t)p * kPrepFloats + 8;
+    int cell = kBinCells - 1;
+    if (__float_as_int(t[7])) {
+        int c = (int)floorf((log2f(t[1]) - g->lv0) * g->inv_lw);
+        c = bin_clampi(c, g->n_cls);
+        const int ix = bin_clampi((int)floorf((t[4] - g->x0) / g->S[c]), g->nx[c]);
+        const int iy = bin_clampi((int)floorf((t[5] - g->y0) / g->S[c]), g->ny[c]);
+        const int iz = bin_clampi((int)floorf((0.5f * (t[2] + t[3]) - g->z0) / g->Sz[c]), g->nz[c]);
+        cell = c * kBinCellsPerClass + (iz * kBinMaxXY + iy) * kBinMaxXY + ix;
+    }
+    box_cell[p] = cell;
+    atomicAdd(&cell_count[cell], 1);
+}
+
+// exclusive scan of cell_count (kBinCells entries) into cell_start (kBinCells + 1), one CTA
+__global__ void __launch_bounds__(1024) nms_bin_scan_kernel(const int* __restrict__ cell_count, int* __restrict__ cell_start) {
+    __shared__ int part[1024];
+    const int t = threadIdx.x;
+    const int per = (kBinCells + 1023) / 1024;
+    const int b = t * per, e = b + per < kBinCells ? b + per : kBinCells;
+    int s = 0;
+    for (int i = b; i < e; ++i) s += cell_count[i];
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { const int v = t >= o ? part[t - o] : 0; __syncthreads(); part[t] += v; __syncthreads(); }
+    int run = part[t] - s;
+    for (int i = b; i < e; ++i) { cell_start[i] = run; run += cell_count[i]; }
+    if (t == 1023) cell_start[kBinCells] = part[1023];
+}
+
+// One warp per box of the chunk.  Lanes take the cells of the (x, y) window of the current class / z slab, each lane walks its own cell's
+// kept entries; entries that survive the group / cull tests are queued and the exact IoU runs on full batches of 32 (cf. nms_cross_kernel).
+__global__ void __launch_bounds__(256) nms_cross_binned_kernel(const float* __restrict__ prep, const int* __restrict__ sgroup, int box_dim,
+                                                               float thr, int ignore_group, int chunk_begin, int chunk_n,
+                                                               const BinGrid* __restrict__ grid, const int* __restrict__ box_cell,
+                                                               const int* __restrict__ cell_start, const int* __restrict__ cell_fill,
+                                                               const int* __restrict__ cell_items, unsigned long long* __restrict__ removed0) {
+    __shared__ int queue[8][64];
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int w = blockIdx.x * 8 + wid;
+    if (w >= chunk_n) return;
+    const int p = chunk_begin + w;
+    const int g = sgroup[p];
+    if (g == ignore_group) { if (lane == 0) atomicOr(&removed0[w >> 6], 1ull << (w & 63)); return; }
+    const float* bp = prep + (size_t)p * kPrepFloats;
+    float btail[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) btail[i] = bp[8 + i];
+    ObbPrep b;
+    float baabb[6];
+    if (box_dim == 7) load_prep(bp, b);
+    else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) baabb[i] = bp[i];
+    }
+    const bool cull_ok = (0.0f <= thr);
+    const float thr_m = thr - 1e-3f;
+    const BinGrid& G = *grid;
+    const bool j_cull = __float_as_int(btail[7]) != 0 && cull_ok;
+    int cj = 0;
+    if (j_cull) cj = bin_clampi((int)floorf((log2f(btail[1]) - G.lv0) * G.inv_lw), G.n_cls);
+    const float zc = 0.5f * (btail[2] + btail[3]), dj = btail[3] - btail[2];
+    int qn = 0;
+    bool sup = false;
+
+    auto exact = [&](int pos) -> bool {                 // the decision of the sequential loop for one kept box
+        const float* ap = prep + (size_t)pos * kPrepFloats;
+        if (box_dim == 7) { ObbPrep a; load_prep(ap, a); return !(iou3d_obb_full(a, b) <= thr); }
+        float aa[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) aa[i] = ap[i];
+        return !(iou3d_aabb(aa, baabb) <= thr);
+    };
+    auto visit = [&](int beg, int end) {                // every lane walks its own entry range; returns through `sup`
+        int e = beg;
+        while (true) {
+            const bool have = e < end;
+            if (!__any_sync(0xffffffffu, have)) break;
+            bool c = false;
+            int pos = 0;
+            if (have) {
+                pos = cell_items[e];
+                if (sgroup[pos] == g) {
+                    const float4* src = reinterpret_cast<const float4*>(prep + (size_t)pos * kPrepFloats + 8);
+                    float at[8];
+                    *reinterpret_cast<float4*>(&at[0]) = __ldg(src); *reinterpret_cast<float4*>(&at[4]) = __ldg(src + 1);
+                    c = !(cull_ok && obb_surely_not_above(at, btail, thr_m));
+                }
+                ++e;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, c);
+            if (m) {
+                if (c) queue[wid][qn + __popc(m & ((1u << lane) - 1u))] = pos;
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) {
+                    const bool hit = exact(queue[wid][lane]);
+                    if (__any_sync(0xffffffffu, hit)) { sup = true; return; }
+                    const int rest = qn - 32;
+                    const int moved = lane < rest ? queue[wid][32 + lane] : 0;
+                    __syncwarp();
+                    if (lane < rest) queue[wid][lane] = moved;
+                    qn = rest;
+                    __syncwarp();
+                }
+            }
+        }
+    };
+
+    // boxes without a cull record sit in the last cell: everyone visits it (lanes stride over its entries)
+    {
+        const int cs = cell_start[kBinCells - 1], cf = cell_fill[kBinCells - 1];
+        // split the range over the lanes in contiguous pieces
+        const int per = (cf + 31) / 32;
+        const int b0 = cs + lane * per, b1 = min(cs + cf, b0 + per);
+        visit(b0, b1 > b0 ? b1 : b0);
+    }
+    if (!sup) {
+        const int c_lo = j_cull ? max(cj - 1, 0) : 0, c_hi = j_cull ? min(cj + 1, G.n_cls - 1) : G.n_cls - 1;
+        for (int c = c_lo; c <= c_hi && !sup; ++c) {
+            int ix0 = 0, ix1 = G.nx[c] - 1, iy0 = 0, iy1 = G.ny[c] - 1, iz0 = 0, iz1 = G.nz[c] - 1;
+            if (j_cull) {
+                const float R = btail[6] + G.rmax[c], Rz = 0.5f * (dj + G.dmax[c]);
+                ix0 = bin_clampi((int)floorf((btail[4] - R - G.x0) / G.S[c]), G.nx[c]); ix1 = bin_clampi((int)floorf((btail[4] + R - G.x0) / G.S[c]), G.nx[c]);
+                iy0 = bin_clampi((int)floorf((btail[5] - R - G.y0) / G.S[c]), G.ny[c]); iy1 = bin_clampi((int)floorf((btail[5] + R - G.y0) / G.S[c]), G.ny[c]);
+                iz0 = bin_clampi((int)floorf((zc - Rz - G.z0) / G.Sz[c]), G.nz[c]); iz1 = bin_clampi((int)floorf((zc + Rz - G.z0) / G.Sz[c]), G.nz[c]);
+            }
+            const int wx = ix1 - ix0 + 1, wy = iy1 - iy0 + 1, nxy = wx * wy;
+            for (int iz = iz0; iz <= iz1 && !sup; ++iz) {
+                for (int k0 = 0; k0 < nxy && !sup; k0 += 32) {
+                    const int k = k0 + lane;
+                    int beg = 0, end = 0;
+                    if (k < nxy) {
+                        const int cell = c * kBinCellsPerClass + (iz * kBinMaxXY + (iy0 + k / wx)) * kBinMaxXY + ix0 + k % wx;
+                        beg = cell_start[cell]; end = beg + cell_fill[cell];
+                    }
+                    visit(beg, end);
+                }
+            }
+        }
+    }
+    if (!sup && qn > 0) {
+        bool hit = false;
+        if (lane < qn) hit = exact(queue[wid][lane]);
+        if (__any_sync(0xffffffffu, hit)) sup = true;
+    }
+    if (sup && lane == 0) atomicOr(&removed0[w >> 6], 1ull << (w & 63));
+}
+
+// files the survivors of a resolved chunk (kept_pos[k0 .. k1)) in their cells
+__global__ void nms_bin_file_kernel(const int* __restrict__ kept_pos, const int* __restrict__ state, int* __restrict__ filed, const int* __restrict__ box_cell,
+                                    const int* __restrict__ cell_start, int* __restrict__ cell_fill, int* __restrict__ cell_items) {
+    const int k0 = filed[0], k1 = state[0];
+    for (int k = k0 + blockIdx.x * blockDim.x + threadIdx.x; k < k1; k += gridDim.x * blockDim.x) {
+        const int pos = kept_pos[k], cell = box_cell[pos];
+        cell_items[cell_start[cell] + atomicAdd(&cell_fill[cell], 1)] = pos;
+    }
+}
+__global__ void nms_bin_filed_kernel(const int* __restrict__ state, int* __restrict__ filed) { filed[0] = state[0]; }
+
 __global__ void nms_state_init_kernel(int* __restrict__ state) {
     const int t = threadIdx.x;
     if (t == 0) state[0] = 0;
@@ -641,9 +917,40 @@ int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t*
         nms_state_init_kernel<<<1, 256, 0, st>>>(w.state);
         NRPN_LAUNCH_CHECK();
         const int chunk = nms_chunk_size(n);
+        static const bool bin_off = [] { const char* e = getenv("NRPN_NMS_BINNED"); return e && e[0] == '0'; }();
+        const bool binned = n >= kBinMinBoxes && !bin_off;
+        int* filed = w.state + 257;
+        if (binned) {
+            // grid of the kept-box index: extents -> classes -> per-class cell sizes -> cell of every box -> segment capacities
+            nms_bin_stats_init_kernel<<<1, 64, 0, st>>>(w.bstats);
+            NRPN_LAUNCH_CHECK();
+            nms_bin_stats_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.prep, n, 0, w.grid, w.bstats);
+            NRPN_LAUNCH_CHECK();
+            nms_bin_grid_kernel<<<1, 32, 0, st>>>(w.bstats, thr - 1e-3f, 0, w.grid);
+            NRPN_LAUNCH_CHECK();
+            nms_bin_stats_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.prep, n, 1, w.grid, w.bstats);
+            NRPN_LAUNCH_CHECK();
+            nms_bin_grid_kernel<<<1, 32, 0, st>>>(w.bstats, thr - 1e-3f, 1, w.grid);
+            NRPN_LAUNCH_CHECK();
+            NRPN_CUDA_TRY(cudaMemsetAsync(w.cell_fill, 0, (size_t)kBinCells * 4, st));
+            nms_bin_assign_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.prep, n, w.grid, w.box_cell, w.cell_fill);
+            NRPN_LAUNCH_CHECK();
+            nms_bin_scan_kernel<<<1, 1024, 0, st>>>(w.cell_fill, w.cell_start);
+            NRPN_LAUNCH_CHECK();
+            NRPN_CUDA_TRY(cudaMemsetAsync(w.cell_fill, 0, (size_t)kBinCells * 4, st));
+            NRPN_CUDA_TRY(cudaMemsetAsync(filed, 0, 4, st));
+        }
         for (int cb = 0; cb < n; cb += chunk) {
             const int cn = n - cb < chunk ? n - cb : chunk;
             const int Wc = ceil_div(cn, 64);
+            if (binned) {
+                nms_bin_file_kernel<<<8, 256, 0, st>>>(w.kept_pos, w.state, filed, w.box_cell, w.cell_start, w.cell_fill, w.cell_items);
+                NRPN_LAUNCH_CHECK();
+                nms_bin_filed_kernel<<<1, 1, 0, st>>>(w.state, filed);
+                NRPN_LAUNCH_CHECK();
+                nms_cross_binned_kernel<<<ceil_div(cn, 8), 256, 0, st>>>(w.prep, w.sgroup, box_dim, thr, ignore_group, cb, cn, w.grid, w.box_cell,
+                                                                         w.cell_start, w.cell_fill, w.cell_items, w.removed0);
+            } else
             nms_cross_kernel<<<ceil_div(cn, 8), 256, 0, st>>>(w.prep, w.sgroup, box_dim, thr, ignore_group, cb, cn,
                                                                      w.kept_pos, w.state, w.removed0);
             NRPN_LAUNCH_CHECK();

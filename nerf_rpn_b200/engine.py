@@ -729,7 +729,10 @@ class _Plan:
         runs on the current stream, the others on branch streams forked from / joined to it -- eagerly, or as parallel branches of the
         captured side-stream graph -- so the chain's critical path is one scene long, not n."""
         fs = self._post[par]
-        if len(fs) == 1 or os.environ.get("NRPN_POST_PARALLEL", "1") == "0":
+        # MEASURED on the B200 (profiles/r02_bench_post_parallel_ab.txt, 4 scenes per step): branches 215.7 scenes/s vs one chain 224.2 / 224.9 --
+        # the chain is off the critical path already (high-priority side stream) and four concurrent chains only take SM slots from the
+        # convolutions; the serial chain is the default, NRPN_POST_PARALLEL=1 selects the branches.
+        if len(fs) == 1 or os.environ.get("NRPN_POST_PARALLEL", "0") != "1":
             for f in fs:
                 f()
             return

@@ -44,6 +44,19 @@ def _down(d):
     return tuple((v - 1) // 2 + 1 for v in d)
 
 
+def bucket_schedule(bwd_lo: Sequence[int], n_params: int, bucket_elems: int):
+    """All-reduce ranges of the flat gradient bucket, in launch order.  bwd_lo[i] = lowest flat offset that is final once backward stage i
+    (construction order: stem, blocks..., FPN, head) has run; stages execute in REVERSE, so gradients become final from the end of the bucket
+    towards its start.  A range [lo, hi) is launched after a stage as soon as at least bucket_elems new elements are final (or the bucket is
+    complete).  Returns [(stage index in execution order, lo, hi)]: disjoint, covering [0, n_params) exactly once."""
+    out, hi = [], n_params
+    for k, lo in enumerate(reversed(list(bwd_lo))):
+        if hi > lo and (hi - lo >= bucket_elems or lo == 0):
+            out.append((k, lo, hi))
+            hi = lo
+    return out
+
+
 class _TConv:
     """One trainable convolution: views of the master weight (+ bias), its 16-bit forward / data-gradient operands and tap table."""
 
@@ -408,6 +421,7 @@ class _TrainPlan:
             cur = nxt
         self._conv_fwd_levels(eng.pred_fwd, eng.pred_shift, [(0, 0, 0)], 256, 128, cur, level_views(self.pred), fdims, relu=False, out_fp32=True)
         self.pred_levels = level_views(self.pred)
+        self.dbg = dict(hs=[level_views(h) for h in hs], dhs=[level_views(h) for h in dhs], dfeats=dfeats, q=q, dq=dq, c_out=c_out)   # tools/debug_train.py
         self.dpred_levels = level_views(self.dpred)
         self.strides = [tuple(dims[k] // d[k] for k in range(3)) for d in fdims]
 
@@ -664,18 +678,18 @@ class _TrainPlan:
         its start (stem): every time >= bucket_elems new elements are final their all-reduce is launched on the comm stream, overlapping
         the dgrad / wgrad of the layers below (run_rpn.py:235-236: DDP's bucketed all-reduce during loss.backward())."""
         eng = self.eng
-        hi = eng.n_params
+        sched = {k: (lo, hi) for k, lo, hi in bucket_schedule(self.bwd_lo, eng.n_params, eng.bucket_elems)}
         self.allreduce_calls = 0
-        for f, lo in zip(reversed(self.bwd), reversed(self.bwd_lo)):
+        for k, f in enumerate(reversed(self.bwd)):
             f()
-            if eng.world > 1 and eng.overlap_allreduce and (hi - lo >= eng.bucket_elems or lo == 0) and hi > lo:
+            if eng.world > 1 and eng.overlap_allreduce and k in sched:
+                lo, hi = sched[k]
                 ev = torch.cuda.Event()
                 ev.record()
                 eng.comm_stream.wait_event(ev)
                 with torch.cuda.stream(eng.comm_stream):
                     torch.distributed.all_reduce(eng.flat_g[lo:hi], group=eng.pg)
                 self.allreduce_calls += 1
-                hi = lo
 
     def run(self, grids, targets, backward=True):
         self.forward_loss(grids, targets)

@@ -74,13 +74,13 @@ ANCHOR_SIZES = ((8,), (16,), (32,), (64,),)
 ASPECT = (((1., 1., 1.), (1., 1., 2.), (1., 2., 2.), (1., 1., 3.), (1., 3., 3.)),) * 4
 
 
-def build_reference_model(rotated=False, seed=0, spread=0.0, **rpn_kw):
+def build_reference_model(rotated=False, seed=0, spread=0.0, layers=(3, 4, 6, 3), **rpn_kw):
     """The reference's ResNet50-FPN + anchor head + wrapper, reference init under torch.manual_seed(seed) (run_rpn.py:171-216).
     spread > 0 multiplies cls_logits.weight so that objectness is not ~0.5 everywhere (SURVEY 8d's score-spread variant)."""
     import torch
     ref = load()
     torch.manual_seed(seed)
-    bb = ref.feature_extractor.ResNet_FPN_256(ref.feature_extractor.Bottleneck, [3, 4, 6, 3], input_dim=4, is_max_pool=True)
+    bb = ref.feature_extractor.ResNet_FPN_256(ref.feature_extractor.Bottleneck, list(layers), input_dim=4, is_max_pool=True)
     ag = ref.anchor.AnchorGenerator3D(ANCHOR_SIZES, ASPECT)
     head = ref.anchor.RPNHead(256, ag.num_anchors_per_location()[0], 4, rotate=rotated)
     if spread:

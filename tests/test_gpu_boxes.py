@@ -119,7 +119,7 @@ def test_nms_chunked_path_large_inputs(ops):
     """BASELINE config 5 sizes (beyond the 32 768-box bit-matrix path): exact against the oracle at 40k-70k boxes,
     size-independent properties at 300k (sorted by score, idempotent, kept set pairwise below the threshold)."""
     rng = np.random.default_rng(17)
-    for n, dim, ext, ngroups in ((40000, 7, 200.0, 1), (50000, 7, 160.0, 4), (70000, 6, 260.0, 1)):
+    for n, dim, ext, ngroups in ((40000, 7, 200.0, 1), (50000, 7, 160.0, 4), (70000, 6, 260.0, 1), (66000, 7, 130.0, 1), (72000, 7, 180.0, 3)):   # >= 65 536: binned kept-box index
         boxes = rand_obb(n, rng, ext, 3, 24) if dim == 7 else rand_aabb(n, rng, ext, 3, 28)
         if dim == 7:
             boxes[:, 2] = rng.random(n) * ext * 0.625
@@ -140,6 +140,36 @@ def test_nms_chunked_path_large_inputs(ops):
     sub = keep[:: max(1, keep.shape[0] // 1500)]
     m = obox.iou_matrix(boxes[sub], boxes[sub]); np.fill_diagonal(m, 0)
     assert np.nanmax(m) <= 0.3                                                        # survivors do not overlap beyond thr
+
+
+def test_nms_binned_index_equals_kept_list_scan(ops, tmp_path):
+    """n >= 65 536 files the kept boxes in a (volume class, x, y, z) grid and visits only the cells a box can interact with; the keep list
+    must equal the plain kept-list scan (NRPN_NMS_BINNED=0, read when the library initialises: run in a second process) at 300 000 boxes."""
+    import subprocess, sys, textwrap
+    rng = np.random.default_rng(23)
+    n = 300000
+    boxes = rand_obb(n, rng, 256.0, 4, 48)
+    boxes[:, 2] = rng.random(n) * 160.0
+    boxes[:40, 3] = 0.0                                       # degenerate boxes have no usable cull record: the "everywhere" cell
+    scores = rng.random(n).astype(np.float32)
+    groups = rng.integers(0, 2, n).astype(np.int32)
+    np.savez(str(tmp_path / "in.npz"), boxes=boxes, scores=scores, groups=groups)
+    keep = run_nms(ops, boxes, scores, groups, 0.3)
+    code = textwrap.dedent(f"""
+        import sys, numpy as np, torch
+        sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+        from nerf_rpn_b200 import ops
+        from nerf_rpn_b200._lib import lib
+        lib().nrpn_set_iou_mode(0)
+        d = np.load({str(tmp_path / 'in.npz')!r})
+        k, nk = ops.nms_device(torch.from_numpy(d['boxes']).cuda(), torch.from_numpy(d['scores']).cuda(), torch.from_numpy(d['groups']).cuda(), 0.3)
+        np.save({str(tmp_path / 'ref.npy')!r}, k[: int(nk.item())].cpu().numpy())
+    """)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env={**os.environ, "NRPN_NMS_BINNED": "0"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = np.load(str(tmp_path / "ref.npy"))
+    assert 1000 < ref.shape[0] < n
+    np.testing.assert_array_equal(keep, ref)
 
 
 def _rpn_inputs_from_golden(r, rot):
