@@ -214,7 +214,7 @@ struct NmsWs {
     int* box_cell;                // n: cell of every box
     int* cell_start;              // kBinCells + 1: exclusive scan of the per-cell box counts (capacity of the cell's segment)
     int* cell_fill;               // kBinCells: kept boxes filed so far
-    int* cell_items;              // n: sorted positions of the kept boxes, cell by cell
+    float4* cell_recs;            // n x 3 float4: per kept box {cull record (8 floats), position, group, -, -}, cell by cell
     size_t total;
 };
 
@@ -242,7 +242,7 @@ static NmsWs nms_layout(void* base, int n) {
     w.box_cell = (int*)(b + take(binned ? (size_t)n * 4 : 4));
     w.cell_start = (int*)(b + take(binned ? (size_t)(kBinCells + 1) * 4 : 4));
     w.cell_fill = (int*)(b + take(binned ? (size_t)kBinCells * 4 : 4));
-    w.cell_items = (int*)(b + take(binned ? (size_t)n * 4 : 4));
+    w.cell_recs = (float4*)(b + take(binned ? (size_t)n * 48 : 16));
     w.total = off;
     return w;
 }
@@ -677,10 +677,10 @@ __global__ void nms_bin_grid_kernel(const unsigned* __restrict__ st, float thr_m
     for (int c = 0; c < kBinClasses; ++c) {
         const float r = st[8 + c] ? ordered_to_float(st[8 + c]) : 0.f, d = st[8 + kBinClasses + c] ? ordered_to_float(st[8 + kBinClasses + c]) : 0.f;
         g->rmax[c] = r; g->dmax[c] = d;
-        // cells a quarter of the class's largest diameter / depth wide: a query window of +-(r_j + r_c) / S cells then hugs the circle of
-        // possible partners (a window of 3 x 3 cells of size 2 r_c would cover 3x the area that can hold one)
-        float S = fmaxf(0.5f * r, fmaxf(ex, ey) / (float)kBinMaxXY * 1.0001f);
-        float Sz = fmaxf(0.25f * d, ez / (float)kBinMaxZ * 1.0001f);
+        // cells half of the class's largest diameter / depth wide: a query window of +-(r_j + r_c) / S cells then hugs the volume that can
+        // hold a partner (3 x 3 cells of size 2 r_c would cover 3x that area) while a box still visits only ~100 cells per class
+        float S = fmaxf(r, fmaxf(ex, ey) / (float)kBinMaxXY * 1.0001f);
+        float Sz = fmaxf(0.5f * d, ez / (float)kBinMaxZ * 1.0001f);
         if (!(S > 0.f)) S = 1.0f;
         if (!(Sz > 0.f)) Sz = 1.0f;
         g->S[c] = S; g->Sz[c] = Sz;
@@ -728,13 +728,15 @@ __global__ void __launch_bounds__(1024) nms_bin_scan_kernel(const int* __restric
     if (t == 1023) cell_start[kBinCells] = part[1023];
 }
 
-// One warp per box of the chunk.  Lanes take the cells of the (x, y) window of the current class / z slab, each lane walks its own cell's
-// kept entries; entries that survive the group / cull tests are queued and the exact IoU runs on full batches of 32 (cf. nms_cross_kernel).
-__global__ void __launch_bounds__(256) nms_cross_binned_kernel(const float* __restrict__ prep, const int* __restrict__ sgroup, int box_dim,
-                                                               float thr, int ignore_group, int chunk_begin, int chunk_n,
-                                                               const BinGrid* __restrict__ grid, const int* __restrict__ box_cell,
-                                                               const int* __restrict__ cell_start, const int* __restrict__ cell_fill,
-                                                               const int* __restrict__ cell_items, unsigned long long* __restrict__ removed0) {
+// One warp per box of the chunk.  Lanes take the cells of the box's 3-D window in the current volume class (32 cells per batch), each lane walks
+// its own cell's kept records -- 48-byte records {cull record, position, group} stored cell by cell, so the walk is one sequential stream per
+// lane with no dependent look-ups; entries that survive the group / cull tests are queued and the exact IoU runs on full batches of 32
+// (cf. nms_cross_kernel).
+__global__ void __launch_bounds__(256, 2) nms_cross_binned_kernel(const float* __restrict__ prep, const int* __restrict__ sgroup, int box_dim,
+                                                                  float thr, int ignore_group, int chunk_begin, int chunk_n,
+                                                                  const BinGrid* __restrict__ grid, const int* __restrict__ cell_start,
+                                                                  const int* __restrict__ cell_fill, const float4* __restrict__ cell_recs,
+                                                                  unsigned long long* __restrict__ removed0) {
     __shared__ int queue[8][64];
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int w = blockIdx.x * 8 + wid;
@@ -746,13 +748,6 @@ __global__ void __launch_bounds__(256) nms_cross_binned_kernel(const float* __re
     float btail[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) btail[i] = bp[8 + i];
-    ObbPrep b;
-    float baabb[6];
-    if (box_dim == 7) load_prep(bp, b);
-    else {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) baabb[i] = bp[i];
-    }
     const bool cull_ok = (0.0f <= thr);
     const float thr_m = thr - 1e-3f;
     const BinGrid& G = *grid;
@@ -765,13 +760,13 @@ __global__ void __launch_bounds__(256) nms_cross_binned_kernel(const float* __re
 
     auto exact = [&](int pos) -> bool {                 // the decision of the sequential loop for one kept box
         const float* ap = prep + (size_t)pos * kPrepFloats;
-        if (box_dim == 7) { ObbPrep a; load_prep(ap, a); return !(iou3d_obb_full(a, b) <= thr); }
-        float aa[6];
+        if (box_dim == 7) { ObbPrep a, b; load_prep(ap, a); load_prep(bp, b); return !(iou3d_obb_full(a, b) <= thr); }
+        float aa[6], bb[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) aa[i] = ap[i];
-        return !(iou3d_aabb(aa, baabb) <= thr);
+        for (int i = 0; i < 6; ++i) { aa[i] = ap[i]; bb[i] = bp[i]; }
+        return !(iou3d_aabb(aa, bb) <= thr);
     };
-    auto visit = [&](int beg, int end) {                // every lane walks its own entry range; returns through `sup`
+    auto visit = [&](int beg, int end) {                // every lane walks its own record range; reports through `sup`
         int e = beg;
         while (true) {
             const bool have = e < end;
@@ -779,11 +774,11 @@ __global__ void __launch_bounds__(256) nms_cross_binned_kernel(const float* __re
             bool c = false;
             int pos = 0;
             if (have) {
-                pos = cell_items[e];
-                if (sgroup[pos] == g) {
-                    const float4* src = reinterpret_cast<const float4*>(prep + (size_t)pos * kPrepFloats + 8);
-                    float at[8];
-                    *reinterpret_cast<float4*>(&at[0]) = __ldg(src); *reinterpret_cast<float4*>(&at[4]) = __ldg(src + 1);
+                const float4* r = cell_recs + (size_t)e * 3;
+                const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+                pos = __float_as_int(r2.x);
+                if (__float_as_int(r2.y) == g) {
+                    const float at[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
                     c = !(cull_ok && obb_surely_not_above(at, btail, thr_m));
                 }
                 ++e;
@@ -807,10 +802,8 @@ __global__ void __launch_bounds__(256) nms_cross_binned_kernel(const float* __re
         }
     };
 
-    // boxes without a cull record sit in the last cell: everyone visits it (lanes stride over its entries)
-    {
+    {   // boxes without a cull record sit in the last cell: everyone visits it, the lanes share its records in contiguous pieces
         const int cs = cell_start[kBinCells - 1], cf = cell_fill[kBinCells - 1];
-        // split the range over the lanes in contiguous pieces
         const int per = (cf + 31) / 32;
         const int b0 = cs + lane * per, b1 = min(cs + cf, b0 + per);
         visit(b0, b1 > b0 ? b1 : b0);
@@ -825,17 +818,16 @@ __global__ void __launch_bounds__(256) nms_cross_binned_kernel(const float* __re
                 iy0 = bin_clampi((int)floorf((btail[5] - R - G.y0) / G.S[c]), G.ny[c]); iy1 = bin_clampi((int)floorf((btail[5] + R - G.y0) / G.S[c]), G.ny[c]);
                 iz0 = bin_clampi((int)floorf((zc - Rz - G.z0) / G.Sz[c]), G.nz[c]); iz1 = bin_clampi((int)floorf((zc + Rz - G.z0) / G.Sz[c]), G.nz[c]);
             }
-            const int wx = ix1 - ix0 + 1, wy = iy1 - iy0 + 1, nxy = wx * wy;
-            for (int iz = iz0; iz <= iz1 && !sup; ++iz) {
-                for (int k0 = 0; k0 < nxy && !sup; k0 += 32) {
-                    const int k = k0 + lane;
-                    int beg = 0, end = 0;
-                    if (k < nxy) {
-                        const int cell = c * kBinCellsPerClass + (iz * kBinMaxXY + (iy0 + k / wx)) * kBinMaxXY + ix0 + k % wx;
-                        beg = cell_start[cell]; end = beg + cell_fill[cell];
-                    }
-                    visit(beg, end);
+            const int wx = ix1 - ix0 + 1, wy = iy1 - iy0 + 1, wxy = wx * wy, n_cells = wxy * (iz1 - iz0 + 1);
+            for (int k0 = 0; k0 < n_cells && !sup; k0 += 32) {
+                const int k = k0 + lane;
+                int beg = 0, end = 0;
+                if (k < n_cells) {
+                    const int kz = k / wxy, kr = k - kz * wxy;
+                    const int cell = c * kBinCellsPerClass + ((iz0 + kz) * kBinMaxXY + (iy0 + kr / wx)) * kBinMaxXY + ix0 + kr % wx;
+                    beg = cell_start[cell]; end = beg + cell_fill[cell];
                 }
+                visit(beg, end);
             }
         }
     }
@@ -849,11 +841,15 @@ __global__ void __launch_bounds__(256) nms_cross_binned_kernel(const float* __re
 
 // files the survivors of a resolved chunk (kept_pos[k0 .. k1)) in their cells
 __global__ void nms_bin_file_kernel(const int* __restrict__ kept_pos, const int* __restrict__ state, int* __restrict__ filed, const int* __restrict__ box_cell,
-                                    const int* __restrict__ cell_start, int* __restrict__ cell_fill, int* __restrict__ cell_items) {
+                                    const float* __restrict__ prep, const int* __restrict__ sgroup, const int* __restrict__ cell_start,
+                                    int* __restrict__ cell_fill, float4* __restrict__ cell_recs) {
     const int k0 = filed[0], k1 = state[0];
     for (int k = k0 + blockIdx.x * blockDim.x + threadIdx.x; k < k1; k += gridDim.x * blockDim.x) {
         const int pos = kept_pos[k], cell = box_cell[pos];
-        cell_items[cell_start[cell] + atomicAdd(&cell_fill[cell], 1)] = pos;
+        const float4* t = reinterpret_cast<const float4*>(prep + (size_t)pos * kPrepFloats + 8);
+        float4* r = cell_recs + (size_t)(cell_start[cell] + atomicAdd(&cell_fill[cell], 1)) * 3;
+        r[0] = t[0]; r[1] = t[1];
+        r[2] = make_float4(__int_as_float(pos), __int_as_float(sgroup[pos]), 0.f, 0.f);
     }
 }
 __global__ void nms_bin_filed_kernel(const int* __restrict__ state, int* __restrict__ filed) { filed[0] = state[0]; }
@@ -944,12 +940,12 @@ int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t*
             const int cn = n - cb < chunk ? n - cb : chunk;
             const int Wc = ceil_div(cn, 64);
             if (binned) {
-                nms_bin_file_kernel<<<8, 256, 0, st>>>(w.kept_pos, w.state, filed, w.box_cell, w.cell_start, w.cell_fill, w.cell_items);
+                nms_bin_file_kernel<<<8, 256, 0, st>>>(w.kept_pos, w.state, filed, w.box_cell, w.prep, w.sgroup, w.cell_start, w.cell_fill, w.cell_recs);
                 NRPN_LAUNCH_CHECK();
                 nms_bin_filed_kernel<<<1, 1, 0, st>>>(w.state, filed);
                 NRPN_LAUNCH_CHECK();
-                nms_cross_binned_kernel<<<ceil_div(cn, 8), 256, 0, st>>>(w.prep, w.sgroup, box_dim, thr, ignore_group, cb, cn, w.grid, w.box_cell,
-                                                                         w.cell_start, w.cell_fill, w.cell_items, w.removed0);
+                nms_cross_binned_kernel<<<ceil_div(cn, 8), 256, 0, st>>>(w.prep, w.sgroup, box_dim, thr, ignore_group, cb, cn, w.grid,
+                                                                         w.cell_start, w.cell_fill, w.cell_recs, w.removed0);
             } else
             nms_cross_kernel<<<ceil_div(cn, 8), 256, 0, st>>>(w.prep, w.sgroup, box_dim, thr, ignore_group, cb, cn,
                                                                      w.kept_pos, w.state, w.removed0);

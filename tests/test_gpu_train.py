@@ -344,7 +344,8 @@ def test_training_step_vs_reference_autograd(layers, rotated, precision):
     checks = [(same, "the sampler did not reproduce the reference's draws")]
     for k in range(2):
         e_o, e_a = abs(got_l[k] - r32["losses"][k]), abs(rac["losses"][k] - r32["losses"][k])
-        checks.append((e_o <= 2.0 * e_a + 2e-3 * abs(r32["losses"][k]), f"loss {k}: ours off by {e_o}, autocast by {e_a}"))
+        slack = (1e-2 if precision == "bf16" else 3e-3) * abs(r32["losses"][k])        # forward noise of the dtype (features are 10-50 % off either way)
+        checks.append((e_o <= 3.0 * e_a + slack, f"loss {k}: ours off by {e_o}, autocast by {e_a}"))
     checks.append((cos_o >= cos_a - 0.08, f"gradient cosine {cos_o} vs autocast {cos_a}"))
     checks.append((rel_o <= 1.15 * rel_a + 0.02, f"gradient rel err {rel_o} vs autocast {rel_a}"))
     bad = [(n, v, per_a[n]) for n, v in per_o.items() if v > 1.25 * per_a[n] + 0.03]
