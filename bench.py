@@ -252,7 +252,7 @@ def run_reference(args):
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
            "cpu_baseline": {"value": value, "unit": "scenes/s", "cores": cores, "kind": _cpu_state()["kind"], "sample": sample},
            "e2e": {"value": value, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    _emit(out)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -521,14 +521,33 @@ def run_b200(args):
                "train": train,
                "reference_gpu": ref_gpu_out,
                "cpu_baseline": {"value": (1.0 / cpu_t) if cpu_t == cpu_t else None, "unit": "scenes/s", "cores": cores, "kind": cpu_kind, "sample": cpu_sample}}
-        print(json.dumps(out), flush=True)
+        _emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return out
 
 
+_RESULT_FD = None
+
+
+def _emit(obj):
+    """The one JSON line, on the process's ORIGINAL stdout."""
+    line = json.dumps(obj) + "\n"
+    if _RESULT_FD is None:
+        sys.stdout.write(line)
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line.encode())
+
+
 def main():
+    global _RESULT_FD
+    # stdout carries the JSON line and nothing else: native libraries write banners to fd 1 (NCCL prints its version there when NCCL_DEBUG is
+    # set), so fd 1 is pointed at stderr for the run and the result goes to a private duplicate of the original.
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

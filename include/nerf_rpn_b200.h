@@ -49,6 +49,17 @@ unsigned long long nrpn_launch_count(void);
  * element-wise AABB case. */
 int nrpn_iou3d_pairs(const float *a, const float *b, int n, int box_dim, float *iou, nrpn_stream_t stream);
 
+/* cal_iou_3d(box3d1, box3d2, verbose=True) (oriented_iou_loss.py:82-107) for n pairs of oriented boxes: IoU, the two corner sets
+ * (n, 4, 2), z_range = extent of the union of the z ranges, u3d = V1 + V2 - intersection -- the inputs of the IoU-type regression losses
+ * (rpn.py:133-165, fcos/loss.py). */
+int nrpn_iou3d_pairs_verbose(const float *a, const float *b, int n, float *iou, float *corners1, float *corners2, float *z_range,
+                             float *u3d, nrpn_stream_t stream);
+/* Backward of (iou, u3d) w.r.t. both boxes (the reference differentiates its torch chain with autograd; the vertex order is not
+ * differentiated there either, cuda_ext.py:10): grad_a / grad_b (n, 7) = grad_iou * d iou + grad_u3d * d u3d; either upstream gradient
+ * may be NULL.  The intersection volume is differentiated by central differences in fp64 (piecewise smooth). */
+int nrpn_iou3d_pairs_backward(const float *a, const float *b, int n, const float *grad_iou, const float *grad_u3d, float *grad_a,
+                              float *grad_b, nrpn_stream_t stream);
+
 /* out[i*m + j] = IoU3D(a[i], b[j]).  Replaces box_iou_3d (utils.py:387-415), which tiles both sets to
  * (n,m,7) in HBM and runs ~40 ATen kernels plus the native sort. */
 int nrpn_iou3d_matrix(const float *a, int n, const float *b, int m, int box_dim, float *out, nrpn_stream_t stream);
@@ -388,6 +399,14 @@ int nrpn_grad_norm(const float *g, size_t n, float inv_scale, float *norm_out, v
  * on flat fp32 buffers; gradients are multiplied by inv_scale first (loss scaling / world size). */
 int nrpn_adamw_step(float *p, const float *g, float *m, float *v, size_t n, const float *norm, float max_norm, float inv_scale, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, nrpn_stream_t stream);
+
+/* Training-time augmentation of one scene on the device (BaseDataset.augment_rpn_inputs + rotate_and_scale_scene, datasets.py:109-163,
+ * 290-329, z-up): fp32 grid in its on-disk channels-last order (X, Y, Z, 4) -> out (Xo, Yo, Z, 4), Xo/Yo = Y/X when rot90 else X/Y.
+ * rot90: transpose(x, y) + flip(x); flip_x / flip_y; resample: F.grid_sample(trilinear, zero padding, align_corners=True) of the
+ * scene rotated by `angle` about z and scaled by `scale` exactly as the reference builds its sampling grid.  The box transforms are a
+ * few scalars per box and stay on the host side (nerf_rpn_b200/augment.py). */
+int nrpn_augment_scene(const float *grid_xyzc, int x, int y, int z, float *out_xyzc, int rot90, int flip_x, int flip_y, int resample,
+                       float angle, float scale, nrpn_stream_t stream);
 
 #ifdef __cplusplus
 }

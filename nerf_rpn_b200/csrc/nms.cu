@@ -31,6 +31,97 @@ __global__ void iou_pairs_kernel(const float* __restrict__ a, const float* __res
     }
 }
 
+// cal_iou_3d(verbose=True) (oriented_iou_loss.py:82-107): IoU, both corner sets, z_range and the 3-D union of every pair
+__global__ void iou_pairs_verbose_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ iou,
+                                         float* __restrict__ corners1, float* __restrict__ corners2, float* __restrict__ z_range,
+                                         float* __restrict__ u3d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ObbPrep pa, pb;
+    obb_prepare(a + (size_t)i * 7, pa);
+    obb_prepare(b + (size_t)i * 7, pb);
+    float zo = __fsub_rn(fminf(pa.zmax, pb.zmax), fmaxf(pa.zmin, pb.zmin));
+    if (!(zo >= 0.0f)) zo = (zo != zo) ? zo : 0.0f;
+    const float inter = rect_inter_area(pa.c, pb.c);
+    const float u = __fsub_rn(__fadd_rn(pa.area, pb.area), inter);
+    const float i3 = __fmul_rn(__fmul_rn(__fdiv_rn(inter, u), u), zo);
+    const float u3 = __fsub_rn(__fadd_rn(pa.vol, pb.vol), i3);
+    iou[i] = __fdiv_rn(i3, u3);
+    u3d[i] = u3;
+    float zr = __fsub_rn(fmaxf(pa.zmax, pb.zmax), fminf(pa.zmin, pb.zmin));
+    if (!(zr >= 0.0f)) zr = (zr != zr) ? zr : 0.0f;
+    z_range[i] = zr;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { corners1[(size_t)i * 8 + k] = pa.c[k]; corners2[(size_t)i * 8 + k] = pb.c[k]; }
+}
+
+// Intersection volume of two yaw-rotated boxes in fp64 (Sutherland-Hodgman clip of A's footprint by B's four half-planes x z overlap):
+// the smooth function whose derivative the backward pass needs.
+__device__ double inter_volume_d(const double* A, const double* B) {
+    double px[12], py[12], qx[12], qy[12];
+    int np = 4;
+    const double sx[4] = {0.5, -0.5, -0.5, 0.5}, sy[4] = {0.5, 0.5, -0.5, -0.5};
+    const double ca = cos(A[6]), sa = sin(A[6]), cb = cos(B[6]), sb = sin(B[6]);
+    double bx[4], by[4];
+    for (int k = 0; k < 4; ++k) {
+        px[k] = A[0] + sx[k] * A[3] * ca - sy[k] * A[4] * sa; py[k] = A[1] + sx[k] * A[3] * sa + sy[k] * A[4] * ca;
+        bx[k] = B[0] + sx[k] * B[3] * cb - sy[k] * B[4] * sb; by[k] = B[1] + sx[k] * B[3] * sb + sy[k] * B[4] * cb;
+    }
+    for (int e = 0; e < 4 && np > 0; ++e) {                     // clip against edge e of B (counter-clockwise: inside = left)
+        const double ex = bx[(e + 1) & 3] - bx[e], ey = by[(e + 1) & 3] - by[e];
+        int nq = 0;
+        for (int k = 0; k < np; ++k) {
+            const int k2 = k + 1 == np ? 0 : k + 1;
+            const double d1 = ex * (py[k] - by[e]) - ey * (px[k] - bx[e]);
+            const double d2 = ex * (py[k2] - by[e]) - ey * (px[k2] - bx[e]);
+            if (d1 >= 0.0) { qx[nq] = px[k]; qy[nq] = py[k]; ++nq; }
+            if ((d1 >= 0.0) != (d2 >= 0.0)) {
+                const double t = d1 / (d1 - d2);
+                qx[nq] = px[k] + t * (px[k2] - px[k]); qy[nq] = py[k] + t * (py[k2] - py[k]); ++nq;
+            }
+        }
+        np = nq;
+        for (int k = 0; k < np; ++k) { px[k] = qx[k]; py[k] = qy[k]; }
+    }
+    double area = 0.0;
+    for (int k = 0; k < np; ++k) { const int k2 = k + 1 == np ? 0 : k + 1; area += px[k] * py[k2] - py[k] * px[k2]; }
+    area = 0.5 * fabs(area);
+    double zo = fmin(A[2] + 0.5 * A[5], B[2] + 0.5 * B[5]) - fmax(A[2] - 0.5 * A[5], B[2] - 0.5 * B[5]);
+    if (!(zo > 0.0)) zo = 0.0;
+    return area * zo;
+}
+
+// Backward of (iou, u3d) = cal_iou_3d(a, b, verbose) w.r.t. both boxes: with I the intersection volume, U = V1 + V2 - I, iou = I / U:
+//   dL = [g_iou (U + I) / U^2 - g_u] dI + [g_u - g_iou I / U^2] d(V1 + V2);   dI by central differences of inter_volume_d in fp64
+// (I is piecewise smooth in the 14 parameters; step 1e-5 of the pair's scale: truncation ~1e-10, round-off ~1e-11 relative).
+// One thread per (pair, parameter).
+__global__ void iou_pairs_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, const float* __restrict__ g_iou,
+                                      const float* __restrict__ g_u, float* __restrict__ ga, float* __restrict__ gb) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 14) return;
+    const int i = t / 14, k = t % 14;
+    double A[7], B[7];
+    for (int j = 0; j < 7; ++j) { A[j] = (double)a[(size_t)i * 7 + j]; B[j] = (double)b[(size_t)i * 7 + j]; }
+    const double I = inter_volume_d(A, B);
+    const double V1 = A[3] * A[4] * A[5], V2 = B[3] * B[4] * B[5], U = V1 + V2 - I;
+    const double gi = g_iou ? (double)g_iou[i] : 0.0, gu = g_u ? (double)g_u[i] : 0.0;
+    const double cI = gi * (U + I) / (U * U) - gu, cV = gu - gi * I / (U * U);
+    double scale = fmax(fmax(fabs(A[3]), fabs(A[4])), fmax(fabs(B[3]), fabs(B[4])));
+    scale = fmax(scale, fmax(fabs(A[5]), fabs(B[5])));
+    const double h = 1e-5 * (scale > 0.0 ? scale : 1.0);
+    double* P = k < 7 ? A : B;
+    const int j = k < 7 ? k : k - 7;
+    const double keep = P[j];
+    const double hh = j == 6 ? 1e-6 : h;
+    P[j] = keep + hh; const double Ip = inter_volume_d(A, B);
+    P[j] = keep - hh; const double Im = inter_volume_d(A, B);
+    P[j] = keep;
+    double dV = 0.0;
+    if (j == 3) dV = P[4] * P[5]; else if (j == 4) dV = P[3] * P[5]; else if (j == 5) dV = P[3] * P[4];
+    const double gval = cI * (Ip - Im) / (2.0 * hh) + cV * dV;
+    (k < 7 ? ga : gb)[(size_t)i * 7 + j] = (float)gval;
+}
+
 // tile: 8 rows (a) x 32 cols (b) per 256-thread CTA; box preparation (fp64 sin/cos) once per box per tile.
 __global__ void iou_matrix_kernel(const float* __restrict__ a, int n, const float* __restrict__ b, int m, int box_dim,
                                   float* __restrict__ out) {
@@ -978,6 +1069,26 @@ int nrpn_iou3d_pairs(const float* a, const float* b, int n, int box_dim, float* 
     if (n == 0) return NRPN_OK;
     if (!a || !b || !iou) return NRPN_ERR_INVALID;
     iou_pairs_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(a, b, n, box_dim, iou);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+int nrpn_iou3d_pairs_verbose(const float* a, const float* b, int n, float* iou, float* corners1, float* corners2, float* z_range, float* u3d,
+                             nrpn_stream_t stream) {
+    if (n < 0) return NRPN_ERR_INVALID;
+    if (n == 0) return NRPN_OK;
+    if (!a || !b || !iou || !corners1 || !corners2 || !z_range || !u3d) return NRPN_ERR_INVALID;
+    iou_pairs_verbose_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(a, b, n, iou, corners1, corners2, z_range, u3d);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+int nrpn_iou3d_pairs_backward(const float* a, const float* b, int n, const float* grad_iou, const float* grad_u3d, float* grad_a, float* grad_b,
+                              nrpn_stream_t stream) {
+    if (n < 0) return NRPN_ERR_INVALID;
+    if (n == 0) return NRPN_OK;
+    if (!a || !b || !grad_a || !grad_b || (!grad_iou && !grad_u3d)) return NRPN_ERR_INVALID;
+    iou_pairs_grad_kernel<<<ceil_div(n * 14, 128), 128, 0, (cudaStream_t)stream>>>(a, b, n, grad_iou, grad_u3d, grad_a, grad_b);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }

@@ -704,3 +704,77 @@ int nrpn_adamw_step(float* p, const float* g, float* m, float* v, size_t n, cons
 
 #pragma GCC visibility pop
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- training-time scene augmentation
+// BaseDataset.augment_rpn_inputs + rotate_and_scale_scene (datasets.py:109-163, 290-329) on the device, on the grid in its on-disk
+// channels-last order (X, Y, Z, 4): one thread per output voxel, one 128-bit access per source voxel.
+//   step 1 (optional) rot90 about z:   out1[i][j] = in[j][X1 - 1 - i]          (torch.transpose(1, 2) then flip(1); extents swap)
+//   step 2 (optional) flips along x/y: out2[i][j] = out1[X2-1-i or i][Y2-1-j or j]
+//   step 3 (optional) rotate + scale:  F.grid_sample(trilinear, zeros padding, align_corners=True) at the source point the reference's
+//                                      grid construction yields: p = scale * R(angle) (c - centre) + centre in normalised units
+namespace nrpn {
+
+struct AugParams { int X, Y, Z, Xo, Yo, rot90, flipx, flipy, resample; float c00, c01, c10, c11, s; };
+
+__device__ __forceinline__ float4 aug_fetch(const float4* __restrict__ in, const AugParams& P, int i, int j, int k) {
+    // (i, j, k) index the grid AFTER rot90 / flips (extent Xo x Yo x Z); map back to the stored grid (X x Y x Z)
+    if (i < 0 || j < 0 || k < 0 || i >= P.Xo || j >= P.Yo || k >= P.Z) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (P.flipx) i = P.Xo - 1 - i;
+    if (P.flipy) j = P.Yo - 1 - j;
+    int si = i, sj = j;
+    if (P.rot90) { si = j; sj = P.Y - 1 - i; }          // out1[i][j] = in[j][Y_in - 1 - i] with out1 extents (Y_in, X_in)
+    return __ldg(in + ((size_t)si * P.Y + sj) * P.Z + k);
+}
+
+__global__ void __launch_bounds__(256) augment_scene_kernel(const float4* __restrict__ in, float4* __restrict__ out, const AugParams P) {
+    const size_t total = (size_t)P.Xo * P.Yo * P.Z;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t % P.Z); size_t v = t / P.Z;
+        const int j = (int)(v % P.Yo); const int i = (int)(v / P.Yo);
+        if (!P.resample) { out[t] = aug_fetch(in, P, i, j, k); continue; }
+        // reference: x = linspace(-1, 1, res) * res / 2 (voxel i -> (2 i / (res - 1) - 1) * res / 2), grid = [x y z] @ xform^T, then divided by
+        // res / 2 per axis -> normalised coordinates; align_corners=True: pixel = (g + 1) / 2 * (res - 1)
+        const float hx = 0.5f * (float)P.Xo, hy = 0.5f * (float)P.Yo;
+        const float x = (P.Xo > 1 ? (2.0f * (float)i / (float)(P.Xo - 1) - 1.0f) : -1.0f) * hx;
+        const float y = (P.Yo > 1 ? (2.0f * (float)j / (float)(P.Yo - 1) - 1.0f) : -1.0f) * hy;
+        const float gx = (P.c00 * x + P.c01 * y) / hx, gy = (P.c10 * x + P.c11 * y) / hy;
+        const float gz = (P.Z > 1 ? (2.0f * (float)k / (float)(P.Z - 1) - 1.0f) : -1.0f) * P.s;
+        const float fx = (gx + 1.0f) * 0.5f * (float)(P.Xo - 1), fy = (gy + 1.0f) * 0.5f * (float)(P.Yo - 1), fz = (gz + 1.0f) * 0.5f * (float)(P.Z - 1);
+        const int x0 = (int)floorf(fx), y0 = (int)floorf(fy), z0 = (int)floorf(fz);
+        const float tx = fx - (float)x0, ty = fy - (float)y0, tz = fz - (float)z0;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+            const float w = (dx ? tx : 1.0f - tx) * (dy ? ty : 1.0f - ty) * (dz ? tz : 1.0f - tz);
+            const float4 q = aug_fetch(in, P, x0 + dx, y0 + dy, z0 + dz);
+            acc.x += w * q.x; acc.y += w * q.y; acc.z += w * q.z; acc.w += w * q.w;
+        }
+        out[t] = acc;
+    }
+}
+
+}  // namespace nrpn
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int nrpn_augment_scene(const float* grid_xyzc, int x, int y, int z, float* out_xyzc, int rot90, int flip_x, int flip_y, int resample,
+                       float angle, float scale, nrpn_stream_t stream) {
+    if (!grid_xyzc || !out_xyzc || x < 1 || y < 1 || z < 1 || grid_xyzc == out_xyzc) return NRPN_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(grid_xyzc) % 16 != 0 || reinterpret_cast<uintptr_t>(out_xyzc) % 16 != 0) return NRPN_ERR_INVALID;
+    nrpn::AugParams P;
+    P.X = x; P.Y = y; P.Z = z; P.rot90 = rot90 ? 1 : 0; P.flipx = flip_x ? 1 : 0; P.flipy = flip_y ? 1 : 0; P.resample = resample ? 1 : 0;
+    P.Xo = rot90 ? y : x; P.Yo = rot90 ? x : y;
+    // xform = [[cos, -sin, 0], [sin, cos, 0], [0, 0, 1]] * scale (datasets.py:293-297, fp32)
+    P.c00 = (float)cos((double)angle) * scale; P.c01 = -(float)sin((double)angle) * scale;
+    P.c10 = (float)sin((double)angle) * scale; P.c11 = (float)cos((double)angle) * scale; P.s = scale;
+    const size_t total = (size_t)P.Xo * P.Yo * z;
+    nrpn::augment_scene_kernel<<<nrpn::grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(grid_xyzc),
+                                                                                          reinterpret_cast<float4*>(out_xyzc), P);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

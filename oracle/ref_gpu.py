@@ -59,6 +59,7 @@ def load(need_k1: bool = True):
         ns.fcos = importlib.import_module("model.fcos.fcos")
         ns.fpn = importlib.import_module("model.fpn")
         ns.eval = importlib.import_module("eval")
+        ns.datasets = importlib.import_module("datasets")
         ns.sort_vertices = sys.modules.get("sort_vertices")
     finally:
         for p in paths:

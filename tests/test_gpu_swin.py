@@ -114,7 +114,7 @@ def _attn_ref_wide(xin, sd, heads, shift, C):
     return o[:, :H, :W, :D, :].contiguous()
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "fp16_w2"])
 def test_config3_swin_s_fcos_small(golden_dir, precision):
     """Swin-S + FPN + FCOS head (OBB) on a 40x52x34 grid vs the reference's golden feature maps / logits / boxes."""
     from nerf_rpn_b200.model import feature_extractor
@@ -135,7 +135,7 @@ def test_config3_swin_s_fcos_small(golden_dir, precision):
         ref = torch.from_numpy(g[f"feat{i}"].astype(np.float32)).cuda()
         rel = ((f[0] - ref).norm() / ref.norm()).item()
         print(f"swin config 3 [{precision}]: feature level {i} norm-wise rel err {rel:.3e}")
-        assert rel < (4e-2 if precision == "bf16" else 4e-3)
+        assert rel < {"bf16": 4e-2, "fp16": 4e-3, "fp16_w2": 2.5e-3}[precision]
     eng = model.engine()
     plan = eng._plans[next(iter(eng._plans))]
     grids = plan.feat_dims
