@@ -439,7 +439,7 @@ def run_b200(args):
         achieved = k_flops / (k_mean * 1e-3) / 1e12
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_full_summary.json")) as f:
                 for row in json.load(f):
                     if row.get("capture") == "head":
                         traffic = (row["dram_read_B"] + row["dram_write_B"]) * B
@@ -447,7 +447,7 @@ def run_b200(args):
             traffic = None
         roofline = {"bound": "tensor", "kernel": "conv3d_igemm_kernel<256,4> (RPN head layer, 3x3x3 256->256 + bias + ReLU over P2..P5)",
                     "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": traffic,
-                    "traffic_source": "profiles/r01_ncu_full_summary.json (dram__bytes_read.sum + dram__bytes_write.sum of an ncu --set full capture, 1 scene/launch) x scenes per launch; a profile number, not measured in this run",
+                    "traffic_source": "profiles/r02_ncu_full_summary.json (dram__bytes_read.sum + dram__bytes_write.sum of an ncu --set full capture, 1 scene/launch) x scenes per launch; a profile number, not measured in this run",
                     "peak_source": how + ", burst figure (kernel timed alone, L2 flushed between launches)",
                     "launch_ms": k_mean, "flops_per_launch": k_flops,
                     "whole_step_frac_of_sustained": (FLOPS_PER_SCENE * world * K * B / (ms * 1e-3) / 1e12) / (sustained * world)}

@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Target for `ncu --nvtx --nvtx-include "target/" --metrics gpu__time_duration.sum`: ONE oriented NMS over n boxes of the config-5 distribution
+(tools/nms_sweep.py), after one untimed run.  argv: n [groups]."""
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nerf_rpn_b200 import ops  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+groups = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+g = torch.Generator().manual_seed(0)
+c = torch.rand(n, 3, generator=g) * torch.tensor([256.0, 256.0, 160.0])
+s = torch.rand(n, 3, generator=g) * 44 + 4
+th = (torch.rand(n, 1, generator=g) - 0.5) * math.pi
+boxes = torch.cat([c, s, th], 1).cuda().contiguous()
+scores = torch.rand(n, generator=g).cuda()
+grp = torch.randint(0, groups, (n,), generator=g).int().cuda() if groups > 1 else None
+keep, nk = ops.nms_device(boxes, scores, grp, 0.3)
+torch.cuda.synchronize()
+torch.cuda.nvtx.range_push("target")
+keep, nk = ops.nms_device(boxes, scores, grp, 0.3)
+torch.cuda.synchronize()
+torch.cuda.nvtx.range_pop()
+print("kept", int(nk.item()))
