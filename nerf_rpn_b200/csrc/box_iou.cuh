@@ -270,18 +270,25 @@ __device__ __forceinline__ bool obb_surely_zero(const float* __restrict__ ta, co
 // evaluating the polygon clip.  On top of the exact-zero tests:  IoU = I / U with I <= min(V_a, V_b), U >= max(V_a, V_b) and
 // I = A_int * z_overlap <= A_i * z_overlap, hence
 //     IoU <= min(V) / max(V)          (boxes of very different volume cannot suppress each other)
-//     IoU <= z_overlap / max(depth)   (a thin slab of z overlap cannot either).
+//     IoU <= z_overlap / max(depth)   (a thin slab of z overlap cannot either)
+//     IoU <= min(A_a, A_b, lens) * z_overlap / max(V)   (footprints that only graze each other cannot either).
 // thr_m = thr - 1e-3: the margin dwarfs every rounding error of the reference's fp32 chain (its value never exceeds the exact IoU by
 // more than ~1e-5: mis-sorted or missing vertices only ever SHRINK the polygon), so the skipped decisions are the reference's.
 __device__ __forceinline__ bool obb_surely_not_above(const float* __restrict__ ta, const float* __restrict__ tb, float thr_m) {
     if (!(__float_as_int(ta[7]) && __float_as_int(tb[7]))) return false;
     const float dx = ta[4] - tb[4], dy = ta[5] - tb[5], rr = ta[6] + tb[6];
-    if (dx * dx + dy * dy > rr * rr) return true;
+    const float d2 = dx * dx + dy * dy;
+    if (d2 > rr * rr) return true;
     const float oz = fminf(ta[3], tb[3]) - fmaxf(ta[2], tb[2]);
     if (!(oz >= 0.0f)) return true;                                           // disjoint z ranges (ta[2] > tb[3] || tb[2] > ta[3])
     if (thr_m > 0.0f) {
-        if (fminf(ta[1], tb[1]) <= thr_m * fmaxf(ta[1], tb[1])) return true;
+        const float vmax = fmaxf(ta[1], tb[1]);
+        if (fminf(ta[1], tb[1]) <= thr_m * vmax) return true;
         if (oz <= thr_m * fmaxf(ta[3] - ta[2], tb[3] - tb[2])) return true;
+        // intersection = footprint overlap x z overlap, union >= the larger volume; the footprint overlap is at most the smaller footprint and at
+        // most the bounding rectangle of the lens the two bounding circles share: (r_a + r_b - distance) x 2 min(r)
+        const float lens = 2.0f * fminf(ta[6], tb[6]) * (rr - sqrtf(d2));
+        if (fminf(fminf(ta[0], tb[0]), lens) * oz <= thr_m * vmax) return true;
     }
     return false;
 }

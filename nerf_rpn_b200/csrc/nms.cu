@@ -275,6 +275,7 @@ constexpr int kPrepFloats = 16;
 // class's largest diameter / depth -- and a box only visits the cells its circle and z range can reach in its three classes.
 // Every candidate still goes through the same cull + exact polygon clip: the keep set is the sequential greedy loop's, bit for bit.
 constexpr int kBinMinBoxes = 65536;
+constexpr int kCellMinBoxes = 16384;     // cell-list path (nms_cells.cuh) from here; it shares the grid / box_cell buffers below
 constexpr int kBinClasses = 16;
 constexpr int kBinMaxXY = 32, kBinMaxZ = 16;
 constexpr int kBinCellsPerClass = kBinMaxXY * kBinMaxXY * kBinMaxZ;
@@ -327,7 +328,7 @@ static NmsWs nms_layout(void* base, int n) {
     w.removed0 = (unsigned long long*)(b + take(64 * 8));
     w.kept_pos = (int*)(b + take((size_t)n * 4));
     w.state = (int*)(b + take(258 * 4));          // [0] kept count, [1..256] per-group starts, [257] kept boxes already filed in the grid
-    const bool binned = n >= kBinMinBoxes;
+    const bool binned = n >= kCellMinBoxes;
     w.grid = (BinGrid*)(b + take(sizeof(BinGrid)));
     w.bstats = (unsigned*)(b + take(kBinStatWords * 4));
     w.box_cell = (int*)(b + take(binned ? (size_t)n * 4 : 4));
@@ -352,12 +353,13 @@ __global__ void nms_keys_kernel(const float* __restrict__ scores, const int32_t*
 }
 
 __global__ void nms_prep_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ boxes, int box_dim,
-                                int n, float* __restrict__ prep, int* __restrict__ sgroup, int* __restrict__ seg) {
+                                int n, float* __restrict__ prep, int* __restrict__ sgroup, int* __restrict__ seg,
+                                const int32_t* __restrict__ group_src = nullptr) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const unsigned long long k = keys[p];
     const int idx = (int)(k & 0xFFFFFFull);
-    const int g = (int)(k >> 56);
+    const int g = group_src ? (int)(group_src[idx] & 0xFF) : (int)(k >> 56);     // keys sorted by score alone carry no group byte
     sgroup[p] = g;
     if (p == 0 || (int)(keys[p - 1] >> 56) != g) seg[g] = p;
     if (p == n - 1 || (int)(keys[p + 1] >> 56) != g) seg[256 + g] = p + 1;
@@ -971,9 +973,109 @@ __global__ void nms_emit_kernel(const unsigned long long* __restrict__ keys2, in
     if (p == 0 && !v) *n_keep = 0;
 }
 
+
+#include "nms_cells.cuh"
+
+static size_t cl_layout(void* base, int n, CellWs* out) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    char* b = (char*)base;
+    CellWs c;
+    c.state = (signed char*)(b + take((size_t)n));
+    c.adj_cnt = (int*)(b + take((size_t)n * 4));
+    c.adj = (int*)(b + take((size_t)n * kAdjSlots * 4));
+    for (CellIndex* X : {&c.A, &c.B}) {
+        X->start = (int*)(b + take((size_t)(kBinCells + 1) * 4));
+        X->cursor = (int*)(b + take((size_t)kBinCells * 4));
+        X->recs = (float4*)(b + take((size_t)n * 48));
+        X->item_start = (int*)(b + take((size_t)(kBinCells + 1) * 4));
+        X->items = (int2*)(b + take(((size_t)n / kQB + kBinCells + 2) * 8));
+    }
+    c.totals = (unsigned long long*)(b + take((size_t)kScanBlocks * 8));
+    c.meta = (int*)(b + take(64));
+    c.und = (int*)(b + take(kRoundBatch * 4));
+    c.fail = (int*)(b + take(64));
+    c.blk = (int*)(b + take(((size_t)n / 1024 + 2) * 4));
+    if (out) *out = c;
+    return off;
+}
+
+// returns NRPN_OK with *declined = true when the input needs the chunked path (nothing has been written to keep / n_keep then)
+static int nms_run_cells(const float* boxes, int box_dim, const float* scores, const int32_t* group, int n, float thr, int ignore_group,
+                         int64_t* keep, int32_t* n_keep, const NmsWs& w, const CellWs& c, cudaStream_t st, bool* declined) {
+    *declined = false;
+    const int n_pad = next_pow2(n);
+    nms_keys_kernel<<<ceil_div(n_pad, 256), 256, 0, st>>>(scores, nullptr, n, n_pad, w.keys);
+    NRPN_LAUNCH_CHECK();
+    int rc = bitonic_sort_u64(w.keys, n_pad, st);
+    if (rc) return rc;
+    nms_prep_kernel<<<ceil_div(n, 128), 128, 0, st>>>(w.keys, boxes, box_dim, n, w.prep, w.sgroup, w.seg, group);
+    NRPN_LAUNCH_CHECK();
+    // grid of the cell lists (shared with the chunked path's index: extents -> volume classes -> per-class cell sizes -> cell of every box)
+    nms_bin_stats_init_kernel<<<1, 64, 0, st>>>(w.bstats);
+    nms_bin_stats_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.prep, n, 0, w.grid, w.bstats);
+    nms_bin_grid_kernel<<<1, 32, 0, st>>>(w.bstats, thr - 1e-3f, 0, w.grid);
+    nms_bin_stats_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.prep, n, 1, w.grid, w.bstats);
+    nms_bin_grid_kernel<<<1, 32, 0, st>>>(w.bstats, thr - 1e-3f, 1, w.grid);
+    NRPN_LAUNCH_CHECK();
+    NRPN_CUDA_TRY(cudaMemsetAsync(w.cell_fill, 0, (size_t)kBinCells * 4, st));
+    nms_bin_assign_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.prep, n, w.grid, w.box_cell, w.cell_fill);
+    NRPN_LAUNCH_CHECK();
+    NRPN_CUDA_TRY(cudaMemsetAsync(c.A.cursor, 0, (size_t)kBinCells * 4, st));
+    NRPN_CUDA_TRY(cudaMemsetAsync(c.B.cursor, 0, (size_t)kBinCells * 4, st));
+    NRPN_CUDA_TRY(cudaMemsetAsync(c.fail, 0, 4, st));
+    cl_state_init_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.sgroup, n, ignore_group, c.state, c.adj_cnt);
+    NRPN_LAUNCH_CHECK();
+
+    static const int pair_grid = [] { int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); return 2 * sms; }();
+    PairArgs pa;
+    pa.prep = w.prep; pa.box_dim = box_dim; pa.thr = thr; pa.grid = w.grid;
+    pa.qstart = c.B.start; pa.qrecs = c.B.recs; pa.item_start = c.B.item_start; pa.items = c.B.items; pa.work = c.meta;
+    pa.state = c.state; pa.adj_cnt = c.adj_cnt; pa.adj = c.adj; pa.fail = c.fail;
+    int b = 0;
+    for (int e = n < kLevel0 ? n : kLevel0; b < n; ) {
+        const int m = e - b;
+        if (b > 0) {
+            cl_build_index(c.A, c, w, 0, b, ST_KEPT, false, st);             // kept boxes of the earlier levels
+            cl_build_index(c.B, c, w, b, e, ST_UNDECIDED, true, st);         // this level's boxes as queries
+            NRPN_LAUNCH_CHECK();
+            NRPN_CUDA_TRY(cudaMemsetAsync(c.meta, 0, 4, st));
+            pa.rstart = c.A.start; pa.rrecs = c.A.recs;
+            cl_pairs_kernel<0><<<pair_grid, kPairThreads, 0, st>>>(pa);
+            NRPN_LAUNCH_CHECK();
+        }
+        cl_build_index(c.B, c, w, b, e, ST_UNDECIDED, true, st);             // the survivors, against each other
+        NRPN_LAUNCH_CHECK();
+        NRPN_CUDA_TRY(cudaMemsetAsync(c.meta, 0, 4, st));
+        pa.rstart = c.B.start; pa.rrecs = c.B.recs;
+        cl_pairs_kernel<1><<<pair_grid, kPairThreads, 0, st>>>(pa);
+        NRPN_LAUNCH_CHECK();
+        const int rgrid = ceil_div(m, 256) < 1184 ? ceil_div(m, 256) : 1184;
+        for (int rounds = 0;; rounds += kRoundBatch) {
+            NRPN_CUDA_TRY(cudaMemsetAsync(c.und, 0, kRoundBatch * 4, st));
+            for (int r = 0; r < kRoundBatch; ++r) cl_round_kernel<<<rgrid, 256, 0, st>>>(c.B.recs, c.B.start, c.adj_cnt, c.adj, c.state, c.und, r);
+            NRPN_LAUNCH_CHECK();
+            int h[2] = {0, 0};
+            NRPN_CUDA_TRY(cudaMemcpyAsync(&h[0], c.und + kRoundBatch - 1, 4, cudaMemcpyDeviceToHost, st));
+            NRPN_CUDA_TRY(cudaMemcpyAsync(&h[1], c.fail, 4, cudaMemcpyDeviceToHost, st));
+            NRPN_CUDA_TRY(cudaStreamSynchronize(st));
+            if (h[1] || rounds > kRoundCap) { *declined = true; return NRPN_OK; }
+            if (h[0] == 0) break;
+        }
+        b = e;
+        e = (long long)e * kLevelGrowth > (long long)n ? n : e * kLevelGrowth;
+    }
+    const int nblk = ceil_div(n, 1024);
+    cl_keep_count_kernel<<<nblk, 1024, 0, st>>>(c.state, n, c.blk);
+    cl_keep_scan_kernel<<<1, 1024, 0, st>>>(c.blk, nblk, n_keep);
+    cl_keep_emit_kernel<<<nblk, 1024, 0, st>>>(c.state, w.keys, n, c.blk, keep);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
 size_t nms_workspace_bytes(int n) {
     if (n <= 0) return 256;
-    return nms_layout(nullptr, n).total + 256;
+    return nms_layout(nullptr, n).total + (n >= kCellMinBoxes ? cl_layout(nullptr, n, nullptr) : 0) + 256;
 }
 
 int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t* group, int n, float thr, int ignore_group,
@@ -984,6 +1086,18 @@ int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t*
     if (ws_bytes < nms_workspace_bytes(n)) return NRPN_ERR_WORKSPACE;
     void* base = (void*)align_up((size_t)ws, 256);
     NmsWs w = nms_layout(base, n);
+    if (n >= kCellMinBoxes && thr >= 0.0f) {
+        static const bool cells_off = [] { const char* e = getenv("NRPN_NMS_CELLS"); return e && e[0] == '0'; }();
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);                    // the level loop reads counters back: not capturable
+        if (!cells_off && cap == cudaStreamCaptureStatusNone) {
+            CellWs c;
+            cl_layout((char*)base + w.total, n, &c);
+            bool declined = false;
+            const int rc = nms_run_cells(boxes, box_dim, scores, group, n, thr, ignore_group, keep, n_keep, w, c, st, &declined);
+            if (rc || !declined) return rc;
+        }
+    }
     const int n_pad = next_pow2(n < 2 ? 2 : n);
     const int W = ceil_div(n, 64);
     NRPN_CUDA_TRY(cudaMemsetAsync(w.seg, 0, 512 * 4, st));

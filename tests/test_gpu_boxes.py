@@ -142,9 +142,10 @@ def test_nms_chunked_path_large_inputs(ops):
     assert np.nanmax(m) <= 0.3                                                        # survivors do not overlap beyond thr
 
 
-def test_nms_binned_index_equals_kept_list_scan(ops, tmp_path):
-    """n >= 65 536 files the kept boxes in a (volume class, x, y, z) grid and visits only the cells a box can interact with; the keep list
-    must equal the plain kept-list scan (NRPN_NMS_BINNED=0, read when the library initialises: run in a second process) at 300 000 boxes."""
+def test_nms_cell_list_path_equals_chunked_kept_list_scan(ops, tmp_path):
+    """n >= 16 384 runs the cell-list path (levels: cross against the kept boxes, adjacency among the survivors, dependency rounds); the keep
+    list must equal the plain chunk-by-chunk kept-list scan (NRPN_NMS_CELLS=0 NRPN_NMS_BINNED=0, read when the library initialises: run in a
+    second process) at 300 000 boxes, 2 groups, 40 degenerate boxes."""
     import subprocess, sys, textwrap
     rng = np.random.default_rng(23)
     n = 300000
@@ -165,11 +166,31 @@ def test_nms_binned_index_equals_kept_list_scan(ops, tmp_path):
         k, nk = ops.nms_device(torch.from_numpy(d['boxes']).cuda(), torch.from_numpy(d['scores']).cuda(), torch.from_numpy(d['groups']).cuda(), 0.3)
         np.save({str(tmp_path / 'ref.npy')!r}, k[: int(nk.item())].cpu().numpy())
     """)
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env={**os.environ, "NRPN_NMS_BINNED": "0"})
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env={**os.environ, "NRPN_NMS_BINNED": "0", "NRPN_NMS_CELLS": "0"})
     assert r.returncode == 0, r.stderr[-2000:]
     ref = np.load(str(tmp_path / "ref.npy"))
     assert 1000 < ref.shape[0] < n
     np.testing.assert_array_equal(keep, ref)
+
+
+def test_nms_cell_list_path_declines_crowds_and_handles_ties(ops):
+    """More than 32 higher-scored overlapping survivors per box overflow the inline predecessor lists: the path must hand over to the chunked
+    one (same keep set as the oracle).  Exact score ties and long suppression chains stay on the cell-list path."""
+    rng = np.random.default_rng(29)
+    base = rand_obb(40, rng, 120.0, 8, 20)
+    crowd = np.repeat(base, 500, axis=0) + rng.normal(0, 0.05, (20000, 7)).astype(np.float32)      # 500 near-copies of each of 40 boxes
+    crowd[:, 3:6] = np.abs(crowd[:, 3:6])
+    scores = rng.random(20000).astype(np.float32)
+    np.testing.assert_array_equal(run_nms(ops, crowd, scores, None, 0.3), obox.nms(crowd, scores, 0.3))
+    n = 18000                                                   # a chain: neighbours overlap at IoU ~ 0.54, scores fall along the chain
+    chain = np.zeros((n, 7), np.float32)
+    chain[:, 0] = np.arange(n) * 3.0; chain[:, 3:6] = 10.0
+    s2 = np.linspace(1.0, 0.0, n).astype(np.float32)
+    k = min(s2[::7].shape[0], s2[1::7].shape[0])
+    s2[::7][:k] = s2[1::7][:k]                                  # ties
+    np.testing.assert_array_equal(run_nms(ops, chain, s2, None, 0.3), obox.nms(chain, s2, 0.3))
+    groups = rng.integers(0, 3, n).astype(np.int32)
+    np.testing.assert_array_equal(run_nms(ops, chain, s2, groups, 0.3), obox.batched_nms(chain, s2, groups, 0.3))
 
 
 def _rpn_inputs_from_golden(r, rot):
