@@ -306,7 +306,8 @@ int nrpn_assign_targets(const float *anchors, int n_anchors, const float *gt, in
 
 /* ------------------------------------------------------------------------------------------------ weight gradient
  * dW[tap][co][ci] = sum_v dY[v][co] * X[v + tap_off][ci] of a stride-1 convolution (training) on tcgen05.
- * Both operands are read in PLANAR layout (N, C, X, Y, z_pitch), 16-bit (nrpn_transpose_to_planar converts a channels-last tensor);
+ * operand_layout 1 (what the training engine uses): both operands are read channels-last where they live (MN-major tcgen05 operands).
+ * operand_layout 0: both operands in PLANAR layout (N, C, X, Y, z_pitch), 16-bit (nrpn_transpose_to_planar converts a channels-last tensor);
  * levels that share the weights (RPN head on P2..P5) accumulate into the same dW.  dw: fp32 (taps, cout, cin), overwritten.
  * cout % 128 == 0; cin % 32 == 0, cin <= 256; tap z offsets in {-1, 0, +1}.  Deterministic (fixed-order reduction of the K-split partial tiles). */
 typedef struct {
@@ -314,6 +315,11 @@ typedef struct {
     const void *x_planar[3]; /* (N, cin,  X, Y, z_pitch): copies shifted along z, [k][z] = x[z + (k - 1)], zero outside; NULL if no tap has dz = k - 1 */
     int32_t n, x, y, z;
     int32_t z_pitch;         /* >= z + 1, multiple of 8; positions without a source MUST be zero (pre-zeroed buffers) */
+    /* operand_layout == 1: the operands where they live, channels-last 16-bit (N, X, Y, Z, ld); no copies, no staging buffers */
+    const void *dy_cl;       /* (N, x, y, z, ld_dy >= cout) */
+    const void *x_cl;        /* (N, xx, xy, xz, ld_x >= cin): the layer input, same grid as dY unless xx / xy / xz say otherwise */
+    int32_t ld_dy, ld_x;     /* row pitches in elements, multiples of 8 */
+    int32_t xx, xy, xz;      /* extents of X when they differ from (x, y, z); 0 = same */
 } nrpn_wgrad_level;
 
 typedef struct {
@@ -327,6 +333,7 @@ typedef struct {
     int32_t act_fp16;
     int32_t dw_layout;       /* 0: dw is (taps, Cout, Cin); 1: dw is (Cout, Cin, taps) = nn.Conv3d.weight's own memory order */
     int32_t accumulate;      /* 1: dw += result (a weight shared by several launches) */
+    int32_t operand_layout;  /* 0: planar copies (dy_planar / x_planar); 1: channels-last tensors (dy_cl / x_cl) read through MN-major descriptors */
 } nrpn_wgrad_desc;
 
 size_t nrpn_conv3d_wgrad_workspace_bytes(const nrpn_wgrad_desc *desc /*host*/);
@@ -399,6 +406,18 @@ int nrpn_grad_norm(const float *g, size_t n, float inv_scale, float *norm_out, v
  * on flat fp32 buffers; gradients are multiplied by inv_scale first (loss scaling / world size). */
 int nrpn_adamw_step(float *p, const float *g, float *m, float *v, size_t n, const float *norm, float max_norm, float inv_scale, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, nrpn_stream_t stream);
+
+/* Which necessary-condition tests may skip the exact polygon clip inside NMS (process-wide; initial value from NRPN_NMS_CULL_MODE, default 0):
+ *   0  exact-zero culls only (bounding circles / z ranges disjoint: the reference computes exactly 0) -- the keep set is provably the reference's;
+ *   1  + volume-ratio and z-overlap-ratio culls, 3  + footprint-lens cull: geometric bounds, applied from 16 384 boxes up only.  The reference's
+ *      vertex sort can report MORE than the geometric IoU in rare degenerate cases, so these modes may differ from it in about
+ *      1e-5 of the boxes; they make the 1 M-box sweep 4-5x faster. */
+void nrpn_set_nms_cull_mode(int mode);
+int nrpn_get_nms_cull_mode(void);
+
+/* Diagnostics of the cell-list NMS path (n >= 16 384 boxes): cumulative counters since the last reset -- out16[0..4] for the cross passes
+ * (records streamed, record x query pair slots, exact IoU evaluations, hits, work items), out16[8..12] the same for the adjacency passes.  Synchronises. */
+int nrpn_nms_cells_stats(unsigned long long *out16, int reset);
 
 /* Training-time augmentation of one scene on the device (BaseDataset.augment_rpn_inputs + rotate_and_scale_scene, datasets.py:109-163,
  * 290-329, z-up): fp32 grid in its on-disk channels-last order (X, Y, Z, 4) -> out (Xo, Yo, Z, 4), Xo/Yo = Y/X when rot90 else X/Y.

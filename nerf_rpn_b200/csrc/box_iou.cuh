@@ -274,6 +274,9 @@ __device__ __forceinline__ bool obb_surely_zero(const float* __restrict__ ta, co
 //     IoU <= min(A_a, A_b, lens) * z_overlap / max(V)   (footprints that only graze each other cannot either).
 // thr_m = thr - 1e-3: the margin dwarfs every rounding error of the reference's fp32 chain (its value never exceeds the exact IoU by
 // more than ~1e-5: mis-sorted or missing vertices only ever SHRINK the polygon), so the skipped decisions are the reference's.
+#ifndef NRPN_LENS_CULL
+#define NRPN_LENS_CULL 1
+#endif
 __device__ __forceinline__ bool obb_surely_not_above(const float* __restrict__ ta, const float* __restrict__ tb, float thr_m) {
     if (!(__float_as_int(ta[7]) && __float_as_int(tb[7]))) return false;
     const float dx = ta[4] - tb[4], dy = ta[5] - tb[5], rr = ta[6] + tb[6];
@@ -288,7 +291,7 @@ __device__ __forceinline__ bool obb_surely_not_above(const float* __restrict__ t
         // intersection = footprint overlap x z overlap, union >= the larger volume; the footprint overlap is at most the smaller footprint and at
         // most the bounding rectangle of the lens the two bounding circles share: (r_a + r_b - distance) x 2 min(r)
         const float lens = 2.0f * fminf(ta[6], tb[6]) * (rr - sqrtf(d2));
-        if (fminf(fminf(ta[0], tb[0]), lens) * oz <= thr_m * vmax) return true;
+        if (NRPN_LENS_CULL && fminf(fminf(ta[0], tb[0]), lens) * oz <= thr_m * vmax) return true;
     }
     return false;
 }

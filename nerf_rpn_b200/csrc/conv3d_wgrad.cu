@@ -154,6 +154,129 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_tap
     }
 }
 
+// ------------------------------------------------------------------------------------------------ channels-last operands (MN-major UMMA)
+// The same contraction with BOTH operands read where they live: channels-last (N, X, Y, Z, ld) tensors.  A TMA box {64 channels, bz, by, bx} of
+// 64 voxels lands in shared memory as 64 rows of 128 bytes (128B swizzle) -- which IS the canonical MN-major operand layout of tcgen05.mma
+// (cute::UMMA make_umma_desc<Major::MN>, SWIZZLE_128B: ((8,n),(8,k)) x 16 bytes : ((1,LBO),(8,SBO)) -- 64 channels contiguous per voxel row, 8 rows
+// per 1024-byte swizzle atom, SBO = 1024 bytes between groups of 8 voxels, LBO = the distance between two 64-channel boxes).  The instruction
+// descriptor's a_major / b_major bits (15, 16) select it.  No transposed copies, no zero-filled staging buffers: the tap offset is a plain
+// coordinate shift of the X box and TMA's out-of-bounds zero fill is the convolution padding.
+//   A = dY box pair  (128 output channels  x 64 voxels),  B = X boxes (n_t input channels x 64 voxels, shifted by the tap)
+struct WgLevelCl { int n, nxb, nyb, nzb, bx, by, bz, brick_begin; };
+struct WgDevCl {
+    int n_levels, n_taps, cin, cout, n_t, m_tiles, n_tiles, splits, total_bricks, fp16, b_boxes;
+    signed char tap[NRPN_CONV_MAX_TAPS][4];
+    WgLevelCl lv[NRPN_CONV_MAX_LEVELS];
+    float* partial;
+};
+struct WgMapsCl { CUtensorMap dy[NRPN_CONV_MAX_LEVELS]; CUtensorMap x[NRPN_CONV_MAX_LEVELS]; };
+constexpr int kWgBox = 64 * 128;               // one {64 channels x 64 voxels} box, 16-bit
+
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {   // LBO = 8192 B (next 64-channel box), SBO = 1024 B (next 8 voxels)
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(kWgBox >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_cl_kernel(const __grid_constant__ WgMapsCl maps, const WgDevCl P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = (2 + P.b_boxes) * kWgBox;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kWgStages;
+    uint64_t* tfull_bar = bars + 2 * kWgStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWgStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::fence_barrier_init();
+        for (int l = 0; l < P.n_levels; ++l) { ptx::prefetch_tmap(&maps.dy[l]); ptx::prefetch_tmap(&maps.x[l]); }
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t idesc = (P.fp16 ? ptx::make_idesc_f16(128, P.n_t) : ptx::make_idesc_bf16(128, P.n_t)) | (1u << 15) | (1u << 16);   // MN-major A and B
+    const int items = P.n_taps * P.m_tiles * P.n_tiles * P.splits;
+    uint32_t tphase = 0;
+    int stage_p = 0, stage_c = 0; uint32_t phase_p = 0, phase_c = 0;
+
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int split = item % P.splits;
+        const int nt = (item / P.splits) % P.n_tiles;
+        const int mt = (item / (P.splits * P.n_tiles)) % P.m_tiles;
+        const int tap = item / (P.splits * P.n_tiles * P.m_tiles);
+        const int b0 = (int)(((long)P.total_bricks * split) / P.splits), b1 = (int)(((long)P.total_bricks * (split + 1)) / P.splits);
+        if (warp == 0) {
+            const bool leader = ptx::elect_one();
+            const int dx = P.tap[tap][0], dy = P.tap[tap][1], dz = P.tap[tap][2];
+            for (int b = b0; b < b1; ++b) {
+                int l = 0;
+#pragma unroll
+                for (int i = 1; i < NRPN_CONV_MAX_LEVELS; ++i) if (i < P.n_levels && b >= P.lv[i].brick_begin) l = i;
+                const WgLevelCl& L = P.lv[l];
+                int t = b - L.brick_begin;
+                const int zb = t % L.nzb; t /= L.nzb;
+                const int yb = t % L.nyb; t /= L.nyb;
+                const int xb = t % L.nxb; const int nb = t / L.nxb;
+                const int z0 = zb * L.bz, y0 = yb * L.by, x0 = xb * L.bx;
+                ptx::mbar_wait(&empty_bar[stage_p], phase_p ^ 1u);
+                if (leader) {
+                    uint8_t* sa = smem + stage_p * stage_bytes;
+                    ptx::mbar_expect_tx(&full_bar[stage_p], (uint32_t)stage_bytes);
+                    ptx::tma_load_5d(sa, &maps.dy[l], &full_bar[stage_p], mt * 128, z0, y0, x0, nb);
+                    ptx::tma_load_5d(sa + kWgBox, &maps.dy[l], &full_bar[stage_p], mt * 128 + 64, z0, y0, x0, nb);
+                    for (int j = 0; j < P.b_boxes; ++j)
+                        ptx::tma_load_5d(sa + (2 + j) * kWgBox, &maps.x[l], &full_bar[stage_p], nt * P.n_t + 64 * j, z0 + dz, y0 + dy, x0 + dx, nb);
+                }
+                __syncwarp();
+                if (++stage_p == kWgStages) { stage_p = 0; phase_p ^= 1u; }
+            }
+        } else if (warp == 1) {
+            const bool leader = ptx::elect_one();
+            for (int b = b0; b < b1; ++b) {
+                ptx::mbar_wait(&full_bar[stage_c], phase_c);
+                ptx::tc_fence_after();
+                const uint32_t sa = ptx::smem_u32(smem + stage_c * stage_bytes);
+                const uint64_t da = make_desc_mn_sw128(sa), db = make_desc_mn_sw128(sa + 2 * kWgBox);
+                if (leader) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)          // 16 voxels per MMA = two 1024-byte atoms further along K
+                        ptx::umma_bf16(tmem, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc, ((b - b0) | k) ? 1u : 0u);
+                    ptx::umma_commit(&empty_bar[stage_c]);
+                }
+                __syncwarp();
+                if (++stage_c == kWgStages) { stage_c = 0; phase_c ^= 1u; }
+            }
+            if (leader) ptx::umma_commit(tfull_bar);
+            __syncwarp();
+        } else {
+            const int q = warp & 3, row = q * 32 + lane;
+            float* out = P.partial + (((((size_t)tap * P.m_tiles + mt) * P.n_tiles + nt) * P.splits + split) * 128 + row) * P.n_t;
+            ptx::mbar_wait(tfull_bar, tphase);
+            ptx::tc_fence_after();
+            const bool empty = (b1 <= b0);
+            for (int c = 0; c < P.n_t; c += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(out + c + j) = empty ? make_float4(0.f, 0.f, 0.f, 0.f)
+                        : make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+            ptx::tc_fence_before();
+        }
+        tphase ^= 1u;
+        __syncthreads();
+        ptx::tc_fence_after();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
+}
+
 // channels-last (N, X*Y*Z, ld) -> planar (N, C, X*Y, Zp) with Zp = z pitch >= Z (a multiple of 8 so that every TMA stride is a
 // multiple of 16 bytes; the pad is never read: the tensor maps carry the logical Z), 16-bit elements, 64 x 64 tiles through smem
 __global__ void __launch_bounds__(256) cl_to_planar_kernel(const uint16_t* __restrict__ in, int ld, int C, long V, int Z, int Zp,
@@ -229,13 +352,114 @@ static int wgrad_plan(const nrpn_wgrad_desc* d, WgDev& P) {
     return NRPN_OK;
 }
 
+// ---- channels-last operands (desc->operand_layout == 1)
+static int pick_box(int extent, int cap) {           // power of two in [1, cap] with the least overhang over `extent`, the larger one on ties
+    int best = 1; long waste = -1;
+    for (int b = 1; b <= cap; b <<= 1) {
+        const long w = (long)ceil_div(extent, b) * b;
+        if (waste < 0 || w <= waste) { waste = w; best = b; }
+    }
+    return best;
+}
+
+static int wgrad_plan_cl(const nrpn_wgrad_desc* d, WgDevCl& P) {
+    if (!d || d->n_levels < 1 || d->n_levels > NRPN_CONV_MAX_LEVELS || d->n_taps < 1 || d->n_taps > NRPN_CONV_MAX_TAPS) return NRPN_ERR_INVALID;
+    if (d->cout < 8 || d->cout % 8 != 0 || d->cin < 32 || d->cin % 32 != 0 || (d->cin > 256 && d->cin % 256 != 0)) return NRPN_ERR_UNSUPPORTED;
+    memset(&P, 0, sizeof(P));
+    P.n_levels = d->n_levels; P.n_taps = d->n_taps; P.cin = d->cin; P.cout = d->cout;
+    P.n_t = d->cin > 256 ? 256 : d->cin; P.n_tiles = d->cin / P.n_t; P.m_tiles = ceil_div(d->cout, 128);
+    P.b_boxes = ceil_div(P.n_t, 64);
+    P.fp16 = d->act_fp16 ? 1 : 0;
+    for (int t = 0; t < d->n_taps; ++t) { P.tap[t][0] = d->tap_off[t][0]; P.tap[t][1] = d->tap_off[t][1]; P.tap[t][2] = d->tap_off[t][2]; P.tap[t][3] = 0; }
+    int bricks = 0;
+    for (int l = 0; l < d->n_levels; ++l) {
+        const nrpn_wgrad_level& S = d->level[l];
+        if (S.n < 1 || S.x < 1 || S.y < 1 || S.z < 1 || !S.dy_cl || !S.x_cl || S.ld_dy < d->cout || S.ld_x < d->cin || S.ld_dy % 8 != 0 || S.ld_x % 8 != 0)
+            return NRPN_ERR_INVALID;
+        WgLevelCl& L = P.lv[l];
+        L.n = S.n;
+        L.bz = pick_box(S.z, 64); L.by = pick_box(S.y, 64 / L.bz); L.bx = 64 / (L.bz * L.by);
+        L.nzb = ceil_div(S.z, L.bz); L.nyb = ceil_div(S.y, L.by); L.nxb = ceil_div(S.x, L.bx);
+        L.brick_begin = bricks;
+        bricks += S.n * L.nxb * L.nyb * L.nzb;
+    }
+    P.total_bricks = bricks;
+    const int base = d->n_taps * P.m_tiles * P.n_tiles;
+    int splits = num_sms() / base;
+    if (splits > bricks) splits = bricks;
+    if (splits < 1) splits = 1;
+    P.splits = splits;
+    return NRPN_OK;
+}
+
+static int wgrad_run_cl(const nrpn_wgrad_desc* d, cudaStream_t st) {
+    WgDevCl P;
+    { const int rc = wgrad_plan_cl(d, P); if (rc) return rc; }
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return NRPN_ERR_NO_DEVICE;
+    WgMapsCl maps;
+    const CUtensorMapDataType dt = d->act_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    for (int l = 0; l < d->n_levels; ++l) {
+        const nrpn_wgrad_level& S = d->level[l];
+        const WgLevelCl& L = P.lv[l];
+        cuuint32_t one[5] = {1, 1, 1, 1, 1};
+        cuuint32_t box[5] = {64, (cuuint32_t)L.bz, (cuuint32_t)L.by, (cuuint32_t)L.bx, 1};
+        // dY: (cout, Z, Y, X, N) with the extents of the OUTPUT grid; X: the input grid (its own extents when they differ)
+        const int xz = S.xz > 0 ? S.xz : S.z, xy = S.xy > 0 ? S.xy : S.y, xx = S.xx > 0 ? S.xx : S.x;
+        {
+            cuuint64_t gdim[5] = {(cuuint64_t)d->cout, (cuuint64_t)S.z, (cuuint64_t)S.y, (cuuint64_t)S.x, (cuuint64_t)S.n};
+            const cuuint64_t e = (cuuint64_t)S.ld_dy * 2;
+            cuuint64_t gstr[4] = {e, e * S.z, e * S.z * S.y, e * S.z * S.y * S.x};
+            CUresult r = encode(&maps.dy[l], dt, 5, const_cast<void*>(S.dy_cl), gdim, gstr, box, one, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return NRPN_ERR_CUDA; }
+        }
+        {
+            cuuint64_t gdim[5] = {(cuuint64_t)d->cin, (cuuint64_t)xz, (cuuint64_t)xy, (cuuint64_t)xx, (cuuint64_t)S.n};
+            const cuuint64_t e = (cuuint64_t)S.ld_x * 2;
+            cuuint64_t gstr[4] = {e, e * xz, e * xz * xy, e * xz * xy * xx};
+            CUresult r = encode(&maps.x[l], dt, 5, const_cast<void*>(S.x_cl), gdim, gstr, box, one, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return NRPN_ERR_CUDA; }
+        }
+    }
+    for (int l = d->n_levels; l < NRPN_CONV_MAX_LEVELS; ++l) { maps.dy[l] = maps.dy[0]; maps.x[l] = maps.x[0]; }
+    P.partial = reinterpret_cast<float*>(align_up((size_t)d->workspace, 256));
+    const int smem = kWgStages * (2 + P.b_boxes) * kWgBox + 1024 + 256;
+    static int smem_set = 0;
+    if (smem > smem_set) {
+        NRPN_CUDA_TRY(cudaFuncSetAttribute(conv3d_wgrad_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set = smem;
+    }
+    const int items = P.n_taps * P.m_tiles * P.n_tiles * P.splits;
+    const int grid = items < num_sms() ? items : num_sms();
+    conv3d_wgrad_cl_kernel<<<grid, kWgThreads, smem, st>>>(maps, P);
+    NRPN_LAUNCH_CHECK();
+    const size_t total = (size_t)P.n_taps * P.cout * P.cin;
+    size_t blocks = ceil_div(total, (size_t)256);
+    if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
+    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(P.partial, P.n_taps, P.m_tiles, P.n_tiles, P.splits, P.n_t, P.cout, P.cin, d->dw,
+                                                        d->dw_layout ? 1 : 0, d->accumulate ? 1 : 0);
+    NRPN_LAUNCH_CHECK();
+    return NRPN_OK;
+}
+
 size_t nrpn_conv3d_wgrad_workspace_bytes(const nrpn_wgrad_desc* d) {
+    if (d && d->operand_layout == 1) {
+        WgDevCl P;
+        if (wgrad_plan_cl(d, P) != NRPN_OK) return 0;
+        return (size_t)P.n_taps * P.m_tiles * P.n_tiles * P.splits * 128 * P.n_t * sizeof(float) + 256;
+    }
     WgDev P;
     if (wgrad_plan(d, P) != NRPN_OK) return 0;
     return (size_t)P.n_taps * P.m_tiles * P.n_tiles * P.splits * 128 * P.n_t * sizeof(float) + 256;
 }
 
 int nrpn_conv3d_wgrad(const nrpn_wgrad_desc* d, nrpn_stream_t stream) {
+    if (d && d->operand_layout == 1) {
+        if (!d->dw || !d->workspace || d->workspace_bytes < nrpn_conv3d_wgrad_workspace_bytes(d)) return NRPN_ERR_WORKSPACE;
+        return wgrad_run_cl(d, (cudaStream_t)stream);
+    }
     WgDev P;
     { const int rc = wgrad_plan(d, P); if (rc) return rc; }
     if (!d->dw || !d->workspace || d->workspace_bytes < nrpn_conv3d_wgrad_workspace_bytes(d)) return NRPN_ERR_WORKSPACE;

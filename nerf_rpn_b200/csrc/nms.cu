@@ -7,13 +7,16 @@
 // 64 rows at a time (warp-shuffle resolve of the diagonal word, coalesced OR of the kept rows), then sort
 // the survivors by score.  No host round trips; everything is stream-ordered.
 namespace nrpn { static __device__ int g_iou_mode = 3; }      // see box_iou.cuh: which build of the reference chain is reproduced
+namespace nrpn { static __device__ int g_lens_cull = 0; }     // footprint-lens cull, bit 1 of the NMS cull mode
 #define NRPN_IOU_MODE (::nrpn::g_iou_mode)
+#define NRPN_LENS_CULL (::nrpn::g_lens_cull)
 #include "box_iou.cuh"
 #include "nms_internal.cuh"
 
 namespace nrpn {
 
 thread_local int g_last_cuda_error = 0;
+static std::atomic<int> g_nms_cull_mode{[] { const char* e = getenv("NRPN_NMS_CULL_MODE"); return e ? atoi(e) & 3 : 0; }()};
 std::atomic<unsigned long long> g_launch_count{0};
 
 // ---------------------------------------------------------------------------------------------- IoU
@@ -276,6 +279,10 @@ constexpr int kPrepFloats = 16;
 // Every candidate still goes through the same cull + exact polygon clip: the keep set is the sequential greedy loop's, bit for bit.
 constexpr int kBinMinBoxes = 65536;
 constexpr int kCellMinBoxes = 16384;     // cell-list path (nms_cells.cuh) from here; it shares the grid / box_cell buffers below
+static int cell_min_boxes() {            // NRPN_NMS_CELLS_MIN: where the cell-list path takes over (tuning runs); the ratio culls keep their 16 384 floor
+    static const int v = [] { const char* e = getenv("NRPN_NMS_CELLS_MIN"); const int k = e ? atoi(e) : kCellMinBoxes; return k < 1024 ? 1024 : k; }();
+    return v;
+}
 constexpr int kBinClasses = 16;
 constexpr int kBinMaxXY = 32, kBinMaxZ = 16;
 constexpr int kBinCellsPerClass = kBinMaxXY * kBinMaxXY * kBinMaxZ;
@@ -328,7 +335,7 @@ static NmsWs nms_layout(void* base, int n) {
     w.removed0 = (unsigned long long*)(b + take(64 * 8));
     w.kept_pos = (int*)(b + take((size_t)n * 4));
     w.state = (int*)(b + take(258 * 4));          // [0] kept count, [1..256] per-group starts, [257] kept boxes already filed in the grid
-    const bool binned = n >= kCellMinBoxes;
+    const bool binned = n >= (cell_min_boxes() < kBinMinBoxes ? cell_min_boxes() : kBinMinBoxes);
     w.grid = (BinGrid*)(b + take(sizeof(BinGrid)));
     w.bstats = (unsigned*)(b + take(kBinStatWords * 4));
     w.box_cell = (int*)(b + take(binned ? (size_t)n * 4 : 4));
@@ -406,7 +413,7 @@ __device__ __forceinline__ void load_prep(const float* __restrict__ s, ObbPrep& 
 constexpr int kMaskThreads = 256;
 
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float* __restrict__ prep, const int* __restrict__ sgroup, int n,
-                                                                int W, int box_dim, float thr, int ignore_group,
+                                                                int W, int box_dim, float thr, float thr_m, int ignore_group,
                                                                 unsigned long long* __restrict__ mask) {
     const int cb = blockIdx.x, rb = blockIdx.y;
     if (cb < rb) return;
@@ -452,7 +459,6 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float* __r
     }
     // ---- phase 1: candidate bits of this thread's 16 columns
     const bool cull_ok = (0.0f <= thr);
-    const float thr_m = thr - 1e-3f;                          // margin of the certain-below-threshold tests (box_iou.cuh)
     unsigned cand = 0u;
     if (row_live) {
         for (int k = 0; k < 16; ++k) {
@@ -562,7 +568,7 @@ constexpr int kCrossTile = 256;      // kept records staged per step (one per th
 // remainder).  "Suppressed by any kept box of my group" does not depend on the order of the tests, so the result is the
 // one of the sequential greedy loop.
 __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict__ prep, const int* __restrict__ sgroup, int box_dim,
-                                                        float thr, int ignore_group, int chunk_begin, int chunk_n,
+                                                        float thr, float thr_m, int ignore_group, int chunk_begin, int chunk_n,
                                                         const int* __restrict__ kept_pos, const int* __restrict__ state,
                                                         unsigned long long* __restrict__ removed0) {
     __shared__ __align__(16) float tile[kCrossTile][8];
@@ -583,7 +589,6 @@ __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict_
     if (lane == 0 && !done) atomicMin(&min_start, start);
     __syncthreads();
     const bool cull_ok = (0.0f <= thr);
-    const float thr_m = thr - 1e-3f;                          // margin of the certain-below-threshold tests (box_iou.cuh)
     const float* bp = prep + (size_t)p * kPrepFloats;
     if (box_dim != 7) {
         // axis-aligned boxes: the IoU itself is a dozen instructions, no staging needed
@@ -826,7 +831,7 @@ __global__ void __launch_bounds__(1024) nms_bin_scan_kernel(const int* __restric
 // lane with no dependent look-ups; entries that survive the group / cull tests are queued and the exact IoU runs on full batches of 32
 // (cf. nms_cross_kernel).
 __global__ void __launch_bounds__(256, 2) nms_cross_binned_kernel(const float* __restrict__ prep, const int* __restrict__ sgroup, int box_dim,
-                                                                  float thr, int ignore_group, int chunk_begin, int chunk_n,
+                                                                  float thr, float thr_m, int ignore_group, int chunk_begin, int chunk_n,
                                                                   const BinGrid* __restrict__ grid, const int* __restrict__ cell_start,
                                                                   const int* __restrict__ cell_fill, const float4* __restrict__ cell_recs,
                                                                   unsigned long long* __restrict__ removed0) {
@@ -842,7 +847,6 @@ __global__ void __launch_bounds__(256, 2) nms_cross_binned_kernel(const float* _
 #pragma unroll
     for (int i = 0; i < 8; ++i) btail[i] = bp[8 + i];
     const bool cull_ok = (0.0f <= thr);
-    const float thr_m = thr - 1e-3f;
     const BinGrid& G = *grid;
     const bool j_cull = __float_as_int(btail[7]) != 0 && cull_ok;
     int cj = 0;
@@ -1002,7 +1006,7 @@ static size_t cl_layout(void* base, int n, CellWs* out) {
 
 // returns NRPN_OK with *declined = true when the input needs the chunked path (nothing has been written to keep / n_keep then)
 static int nms_run_cells(const float* boxes, int box_dim, const float* scores, const int32_t* group, int n, float thr, int ignore_group,
-                         int64_t* keep, int32_t* n_keep, const NmsWs& w, const CellWs& c, cudaStream_t st, bool* declined) {
+                         int64_t* keep, int32_t* n_keep, const NmsWs& w, const CellWs& c, cudaStream_t st, bool* declined, float thr_m) {
     *declined = false;
     const int n_pad = next_pow2(n);
     nms_keys_kernel<<<ceil_div(n_pad, 256), 256, 0, st>>>(scores, nullptr, n, n_pad, w.keys);
@@ -1014,9 +1018,9 @@ static int nms_run_cells(const float* boxes, int box_dim, const float* scores, c
     // grid of the cell lists (shared with the chunked path's index: extents -> volume classes -> per-class cell sizes -> cell of every box)
     nms_bin_stats_init_kernel<<<1, 64, 0, st>>>(w.bstats);
     nms_bin_stats_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.prep, n, 0, w.grid, w.bstats);
-    nms_bin_grid_kernel<<<1, 32, 0, st>>>(w.bstats, thr - 1e-3f, 0, w.grid);
+    nms_bin_grid_kernel<<<1, 32, 0, st>>>(w.bstats, thr_m, 0, w.grid);
     nms_bin_stats_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.prep, n, 1, w.grid, w.bstats);
-    nms_bin_grid_kernel<<<1, 32, 0, st>>>(w.bstats, thr - 1e-3f, 1, w.grid);
+    nms_bin_grid_kernel<<<1, 32, 0, st>>>(w.bstats, thr_m, 1, w.grid);
     NRPN_LAUNCH_CHECK();
     NRPN_CUDA_TRY(cudaMemsetAsync(w.cell_fill, 0, (size_t)kBinCells * 4, st));
     nms_bin_assign_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.prep, n, w.grid, w.box_cell, w.cell_fill);
@@ -1029,7 +1033,7 @@ static int nms_run_cells(const float* boxes, int box_dim, const float* scores, c
 
     static const int pair_grid = [] { int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); return 2 * sms; }();
     PairArgs pa;
-    pa.prep = w.prep; pa.box_dim = box_dim; pa.thr = thr; pa.grid = w.grid;
+    pa.prep = w.prep; pa.box_dim = box_dim; pa.thr = thr; pa.thr_m = thr_m; pa.grid = w.grid;
     pa.qstart = c.B.start; pa.qrecs = c.B.recs; pa.item_start = c.B.item_start; pa.items = c.B.items; pa.work = c.meta;
     pa.state = c.state; pa.adj_cnt = c.adj_cnt; pa.adj = c.adj; pa.fail = c.fail;
     int b = 0;
@@ -1075,7 +1079,7 @@ static int nms_run_cells(const float* boxes, int box_dim, const float* scores, c
 
 size_t nms_workspace_bytes(int n) {
     if (n <= 0) return 256;
-    return nms_layout(nullptr, n).total + (n >= kCellMinBoxes ? cl_layout(nullptr, n, nullptr) : 0) + 256;
+    return nms_layout(nullptr, n).total + (n >= cell_min_boxes() ? cl_layout(nullptr, n, nullptr) : 0) + 256;
 }
 
 int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t* group, int n, float thr, int ignore_group,
@@ -1086,7 +1090,23 @@ int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t*
     if (ws_bytes < nms_workspace_bytes(n)) return NRPN_ERR_WORKSPACE;
     void* base = (void*)align_up((size_t)ws, 256);
     NmsWs w = nms_layout(base, n);
-    if (n >= kCellMinBoxes && thr >= 0.0f) {
+    // Cull mode (nrpn_set_nms_cull_mode).  The exact-zero culls (bounding circles / z ranges disjoint -> the reference computes exactly 0) are always
+    // on.  The RATIO culls (volume ratio, z-overlap ratio, footprint lens; box_iou.cuh) bound the GEOMETRIC IoU -- but the reference's vertex sort
+    // replaces an unsortable vertex (mean-centred y == 0.0f, coincident points) by corner 0 of the first box, and then reports MORE than the geometric
+    // value (~1e-8 of the touching pairs; 1-3 of 85 702 kept boxes at 256 000 boxes).  They are therefore opt-in (bit 0: volume /
+    // depth ratios, bit 1: + footprint lens), only ever applied from 16 384 boxes up, and the default keep set is provably the sequential loop's.
+    const int cull_mode = g_nms_cull_mode.load(std::memory_order_relaxed);
+    const float thr_m = ((cull_mode & 1) && n >= kCellMinBoxes) ? thr - 1e-3f : 0.0f;
+    {
+        static std::atomic<int> applied{-1};
+        const int lens = (cull_mode >> 1) & 1;
+        if (applied.load(std::memory_order_relaxed) != lens) {
+            NRPN_CUDA_TRY(cudaMemcpyToSymbolAsync(g_lens_cull, &lens, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+            NRPN_CUDA_TRY(cudaStreamSynchronize(st));
+            applied.store(lens, std::memory_order_relaxed);
+        }
+    }
+    if (n >= cell_min_boxes() && thr >= 0.0f) {
         static const bool cells_off = [] { const char* e = getenv("NRPN_NMS_CELLS"); return e && e[0] == '0'; }();
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cap);                    // the level loop reads counters back: not capturable
@@ -1094,7 +1114,7 @@ int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t*
             CellWs c;
             cl_layout((char*)base + w.total, n, &c);
             bool declined = false;
-            const int rc = nms_run_cells(boxes, box_dim, scores, group, n, thr, ignore_group, keep, n_keep, w, c, st, &declined);
+            const int rc = nms_run_cells(boxes, box_dim, scores, group, n, thr, ignore_group, keep, n_keep, w, c, st, &declined, thr_m);
             if (rc || !declined) return rc;
         }
     }
@@ -1109,7 +1129,7 @@ int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t*
     nms_prep_kernel<<<ceil_div(n, 128), 128, 0, st>>>(w.keys, boxes, box_dim, n, w.prep, w.sgroup, w.seg);
     NRPN_LAUNCH_CHECK();
     if (nms_use_matrix(n, max_group)) {
-        nms_mask_kernel<<<dim3(W, W), kMaskThreads, 0, st>>>(w.prep, w.sgroup, n, W, box_dim, thr, ignore_group, w.mask);
+        nms_mask_kernel<<<dim3(W, W), kMaskThreads, 0, st>>>(w.prep, w.sgroup, n, W, box_dim, thr, thr_m, ignore_group, w.mask);
         NRPN_LAUNCH_CHECK();
         nms_resolve_kernel<<<256, 256, 0, st>>>(w.mask, W, n, w.seg, ignore_group, w.keepbits);
         NRPN_LAUNCH_CHECK();
@@ -1127,11 +1147,11 @@ int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t*
             NRPN_LAUNCH_CHECK();
             nms_bin_stats_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.prep, n, 0, w.grid, w.bstats);
             NRPN_LAUNCH_CHECK();
-            nms_bin_grid_kernel<<<1, 32, 0, st>>>(w.bstats, thr - 1e-3f, 0, w.grid);
+            nms_bin_grid_kernel<<<1, 32, 0, st>>>(w.bstats, thr_m, 0, w.grid);
             NRPN_LAUNCH_CHECK();
             nms_bin_stats_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.prep, n, 1, w.grid, w.bstats);
             NRPN_LAUNCH_CHECK();
-            nms_bin_grid_kernel<<<1, 32, 0, st>>>(w.bstats, thr - 1e-3f, 1, w.grid);
+            nms_bin_grid_kernel<<<1, 32, 0, st>>>(w.bstats, thr_m, 1, w.grid);
             NRPN_LAUNCH_CHECK();
             NRPN_CUDA_TRY(cudaMemsetAsync(w.cell_fill, 0, (size_t)kBinCells * 4, st));
             nms_bin_assign_kernel<<<ceil_div(n, 256), 256, 0, st>>>(w.prep, n, w.grid, w.box_cell, w.cell_fill);
@@ -1149,13 +1169,13 @@ int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t*
                 NRPN_LAUNCH_CHECK();
                 nms_bin_filed_kernel<<<1, 1, 0, st>>>(w.state, filed);
                 NRPN_LAUNCH_CHECK();
-                nms_cross_binned_kernel<<<ceil_div(cn, 8), 256, 0, st>>>(w.prep, w.sgroup, box_dim, thr, ignore_group, cb, cn, w.grid,
+                nms_cross_binned_kernel<<<ceil_div(cn, 8), 256, 0, st>>>(w.prep, w.sgroup, box_dim, thr, thr_m, ignore_group, cb, cn, w.grid,
                                                                          w.cell_start, w.cell_fill, w.cell_recs, w.removed0);
             } else
-            nms_cross_kernel<<<ceil_div(cn, 8), 256, 0, st>>>(w.prep, w.sgroup, box_dim, thr, ignore_group, cb, cn,
+            nms_cross_kernel<<<ceil_div(cn, 8), 256, 0, st>>>(w.prep, w.sgroup, box_dim, thr, thr_m, ignore_group, cb, cn,
                                                                      w.kept_pos, w.state, w.removed0);
             NRPN_LAUNCH_CHECK();
-            nms_mask_kernel<<<dim3(Wc, Wc), kMaskThreads, 0, st>>>(w.prep + (size_t)cb * kPrepFloats, w.sgroup + cb, cn, Wc, box_dim, thr,
+            nms_mask_kernel<<<dim3(Wc, Wc), kMaskThreads, 0, st>>>(w.prep + (size_t)cb * kPrepFloats, w.sgroup + cb, cn, Wc, box_dim, thr, thr_m,
                                                         ignore_group, w.mask);
             NRPN_LAUNCH_CHECK();
             nms_chunk_resolve_kernel<<<1, 256, 0, st>>>(w.mask, Wc, cb, cn, w.sgroup, w.removed0, w.kept_pos, w.state, w.keepbits);
@@ -1177,6 +1197,15 @@ using namespace nrpn;
 
 extern "C" {
 #pragma GCC visibility push(default)
+
+void nrpn_set_nms_cull_mode(int mode) { g_nms_cull_mode.store(mode & 3, std::memory_order_relaxed); }
+int nrpn_get_nms_cull_mode(void) { return g_nms_cull_mode.load(std::memory_order_relaxed); }
+
+int nrpn_nms_cells_stats(unsigned long long* out16, int reset) {
+    if (out16) NRPN_CUDA_TRY(cudaMemcpyFromSymbol(out16, g_cl_stats, 16 * sizeof(unsigned long long)));
+    if (reset) { const unsigned long long z[16] = {0}; NRPN_CUDA_TRY(cudaMemcpyToSymbol(g_cl_stats, z, sizeof(z))); }
+    return NRPN_OK;
+}
 
 int nrpn_iou3d_pairs(const float* a, const float* b, int n, int box_dim, float* iou, nrpn_stream_t stream) {
     if (n < 0 || (box_dim != 6 && box_dim != 7)) return NRPN_ERR_INVALID;

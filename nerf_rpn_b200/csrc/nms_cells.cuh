@@ -116,8 +116,44 @@ __global__ void cl_scatter_kernel(const signed char* __restrict__ state, const i
     r[2] = make_float4(__int_as_float(p), __int_as_float(sgroup[p]), 0.f, 0.f);
 }
 
+// diagnostics (nrpn_nms_cells_stats): [0] records streamed, [1] pair slots (records x queries of the item, before the group / order / already-dropped filters), [2] exact IoU evaluations, [3] hits,
+// [4] work items; per mode: +0 cross, +8 adjacency
+static __device__ unsigned long long g_cl_stats[16];
+
+// obb_surely_not_above (box_iou.cuh) on two cull records held in registers / shared memory as float4 pairs {area, vol, zmin, zmax}, {cx, cy, rad,
+// cullable}: the same tests in the same order, written on scalars so that nothing is addressed through a pointer (the pointer form put both
+// records in local memory inside the pair loop: 16 G local-load sectors in one pass at 1 M boxes, profiles/r02_nms_cells_ncu.md).
+__device__ __forceinline__ bool cl_needs_exact(const float4 a0, const float4 a1, const float4 b0, const float4 b1, const float thr_m) {
+    if (!(__float_as_int(a1.w) && __float_as_int(b1.w))) return true;
+    const float dx = a1.x - b1.x, dy = a1.y - b1.y, rr = a1.z + b1.z;
+    const float d2 = dx * dx + dy * dy;
+    if (d2 > rr * rr) return false;
+    const float oz = fminf(a0.w, b0.w) - fmaxf(a0.z, b0.z);
+    if (!(oz >= 0.0f)) return false;
+    if (thr_m > 0.0f) {
+        const float vmax = fmaxf(a0.y, b0.y);
+        if (fminf(a0.y, b0.y) <= thr_m * vmax) return false;
+        if (oz <= thr_m * fmaxf(a0.w - a0.z, b0.w - b0.z)) return false;
+        const float lens = 2.0f * fminf(a1.z, b1.z) * (rr - sqrtf(d2));
+        if (NRPN_LENS_CULL && fminf(fminf(a0.x, b0.x), lens) * oz <= thr_m * vmax) return false;
+    }
+    return true;
+}
+
+// the decision of the sequential loop for one pair: a = the higher-scored ("picked") box, b = the candidate (operand order matters: the reference's
+// vertex sort is not symmetric).  Kept out of line so that the polygon clip's registers and stack stay out of the pair loop.
+__device__ __noinline__ bool cl_exact(const float* __restrict__ prep, int box_dim, float thr, int pj, int pq) {
+    const float* ap = prep + (size_t)pj * kPrepFloats;
+    const float* bp = prep + (size_t)pq * kPrepFloats;
+    if (box_dim == 7) { ObbPrep a, b; load_prep(ap, a); load_prep(bp, b); return !(iou3d_obb_full(a, b) <= thr); }
+    float aa[6], bb[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { aa[i] = ap[i]; bb[i] = bp[i]; }
+    return !(iou3d_aabb(aa, bb) <= thr);
+}
+
 struct PairArgs {
-    const float* prep; int box_dim; float thr;
+    const float* prep; int box_dim; float thr, thr_m;
     const BinGrid* grid;
     const int* qstart; const float4* qrecs; const int* item_start; const int2* items; int* work;
     const int* rstart; const float4* rrecs;
@@ -132,23 +168,15 @@ __global__ void __launch_bounds__(kPairThreads, 2) cl_pairs_kernel(const PairArg
     __shared__ int q_pos[kQB], q_grp[kQB], q_dead[kQB];
     __shared__ int r_beg[kMaxRows], r_pre[kMaxRows + 1];
     __shared__ int2 queue[kPairThreads / 32][64];
-    __shared__ int s_item, s_dead, s_scan[kPairThreads];
+    __shared__ int s_item, s_dead, s_scan[kPairThreads], s_win[3][6];
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const BinGrid& G = *A.grid;
     const int n_items = A.item_start[kBinCells];
-    const float thr = A.thr, thr_m = thr - 1e-3f;
+    const float thr = A.thr, thr_m = A.thr_m;
     const int box_dim = A.box_dim;
     const float* __restrict__ prep = A.prep;
 
-    auto exact = [&](int pj, int pq) -> bool {            // a = the higher-scored ("picked") box, b = the candidate: the sequential loop's operand order
-        const float* ap = prep + (size_t)pj * kPrepFloats;
-        const float* bp = prep + (size_t)pq * kPrepFloats;
-        if (box_dim == 7) { ObbPrep a, b; load_prep(ap, a); load_prep(bp, b); return !(iou3d_obb_full(a, b) <= thr); }
-        float aa[6], bb[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { aa[i] = ap[i]; bb[i] = bp[i]; }
-        return !(iou3d_aabb(aa, bb) <= thr);
-    };
+    auto exact = [&](int pj, int pq) -> bool { return cl_exact(prep, box_dim, thr, pj, pq); };
     auto on_hit = [&](int q, int pj) {
         if (MODE == 0) {
             if (atomicExch(&q_dead[q], 1) == 0) atomicAdd(&s_dead, 1);
@@ -160,12 +188,14 @@ __global__ void __launch_bounds__(kPairThreads, 2) cl_pairs_kernel(const PairArg
         }
     };
 
+    unsigned long long st_rec = 0, st_pair = 0, st_exact = 0, st_hit = 0, st_item = 0;
     for (;;) {
         __syncthreads();
         if (tid == 0) { s_item = atomicAdd(A.work, 1); s_dead = 0; }
         __syncthreads();
         const int item = s_item;
         if (item >= n_items) break;
+        if (tid == 0) ++st_item;
         const int2 it = A.items[item];
         const int cell = it.x;
         const int qb = A.qstart[cell] + it.y * kQB;
@@ -188,36 +218,37 @@ __global__ void __launch_bounds__(kPairThreads, 2) cl_pairs_kernel(const PairArg
             const float lox = hx == 0 ? -big : G.x0 + (float)hx * G.S[c], hix = hx == G.nx[c] - 1 ? big : G.x0 + (float)(hx + 1) * G.S[c];
             const float loy = hy == 0 ? -big : G.y0 + (float)hy * G.S[c], hiy = hy == G.ny[c] - 1 ? big : G.y0 + (float)(hy + 1) * G.S[c];
             const float loz = hz == 0 ? -big : G.z0 + (float)hz * G.Sz[c], hiz = hz == G.nz[c] - 1 ? big : G.z0 + (float)(hz + 1) * G.Sz[c];
-            int roff[4], wy_[3], ix0_[3], ix1_[3], iy0_[3], iz0_[3];
-            roff[0] = 0;
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci) {
-                const int cc = c - 1 + ci;
-                int rows = 0;
-                wy_[ci] = 1; ix0_[ci] = ix1_[ci] = iy0_[ci] = iz0_[ci] = 0;
+            // per neighbour class (c - 1, c, c + 1): the cells the queries' circles / z ranges can reach -> s_win[ci] = {rows, wy, ix0, ix1, iy0, iz0}
+            if (tid < 3) {
+                const int ci = tid, cc = c - 1 + ci;
+                int rows = 0, wy = 1, x0 = 0, x1 = 0, y0 = 0, z0 = 0;
                 if (cc >= 0 && cc < G.n_cls) {
                     const float R = (G.rmax[c] + G.rmax[cc]) * 1.0005f + 1e-3f, Rz = 0.5f * (G.dmax[c] + G.dmax[cc]) * 1.0005f + 1e-3f;
                     const float S = G.S[cc], Sz = G.Sz[cc];
-                    const int x0 = bin_clampi((int)floorf(fmaxf((lox - R - G.x0) / S, -1.0f)), G.nx[cc]);
-                    const int x1 = bin_clampi((int)floorf(fminf((hix + R - G.x0) / S, 1.0e6f)), G.nx[cc]);
-                    const int y0 = bin_clampi((int)floorf(fmaxf((loy - R - G.y0) / S, -1.0f)), G.ny[cc]);
+                    x0 = bin_clampi((int)floorf(fmaxf((lox - R - G.x0) / S, -1.0f)), G.nx[cc]);
+                    x1 = bin_clampi((int)floorf(fminf((hix + R - G.x0) / S, 1.0e6f)), G.nx[cc]);
+                    y0 = bin_clampi((int)floorf(fmaxf((loy - R - G.y0) / S, -1.0f)), G.ny[cc]);
                     const int y1 = bin_clampi((int)floorf(fminf((hiy + R - G.y0) / S, 1.0e6f)), G.ny[cc]);
-                    const int z0 = bin_clampi((int)floorf(fmaxf((loz - Rz - G.z0) / Sz, -1.0f)), G.nz[cc]);
+                    z0 = bin_clampi((int)floorf(fmaxf((loz - Rz - G.z0) / Sz, -1.0f)), G.nz[cc]);
                     const int z1 = bin_clampi((int)floorf(fminf((hiz + Rz - G.z0) / Sz, 1.0e6f)), G.nz[cc]);
-                    ix0_[ci] = x0; ix1_[ci] = x1; iy0_[ci] = y0; iz0_[ci] = z0; wy_[ci] = y1 - y0 + 1;
-                    rows = wy_[ci] * (z1 - z0 + 1);
+                    wy = y1 - y0 + 1;
+                    rows = wy * (z1 - z0 + 1);
                 }
-                roff[ci + 1] = roff[ci] + rows;
+                s_win[ci][0] = rows; s_win[ci][1] = wy; s_win[ci][2] = x0; s_win[ci][3] = x1; s_win[ci][4] = y0; s_win[ci][5] = z0;
             }
-            nrows = roff[3] + 1;                           // + the "everywhere" cell
+            __syncthreads();
+            const int rows0 = s_win[0][0], rows1 = s_win[1][0], rows2 = s_win[2][0];
+            const int off1 = rows0, off2 = rows0 + rows1, off3 = off2 + rows2;
+            nrows = off3 + 1;                              // + the "everywhere" cell
             for (int r = tid; r < nrows; r += kPairThreads) {
                 int beg, end;
-                if (r == roff[3]) { beg = A.rstart[kBinCells - 1]; end = A.rstart[kBinCells]; }
+                if (r == off3) { beg = A.rstart[kBinCells - 1]; end = A.rstart[kBinCells]; }
                 else {
-                    const int ci = r >= roff[2] ? 2 : (r >= roff[1] ? 1 : 0);
-                    const int local = r - roff[ci], iy = iy0_[ci] + local % wy_[ci], iz = iz0_[ci] + local / wy_[ci];
+                    const int ci = r >= off2 ? 2 : (r >= off1 ? 1 : 0);
+                    const int local = r - (ci == 2 ? off2 : (ci == 1 ? off1 : 0));
+                    const int wy = s_win[ci][1], iy = s_win[ci][4] + local % wy, iz = s_win[ci][5] + local / wy;
                     const int base = (c - 1 + ci) * kBinCellsPerClass + (iz * kBinMaxXY + iy) * kBinMaxXY;
-                    beg = A.rstart[base + ix0_[ci]]; end = A.rstart[base + ix1_[ci] + 1];
+                    beg = A.rstart[base + s_win[ci][2]]; end = A.rstart[base + s_win[ci][3] + 1];
                 }
                 r_beg[r] = beg; r_pre[r] = end - beg;
             }
@@ -255,14 +286,12 @@ __global__ void __launch_bounds__(kPairThreads, 2) cl_pairs_kernel(const PairArg
                 pj = __float_as_int(r2.x); gj = __float_as_int(r2.y);
             }
             if (!__any_sync(0xffffffffu, have)) continue;
-            const float ta[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            st_rec += have; st_pair += have ? nq : 0;
             for (int q = 0; q < nq; ++q) {
                 if (MODE == 0 && *(volatile int*)&q_dead[q]) continue;
                 bool c = false;
                 if (have && gj == q_grp[q] && (MODE == 0 || pj < q_pos[q])) {
-                    const float4 b0 = q_t0[q], b1 = q_t1[q];
-                    const float tb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                    c = !obb_surely_not_above(ta, tb, thr_m);
+                    c = cl_needs_exact(t0, t1, q_t0[q], q_t1[q], thr_m);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, c);
                 if (!m) continue;
@@ -271,7 +300,8 @@ __global__ void __launch_bounds__(kPairThreads, 2) cl_pairs_kernel(const PairArg
                 __syncwarp();
                 if (qn >= 32) {
                     const int2 e = queue[wid][lane];
-                    if (exact(e.y, q_pos[e.x])) on_hit(e.x, e.y);
+                    ++st_exact;
+                    if (exact(e.y, q_pos[e.x])) { on_hit(e.x, e.y); ++st_hit; }
                     const int rest = qn - 32;
                     const int2 moved = lane < rest ? queue[wid][32 + lane] : make_int2(0, 0);
                     __syncwarp();
@@ -284,13 +314,22 @@ __global__ void __launch_bounds__(kPairThreads, 2) cl_pairs_kernel(const PairArg
         if (qn > 0) {
             if (lane < qn) {
                 const int2 e = queue[wid][lane];
-                if (!(MODE == 0 && *(volatile int*)&q_dead[e.x]) && exact(e.y, q_pos[e.x])) on_hit(e.x, e.y);
+                if (!(MODE == 0 && *(volatile int*)&q_dead[e.x])) { ++st_exact; if (exact(e.y, q_pos[e.x])) { on_hit(e.x, e.y); ++st_hit; } }
             }
             __syncwarp();
         }
         if (MODE == 0) {
             __syncthreads();
             if (tid < nq && q_dead[tid]) A.state[q_pos[tid]] = ST_REMOVED;
+        }
+    }
+    {   // one atomic per warp and counter
+        unsigned long long v[5] = {st_rec, st_pair, st_exact, st_hit, st_item};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+            if (lane == 0 && v[k]) atomicAdd(&g_cl_stats[MODE * 8 + k], v[k]);
         }
     }
 }

@@ -29,6 +29,12 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 # ------------------------------------------------------------------------------------------------ boxes
+def set_nms_cull_mode(mode: int) -> None:
+    """0 (default): only exact-zero culls -- the keep set is provably the reference's.  1 / 3: + geometric ratio culls (+ footprint lens) from
+    16 384 boxes up: 4-5x faster at 1 M boxes, may differ from the reference in ~1e-5 of the boxes (include/nerf_rpn_b200.h)."""
+    lib().nrpn_set_nms_cull_mode(int(mode))
+
+
 def iou3d_pairs(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     a = _req(a, torch.float32, "a"); b = _req(b, torch.float32, "b")
     if a.shape != b.shape or a.dim() != 2 or a.shape[1] not in (6, 7):
@@ -232,9 +238,12 @@ def to_planar(x: torch.Tensor, z_shift: int = 0) -> torch.Tensor:
     return buf[..., :Z]
 
 
-def conv3d_wgrad(dys: Sequence[torch.Tensor], xs: Sequence[torch.Tensor], taps: Sequence[Sequence[int]]) -> torch.Tensor:
+def conv3d_wgrad(dys: Sequence[torch.Tensor], xs: Sequence[torch.Tensor], taps: Sequence[Sequence[int]], operands: str = "channels_last") -> torch.Tensor:
     """dW (taps, Cout, Cin) fp32 of a stride-1 'same' conv from channels-last 16-bit dY (N,X,Y,Z,Cout) and X (N,X,Y,Z,Cin), one pair per
-    pyramid level that shares the weights (tap z offsets in {-1, 0, +1})."""
+    pyramid level that shares the weights.  operands="channels_last": the tensors are read where they live (MN-major tcgen05 operands);
+    "planar": through transposed, z-shifted staging copies (tap z offsets in {-1, 0, +1}) -- the earlier path, kept for comparison."""
+    if operands == "channels_last":
+        return _conv3d_wgrad_cl(dys, xs, taps)
     d = WgradDesc()
     d.cout, d.cin, d.n_taps = int(dys[0].shape[-1]), int(xs[0].shape[-1]), len(taps)
     for t, off in enumerate(taps):
@@ -264,6 +273,33 @@ def conv3d_wgrad(dys: Sequence[torch.Tensor], xs: Sequence[torch.Tensor], taps: 
     need = lib().nrpn_conv3d_wgrad_workspace_bytes(ctypes.byref(d))
     if need == 0:
         raise ValueError("conv3d_wgrad: unsupported shape (cout % 128 == 0, cin % 32 == 0, cin <= 256)")
+    ws = _workspace(need, dys[0].device)
+    d.dw, d.workspace, d.workspace_bytes = dw.data_ptr(), ws.data_ptr(), ws.numel()
+    check(lib().nrpn_conv3d_wgrad(ctypes.byref(d), _stream()), "conv3d_wgrad")
+    return dw
+
+
+def _conv3d_wgrad_cl(dys, xs, taps):
+    d = WgradDesc()
+    d.cout, d.cin, d.n_taps = int(dys[0].shape[-1]), int(xs[0].shape[-1]), len(taps)
+    for t, off in enumerate(taps):
+        for k in range(3):
+            d.tap_off[t][k] = int(off[k])
+    d.n_levels = len(dys)
+    for i, (dy, x) in enumerate(zip(dys, xs)):
+        f16 = _act16(dy, "dy")
+        if _act16(x, "x") != f16 or dy.shape[0] != x.shape[0] or not (dy.is_contiguous() and x.is_contiguous()):
+            raise ValueError("conv3d_wgrad: dy and x must be contiguous (N,X,Y,Z,C) tensors of one dtype and batch")
+        lv = d.level[i]
+        lv.dy_cl, lv.x_cl, lv.ld_dy, lv.ld_x = dy.data_ptr(), x.data_ptr(), int(dy.shape[-1]), int(x.shape[-1])
+        lv.n, lv.x, lv.y, lv.z = int(dy.shape[0]), int(dy.shape[1]), int(dy.shape[2]), int(dy.shape[3])
+        lv.xx, lv.xy, lv.xz = int(x.shape[1]), int(x.shape[2]), int(x.shape[3])
+    d.act_fp16 = f16
+    d.operand_layout = 1
+    dw = torch.empty((len(taps), d.cout, d.cin), dtype=torch.float32, device=dys[0].device)
+    need = lib().nrpn_conv3d_wgrad_workspace_bytes(ctypes.byref(d))
+    if need == 0:
+        raise ValueError("conv3d_wgrad: unsupported shape (cout % 8 == 0, cin % 32 == 0, cin <= 256 or cin % 256 == 0)")
     ws = _workspace(need, dys[0].device)
     d.dw, d.workspace, d.workspace_bytes = dw.data_ptr(), ws.data_ptr(), ws.numel()
     check(lib().nrpn_conv3d_wgrad(ctypes.byref(d), _stream()), "conv3d_wgrad")

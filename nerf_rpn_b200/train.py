@@ -19,6 +19,7 @@ PyTorch here: buffers, streams, torch.distributed (NCCL) and the RNG of the samp
 There is no autograd graph and no eager-PyTorch compute on this path.
 """
 import ctypes
+import os
 import math
 from typing import List, Optional, Sequence
 
@@ -26,6 +27,9 @@ import torch
 
 from . import ops, packing
 from ._lib import RpnDesc, WgradDesc, check, lib
+
+
+_WGRAD_PLANAR = os.environ.get("NRPN_WGRAD_PLANAR", "0") == "1"      # earlier wgrad operand path (transposed staging copies), for A/B runs
 
 
 def _stream():
@@ -515,7 +519,14 @@ class _TrainPlan:
                 d.tap_off[t][k] = int(off[k])
         dzs = sorted({int(off[2]) for off in taps})
         d.n_levels = len(dys)
-        for i, (dy, x) in enumerate(zip(dys, xs)):
+        if not _WGRAD_PLANAR:                       # operands where they live: channels-last tensors through MN-major descriptors
+            for i, (dy, x) in enumerate(zip(dys, xs)):
+                lv = d.level[i]
+                lv.dy_cl, lv.x_cl, lv.ld_dy, lv.ld_x = dy.data_ptr(), x.data_ptr(), int(dy.shape[-1]), int(x.shape[-1])
+                lv.n, lv.x, lv.y, lv.z = int(dy.shape[0]), int(dy.shape[1]), int(dy.shape[2]), int(dy.shape[3])
+                lv.xx, lv.xy, lv.xz = int(x.shape[1]), int(x.shape[2]), int(x.shape[3])
+            d.operand_layout = 1
+        for i, (dy, x) in enumerate(zip(dys, xs) if _WGRAD_PLANAR else ()):
             n, X, Y, Zx = x.shape[0], x.shape[1], x.shape[2], x.shape[3]
             zl = max(Zx, dy.shape[3])
             zp = _ru(zl + 1, 8)

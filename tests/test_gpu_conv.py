@@ -311,8 +311,10 @@ def test_conv_data_gradient_runs_on_the_forward_kernel(ops, dims, cin, cout, k):
     ([(9, 12, 10), (5, 6, 5)], 128, 256, 3, torch.bfloat16),        # two levels sharing the weights, ragged bricks
     ([(6, 7, 9)], 256, 128, 1, torch.float16),
 ])
-def test_conv_weight_gradient_vs_autograd(ops, level_dims, cin, cout, k, dtype):
-    """dW of a stride-1 'same' Conv3d on tcgen05 (planar operands, K = voxels) against torch.autograd on the rounded operands."""
+@pytest.mark.parametrize("operands", ["channels_last", "planar"])
+def test_conv_weight_gradient_vs_autograd(ops, level_dims, cin, cout, k, dtype, operands):
+    """dW of a stride-1 'same' Conv3d on tcgen05 (K = voxels; channels-last tensors as MN-major operands, or the earlier planar staging copies)
+    against torch.autograd on the rounded operands."""
     g = torch.Generator(device="cuda").manual_seed(61)
     w = torch.zeros((cout, cin, k, k, k), device="cuda", requires_grad=True)
     dys, xs, ref = [], [], torch.zeros_like(w)
@@ -327,12 +329,12 @@ def test_conv_weight_gradient_vs_autograd(ops, level_dims, cin, cout, k, dtype):
         assert torch.equal(sh[..., :-1], x.permute(0, 4, 1, 2, 3)[..., 1:]) and sh[..., -1].abs().max().item() == 0
         xs.append(x); dys.append(dy)
     taps = [(a - k // 2, b - k // 2, c - k // 2) for a in range(k) for b in range(k) for c in range(k)]
-    dw = ops.conv3d_wgrad(dys, xs, taps)
+    dw = ops.conv3d_wgrad(dys, xs, taps, operands=operands)
     torch.cuda.synchronize()
     refp = ref.permute(2, 3, 4, 0, 1).reshape(len(taps), cout, cin)
     assert not torch.isnan(dw).any()
     assert (dw - refp).abs().max().item() <= 2e-3 * refp.abs().max().item(), _diagnose(dw, refp, "wgrad")
-    assert torch.equal(dw, ops.conv3d_wgrad(dys, xs, taps)), "weight gradients must be bit-reproducible"
+    assert torch.equal(dw, ops.conv3d_wgrad(dys, xs, taps, operands=operands)), "weight gradients must be bit-reproducible"
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])

@@ -21,8 +21,16 @@ scores = torch.rand(n, generator=g).cuda()
 grp = torch.randint(0, groups, (n,), generator=g).int().cuda() if groups > 1 else None
 keep, nk = ops.nms_device(boxes, scores, grp, 0.3)
 torch.cuda.synchronize()
+import ctypes
+from nerf_rpn_b200._lib import lib
+st = (ctypes.c_ulonglong * 16)()
+lib().nrpn_nms_cells_stats(st, 1)
 torch.cuda.nvtx.range_push("target")
 keep, nk = ops.nms_device(boxes, scores, grp, 0.3)
 torch.cuda.synchronize()
 torch.cuda.nvtx.range_pop()
 print("kept", int(nk.item()))
+lib().nrpn_nms_cells_stats(st, 0)
+names = ("records streamed", "pair tests", "exact IoU evaluations", "hits", "work items")
+for mode, off in (("cross", 0), ("adjacency", 8)):
+    print(mode, {k: int(st[off + i]) for i, k in enumerate(names)})
