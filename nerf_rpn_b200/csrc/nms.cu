@@ -278,7 +278,9 @@ constexpr int kPrepFloats = 16;
 // class's largest diameter / depth -- and a box only visits the cells its circle and z range can reach in its three classes.
 // Every candidate still goes through the same cull + exact polygon clip: the keep set is the sequential greedy loop's, bit for bit.
 constexpr int kBinMinBoxes = 65536;
-constexpr int kCellMinBoxes = 16384;     // cell-list path (nms_cells.cuh) from here; it shares the grid / box_cell buffers below
+constexpr int kCellMinBoxes = 12288;     // cell-list path (nms_cells.cuh) from here (above the 4 x 2 500 boxes of a scene's proposals, whose NMS runs
+                                         // inside the captured launch sequence); it shares the grid / box_cell buffers below
+constexpr int kRatioCullMinBoxes = 16384; // opt-in geometric culls (nrpn_set_nms_cull_mode) never apply below this
 static int cell_min_boxes() {            // NRPN_NMS_CELLS_MIN: where the cell-list path takes over (tuning runs); the ratio culls keep their 16 384 floor
     static const int v = [] { const char* e = getenv("NRPN_NMS_CELLS_MIN"); const int k = e ? atoi(e) : kCellMinBoxes; return k < 1024 ? 1024 : k; }();
     return v;
@@ -1096,7 +1098,7 @@ int nms_run(const float* boxes, int box_dim, const float* scores, const int32_t*
     // value (~1e-8 of the touching pairs; 1-3 of 85 702 kept boxes at 256 000 boxes).  They are therefore opt-in (bit 0: volume /
     // depth ratios, bit 1: + footprint lens), only ever applied from 16 384 boxes up, and the default keep set is provably the sequential loop's.
     const int cull_mode = g_nms_cull_mode.load(std::memory_order_relaxed);
-    const float thr_m = ((cull_mode & 1) && n >= kCellMinBoxes) ? thr - 1e-3f : 0.0f;
+    const float thr_m = ((cull_mode & 1) && n >= kRatioCullMinBoxes) ? thr - 1e-3f : 0.0f;
     {
         static std::atomic<int> applied{-1};
         const int lens = (cull_mode >> 1) & 1;
