@@ -22,6 +22,7 @@ scenes are independent, no collective on the inference path).  ONE
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess

@@ -982,6 +982,11 @@ __global__ void nms_emit_kernel(const unsigned long long* __restrict__ keys2, in
 
 #include "nms_cells.cuh"
 
+static int level_growth_pct() {          // level e -> e * pct / 100 (NRPN_NMS_LEVEL_GROWTH_PCT, tuning runs; >= 110)
+    static const int v = [] { const char* e = getenv("NRPN_NMS_LEVEL_GROWTH_PCT"); const int k = e ? atoi(e) : kLevelGrowth * 100; return k < 110 ? 110 : k; }();
+    return v;
+}
+
 static size_t cl_layout(void* base, int n, CellWs* out) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -1069,7 +1074,7 @@ static int nms_run_cells(const float* boxes, int box_dim, const float* scores, c
             if (h[0] == 0) break;
         }
         b = e;
-        e = (long long)e * kLevelGrowth > (long long)n ? n : e * kLevelGrowth;
+        { const long long nx = (long long)e * level_growth_pct() / 100; e = nx > (long long)n ? n : (int)nx; }
     }
     const int nblk = ceil_div(n, 1024);
     cl_keep_count_kernel<<<nblk, 1024, 0, st>>>(c.state, n, c.blk);

@@ -12,6 +12,7 @@ from nerf_rpn_b200 import ops  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 groups = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+ops.set_nms_cull_mode(int(sys.argv[3]) if len(sys.argv) > 3 else 0)
 g = torch.Generator().manual_seed(0)
 c = torch.rand(n, 3, generator=g) * torch.tensor([256.0, 256.0, 160.0])
 s = torch.rand(n, 3, generator=g) * 44 + 4
@@ -29,8 +30,10 @@ torch.cuda.nvtx.range_push("target")
 keep, nk = ops.nms_device(boxes, scores, grp, 0.3)
 torch.cuda.synchronize()
 torch.cuda.nvtx.range_pop()
-print("kept", int(nk.item()))
 lib().nrpn_nms_cells_stats(st, 0)
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record(); keep, nk = ops.nms_device(boxes, scores, grp, 0.3); b.record(); torch.cuda.synchronize()
+print("kept", int(nk.item()), "ms", round(a.elapsed_time(b), 2), "cull mode", int(lib().nrpn_get_nms_cull_mode()))
 names = ("records streamed", "pair tests", "exact IoU evaluations", "hits", "work items")
 for mode, off in (("cross", 0), ("adjacency", 8)):
     print(mode, {k: int(st[off + i]) for i, k in enumerate(names)})
