@@ -527,12 +527,43 @@ constexpr int kBgBlocks = 256;
 
 __global__ void __launch_bounds__(256) bias_grad_partial_kernel(const __nv_bfloat16* __restrict__ dy, long rows, int c, int ld, int fp16,
                                                                 float* __restrict__ partial) {
-    // block b sums rows b, b + gridDim.x, ...; thread t owns channels t, t + 256, ...
+    // block b sums rows b, b + gridDim.x, ...; thread t owns channels t, t + 256, ...  (any c / ld: the general form)
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
         float s = 0.f;
         for (long r = blockIdx.x; r < rows; r += gridDim.x) s += load_act(dy + (size_t)r * ld + ch, fp16);
         partial[(size_t)blockIdx.x * c + ch] = s;
     }
+}
+
+// c % 8 == 0, c <= 2048, 16-byte aligned rows: a thread owns 8 channels (one 128-bit load per row) and one of 256 / (c / 8) row lanes; the lanes of a
+// block are added in a fixed order through shared memory (bit-reproducible).  (The general form above reads 2 bytes per thread and row: 66 us per
+// call on the 187 k x 256 head gradients.)
+__global__ void __launch_bounds__(256) bias_grad_partial_vec_kernel(const __nv_bfloat16* __restrict__ dy, long rows, int c, int ld, int fp16,
+                                                                    float* __restrict__ partial) {
+    extern __shared__ float sm[];                            // [c]
+    const int cgs = c >> 3, lanes = 256 / cgs;
+    const int cg = threadIdx.x % cgs, lane = threadIdx.x / cgs;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
+    if (lane < lanes) {
+        for (long r = (long)blockIdx.x * lanes + lane; r < rows; r += (long)gridDim.x * lanes) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)r * ld + cg * 8));
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 f = unpack_act2(w[k], fp16); s[2 * k] += f.x; s[2 * k + 1] += f.y; }
+        }
+    }
+    for (int i = threadIdx.x; i < c; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    for (int l = 0; l < lanes; ++l) {
+        if (lane == l) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sm[cg * 8 + k] += s[k];
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < c; i += blockDim.x) partial[(size_t)blockIdx.x * c + i] = sm[i];
 }
 
 __global__ void bias_grad_final_kernel(const float* __restrict__ partial, int blocks, int c, float* __restrict__ db) {
@@ -572,8 +603,12 @@ int nrpn_bias_grad(const void* dy_cl, long rows, int c, int ld, int act_fp16, fl
     if (workspace_bytes < nrpn_bias_grad_workspace_bytes(c)) return NRPN_ERR_WORKSPACE;
     float* partial = reinterpret_cast<float*>(nrpn::align_up((size_t)workspace, 256));
     const int blocks = rows < nrpn::kBgBlocks ? (int)rows : nrpn::kBgBlocks;
-    nrpn::bias_grad_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_cl), rows, c, ld,
-                                                                          act_fp16 ? 1 : 0, partial);
+    if (c % 8 == 0 && c <= 2048 && ld % 8 == 0 && reinterpret_cast<uintptr_t>(dy_cl) % 16 == 0)
+        nrpn::bias_grad_partial_vec_kernel<<<blocks, 256, c * sizeof(float), (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_cl), rows, c, ld,
+                                                                                                  act_fp16 ? 1 : 0, partial);
+    else
+        nrpn::bias_grad_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_cl), rows, c, ld,
+                                                                              act_fp16 ? 1 : 0, partial);
     NRPN_LAUNCH_CHECK();
     nrpn::bias_grad_final_kernel<<<nrpn::ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(partial, blocks, c, db);
     NRPN_LAUNCH_CHECK();

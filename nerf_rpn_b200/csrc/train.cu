@@ -477,13 +477,29 @@ __global__ void __launch_bounds__(256) rpn_loss_kernel(const LossDev P, const lo
 // written: the buffers are zero-filled once at allocation.
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int taps, __nv_bfloat16* __restrict__ fwd,
                                                            int fwd_rows, int fwd_cols, __nv_bfloat16* __restrict__ bwd, int bwd_rows, int bwd_cols, int fp16) {
-    const size_t total = (size_t)cout * cin * taps;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int t = (int)(i % taps); size_t v = i / taps;
-        const int ci = (int)(v % cin); const int co = (int)(v / cin);
-        const float val = w[i];
-        store_act(fwd + ((size_t)t * fwd_rows + co) * fwd_cols + ci, val, fp16);
-        if (bwd) store_act(bwd + ((size_t)(taps - 1 - t) * bwd_rows + ci) * bwd_cols + co, val, fp16);
+    // A 16 (co) x 16 (ci) x taps tile through shared memory: the master weight is read in runs of 16 * taps contiguous floats, both operands are
+    // written in runs of 16 contiguous 16-bit values (one 32-byte sector).  (One thread per master-weight element wrote 2-byte values `rows * cols`
+    // apart: 1.1 ms per training step for 184 MB.)
+    extern __shared__ float tile[];                         // [16 co][16 ci][taps]
+    const int co0 = blockIdx.y * 16, ci0 = blockIdx.x * 16;
+    const int run = 16 * taps;
+    for (int i = threadIdx.x; i < 16 * run; i += blockDim.x) {
+        const int co = i / run, r = i - co * run;            // r = ci_local * taps + t
+        const int ci = r / taps;
+        tile[i] = (co0 + co < cout && ci0 + ci < cin) ? w[((size_t)(co0 + co) * cin + ci0) * taps + r] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16 * run; i += blockDim.x) {
+        const int ci = i & 15, co = (i >> 4) & 15, t = i >> 8;
+        if (co0 + co < cout && ci0 + ci < cin)
+            store_act(fwd + ((size_t)t * fwd_rows + co0 + co) * fwd_cols + ci0 + ci, tile[(co * 16 + ci) * taps + t], fp16);
+    }
+    if (bwd) {
+        for (int i = threadIdx.x; i < 16 * run; i += blockDim.x) {
+            const int co = i & 15, ci = (i >> 4) & 15, t = i >> 8;
+            if (co0 + co < cout && ci0 + ci < cin)
+                store_act(bwd + ((size_t)(taps - 1 - t) * bwd_rows + ci0 + ci) * bwd_cols + co0 + co, tile[(co * 16 + ci) * taps + t], fp16);
+        }
     }
 }
 
@@ -677,8 +693,12 @@ int nrpn_pack_weights(const float* w, int cout, int cin, int taps, void* fwd, in
     if (!w || !fwd || cout < 1 || cin < 1 || taps < 1 || fwd_rows < cout || fwd_cols < cin) return NRPN_ERR_INVALID;
     if (bwd && (bwd_rows < cin || bwd_cols < cout)) return NRPN_ERR_INVALID;
     const size_t total = (size_t)cout * cin * taps;
-    pack_weights_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(w, cout, cin, taps, reinterpret_cast<__nv_bfloat16*>(fwd), fwd_rows, fwd_cols,
-                                                                              reinterpret_cast<__nv_bfloat16*>(bwd), bwd_rows, bwd_cols, act_fp16 ? 1 : 0);
+    (void)total;
+    const dim3 grid((unsigned)ceil_div(cin, 16), (unsigned)ceil_div(cout, 16));
+    const size_t smem = (size_t)256 * taps * sizeof(float);
+    if (grid.y > 65535 || smem > 48 * 1024) return NRPN_ERR_UNSUPPORTED;        // taps <= 48 (3^3 = 27; the 7^3 stem goes through nrpn_gather_pack)
+    pack_weights_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(w, cout, cin, taps, reinterpret_cast<__nv_bfloat16*>(fwd), fwd_rows, fwd_cols,
+                                                                   reinterpret_cast<__nv_bfloat16*>(bwd), bwd_rows, bwd_cols, act_fp16 ? 1 : 0);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
