@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--skip-extras", action="store_true", help="exploration runs only: omit variants / train / reference_gpu legs")
     ap.add_argument("--scenes-per-step", type=int, default=int(os.environ.get("NRPN_SCENES_PER_STEP", "4")),
                     help="scenes per rank per step (one engine launch); weights are read once per step")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer (default): the headline; train: BASELINE config 4's training step as the line's value (the default line carries it under `train`)")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 5],
                     help="BASELINE.json configuration: 2 = the headline (default); 1 = VGG19 + anchor head on a 32^3 grid; 3 = Swin-S + FCOS (OBB) on "
                          "200x200x130; 5 = oriented IoU + NMS sweep 1k..1M boxes")
@@ -768,6 +770,116 @@ def run_config(args):
     return out
 
 
+def _train_reference_cpu(budget_s=40.0):
+    """The reference's own training step (model.train(): forward with targets, loss.backward()) on the host cores, on a 40x64x64 block (1/64 of a
+    scene) with 4 planted boxes -- a full scene's fp32 autograd graph needs ~100 GB."""
+    import torch
+    from oracle import ref_gpu
+    stub = os.path.join(ROOT, "tools", "ref_stub")
+    sys.path.insert(0, stub)
+    try:
+        ref_gpu.load(need_k1=False)
+    finally:
+        sys.path.remove(stub)
+    threads = min(os.cpu_count() or 1, 32)
+    torch.set_num_threads(threads)
+    m = ref_gpu.build_reference_model(rotated=True, seed=0).train()
+    sub = (40, 64, 64)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(4, *sub, generator=g)
+    ctr = torch.rand(4, 3, generator=g) * torch.tensor(sub, dtype=torch.float32) * 0.6 + torch.tensor(sub, dtype=torch.float32) * 0.2
+    gt = torch.cat([ctr, torch.rand(4, 3, generator=g) * 10 + 6, (torch.rand(4, 1, generator=g) - 0.5) * math.pi], 1)
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        _, losses, _ = m([x.clone()], [gt.clone()])
+        (losses["loss_objectness"] + 5.0 * losses["loss_rpn_box_reg"]).backward()
+    step()
+    times, t_all = [], time.perf_counter()
+    while len(times) < 3 and time.perf_counter() - t_all < budget_s:
+        t0 = time.perf_counter(); step(); times.append(time.perf_counter() - t0)
+    frac = (sub[0] * sub[1] * sub[2]) / float(DIMS[0] * DIMS[1] * DIMS[2])
+    sec = statistics.mean(times) / frac
+    return {"value": 1.0 / sec, "unit": "scenes/s", "cores": threads, "kind": "reference",
+            "sample": f"forward + loss + backward of the UNMODIFIED reference (oracle/_ref, fp32 autograd) on a {sub[0]}x{sub[1]}x{sub[2]} block = 1/64 scene, "
+                      f"scaled by voxels; {len(times)} runs, {threads} threads; no optimiser step"}
+
+
+def run_train(args):
+    """`--mode train`: BASELINE config 4 (ResNet50-FPN + anchor head --rotated_bbox, one 160x256x256 scene per rank and step, data parallel with ONE NCCL
+    all-reduce of the flat gradient bucket overlapped with the backward pass) as the headline value."""
+    import torch
+    import torch.distributed as dist
+    rank, local, world, barrier, max_over_ranks = _cfg_dist()
+    K, W = args.steps, max(args.warmup, 3)
+    burst, sustained, how = measured_peaks()
+    model = build_model(rotated=True, spread=0.0).cuda().train()
+    eng = model.train_engine(precision="bf16", lr=1e-4, weight_decay=0.01, clip_grad_norm=0.1, reg_loss_weight=5.0,
+                             process_group=dist.group.WORLD if world > 1 else None)
+    host = [synth_scene(rank * 1000 + i, "dataset").permute(1, 2, 3, 0).contiguous().pin_memory().permute(3, 0, 1, 2) for i in range(2)]
+    grids = [h.cuda()[None] for h in host]
+    gts = [[planted_boxes(rank * 1000 + i).cuda()] for i in range(2)]
+    gts_host = [planted_boxes(rank * 1000 + i).pin_memory() for i in range(2)]
+    for i in range(W):
+        eng.train_step(grids[i % 2], gts[i % 2])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        losses = eng.train_step(grids[i % 2], gts[i % 2])
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(K):
+        x = host[i % 2].cuda(non_blocking=True)[None]
+        t = [gts_host[i % 2].cuda(non_blocking=True)]
+        host_losses = eng.train_step(x, t).cpu()
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    plan = eng.plan(1, DIMS)
+    out = None
+    if rank == 0:
+        try:
+            cpu = {"value": None, "unit": "scenes/s", "cores": 0, "kind": "reference", "sample": "not timed (N > 1 or --skip-cpu-baseline)"} \
+                if (args.skip_cpu_baseline or world > 1) else _train_reference_cpu()
+        except Exception as e:                                        # noqa: BLE001
+            cpu = {"value": None, "unit": "scenes/s", "cores": 0, "kind": "reference", "sample": "unavailable: " + repr(e)}
+        tf = 3.0 * FLOPS_PER_SCENE * K / (ms * 1e-3) / 1e12          # forward + data gradient + weight gradient
+        out = {"metric": "training scenes/sec", "value": world * K / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "bf16 (activations / gradients; fp32 master weights, accumulation, optimiser state)", "data": "synthetic",
+               "config": {"workload": "BASELINE config 4: ResNet50-3D+FPN+anchor head --rotated_bbox, one 160x256x256x4 scene per rank per step, 16 planted OBBs, "
+                                      "256 sampled anchors, BCE + smooth-L1 (x5), clip_grad_norm 0.1, AdamW lr 1e-4 wd 0.01",
+                          "scenes_per_step_per_gpu": 1, "parallelism": f"dp{world}",
+                          "collective": (f"one NCCL all-reduce (sum) of the flat fp32 gradient bucket per step: {eng.n_params} parameters = {eng.n_params * 4 / 1e6:.0f} MB, "
+                                         f"in {getattr(plan, 'allreduce_calls', 0)} ranges launched on a communication stream as the backward pass finalises them")
+                                        if world > 1 else "none at N = 1 (the all-reduce is skipped)",
+                          "l2": "two 168 MB input grids alternate; ~6 GB of activations / gradients stream per step",
+                          "losses_last_step": [round(v, 5) for v in losses.tolist()]},
+               "clocks": clocks,
+               "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e / K,
+                       "h2d_bytes_per_step": int(host[0].numel() * 4 + gts_host[0].numel() * 4), "d2h_bytes_per_step": int(host_losses.numel() * 4),
+                       "api": "RPNTrainEngine.train_step (model.train_engine()): pinned host grid + boxes in, the two losses read back every step"},
+               "gpu_launches": None,
+               "roofline": {"bound": "tensor", "kernel": "whole training step (forward + dgrad + wgrad = 3 x the forward's convolution FLOPs)", "achieved": tf,
+                            "peak": sustained, "unit": "TFLOP/s", "frac": tf / sustained, "traffic": None, "flops_per_step": 3.0 * FLOPS_PER_SCENE,
+                            "peak_source": how + ", sustained figure", "note": "per-kernel split: profiles/r02_train_step_kernels.md"},
+               "cpu_baseline": cpu}
+        _emit(out)
+    del eng, model
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
 _RESULT_FD = None
 
 
@@ -791,6 +903,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "train":
+        run_train(args)
     elif args.config != 2:
         run_config(args)
     else:
