@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--skip-extras", action="store_true", help="exploration runs only: omit variants / train / reference_gpu legs")
     ap.add_argument("--scenes-per-step", type=int, default=int(os.environ.get("NRPN_SCENES_PER_STEP", "4")),
                     help="scenes per rank per step (one engine launch); weights are read once per step")
+    ap.add_argument("--cpu-train-baseline", action="store_true", help=argparse.SUPPRESS)       # child process of --mode train
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer (default): the headline; train: BASELINE config 4's training step as the line's value (the default line carries it under `train`)")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 5],
@@ -847,8 +848,14 @@ def run_train(args):
     out = None
     if rank == 0:
         try:
-            cpu = {"value": None, "unit": "scenes/s", "cores": 0, "kind": "reference", "sample": "not timed (N > 1 or --skip-cpu-baseline)"} \
-                if (args.skip_cpu_baseline or world > 1) else _train_reference_cpu()
+            if args.skip_cpu_baseline or world > 1:
+                cpu = {"value": None, "unit": "scenes/s", "cores": 0, "kind": "reference", "sample": "not timed (N > 1 or --skip-cpu-baseline)"}
+            else:       # in a child process without a visible GPU: the reference's OBB code hard-codes `.cuda()` (utils.py:412) and would mix devices
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-train-baseline"], capture_output=True, text=True, timeout=600,
+                                   env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+                if r.returncode != 0:
+                    raise RuntimeError(r.stderr[-300:])
+                cpu = json.loads(r.stdout.strip().splitlines()[-1])
         except Exception as e:                                        # noqa: BLE001
             cpu = {"value": None, "unit": "scenes/s", "cores": 0, "kind": "reference", "sample": "unavailable: " + repr(e)}
         tf = 3.0 * FLOPS_PER_SCENE * K / (ms * 1e-3) / 1e12          # forward + data gradient + weight gradient
@@ -901,7 +908,9 @@ def main():
     _RESULT_FD = os.dup(1)
     os.dup2(2, 1)
     args = parse()
-    if args.impl == "reference":
+    if args.cpu_train_baseline:
+        _emit(_train_reference_cpu())
+    elif args.impl == "reference":
         run_reference(args)
     elif args.mode == "train":
         run_train(args)

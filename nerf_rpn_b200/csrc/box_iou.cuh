@@ -308,11 +308,45 @@ __device__ __forceinline__ float iou3d_obb_full(const ObbPrep& a, const ObbPrep&
     return __fdiv_rn(i3, u3);
 }
 
+// Separating-axis test with a margin: true only when, along an edge direction of one of the two rectangles, the projections of the two corner sets are
+// further apart than 1e-3 of the boxes' size (+ 8e-6 of the coordinate magnitude) -- three orders of magnitude above anything fp32 rounding or the
+// reference's 1e-6 corner tolerance can move.  Then no edge pair crosses (t or u is far outside (0, 1), or the edges are parallel), no corner lies
+// inside the other rectangle, every mask of the reference is false, its vertex list is empty and it returns exactly 0 (box_intersection_2d.py:11-79,
+// sort_vert_kernel.cu:62: num_valid < 3 -> pad vertex only).  An exact-zero cull like the bounding-circle test, ~40 % sharper on touching circles.
+__device__ __forceinline__ bool obb_footprints_surely_disjoint(const ObbPrep& a, const ObbPrep& b) {
+    if (!(a.cullable && b.cullable)) return false;
+    const float scale = fmaxf(fmaxf(fabsf(a.cx), fabsf(a.cy)), fmaxf(fabsf(b.cx), fabsf(b.cy)));
+    const float margin = 1e-3f * (a.rad + b.rad) + 8e-6f * scale;
+#pragma unroll
+    for (int ax = 0; ax < 4; ++ax) {
+        const float* s = ax < 2 ? a.c : b.c;
+        const int k = (ax & 1) ? 3 : 1;                         // edge corner0 -> corner1 and corner0 -> corner3
+        const float ex = s[2 * k] - s[0], ey = s[2 * k + 1] - s[1];
+        const float len = sqrtf(ex * ex + ey * ey);
+        float amin = 3.0e38f, amax = -3.0e38f, bmin = 3.0e38f, bmax = -3.0e38f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float pa = a.c[2 * i] * ex + a.c[2 * i + 1] * ey, pb = b.c[2 * i] * ex + b.c[2 * i + 1] * ey;
+            amin = fminf(amin, pa); amax = fmaxf(amax, pa); bmin = fminf(bmin, pb); bmax = fmaxf(bmax, pb);
+        }
+        const float gap = fmaxf(bmin - amax, amin - bmax);
+        if (len > 0.0f && gap > margin * len) return true;
+    }
+    return false;
+}
+
+// NMS decision for one pair: does the picked box a suppress the candidate b at threshold thr?  (`!(iou <= thr)` keeps the reference's NaN behaviour.)
+__device__ __forceinline__ bool obb_suppresses(const ObbPrep& a, const ObbPrep& b, float thr) {
+    if (thr >= 0.0f && obb_footprints_surely_disjoint(a, b)) return false;      // the reference computes exactly 0, and !(0 <= thr) is false
+    return !(iou3d_obb_full(a, b) <= thr);
+}
+
 __device__ __forceinline__ float iou3d_obb(const ObbPrep& a, const ObbPrep& b, bool allow_cull) {
     if (allow_cull && a.cullable && b.cullable) {
         const float dx = a.cx - b.cx, dy = a.cy - b.cy, rr = a.rad + b.rad;
         if (dx * dx + dy * dy > rr * rr) return 0.0f;           // footprints cannot touch -> reference yields exactly 0
         if (a.zmin > b.zmax || b.zmin > a.zmax) return 0.0f;     // z_overlap clamps to 0
+        if (obb_footprints_surely_disjoint(a, b)) return 0.0f;    // no vertex at all -> intersection exactly 0
     }
     return iou3d_obb_full(a, b);
 }

@@ -493,8 +493,7 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float* __r
         ObbPrep a, b;
         load_prep(sr[r], a);
         load_prep(sp[c], b);
-        const float iou = iou3d_obb_full(a, b);
-        if (!(iou <= thr)) atomicOr(&sbits[r], 1ull << c);
+        if (obb_suppresses(a, b, thr)) atomicOr(&sbits[r], 1ull << c);
     }
     __syncthreads();
     if (t < 64 && row0 + t < n) mask[(size_t)(row0 + t) * W + cb] = sbits[t];
@@ -645,7 +644,7 @@ __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict_
                     if (qn >= 32) {
                         ObbPrep a;
                         load_prep(prep + (size_t)queue[wid][lane] * kPrepFloats, a);
-                        const bool hit = !(iou3d_obb_full(a, b) <= thr);
+                        const bool hit = obb_suppresses(a, b, thr);
                         if (__any_sync(0xffffffffu, hit)) { sup = true; done = true; break; }
                         const int rest = qn - 32;
                         const int moved = lane < rest ? queue[wid][32 + lane] : 0;
@@ -664,7 +663,7 @@ __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict_
         if (lane < qn) {
             ObbPrep a;
             load_prep(prep + (size_t)queue[wid][lane] * kPrepFloats, a);
-            hit = !(iou3d_obb_full(a, b) <= thr);
+            hit = obb_suppresses(a, b, thr);
         }
         if (__any_sync(0xffffffffu, hit)) sup = true;
     }
@@ -859,7 +858,7 @@ __global__ void __launch_bounds__(256, 2) nms_cross_binned_kernel(const float* _
 
     auto exact = [&](int pos) -> bool {                 // the decision of the sequential loop for one kept box
         const float* ap = prep + (size_t)pos * kPrepFloats;
-        if (box_dim == 7) { ObbPrep a, b; load_prep(ap, a); load_prep(bp, b); return !(iou3d_obb_full(a, b) <= thr); }
+        if (box_dim == 7) { ObbPrep a, b; load_prep(ap, a); load_prep(bp, b); return obb_suppresses(a, b, thr); }
         float aa[6], bb[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) { aa[i] = ap[i]; bb[i] = bp[i]; }

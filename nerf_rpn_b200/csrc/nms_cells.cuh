@@ -145,7 +145,7 @@ __device__ __forceinline__ bool cl_needs_exact(const float4 a0, const float4 a1,
 __device__ __noinline__ bool cl_exact(const float* __restrict__ prep, int box_dim, float thr, int pj, int pq) {
     const float* ap = prep + (size_t)pj * kPrepFloats;
     const float* bp = prep + (size_t)pq * kPrepFloats;
-    if (box_dim == 7) { ObbPrep a, b; load_prep(ap, a); load_prep(bp, b); return !(iou3d_obb_full(a, b) <= thr); }
+    if (box_dim == 7) { ObbPrep a, b; load_prep(ap, a); load_prep(bp, b); return obb_suppresses(a, b, thr); }
     float aa[6], bb[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) { aa[i] = ap[i]; bb[i] = bp[i]; }
