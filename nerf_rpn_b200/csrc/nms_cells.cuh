@@ -140,12 +140,25 @@ __device__ __forceinline__ bool cl_needs_exact(const float4 a0, const float4 a1,
     return true;
 }
 
+// obb_footprints_surely_disjoint (box_iou.cuh) straight on two prepared records (16 floats: 8 corner coordinates, area, vol, zmin, zmax, cx, cy, rad,
+// cullable): the second filter stage, run on full warps of queued pairs before the exact clip
+__device__ __forceinline__ bool cl_sat_disjoint(const float* __restrict__ pa, const float* __restrict__ pb) {
+    ObbPrep a, b;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(pa)), a1 = __ldg(reinterpret_cast<const float4*>(pa) + 1), a3 = __ldg(reinterpret_cast<const float4*>(pa) + 3);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(pb)), b1 = __ldg(reinterpret_cast<const float4*>(pb) + 1), b3 = __ldg(reinterpret_cast<const float4*>(pb) + 3);
+    a.c[0] = a0.x; a.c[1] = a0.y; a.c[2] = a0.z; a.c[3] = a0.w; a.c[4] = a1.x; a.c[5] = a1.y; a.c[6] = a1.z; a.c[7] = a1.w;
+    b.c[0] = b0.x; b.c[1] = b0.y; b.c[2] = b0.z; b.c[3] = b0.w; b.c[4] = b1.x; b.c[5] = b1.y; b.c[6] = b1.z; b.c[7] = b1.w;
+    a.cx = a3.x; a.cy = a3.y; a.rad = a3.z; a.cullable = __float_as_int(a3.w);
+    b.cx = b3.x; b.cy = b3.y; b.rad = b3.z; b.cullable = __float_as_int(b3.w);
+    return obb_footprints_surely_disjoint(a, b);
+}
+
 // the decision of the sequential loop for one pair: a = the higher-scored ("picked") box, b = the candidate (operand order matters: the reference's
 // vertex sort is not symmetric).  Kept out of line so that the polygon clip's registers and stack stay out of the pair loop.
 __device__ __noinline__ bool cl_exact(const float* __restrict__ prep, int box_dim, float thr, int pj, int pq) {
     const float* ap = prep + (size_t)pj * kPrepFloats;
     const float* bp = prep + (size_t)pq * kPrepFloats;
-    if (box_dim == 7) { ObbPrep a, b; load_prep(ap, a); load_prep(bp, b); return obb_suppresses(a, b, thr); }
+    if (box_dim == 7) { ObbPrep a, b; load_prep(ap, a); load_prep(bp, b); return !(iou3d_obb_full(a, b) <= thr); }      // the SAT stage ran before
     float aa[6], bb[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) { aa[i] = ap[i]; bb[i] = bp[i]; }
@@ -167,7 +180,8 @@ __global__ void __launch_bounds__(kPairThreads, 2) cl_pairs_kernel(const PairArg
     __shared__ float4 q_t0[kQB], q_t1[kQB];
     __shared__ int q_pos[kQB], q_grp[kQB], q_dead[kQB];
     __shared__ int r_beg[kMaxRows], r_pre[kMaxRows + 1];
-    __shared__ int2 queue[kPairThreads / 32][64];
+    __shared__ int2 queue[kPairThreads / 32][64];        // stage 1: survivors of the cheap necessary conditions
+    __shared__ int2 queue2[kPairThreads / 32][64];       // stage 2: survivors of the separating-axis test, waiting for the exact clip
     __shared__ int s_item, s_dead, s_scan[kPairThreads], s_win[3][6];
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const BinGrid& G = *A.grid;
@@ -270,7 +284,40 @@ __global__ void __launch_bounds__(kPairThreads, 2) cl_pairs_kernel(const PairArg
         }
         const int total = r_pre[nrows];
         // ---- stream the records: one per thread and step; warps run independently from here
-        int qn = 0;
+        int qn = 0, qn2 = 0;
+        const bool obb = box_dim == 7 && thr >= 0.0f;
+        auto drain2 = [&](int count) {                       // exact clip on the first `count` (<= 32) entries of stage 2
+            if (lane < count) {
+                const int2 e = queue2[wid][lane];
+                if (!(MODE == 0 && *(volatile int*)&q_dead[e.x])) { ++st_exact; if (exact(e.y, q_pos[e.x])) { on_hit(e.x, e.y); ++st_hit; } }
+            }
+            __syncwarp();
+            const int rest = qn2 - count;
+            const int2 moved = lane < rest ? queue2[wid][count + lane] : make_int2(0, 0);
+            __syncwarp();
+            if (lane < rest) queue2[wid][lane] = moved;
+            qn2 = rest;
+            __syncwarp();
+        };
+        auto drain1 = [&](int count) {                       // separating-axis test on the first `count` (<= 32) entries of stage 1 -> stage 2
+            bool keep = false;
+            int2 e = make_int2(0, 0);
+            if (lane < count) {
+                e = queue[wid][lane];
+                keep = !(MODE == 0 && *(volatile int*)&q_dead[e.x]);
+                if (keep && obb) keep = !cl_sat_disjoint(prep + (size_t)e.y * kPrepFloats, prep + (size_t)q_pos[e.x] * kPrepFloats);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) queue2[wid][qn2 + __popc(m & ((1u << lane) - 1u))] = e;
+            qn2 += __popc(m);
+            const int rest = qn - count;
+            const int2 moved = lane < rest ? queue[wid][count + lane] : make_int2(0, 0);
+            __syncwarp();
+            if (lane < rest) queue[wid][lane] = moved;
+            qn = rest;
+            __syncwarp();
+            if (qn2 >= 32) drain2(32);
+        };
         for (int base = 0; base < total; base += kPairThreads) {
             if (MODE == 0 && *(volatile int*)&s_dead >= nq) break;
             const int gidx = base + tid;
@@ -298,26 +345,11 @@ __global__ void __launch_bounds__(kPairThreads, 2) cl_pairs_kernel(const PairArg
                 if (c) queue[wid][qn + __popc(m & ((1u << lane) - 1u))] = make_int2(q, pj);
                 qn += __popc(m);
                 __syncwarp();
-                if (qn >= 32) {
-                    const int2 e = queue[wid][lane];
-                    ++st_exact;
-                    if (exact(e.y, q_pos[e.x])) { on_hit(e.x, e.y); ++st_hit; }
-                    const int rest = qn - 32;
-                    const int2 moved = lane < rest ? queue[wid][32 + lane] : make_int2(0, 0);
-                    __syncwarp();
-                    if (lane < rest) queue[wid][lane] = moved;
-                    qn = rest;
-                    __syncwarp();
-                }
+                if (qn >= 32) drain1(32);
             }
         }
-        if (qn > 0) {
-            if (lane < qn) {
-                const int2 e = queue[wid][lane];
-                if (!(MODE == 0 && *(volatile int*)&q_dead[e.x])) { ++st_exact; if (exact(e.y, q_pos[e.x])) { on_hit(e.x, e.y); ++st_hit; } }
-            }
-            __syncwarp();
-        }
+        if (qn > 0) drain1(qn);
+        if (qn2 > 0) drain2(qn2);
         if (MODE == 0) {
             __syncthreads();
             if (tid < nq && q_dead[tid]) A.state[q_pos[tid]] = ST_REMOVED;

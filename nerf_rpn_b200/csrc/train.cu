@@ -96,22 +96,22 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const __nv_bfloat16* _
 template <int MODE>
 __global__ void chan_reduce_final_kernel(const float* __restrict__ partial, int blocks, int c, long rows, float eps, float* __restrict__ out,
                                          float* __restrict__ running_mean, float* __restrict__ running_var, float momentum) {
-    // 32 channels per CTA, 8 threads per channel: thread (kl, ch) sums the partials of blocks kl, kl + 8, ...; the eight sums are added in a
-    // fixed order (bit-reproducible).  (One thread per channel walked all 296 partials alone: 46 us per call, 106 calls per training step.)
-    __shared__ double red[2][8][32];
-    const int cl = threadIdx.x & 31, kl = threadIdx.x >> 5;
-    const int ch = blockIdx.x * 32 + cl;
+    // 8 channels per CTA, 32 threads per channel: thread (kl, ch) sums the partials of blocks kl, kl + 32, ...; the 32 sums are added in a fixed
+    // order (bit-reproducible).  (One thread per channel walked all 296 partials alone: 46 us per call, 106 calls per training step.)
+    __shared__ double red[2][32][8];
+    const int cl = threadIdx.x & 7, kl = threadIdx.x >> 3;
+    const int ch = blockIdx.x * 8 + cl;
     double a = 0.0, b = 0.0;
     if (ch < c) {
-#pragma unroll 4
-        for (int k = kl; k < blocks; k += 8) { a += (double)partial[((size_t)k * 2) * c + ch]; b += (double)partial[((size_t)k * 2 + 1) * c + ch]; }
+#pragma unroll 5
+        for (int k = kl; k < blocks; k += 32) { a += (double)partial[((size_t)k * 2) * c + ch]; b += (double)partial[((size_t)k * 2 + 1) * c + ch]; }
     }
     red[0][kl][cl] = a; red[1][kl][cl] = b;
     __syncthreads();
     if (kl != 0 || ch >= c) return;
     a = 0.0; b = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { a += red[0][k][cl]; b += red[1][k][cl]; }
+    for (int k = 0; k < 32; ++k) { a += red[0][k][cl]; b += red[1][k][cl]; }
     if (MODE == 0) {
         const double mean = a / (double)rows;
         double var = b / (double)rows - mean * mean;
@@ -585,7 +585,7 @@ int nrpn_bn_stats(const void* y, long rows, int c, int act_fp16, float eps, floa
     chan_reduce_kernel<0><<<blocks, 256, 2 * c * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(y), nullptr, nullptr, rows, c, nullptr, 0,
                                                                      act_fp16 ? 1 : 0, partial);
     NRPN_LAUNCH_CHECK();
-    chan_reduce_final_kernel<0><<<ceil_div(c, 32), 256, 0, st>>>(partial, blocks, c, rows, eps, stats, running_mean, running_var, momentum);
+    chan_reduce_final_kernel<0><<<ceil_div(c, 8), 256, 0, st>>>(partial, blocks, c, rows, eps, stats, running_mean, running_var, momentum);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
@@ -612,7 +612,7 @@ int nrpn_bn_backward(const void* dout, const void* act, const void* y, void* dy,
     chan_reduce_kernel<1><<<blocks, 256, 2 * c * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(act),
                                                                      reinterpret_cast<const __nv_bfloat16*>(y), rows, c, stats, relu ? 1 : 0, f, partial);
     NRPN_LAUNCH_CHECK();
-    chan_reduce_final_kernel<1><<<ceil_div(c, 32), 256, 0, st>>>(partial, blocks, c, rows, 0.f, sums, nullptr, nullptr, 0.f);
+    chan_reduce_final_kernel<1><<<ceil_div(c, 8), 256, 0, st>>>(partial, blocks, c, rows, 0.f, sums, nullptr, nullptr, 0.f);
     NRPN_LAUNCH_CHECK();
     const size_t chunks = (size_t)rows * (c / 8);
     bn_backward_apply_kernel<<<grid1d(chunks, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<const __nv_bfloat16*>(act),

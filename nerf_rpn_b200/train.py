@@ -141,8 +141,11 @@ class RPNTrainEngine:
         bb, rpn = model.backbone, model.rpn
         if type(bb).__name__ != "ResNet_FPN_256":
             raise NotImplementedError("nerf_rpn_b200: the training engine implements ResNet_FPN_256 + RPNHead (BASELINE config 4)")
-        if rpn.reg_loss_type != "smooth_l1":
-            raise NotImplementedError("nerf_rpn_b200: reg_loss_type other than smooth_l1 is not implemented in the training engine")
+        if rpn.reg_loss_type not in ("smooth_l1", "iou", "linear_iou"):
+            raise NotImplementedError("nerf_rpn_b200: reg_loss_type giou / diou is not implemented (cal_giou_3d / cal_diou_3d are not built)")
+        if rpn.reg_loss_type != "smooth_l1" and not rpn.rotate:
+            raise NotImplementedError("nerf_rpn_b200: the IoU-type regression losses exist for --rotated_bbox only (as in the reference, rpn.py:216-217)")
+        self.reg_loss_type = rpn.reg_loss_type
         self.model, self.bb, self.head, self.rpn = model, bb, rpn.head, rpn
         self.device = next(bb.parameters()).device
         if self.device.type != "cuda":
@@ -682,7 +685,56 @@ class _TrainPlan:
             desc = ops.make_rpn_desc(preds, self.feat_dims, self.strides, eng.cells, eng.A, eng.rotated, 1, 1, 0.5, 0.0, 1e-3, self.dims)
             arr = (ctypes.c_void_p * len(dpreds))(*[t.data_ptr() for t in dpreds])
             check(L.nrpn_rpn_loss(ctypes.byref(desc), arr, _p(pos), int(pos.numel()), _p(neg), int(neg.numel()), _p(gtp), max(norm, 1.0), float(w_obj),
-                                  float(w_reg), float(eng.loss_scale), _p(eng.losses), None, self.f16, _stream()), "rpn_loss")
+                                  float(w_reg) if eng.reg_loss_type == "smooth_l1" else 0.0, float(eng.loss_scale), _p(eng.losses), None, self.f16, _stream()),
+                  "rpn_loss")
+        if eng.reg_loss_type != "smooth_l1":
+            self._iou_reg_loss(float(w_reg), max(norm, 1.0))
+
+    # ---- IoU-type regression loss (RotatedIOULoss, rpn.py:133-165, reg_loss_type "iou" / "linear_iou") on the <= 128 sampled positives per mesh
+    def _split_anchor_index(self, idx):
+        """flat anchor index of one mesh -> (level, voxel within the level, anchor): index = level offset + voxel * A + a (rpn.py:20-27)."""
+        A = self.eng.A
+        vox = [d[0] * d[1] * d[2] for d in self.feat_dims]
+        bounds = torch.tensor([0] + [v * A for v in vox], device=idx.device).cumsum(0)
+        level = torch.bucketize(idx, bounds[1:], right=True)
+        local = idx - bounds[level]
+        return level, local // A, local % A
+
+    def _iou_reg_loss(self, w_reg, norm):
+        """loss = sum over sampled positives of -log((I + 1) / (U + 1)) (or 1 - ...) / number of sampled anchors, on the boxes DECODED from the head's
+        deltas; its gradient w.r.t. the deltas (autograd through decode + the IoU Function) is written into d(pred) like the fused kernel does."""
+        from .model.coder_torch import decode_obb
+        from .model.rotated_iou.oriented_iou_loss import cal_iou_3d
+        eng = self.eng
+        A, code = eng.A, 8
+        anchors = self._anchors()
+        total = torch.zeros((), dtype=torch.float32, device=eng.device)
+        for i, (pos, neg, gtp) in enumerate(self.last_samples):
+            if pos.numel() == 0:
+                continue
+            level, vox, a = self._split_anchor_index(pos)
+            cols = (A + a * code).view(-1, 1) + torch.arange(code, device=pos.device).view(1, -1)
+            deltas = torch.empty((pos.numel(), code), dtype=torch.float32, device=eng.device)
+            for l, p in enumerate(self.pred_levels):
+                m = level == l
+                if m.any():
+                    deltas[m] = p[i].reshape(-1, 128)[vox[m].view(-1, 1), cols[m]]
+            with torch.enable_grad():
+                d = deltas.detach().requires_grad_(True)
+                boxes = decode_obb(anchors[pos], d)
+                iou, _, _, _, union = cal_iou_3d(boxes.unsqueeze(0), gtp.unsqueeze(0), verbose=True)
+                ratio = (iou * union + 1.0) / (union + 1.0)
+                losses = -torch.log(ratio) if eng.reg_loss_type == "iou" else 1.0 - ratio
+                loss = losses.sum() / norm
+                (g,) = torch.autograd.grad(loss, d)
+            total = total + loss.detach()
+            if w_reg != 0.0:
+                g = (g * (w_reg * eng.loss_scale)).to(self.dpred.dtype)
+                for l, dp in enumerate(self.dpred_levels):
+                    m = level == l
+                    if m.any():
+                        dp[i].reshape(-1, 128)[vox[m].view(-1, 1), cols[m]] = g[m]
+        eng.losses[1] = total
 
     def backward(self):
         """Backward launches in reverse construction order.  Gradients become final from the END of the flat bucket (head, FPN) towards

@@ -196,6 +196,55 @@ def test_full_size_feature_maps_vs_reference_fp32_on_this_gpu(dims, precision):
     assert max(rels) <= FEATURE_TOL[precision], rels
 
 
+SWIN_TOL = {"fp16_w2": 2.5e-3, "fp16": 2.5e-3, "bf16": 2.0e-2}
+
+
+@pytest.mark.parametrize("precision", ["fp16_w2", "bf16"])
+def test_config3_swin_s_fcos_full_size_vs_reference_on_this_gpu(precision):
+    """BASELINE config 3 at ITS size (Swin-S 3D window attention + FPN + FCOS head, --rotated_bbox, one 200x200x130 grid): pyramid features and the
+    FCOS head's three outputs of OUR modules against the reference's own modules in fp32 on this GPU (same seed-0 state_dict), norm-wise."""
+    import argparse
+    from nerf_rpn_b200.model.fcos.fcos import FCOSOverNeRF
+    from nerf_rpn_b200.model.feature_extractor import SwinTransformer_FPN
+    ref = ref_gpu.load()
+    dims = (200, 200, 130)
+    kw = dict(patch_size=[4, 4, 4], embed_dim=96, depths=[2, 2, 18, 2], num_heads=[3, 6, 12, 24], window_size=[4, 4, 4], stochastic_depth_prob=0.0,
+              expand_dim=True)
+    fa = argparse.Namespace(num_convs=4, norm_reg_targets=True, centerness_on_reg=True, rotated_bbox=True, pre_nms_thresh=0.0, pre_nms_top_n=2500,
+                            nms_thresh=0.3, fpn_post_nms_top_n=2500, min_size=0.0)
+    torch.manual_seed(0)
+    rbb = ref.feature_extractor.SwinTransformer_FPN(**kw).cuda().eval()
+    rhead = ref.fcos.FCOSHead(256, 4, [4, 8, 16, 32], norm_reg_targets=True, centerness_on_reg=True, use_obb=True).cuda().eval()
+    g = torch.Generator().manual_seed(1000)
+    x = torch.rand(*dims, 4, generator=g).permute(3, 0, 1, 2).contiguous()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            rf = rbb(x.cuda()[None])
+            rl, rr, rc = rhead(list(rf))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    bb = SwinTransformer_FPN(**kw)
+    bb.load_state_dict({k: v.cpu() for k, v in rbb.state_dict().items()})
+    model = FCOSOverNeRF(fa, bb, [4, 8, 16, 32], precision=precision)
+    model.fcos_module.head.load_state_dict({k: v.cpu() for k, v in rhead.state_dict().items()})
+    model = model.cuda().eval()
+    with torch.no_grad():
+        boxes, _, scores = model([x.cuda()])
+        plan = model.engine()._plans[next(iter(model.engine()._plans))]
+        feats = [f[..., :256].permute(0, 4, 1, 2, 3).float() for f in plan.features]      # channels-last pyramid buffers of the plan
+    torch.cuda.synchronize()
+    assert boxes[0].shape[0] > 0 and torch.isfinite(boxes[0]).all()
+    rels = []
+    for i, (f, r) in enumerate(zip(feats, rf)):
+        assert tuple(f.shape) == tuple(r.shape), (f.shape, r.shape)
+        rel = ((f - r).norm() / r.norm()).item()
+        rels.append(rel)
+        print(f"config 3 [{precision}] P{i + 2} {tuple(r.shape[2:])}: ours vs reference-fp32 {rel:.3e}")
+    assert max(rels) <= SWIN_TOL[precision], rels
+
+
 # ------------------------------------------------------------------------------------------------ the unmodified driver (row b)
 def _write_scenes(tmp, n_scenes, dims, n_gt=12):
     import pandas as pd

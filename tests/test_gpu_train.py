@@ -292,6 +292,16 @@ def _grad_metrics(grads, ref):
 
 @pytest.mark.parametrize("layers,rotated,precision", [((2, 1, 1, 1), True, "fp16"), ((2, 1, 1, 1), False, "bf16"), ((3, 4, 6, 3), True, "bf16"), ((3, 4, 6, 3), False, "fp16")])
 def test_training_step_vs_reference_autograd(layers, rotated, precision):
+    _training_step_parity(layers, rotated, precision, (64, 96, 80), 12)
+
+
+def test_training_step_full_size_config4_vs_reference_autograd():
+    """BASELINE config 4 at ITS size: ResNet50-FPN + anchor head --rotated_bbox, one 160x256x256 scene, 16 planted boxes, bf16 engine against the
+    reference's fp32 autograd and its own bf16 autocast run on this GPU (same criteria as the 64x96x80 cases)."""
+    _training_step_parity((3, 4, 6, 3), True, "bf16", (160, 256, 256), 16)
+
+
+def _training_step_parity(layers, rotated, precision, dims, n_gt):
     """One training step at 64x96x80 with 12 planted boxes against the UNMODIFIED reference (oracle/_ref: its modules in train mode, its own
     compute_loss, torch autograd, clip_grad_norm_, torch.optim.AdamW) on this GPU, same seed-0 weights, same sampled anchors.
     What "parity" can mean here was MEASURED (tools/debug_train.py, profiles/r02_debug_train.log): with BatchNorm on batch statistics and the
@@ -307,8 +317,7 @@ def test_training_step_vs_reference_autograd(layers, rotated, precision):
     from nerf_rpn_b200.model.feature_extractor import Bottleneck, ResNet_FPN_256
     from nerf_rpn_b200.model.nerf_rpn import NeRFRegionProposalNetwork
     from nerf_rpn_b200.train import RPNTrainEngine
-    dims = (64, 96, 80)
-    grid, gt = _planted(dims, 12, 11, rotated)
+    grid, gt = _planted(dims, n_gt, 11, rotated)
     grid, gt = grid.cuda(), gt.cuda()
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
@@ -335,7 +344,7 @@ def test_training_step_vs_reference_autograd(layers, rotated, precision):
     grads = [eng.grad_of(p).view(p.shape).clone() * inv for p in params]
     cos_o, rel_o, per_o = _grad_metrics(grads, r32)
     cos_a, rel_a, per_a = _grad_metrics(rac["grads"], r32)
-    tag = f"[{layers} {'OBB' if rotated else 'AABB'} {precision}]"
+    tag = f"[{layers} {'OBB' if rotated else 'AABB'} {precision} {dims[0]}x{dims[1]}x{dims[2]}]"
     print(f"{tag} sampler reproduces the reference's draws: {same} ({pos_o.numel()} pos / {neg_o.numel()} neg)")
     print(f"{tag} losses: ours {got_l}  reference fp32 {r32['losses']}  reference autocast {rac['losses']}")
     print(f"{tag} gradient vs reference fp32: ours cosine {cos_o:.4f} rel {rel_o:.3f} | reference autocast cosine {cos_a:.4f} rel {rel_a:.3f}")
@@ -361,3 +370,67 @@ def test_training_step_vs_reference_autograd(layers, rotated, precision):
     checks.append((abs(d_ours.norm().item() - d_ref.norm().item()) <= 0.02 * d_ref.norm().item(), "size of the first AdamW update"))
     failed = [msg for ok, msg in checks if not ok]
     assert not failed, failed
+
+
+@pytest.mark.parametrize("loss_type", ["iou", "linear_iou"])
+def test_iou_regression_loss_vs_reference_rotated_iou_loss(loss_type):
+    """--reg_loss_type iou / linear_iou (RotatedIOULoss, rpn.py:133-165) in the training engine: the loss value and its gradient w.r.t. the head's
+    deltas against the REFERENCE's own coder + RotatedIOULoss + autograd evaluated on the engine's fp32 deltas, same sampled positives; and the whole
+    step's regression loss against the reference network in fp32 (feature noise of the 16-bit forward only)."""
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref not staged")
+    from nerf_rpn_b200.model.anchor import AnchorGenerator3D, RPNHead
+    from nerf_rpn_b200.model.feature_extractor import Bottleneck, ResNet_FPN_256
+    from nerf_rpn_b200.model.nerf_rpn import NeRFRegionProposalNetwork
+    from nerf_rpn_b200.train import RPNTrainEngine
+    layers, dims = (2, 1, 1, 1), (64, 96, 80)
+    grid, gt = _planted(dims, 12, 11, True)
+    grid, gt = grid.cuda(), gt.cuda()
+    rm = ref_gpu.build_reference_model(rotated=True, seed=0, layers=layers, rpn_fg_iou_thresh=0.35, rpn_bg_iou_thresh=0.2, reg_loss_type=loss_type).cuda().train()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(123)
+        _, ref_losses, _ = rm([grid], [gt])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    backbone = ResNet_FPN_256(Bottleneck, list(layers), input_dim=4, is_max_pool=True)
+    head = RPNHead(256, 13, 4, rotate=True)
+    backbone.load_state_dict(rm.backbone.state_dict()); head.load_state_dict(rm.rpn.head.state_dict())
+    model = NeRFRegionProposalNetwork(backbone, AnchorGenerator3D(ref_gpu.ANCHOR_SIZES, ref_gpu.ASPECT), head, rpn_fg_iou_thresh=0.35, rpn_bg_iou_thresh=0.2,
+                                      rotated_bbox=True, reg_loss_type=loss_type).cuda().train()
+    eng = RPNTrainEngine(model, precision="fp16", lr=1e-4, weight_decay=0.01, clip_grad_norm=0.1, reg_loss_weight=5.0)
+    plan = eng.plan(1, dims)
+    torch.manual_seed(123)
+    out = eng.forward_backward(grid[None], [gt])
+    torch.cuda.synchronize()
+    pos, neg, gtp = plan.last_samples[0]
+    assert pos.numel() >= 8
+    norm = float(pos.numel() + neg.numel())
+    # the engine's own deltas of the sampled positives (fp32 predictor output), decoded and scored by the REFERENCE's code
+    A, code = eng.A, 8
+    level, vox, a = plan._split_anchor_index(pos)
+    cols = (A + a * code).view(-1, 1) + torch.arange(code, device=pos.device).view(1, -1)
+    deltas = torch.empty((pos.numel(), code), device="cuda")
+    dgot = torch.empty((pos.numel(), code), device="cuda")
+    for l in range(len(plan.pred_levels)):
+        m = level == l
+        if m.any():
+            deltas[m] = plan.pred_levels[l][0].reshape(-1, 128)[vox[m].view(-1, 1), cols[m]]
+            dgot[m] = plan.dpred_levels[l][0].reshape(-1, 128)[vox[m].view(-1, 1), cols[m]].float()
+    d = deltas.clone().requires_grad_(True)
+    boxes = rm.rpn.box_coder.decode_single(d, plan._anchors()[pos])
+    want = rm.rpn.rotated_iou_loss(boxes, gtp) / norm
+    (gwant,) = torch.autograd.grad(want, d)
+    got_loss = float(out[1])
+    print(f"[{loss_type}] regression loss: engine {got_loss:.6f}  reference code on the engine's deltas {want.item():.6f}  reference network fp32 "
+          f"{ref_losses['loss_rpn_box_reg'].item():.6f}  ({pos.numel()} positives)")
+    assert abs(got_loss - want.item()) <= 2e-4 * abs(want.item()) + 1e-7
+    assert abs(got_loss - ref_losses["loss_rpn_box_reg"].item()) <= 0.05 * abs(ref_losses["loss_rpn_box_reg"].item())
+    scale = 5.0 * eng.loss_scale
+    err = (dgot / scale - gwant).abs().max().item()
+    print(f"[{loss_type}] d loss / d deltas: max abs err {err:.3e} of scale {gwant.abs().max().item():.3e}")
+    assert err <= 2e-2 * gwant.abs().max().item()
+    grads = [eng.grad_of(p) for p in head.bbox_pred.parameters()]
+    assert all(torch.isfinite(g).all() and g.abs().sum() > 0 for g in grads)
