@@ -423,8 +423,9 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float* __r
     __shared__ __align__(16) float sr[64][kPrepFloats];      // rows
     __shared__ int sg[64], sgr[64];
     __shared__ unsigned long long sbits[64];
-    __shared__ unsigned short list[4096];
+    __shared__ unsigned short list[4096], list2[4096];
     __shared__ int warp_total[kMaskThreads / 32];
+    __shared__ int s_total2;
     const int t = threadIdx.x;
     const int col0 = cb * 64, row0 = rb * 64;
     const int row_last = min(row0 + 63, n - 1);
@@ -437,6 +438,7 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float* __r
         if (c < n) *reinterpret_cast<float4*>(&sp[rec][part * 4]) = *reinterpret_cast<const float4*>(prep + (size_t)c * kPrepFloats + part * 4);
         if (r < n) *reinterpret_cast<float4*>(&sr[rec][part * 4]) = *reinterpret_cast<const float4*>(prep + (size_t)r * kPrepFloats + part * 4);
         if (t < 64) { sg[t] = (col0 + t < n) ? sgroup[col0 + t] : -1; sgr[t] = (row0 + t < n) ? sgroup[row0 + t] : -2; sbits[t] = 0ull; }
+        if (t == 0) s_total2 = 0;
     }
     __syncthreads();
     // thread <-> (row, 16-column quarter)
@@ -487,13 +489,38 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float* __r
         list[base++] = (unsigned short)((rl << 6) | (quarter * 16 + k));
     }
     __syncthreads();
+    // ---- phase 1.5: separating-axis test (exact-zero cull, box_iou.cuh) on the compacted pairs, survivors compacted again -- the test is ~200
+    // instructions against ~7 000 for the clip, and a warp only skips the clip when ALL of its 32 pairs are separable, so it has to run first
+    const unsigned short* todo = list;
+    int total2 = total;
+    if (cull_ok) {
+        for (int i0 = 0; i0 < total; i0 += kMaskThreads) {
+            const int i = i0 + t;
+            bool keep = false;
+            int e = 0;
+            if (i < total) {
+                e = list[i];
+                ObbPrep a, b;
+                load_prep(sr[e >> 6], a);
+                load_prep(sp[e & 63], b);
+                keep = !obb_footprints_surely_disjoint(a, b);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            int wbase = 0;
+            if (lane == 0 && m) wbase = atomicAdd(&s_total2, __popc(m));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (keep) list2[wbase + __popc(m & ((1u << lane) - 1u))] = (unsigned short)e;
+        }
+        __syncthreads();
+        todo = list2; total2 = s_total2;
+    }
     // ---- phase 2: one candidate pair per thread
-    for (int i = t; i < total; i += kMaskThreads) {
-        const int e = list[i], r = e >> 6, c = e & 63;
+    for (int i = t; i < total2; i += kMaskThreads) {
+        const int e = todo[i], r = e >> 6, c = e & 63;
         ObbPrep a, b;
         load_prep(sr[r], a);
         load_prep(sp[c], b);
-        if (obb_suppresses(a, b, thr)) atomicOr(&sbits[r], 1ull << c);
+        if (!(iou3d_obb_full(a, b) <= thr)) atomicOr(&sbits[r], 1ull << c);
     }
     __syncthreads();
     if (t < 64 && row0 + t < n) mask[(size_t)(row0 + t) * W + cb] = sbits[t];
@@ -574,7 +601,7 @@ __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict_
                                                         unsigned long long* __restrict__ removed0) {
     __shared__ __align__(16) float tile[kCrossTile][8];
     __shared__ int tile_pos[kCrossTile];
-    __shared__ int queue[8][64];
+    __shared__ int queue[8][64], queue2[8][64];
     __shared__ int min_start;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int w = blockIdx.x * 8 + wid;
@@ -618,7 +645,7 @@ __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict_
     float btail[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) btail[i] = bp[8 + i];
-    int qn = 0;
+    int qn = 0, qn2 = 0;
     for (int k0 = min_start; k0 < kc; k0 += kCrossTile) {
         {
             const int k = k0 + tid;
@@ -642,28 +669,48 @@ __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict_
                     qn += __popc(m);
                     __syncwarp();
                     if (qn >= 32) {
+                        // stage 2: separating-axis test on a full warp of queued kept boxes; its survivors wait for a full warp of exact clips
+                        const int pos_a = queue[wid][lane];
                         ObbPrep a;
-                        load_prep(prep + (size_t)queue[wid][lane] * kPrepFloats, a);
-                        const bool hit = obb_suppresses(a, b, thr);
-                        if (__any_sync(0xffffffffu, hit)) { sup = true; done = true; break; }
+                        load_prep(prep + (size_t)pos_a * kPrepFloats, a);
+                        const bool keep = !(cull_ok && obb_footprints_surely_disjoint(a, b));
+                        const unsigned m2 = __ballot_sync(0xffffffffu, keep);
+                        if (keep) queue2[wid][qn2 + __popc(m2 & ((1u << lane) - 1u))] = pos_a;
+                        qn2 += __popc(m2);
                         const int rest = qn - 32;
                         const int moved = lane < rest ? queue[wid][32 + lane] : 0;
                         __syncwarp();
                         if (lane < rest) queue[wid][lane] = moved;
                         qn = rest;
                         __syncwarp();
+                        if (qn2 >= 32) {
+                            load_prep(prep + (size_t)queue2[wid][lane] * kPrepFloats, a);
+                            const bool hit = !(iou3d_obb_full(a, b) <= thr);
+                            if (__any_sync(0xffffffffu, hit)) { sup = true; done = true; break; }
+                            const int rest2 = qn2 - 32;
+                            const int moved2 = lane < rest2 ? queue2[wid][32 + lane] : 0;
+                            __syncwarp();
+                            if (lane < rest2) queue2[wid][lane] = moved2;
+                            qn2 = rest2;
+                            __syncwarp();
+                        }
                     }
                 }
             }
         }
         if (__syncthreads_and(done ? 1 : 0)) break;          // also fences the tile before it is overwritten
     }
-    if (!done && qn > 0) {
+    if (!done) {                                                  // remainders of both stages (each fewer than 32 entries)
         bool hit = false;
         if (lane < qn) {
             ObbPrep a;
             load_prep(prep + (size_t)queue[wid][lane] * kPrepFloats, a);
             hit = obb_suppresses(a, b, thr);
+        }
+        if (lane < qn2) {
+            ObbPrep a;
+            load_prep(prep + (size_t)queue2[wid][lane] * kPrepFloats, a);
+            hit = hit || !(iou3d_obb_full(a, b) <= thr);
         }
         if (__any_sync(0xffffffffu, hit)) sup = true;
     }
