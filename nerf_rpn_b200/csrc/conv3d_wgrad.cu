@@ -165,48 +165,56 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_tap
 struct WgLevelCl { int n, nxb, nyb, nzb, bx, by, bz, brick_begin; };
 struct WgDevCl {
     int n_levels, n_taps, cin, cout, n_t, m_tiles, n_tiles, splits, total_bricks, fp16, b_boxes;
+    int m_pair, m_items, stages;           // Cout slices per work item (1 or 2: two TMEM accumulators share one X tile), items along Cout, ring depth
     signed char tap[NRPN_CONV_MAX_TAPS][4];
     WgLevelCl lv[NRPN_CONV_MAX_LEVELS];
     float* partial;
 };
 struct WgMapsCl { CUtensorMap dy[NRPN_CONV_MAX_LEVELS]; CUtensorMap x[NRPN_CONV_MAX_LEVELS]; };
 constexpr int kWgBox = 64 * 128;               // one {64 channels x 64 voxels} box, 16-bit
+constexpr int kWgMaxStages = 4;
 
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {   // LBO = 8192 B (next 64-channel box), SBO = 1024 B (next 8 voxels)
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(kWgBox >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// With Cout >= 256 one work item computes TWO 128-channel slices of Cout against the same X tile (accumulators in TMEM columns [0, n_t) and
+// [256, 256 + n_t)): the kernel is bound by the shared-memory fill rate out of L2 (48 KB per four MMAs at N = 256: 11.7 TB/s in the head layer),
+// and sharing X cuts that to 32 KB.
 __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_cl_kernel(const __grid_constant__ WgMapsCl maps, const WgDevCl P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_bytes = (2 + P.b_boxes) * kWgBox;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
+    const int a_boxes = 2 * P.m_pair;
+    const int stage_bytes = (a_boxes + P.b_boxes) * kWgBox;
+    const int stages = P.stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
     uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + kWgStages;
-    uint64_t* tfull_bar = bars + 2 * kWgStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+    uint64_t* empty_bar = bars + kWgMaxStages;
+    uint64_t* tfull_bar = bars + 2 * kWgMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgMaxStages + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tmem_cols = P.m_pair == 2 ? 512u : 256u;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kWgStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < stages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
         ptx::mbar_init(tfull_bar, 1);
         ptx::fence_barrier_init();
         for (int l = 0; l < P.n_levels; ++l) { ptx::prefetch_tmap(&maps.dy[l]); ptx::prefetch_tmap(&maps.x[l]); }
     }
-    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 256); ptx::tmem_relinquish(); }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, tmem_cols); ptx::tmem_relinquish(); }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t idesc = (P.fp16 ? ptx::make_idesc_f16(128, P.n_t) : ptx::make_idesc_bf16(128, P.n_t)) | (1u << 15) | (1u << 16);   // MN-major A and B
-    const int items = P.n_taps * P.m_tiles * P.n_tiles * P.splits;
+    const int items = P.n_taps * P.m_items * P.n_tiles * P.splits;
     uint32_t tphase = 0;
     int stage_p = 0, stage_c = 0; uint32_t phase_p = 0, phase_c = 0;
 
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int split = item % P.splits;
         const int nt = (item / P.splits) % P.n_tiles;
-        const int mt = (item / (P.splits * P.n_tiles)) % P.m_tiles;
-        const int tap = item / (P.splits * P.n_tiles * P.m_tiles);
+        const int mi = (item / (P.splits * P.n_tiles)) % P.m_items;
+        const int tap = item / (P.splits * P.n_tiles * P.m_items);
         const int b0 = (int)(((long)P.total_bricks * split) / P.splits), b1 = (int)(((long)P.total_bricks * (split + 1)) / P.splits);
         if (warp == 0) {
             const bool leader = ptx::elect_one();
@@ -225,13 +233,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_cl_kernel(const __
                 if (leader) {
                     uint8_t* sa = smem + stage_p * stage_bytes;
                     ptx::mbar_expect_tx(&full_bar[stage_p], (uint32_t)stage_bytes);
-                    ptx::tma_load_5d(sa, &maps.dy[l], &full_bar[stage_p], mt * 128, z0, y0, x0, nb);
-                    ptx::tma_load_5d(sa + kWgBox, &maps.dy[l], &full_bar[stage_p], mt * 128 + 64, z0, y0, x0, nb);
+                    for (int j = 0; j < a_boxes; ++j)          // Cout slice (mi * m_pair + j / 2), 64-channel half j % 2 (beyond Cout: zero-filled)
+                        ptx::tma_load_5d(sa + j * kWgBox, &maps.dy[l], &full_bar[stage_p], (mi * P.m_pair) * 128 + 64 * j, z0, y0, x0, nb);
                     for (int j = 0; j < P.b_boxes; ++j)
-                        ptx::tma_load_5d(sa + (2 + j) * kWgBox, &maps.x[l], &full_bar[stage_p], nt * P.n_t + 64 * j, z0 + dz, y0 + dy, x0 + dx, nb);
+                        ptx::tma_load_5d(sa + (a_boxes + j) * kWgBox, &maps.x[l], &full_bar[stage_p], nt * P.n_t + 64 * j, z0 + dz, y0 + dy, x0 + dx, nb);
                 }
                 __syncwarp();
-                if (++stage_p == kWgStages) { stage_p = 0; phase_p ^= 1u; }
+                if (++stage_p == stages) { stage_p = 0; phase_p ^= 1u; }
             }
         } else if (warp == 1) {
             const bool leader = ptx::elect_one();
@@ -239,32 +247,39 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_cl_kernel(const __
                 ptx::mbar_wait(&full_bar[stage_c], phase_c);
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + stage_c * stage_bytes);
-                const uint64_t da = make_desc_mn_sw128(sa), db = make_desc_mn_sw128(sa + 2 * kWgBox);
+                const uint64_t db = make_desc_mn_sw128(sa + a_boxes * kWgBox);
                 if (leader) {
+                    for (int mp = 0; mp < P.m_pair; ++mp) {
+                        const uint64_t da = make_desc_mn_sw128(sa + mp * 2 * kWgBox);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)          // 16 voxels per MMA = two 1024-byte atoms further along K
-                        ptx::umma_bf16(tmem, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc, ((b - b0) | k) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k)          // 16 voxels per MMA = two 1024-byte atoms further along K
+                            ptx::umma_bf16(tmem + (uint32_t)(mp * 256), da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc, ((b - b0) | k) ? 1u : 0u);
+                    }
                     ptx::umma_commit(&empty_bar[stage_c]);
                 }
                 __syncwarp();
-                if (++stage_c == kWgStages) { stage_c = 0; phase_c ^= 1u; }
+                if (++stage_c == stages) { stage_c = 0; phase_c ^= 1u; }
             }
             if (leader) ptx::umma_commit(tfull_bar);
             __syncwarp();
         } else {
             const int q = warp & 3, row = q * 32 + lane;
-            float* out = P.partial + (((((size_t)tap * P.m_tiles + mt) * P.n_tiles + nt) * P.splits + split) * 128 + row) * P.n_t;
             ptx::mbar_wait(tfull_bar, tphase);
             ptx::tc_fence_after();
             const bool empty = (b1 <= b0);
-            for (int c = 0; c < P.n_t; c += 32) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-                ptx::tmem_ld_wait();
+            for (int mp = 0; mp < P.m_pair; ++mp) {
+                const int mt = mi * P.m_pair + mp;
+                if (mt >= P.m_tiles) break;
+                float* out = P.partial + (((((size_t)tap * P.m_tiles + mt) * P.n_tiles + nt) * P.splits + split) * 128 + row) * P.n_t;
+                for (int c = 0; c < P.n_t; c += 32) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mp * 256 + c), r);
+                    ptx::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(out + c + j) = empty ? make_float4(0.f, 0.f, 0.f, 0.f)
-                        : make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(out + c + j) = empty ? make_float4(0.f, 0.f, 0.f, 0.f)
+                            : make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                }
             }
             ptx::tc_fence_before();
         }
@@ -274,7 +289,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_cl_kernel(const __
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, tmem_cols); }
 }
 
 // channels-last (N, X*Y*Z, ld) -> planar (N, C, X*Y, Zp) with Zp = z pitch >= Z (a multiple of 8 so that every TMA stride is a
@@ -352,6 +367,23 @@ static int wgrad_plan(const nrpn_wgrad_desc* d, WgDev& P) {
     return NRPN_OK;
 }
 
+// K-splits of a wgrad launch: the work items (taps x Cout slices x Cin slices x splits) run on a persistent grid of one CTA per SM, so the split count
+// is chosen for the fullest last wave (3^3 256->256: 54 base items; 2 splits = 108 items filled 73 % of 148 SMs, 8 splits = 432 items fill 97 % of
+// three waves), smallest count on ties, and at least 8 voxel bricks per split.
+static int wgrad_pick_splits(int base, int bricks) {
+    const int sms = num_sms();
+    int best = 1; double best_util = 0.0;
+    const int sp_max = 2 * sms / base + 1 > 32 ? 2 * sms / base + 1 : 32;
+    for (int sp = 1; sp <= sp_max; ++sp) {
+        if (sp > 1 && bricks / sp < 8) break;
+        const long items = (long)base * sp;
+        const long waves = (items + sms - 1) / sms;
+        const double util = (double)items / (double)(waves * sms);
+        if (util > best_util + 0.02) { best_util = util; best = sp; }
+    }
+    return best;
+}
+
 // ---- channels-last operands (desc->operand_layout == 1)
 static int pick_box(int extent, int cap) {           // power of two in [1, cap] with the least overhang over `extent`, the larger one on ties
     int best = 1; long waste = -1;
@@ -369,6 +401,15 @@ static int wgrad_plan_cl(const nrpn_wgrad_desc* d, WgDevCl& P) {
     P.n_levels = d->n_levels; P.n_taps = d->n_taps; P.cin = d->cin; P.cout = d->cout;
     P.n_t = d->cin > 256 ? 256 : d->cin; P.n_tiles = d->cin / P.n_t; P.m_tiles = ceil_div(d->cout, 128);
     P.b_boxes = ceil_div(P.n_t, 64);
+    static const bool pair_off = [] { const char* e = getenv("NRPN_WGRAD_MPAIR"); return e && e[0] == '0'; }();
+    P.m_pair = (P.m_tiles >= 2 && !pair_off) ? 2 : 1;
+    P.m_items = ceil_div(P.m_tiles, P.m_pair);
+    {
+        const int stage = (2 * P.m_pair + P.b_boxes) * kWgBox;
+        int st = (227 * 1024 - 2048) / stage;
+        P.stages = st > kWgMaxStages ? kWgMaxStages : st;
+        if (P.stages < 2) return NRPN_ERR_UNSUPPORTED;
+    }
     P.fp16 = d->act_fp16 ? 1 : 0;
     for (int t = 0; t < d->n_taps; ++t) { P.tap[t][0] = d->tap_off[t][0]; P.tap[t][1] = d->tap_off[t][1]; P.tap[t][2] = d->tap_off[t][2]; P.tap[t][3] = 0; }
     int bricks = 0;
@@ -384,11 +425,8 @@ static int wgrad_plan_cl(const nrpn_wgrad_desc* d, WgDevCl& P) {
         bricks += S.n * L.nxb * L.nyb * L.nzb;
     }
     P.total_bricks = bricks;
-    const int base = d->n_taps * P.m_tiles * P.n_tiles;
-    int splits = num_sms() / base;
-    if (splits > bricks) splits = bricks;
-    if (splits < 1) splits = 1;
-    P.splits = splits;
+    const int base = d->n_taps * P.m_items * P.n_tiles;
+    P.splits = wgrad_pick_splits(base, bricks);
     return NRPN_OK;
 }
 
@@ -425,13 +463,13 @@ static int wgrad_run_cl(const nrpn_wgrad_desc* d, cudaStream_t st) {
     }
     for (int l = d->n_levels; l < NRPN_CONV_MAX_LEVELS; ++l) { maps.dy[l] = maps.dy[0]; maps.x[l] = maps.x[0]; }
     P.partial = reinterpret_cast<float*>(align_up((size_t)d->workspace, 256));
-    const int smem = kWgStages * (2 + P.b_boxes) * kWgBox + 1024 + 256;
+    const int smem = P.stages * (2 * P.m_pair + P.b_boxes) * kWgBox + 1024 + 256;
     static int smem_set = 0;
     if (smem > smem_set) {
         NRPN_CUDA_TRY(cudaFuncSetAttribute(conv3d_wgrad_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         smem_set = smem;
     }
-    const int items = P.n_taps * P.m_tiles * P.n_tiles * P.splits;
+    const int items = P.n_taps * P.m_items * P.n_tiles * P.splits;
     const int grid = items < num_sms() ? items : num_sms();
     conv3d_wgrad_cl_kernel<<<grid, kWgThreads, smem, st>>>(maps, P);
     NRPN_LAUNCH_CHECK();
