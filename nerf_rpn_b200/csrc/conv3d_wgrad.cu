@@ -166,6 +166,7 @@ struct WgLevelCl { int n, nxb, nyb, nzb, bx, by, bz, brick_begin; };
 struct WgDevCl {
     int n_levels, n_taps, cin, cout, n_t, m_tiles, n_tiles, splits, total_bricks, fp16, b_boxes;
     int m_pair, m_items, stages;           // Cout slices per work item (1 or 2: two TMEM accumulators share one X tile), items along Cout, ring depth
+    int t_group, n_groups, acc_stride;     // taps per work item (their accumulators share one dY tile), tap groups, TMEM columns between accumulators
     signed char tap[NRPN_CONV_MAX_TAPS][4];
     WgLevelCl lv[NRPN_CONV_MAX_LEVELS];
     float* partial;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_cl_kernel(const __
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int a_boxes = 2 * P.m_pair;
-    const int stage_bytes = (a_boxes + P.b_boxes) * kWgBox;
+    const int stage_bytes = (a_boxes + P.t_group * P.b_boxes) * kWgBox;
     const int stages = P.stages;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
     uint64_t* full_bar = bars;
@@ -193,7 +194,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_cl_kernel(const __
     uint64_t* tfull_bar = bars + 2 * kWgMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgMaxStages + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tmem_cols = P.m_pair == 2 ? 512u : 256u;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < P.m_pair * P.t_group * P.acc_stride) tmem_cols <<= 1;
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
         ptx::mbar_init(tfull_bar, 1);
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_cl_kernel(const __
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t idesc = (P.fp16 ? ptx::make_idesc_f16(128, P.n_t) : ptx::make_idesc_bf16(128, P.n_t)) | (1u << 15) | (1u << 16);   // MN-major A and B
-    const int items = P.n_taps * P.m_items * P.n_tiles * P.splits;
+    const int items = P.n_groups * P.m_items * P.n_tiles * P.splits;
     uint32_t tphase = 0;
     int stage_p = 0, stage_c = 0; uint32_t phase_p = 0, phase_c = 0;
 
@@ -214,11 +216,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_cl_kernel(const __
         const int split = item % P.splits;
         const int nt = (item / P.splits) % P.n_tiles;
         const int mi = (item / (P.splits * P.n_tiles)) % P.m_items;
-        const int tap = item / (P.splits * P.n_tiles * P.m_items);
+        const int tap0 = (item / (P.splits * P.n_tiles * P.m_items)) * P.t_group;
+        const int ntap = P.n_taps - tap0 < P.t_group ? P.n_taps - tap0 : P.t_group;        // taps of this item: tap0 .. tap0 + ntap - 1
         const int b0 = (int)(((long)P.total_bricks * split) / P.splits), b1 = (int)(((long)P.total_bricks * (split + 1)) / P.splits);
         if (warp == 0) {
             const bool leader = ptx::elect_one();
-            const int dx = P.tap[tap][0], dy = P.tap[tap][1], dz = P.tap[tap][2];
             for (int b = b0; b < b1; ++b) {
                 int l = 0;
 #pragma unroll
@@ -232,11 +234,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_cl_kernel(const __
                 ptx::mbar_wait(&empty_bar[stage_p], phase_p ^ 1u);
                 if (leader) {
                     uint8_t* sa = smem + stage_p * stage_bytes;
-                    ptx::mbar_expect_tx(&full_bar[stage_p], (uint32_t)stage_bytes);
+                    ptx::mbar_expect_tx(&full_bar[stage_p], (uint32_t)((a_boxes + ntap * P.b_boxes) * kWgBox));
                     for (int j = 0; j < a_boxes; ++j)          // Cout slice (mi * m_pair + j / 2), 64-channel half j % 2 (beyond Cout: zero-filled)
                         ptx::tma_load_5d(sa + j * kWgBox, &maps.dy[l], &full_bar[stage_p], (mi * P.m_pair) * 128 + 64 * j, z0, y0, x0, nb);
-                    for (int j = 0; j < P.b_boxes; ++j)
-                        ptx::tma_load_5d(sa + (a_boxes + j) * kWgBox, &maps.x[l], &full_bar[stage_p], nt * P.n_t + 64 * j, z0 + dz, y0 + dy, x0 + dx, nb);
+                    for (int ti = 0; ti < ntap; ++ti) {        // one X tile per tap of the group: the tap is a coordinate shift
+                        const int dx = P.tap[tap0 + ti][0], dy = P.tap[tap0 + ti][1], dz = P.tap[tap0 + ti][2];
+                        for (int j = 0; j < P.b_boxes; ++j)
+                            ptx::tma_load_5d(sa + (a_boxes + ti * P.b_boxes + j) * kWgBox, &maps.x[l], &full_bar[stage_p], nt * P.n_t + 64 * j, z0 + dz, y0 + dy,
+                                             x0 + dx, nb);
+                    }
                 }
                 __syncwarp();
                 if (++stage_p == stages) { stage_p = 0; phase_p ^= 1u; }
@@ -247,13 +253,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_cl_kernel(const __
                 ptx::mbar_wait(&full_bar[stage_c], phase_c);
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + stage_c * stage_bytes);
-                const uint64_t db = make_desc_mn_sw128(sa + a_boxes * kWgBox);
                 if (leader) {
-                    for (int mp = 0; mp < P.m_pair; ++mp) {
-                        const uint64_t da = make_desc_mn_sw128(sa + mp * 2 * kWgBox);
+                    for (int ti = 0; ti < ntap; ++ti) {
+                        const uint64_t db = make_desc_mn_sw128(sa + (a_boxes + ti * P.b_boxes) * kWgBox);
+                        for (int mp = 0; mp < P.m_pair; ++mp) {
+                            const uint64_t da = make_desc_mn_sw128(sa + mp * 2 * kWgBox);
+                            const uint32_t acc = tmem + (uint32_t)((mp * P.t_group + ti) * P.acc_stride);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)          // 16 voxels per MMA = two 1024-byte atoms further along K
-                            ptx::umma_bf16(tmem + (uint32_t)(mp * 256), da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc, ((b - b0) | k) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k)      // 16 voxels per MMA = two 1024-byte atoms further along K
+                                ptx::umma_bf16(acc, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc, ((b - b0) | k) ? 1u : 0u);
+                        }
                     }
                     ptx::umma_commit(&empty_bar[stage_c]);
                 }
@@ -267,13 +276,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3d_wgrad_cl_kernel(const __
             ptx::mbar_wait(tfull_bar, tphase);
             ptx::tc_fence_after();
             const bool empty = (b1 <= b0);
-            for (int mp = 0; mp < P.m_pair; ++mp) {
-                const int mt = mi * P.m_pair + mp;
+            for (int am = 0; am < P.m_pair * ntap; ++am) {
+                const int mp = am / ntap, ti = am - mp * ntap;
+                const int mt = mi * P.m_pair + mp, tap = tap0 + ti;
                 if (mt >= P.m_tiles) break;
                 float* out = P.partial + (((((size_t)tap * P.m_tiles + mt) * P.n_tiles + nt) * P.splits + split) * 128 + row) * P.n_t;
                 for (int c = 0; c < P.n_t; c += 32) {
                     uint32_t r[32];
-                    ptx::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mp * 256 + c), r);
+                    ptx::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((mp * P.t_group + ti) * P.acc_stride + c), r);
                     ptx::tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -405,7 +415,19 @@ static int wgrad_plan_cl(const nrpn_wgrad_desc* d, WgDevCl& P) {
     P.m_pair = (P.m_tiles >= 2 && !pair_off) ? 2 : 1;
     P.m_items = ceil_div(P.m_tiles, P.m_pair);
     {
-        const int stage = (2 * P.m_pair + P.b_boxes) * kWgBox;
+        // taps per work item: their accumulators share one dY tile (the fill rate out of L2 bounds this kernel: 24 KB per four MMAs at N = 64 with one
+        // tap, 12 KB with four); as many as TMEM (512 columns) and a ring of >= 3 stages allow, at most 4
+        static const bool group_off = [] { const char* e = getenv("NRPN_WGRAD_TAPGROUP"); return e && e[0] == '0'; }();
+        P.acc_stride = 32;
+        while (P.acc_stride < P.n_t) P.acc_stride <<= 1;
+        P.t_group = 1;
+        for (int t = 2; t <= 4 && !group_off; t <<= 1) {
+            if (t > d->n_taps || P.m_pair * t * P.acc_stride > 512) break;
+            if ((227 * 1024 - 2048) / ((2 * P.m_pair + t * P.b_boxes) * kWgBox) < 3) break;
+            P.t_group = t;
+        }
+        P.n_groups = ceil_div(d->n_taps, P.t_group);
+        const int stage = (2 * P.m_pair + P.t_group * P.b_boxes) * kWgBox;
         int st = (227 * 1024 - 2048) / stage;
         P.stages = st > kWgMaxStages ? kWgMaxStages : st;
         if (P.stages < 2) return NRPN_ERR_UNSUPPORTED;
@@ -425,7 +447,7 @@ static int wgrad_plan_cl(const nrpn_wgrad_desc* d, WgDevCl& P) {
         bricks += S.n * L.nxb * L.nyb * L.nzb;
     }
     P.total_bricks = bricks;
-    const int base = d->n_taps * P.m_items * P.n_tiles;
+    const int base = P.n_groups * P.m_items * P.n_tiles;
     P.splits = wgrad_pick_splits(base, bricks);
     return NRPN_OK;
 }
@@ -463,13 +485,13 @@ static int wgrad_run_cl(const nrpn_wgrad_desc* d, cudaStream_t st) {
     }
     for (int l = d->n_levels; l < NRPN_CONV_MAX_LEVELS; ++l) { maps.dy[l] = maps.dy[0]; maps.x[l] = maps.x[0]; }
     P.partial = reinterpret_cast<float*>(align_up((size_t)d->workspace, 256));
-    const int smem = P.stages * (2 * P.m_pair + P.b_boxes) * kWgBox + 1024 + 256;
+    const int smem = P.stages * (2 * P.m_pair + P.t_group * P.b_boxes) * kWgBox + 1024 + 256;
     static int smem_set = 0;
     if (smem > smem_set) {
         NRPN_CUDA_TRY(cudaFuncSetAttribute(conv3d_wgrad_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         smem_set = smem;
     }
-    const int items = P.n_taps * P.m_items * P.n_tiles * P.splits;
+    const int items = P.n_groups * P.m_items * P.n_tiles * P.splits;
     const int grid = items < num_sms() ? items : num_sms();
     conv3d_wgrad_cl_kernel<<<grid, kWgThreads, smem, st>>>(maps, P);
     NRPN_LAUNCH_CHECK();
