@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const __nv_bfloat16* _
     if (lane < lanes) {
         const long per = ceil_div(rows, (long)gridDim.x);
         const long r0 = (long)blockIdx.x * per, r1 = min(rows, r0 + per);
-        for (long r = r0 + lane; r < r1; r += lanes) {
+#pragma unroll 4
+        for (long r = r0 + lane; r < r1; r += lanes) {       // unrolled: four rows' loads in flight per thread
             const size_t off = (size_t)r * c + cg * 8;
             const uint4 av = __ldg(reinterpret_cast<const uint4*>(a + off));
             const uint32_t* aw = reinterpret_cast<const uint32_t*>(&av);
@@ -131,12 +132,23 @@ __global__ void chan_reduce_final_kernel(const float* __restrict__ partial, int 
 }
 
 // out = act(gamma * (y - mean) * rstd + beta (+ res))
+// When the number of 8-channel groups divides the block size (every power-of-two width of the path) a thread sees the SAME eight channels in every
+// iteration of its grid-stride loop: the per-channel constants are loaded once (the first version fetched 32 / 40 scalars and ran a 64-bit modulo per
+// 16 bytes of data: 1.36 / 1.73 ms per training step against 0.6 / 1.2 ms of HBM time).
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ res,
                                                        __nv_bfloat16* __restrict__ out, size_t chunks, int c, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta, int relu, int fp16) {
     const int cgs = c >> 3;
+    const bool fixed = (256 % cgs) == 0;
+    float mean[8], rstd[8], gam[8], bet[8];
+    auto consts = [&](int c0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { mean[k] = stats[c0 + k]; rstd[k] = stats[c + c0 + k]; gam[k] = gamma[c0 + k]; bet[k] = beta[c0 + k]; }
+    };
+    if (fixed) consts((int)(threadIdx.x % cgs) * 8);
+#pragma unroll 2
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (size_t)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % cgs) * 8;
+        if (!fixed) consts((int)(i % cgs) * 8);
         const uint4 yv = __ldg(reinterpret_cast<const uint4*>(y) + i);
         const uint32_t* yw = reinterpret_cast<const uint32_t*>(&yv);
         uint4 rv = make_uint4(0, 0, 0, 0);
@@ -146,9 +158,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float2 f = unpack_act2(yw[k], fp16);
-            const int ca = c0 + 2 * k, cb = ca + 1;
-            float va = (f.x - stats[ca]) * stats[c + ca] * gamma[ca] + beta[ca];
-            float vb = (f.y - stats[cb]) * stats[c + cb] * gamma[cb] + beta[cb];
+            float va = (f.x - mean[2 * k]) * rstd[2 * k] * gam[2 * k] + bet[2 * k];
+            float vb = (f.y - mean[2 * k + 1]) * rstd[2 * k + 1] * gam[2 * k + 1] + bet[2 * k + 1];
             if (res) { const float2 r = unpack_act2(rw[k], fp16); va += r.x; vb += r.y; }
             if (relu) { va = fmaxf(va, 0.f); vb = fmaxf(vb, 0.f); }
             o[k] = pack_act2(va, vb, fp16);
@@ -165,8 +176,18 @@ __global__ void __launch_bounds__(256) bn_backward_apply_kernel(const __nv_bfloa
                                                                 const float* __restrict__ sums, int relu, int fp16) {
     const int cgs = c >> 3;
     const float inv_m = 1.0f / (float)rows;
+    const bool fixed = (256 % cgs) == 0;
+    float mean[8], rstd[8], gam[8], s1[8], s2[8];              // s1 = sum(g xhat) / M (dgamma / M), s2 = sum(g) / M (dbeta / M)
+    auto consts = [&](int c0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            mean[k] = stats[c0 + k]; rstd[k] = stats[c + c0 + k]; gam[k] = gamma[c0 + k];
+            s1[k] = sums[c0 + k] * inv_m; s2[k] = sums[c + c0 + k] * inv_m;
+        }
+    };
+    if (fixed) consts((int)(threadIdx.x % cgs) * 8);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (size_t)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % cgs) * 8;
+        if (!fixed) consts((int)(i % cgs) * 8);
         const uint4 gv = __ldg(reinterpret_cast<const uint4*>(dout) + i);
         const uint4 yv = __ldg(reinterpret_cast<const uint4*>(y) + i);
         uint4 ov = make_uint4(0, 0, 0, 0);
@@ -180,10 +201,10 @@ __global__ void __launch_bounds__(256) bn_backward_apply_kernel(const __nv_bfloa
             float2 g = unpack_act2(gw[k], fp16);
             const float2 yy = unpack_act2(yw[k], fp16);
             if (relu) { const float2 a = unpack_act2(ow[k], fp16); if (!(a.x > 0.f)) g.x = 0.f; if (!(a.y > 0.f)) g.y = 0.f; }
-            const int ca = c0 + 2 * k, cb = ca + 1;
-            const float xa = (yy.x - stats[ca]) * stats[c + ca], xb = (yy.y - stats[cb]) * stats[c + cb];
-            const float da = gamma[ca] * stats[c + ca] * (g.x - sums[c + ca] * inv_m - xa * sums[ca] * inv_m);
-            const float db = gamma[cb] * stats[c + cb] * (g.y - sums[c + cb] * inv_m - xb * sums[cb] * inv_m);
+            const int ka = 2 * k, kb = ka + 1;
+            const float xa = (yy.x - mean[ka]) * rstd[ka], xb = (yy.y - mean[kb]) * rstd[kb];
+            const float da = gam[ka] * rstd[ka] * (g.x - s2[ka] - xa * s1[ka]);
+            const float db = gam[kb] * rstd[kb] * (g.y - s2[kb] - xb * s1[kb]);
             o[k] = pack_act2(da, db, fp16);
             gm[k] = pack_act2(g.x, g.y, fp16);
         }
