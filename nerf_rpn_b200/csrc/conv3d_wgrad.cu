@@ -1,18 +1,17 @@
-// Weight gradient of a stride-1 'same' 3-D convolution on tcgen05 (training building block):
+// Weight gradient of a stride-1 'same' 3-D convolution on tcgen05 (training):
 //     dW[tap][co][ci] = sum over voxels v   dY[v][co] * X[v + tap_offset][ci]
-// The contraction runs over VOXELS, but activations are channels-last (a voxel's channels are contiguous), i.e. both operands
-// would be MN-major.  Instead of MN-major descriptors the two tensors are first transposed to a planar (N, C, X, Y, Z) layout
-// (z pitch padded with at least one ZERO column) by a bandwidth kernel.  The (y, z) plane is then addressed as ONE flattened axis
-// of Y * z_pitch elements: a TMA box {64 flattened voxels, 1 x, channels, 1} lands in shared memory as `channels` rows of exactly
-// 128 bytes -- the 128B-swizzled K-major layout every other kernel of this library feeds to tcgen05.mma (an inner box narrower
-// than the swizzle span is NOT laid out densely by TMA, hence 64 contiguous elements).  TMA needs 16-byte aligned inner
-// coordinates, so a y shift is the flattened offset dy * z_pitch (z_pitch % 8 == 0) and a z shift of -1 / +1 reads a z-SHIFTED
-// COPY of X^T written by the transpose kernel (zero where the source falls outside); stepping off the plane is TMA's zero fill:
-//     A = dY^T brick (128 output channels x 64 voxels),  B = X^T brick shifted by the tap (N_T input channels x 64 voxels),
-//     D (128 x N_T, fp32 in TMEM) += A * B^T      -- out-of-range voxels are zero-filled by TMA (= the convolution padding).
-// Work item = (tap, 128-channel slice of Cout, K-split); every item streams its share of the voxel bricks of all pyramid
-// levels (levels that share the weights, e.g. the RPN head on P2..P5) and writes one fp32 partial tile; a second kernel sums
-// the partial tiles in a fixed order (bit-reproducible) into dW (taps, Cout, Cin) fp32.
+// The contraction runs over VOXELS, for which channels-last activations (a voxel's channels are contiguous) are MN-major operands.
+// Two operand paths, selected by nrpn_wgrad_desc.operand_layout:
+//   1 (what the training engine uses, conv3d_wgrad_cl_kernel below): both tensors are read where they live through MN-major shared-memory
+//     descriptors; a tap is a coordinate shift of the X box, TMA's zero fill is the padding; work items share tiles across Cout slices / taps.
+//   0 (round 1, conv3d_wgrad_kernel, kept for A/B runs): the tensors are first transposed to a planar (N, C, X, Y, z_pitch) layout by a bandwidth
+//     kernel so that K-major descriptors can be used: the (y, z) plane is addressed as ONE flattened axis of Y * z_pitch elements, a TMA box
+//     {64 flattened voxels, 1 x, channels, 1} lands as `channels` rows of exactly 128 bytes; TMA needs 16-byte aligned inner coordinates, so a y shift
+//     is the flattened offset dy * z_pitch (z_pitch % 8 == 0) and a z shift of -1 / +1 reads a z-SHIFTED COPY of X^T written by the transpose kernel.
+// In both: D (128 x N_T, fp32 in TMEM) += A * B^T with A = dY brick (128 output channels x 64 voxels), B = X brick shifted by the tap (N_T input
+// channels x 64 voxels).  Work item = (tap or tap group, Cout slice(s), Cin slice, K-split); every item streams its share of the voxel bricks of all
+// pyramid levels that share the weights (the RPN head on P2..P5) and writes fp32 partial tiles; a second kernel sums them in a fixed order
+// (bit-reproducible) into dW (taps, Cout, Cin) or nn.Conv3d.weight's own (Cout, Cin, taps) order.
 #include <cstdlib>
 #include <cstring>
 #include "common.cuh"

@@ -5,7 +5,10 @@
 // suppression bit-matrix only for same-group upper-triangle tiles (one thread per row, 64 columns per word,
 // exact-zero culling by bounding circle / z range), resolve each group with one CTA that walks the matrix
 // 64 rows at a time (warp-shuffle resolve of the diagonal word, coalesced OR of the kept rows), then sort
-// the survivors by score.  No host round trips; everything is stream-ordered.
+// the survivors by score.  No host round trips; everything is stream-ordered.  Beyond a scene's proposals: chunked kept-list scan (groups above
+// 3 072 boxes) and, from 12 288 boxes, the cell-list path of nms_cells.cuh (levels: cross / adjacency / dependency rounds; reads a counter back per
+// batch of rounds, so it is skipped under stream capture).  Every path decides a pair with the exact IoU of the sequential loop; what may skip the
+// polygon clip is controlled by nrpn_set_nms_cull_mode (default: exact-zero tests only -> the keep set is provably the reference's).
 namespace nrpn { static __device__ int g_iou_mode = 3; }      // see box_iou.cuh: which build of the reference chain is reproduced
 namespace nrpn { static __device__ int g_lens_cull = 0; }     // footprint-lens cull, bit 1 of the NMS cull mode
 #define NRPN_IOU_MODE (::nrpn::g_iou_mode)
