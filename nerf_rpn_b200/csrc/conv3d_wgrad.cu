@@ -388,7 +388,7 @@ static int wgrad_pick_splits(int base, int bricks) {
         const long items = (long)base * sp;
         const long waves = (items + sms - 1) / sms;
         const double util = (double)items / (double)(waves * sms);
-        if (util > best_util + 0.02) { best_util = util; best = sp; }
+        if (util > best_util + 0.08) { best_util = util; best = sp; }        // every extra split is another 128 x N fp32 partial tile to write and reduce
     }
     return best;
 }
@@ -625,11 +625,19 @@ __global__ void __launch_bounds__(256) bias_grad_partial_vec_kernel(const __nv_b
     for (int i = threadIdx.x; i < c; i += blockDim.x) partial[(size_t)blockIdx.x * c + i] = sm[i];
 }
 
-__global__ void bias_grad_final_kernel(const float* __restrict__ partial, int blocks, int c, float* __restrict__ db) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= c) return;
+__global__ void __launch_bounds__(256) bias_grad_final_kernel(const float* __restrict__ partial, int blocks, int c, float* __restrict__ db) {
+    // 8 channels per CTA, 32 threads per channel (partials b, b + 32, ...), the 32 sums added in a fixed order: bit-reproducible
+    __shared__ float red[32][8];
+    const int cl = threadIdx.x & 7, kl = threadIdx.x >> 3;
+    const int ch = blockIdx.x * 8 + cl;
     float s = 0.f;
-    for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * c + ch];
+    if (ch < c) for (int b = kl; b < blocks; b += 32) s += partial[(size_t)b * c + ch];
+    red[kl][cl] = s;
+    __syncthreads();
+    if (kl != 0 || ch >= c) return;
+    s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) s += red[k][cl];
     db[ch] = s;
 }
 
@@ -669,7 +677,7 @@ int nrpn_bias_grad(const void* dy_cl, long rows, int c, int ld, int act_fp16, fl
         nrpn::bias_grad_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy_cl), rows, c, ld,
                                                                               act_fp16 ? 1 : 0, partial);
     NRPN_LAUNCH_CHECK();
-    nrpn::bias_grad_final_kernel<<<nrpn::ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(partial, blocks, c, db);
+    nrpn::bias_grad_final_kernel<<<nrpn::ceil_div(c, 8), 256, 0, (cudaStream_t)stream>>>(partial, blocks, c, db);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
