@@ -29,7 +29,37 @@ from . import ops, packing
 from ._lib import RpnDesc, WgradDesc, check, lib
 
 
+_TRAIN_GRAPH = os.environ.get("NRPN_TRAIN_GRAPH", "1") != "0"          # static launch lists of the training step replayed as CUDA graphs
 _WGRAD_PLANAR = os.environ.get("NRPN_WGRAD_PLANAR", "0") == "1"      # earlier wgrad operand path (transposed staging copies), for A/B runs
+
+
+
+def _replay_static(state: dict, name: str, fns, enabled: bool = True):
+    """Runs a STATIC launch list (fixed kernels, shapes and pointers): eagerly the first two times -- scratch buffers and workspaces are allocated
+    lazily --, then captured once into a CUDA graph and replayed (the ~700 launches of a training step otherwise cost ~5 ms of ctypes calls and
+    leave gaps between the many few-microsecond kernels of the deep stages).  A failed capture falls back to eager launches for good."""
+    st = state.setdefault(name, {"runs": 0, "graph": None, "failed": False})
+    if st["graph"] is not None:
+        st["graph"].replay()
+        return
+    if not (enabled and _TRAIN_GRAPH) or st["failed"] or st["runs"] < 2:
+        for f in fns:
+            f()
+        st["runs"] += 1
+        return
+    try:
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            for f in fns:
+                f()
+        st["graph"] = g
+        g.replay()
+    except Exception:                                         # noqa: BLE001 -- anything that cannot be captured: stay eager
+        st["failed"] = True
+        torch.cuda.synchronize()
+        for f in fns:
+            f()
 
 
 def _stream():
@@ -169,6 +199,7 @@ class RPNTrainEngine:
         self._build_layers()
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self._plans = {}
+        self._graphs = {}                      # captured static launch lists (repack)
         self.comm_stream = torch.cuda.Stream(device=self.device)
         self._norm = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._norm_ws = torch.empty(lib().nrpn_grad_norm_workspace_bytes(), dtype=torch.uint8, device=self.device)
@@ -250,6 +281,9 @@ class RPNTrainEngine:
     def repack(self):
         """fp32 master weights -> 16-bit GEMM operands (after every optimiser step / checkpoint load)."""
         self._packed_ver = tuple(p._version for p in self._params)
+        _replay_static(self._graphs, "repack", [self._repack_launches])
+
+    def _repack_launches(self):
         for c in self.all_convs:
             c.repack()
         hd, A = self.head, self.A
@@ -306,6 +340,7 @@ class _TrainPlan:
         self.bwd_lo: List[int] = []              # lowest flat-parameter offset whose gradient is final once bwd[i] has run
         self.f16 = eng.f16
         self._scratch = {}
+        self._graphs = {}
         self._ws = None
         X, Y, Z = dims
         L = lib()
@@ -654,8 +689,8 @@ class _TrainPlan:
             self._src = grids
         else:
             self._src = grids.contiguous()
-        for f in self.fwd:
-            f()
+        self.fwd[0]()                                               # stem packing reads the caller's grid: its pointer changes from step to step
+        _replay_static(self._graphs, "fwd", self.fwd[1:])
         anchors = self._anchors()
         samples = []
         forced = getattr(self, "forced_samples", None)         # tests: (pos, neg) index tensors per mesh instead of the sampler's draw
@@ -741,11 +776,18 @@ class _TrainPlan:
         its start (stem): every time >= bucket_elems new elements are final their all-reduce is launched on the comm stream, overlapping
         the dgrad / wgrad of the layers below (run_rpn.py:235-236: DDP's bucketed all-reduce during loss.backward())."""
         eng = self.eng
+        if not (eng.world > 1 and eng.overlap_allreduce):
+            self.allreduce_calls = 0
+            _replay_static(self._graphs, "bwd", list(reversed(self.bwd)))
+            return
         sched = {k: (lo, hi) for k, lo, hi in bucket_schedule(self.bwd_lo, eng.n_params, eng.bucket_elems)}
         self.allreduce_calls = 0
-        for k, f in enumerate(reversed(self.bwd)):
-            f()
-            if eng.world > 1 and eng.overlap_allreduce and k in sched:
+        order = list(reversed(self.bwd))
+        start = 0
+        for seg, k in enumerate(sorted(sched) + ([len(order) - 1] if (len(order) - 1) not in sched else [])):
+            _replay_static(self._graphs, f"bwd{seg}", order[start:k + 1])      # the launches between two all-reduce points: one graph each
+            start = k + 1
+            if k in sched:
                 lo, hi = sched[k]
                 ev = torch.cuda.Event()
                 ev.record()

@@ -13,7 +13,7 @@ model = bench.build_model(rotated=True, spread=0.0).cuda().train()
 eng = model.train_engine(precision="bf16", lr=1e-4, weight_decay=0.01, clip_grad_norm=0.1, reg_loss_weight=5.0)
 grid = bench.synth_scene(0, "dataset").permute(1, 2, 3, 0).contiguous().cuda().permute(3, 0, 1, 2)[None]
 gt = [bench.planted_boxes(0).cuda()]
-for _ in range(2):
+for _ in range(4):                       # two eager steps, the graph capture, one replay
     eng.train_step(grid, gt)
 torch.cuda.synchronize()
 if os.environ.get("NCU_TRAIN_TIME", "1") == "1":
