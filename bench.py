@@ -311,7 +311,7 @@ def device_throughput(model, dev_batches, K, W, barrier, sampler=None):
     return e0.elapsed_time(e1), plan, int(plan.out_count[0].item())
 
 
-def train_leg(rank, local, world, barrier, steps=5, warm=2):
+def train_leg(rank, local, world, barrier, steps=8, warm=4):       # warm-up covers the two eager steps + the graph capture of the launch lists
     """BASELINE config 4: ResNet50-FPN + anchor head, --rotated_bbox, one 160x256x256 scene per rank per step, data parallel: forward,
     target assignment + sampling + losses, backward (dgrad / wgrad on tcgen05), NCCL all-reduce of the flat gradient bucket overlapped
     with the backward pass, clip_grad_norm_(0.1) + AdamW.  bf16 activations / gradients, fp32 master weights and accumulation."""
@@ -812,7 +812,7 @@ def run_train(args):
     import torch
     import torch.distributed as dist
     rank, local, world, barrier, max_over_ranks = _cfg_dist()
-    K, W = args.steps, max(args.warmup, 3)
+    K, W = args.steps, max(args.warmup, 4)             # two eager steps, the graph capture, one replay
     burst, sustained, how = measured_peaks()
     model = build_model(rotated=True, spread=0.0).cuda().train()
     eng = model.train_engine(precision="bf16", lr=1e-4, weight_decay=0.01, clip_grad_norm=0.1, reg_loss_weight=5.0,
