@@ -31,3 +31,21 @@ def test_torch_decode_matches_device_decode(tmp_path):
     assert np.abs(err).max() < 1e-3, np.abs(err).max(0)
     got.sum().backward()
     assert torch.isfinite(dt.grad).all() and dt.grad.abs().sum() > 0
+
+
+def test_split_anchor_index_matches_the_flat_anchor_order():
+    """index = level offset + voxel * A + a (rpn.py:20-27): the helper the IoU-type loss uses to find a sampled anchor's deltas."""
+    from nerf_rpn_b200 import train as T
+    plan = T._TrainPlan.__new__(T._TrainPlan)
+    plan.feat_dims = [(4, 6, 5), (2, 3, 3), (1, 2, 2)]
+    plan.eng = type("E", (), {"A": 13})()
+    A = 13
+    want = []
+    for l, d in enumerate(plan.feat_dims):
+        for v in range(d[0] * d[1] * d[2]):
+            for a in range(A):
+                want.append((l, v, a))
+    idx = torch.arange(len(want))
+    level, vox, a = plan._split_anchor_index(idx)
+    got = list(zip(level.tolist(), vox.tolist(), a.tolist()))
+    assert got == want
