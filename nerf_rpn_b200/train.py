@@ -171,8 +171,8 @@ class RPNTrainEngine:
         bb, rpn = model.backbone, model.rpn
         if type(bb).__name__ != "ResNet_FPN_256":
             raise NotImplementedError("nerf_rpn_b200: the training engine implements ResNet_FPN_256 + RPNHead (BASELINE config 4)")
-        if rpn.reg_loss_type not in ("smooth_l1", "iou", "linear_iou"):
-            raise NotImplementedError("nerf_rpn_b200: reg_loss_type giou / diou is not implemented (cal_giou_3d / cal_diou_3d are not built)")
+        if rpn.reg_loss_type not in ("smooth_l1", "iou", "linear_iou", "giou", "diou"):
+            raise NotImplementedError(f"nerf_rpn_b200: unknown reg_loss_type {rpn.reg_loss_type!r}")
         if rpn.reg_loss_type != "smooth_l1" and not rpn.rotate:
             raise NotImplementedError("nerf_rpn_b200: the IoU-type regression losses exist for --rotated_bbox only (as in the reference, rpn.py:216-217)")
         self.reg_loss_type = rpn.reg_loss_type
@@ -725,7 +725,7 @@ class _TrainPlan:
         if eng.reg_loss_type != "smooth_l1":
             self._iou_reg_loss(float(w_reg), max(norm, 1.0))
 
-    # ---- IoU-type regression loss (RotatedIOULoss, rpn.py:133-165, reg_loss_type "iou" / "linear_iou") on the <= 128 sampled positives per mesh
+    # ---- IoU-type regression losses (RotatedIOULoss, rpn.py:133-165: "iou", "linear_iou", "giou", "diou") on the <= 128 sampled positives per mesh
     def _split_anchor_index(self, idx):
         """flat anchor index of one mesh -> (level, voxel within the level, anchor): index = level offset + voxel * A + a (rpn.py:20-27)."""
         A = self.eng.A
@@ -736,10 +736,10 @@ class _TrainPlan:
         return level, local // A, local % A
 
     def _iou_reg_loss(self, w_reg, norm):
-        """loss = sum over sampled positives of -log((I + 1) / (U + 1)) (or 1 - ...) / number of sampled anchors, on the boxes DECODED from the head's
+        """loss = sum over sampled positives of -log((I + 1) / (U + 1)) (or 1 - ..., or the GIoU / DIoU loss) / number of sampled anchors, on the boxes DECODED from the head's
         deltas; its gradient w.r.t. the deltas (autograd through decode + the IoU Function) is written into d(pred) like the fused kernel does."""
         from .model.coder_torch import decode_obb
-        from .model.rotated_iou.oriented_iou_loss import cal_iou_3d
+        from .model.rotated_iou.oriented_iou_loss import cal_diou_3d, cal_giou_3d, cal_iou_3d
         eng = self.eng
         A, code = eng.A, 8
         anchors = self._anchors()
@@ -757,9 +757,14 @@ class _TrainPlan:
             with torch.enable_grad():
                 d = deltas.detach().requires_grad_(True)
                 boxes = decode_obb(anchors[pos], d)
-                iou, _, _, _, union = cal_iou_3d(boxes.unsqueeze(0), gtp.unsqueeze(0), verbose=True)
-                ratio = (iou * union + 1.0) / (union + 1.0)
-                losses = -torch.log(ratio) if eng.reg_loss_type == "iou" else 1.0 - ratio
+                if eng.reg_loss_type == "giou":
+                    losses = cal_giou_3d(boxes.unsqueeze(0), gtp.unsqueeze(0))[0]
+                elif eng.reg_loss_type == "diou":
+                    losses = cal_diou_3d(boxes.unsqueeze(0), gtp.unsqueeze(0))[0]
+                else:
+                    iou, _, _, _, union = cal_iou_3d(boxes.unsqueeze(0), gtp.unsqueeze(0), verbose=True)
+                    ratio = (iou * union + 1.0) / (union + 1.0)
+                    losses = -torch.log(ratio) if eng.reg_loss_type == "iou" else 1.0 - ratio
                 loss = losses.sum() / norm
                 (g,) = torch.autograd.grad(loss, d)
             total = total + loss.detach()

@@ -372,9 +372,9 @@ def _training_step_parity(layers, rotated, precision, dims, n_gt):
     assert not failed, failed
 
 
-@pytest.mark.parametrize("loss_type", ["iou", "linear_iou"])
+@pytest.mark.parametrize("loss_type", ["iou", "linear_iou", "giou", "diou"])
 def test_iou_regression_loss_vs_reference_rotated_iou_loss(loss_type):
-    """--reg_loss_type iou / linear_iou (RotatedIOULoss, rpn.py:133-165) in the training engine: the loss value and its gradient w.r.t. the head's
+    """--reg_loss_type iou / linear_iou / giou / diou (RotatedIOULoss, rpn.py:133-165) in the training engine: the loss value and its gradient w.r.t. the head's
     deltas against the REFERENCE's own coder + RotatedIOULoss + autograd evaluated on the engine's fp32 deltas, same sampled positives; and the whole
     step's regression loss against the reference network in fp32 (feature noise of the 16-bit forward only)."""
     from oracle import ref_gpu
