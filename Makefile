@@ -3,7 +3,7 @@ NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
 CSRC := nerf_rpn_b200/csrc
-OBJ := build/nms.o build/rpn_post.o build/conv3d_igemm.o build/conv3d_slab.o build/conv3d_wgrad.o build/pointwise.o build/groupnorm.o build/fcos_post.o build/swin.o build/eval.o build/targets.o build/train.o
+OBJ := build/nms.o build/rpn_post.o build/conv3d_igemm.o build/conv3d_slab.o build/conv3d_wgrad.o build/pointwise.o build/groupnorm.o build/fcos_post.o build/swin.o build/eval.o build/targets.o build/train.o build/fcos_loss.o
 LIB := nerf_rpn_b200/lib/libnerf_rpn_b200.so
 
 all: $(LIB) oracle

@@ -407,6 +407,52 @@ int nrpn_grad_norm(const float *g, size_t n, float inv_scale, float *norm_out, v
 int nrpn_adamw_step(float *p, const float *g, float *m, float *v, size_t n, const float *norm, float max_norm, float inv_scale, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, nrpn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------ FCOS training loss
+ * FCOSLossComputation (fcos/loss.py:185-591) on the device, in two calls.
+ *
+ * nrpn_fcos_targets = prepare_targets / compute_targets_for_locations[_obb] / get_sample_region (loss.py:213-441) for ONE scene: every
+ * location of every level against every ground-truth box (AABB (G,6) or OBB (G,7): encode_fcos_obb, fcos/utils.py:64-108), centre
+ * sampling, the level's object-size range, smallest box wins (first minimum), without the (locations, G, 8) tensors.  locations (P,3)
+ * f32 = the levels' compute_locations (fcos.py:221-250) concatenated, P = sum n_points.  labels (P) f32 in {0, 1}; reg_targets
+ * (P, 6|8) f32: l, t, f, r, b, ba (divided by the level's stride when norm_reg_targets) + alpha, beta.  n_gt == 0: zeros (loss.py:324-328).
+ * Any G (ground truth is streamed through shared memory in chunks). */
+typedef struct {
+    int32_t n_levels;
+    int32_t n_points[NRPN_RPN_MAX_LEVELS];
+    int32_t stride[NRPN_RPN_MAX_LEVELS];
+    float size_lo[NRPN_RPN_MAX_LEVELS], size_hi[NRPN_RPN_MAX_LEVELS]; /* object_sizes_of_interest (loss.py:263-268): -1,16 / 16,32 / 32,64 / 64,1e8 */
+    float center_sampling_radius;                                      /* <= 0: every location strictly inside a box is a candidate */
+    int32_t norm_reg_targets;
+} nrpn_fcos_target_desc;
+int nrpn_fcos_targets(const nrpn_fcos_target_desc *desc /*host*/, const float *locations, const float *gt, int n_gt, int gt_dim,
+                      float *labels, float *reg_targets, nrpn_stream_t stream);
+
+/* nrpn_fcos_loss = FCOSLossComputation.__call__ (loss.py:487-591) up to the two normalisers: sigmoid focal loss over every (unmasked)
+ * location, and on the positives the centerness target, BCE-with-logits of the centerness branch, the box regression loss weighted by
+ * the centerness target (loss_type 0: smooth-L1 on all 6|8 channels; AABB head: 1 -log(iou), 2 1 - iou, 3 1 - giou of IOULoss :78-131)
+ * and, for the OBB head with additional_l1, the smooth-L1 of alpha / beta.  For use_obb with loss_type >= 1 the rotated-IoU term itself
+ * (RotatedIOULoss :134-181) is NOT computed here: the caller adds it on the gathered positives (cal_iou_3d & co. with their own backward).
+ * Per level the head's NCDHW outputs are read where they are: cls (N,1,P_l), reg (N,6|8,P_l), ctr (N,1,P_l) fp32; d* (same shapes,
+ * all three NULL for a forward-only call) receive the UN-normalised gradients of sums[0], sums[3] + sums[5], sums[4] (zeros where none).
+ * labels (N,P) / reg_targets (N,P,6|8): nrpn_fcos_targets per scene; mask (N,P) u8 or NULL: compute_padding_masks (0 = dropped).
+ * centerness_targets (N,P) f32 or NULL: the positives' centerness target (0 elsewhere).
+ * sums[8] (device, fp64, fixed-order reduction): 0 focal sum, 1 positives, 2 sum of centerness targets, 3 weighted regression sum,
+ * 4 centerness BCE sum, 5 weighted alpha/beta smooth-L1 sum, 6-7 zero.  The caller all-reduces [1], [2] over the ranks and divides
+ * (loss.py:541-576): loss_cls = [0] / max([1]/W, 1), loss_reg = ([3] + [5]) / ([2]/W), loss_centerness = [4] / max([1]/W, 1). */
+typedef struct {
+    const float *cls, *reg, *ctr;
+    float *dcls, *dreg, *dctr;
+    int32_t n_points;
+} nrpn_fcos_loss_level;
+typedef struct {
+    int32_t n_levels;
+    nrpn_fcos_loss_level level[NRPN_RPN_MAX_LEVELS];
+    int32_t n_images, use_obb, loss_type, additional_l1;
+} nrpn_fcos_loss_desc;
+size_t nrpn_fcos_loss_workspace_bytes(void);
+int nrpn_fcos_loss(const nrpn_fcos_loss_desc *desc /*host*/, const float *labels, const float *reg_targets, const uint8_t *mask,
+                   float *centerness_targets, double *sums, void *workspace, size_t workspace_bytes, nrpn_stream_t stream);
+
 /* Which necessary-condition tests may skip the exact polygon clip inside NMS (process-wide; initial value from NRPN_NMS_CULL_MODE, default 0):
  *   0  exact-zero culls only (bounding circles / z ranges disjoint: the reference computes exactly 0) -- the keep set is provably the reference's;
  *   1  + volume-ratio and z-overlap-ratio culls, 3  + footprint-lens cull: geometric bounds, applied from 16 384 boxes up only.  The reference's

@@ -76,6 +76,22 @@ class FcosDesc(ctypes.Structure):
                 ("padded", ctypes.c_int32)]
 
 
+class FcosTargetDesc(ctypes.Structure):
+    _fields_ = [("n_levels", ctypes.c_int32), ("n_points", ctypes.c_int32 * MAX_LEVELS), ("stride", ctypes.c_int32 * MAX_LEVELS),
+                ("size_lo", ctypes.c_float * MAX_LEVELS), ("size_hi", ctypes.c_float * MAX_LEVELS),
+                ("center_sampling_radius", ctypes.c_float), ("norm_reg_targets", ctypes.c_int32)]
+
+
+class FcosLossLevel(ctypes.Structure):
+    _fields_ = [("cls", ctypes.c_void_p), ("reg", ctypes.c_void_p), ("ctr", ctypes.c_void_p), ("dcls", ctypes.c_void_p),
+                ("dreg", ctypes.c_void_p), ("dctr", ctypes.c_void_p), ("n_points", ctypes.c_int32)]
+
+
+class FcosLossDesc(ctypes.Structure):
+    _fields_ = [("n_levels", ctypes.c_int32), ("level", FcosLossLevel * MAX_LEVELS), ("n_images", ctypes.c_int32),
+                ("use_obb", ctypes.c_int32), ("loss_type", ctypes.c_int32), ("additional_l1", ctypes.c_int32)]
+
+
 _SIGNATURES = {
     "nrpn_version": (ctypes.c_int, []),
     "nrpn_status_string": (ctypes.c_char_p, [ctypes.c_int]),
@@ -163,6 +179,10 @@ _SIGNATURES = {
     "nrpn_grad_norm": (ctypes.c_int, [c_f32p, ctypes.c_size_t, ctypes.c_float, c_f32p, ctypes.c_void_p, ctypes.c_size_t, c_stream]),
     "nrpn_adamw_step": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_size_t, c_f32p, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                        ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, c_stream]),
+    "nrpn_fcos_targets": (ctypes.c_int, [ctypes.POINTER(FcosTargetDesc), c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, c_f32p, c_f32p, c_stream]),
+    "nrpn_fcos_loss_workspace_bytes": (ctypes.c_size_t, []),
+    "nrpn_fcos_loss": (ctypes.c_int, [ctypes.POINTER(FcosLossDesc), c_f32p, c_f32p, ctypes.c_void_p, c_f32p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_size_t, c_stream]),
     "nrpn_set_nms_cull_mode": (None, [ctypes.c_int]),
     "nrpn_get_nms_cull_mode": (ctypes.c_int, []),
     "nrpn_nms_cells_stats": (ctypes.c_int, [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]),

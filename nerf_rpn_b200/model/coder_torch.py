@@ -38,3 +38,29 @@ def decode_obb(anchors: torch.Tensor, deltas: torch.Tensor) -> torch.Tensor:
     th = torch.where(swap, theta, theta + _PI / 2)
     th = torch.remainder(th + _PI / 2, _PI) - _PI / 2
     return torch.stack([xm, ym, gz, wr, hr, gd, th], 1)
+
+
+def decode_fcos_obb(locations: torch.Tensor, reg: torch.Tensor) -> torch.Tensor:
+    """FCOS midpoint-offset decode (fcos/utils.py:12-61), differentiable: locations (P,3), reg (P,8) = distances to the six faces of the OBB's
+    AABB + (alpha, beta) -> (P,7) (x,y,z,w,l,h,theta).  Inference runs the same formulas inside nrpn_fcos_proposals (csrc/fcos_post.cu); here they
+    are torch ops because the rotated-IoU loss of the FCOS head back-propagates through them on the positive locations of a training step."""
+    lo = locations - reg[:, 0:3]
+    hi = locations + reg[:, 3:6]
+    ext = hi[:, :2] - lo[:, :2]
+    c = (lo + hi) / 2
+    v = (hi[:, :2] + lo[:, :2]) / 2 + reg[:, 6:8] * ext                     # the vertex on the top edge (x) / on the right edge (y)
+    v = torch.maximum(torch.minimum(v, hi[:, :2]), lo[:, :2])               # clamp(min=lo, max=hi)
+    v0 = torch.stack([v[:, 0], hi[:, 1]], 1) - c[:, :2]
+    v1 = torch.stack([hi[:, 0], v[:, 1]], 1) - c[:, :2]
+    d0, d1 = torch.norm(v0, dim=1), torch.norm(v1, dim=1)
+    dmax = torch.max(d0, d1)
+    c2 = c[:, :2]
+    v0 = v0 / (d0[:, None] + 1e-7) * dmax[:, None] + c2                     # rectangularise: both half diagonals as long as the longer one
+    v1 = v1 / (d1[:, None] + 1e-7) * dmax[:, None] + c2                     # (centre added back first, as the reference does: a degenerate
+    length = torch.norm(v0 - v1, dim=1)                                     #  box -- opposite corners -- then has mid == 0 exactly)
+    mid = (v0 + v1) / 2 - c2
+    width = torch.norm(mid, dim=1) * 2
+    degenerate = (mid[:, 0] == 0) & (mid[:, 1] == 0)
+    mx = torch.where(degenerate, torch.full_like(mid[:, 0], 1e-7), mid[:, 0])
+    theta = torch.atan2(mid[:, 1], mx)
+    return torch.stack([c[:, 0], c[:, 1], c[:, 2], width, length, hi[:, 2] - lo[:, 2], theta], 1)

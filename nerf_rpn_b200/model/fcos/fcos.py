@@ -2,8 +2,10 @@
 FCOSOverNeRF :287-386) and fcos/inference.py:11-46 (FCOSPostProcessor's hyper-parameters): same class names, constructor
 arguments, attribute / parameter names (state_dict keys `fcos_module.head.{cls_tower,bbox_tower}.{i}.*`, `cls_logits.*`,
 `bbox_pred.*`, `centerness.*`, `scales.{i}.scale`) and creation / init order, so seeds and checkpoints line up.
-Inference (`--norm_reg_targets --centerness_on_reg`, the flags of test_fcos.sh) runs on the fused B200 engine; training
-(fcos/loss.py) is not implemented in this round."""
+Inference (`--norm_reg_targets --centerness_on_reg`, the flags of test_fcos.sh) runs on the fused B200 engine.  The training LOSS
+(fcos/loss.py) is built (`FCOSModule.loss_evaluator`, model/fcos/loss.py: two kernels + one autograd node over the head outputs);
+the backward pass of the FCOS towers (GroupNorm) and a captured FCOS training step are not, so `FCOSOverNeRF.forward` still raises
+in training mode."""
 import math
 from typing import List
 
@@ -13,6 +15,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ...precision import EngineHolder, resolve as _resolve_precision
+from .loss import FCOSLossComputation
 
 
 class Scale(nn.Module):
@@ -79,12 +82,41 @@ class FCOSModule(nn.Module):
                              centerness_on_reg=args.centerness_on_reg, use_obb=args.rotated_bbox)
         self.box_selector_test = FCOSPostProcessor(args.pre_nms_thresh, args.pre_nms_top_n, args.nms_thresh,
                                                    args.fpn_post_nms_top_n, args.min_size, 1, use_obb=args.rotated_bbox)
-        self.loss_evaluator = None           # fcos/loss.py (training) is not part of this round
+        # fcos.py:152-158; the defaults are run_fcos.py:103-111's for callers that build `args` for inference only
+        self.loss_evaluator = FCOSLossComputation(
+            fpn_strides, getattr(args, "center_sampling_radius", 1.5), getattr(args, "iou_loss_type", "iou"), args.norm_reg_targets,
+            world_size=world_size, use_obb=args.rotated_bbox, use_additional_l1_loss=getattr(args, "use_additional_l1_loss", False),
+            proj2d_loss_weight=getattr(args, "proj2d_loss_weight", 0.0))
         self.fpn_strides = fpn_strides
         self.world_size = world_size
 
     def forward(self, grid_sizes, features, targets=None, objectness_output_paths=None):
         raise RuntimeError("nerf_rpn_b200.FCOSModule runs inside FCOSOverNeRF.forward (one captured launch sequence)")
+
+    def _forward_train(self, locations, box_cls, box_regression, centerness, targets, padding_masks):
+        """fcos.py:200-210: the three losses of the head outputs (differentiable w.r.t. them)."""
+        loss_box_cls, loss_box_reg, loss_centerness = self.loss_evaluator(locations, box_cls, box_regression, centerness, targets,
+                                                                          padding_masks=padding_masks)
+        return None, None, {"loss_cls": loss_box_cls, "loss_reg": loss_box_reg, "loss_centerness": loss_centerness}
+
+    def compute_locations(self, features):
+        """fcos.py:221-250: per level (w * l * h, 3), z fastest, voxel index * stride + stride // 2."""
+        locations = []
+        for level, feature in enumerate(features):
+            w, l, h = feature.size()[-3:]
+            stride = self.fpn_strides[level]
+            axes = [torch.arange(0, n * stride, step=stride, dtype=torch.float32, device=feature.device) for n in (w, l, h)]
+            grid = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, 3)
+            locations.append(grid + stride // 2)
+        return locations
+
+    def compute_padding_masks(self, locations, ori_sizes):
+        """fcos.py:252-266: per level (N, P_l) bool, True where the location lies inside the scene's own extent."""
+        masks = []
+        for loc in locations:
+            size = torch.tensor([list(s) for s in ori_sizes], dtype=loc.dtype, device=loc.device)          # (N, 3)
+            masks.append((loc[None] < size[:, None]).all(dim=-1))
+        return masks
 
 
 class FCOSOverNeRF(EngineHolder, nn.Module):
@@ -121,7 +153,8 @@ class FCOSOverNeRF(EngineHolder, nn.Module):
 
     def forward(self, meshes, targets=None, objectness_output_paths=None):
         if self.training:
-            raise NotImplementedError("nerf_rpn_b200: FCOS training (fcos/loss.py) is not implemented by the B200 engine yet")
+            raise NotImplementedError("nerf_rpn_b200: the FCOS training step (backward through the GroupNorm towers) is not built; the loss itself is: "
+                                      "fcos_module.loss_evaluator(locations, box_cls, box_regression, centerness, targets, padding_masks)")
         if objectness_output_paths is not None:
             raise NotImplementedError("nerf_rpn_b200: --output_voxel_scores export is not implemented")
         original_mesh_sizes = []

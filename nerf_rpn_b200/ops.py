@@ -7,7 +7,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import WgradDesc, ConvDesc, FcosDesc, GnLevel, RpnDesc, check, lib
+from ._lib import WgradDesc, ConvDesc, FcosDesc, FcosLossDesc, FcosTargetDesc, GnLevel, RpnDesc, check, lib
 
 
 def _stream():
@@ -484,6 +484,78 @@ def fcos_proposals(desc: FcosDesc, device, out=None, workspace: Optional[torch.T
     check(lib().nrpn_fcos_proposals(ctypes.byref(desc), _ptr(boxes), _ptr(scores), _ptr(count), _ptr(ws), ws.numel(), _stream()),
           "fcos_proposals")
     return boxes, scores, count
+
+
+# ------------------------------------------------------------------------------------------------ FCOS training loss (fcos/loss.py)
+FCOS_SIZES_OF_INTEREST = ((-1.0, 16.0), (16.0, 32.0), (32.0, 64.0), (64.0, 100000000.0))          # loss.py:263-268
+FCOS_LOSS_TYPES = {"smooth_l1": 0, "iou": 1, "linear_iou": 2, "giou": 3}
+
+
+def fcos_targets(locations: torch.Tensor, n_points: Sequence[int], strides: Sequence[int], gt: torch.Tensor, center_sampling_radius: float,
+                 norm_reg_targets: bool = True):
+    """One scene: locations (P,3) f32 (levels concatenated), gt (G, 6|7) -> labels (P) f32 in {0,1}, reg_targets (P, 6|8) f32
+    (prepare_targets / compute_targets_for_locations[_obb], loss.py:262-441)."""
+    locations = _req(locations, torch.float32, "locations")
+    gt = _req(gt, torch.float32, "gt")
+    if len(n_points) != len(strides) or not 1 <= len(n_points) <= _lib.MAX_LEVELS:
+        raise ValueError(f"nerf_rpn_b200: FCOS targets take 1..{_lib.MAX_LEVELS} levels (object_sizes_of_interest has four rows, fcos/loss.py:263-268)")
+    if gt.dim() != 2 or gt.shape[1] not in (6, 7) or locations.shape != (sum(n_points), 3):
+        raise ValueError("nerf_rpn_b200: gt must be (G, 6|7) and locations (sum(n_points), 3)")
+    d = FcosTargetDesc()
+    d.n_levels = len(n_points)
+    for l, (n, s) in enumerate(zip(n_points, strides)):
+        d.n_points[l], d.stride[l] = int(n), int(s)
+        d.size_lo[l], d.size_hi[l] = FCOS_SIZES_OF_INTEREST[l]
+    d.center_sampling_radius = float(center_sampling_radius)
+    d.norm_reg_targets = int(bool(norm_reg_targets))
+    p, dim = locations.shape[0], 8 if gt.shape[1] == 7 else 6
+    labels = torch.empty((p,), dtype=torch.float32, device=locations.device)
+    reg = torch.empty((p, dim), dtype=torch.float32, device=locations.device)
+    check(lib().nrpn_fcos_targets(ctypes.byref(d), _ptr(locations), _ptr(gt) if gt.shape[0] else ctypes.c_void_p(0), int(gt.shape[0]), int(gt.shape[1]),
+                                  _ptr(labels), _ptr(reg), _stream()), "fcos_targets")
+    return labels, reg
+
+
+def fcos_loss_sums(box_cls, box_regression, centerness, labels: torch.Tensor, reg_targets: torch.Tensor, mask: Optional[torch.Tensor],
+                   loss_type: str, use_obb: bool, additional_l1: bool, want_grad: bool = True):
+    """The head's per-level NCDHW outputs + targets (N,P) / (N,P,D) [+ mask (N,P) u8] -> (sums (8,) f64 on the device, centerness targets (N,P),
+    raw gradients (dcls, dreg, dctr lists shaped like the inputs) or None); see nrpn_fcos_loss in include/nerf_rpn_b200.h."""
+    n_lvl = len(box_cls)
+    if not (n_lvl == len(box_regression) == len(centerness)) or not 1 <= n_lvl <= _lib.MAX_LEVELS:
+        raise ValueError("nerf_rpn_b200: FCOS loss takes the same 1..4 levels for box_cls, box_regression and centerness")
+    dim = 8 if use_obb else 6
+    n = box_cls[0].shape[0]
+    d = FcosLossDesc()
+    d.n_levels, d.n_images, d.use_obb, d.additional_l1 = n_lvl, n, int(bool(use_obb)), int(bool(additional_l1))
+    d.loss_type = FCOS_LOSS_TYPES[loss_type]
+    grads = ([], [], []) if want_grad else None
+    total = 0
+    for l in range(n_lvl):
+        c, r, t = _req(box_cls[l], torch.float32, "box_cls"), _req(box_regression[l], torch.float32, "box_regression"), _req(centerness[l], torch.float32, "centerness")
+        pl = c[0, 0].numel()
+        if c.shape[:2] != (n, 1) or r.shape[:2] != (n, dim) or t.shape[:2] != (n, 1) or r[0, 0].numel() != pl or t[0, 0].numel() != pl:
+            raise ValueError("nerf_rpn_b200: FCOS head outputs must be (N,1,w,l,h), (N,6|8,w,l,h), (N,1,w,l,h) per level")
+        L = d.level[l]
+        L.cls, L.reg, L.ctr, L.n_points = c.data_ptr(), r.data_ptr(), t.data_ptr(), pl
+        if want_grad:
+            for lst, src in zip(grads, (c, r, t)):
+                lst.append(torch.empty_like(src))
+            L.dcls, L.dreg, L.dctr = grads[0][l].data_ptr(), grads[1][l].data_ptr(), grads[2][l].data_ptr()
+        total += pl
+    labels = _req(labels, torch.float32, "labels"); reg_targets = _req(reg_targets, torch.float32, "reg_targets")
+    if labels.shape != (n, total) or reg_targets.shape != (n, total, dim):
+        raise ValueError("nerf_rpn_b200: labels must be (N, P) and reg_targets (N, P, 6|8) with P = all levels' locations")
+    if mask is not None:
+        mask = _req(mask, torch.uint8, "mask")
+        if mask.shape != (n, total):
+            raise ValueError("nerf_rpn_b200: mask must be (N, P)")
+    dev = labels.device
+    sums = torch.empty((8,), dtype=torch.float64, device=dev)
+    ct = torch.empty((n, total), dtype=torch.float32, device=dev)
+    ws = _workspace(lib().nrpn_fcos_loss_workspace_bytes(), dev)
+    check(lib().nrpn_fcos_loss(ctypes.byref(d), _ptr(labels), _ptr(reg_targets), _ptr(mask), _ptr(ct), _ptr(sums), _ptr(ws), ws.numel(), _stream()),
+          "fcos_loss")
+    return sums, ct, grads
 
 
 # ------------------------------------------------------------------------------------------------ Swin

@@ -540,7 +540,84 @@ def gen_losses():
     np.savez_compressed(os.path.join(OUT, "loss_small.npz"), **out)
 
 
+FCOS_LOSS_CASES = (  # name, rotated, iou_loss_type, center_sampling_radius, additional_l1, batch
+    ("aabb_iou", False, "iou", 1.5, False, 2), ("aabb_giou", False, "giou", 1.5, False, 2), ("aabb_linear", False, "linear_iou", 0.0, False, 1),
+    ("aabb_sl1", False, "smooth_l1", 1.5, False, 2), ("obb_sl1", True, "smooth_l1", 1.5, False, 2), ("obb_iou_l1", True, "iou", 1.5, True, 2),
+    ("obb_nocs", True, "smooth_l1", 0.0, False, 1), ("aabb_empty", False, "iou", 1.5, False, 2))
+
+
+def fcos_loss_inputs(name, rotated, batch, seed):
+    """Synthetic head outputs + ground truth of one case (shared by tools/make_golden.py and the tests through the stored arrays)."""
+    g = torch.Generator().manual_seed(seed)
+    mesh = (64, 80, 48)
+    strides = [4, 8, 16, 32]
+    grids = [tuple(int(math.ceil(m / s)) for m in mesh) for s in strides]
+    D = 8 if rotated else 6
+    cls = [torch.randn(batch, 1, *gr, generator=g) * 2 - 2 for gr in grids]
+    reg = [torch.cat([torch.rand(batch, 6, *gr, generator=g) * 3 + 0.1] + ([torch.randn(batch, 2, *gr, generator=g) * 0.3] if rotated else []), 1)
+           for gr in grids]
+    ctr = [torch.randn(batch, 1, *gr, generator=g) for gr in grids]
+    sizes = [mesh, (52, 80, 40)][:batch]
+    gts = []
+    for b in range(batch):
+        n = 0 if name.endswith("empty") and b == 1 else 9
+        sz = torch.tensor(sizes[b], dtype=torch.float32)
+        ext = torch.rand(n, 3, generator=g) * torch.tensor([60.0, 60.0, 40.0]) + 5.0                  # sizes 5 .. 65: every level's range is hit
+        ctrs = torch.rand(n, 3, generator=g) * sz
+        if rotated:
+            gts.append(torch.cat([ctrs, ext, (torch.rand(n, 1, generator=g) - 0.5) * math.pi], 1))
+        else:
+            gts.append(torch.cat([ctrs - ext / 2, ctrs + ext / 2], 1))
+    if rotated and batch > 0 and len(gts[0]) > 1:
+        gts[0][0, 6] = 0.0                                                                            # the "theta too small" branch of encode_fcos_obb
+        gts[0][1, 6] = 1e-4
+    return strides, grids, sizes, cls, reg, ctr, gts
+
+
+def gen_fcos_loss():
+    """FCOSLossComputation of the unmodified reference (fcos/loss.py) on CPU: targets (level first), the three losses and their gradients w.r.t. the
+    head outputs, AABB and OBB heads, every loss type that runs on a GPU-less box (the rotated IoU goes through the stub vertex sort)."""
+    import argparse
+    from model.fcos.fcos import FCOSModule
+    out = {}
+    for ci, (name, rotated, loss_type, radius, add_l1, batch) in enumerate(FCOS_LOSS_CASES):
+        strides, grids, sizes, cls, reg, ctr, gts = fcos_loss_inputs(name, rotated, batch, 100 + ci)
+        args = argparse.Namespace(num_convs=1, norm_reg_targets=True, centerness_on_reg=True, rotated_bbox=rotated, pre_nms_thresh=0.0,
+                                  pre_nms_top_n=100, nms_thresh=0.3, fpn_post_nms_top_n=100, min_size=0.0, center_sampling_radius=radius,
+                                  iou_loss_type=loss_type, use_additional_l1_loss=add_l1, proj2d_loss_weight=0.0)
+        mod = FCOSModule(args, 256, strides)
+        locations = mod.compute_locations(cls)
+        masks = mod.compute_padding_masks(locations, sizes) if batch > 1 else None
+        for t in cls + reg + ctr:
+            t.requires_grad_(True)
+        ev = mod.loss_evaluator
+        labels, reg_targets = ev.prepare_targets(locations, [t.clone() for t in gts])
+        l_cls, l_reg, l_ctr = ev(locations, cls, reg, ctr, gts, masks)
+        (l_cls + 2.0 * l_reg + 3.0 * l_ctr).backward()
+        out[f"{name}/losses"] = np.array([l_cls.item(), l_reg.item(), l_ctr.item()], np.float64)
+        for l in range(4):
+            out[f"{name}/cls{l}"] = cls[l].detach().numpy(); out[f"{name}/reg{l}"] = reg[l].detach().numpy(); out[f"{name}/ctr{l}"] = ctr[l].detach().numpy()
+            out[f"{name}/dcls{l}"] = cls[l].grad.numpy(); out[f"{name}/dreg{l}"] = reg[l].grad.numpy(); out[f"{name}/dctr{l}"] = ctr[l].grad.numpy()
+            out[f"{name}/labels{l}"] = labels[l].numpy(); out[f"{name}/reg_targets{l}"] = reg_targets[l].numpy()
+            if masks is not None:
+                out[f"{name}/mask{l}"] = masks[l].numpy()
+        for b in range(batch):
+            out[f"{name}/gt{b}"] = gts[b].numpy()
+        out[f"{name}/sizes"] = np.array(sizes, np.int64)
+        print(name, "losses", out[f"{name}/losses"], "positives", int(sum((lb > 0).sum() for lb in labels)))
+    from model.fcos.utils import decode_fcos_obb
+    g = torch.Generator().manual_seed(77)
+    loc = torch.rand(3000, 3, generator=g) * 100
+    reg = torch.cat([torch.rand(3000, 6, generator=g) * 12 + 0.05, torch.randn(3000, 2, generator=g) * 0.35], 1)
+    reg[:40, 6:] = 0.0                                                       # vertices at the edge midpoints: theta = pi/4 exactly-ish
+    reg[40:80, 6] = 0.5; reg[40:80, 7] = -0.5                                # clamped to the AABB corner: an axis-aligned box
+    out["decode/loc"], out["decode/reg"], out["decode/boxes"] = loc.numpy(), reg.numpy(), decode_fcos_obb(loc, reg).numpy()
+    np.savez_compressed(os.path.join(OUT, "fcos_loss.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--fcos-loss-only" in sys.argv:
+        gen_fcos_loss(); sys.exit(0)
     if "--losses-only" in sys.argv:
         sys.path.insert(0, ROOT); gen_losses(); sys.exit(0)
     if "--targets-only" in sys.argv:
@@ -565,3 +642,4 @@ if __name__ == "__main__":
     sys.path.insert(0, ROOT); gen_recall()
     gen_targets()
     gen_losses()
+    gen_fcos_loss()
