@@ -298,7 +298,7 @@ int nrpn_rowmax_f32(const float *m, int rows, int cols, float *maxv, int32_t *ar
  * (G, N) matrix.  anchors (N,6) f32 [x1,y1,z1,x2,y2,z2]; gt (G,6) AABB or (G,7) OBB; valid: optional (N) u8 padding mask
  * (0 = anchor in a padded voxel: enters the matcher as -1.0, label -1).  labels (N) f32 in {1, 0, -1}; matched_idxs (N) i64:
  * the matcher's output (GT index, -1 below low, -2 between thresholds); gather gt[clamp(idx, 0)] for the matched boxes.
- * G <= 1024.  G == 0 is the caller's "background mesh" case (rpn.py:246-250) and is rejected here. */
+ * Any G (ground truth streamed through shared memory in chunks of 1 024).  G == 0 is the caller's "background mesh" case (rpn.py:246-250) and is rejected here. */
 size_t nrpn_assign_targets_workspace_bytes(int n_anchors, int n_gt);
 int nrpn_assign_targets(const float *anchors, int n_anchors, const float *gt, int n_gt, int gt_dim, const uint8_t *valid,
                         float high_threshold, float low_threshold, int allow_low_quality_matches, float *labels,

@@ -51,9 +51,6 @@ __global__ void __launch_bounds__(kTgtThreads) tgt_match_kernel(TgtDev P) {
     __shared__ float sgt[kTgtMaxGt][6];
     __shared__ unsigned smax[kTgtMaxGt];          // pass 1: CTA-local per-GT maxima; pass 2: the global maxima
     const int t = threadIdx.x, lane = t & 31;
-    for (int i = t; i < P.g * 6; i += kTgtThreads) sgt[i / 6][i % 6] = P.gt6[i];
-    for (int i = t; i < P.g; i += kTgtThreads) smax[i] = (PASS == 1) ? 0u : P.gmax[i];
-    __syncthreads();
     const long base = ((long)blockIdx.x * kTgtThreads) * kTgtPerThread;
     float a[kTgtPerThread][6];
     bool live[kTgtPerThread], masked[kTgtPerThread];
@@ -67,23 +64,35 @@ __global__ void __launch_bounds__(kTgtThreads) tgt_match_kernel(TgtDev P) {
         for (int k = 0; k < 6; ++k) a[u][k] = live[u] ? P.anchors[i * 6 + k] : 0.0f;
         best[u] = -INFINITY; arg[u] = 0; tie[u] = false;
     }
-    for (int g = 0; g < P.g; ++g) {
-        float m = -INFINITY;
+    // the ground truth goes through shared memory in chunks of kTgtMaxGt boxes (one chunk for every scene of the reference's datasets)
+    for (int g0 = 0; g0 < P.g; g0 += kTgtMaxGt) {
+        const int gc = min(kTgtMaxGt, P.g - g0);
+        if (g0 > 0) __syncthreads();
+        for (int i = t; i < gc * 6; i += kTgtThreads) sgt[i / 6][i % 6] = P.gt6[(size_t)g0 * 6 + i];
+        for (int i = t; i < gc; i += kTgtThreads) smax[i] = (PASS == 1) ? 0u : P.gmax[g0 + i];
+        __syncthreads();
+        for (int g = 0; g < gc; ++g) {
+            float m = -INFINITY;
 #pragma unroll
-        for (int u = 0; u < kTgtPerThread; ++u) {
-            if (!live[u]) continue;
-            const float iou = masked[u] ? -1.0f : iou3d_aabb(sgt[g], a[u]);
+            for (int u = 0; u < kTgtPerThread; ++u) {
+                if (!live[u]) continue;
+                const float iou = masked[u] ? -1.0f : iou3d_aabb(sgt[g], a[u]);
+                if (PASS == 1) {
+                    if (iou > best[u]) { best[u] = iou; arg[u] = g0 + g; }     // first maximum, like torch.max on CPU
+                    m = fmaxf(m, iou);
+                } else {
+                    tie[u] = tie[u] || (float_to_ordered(iou) == smax[g]);
+                }
+            }
             if (PASS == 1) {
-                if (iou > best[u]) { best[u] = iou; arg[u] = g; }     // first maximum, like torch.max on CPU
-                m = fmaxf(m, iou);
-            } else {
-                tie[u] = tie[u] || (float_to_ordered(iou) == smax[g]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (lane == 0 && m > -INFINITY) atomicMax(&smax[g], float_to_ordered(m));
             }
         }
         if (PASS == 1) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (lane == 0 && m > -INFINITY) atomicMax(&smax[g], float_to_ordered(m));
+            __syncthreads();
+            for (int i = t; i < gc; i += kTgtThreads) if (smax[i]) atomicMax(&P.gmax[g0 + i], smax[i]);
         }
     }
     if (PASS == 1) {
@@ -92,8 +101,6 @@ __global__ void __launch_bounds__(kTgtThreads) tgt_match_kernel(TgtDev P) {
             const long i = base + (long)u * kTgtThreads + t;
             if (live[u]) { P.best_val[i] = best[u]; P.best_idx[i] = arg[u]; }
         }
-        __syncthreads();
-        for (int i = t; i < P.g; i += kTgtThreads) if (smax[i]) atomicMax(&P.gmax[i], smax[i]);
     } else {
 #pragma unroll
         for (int u = 0; u < kTgtPerThread; ++u) {
@@ -132,7 +139,6 @@ int nrpn_assign_targets(const float* anchors, int n_anchors, const float* gt, in
     if (n_anchors == 0) return NRPN_OK;
     if (n_gt == 0) return NRPN_ERR_INVALID;          // the reference handles empty targets before the matcher (rpn.py:246-250)
     if (!anchors || !gt || !labels || !matched_idxs || !workspace) return NRPN_ERR_INVALID;
-    if (n_gt > kTgtMaxGt) return NRPN_ERR_UNSUPPORTED;
     if (workspace_bytes < nrpn_assign_targets_workspace_bytes(n_anchors, n_gt)) return NRPN_ERR_WORKSPACE;
     char* b = reinterpret_cast<char*>(align_up((size_t)workspace, 256));
     TgtDev P;

@@ -75,3 +75,25 @@ def test_assign_targets_module_api_and_full_size():
     strong = vals >= np.float32(0.35)
     assert np.all(lab_c[sel][strong] == 1) and np.all(idx_c[sel][strong] == m.argmax(axis=0)[strong])
     assert np.all(lab_c[sel][vals < np.float32(0.2)] != -1)          # below the low threshold: background, or a low-quality positive
+
+
+@pytest.mark.parametrize("dim", [6, 7])
+def test_assign_targets_streams_more_than_one_chunk_of_ground_truth(dim):
+    """G = 2 500 boxes (three shared-memory chunks of 1 024; the reference has no limit): labels and matcher indices == the oracle, incl. the
+    first-maximum rule and the low-quality matches across chunk borders (duplicated boxes in different chunks tie exactly)."""
+    from nerf_rpn_b200 import ops
+    rng = np.random.default_rng(40 + dim)
+    anchors = small_anchors()
+    ext = float(anchors[:, 3:].max())
+    G = 2500
+    c, half = rng.random((G, 3)) * ext, rng.random((G, 3)) * 6 + 1.5
+    gt = (np.concatenate([c - half, c + half], 1) if dim == 6 else np.concatenate([c, 2 * half, (rng.random((G, 1)) - 0.5) * np.pi], 1)).astype(np.float32)
+    gt[1500:1600] = gt[100:200]                       # exact duplicates in another chunk: equal IoUs, the lower index must win
+    gt[2400:2450] = gt[1100:1150]
+    valid = rng.random(anchors.shape[0]) > 0.1
+    for v in (None, valid):
+        ol, oi = T.assign(anchors.numpy(), gt, v, 0.35, 0.2)
+        lab, idx = ops.assign_targets(anchors.cuda(), torch.from_numpy(gt).cuda(), None if v is None else torch.from_numpy(v).cuda(), 0.35, 0.2, True)
+        np.testing.assert_array_equal(lab.cpu().numpy(), ol)
+        np.testing.assert_array_equal(idx.cpu().numpy(), oi)
+        assert (ol == 1).sum() > 500
