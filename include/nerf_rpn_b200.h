@@ -286,7 +286,7 @@ int nrpn_fcos_proposals(const nrpn_fcos_desc *desc /*host*/, float *boxes, float
  * overlaps: (n_proposals, n_gt) fp32 IoU matrix (nrpn_iou3d_matrix of the score-sorted, limit-truncated proposals against the
  * ground truth); gt_overlaps: min(n_proposals, n_gt) fp32, the IoU recorded at each step of the reference loop (the rest of
  * the reference's zero-initialised vector is left to the caller).  Ties: lowest ground-truth index, then lowest proposal
- * index, as torch.max on CPU.  n_proposals <= 32 768, n_gt <= 4 096. */
+ * index, as torch.max on CPU.  n_proposals <= 262 144, n_gt <= 4 096. */
 int nrpn_recall_match(const float *overlaps, int n_proposals, int n_gt, float *gt_overlaps, nrpn_stream_t stream);
 /* Row-wise maximum and first arg-max of a (rows, cols) fp32 matrix (torch.max(dim=1) tie rule): the per-detection step of
  * evaluate_box_proposals_ap (eval.py:355-358) for a whole scene's IoU matrix. */

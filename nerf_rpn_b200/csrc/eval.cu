@@ -10,7 +10,8 @@
 namespace nrpn {
 
 constexpr int kMatchThreads = 256;
-constexpr int kMatchMaxGt = 4096;
+constexpr int kMatchMaxGt = 4096;            // 12 bits of the key
+constexpr int kMatchMaxProposals = 262144;   // one bit each in (dynamic) shared memory: 32 KB; the key has 20 bits for them
 
 // key: larger is better. value (fp32, -1 for used) ordered, then lower gt, then lower proposal.
 __device__ __forceinline__ unsigned long long match_key(float v, int gt, int prop) {
@@ -21,7 +22,7 @@ __device__ __forceinline__ unsigned long long match_key(float v, int gt, int pro
 __global__ void __launch_bounds__(kMatchThreads) recall_match_kernel(const float* __restrict__ overlaps, int P, int G,
                                                                      float* __restrict__ gt_overlaps) {
     __shared__ unsigned long long red[kMatchThreads / 32];
-    __shared__ unsigned row_used[32768 / 32];               // n_proposals <= 32 768 (host check)
+    extern __shared__ unsigned row_used[];                  // ceil(P / 32) words (host check: P <= kMatchMaxProposals)
     __shared__ unsigned col_used[kMatchMaxGt / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < (P + 31) / 32; i += kMatchThreads) row_used[i] = 0u;
@@ -87,8 +88,8 @@ int nrpn_recall_match(const float* overlaps, int n_proposals, int n_gt, float* g
     if (n_proposals < 0 || n_gt < 0) return NRPN_ERR_INVALID;
     if (n_proposals == 0 || n_gt == 0) return NRPN_OK;
     if (!overlaps || !gt_overlaps) return NRPN_ERR_INVALID;
-    if (n_gt > kMatchMaxGt || n_proposals > 32768) return NRPN_ERR_UNSUPPORTED;
-    recall_match_kernel<<<1, kMatchThreads, 0, (cudaStream_t)stream>>>(overlaps, n_proposals, n_gt, gt_overlaps);
+    if (n_gt > kMatchMaxGt || n_proposals > kMatchMaxProposals) return NRPN_ERR_UNSUPPORTED;
+    recall_match_kernel<<<1, kMatchThreads, (size_t)ceil_div(n_proposals, 32) * sizeof(unsigned), (cudaStream_t)stream>>>(overlaps, n_proposals, n_gt, gt_overlaps);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
