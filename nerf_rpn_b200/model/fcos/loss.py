@@ -13,13 +13,15 @@ The rotated-IoU term of the OBB head (RotatedIOULoss, loss.py:134-181) is evalua
 decode (model/coder_torch.py decode_fcos_obb) + cal_iou_3d / cal_giou_3d / cal_diou_3d (fused IoU kernel and its backward), and its gradient is added to
 the regression gradient of the node.  The two normalisers (positives, sum of centerness targets; `reduce_sum`, loss.py:202-208) are all-reduced
 as ONE two-element fp64 tensor and stay on the device: the axis-aligned / smooth-L1 paths never synchronise the host.
-The 2-D projection loss (proj2d_loss_weight > 0, loss.py:452-485) is not built.  No CPU path: CUDA tensors only."""
+The 2-D projection loss of the OBB head (proj2d_loss_weight > 0, loss.py:452-485; model/proj2d.py) rides on the same gathered positives.
+No CPU path: CUDA tensors only."""
 from typing import List, Optional
 
 import torch
 
 from ... import ops
 from ..coder_torch import decode_fcos_obb
+from ..proj2d import fcos_projection_loss
 
 INF = 100000000
 
@@ -65,13 +67,14 @@ class _FCOSLoss(torch.autograd.Function):
     def forward(ctx, ev, labels, reg_targets, mask, n_levels, *heads):
         box_cls, box_reg, ctrness = heads[:n_levels], heads[n_levels:2 * n_levels], heads[2 * n_levels:]
         rotated_iou = ev.use_obb and ev.iou_loss_type != "smooth_l1"
+        proj2d = ev.use_obb and ev.proj2d_loss_weight > 0
         kernel_type = "iou" if ev.iou_loss_type == "diou" else ev.iou_loss_type          # diou exists for the rotated head only (ignored by the kernel there)
         want_grad = any(ctx.needs_input_grad[5:])
         sums, ct, grads = ops.fcos_loss_sums([t.detach() for t in box_cls], [t.detach() for t in box_reg], [t.detach() for t in ctrness], labels,
                                              reg_targets, mask, kernel_type, ev.use_obb, ev.use_additional_l1_loss, want_grad=want_grad)
         reg_raw = sums[3] + sums[5]
-        if rotated_iou:
-            reg_raw = reg_raw + _FCOSLoss._rotated_term(ev, box_reg, labels, reg_targets, mask, ct, grads)
+        if rotated_iou or proj2d:
+            reg_raw = reg_raw + _FCOSLoss._positives_term(ev, rotated_iou, proj2d, box_reg, labels, reg_targets, mask, ct, grads)
         num_pos_avg, sum_ct_avg = normalisers(torch.stack([sums[1], sums[2]]), ev.world_size)
         loss_cls = sums[0] / num_pos_avg
         loss_ctr = sums[4] / num_pos_avg
@@ -85,8 +88,9 @@ class _FCOSLoss(torch.autograd.Function):
         return loss_cls.float(), loss_reg.float(), loss_ctr.float()
 
     @staticmethod
-    def _rotated_term(ev, box_reg, labels, reg_targets, mask, ct, grads):
-        """sum_i w_i * RotatedIOULoss_i over the positives; its gradient w.r.t. the 8 regression channels is accumulated into grads[1]."""
+    def _positives_term(ev, rotated_iou, proj2d, box_reg, labels, reg_targets, mask, ct, grads):
+        """The terms of the OBB head evaluated on the gathered positives: sum_i w_i * RotatedIOULoss_i and / or proj2d_loss_weight * the 2-D
+        projection loss; the gradient w.r.t. the 8 regression channels is accumulated into grads[1]."""
         pos = labels > 0 if mask is None else (labels > 0) & (mask != 0)
         idx = torch.nonzero(pos)                                                         # host sync: the positives' count sizes the gather
         if idx.shape[0] == 0:
@@ -106,7 +110,12 @@ class _FCOSLoss(torch.autograd.Function):
         pred = torch.cat(preds).requires_grad_(grads is not None)
         tgt, w = reg_targets[n_idx[order], q_idx[order]], ct[n_idx[order], q_idx[order]]
         with torch.enable_grad():
-            raw = (rotated_iou_losses(pred, tgt, ev.iou_loss_type) * w).sum()
+            raw = pred.sum() * 0
+            if rotated_iou:
+                raw = raw + (rotated_iou_losses(pred, tgt, ev.iou_loss_type) * w).sum()
+            if proj2d:
+                zero = torch.zeros(pred.shape[0], 3, device=pred.device)
+                raw = raw + ev.proj2d_loss_weight * fcos_projection_loss(decode_fcos_obb(zero, pred), decode_fcos_obb(zero, tgt), w)
             if grads is not None:
                 g, = torch.autograd.grad(raw, pred)
         if grads is not None:
@@ -140,8 +149,6 @@ class FCOSLossComputation(object):
                  proj2d_loss_weight=0.0):
         if iou_loss_type not in ("smooth_l1", "iou", "linear_iou", "giou") and not (use_obb and iou_loss_type == "diou"):
             raise NotImplementedError(f"iou_loss_type {iou_loss_type!r}: the reference implements iou / linear_iou / giou (+ diou for OBB) and smooth_l1")
-        if proj2d_loss_weight > 0:
-            raise NotImplementedError("nerf_rpn_b200: the 2-D projection loss (proj2d_loss_weight > 0, fcos/loss.py:452-485) is not built")
         if len(fpn_strides) > 4:
             raise NotImplementedError("object_sizes_of_interest has four rows (fcos/loss.py:263-268): at most 4 levels")
         self.fpn_strides = list(fpn_strides)

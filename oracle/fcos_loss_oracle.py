@@ -6,6 +6,7 @@ Follows nerf_rpn/model/fcos/loss.py of the reference:
   targets                    prepare_targets :262-316, compute_targets_for_locations[_obb] :318-441, get_sample_region :213-260
   centerness_targets         compute_centerness_targets :443-450
   aabb_iou_losses            IOULoss.forward :78-131 (per box, before the weighted sum)
+  projection_loss_2d         compute_2d_projection_loss :452-485 (+ decode_fcos_obb, get_w2cs, project, obb2points_3d of fcos/utils.py)
   loss                       FCOSLossComputation.__call__ :487-591 (single rank: world_size 1), AABB head or OBB head with smooth-L1;
                              the rotated-IoU term of the OBB head (RotatedIOULoss :134-181) needs the reference's CUDA-only vertex sort and
                              is checked against the staged reference itself on the GPU box (tests/test_gpu_fcos_loss.py).
@@ -124,7 +125,53 @@ def flatten_level_first(per_level, channels):
     return torch.cat([t.permute(0, 2, 3, 4, 1).reshape(-1, channels) for t in per_level], 0)
 
 
-def loss(box_cls, box_regression, centerness, labels, reg_targets, masks, iou_loss_type, use_obb=False, use_additional_l1_loss=False):
+def decode_obb(reg: torch.Tensor) -> torch.Tensor:
+    """decode_fcos_obb (fcos/utils.py:12-61) at location 0: (K, 8) -> (K, 7)."""
+    x0, y0, z0, x1, y1, z1 = -reg[:, 0], -reg[:, 1], -reg[:, 2], reg[:, 3], reg[:, 4], reg[:, 5]
+    vx = torch.clamp((x1 + x0) / 2 + reg[:, 6] * (x1 - x0), min=x0, max=x1)
+    vy = torch.clamp((y1 + y0) / 2 + reg[:, 7] * (y1 - y0), min=y0, max=y1)
+    c = torch.stack([(x0 + x1) / 2, (y0 + y1) / 2, (z0 + z1) / 2], 1)
+    v0, v1 = torch.stack([vx, y1], 1) - c[:, :2], torch.stack([x1, vy], 1) - c[:, :2]
+    d0, d1 = v0.norm(dim=1), v1.norm(dim=1)
+    dm = torch.max(d0, d1)
+    v0 = v0 / (d0[:, None] + 1e-7) * dm[:, None] + c[:, :2]
+    v1 = v1 / (d1[:, None] + 1e-7) * dm[:, None] + c[:, :2]
+    mid = (v0 + v1) / 2 - c[:, :2]
+    mx = torch.where((mid[:, 0] == 0) & (mid[:, 1] == 0), torch.full_like(mid[:, 0], 1e-7), mid[:, 0])
+    return torch.stack([c[:, 0], c[:, 1], c[:, 2], mid.norm(dim=1) * 2, (v0 - v1).norm(dim=1), z1 - z0, torch.atan2(mid[:, 1], mx)], 1)
+
+
+def projection_2d(points: torch.Tensor, res=160.0) -> torch.Tensor:
+    """get_w2cs + project (fcos/utils.py:300-377): (M, 3) -> (4 M, 2) pixels in the four corner cameras of a `res` scene."""
+    K = torch.tensor([[600.0, 0, 320.0], [0, 600.0, 240.0], [0, 0, 1.0]])
+    ctr = np.full(3, res / 2)
+    out = []
+    for dx, dy in ((res, res), (res, -res), (-res, res), (-res, -res)):
+        cam = ctr + np.array([dx, dy, res])
+        zax = (cam - ctr) / np.linalg.norm(cam - ctr)
+        xax = np.cross([0.0, 0.0, 1.0], zax); xax /= np.linalg.norm(xax)
+        yax = np.cross(zax, xax); yax /= np.linalg.norm(yax)
+        c2w = np.eye(4); c2w[:3, :3] = np.stack([xax, yax, zax], 1); c2w[:3, 3] = cam
+        w2c = torch.tensor(np.linalg.inv(c2w), dtype=torch.float32)
+        camc = w2c @ torch.cat([points, torch.ones(len(points), 1)], 1).t()
+        pic = K @ camc[:3]
+        out.append((pic[:2] / pic[2]).t())
+    return torch.cat(out, 0)
+
+
+def projection_loss_2d(reg: torch.Tensor, rt: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """compute_2d_projection_loss (fcos/loss.py:452-485)."""
+    def pts(b):
+        v = torch.stack([b[:, 3] / 2 * torch.cos(b[:, 6]) - b[:, 4] / 2 * torch.sin(b[:, 6]), b[:, 3] / 2 * torch.sin(b[:, 6]) + b[:, 4] / 2 * torch.cos(b[:, 6]),
+                         b[:, 5] / 2], 1)
+        return torch.cat([b[:, :3] - v, b[:, :3] + v], 0)
+    l2 = torch.nn.functional.smooth_l1_loss(projection_2d(pts(decode_obb(reg))), projection_2d(pts(decode_obb(rt))), beta=1 / 9, reduction="none") / 160
+    factor = l2.shape[0] // weights.shape[0]
+    return (l2 * weights[:, None].repeat(factor, 1)).sum() / (factor * l2.shape[1])
+
+
+def loss(box_cls, box_regression, centerness, labels, reg_targets, masks, iou_loss_type, use_obb=False, use_additional_l1_loss=False,
+         proj2d_loss_weight=0.0):
     """box_cls / box_regression / centerness: lists of (N, C, w, l, h) torch tensors (may require grad); labels / reg_targets: per scene
     (P,) / (P, D) numpy from `targets`; masks: None or list per level of (N, P_l) bool.  -> (loss_cls, loss_reg, loss_centerness) and the
     raw sums dict.  OBB with an IoU-type loss returns loss_reg WITHOUT the rotated-IoU term (see the module docstring)."""
@@ -166,5 +213,7 @@ def loss(box_cls, box_regression, centerness, labels, reg_targets, masks, iou_lo
         add = (torch.nn.functional.smooth_l1_loss(reg[:, 6:], rt[:, 6:], reduction="none") * ct[:, None]).sum()
         sums["add_l1"] = add
         loss_reg = loss_reg + add / ct.sum()
+    if use_obb and proj2d_loss_weight > 0:
+        loss_reg = loss_reg + projection_loss_2d(reg, rt, ct) / ct.sum() * proj2d_loss_weight
     sums["bce"] = torch.nn.functional.binary_cross_entropy_with_logits(ctr, ct, reduction="sum")
     return loss_cls, loss_reg, sums["bce"] / n_pos, sums

@@ -15,10 +15,11 @@ import torch
 from oracle import fcos_loss_oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CASES = {  # name: (rotated, iou_loss_type, center_sampling_radius, additional_l1, batch)   == tools/make_golden.py FCOS_LOSS_CASES
-    "aabb_iou": (False, "iou", 1.5, False, 2), "aabb_giou": (False, "giou", 1.5, False, 2), "aabb_linear": (False, "linear_iou", 0.0, False, 1),
-    "aabb_sl1": (False, "smooth_l1", 1.5, False, 2), "obb_sl1": (True, "smooth_l1", 1.5, False, 2), "obb_iou_l1": (True, "iou", 1.5, True, 2),
-    "obb_nocs": (True, "smooth_l1", 0.0, False, 1), "aabb_empty": (False, "iou", 1.5, False, 2)}
+CASES = {  # name: (rotated, iou_loss_type, center_sampling_radius, additional_l1, batch, proj2d_loss_weight)   == tools/make_golden.py FCOS_LOSS_CASES
+    "aabb_iou": (False, "iou", 1.5, False, 2, 0.0), "aabb_giou": (False, "giou", 1.5, False, 2, 0.0), "aabb_linear": (False, "linear_iou", 0.0, False, 1, 0.0),
+    "aabb_sl1": (False, "smooth_l1", 1.5, False, 2, 0.0), "obb_sl1": (True, "smooth_l1", 1.5, False, 2, 0.0), "obb_iou_l1": (True, "iou", 1.5, True, 2, 0.0),
+    "obb_nocs": (True, "smooth_l1", 0.0, False, 1, 0.0), "aabb_empty": (False, "iou", 1.5, False, 2, 0.0),
+    "obb_sl1_p2d": (True, "smooth_l1", 1.5, False, 2, 0.5), "obb_iou_p2d": (True, "iou", 1.5, True, 1, 0.25)}
 STRIDES = [4, 8, 16, 32]
 LOSS_TYPE = {"smooth_l1": 0, "iou": 1, "linear_iou": 2, "giou": 3}
 WEIGHTS = (1.0, 2.0, 3.0)          # the golden gradients are those of loss_cls + 2 loss_reg + 3 loss_centerness
@@ -30,8 +31,8 @@ def golden(golden_dir):
 
 
 def load_case(g, name):
-    rotated, loss_type, radius, add_l1, batch = CASES[name]
-    c = dict(rotated=rotated, loss_type=loss_type, radius=radius, add_l1=add_l1, batch=batch)
+    rotated, loss_type, radius, add_l1, batch, proj2d = CASES[name]
+    c = dict(rotated=rotated, loss_type=loss_type, radius=radius, add_l1=add_l1, batch=batch, proj2d=proj2d)
     for k in ("cls", "reg", "ctr", "dcls", "dreg", "dctr", "labels", "reg_targets"):
         c[k] = [g[f"{name}/{k}{l}"] for l in range(4)]
     c["mask"] = [g[f"{name}/mask{l}"] for l in range(4)] if batch > 1 else None
@@ -68,7 +69,7 @@ def test_oracle_loss_and_gradients_match_reference(golden, name):
     c = load_case(golden, name)
     cls, reg, ctr = ([torch.tensor(a, requires_grad=True) for a in c[k]] for k in ("cls", "reg", "ctr"))
     lab, rt = per_scene(c["labels"], c["n_per"], c["batch"]), per_scene(c["reg_targets"], c["n_per"], c["batch"])
-    l_cls, l_reg, l_ctr, _ = O.loss(cls, reg, ctr, lab, rt, c["mask"], c["loss_type"], c["rotated"], c["add_l1"])
+    l_cls, l_reg, l_ctr, _ = O.loss(cls, reg, ctr, lab, rt, c["mask"], c["loss_type"], c["rotated"], c["add_l1"], c["proj2d"])
     rotated_iou = c["rotated"] and c["loss_type"] != "smooth_l1"
     np.testing.assert_allclose(l_cls.item(), c["losses"][0], rtol=1e-5)
     np.testing.assert_allclose(l_ctr.item(), c["losses"][2], rtol=1e-5)
@@ -146,7 +147,7 @@ def test_device_functions_loss_and_gradients(shim, golden, name):
     assert n_pos == kept.sum() and n_pos > 0
     np.testing.assert_allclose(ct[kept].sum(dtype=np.float64), sum_ct, rtol=1e-6)
     assert (ct[~kept] == 0).all()
-    rotated_iou = c["rotated"] and c["loss_type"] != "smooth_l1"
+    rotated_iou = (c["rotated"] and c["loss_type"] != "smooth_l1") or c["proj2d"] > 0     # terms of the gathered positives: not the kernel's
     np.testing.assert_allclose(focal / max(n_pos, 1.0), c["losses"][0], rtol=1e-5)
     np.testing.assert_allclose(bce / max(n_pos, 1.0), c["losses"][2], rtol=1e-5)
     if not rotated_iou:
@@ -157,7 +158,7 @@ def test_device_functions_loss_and_gradients(shim, golden, name):
         np.testing.assert_allclose(WEIGHTS[2] * grads["ctr"][l] / max(n_pos, 1.0), c["dctr"][l], rtol=2e-4, atol=1e-7)
         if not rotated_iou:
             np.testing.assert_allclose(WEIGHTS[1] * grads["reg"][l] / sum_ct, c["dreg"][l], rtol=2e-4, atol=1e-7)
-        else:                                       # only the alpha / beta smooth-L1 is the kernel's: channels 0..5 wait for the rotated-IoU term
+        elif c["loss_type"] != "smooth_l1":         # only the alpha / beta smooth-L1 is the kernel's: channels 0..5 wait for the rotated-IoU term
             assert (grads["reg"][l][:, :6] == 0).all() and np.abs(grads["reg"][l][:, 6:]).sum() > 0 or l == 3
 
 
@@ -221,7 +222,7 @@ def _module(c, world_size=1):
     from nerf_rpn_b200.model.fcos.fcos import FCOSModule
     args = argparse.Namespace(num_convs=1, norm_reg_targets=True, centerness_on_reg=True, rotated_bbox=c["rotated"], pre_nms_thresh=0.0, pre_nms_top_n=100,
                               nms_thresh=0.3, fpn_post_nms_top_n=100, min_size=0.0, center_sampling_radius=c["radius"], iou_loss_type=c["loss_type"],
-                              use_additional_l1_loss=c["add_l1"], proj2d_loss_weight=0.0)
+                              use_additional_l1_loss=c["add_l1"], proj2d_loss_weight=c["proj2d"])
     return FCOSModule(args, 256, STRIDES, world_size=world_size)
 
 
@@ -265,11 +266,11 @@ def test_module_host_logic_against_reference(host_ops, golden, name):
     for l in range(4):
         np.testing.assert_allclose(cls[l].grad.numpy(), c["dcls"][l], rtol=2e-4, atol=1e-7)
         np.testing.assert_allclose(ctr[l].grad.numpy(), c["dctr"][l], rtol=2e-4, atol=1e-7)
-    if not rotated_iou:
+    if not rotated_iou:                  # incl. obb_sl1_p2d: decode + projection are torch ops and run here as they do on the GPU
         np.testing.assert_allclose(losses["loss_reg"].item(), c["losses"][1], rtol=1e-5)
         for l in range(4):
-            np.testing.assert_allclose(reg[l].grad.numpy(), c["dreg"][l], rtol=2e-4, atol=1e-7)
-    else:                                # stand-in: sum_i ct_i |pred_i - tgt_i|^2 / sum ct (+ the alpha / beta smooth-L1), gradient 2 ct (pred - tgt) / sum ct
+            np.testing.assert_allclose(reg[l].grad.numpy(), c["dreg"][l], rtol=2e-4, atol=2e-7)
+    elif c["proj2d"] == 0:                                # stand-in: sum_i ct_i |pred_i - tgt_i|^2 / sum ct (+ the alpha / beta smooth-L1), gradient 2 ct (pred - tgt) / sum ct
         N = c["batch"]
         labs = np.stack(per_scene(c["labels"], c["n_per"], N)); rts = np.stack(per_scene(c["reg_targets"], c["n_per"], N))
         m = np.ones_like(labs, bool) if c["mask"] is None else np.concatenate([mm.reshape(N, -1) for mm in c["mask"]], 1)

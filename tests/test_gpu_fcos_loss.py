@@ -28,21 +28,21 @@ def golden(golden_dir):
     return np.load(os.path.join(golden_dir, "fcos_loss.npz"))
 
 
-def fcos_args(rotated, loss_type, radius, add_l1):
+def fcos_args(rotated, loss_type, radius, add_l1, proj2d=0.0):
     return argparse.Namespace(num_convs=1, norm_reg_targets=True, centerness_on_reg=True, rotated_bbox=rotated, pre_nms_thresh=0.0, pre_nms_top_n=100,
                               nms_thresh=0.3, fpn_post_nms_top_n=100, min_size=0.0, center_sampling_radius=radius, iou_loss_type=loss_type,
-                              use_additional_l1_loss=add_l1, proj2d_loss_weight=0.0)
+                              use_additional_l1_loss=add_l1, proj2d_loss_weight=proj2d)
 
 
-def our_module(rotated, loss_type, radius, add_l1):
+def our_module(rotated, loss_type, radius, add_l1, proj2d=0.0):
     from nerf_rpn_b200.model.fcos.fcos import FCOSModule
-    return FCOSModule(fcos_args(rotated, loss_type, radius, add_l1), 256, STRIDES)
+    return FCOSModule(fcos_args(rotated, loss_type, radius, add_l1, proj2d), 256, STRIDES)
 
 
 @pytest.mark.parametrize("name", list(CASES))
 def test_kernels_match_reference_golden(golden, name):
     c = load_case(golden, name)
-    mod = our_module(c["rotated"], c["loss_type"], c["radius"], c["add_l1"])
+    mod = our_module(c["rotated"], c["loss_type"], c["radius"], c["add_l1"], c["proj2d"])
     cls, reg, ctr = ([torch.tensor(a, device="cuda", requires_grad=True) for a in c[k]] for k in ("cls", "reg", "ctr"))
     locs = mod.compute_locations(cls)
     sizes = golden[f"{name}/sizes"]
@@ -58,18 +58,19 @@ def test_kernels_match_reference_golden(golden, name):
     _, _, losses = mod._forward_train(locs, cls, reg, ctr, gts, masks)
     got = [losses[k].item() for k in ("loss_cls", "loss_reg", "loss_centerness")]
     rotated_iou = c["rotated"] and c["loss_type"] != "smooth_l1"
+    gathered = rotated_iou or c["proj2d"] > 0                    # terms evaluated on the gathered positives (torch ops around the IoU kernels)
     np.testing.assert_allclose(got[0], c["losses"][0], rtol=1e-5)
     np.testing.assert_allclose(got[2], c["losses"][2], rtol=1e-5)
-    np.testing.assert_allclose(got[1], c["losses"][1], rtol=2e-4 if rotated_iou else 1e-5)      # golden rotated IoU: CPU run with a stand-in vertex sort
+    np.testing.assert_allclose(got[1], c["losses"][1], rtol=2e-4 if rotated_iou else 2e-5)      # golden rotated IoU: CPU run with a stand-in vertex sort
     (WEIGHTS[0] * losses["loss_cls"] + WEIGHTS[1] * losses["loss_reg"] + WEIGHTS[2] * losses["loss_centerness"]).backward()
     for l in range(4):
         np.testing.assert_allclose(cls[l].grad.cpu().numpy(), c["dcls"][l], rtol=2e-4, atol=1e-7)
         np.testing.assert_allclose(ctr[l].grad.cpu().numpy(), c["dctr"][l], rtol=2e-4, atol=1e-7)
-        if not rotated_iou:
+        if not gathered:
             np.testing.assert_allclose(reg[l].grad.cpu().numpy(), c["dreg"][l], rtol=2e-4, atol=1e-7)
-    if rotated_iou:
+    if gathered:
         a = torch.cat([t.grad.flatten() for t in reg]).cpu().double(); b = torch.cat([torch.tensor(t).flatten() for t in c["dreg"]]).double()
-        assert ((a - b).norm() / b.norm()).item() < 3e-3
+        assert ((a - b).norm() / b.norm()).item() < (3e-3 if rotated_iou else 1e-4)
 
 
 def test_deterministic_and_forward_only(golden):
@@ -104,19 +105,20 @@ def scene_inputs(rotated, batch, seed, mesh=(200, 200, 130), n_gt=30):
     return grids, sizes, cls, reg, ctr, gts
 
 
-FULL_CASES = [(False, "iou", 1.5, False, 2), (False, "giou", 0.0, False, 1), (False, "linear_iou", 1.5, False, 1), (False, "smooth_l1", 1.5, False, 2),
-              (True, "smooth_l1", 1.5, False, 2), (True, "iou", 1.5, True, 2), (True, "linear_iou", 1.5, False, 1), (True, "giou", 1.5, True, 1),
-              (True, "diou", 0.0, False, 1)]
+FULL_CASES = [(False, "iou", 1.5, False, 2, 0.0), (False, "giou", 0.0, False, 1, 0.0), (False, "linear_iou", 1.5, False, 1, 0.0),
+              (False, "smooth_l1", 1.5, False, 2, 0.0), (True, "smooth_l1", 1.5, False, 2, 0.0), (True, "iou", 1.5, True, 2, 0.0),
+              (True, "linear_iou", 1.5, False, 1, 0.0), (True, "giou", 1.5, True, 1, 0.0), (True, "diou", 0.0, False, 1, 0.0),
+              (True, "smooth_l1", 1.5, False, 1, 0.5), (True, "iou", 1.5, True, 1, 0.3)]
 
 
 @needs_ref
-@pytest.mark.parametrize("rotated,loss_type,radius,add_l1,batch", FULL_CASES)
-def test_full_size_against_reference_on_the_gpu(rotated, loss_type, radius, add_l1, batch):
+@pytest.mark.parametrize("rotated,loss_type,radius,add_l1,batch,proj2d", FULL_CASES)
+def test_full_size_against_reference_on_the_gpu(rotated, loss_type, radius, add_l1, batch, proj2d):
     """FCOSLossComputation of the staged reference, run on this GPU, at BASELINE config 3's locations (94 k per scene)."""
     ref = ref_gpu.load()
     grids, sizes, cls, reg, ctr, gts = scene_inputs(rotated, batch, 40 + len(loss_type) + int(rotated))
-    rmod = ref.fcos.FCOSModule(fcos_args(rotated, loss_type, radius, add_l1), 256, STRIDES).cuda()
-    mod = our_module(rotated, loss_type, radius, add_l1)
+    rmod = ref.fcos.FCOSModule(fcos_args(rotated, loss_type, radius, add_l1, proj2d), 256, STRIDES).cuda()
+    mod = our_module(rotated, loss_type, radius, add_l1, proj2d)
     locs = rmod.compute_locations(cls)
     for a, b in zip(mod.compute_locations(cls), locs):
         assert torch.equal(a, b)
@@ -143,19 +145,20 @@ def test_full_size_against_reference_on_the_gpu(rotated, loss_type, radius, add_
     g_cls, g_reg, g_ctr = mod.loss_evaluator(locs, cls, reg, ctr, gts, masks)
     (WEIGHTS[0] * g_cls + WEIGHTS[1] * g_reg + WEIGHTS[2] * g_ctr).backward()
     rotated_iou = rotated and loss_type != "smooth_l1"
+    gathered = rotated_iou or proj2d > 0
     torch.testing.assert_close(g_cls, w_cls, rtol=2e-5, atol=0)
     torch.testing.assert_close(g_ctr, w_ctr, rtol=2e-5, atol=0)
     torch.testing.assert_close(g_reg, w_reg, rtol=1e-4 if rotated_iou else 2e-5, atol=0)
     for l in range(4):
         torch.testing.assert_close(cls[l].grad, want_g[0][l], rtol=2e-4, atol=1e-8)
         torch.testing.assert_close(ctr[l].grad, want_g[2][l], rtol=2e-4, atol=1e-8)
-        if not rotated_iou:
+        if not gathered:
             torch.testing.assert_close(reg[l].grad, want_g[1][l], rtol=2e-4, atol=1e-8)
-    if rotated_iou:
+    if gathered:
         a = torch.cat([t.grad.flatten() for t in reg]).double(); b = torch.cat([t.flatten() for t in want_g[1]]).double()
         # without centre sampling every location inside a box is a positive, also those whose predicted box barely touches the target: there the
         # intersection polygon changes its vertex set within the finite-difference step of the IoU backward (measured 7.6e-3 on the B200)
-        assert ((a - b).norm() / b.norm()).item() < (3e-3 if radius > 0 else 2e-2)
+        assert ((a - b).norm() / b.norm()).item() < ((3e-3 if radius > 0 else 2e-2) if rotated_iou else 1e-4)
         assert (a != 0).sum() == (b != 0).sum() or abs(int((a != 0).sum()) - int((b != 0).sum())) < 0.01 * int((b != 0).sum())
 
 

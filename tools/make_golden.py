@@ -543,7 +543,8 @@ def gen_losses():
 FCOS_LOSS_CASES = (  # name, rotated, iou_loss_type, center_sampling_radius, additional_l1, batch
     ("aabb_iou", False, "iou", 1.5, False, 2), ("aabb_giou", False, "giou", 1.5, False, 2), ("aabb_linear", False, "linear_iou", 0.0, False, 1),
     ("aabb_sl1", False, "smooth_l1", 1.5, False, 2), ("obb_sl1", True, "smooth_l1", 1.5, False, 2), ("obb_iou_l1", True, "iou", 1.5, True, 2),
-    ("obb_nocs", True, "smooth_l1", 0.0, False, 1), ("aabb_empty", False, "iou", 1.5, False, 2))
+    ("obb_nocs", True, "smooth_l1", 0.0, False, 1), ("aabb_empty", False, "iou", 1.5, False, 2),
+    ("obb_sl1_p2d", True, "smooth_l1", 1.5, False, 2, 0.5), ("obb_iou_p2d", True, "iou", 1.5, True, 1, 0.25))
 
 
 def fcos_loss_inputs(name, rotated, batch, seed):
@@ -580,11 +581,13 @@ def gen_fcos_loss():
     import argparse
     from model.fcos.fcos import FCOSModule
     out = {}
-    for ci, (name, rotated, loss_type, radius, add_l1, batch) in enumerate(FCOS_LOSS_CASES):
+    for ci, case in enumerate(FCOS_LOSS_CASES):
+        name, rotated, loss_type, radius, add_l1, batch = case[:6]
+        proj2d = case[6] if len(case) > 6 else 0.0
         strides, grids, sizes, cls, reg, ctr, gts = fcos_loss_inputs(name, rotated, batch, 100 + ci)
         args = argparse.Namespace(num_convs=1, norm_reg_targets=True, centerness_on_reg=True, rotated_bbox=rotated, pre_nms_thresh=0.0,
                                   pre_nms_top_n=100, nms_thresh=0.3, fpn_post_nms_top_n=100, min_size=0.0, center_sampling_radius=radius,
-                                  iou_loss_type=loss_type, use_additional_l1_loss=add_l1, proj2d_loss_weight=0.0)
+                                  iou_loss_type=loss_type, use_additional_l1_loss=add_l1, proj2d_loss_weight=proj2d)
         mod = FCOSModule(args, 256, strides)
         locations = mod.compute_locations(cls)
         masks = mod.compute_padding_masks(locations, sizes) if batch > 1 else None
