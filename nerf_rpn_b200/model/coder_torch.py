@@ -10,6 +10,19 @@ _MAX_RATIO = abs(math.log(16 / 1000))
 _PI = 3.141592                      # the reference's literal (misc.py:8)
 
 
+_XFORM_CLIP = math.log(2000.0)      # AABBCoder.bbox_xform_clip (coder/AABB_coder.py:66)
+
+
+def decode_aabb(anchors: torch.Tensor, deltas: torch.Tensor) -> torch.Tensor:
+    """AABBCoder.decode_single (coder/AABB_coder.py:86-137), differentiable: anchors (P,6), deltas (P,6) (dx,dy,dz,dw,dh,dd) -> (P,6) corners.
+    Used by the 2-D projection loss of the axis-aligned head (model/proj2d.py); inference decodes in csrc/rpn_decode.cuh."""
+    size = anchors[:, 3:] - anchors[:, :3]
+    ctr = anchors[:, :3] + 0.5 * size
+    centre = deltas[:, :3] * size + ctr
+    half = 0.5 * (torch.exp(deltas[:, 3:].clamp(max=_XFORM_CLIP)) * size)
+    return torch.cat([centre - half, centre + half], 1)
+
+
 def decode_obb(anchors: torch.Tensor, deltas: torch.Tensor) -> torch.Tensor:
     """anchors (P,6) [x1,y1,z1,x2,y2,z2], deltas (P,8) (dx,dy,dz,dw,dh,dd,da,db) -> (P,7) (x,y,z,w,h,d,theta)."""
     dx, dy, dz, dw, dh, dd, da, db = deltas.unbind(1)

@@ -26,15 +26,15 @@ class _RPNTrainStep(torch.autograd.Function):
     def forward(ctx, eng, grids, targets, *params):
         n, c, X, Y, Z = grids.shape
         plan = eng.plan(n, (X, Y, Z))
-        plan.forward_loss(grids, targets, 1.0, 1.0)
+        plan.forward_loss(grids, targets, 1.0, 1.0, 0.0, eval_2d=True)          # the 2-D projection loss is reported like the reference does
         ctx.eng, ctx.plan = eng, plan
         losses = eng.losses.clone()
-        return losses[0].clone(), losses[1].clone()          # fresh 0-dim tensors (run_rpn.py:385 scales them in place)
+        return losses[0].clone(), losses[1].clone(), eng.loss_2d.clone()          # fresh 0-dim tensors (run_rpn.py:385-386 scales them in place)
 
     @staticmethod
-    def backward(ctx, g_obj, g_reg):
+    def backward(ctx, g_obj, g_reg, g_2d):
         eng, plan = ctx.eng, ctx.plan
-        plan.loss_grad(float(g_obj), float(g_reg))          # the loss weights arrive as the upstream gradients (run_rpn.py:385-387)
+        plan.loss_grad(float(g_obj), float(g_reg), float(g_2d))          # the loss weights arrive as the upstream gradients (run_rpn.py:385-387)
         plan.backward()
         inv = 1.0 / eng.loss_scale
         grads = []
@@ -146,9 +146,8 @@ class NeRFRegionProposalNetwork(nn.Module):
         eng.sync_parameters()
         grids = torch.stack([m if m.is_cuda else m.cuda() for m in meshes], 0).float()
         params = list(self.backbone.parameters()) + list(self.rpn.head.parameters())
-        l_obj, l_reg = _RPNTrainStep.apply(eng, grids, [t for t in targets], *params)
-        zero = torch.zeros((), dtype=torch.float32, device=grids.device)    # 2-D projection loss: weight 0 in every shipped recipe, not evaluated
-        return [None, None, None], {"loss_objectness": l_obj, "loss_rpn_box_reg": l_reg, "loss_rpn_box_reg_2d": zero}, None
+        l_obj, l_reg, l_2d = _RPNTrainStep.apply(eng, grids, [t for t in targets], *params)
+        return [None, None, None], {"loss_objectness": l_obj, "loss_rpn_box_reg": l_reg, "loss_rpn_box_reg_2d": l_2d}, None
 
     def forward(self, meshes, targets=None, objectness_output_paths=None):
         if self.training:

@@ -165,7 +165,7 @@ class RPNTrainEngine:
 
     def __init__(self, model, precision: str = "bf16", lr: float = 1e-4, weight_decay: float = 0.01, betas=(0.9, 0.999), eps: float = 1e-8,
                  clip_grad_norm: float = 0.1, reg_loss_weight: float = 5.0, process_group=None, bucket_mb: float = 32.0,
-                 loss_scale: Optional[float] = None, seed: Optional[int] = None):
+                 loss_scale: Optional[float] = None, seed: Optional[int] = None, reg_loss_weight_2d: float = 0.0):
         if precision not in ("bf16", "fp16"):
             raise ValueError("training runs with bf16 (default) or fp16 (with a static loss scale) 16-bit activations / gradients")
         bb, rpn = model.backbone, model.rpn
@@ -186,6 +186,7 @@ class RPNTrainEngine:
         self.loss_scale = float(loss_scale) if loss_scale is not None else (1024.0 if precision == "fp16" else 1.0)
         self.lr, self.wd, self.betas, self.eps, self.clip = lr, weight_decay, betas, eps, clip_grad_norm
         self.w_reg = reg_loss_weight
+        self.w_2d = reg_loss_weight_2d      # --reg_loss_weight_2d (run_rpn.py:91, default 0): the 2-D projection loss is evaluated only when it is non-zero
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if (process_group is not None or
                                                                          (torch.distributed.is_available() and torch.distributed.is_initialized())) else 1
@@ -205,6 +206,7 @@ class RPNTrainEngine:
         self._norm_ws = torch.empty(lib().nrpn_grad_norm_workspace_bytes(), dtype=torch.uint8, device=self.device)
         self._red_ws = torch.empty(lib().nrpn_chan_reduce_workspace_bytes(2048), dtype=torch.uint8, device=self.device)
         self.losses = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self.loss_2d = torch.zeros((), dtype=torch.float32, device=self.device)        # loss_rpn_box_reg_2d (unweighted), when evaluated
         self.overlap_allreduce = True       # False: leave the gradient all-reduce to the caller (DDP wrapping the autograd compat path)
         self.gen = None
         if seed is not None:
@@ -682,8 +684,8 @@ class _TrainPlan:
         perm2 = torch.randperm(negative.numel(), device=negative.device, generator=g)[:num_neg]
         return positive[perm1].contiguous(), negative[perm2].contiguous()
 
-    def forward_loss(self, grids, targets, w_obj=1.0, w_reg=None):
-        """Forward launches, target assignment, sampling, losses; fills d(pred) for the weighted sum w_obj * L_obj + w_reg * L_reg."""
+    def forward_loss(self, grids, targets, w_obj=1.0, w_reg=None, w_2d=None, eval_2d=False):
+        """Forward launches, target assignment, sampling, losses; fills d(pred) for the weighted sum w_obj * L_obj + w_reg * L_reg (+ w_2d * L_2d)."""
         eng, n = self.eng, self.n
         if ops.is_channels_last_grid(grids) or grids.is_contiguous():
             self._src = grids
@@ -705,10 +707,11 @@ class _TrainPlan:
             pos, neg = self._sample(labels) if forced is None else (forced[i][0].contiguous(), forced[i][1].contiguous())
             samples.append((pos, neg, gt[idx[pos].clamp(min=0)].contiguous()))
         self.last_samples = samples
-        self.loss_grad(w_obj, eng.w_reg if w_reg is None else w_reg)
+        self.loss_grad(w_obj, eng.w_reg if w_reg is None else w_reg, eng.w_2d if w_2d is None else w_2d, eval_2d)
 
-    def loss_grad(self, w_obj, w_reg):
-        """(Re)computes the two losses and d(w_obj * L_obj + w_reg * L_reg)/d(pred) * loss_scale for the samples of the last forward."""
+    def loss_grad(self, w_obj, w_reg, w_2d=0.0, eval_2d=False):
+        """(Re)computes the losses and d(w_obj * L_obj + w_reg * L_reg + w_2d * L_2d)/d(pred) * loss_scale for the samples of the last forward.
+        The 2-D projection loss (rpn.py:421-453) is evaluated when its weight is non-zero or eval_2d asks for its value."""
         eng, L, n = self.eng, lib(), self.n
         samples = self.last_samples
         norm = float(sum(p.numel() + q.numel() for p, q, _ in samples))
@@ -724,6 +727,55 @@ class _TrainPlan:
                   "rpn_loss")
         if eng.reg_loss_type != "smooth_l1":
             self._iou_reg_loss(float(w_reg), max(norm, 1.0))
+        eng.loss_2d.zero_()
+        if float(w_2d) != 0.0 or eval_2d:
+            self._proj2d_loss(float(w_2d))
+
+    def _gather_deltas(self, i, pos):
+        """The head's regression deltas (fp32 predictor output) of the flat anchor indices `pos` of mesh i, and where they live."""
+        A, code = self.eng.A, self.eng.code
+        level, vox, a = self._split_anchor_index(pos)
+        cols = (A + a * code).view(-1, 1) + torch.arange(code, device=pos.device).view(1, -1)
+        deltas = torch.empty((pos.numel(), code), dtype=torch.float32, device=self.eng.device)
+        for l, p in enumerate(self.pred_levels):
+            m = level == l
+            if m.any():
+                deltas[m] = p[i].reshape(-1, 128)[vox[m].view(-1, 1), cols[m]]
+        return deltas, level, vox, cols
+
+    def _proj2d_loss(self, w_2d):
+        """loss_rpn_box_reg_2d (rpn.py:421-453): the sampled positives' DECODED boxes and their matched ground truth, two points each, projected into
+        four cameras, smooth-L1 / positives / max mesh dimension (model/proj2d.py); with a non-zero weight its gradient w.r.t. the deltas (autograd
+        through the torch decode) is ADDED to d(pred).  A step without any positive gives 0 here (0 / 0 = NaN in the reference)."""
+        from .model.coder_torch import decode_aabb, decode_obb
+        from .model.proj2d import rpn_projection_loss
+        eng = self.eng
+        n_pos = sum(int(p.numel()) for p, _, _ in self.last_samples)
+        if n_pos == 0:
+            return
+        res = float(max(self.dims))
+        anchors = self._anchors()
+        total = torch.zeros((), dtype=torch.float32, device=eng.device)
+        for i, (pos, neg, gtp) in enumerate(self.last_samples):
+            if pos.numel() == 0:
+                continue
+            deltas, level, vox, cols = self._gather_deltas(i, pos)
+            with torch.enable_grad():
+                d = deltas.detach().requires_grad_(w_2d != 0.0)
+                boxes = decode_obb(anchors[pos], d) if eng.rotated else decode_aabb(anchors[pos], d)
+                loss = rpn_projection_loss(boxes, gtp, n_pos, res)
+                if w_2d != 0.0:
+                    (g,) = torch.autograd.grad(loss, d)
+            total = total + loss.detach()
+            if w_2d != 0.0:
+                g = g * (w_2d * eng.loss_scale)
+                for l, dp in enumerate(self.dpred_levels):
+                    m = level == l
+                    if m.any():
+                        view = dp[i].reshape(-1, 128)
+                        rows = vox[m].view(-1, 1)
+                        view[rows, cols[m]] = (view[rows, cols[m]].float() + g[m]).to(view.dtype)
+        eng.loss_2d.copy_(total)
 
     # ---- IoU-type regression losses (RotatedIOULoss, rpn.py:133-165: "iou", "linear_iou", "giou", "diou") on the <= 128 sampled positives per mesh
     def _split_anchor_index(self, idx):

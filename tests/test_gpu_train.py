@@ -434,3 +434,88 @@ def test_iou_regression_loss_vs_reference_rotated_iou_loss(loss_type):
     assert err <= 2e-2 * gwant.abs().max().item()
     grads = [eng.grad_of(p) for p in head.bbox_pred.parameters()]
     assert all(torch.isfinite(g).all() and g.abs().sum() > 0 for g in grads)
+
+
+@pytest.mark.parametrize("rotated", [True, False])
+def test_projection_2d_loss_vs_reference(rotated):
+    """loss_rpn_box_reg_2d (rpn.py:421-453, --reg_loss_weight_2d): the engine's value and its gradient w.r.t. the head's deltas against the REFERENCE's own
+    coder + get_w2cs / project / obb2points_3d + autograd evaluated on the engine's fp32 deltas (same sampled positives); the whole step's value against
+    the reference network in fp32; and the drop-in loop (losses dict with a grad_fn, weight applied outside the model as run_rpn.py:385-387 does)."""
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref not staged")
+    from nerf_rpn_b200.model.anchor import AnchorGenerator3D, RPNHead
+    from nerf_rpn_b200.model.feature_extractor import Bottleneck, ResNet_FPN_256
+    from nerf_rpn_b200.model.nerf_rpn import NeRFRegionProposalNetwork
+    from nerf_rpn_b200.train import RPNTrainEngine
+    ref = ref_gpu.load()
+    layers, dims = (2, 1, 1, 1), (64, 96, 80)
+    grid, gt = _planted(dims, 12, 11, rotated)
+    grid, gt = grid.cuda(), gt.cuda()
+    rm = ref_gpu.build_reference_model(rotated=rotated, seed=0, layers=layers, rpn_fg_iou_thresh=0.35, rpn_bg_iou_thresh=0.2).cuda().train()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(123)
+        _, ref_losses, _ = rm([grid], [gt])
+        backbone = ResNet_FPN_256(Bottleneck, list(layers), input_dim=4, is_max_pool=True)
+        head = RPNHead(256, 13, 4, rotate=rotated)
+        backbone.load_state_dict(rm.backbone.state_dict()); head.load_state_dict(rm.rpn.head.state_dict())
+        model = NeRFRegionProposalNetwork(backbone, AnchorGenerator3D(ref_gpu.ANCHOR_SIZES, ref_gpu.ASPECT), head, rpn_fg_iou_thresh=0.35, rpn_bg_iou_thresh=0.2,
+                                          rotated_bbox=rotated).cuda().train()
+        w2d = 0.7
+        eng = RPNTrainEngine(model, precision="fp16", lr=1e-4, weight_decay=0.01, clip_grad_norm=0.1, reg_loss_weight=0.0, reg_loss_weight_2d=w2d)
+        plan = eng.plan(1, dims)
+        torch.manual_seed(123)
+        eng.forward_backward(grid[None], [gt])
+        torch.cuda.synchronize()
+        pos, neg, gtp = plan.last_samples[0]
+        assert pos.numel() >= 8
+        deltas, level, vox, cols = plan._gather_deltas(0, pos)
+        dgot = torch.empty_like(deltas)
+        for l in range(len(plan.pred_levels)):
+            m = level == l
+            if m.any():
+                dgot[m] = plan.dpred_levels[l][0].reshape(-1, 128)[vox[m].view(-1, 1), cols[m]].float()
+        # the reference's own pieces on the engine's deltas
+        d = deltas.clone().requires_grad_(True)
+        boxes = rm.rpn.box_coder.decode_single(d, plan._anchors()[pos])
+        res = max(dims)
+        if rotated:
+            from_ref = ref.rpn.obb2points_3d
+            p3, t3 = from_ref(boxes), from_ref(gtp)
+        else:
+            p3, t3 = torch.cat([boxes[:, :3], boxes[:, 3:]], 0), torch.cat([gtp[:, :3], gtp[:, 3:]], 0)
+        ones = torch.ones(p3.shape[0], 1, device="cuda")
+        K = torch.tensor([[600.0, 0, 320.0], [0, 600.0, 240.0], [0, 0, 1.0]], device="cuda")
+        pp, tt = [], []
+        for pose in ref.rpn.get_w2cs(res=res):
+            pp.append(ref.rpn.project(K, pose, torch.cat([p3, ones], 1))); tt.append(ref.rpn.project(K, pose, torch.cat([t3, ones], 1)))
+        want = F.smooth_l1_loss(torch.cat(pp), torch.cat(tt), beta=1 / 9, reduction="sum") / pos.numel() / res
+        (gwant,) = torch.autograd.grad(want, d)
+        got = eng.loss_2d.item()
+        print(f"[2d rotated={rotated}] engine {got:.6f}  reference code on the engine's deltas {want.item():.6f}  reference network fp32 "
+              f"{ref_losses['loss_rpn_box_reg_2d'].item():.6f}  ({pos.numel()} positives)")
+        assert abs(got - want.item()) <= 1e-4 * abs(want.item()) + 1e-7
+        assert abs(got - ref_losses["loss_rpn_box_reg_2d"].item()) <= 0.05 * abs(ref_losses["loss_rpn_box_reg_2d"].item())
+        err = (dgot / (w2d * eng.loss_scale) - gwant).abs().max().item()
+        print(f"[2d rotated={rotated}] d loss / d deltas: max abs err {err:.3e} of scale {gwant.abs().max().item():.3e}")
+        assert err <= 1e-2 * gwant.abs().max().item()                      # d(pred) is 16-bit
+        # weight 0 (every shipped recipe): nothing is evaluated on the native path
+        eng0 = RPNTrainEngine(model, precision="fp16", reg_loss_weight=5.0)
+        torch.manual_seed(123)
+        eng0.forward_backward(grid[None], [gt])
+        assert eng0.loss_2d.item() == 0.0
+        # the drop-in loop: the weight arrives as the upstream gradient
+        model._train_engine = None
+        torch.manual_seed(123)
+        _, losses, _ = model([grid], [gt])
+        l2d = losses["loss_rpn_box_reg_2d"]
+        assert l2d.requires_grad and abs(l2d.item() - ref_losses["loss_rpn_box_reg_2d"].item()) <= 0.1 * abs(ref_losses["loss_rpn_box_reg_2d"].item())
+        losses["loss_rpn_box_reg"] *= 5.0
+        losses["loss_rpn_box_reg_2d"] *= 0.3
+        (losses["loss_objectness"] + losses["loss_rpn_box_reg"] + losses["loss_rpn_box_reg_2d"]).backward()
+        gh = head.bbox_pred.weight.grad
+        assert gh is not None and torch.isfinite(gh).all() and gh.abs().sum() > 0
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

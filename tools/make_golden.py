@@ -618,7 +618,43 @@ def gen_fcos_loss():
     np.savez_compressed(os.path.join(OUT, "fcos_loss.npz"), **out)
 
 
+def gen_proj2d():
+    """loss_rpn_box_reg_2d through the reference's own RegionProposalNetwork.compute_loss (rpn.py:372-456) on CPU, both heads: value and gradient w.r.t. the
+    decoded boxes (the path the 2-D projection loss back-propagates through, rpn.py:516-518), plus the coders' decode of the deltas."""
+    from model.coder import AABBCoder, MidpointOffsetCoder
+    from model.rpn import RegionProposalNetwork
+    out = {}
+    for kind, rotated, res in (("aabb", False, 200), ("obb", True, 160)):
+        g = torch.Generator().manual_seed(31 + int(rotated))
+        n, n_pos, n_neg = 600, 48, 300
+        ag = AnchorGenerator3D(ANCHOR_SIZES, ASPECT)
+        rpn = RegionProposalNetwork(ag, RPNHead(256, 13, 1, rotate=rotated), 0.35, 0.2, 256, 0.5, dict(training=100, testing=100),
+                                    dict(training=100, testing=100), 0.3, rotated_bbox=rotated)
+        c, half = torch.rand(n, 3, generator=g) * res, torch.rand(n, 3, generator=g) * 20 + 2
+        anchors = torch.cat([c - half, c + half], 1)
+        deltas = (torch.randn(n, 8 if rotated else 6, generator=g) * 0.3).requires_grad_(True)
+        pred = rpn.box_coder.decode_single(deltas, anchors)
+        pred_leaf = pred.detach().clone().requires_grad_(True)
+        if rotated:
+            tgt = torch.cat([pred.detach()[:, :3] + torch.randn(n, 3, generator=g) * 3, pred.detach()[:, 3:6] * (torch.rand(n, 3, generator=g) + 0.5),
+                             (torch.rand(n, 1, generator=g) - 0.5) * math.pi], 1)
+        else:
+            tgt = pred.detach() + torch.randn(n, 6, generator=g) * 3
+        labels = torch.full((n,), -1.0)
+        labels[:n_pos] = 1.0; labels[n_pos:n_pos + n_neg] = 0.0
+        torch.manual_seed(3)
+        l_obj, l_3d, l_2d = rpn.compute_loss(torch.randn(n, 1, generator=g), deltas.detach(), [labels], [torch.zeros(n, deltas.shape[1])], pred_leaf, [tgt], res)
+        l_2d.backward()
+        out.update({f"{kind}_anchors": anchors.numpy(), f"{kind}_deltas": deltas.detach().numpy(), f"{kind}_decoded": pred.detach().numpy(),
+                    f"{kind}_target": tgt.numpy(), f"{kind}_loss_2d": np.float64(l_2d.item()), f"{kind}_dpred": pred_leaf.grad.numpy(),
+                    f"{kind}_n_pos": np.int64(n_pos), f"{kind}_res": np.int64(res)})
+        print("proj2d", kind, "loss_2d", l_2d.item(), "grad norm", float(pred_leaf.grad.norm()))
+    np.savez_compressed(os.path.join(OUT, "proj2d.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--proj2d-only" in sys.argv:
+        gen_proj2d(); sys.exit(0)
     if "--fcos-loss-only" in sys.argv:
         gen_fcos_loss(); sys.exit(0)
     if "--losses-only" in sys.argv:
@@ -646,3 +682,4 @@ if __name__ == "__main__":
     gen_targets()
     gen_losses()
     gen_fcos_loss()
+    gen_proj2d()
