@@ -5,7 +5,7 @@
 //                         masks and the volume matrix are never materialised.  16 B read per location, 4 + 24|32 B written.
 //   fcos_loss_kernel    : one thread per (scene, location): focal term of every location, and on the positives the centerness target,
 //                         its BCE, the centerness-weighted regression loss, all with their gradients written into the NCDHW layout the
-//                         head produced; six fp64 partial sums per CTA, added in CTA order by fcos_loss_final_kernel (deterministic).
+//                         head produced; six fp64 partial sums per CTA, added in a fixed order by fcos_loss_final_kernel (deterministic).
 // The per-element arithmetic is in fcos_loss.cuh (shared with tests/host_shim).
 #include <string.h>
 #include "common.cuh"
@@ -79,13 +79,16 @@ __global__ void __launch_bounds__(kFlThreads) fcos_loss_kernel(const FcosLossDev
     }
 }
 
-__global__ void fcos_loss_final_kernel(const double* __restrict__ partial, int blocks, double* __restrict__ sums) {
-    const int k = threadIdx.x;
-    if (k >= 8) return;
+// Warp k adds the CTA partials of sum k: lane l takes CTAs l, l + 32, ... in order, then a fixed shuffle tree -- the same order on every run
+// (a single thread walking the 592 partials took 26 us, half of the whole loss: profiles/r02_fcos_loss_ncu.md).
+__global__ void __launch_bounds__(256) fcos_loss_final_kernel(const double* __restrict__ partial, int blocks, double* __restrict__ sums) {
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double v = 0.0;
     if (k < kFlSums)
-        for (int b = 0; b < blocks; ++b) v += partial[(size_t)b * kFlSums + k];
-    sums[k] = v;
+        for (int b = lane; b < blocks; b += 32) v += partial[(size_t)b * kFlSums + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sums[k] = v;                 // k = 0..7; 6 and 7 are zero
 }
 
 }  // namespace nrpn
@@ -156,7 +159,7 @@ int nrpn_fcos_loss(const nrpn_fcos_loss_desc* d, const float* labels, const floa
     blocks = blocks < 1 ? 1 : (blocks > kFlMaxBlocks ? kFlMaxBlocks : blocks);
     fcos_loss_kernel<<<blocks, kFlThreads, 0, st>>>(P, partial);
     NRPN_LAUNCH_CHECK();
-    fcos_loss_final_kernel<<<1, 32, 0, st>>>(partial, blocks, sums);
+    fcos_loss_final_kernel<<<1, 256, 0, st>>>(partial, blocks, sums);
     NRPN_LAUNCH_CHECK();
     return NRPN_OK;
 }
