@@ -60,6 +60,9 @@ class ScenePipeline:
         """host_grids: iterable of pinned fp32 (4,W,L,H) tensors -- contiguous, or the dataset's views of (W,L,H,4) arrays (then the
         H2D copy is a plain memcpy of the on-disk layout and the stem packing reads it channels-last). Returns a list of (boxes, scores, levels) CPU tensors
         (or only the number of scenes processed when collect=False)."""
+        if self.model.engine() is not self.eng:            # hyper-parameters / precision of the model changed: its engine was rebuilt (engine() key)
+            raise RuntimeError("nerf_rpn_b200: the model's engine changed since this ScenePipeline was built (its pinned result buffers are sized "
+                               "for the old post_nms_top_n / box type): create a new ScenePipeline")
         cur = torch.cuda.current_stream(self.device)
         grids = list(host_grids)
         if len(grids) % self.batch:
