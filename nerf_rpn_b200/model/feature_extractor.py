@@ -96,8 +96,9 @@ class ResNet_FPN_256(EngineHolder, nn.Module):
 def _not_built(name):
     class _Missing(nn.Module):
         def __init__(self, *a, **k):
-            raise NotImplementedError(f"nerf_rpn_b200: backbone {name} is not implemented yet (round 1 covers "
-                                      "ResNet_FPN_256; see DESIGN.md 'what comes next')")
+            raise NotImplementedError(f"nerf_rpn_b200: backbone {name} is not implemented by the B200 engine (built: ResNet_FPN_256, VGG_FPN, "
+                                      "SwinTransformer_FPN -- the backbones of BASELINE.json's configurations; the name is importable because "
+                                      "run_rpn.py:18-20 imports it)")
     _Missing.__name__ = name
     return _Missing
 
