@@ -110,6 +110,17 @@ class FCOSModule(nn.Module):
             locations.append(grid + stride // 2)
         return locations
 
+    def output_objectness(self, box_cls, centerness, ori_sizes, output_paths):
+        """--output_voxel_scores of run_fcos.py (fcos.py:268-284): per scene an npz with one array per level, sqrt(sigmoid(cls) * sigmoid(centerness))
+        cropped to the scene's own extent ceil(size / stride).  File export: host-side plumbing on the head's outputs."""
+        for i in range(len(ori_sizes)):
+            all_levels = {}
+            for level in range(len(box_cls)):
+                score = torch.sqrt(box_cls[level][i].sigmoid() * centerness[level][i].sigmoid())
+                w, l, h = np.ceil(np.array(ori_sizes[i]) / self.fpn_strides[level]).astype(int)
+                all_levels[str(level)] = score[0, :w, :l, :h].cpu().numpy()
+            np.savez_compressed(output_paths[i], **all_levels)
+
     def compute_padding_masks(self, locations, ori_sizes):
         """fcos.py:252-266: per level (N, P_l) bool, True where the location lies inside the scene's own extent."""
         masks = []
@@ -155,8 +166,6 @@ class FCOSOverNeRF(EngineHolder, nn.Module):
         if self.training:
             raise NotImplementedError("nerf_rpn_b200: the FCOS training step (backward through the GroupNorm towers) is not built; the loss itself is: "
                                       "fcos_module.loss_evaluator(locations, box_cls, box_regression, centerness, targets, padding_masks)")
-        if objectness_output_paths is not None:
-            raise NotImplementedError("nerf_rpn_b200: --output_voxel_scores export is not implemented")
         original_mesh_sizes = []
         for mesh in meshes:
             val = mesh.shape[-3:]
@@ -167,6 +176,13 @@ class FCOSOverNeRF(EngineHolder, nn.Module):
         mesh_tensors = meshes[0].unsqueeze(0) if len(meshes) == 1 else torch.stack(meshes, dim=0)
         if not mesh_tensors.is_contiguous():
             mesh_tensors = mesh_tensors.contiguous()
+        if objectness_output_paths is not None:
+            # the export reads the head's class / centerness maps: the stand-alone (eager) forwards of the backbone and the head produce them as
+            # NCDHW fp32 tensors, next to the fused run below that produces the proposals (an export option, not the timed path)
+            with torch.no_grad():
+                feats = list(self.backbone(mesh_tensors))
+                box_cls, _, ctrness = self.fcos_module.head(feats)
+            self.fcos_module.output_objectness(box_cls, ctrness, original_mesh_sizes, objectness_output_paths)
         plan = self.engine().forward_device(mesh_tensors, original_mesh_sizes)
         torch.cuda.current_stream().wait_event(plan.done)
         counts = plan.out_count.tolist()

@@ -42,3 +42,30 @@ def test_fcos_module_mirror_seeds_and_keys(golden_dir):
     assert len(keys) == 2 * 4 * 4 + 6 + 5                      # 2 towers x 4 x (conv w,b + GN w,b) + 3 predictors + 5 scales
     with pytest.raises(NotImplementedError):
         model.train()(None)
+
+
+def test_output_objectness_export(tmp_path):
+    """FCOSModule.output_objectness (--output_voxel_scores of run_fcos.py, fcos.py:268-284): npz per scene, one array per level,
+    sqrt(sigmoid(cls) * sigmoid(centerness)) cropped to ceil(size / stride)."""
+    import argparse
+    import numpy as np
+    import torch
+    from nerf_rpn_b200.model.fcos.fcos import FCOSModule
+    args = argparse.Namespace(num_convs=1, norm_reg_targets=True, centerness_on_reg=True, rotated_bbox=True, pre_nms_thresh=0.0, pre_nms_top_n=10,
+                              nms_thresh=0.3, fpn_post_nms_top_n=10, min_size=0.0)
+    mod = FCOSModule(args, 256, [4, 8, 16, 32])
+    g = torch.Generator().manual_seed(0)
+    grids = [(10, 12, 8), (5, 6, 4), (3, 3, 2), (2, 2, 1)]
+    cls = [torch.randn(2, 1, *d, generator=g) for d in grids]
+    ctr = [torch.randn(2, 1, *d, generator=g) for d in grids]
+    sizes = [(40, 48, 32), (33, 20, 30)]
+    paths = [str(tmp_path / f"s{i}.npz") for i in range(2)]
+    mod.output_objectness(cls, ctr, sizes, paths)
+    for i, p in enumerate(paths):
+        z = np.load(p)
+        assert sorted(z.files) == ["0", "1", "2", "3"]
+        for l, s in enumerate([4, 8, 16, 32]):
+            w, ll, h = [int(np.ceil(v / s)) for v in sizes[i]]
+            want = np.sqrt(1 / (1 + np.exp(-cls[l][i, 0].numpy().astype(np.float64))) / (1 + np.exp(-ctr[l][i, 0].numpy().astype(np.float64))))[:w, :ll, :h]
+            assert z[str(l)].shape == (w, ll, h)
+            np.testing.assert_allclose(z[str(l)], want, rtol=1e-5)
