@@ -319,3 +319,77 @@ def test_normalisers_all_reduce_two_ranks_gloo():
     for rank, n_pos, s_ct, none_pos, none_ct in out:
         assert n_pos == 1.5 and s_ct == 0.625            # totals (3, 1.25) / 2 ranks on BOTH ranks
         assert none_pos == 1.0 and none_ct == 0.0        # max(0 / 2, 1) = 1
+
+
+# ------------------------------------------------------------------------------------------------ randomised: device functions vs the oracle
+FUZZ = [(False, 40, 1.5), (False, 40, 0.0), (False, 7, 2.5), (False, 1, 1.0), (False, 0, 1.5), (True, 40, 1.5), (True, 7, 0.0), (True, 0, 1.0),
+        (False, 300, 1.5), (True, 300, 0.0)]
+
+
+@pytest.mark.parametrize("seed", range(len(FUZZ)))
+def test_device_functions_fuzz_against_oracle(shim, seed):
+    """Random level layouts, strides, centre-sampling radii, normalisation on / off, integer-aligned boxes (exact ties of volume and of the > 0 tests),
+    boxes outside the grid, G in {0, 1, many}: targets of the host-built device functions == the oracle; AABB losses and gradients == autograd."""
+    rng = np.random.default_rng(100 + seed)
+    n_levels = int(rng.integers(1, 5))
+    strides = [4, 8, 16, 32][:n_levels]
+    mesh = rng.integers(20, 70, 3)
+    grids = [tuple(int(np.ceil(m / s)) for m in mesh) for s in strides]
+    locs = O.compute_locations(grids, strides)
+    n_per = [len(p) for p in locs]
+    rotated, G, radius = FUZZ[seed]
+    norm = bool(rng.integers(0, 2))
+    ext = rng.random((G, 3)) * 50 + 3
+    ctrs = rng.random((G, 3)) * (mesh + 20) - 10
+    if G > 4:                                                  # integer boxes: locations exactly on faces (reg == 0) and equal volumes
+        ext[: G // 2] = rng.integers(2, 12, (G // 2, 3)) * 4.0
+        ctrs[: G // 2] = rng.integers(0, 16, (G // 2, 3)) * 4.0 + 2.0
+        ext[1] = ext[0]
+    gt = (np.concatenate([ctrs, ext, (rng.random((G, 1)) - 0.5) * np.pi], 1) if rotated else np.concatenate([ctrs - ext / 2, ctrs + ext / 2], 1)).astype(np.float32)
+    if rotated and G > 4:
+        gt[: G // 2, 6] = 0.0
+    want_l, want_r = O.targets(locs, strides, gt.reshape(G, 7 if rotated else 6), radius, norm)
+    c = dict(grids=grids, n_per=n_per, radius=radius, rotated=rotated, gt=[gt.reshape(G, 7 if rotated else 6)])
+    loc_all = np.ascontiguousarray(np.concatenate(locs))
+    begin = np.concatenate([[0], np.cumsum(n_per)]).astype(np.int32)
+    rs = np.array([np.float32(s * radius) if radius > 0 else 0.0 for s in strides], np.float32)
+    soi = np.array(O.SIZES_OF_INTEREST, np.float32)
+    lo, hi = np.ascontiguousarray(soi[:, 0]), np.ascontiguousarray(soi[:, 1])
+    nd = np.array(strides, np.float32)
+    D = 8 if rotated else 6
+    labels = np.empty(begin[-1], np.float32); rt = np.empty((begin[-1], D), np.float32)
+    g2 = np.ascontiguousarray(c["gt"][0])
+    shim.shim_fcos_targets(_fp(loc_all), _fp(begin), n_levels, _fp(rs), _fp(lo), _fp(hi), int(norm), _fp(nd), _fp(g2), G, 7 if rotated else 6, _fp(labels), _fp(rt))
+    np.testing.assert_array_equal(labels, want_l)
+    if rotated:
+        np.testing.assert_allclose(rt, want_r, rtol=1e-5, atol=1e-5)
+    else:
+        np.testing.assert_array_equal(rt, want_r)
+    if rotated or G == 0 or want_l.sum() == 0:
+        return
+    # losses of the axis-aligned head on these targets
+    loss_type = ["iou", "linear_iou", "giou", "smooth_l1"][seed % 4]
+    N = 1
+    tg = torch.Generator().manual_seed(seed)
+    cls = [torch.randn(N, 1, *gr, generator=tg) for gr in grids]
+    reg = [torch.rand(N, 6, *gr, generator=tg) * 3 + 0.05 for gr in grids]
+    ctr = [torch.randn(N, 1, *gr, generator=tg) for gr in grids]
+    for lst in (cls, reg, ctr):
+        for t in lst:
+            t.requires_grad_(True)
+    l_cls, l_reg, l_ctr, _ = O.loss(cls, reg, ctr, [want_l], [want_r], None, loss_type, False, False)
+    (l_cls + 2.0 * l_reg + 3.0 * l_ctr).backward()
+    arrs = [[np.ascontiguousarray(t.detach().numpy()) for t in lst] for lst in (cls, reg, ctr)]
+    grads = [[np.full_like(a, np.nan) for a in lst] for lst in arrs]
+    PP = ctypes.c_void_p * n_levels
+    pp = lambda lst: PP(*[a.ctypes.data for a in lst])
+    ct = np.empty((1, begin[-1]), np.float32); sums = np.zeros(6, np.float64)
+    lab2, rt2 = np.ascontiguousarray(want_l[None]), np.ascontiguousarray(want_r[None])
+    shim.shim_fcos_loss(n_levels, _fp(np.array(n_per, np.int32)), 1, 0, LOSS_TYPE[loss_type], 0, pp(arrs[0]), pp(arrs[1]), pp(arrs[2]), pp(grads[0]), pp(grads[1]),
+                        pp(grads[2]), _fp(lab2), _fp(rt2), ctypes.c_void_p(0), _fp(ct), _fp(sums))
+    focal, n_pos, sum_ct, reg_raw, bce, _ = sums
+    np.testing.assert_allclose([focal / max(n_pos, 1), reg_raw / sum_ct, bce / max(n_pos, 1)], [l_cls.item(), l_reg.item(), l_ctr.item()], rtol=2e-5)
+    for l in range(n_levels):
+        np.testing.assert_allclose(grads[0][l] / max(n_pos, 1), cls[l].grad.numpy(), rtol=3e-4, atol=1e-7)
+        np.testing.assert_allclose(2.0 * grads[1][l] / sum_ct, reg[l].grad.numpy(), rtol=3e-4, atol=1e-7)
+        np.testing.assert_allclose(3.0 * grads[2][l] / max(n_pos, 1), ctr[l].grad.numpy(), rtol=3e-4, atol=1e-7)
