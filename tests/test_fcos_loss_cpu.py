@@ -175,12 +175,9 @@ def test_torch_fcos_decode_matches_reference(golden):
 # ------------------------------------------------------------------------------------------------ host logic of nerf_rpn_b200/model/fcos/loss.py
 # The module's kernels cannot run here; its HOST side (target layout, mask concatenation, the autograd node, the gather / scatter of the
 # rotated-IoU term, the normalisers) can: the two ops are replaced by the host build of the same device functions (tests only).
-@pytest.fixture()
-def host_ops(shim, monkeypatch):
-    from nerf_rpn_b200 import ops
-
+def make_host_ops(shim):
+    """(fcos_targets, fcos_loss_sums) with the signatures of nerf_rpn_b200.ops, running the host build of the device functions on CPU tensors."""
     def fcos_targets(locations, n_points, strides, gt, radius, norm=True):
-        c = dict(grids=None, n_per=list(n_points), radius=radius, rotated=gt.shape[1] == 7, gt=[gt.numpy()])
         loc = np.ascontiguousarray(locations.numpy())
         begin = np.concatenate([[0], np.cumsum(n_points)]).astype(np.int32)
         rs = np.array([np.float32(s * radius) if radius > 0 else 0.0 for s in strides], np.float32)
@@ -188,7 +185,7 @@ def host_ops(shim, monkeypatch):
         lo, hi = np.ascontiguousarray(soi[:, 0]), np.ascontiguousarray(soi[:, 1])
         nd = np.array(strides, np.float32)
         g = np.ascontiguousarray(gt.numpy(), np.float32)
-        D = 8 if c["rotated"] else 6
+        D = 8 if gt.shape[1] == 7 else 6
         labels = np.empty(begin[-1], np.float32); rt = np.empty((begin[-1], D), np.float32)
         shim.shim_fcos_targets(_fp(loc), _fp(begin), len(n_points), _fp(rs), _fp(lo), _fp(hi), int(norm), _fp(nd), _fp(g), g.shape[0], gt.shape[1],
                                _fp(labels), _fp(rt))
@@ -209,12 +206,32 @@ def host_ops(shim, monkeypatch):
                             _fp(lab), _fp(rt), null if m is None else _fp(m), _fp(ct), _fp(sums))
         g = tuple([torch.from_numpy(a) for a in lst] for lst in grads) if want_grad else None
         return torch.from_numpy(sums), torch.from_numpy(ct), g
-    monkeypatch.setattr(ops, "fcos_targets", fcos_targets)
-    monkeypatch.setattr(ops, "fcos_loss_sums", fcos_loss_sums)
-    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    return fcos_targets, fcos_loss_sums
+
+
+def patch_host_ops(shim, setattr_):
+    """Route the module's two ops to the host build and let CPU tensors pass its CUDA checks (tests only)."""
+    from nerf_rpn_b200 import ops
+    fcos_targets, fcos_loss_sums = make_host_ops(shim)
+    setattr_(ops, "fcos_targets", fcos_targets)
+    setattr_(ops, "fcos_loss_sums", fcos_loss_sums)
+    setattr_(torch.Tensor, "is_cuda", property(lambda self: True))
     _to = torch.Tensor.to
-    monkeypatch.setattr(torch.Tensor, "to", lambda self, *a, **k: _to(self, *a, **{kk: ("cpu" if kk == "device" else v) for kk, v in k.items()}))
+    setattr_(torch.Tensor, "to", lambda self, *a, **k: _to(self, *a, **{kk: ("cpu" if kk == "device" else v) for kk, v in k.items()}))
     return ops
+
+
+@pytest.fixture(scope="module")
+def shim_path(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("shim_mp") / "libfcos_loss_shim.so")
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-o", out,
+                           os.path.join(ROOT, "tests", "host_shim", "fcos_loss_host.cpp")])
+    return out
+
+
+@pytest.fixture()
+def host_ops(shim, monkeypatch):
+    return patch_host_ops(shim, monkeypatch.setattr)
 
 
 def _module(c, world_size=1):
@@ -393,3 +410,56 @@ def test_device_functions_fuzz_against_oracle(shim, seed):
         np.testing.assert_allclose(grads[0][l] / max(n_pos, 1), cls[l].grad.numpy(), rtol=3e-4, atol=1e-7)
         np.testing.assert_allclose(2.0 * grads[1][l] / sum_ct, reg[l].grad.numpy(), rtol=3e-4, atol=1e-7)
         np.testing.assert_allclose(3.0 * grads[2][l] / max(n_pos, 1), ctr[l].grad.numpy(), rtol=3e-4, atol=1e-7)
+
+
+def _two_rank_loss_worker(rank, world, port, shim_file, golden_file, names, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    patch_host_ops(ctypes.CDLL(shim_file), setattr)
+    g = np.load(golden_file)
+    c = load_case(g, names[rank])
+    mod = _module(c, world_size=world)
+    cls, reg, ctr = ([torch.tensor(a, requires_grad=True) for a in c[k]] for k in ("cls", "reg", "ctr"))
+    locs = mod.compute_locations(cls)
+    masks = mod.compute_padding_masks(locs, [tuple(int(v) for v in s) for s in g[f"{names[rank]}/sizes"]]) if c["batch"] > 1 else None
+    _, _, losses = mod._forward_train(locs, cls, reg, ctr, [torch.tensor(t) for t in c["gt"]], masks)
+    (losses["loss_cls"] + 2.0 * losses["loss_reg"] + 3.0 * losses["loss_centerness"]).backward()
+    q.put((rank, [losses[k].item() for k in ("loss_cls", "loss_reg", "loss_centerness")], [float(t.grad.abs().sum()) for t in (cls[0], reg[0], ctr[0])]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_loss_normalisers_end_to_end_gloo(shim_path, golden, golden_dir):
+    """8(e) C3 end to end at world size 2 (gloo, host build of the kernels): rank 0 = case aabb_iou, rank 1 = case aabb_empty.  Each rank's losses and
+    gradients must equal its single-rank golden values rescaled by (own normaliser) / (average normaliser over the ranks), loss.py:541-576."""
+    import socket
+    import torch.multiprocessing as mp
+    names = ("aabb_iou", "aabb_empty")
+    single = []
+    for nm in names:                                   # the single-rank raw sums behind the goldens
+        c = load_case(golden, nm)
+        N = c["batch"]
+        lab = np.stack(per_scene(c["labels"], c["n_per"], N))
+        m = np.concatenate([mm.reshape(N, -1) for mm in c["mask"]], 1)
+        rt = np.stack(per_scene(c["reg_targets"], c["n_per"], N))
+        pos = (lab > 0) & m
+        ct = O.centerness_targets(torch.tensor(rt[pos])).numpy()
+        single.append((float(pos.sum()), float(ct.sum(dtype=np.float64)), c["losses"], [np.abs(c[k][0]).sum() for k in ("dcls", "dreg", "dctr")]))
+    avg_pos = max((single[0][0] + single[1][0]) / 2, 1.0)
+    avg_ct = (single[0][1] + single[1][1]) / 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    gfile = os.path.join(golden_dir, "fcos_loss.npz")
+    ps = [ctx.Process(target=_two_rank_loss_worker, args=(r, 2, port, shim_path, gfile, names, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = sorted(q.get(timeout=180) for _ in ps)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, losses, gsum in out:
+        n_pos, s_ct, want, gwant = single[rank]
+        f_pos, f_ct = max(n_pos, 1.0) / avg_pos, s_ct / avg_ct
+        np.testing.assert_allclose(losses, [want[0] * f_pos, want[1] * f_ct, want[2] * f_pos], rtol=2e-5)
+        np.testing.assert_allclose(gsum, [gwant[0] * f_pos, gwant[1] * f_ct, gwant[2] * f_pos], rtol=2e-4)
+    assert abs(single[0][0] - single[1][0]) > 10           # the two ranks really have different normalisers
